@@ -1,0 +1,138 @@
+"""ctypes binding of libartic_sm100.so (the C ABI declared in include/artic.h).
+
+The product path has NO fallback: if the library is missing or a kernel reports an
+error, the call raises.  Nothing here imports ``oracle``.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libartic_sm100.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+MAX_TAPS = 48
+TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16}
+DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+class Seq(C.Structure):
+    _fields_ = [("s_outer", C.c_int64), ("s_inner", C.c_int64), ("s_row", C.c_int64),
+                ("n_inner", C.c_int32), ("len", C.c_int32)]
+
+
+class TapConv(C.Structure):
+    _fields_ = [("X", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p),
+                ("res_pre", C.c_void_p), ("mask", C.c_void_p), ("res", C.c_void_p), ("res2", C.c_void_p),
+                ("Y", C.c_void_p), ("Y2", C.c_void_p),
+                ("x", Seq), ("y", Seq),
+                ("N", C.c_int32), ("G", C.c_int32), ("Cig", C.c_int32), ("Cog", C.c_int32),
+                ("q0", C.c_int32), ("nq", C.c_int32), ("si", C.c_int32), ("so", C.c_int32), ("ro", C.c_int32),
+                ("ntaps", C.c_int32),
+                ("off", C.c_int32 * MAX_TAPS), ("widx", C.c_int32 * MAX_TAPS),
+                ("alpha", C.c_float), ("mask_slope", C.c_float), ("act_slope", C.c_float),
+                ("act", C.c_int32), ("dtype", C.c_int32)]
+
+
+class TapWgrad(C.Structure):
+    _fields_ = [("X", C.c_void_p), ("dY", C.c_void_p), ("dW", C.c_void_p),
+                ("x", Seq), ("y", Seq),
+                ("N", C.c_int32), ("G", C.c_int32), ("Cig", C.c_int32), ("Cog", C.c_int32),
+                ("q0", C.c_int32), ("nq", C.c_int32), ("si", C.c_int32), ("so", C.c_int32),
+                ("ntaps", C.c_int32),
+                ("off", C.c_int32 * MAX_TAPS), ("yoff", C.c_int32 * MAX_TAPS), ("widx", C.c_int32 * MAX_TAPS),
+                ("dtype", C.c_int32)]
+
+
+class AdamHyper(C.Structure):
+    _fields_ = [("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("gamma", C.c_float), ("step", C.c_int32), ("n_milestones", C.c_int32),
+                ("milestones", C.c_int32 * 8)]
+
+
+_i32, _i64, _f, _p = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+#: every exported symbol of include/artic.h: name -> (restype, argtypes)
+SIGNATURES = {
+    "artic_version": (C.c_int, []),
+    "artic_arch": (C.c_char_p, []),
+    "artic_last_error": (C.c_char_p, []),
+    "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
+    "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
+    "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),
+    "artic_weight_prep": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _i32, _p]),
+    "artic_weight_unprep": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "artic_gen_input": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "artic_gen_input_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "artic_mean3_act": (C.c_int, [_p, _p, _p, _p, _i64, _f, _i32, _p]),
+    "artic_tanh_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
+    "artic_cast": (C.c_int, [_p, _i32, _p, _i32, _i64, _p]),
+    "artic_concat_time": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i64, _i32, _p]),
+    "artic_avgpool1d": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "artic_avgpool1d_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "artic_reflect_pad_right": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
+    "artic_reflect_pad_right_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "artic_sqerr_sum": (C.c_int, [_p, _i64, _f, _f, _p, _i32, _p]),
+    "artic_sqerr_bwd": (C.c_int, [_p, _i64, _f, _f, _p, _i32, _i32, _p]),
+    "artic_l1_sum": (C.c_int, [_p, _p, _i64, _f, _p, _i32, _p]),
+    "artic_l1_bwd": (C.c_int, [_p, _p, _i64, _f, _p, _i32, _i32, _p]),
+    "artic_stft_loss_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _p]),
+    "artic_stft_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _f, _f, _p, _p]),
+    "artic_mel_loss_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _f, _f, _p, _p]),
+    "artic_mel_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _f, _f, _p, _p]),
+    "artic_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
+    "artic_adam_tick": (C.c_int, [_p, _p]),
+}
+
+_lib = None
+#: number of kernel-launching C-ABI calls issued by this process (bench.py reports it)
+launch_count = 0
+
+
+class ArticError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ArticError(
+            f"{LIB_PATH} not found: build it with `python -m articulatory_b200.build` "
+            "(there is no CPU / PyTorch fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Call a kernel-launching entry point on the current CUDA stream; raise on error."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    launch_count += 1
+    if rc != 0:
+        raise ArticError(f"{name} failed ({rc}): {lib.artic_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t, what="tensor"):
+    if not t.is_cuda:
+        raise ArticError(f"{what} must live on a CUDA device: the articulatory_b200 hot path is "
+                         "sm_100a kernels only (no CPU fallback)")

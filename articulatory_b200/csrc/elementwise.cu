@@ -1,0 +1,324 @@
+// Small fused elementwise / reduction kernels of the path (HBM- or latency-bound).
+#include "common.cuh"
+
+namespace artic {
+
+static inline int grid_for(int64_t n, int per_block = 256) {
+  int64_t b = (n + per_block - 1) / per_block;
+  const int64_t cap = 16LL * num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define GRID_STRIDE(i, n) \
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+template <typename T>
+__global__ void gen_input_kernel(const float* __restrict__ c, const T* __restrict__ ar, T* __restrict__ out, int B,
+                                 int Cc, int Ca, int Tn) {
+  const int C = Cc + Ca;
+  const int64_t n = (int64_t)B * Tn * C;
+  GRID_STRIDE(i, n) {
+    const int ch = (int)(i % C);
+    const int64_t r = i / C;
+    const int t = (int)(r % Tn);
+    const int b = (int)(r / Tn);
+    float v;
+    if (ch < Cc) v = c[((int64_t)b * Cc + ch) * Tn + t];
+    else v = ld_f(ar + (int64_t)b * Ca + (ch - Cc));
+    st_f(out + i, v);
+  }
+}
+
+template <typename T>
+__global__ void gen_input_bwd_kernel(const T* __restrict__ dX, float* __restrict__ d_ar, int B, int Cc, int Ca, int Tn) {
+  // one thread per (b, a); Tn is small (<= a few hundred frames)
+  const int64_t n = (int64_t)B * Ca;
+  GRID_STRIDE(i, n) {
+    const int a = (int)(i % Ca);
+    const int b = (int)(i / Ca);
+    float s = 0.f;
+    for (int t = 0; t < Tn; ++t) s += ld_f(dX + ((int64_t)b * Tn + t) * (Cc + Ca) + Cc + a);
+    d_ar[i] = s;
+  }
+}
+
+template <typename T>
+__global__ void mean3_act_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
+                                 T* __restrict__ out, int64_t n, float slope) {
+  GRID_STRIDE(i, n) {
+    float v = (ld_f(a + i) + ld_f(b + i) + ld_f(c + i)) / 3.0f;
+    st_f(out + i, v > 0.f ? v : slope * v);
+  }
+}
+
+template <typename T>
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, T* __restrict__ dpre, int64_t n) {
+  GRID_STRIDE(i, n) { st_f(dpre + i, dy[i] * (1.f - y[i] * y[i])); }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+  GRID_STRIDE(i, n) { st_f(d + i, ld_f(s + i)); }
+}
+
+template <typename T>
+__global__ void concat_time_kernel(const float* __restrict__ ar, const float* __restrict__ y, T* __restrict__ out, int B,
+                                   int La, int Ly, int64_t pitch) {
+  const int L = La + Ly;
+  const int64_t n = (int64_t)B * L;
+  GRID_STRIDE(i, n) {
+    const int l = (int)(i % L);
+    const int b = (int)(i / L);
+    const float v = l < La ? ar[(int64_t)b * La + l] : y[(int64_t)b * Ly + (l - La)];
+    st_f(out + (int64_t)b * pitch + l, v);
+  }
+}
+
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int L, int Lout, int k, int stride,
+                               int pad) {
+  const int64_t n = (int64_t)B * Lout;
+  GRID_STRIDE(i, n) {
+    const int o = (int)(i % Lout);
+    const int b = (int)(i / Lout);
+    float s = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int l = o * stride - pad + j;
+      if (l >= 0 && l < L) s += ld_f(x + (int64_t)b * L + l);
+    }
+    st_f(y + i, s / (float)k);  // count_include_pad=True: divisor is always k
+  }
+}
+
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int L, int Lout, int k,
+                                   int stride, int pad, int accumulate) {
+  const int64_t n = (int64_t)B * L;
+  GRID_STRIDE(i, n) {
+    const int l = (int)(i % L);
+    const int b = (int)(i / L);
+    // outputs o with o*stride - pad <= l <= o*stride - pad + k - 1
+    float s = 0.f;
+    const int lo_num = l + pad - (k - 1);
+    int o_lo = lo_num <= 0 ? 0 : (lo_num + stride - 1) / stride;
+    int o_hi = (l + pad) / stride;
+    if (o_hi > Lout - 1) o_hi = Lout - 1;
+    for (int o = o_lo; o <= o_hi; ++o) s += ld_f(dy + (int64_t)b * Lout + o);
+    s /= (float)k;
+    if (accumulate) s += ld_f(dx + i);
+    st_f(dx + i, s);
+  }
+}
+
+template <typename T>
+__global__ void reflect_pad_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int L, int Lp) {
+  const int64_t n = (int64_t)B * Lp;
+  GRID_STRIDE(i, n) {
+    const int l = (int)(i % Lp);
+    const int b = (int)(i / Lp);
+    const int src = l < L ? l : 2 * (L - 1) - l;
+    y[i] = x[(int64_t)b * L + src];
+  }
+}
+
+template <typename T>
+__global__ void reflect_pad_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int L, int Lp, int accumulate) {
+  const int64_t n = (int64_t)B * L;
+  GRID_STRIDE(i, n) {
+    const int l = (int)(i % L);
+    const int b = (int)(i / L);
+    float s = ld_f(dy + (int64_t)b * Lp + l);
+    const int m = 2 * (L - 1) - l;  // padded index that mirrors onto l
+    if (m >= L && m < Lp) s += ld_f(dy + (int64_t)b * Lp + m);
+    if (accumulate) s += ld_f(dx + i);
+    st_f(dx + i, s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sqerr_sum_kernel(const T* __restrict__ x, int64_t n, float target, float scale,
+                                                        float* __restrict__ slot) {
+  __shared__ float red[32];
+  float s = 0.f;
+  GRID_STRIDE(i, n) {
+    const float d = ld_f(x + i) - target;
+    s = fmaf(d, d, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(slot, s * scale);
+}
+
+template <typename T>
+__global__ void sqerr_bwd_kernel(const T* __restrict__ x, int64_t n, float target, float scale, T* __restrict__ dx,
+                                 int accumulate) {
+  GRID_STRIDE(i, n) {
+    float g = 2.f * scale * (ld_f(x + i) - target);
+    if (accumulate) g += ld_f(dx + i);
+    st_f(dx + i, g);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) l1_sum_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n,
+                                                     float scale, float* __restrict__ slot) {
+  __shared__ float red[32];
+  float s = 0.f;
+  GRID_STRIDE(i, n) s += fabsf(ld_f(a + i) - ld_f(b + i));
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(slot, s * scale);
+}
+
+template <typename T>
+__global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, float scale, T* __restrict__ da,
+                              int accumulate) {
+  GRID_STRIDE(i, n) {
+    const float d = ld_f(a + i) - ld_f(b + i);
+    float g = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+    if (accumulate) g += ld_f(da + i);
+    st_f(da + i, g);
+  }
+}
+
+}  // namespace artic
+
+using namespace artic;
+typedef __nv_bfloat16 bf16;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define DISPATCH(dtype, CALL_F32, CALL_BF16)                             \
+  do {                                                                   \
+    ARTIC_CHECK_ARG(dtype == ARTIC_F32 || dtype == ARTIC_BF16, "bad dtype"); \
+    if (dtype == ARTIC_BF16) { CALL_BF16; } else { CALL_F32; }           \
+    ARTIC_LAUNCH_CHECK();                                                \
+    return ARTIC_OK;                                                     \
+  } while (0)
+
+extern "C" int artic_gen_input(const float* c, const void* ar_feats, void* out, int32_t B, int32_t Cc, int32_t Ca,
+                               int32_t T, int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(c && out && (ar_feats || Ca == 0), "null pointer");
+  const int64_t n = (int64_t)B * T * (Cc + Ca);
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (gen_input_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(c, (const float*)ar_feats, (float*)out, B, Cc, Ca, T)),
+           (gen_input_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(c, (const bf16*)ar_feats, (bf16*)out, B, Cc, Ca, T)));
+}
+
+extern "C" int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int32_t Ca, int32_t T,
+                                   int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(dX && d_ar, "null pointer");
+  const int64_t n = (int64_t)B * Ca;
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (gen_input_bwd_kernel<float><<<grid_for(n, 64), 64, 0, ST(stream)>>>((const float*)dX, d_ar, B, Cc, Ca, T)),
+           (gen_input_bwd_kernel<bf16><<<grid_for(n, 64), 64, 0, ST(stream)>>>((const bf16*)dX, d_ar, B, Cc, Ca, T)));
+}
+
+extern "C" int artic_mean3_act(const void* a, const void* b, const void* c, void* out_act, int64_t n, float slope,
+                               int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(a && b && c && out_act, "null pointer");
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (mean3_act_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, (const float*)c, (float*)out_act, n, slope)),
+           (mean3_act_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out_act, n, slope)));
+}
+
+extern "C" int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64_t n, int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(dy && y && dpre, "null pointer");
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (tanh_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(dy, y, (float*)dpre, n)),
+           (tanh_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(dy, y, (bf16*)dpre, n)));
+}
+
+extern "C" int artic_cast(const void* src, int32_t sd, void* dst, int32_t dd, int64_t n, void* stream) {
+  ARTIC_CHECK_ARG(src && dst, "null pointer");
+  ARTIC_CHECK_ARG((sd == ARTIC_F32 || sd == ARTIC_BF16) && (dd == ARTIC_F32 || dd == ARTIC_BF16), "bad dtype");
+  if (n == 0) return ARTIC_OK;
+  const int g = grid_for(n);
+  if (sd == ARTIC_F32 && dd == ARTIC_F32) cast_kernel<float, float><<<g, 256, 0, ST(stream)>>>((const float*)src, (float*)dst, n);
+  else if (sd == ARTIC_F32) cast_kernel<float, bf16><<<g, 256, 0, ST(stream)>>>((const float*)src, (bf16*)dst, n);
+  else if (dd == ARTIC_F32) cast_kernel<bf16, float><<<g, 256, 0, ST(stream)>>>((const bf16*)src, (float*)dst, n);
+  else cast_kernel<bf16, bf16><<<g, 256, 0, ST(stream)>>>((const bf16*)src, (bf16*)dst, n);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}
+
+extern "C" int artic_concat_time(const float* ar, const float* y, void* out, int32_t B, int32_t La, int32_t Ly,
+                                 int64_t out_pitch, int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(y && out && (ar || La == 0), "null pointer");
+  ARTIC_CHECK_ARG(out_pitch >= (int64_t)La + Ly, "pitch too small");
+  const int64_t n = (int64_t)B * (La + Ly);
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (concat_time_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(ar, y, (float*)out, B, La, Ly, out_pitch)),
+           (concat_time_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(ar, y, (bf16*)out, B, La, Ly, out_pitch)));
+}
+
+extern "C" int artic_avgpool1d(const void* x, void* y, int32_t B, int32_t L, int32_t Lout, int32_t k, int32_t stride,
+                               int32_t pad, int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(x && y, "null pointer");
+  ARTIC_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && Lout == (L + 2 * pad - k) / stride + 1, "bad pooling geometry");
+  const int64_t n = (int64_t)B * Lout;
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (avgpool_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)x, (float*)y, B, L, Lout, k, stride, pad)),
+           (avgpool_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)y, B, L, Lout, k, stride, pad)));
+}
+
+extern "C" int artic_avgpool1d_bwd(const void* dy, void* dx, int32_t B, int32_t L, int32_t Lout, int32_t k,
+                                   int32_t stride, int32_t pad, int32_t accumulate, int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(dy && dx, "null pointer");
+  ARTIC_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && Lout == (L + 2 * pad - k) / stride + 1, "bad pooling geometry");
+  const int64_t n = (int64_t)B * L;
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (avgpool_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)dy, (float*)dx, B, L, Lout, k, stride, pad, accumulate)),
+           (avgpool_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)dy, (bf16*)dx, B, L, Lout, k, stride, pad, accumulate)));
+}
+
+extern "C" int artic_reflect_pad_right(const void* x, void* y, int32_t B, int32_t L, int32_t Lp, int32_t dtype,
+                                       void* stream) {
+  ARTIC_CHECK_ARG(x && y, "null pointer");
+  ARTIC_CHECK_ARG(Lp >= L && Lp - L < L, "reflect pad must be smaller than the input");
+  const int64_t n = (int64_t)B * Lp;
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (reflect_pad_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)x, (float*)y, B, L, Lp)),
+           (reflect_pad_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)y, B, L, Lp)));
+}
+
+extern "C" int artic_reflect_pad_right_bwd(const void* dy, void* dx, int32_t B, int32_t L, int32_t Lp,
+                                           int32_t accumulate, int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(dy && dx, "null pointer");
+  ARTIC_CHECK_ARG(Lp >= L && Lp - L < L, "reflect pad must be smaller than the input");
+  const int64_t n = (int64_t)B * L;
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (reflect_pad_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)dy, (float*)dx, B, L, Lp, accumulate)),
+           (reflect_pad_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)dy, (bf16*)dx, B, L, Lp, accumulate)));
+}
+
+extern "C" int artic_sqerr_sum(const void* x, int64_t n, float target, float scale, float* slot, int32_t dtype,
+                               void* stream) {
+  ARTIC_CHECK_ARG(x && slot, "null pointer");
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (sqerr_sum_kernel<float><<<grid_for(n, 1024), 256, 0, ST(stream)>>>((const float*)x, n, target, scale, slot)),
+           (sqerr_sum_kernel<bf16><<<grid_for(n, 1024), 256, 0, ST(stream)>>>((const bf16*)x, n, target, scale, slot)));
+}
+
+extern "C" int artic_sqerr_bwd(const void* x, int64_t n, float target, float scale, void* dx, int32_t accumulate,
+                               int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(x && dx, "null pointer");
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (sqerr_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)x, n, target, scale, (float*)dx, accumulate)),
+           (sqerr_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)x, n, target, scale, (bf16*)dx, accumulate)));
+}
+
+extern "C" int artic_l1_sum(const void* a, const void* b, int64_t n, float scale, float* slot, int32_t dtype,
+                            void* stream) {
+  ARTIC_CHECK_ARG(a && b && slot, "null pointer");
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (l1_sum_kernel<float><<<grid_for(n, 1024), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, n, scale, slot)),
+           (l1_sum_kernel<bf16><<<grid_for(n, 1024), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, n, scale, slot)));
+}
+
+extern "C" int artic_l1_bwd(const void* a, const void* b, int64_t n, float scale, void* da, int32_t accumulate,
+                            int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(a && b && da, "null pointer");
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (l1_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, n, scale, (float*)da, accumulate)),
+           (l1_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, n, scale, (bf16*)da, accumulate)));
+}

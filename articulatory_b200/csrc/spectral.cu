@@ -1,0 +1,385 @@
+// Fused spectral losses: framing (reflect pad, centred window) -> shared-memory Stockham
+// FFT of z = w*(x + i*y) (one complex FFT yields both spectra) -> magnitude -> loss partial
+// sums, and the matching backward (spectrogram recomputed, adjoint FFT, overlap-add).
+// No spectrogram ever touches HBM.  Algorithmic HBM bytes: read x, y; write dL/dx.
+#include "common.cuh"
+
+namespace artic {
+
+struct FrameGeom {
+  int T, N, hop, win, lpad;  // lpad = (N - win) / 2 : torch.stft centres the window in n_fft
+};
+
+__device__ __forceinline__ int reflect_index(int t, int T) {
+  if (t < 0) t = -t;
+  if (t >= T) t = 2 * (T - 1) - t;
+  return t;
+}
+
+// Radix-2 Stockham autosort FFT (forward, e^{-i...}), natural-order in and out.
+// Source is (r0,i0); returns 0 if the result ends in (r0,i0), 1 if in (r1,i1).
+__device__ __forceinline__ int fft_stockham(float* r0, float* i0, float* r1, float* i1, const float* twr,
+                                            const float* twi, int N) {
+  int cur = 0;
+  const int half = N >> 1;
+  for (int s = 1; s < N; s <<= 1) {
+    const float* xr = cur ? r1 : r0;
+    const float* xi = cur ? i1 : i0;
+    float* yr = cur ? r0 : r1;
+    float* yi = cur ? i0 : i1;
+    for (int b = threadIdx.x; b < half; b += blockDim.x) {
+      const int q = b & (s - 1);
+      const int ps = b - q;
+      const float ar = xr[b], ai = xi[b];
+      const float br = xr[b + half], bi = xi[b + half];
+      const float wr = twr[ps], wi = twi[ps];
+      const int o = q + 2 * ps;
+      yr[o] = ar + br;
+      yi[o] = ai + bi;
+      const float dr = ar - br, di = ai - bi;
+      yr[o + s] = dr * wr - di * wi;
+      yi[o + s] = dr * wi + di * wr;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  return cur;
+}
+
+__device__ __forceinline__ void make_twiddles(float* twr, float* twi, int N) {
+  for (int k = threadIdx.x; k < (N >> 1); k += blockDim.x) {
+    float s, c;
+    sincospif(2.0f * (float)k / (float)N, &s, &c);
+    twr[k] = c;
+    twi[k] = -s;
+  }
+}
+
+// Load frame f of (x, y) into (re, im) with window and reflect padding.
+__device__ __forceinline__ void load_frame(const float* __restrict__ x, const float* __restrict__ y,
+                                           const float* __restrict__ window, const FrameGeom& g, int f, float* re,
+                                           float* im) {
+  const int start = f * g.hop - (g.N >> 1);
+  for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    const int wn = n - g.lpad;
+    if (wn >= 0 && wn < g.win) {
+      const float w = __ldg(window + wn);
+      const int t = reflect_index(start + n, g.T);
+      a = w * __ldg(x + t);
+      b = w * __ldg(y + t);
+    }
+    re[n] = a;
+    im[n] = b;
+  }
+}
+
+// Split Z = FFT(x + i y) into the two Hermitian spectra at bin k (0 <= k <= N/2).
+__device__ __forceinline__ void split_bin(const float* zr, const float* zi, int k, int N, float& xr, float& xi,
+                                          float& yr, float& yi) {
+  const int k2 = (N - k) & (N - 1);
+  const float ar = zr[k], ai = zi[k], br = zr[k2], bi = zi[k2];
+  xr = 0.5f * (ar + br);
+  xi = 0.5f * (ai - bi);
+  yr = 0.5f * (ai + bi);
+  yi = -0.5f * (ar - br);
+}
+
+// smem layout (floats): r0[N] i0[N] r1[N] i1[N] twr[N/2] twi[N/2] red[32] extra[...]
+struct Smem {
+  float *r0, *i0, *r1, *i1, *twr, *twi, *red, *extra;
+  __device__ Smem(float* base, int N) {
+    r0 = base; i0 = r0 + N; r1 = i0 + N; i1 = r1 + N; twr = i1 + N; twi = twr + (N >> 1);
+    red = twi + (N >> 1); extra = red + 32;
+  }
+};
+
+__global__ void __launch_bounds__(512) stft_loss_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            FrameGeom g, const float* __restrict__ window, float eps,
+                                                            float* __restrict__ sums) {
+  extern __shared__ __align__(16) float smem_f[];
+  Smem sm(smem_f, g.N);
+  const int f = blockIdx.x, b = blockIdx.y;
+  make_twiddles(sm.twr, sm.twi, g.N);
+  load_frame(x + (int64_t)b * g.T, y + (int64_t)b * g.T, window, g, f, sm.r0, sm.i0);
+  __syncthreads();
+  const int cur = fft_stockham(sm.r0, sm.i0, sm.r1, sm.i1, sm.twr, sm.twi, g.N);
+  const float* zr = cur ? sm.r1 : sm.r0;
+  const float* zi = cur ? sm.i1 : sm.i0;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int k = threadIdx.x; k <= (g.N >> 1); k += blockDim.x) {
+    float xr, xi, yr, yi;
+    split_bin(zr, zi, k, g.N, xr, xi, yr, yi);
+    const float xm = sqrtf(fmaxf(xr * xr + xi * xi, eps));
+    const float ym = sqrtf(fmaxf(yr * yr + yi * yi, eps));
+    const float d = ym - xm;
+    s0 = fmaf(d, d, s0);
+    s1 = fmaf(ym, ym, s1);
+    s2 += fabsf(logf(ym) - logf(xm));
+  }
+  s0 = block_sum(s0, sm.red);
+  s1 = block_sum(s1, sm.red);
+  s2 = block_sum(s2, sm.red);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 0, s0);
+    atomicAdd(sums + 1, s1);
+    atomicAdd(sums + 2, s2);
+  }
+}
+
+// Adjoint of the framing + rFFT: the caller has written conj(G[k]) for k <= N/2 (zeros above)
+// into (gr, gi); result dx_frame[n] = w[n] * Re(FFT(conj G))[n] is overlap-added into dx.
+__device__ __forceinline__ void adjoint_to_dx(float* gr, float* gi, float* orr, float* oi, const Smem& sm,
+                                              const FrameGeom& g, const float* __restrict__ window, int f,
+                                              float* __restrict__ dx) {
+  const int cur = fft_stockham(gr, gi, orr, oi, sm.twr, sm.twi, g.N);
+  const float* rr = cur ? orr : gr;
+  const int start = f * g.hop - (g.N >> 1);
+  for (int wn = threadIdx.x; wn < g.win; wn += blockDim.x) {
+    const int n = wn + g.lpad;
+    const int t = reflect_index(start + n, g.T);
+    atomicAdd(dx + t, __ldg(window + wn) * rr[n]);
+  }
+}
+
+__global__ void __launch_bounds__(512) stft_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            FrameGeom g, const float* __restrict__ window, float eps,
+                                                            const float* __restrict__ sums, float w_sc, float w_mag,
+                                                            float inv_numel, float* __restrict__ dx) {
+  extern __shared__ __align__(16) float smem_f[];
+  Smem sm(smem_f, g.N);
+  const int f = blockIdx.x, b = blockIdx.y;
+  make_twiddles(sm.twr, sm.twi, g.N);
+  load_frame(x + (int64_t)b * g.T, y + (int64_t)b * g.T, window, g, f, sm.r0, sm.i0);
+  __syncthreads();
+  const int cur = fft_stockham(sm.r0, sm.i0, sm.r1, sm.i1, sm.twr, sm.twi, g.N);
+  const float* zr = cur ? sm.r1 : sm.r0;
+  const float* zi = cur ? sm.i1 : sm.i0;
+  float* gr = cur ? sm.r0 : sm.r1;  // the other buffer
+  float* gi = cur ? sm.i0 : sm.i1;
+  const float S0 = sums[0], S1 = sums[1];
+  const float c_sc = (S0 > 0.f && S1 > 0.f) ? w_sc * rsqrtf(S0) * rsqrtf(S1) : 0.f;
+  const float c_mag = w_mag * inv_numel;
+  const int half = g.N >> 1;
+  for (int k = threadIdx.x; k <= half; k += blockDim.x) {
+    float xr, xi, yr, yi;
+    split_bin(zr, zi, k, g.N, xr, xi, yr, yi);
+    const float px = xr * xr + xi * xi;
+    const float xm = sqrtf(fmaxf(px, eps));
+    const float ym = sqrtf(fmaxf(yr * yr + yi * yi, eps));
+    // d/dxm [ w_sc * sqrt(S0)/sqrt(S1) + w_mag/numel * |ln ym - ln xm| ]
+    const float dl = logf(ym) - logf(xm);
+    float gk = c_sc * (xm - ym) - c_mag * (dl > 0.f ? 1.f : (dl < 0.f ? -1.f : 0.f)) / xm;
+    if (!(px >= eps)) gk = 0.f;  // clamp(min=eps) passes gradient only where px >= eps
+    const float sc = gk / xm;
+    gr[k] = sc * xr;
+    gi[k] = -sc * xi;  // conj
+    if (k > 0 && k < half) {
+      gr[g.N - k] = 0.f;
+      gi[g.N - k] = 0.f;
+    }
+  }
+  __syncthreads();
+  adjoint_to_dx(gr, gi, const_cast<float*>(zr), const_cast<float*>(zi), sm, g, window, f, dx + (int64_t)b * g.T);
+}
+
+// ---- mel ---------------------------------------------------------------------------
+// Mel projection of the two amplitude spectra held in (ax, ay)[0..N/2] -> extra[0..2*n_mels):
+// mel_x at extra[m], mel_y at extra[n_mels + m].  Uses extra[2*n_mels ...] as scratch.
+__device__ __forceinline__ void mel_project(const float* ax, const float* ay, const float* __restrict__ melmat,
+                                            int n_bins, int n_mels, float* extra) {
+  const int ngroups = max(1, (int)blockDim.x / n_mels);
+  float* part = extra + 2 * n_mels;  // [ngroups][2][n_mels]
+  const int gi = threadIdx.x / n_mels, m = threadIdx.x % n_mels;
+  if (gi < ngroups) {
+    float sx = 0.f, sy = 0.f;
+    for (int k = gi; k < n_bins; k += ngroups) {
+      const float w = __ldg(melmat + (int64_t)k * n_mels + m);
+      sx = fmaf(ax[k], w, sx);
+      sy = fmaf(ay[k], w, sy);
+    }
+    part[(gi * 2 + 0) * n_mels + m] = sx;
+    part[(gi * 2 + 1) * n_mels + m] = sy;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_mels) {
+    float sx = 0.f, sy = 0.f;
+    for (int i = 0; i < ngroups; ++i) {
+      sx += part[(i * 2 + 0) * n_mels + threadIdx.x];
+      sy += part[(i * 2 + 1) * n_mels + threadIdx.x];
+    }
+    extra[threadIdx.x] = sx;
+    extra[n_mels + threadIdx.x] = sy;
+  }
+  __syncthreads();
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(512) mel_loss_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                       FrameGeom g, const float* __restrict__ window,
+                                                       const float* __restrict__ melmat, int n_mels, float eps,
+                                                       float log_scale, float scale, float* __restrict__ slot,
+                                                       float* __restrict__ dx) {
+  extern __shared__ __align__(16) float smem_f[];
+  Smem sm(smem_f, g.N);
+  const int f = blockIdx.x, b = blockIdx.y;
+  const int half = g.N >> 1, n_bins = half + 1;
+  make_twiddles(sm.twr, sm.twi, g.N);
+  load_frame(x + (int64_t)b * g.T, y + (int64_t)b * g.T, window, g, f, sm.r0, sm.i0);
+  __syncthreads();
+  const int cur = fft_stockham(sm.r0, sm.i0, sm.r1, sm.i1, sm.twr, sm.twi, g.N);
+  const float* zr = cur ? sm.r1 : sm.r0;
+  const float* zi = cur ? sm.i1 : sm.i0;
+  float* ax = cur ? sm.r0 : sm.r1;  // other buffer: amplitudes
+  float* ay = cur ? sm.i0 : sm.i1;
+  for (int k = threadIdx.x; k <= half; k += blockDim.x) {
+    float xr, xi, yr, yi;
+    split_bin(zr, zi, k, g.N, xr, xi, yr, yi);
+    ax[k] = sqrtf(fmaxf(xr * xr + xi * xi, eps));
+    ay[k] = sqrtf(fmaxf(yr * yr + yi * yi, eps));
+  }
+  __syncthreads();
+  mel_project(ax, ay, melmat, n_bins, n_mels, sm.extra);
+  if (!BWD) {
+    float s = 0.f;
+    if (threadIdx.x < n_mels) {
+      const float lx = logf(fmaxf(sm.extra[threadIdx.x], eps)) * log_scale;
+      const float ly = logf(fmaxf(sm.extra[n_mels + threadIdx.x], eps)) * log_scale;
+      s = fabsf(lx - ly);
+    }
+    s = block_sum(s, sm.red);
+    if (threadIdx.x == 0) atomicAdd(slot, s * scale);
+    return;
+  } else {
+    // d/dmel_x of scale * |log(clamp(mel_x)) - log(clamp(mel_y))| * log_scale
+    float* dm = sm.extra + 2 * n_mels;  // overwrite the (now dead) partial-sum scratch
+    if (threadIdx.x < n_mels) {
+      const float mx = sm.extra[threadIdx.x], my = sm.extra[n_mels + threadIdx.x];
+      const float lx = logf(fmaxf(mx, eps)) * log_scale;
+      const float ly = logf(fmaxf(my, eps)) * log_scale;
+      const float d = lx - ly;
+      float gm = (d > 0.f ? scale : (d < 0.f ? -scale : 0.f)) * log_scale / fmaxf(mx, eps);
+      if (!(mx >= eps)) gm = 0.f;
+      dm[threadIdx.x] = gm;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k <= half; k += blockDim.x) {
+      float xr, xi, yr, yi;
+      split_bin(zr, zi, k, g.N, xr, xi, yr, yi);
+      const float px = xr * xr + xi * xi;
+      float da = 0.f;
+      const float* mrow = melmat + (int64_t)k * n_mels;
+      for (int m = 0; m < n_mels; ++m) da = fmaf(dm[m], __ldg(mrow + m), da);
+      if (!(px >= eps)) da = 0.f;
+      const float sc = da / ax[k];
+      ax[k] = sc * xr;
+      ay[k] = -sc * xi;
+      if (k > 0 && k < half) {
+        ax[g.N - k] = 0.f;
+        ay[g.N - k] = 0.f;
+      }
+    }
+    __syncthreads();
+    adjoint_to_dx(ax, ay, const_cast<float*>(zr), const_cast<float*>(zi), sm, g, window, f, dx + (int64_t)b * g.T);
+  }
+}
+
+static int check_geom(int B, int T, int n_fft, int hop, int win) {
+  if (B < 0 || T < 1 || hop < 1 || win < 1 || win > n_fft) return 0;
+  if (n_fft < 64 || n_fft > 4096 || (n_fft & (n_fft - 1))) return 0;
+  if (T <= n_fft / 2) return 0;  // reflect padding needs pad < T (same rule as torch.stft)
+  return 1;
+}
+
+static size_t smem_bytes(int N, int n_mels) {
+  const int ngroups = n_mels > 0 ? (512 / n_mels > 0 ? 512 / n_mels : 1) : 0;
+  return sizeof(float) * ((size_t)5 * N + 32 + 2 * n_mels + (size_t)2 * ngroups * n_mels + 16);
+}
+
+template <typename K>
+static int ensure_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(%zu B smem): %s", bytes, cudaGetErrorString(e));
+      return ARTIC_ECUDA;
+    }
+  }
+  return ARTIC_OK;
+}
+
+static int fft_threads(int N) { return (N / 2) < 512 ? (N / 2) : 512; }
+
+}  // namespace artic
+
+using namespace artic;
+
+extern "C" int artic_stft_loss_fwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft, int32_t hop,
+                                   int32_t win_length, const float* window, float eps, float* sums, void* stream) {
+  ARTIC_CHECK_ARG(x && y && window && sums, "null pointer");
+  ARTIC_CHECK_ARG(check_geom(B, T, n_fft, hop, win_length), "unsupported STFT geometry");
+  if (B == 0) return ARTIC_OK;
+  FrameGeom g{T, n_fft, hop, win_length, (n_fft - win_length) / 2};
+  const size_t sb = smem_bytes(n_fft, 0);
+  int rc = ensure_smem(stft_loss_fwd_kernel, sb);
+  if (rc) return rc;
+  dim3 grid(1 + T / hop, B);
+  stft_loss_fwd_kernel<<<grid, fft_threads(n_fft), sb, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, g, window, eps, sums);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}
+
+extern "C" int artic_stft_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft, int32_t hop,
+                                   int32_t win_length, const float* window, float eps, const float* sums, float w_sc,
+                                   float w_mag, float* dx, void* stream) {
+  ARTIC_CHECK_ARG(x && y && window && sums && dx, "null pointer");
+  ARTIC_CHECK_ARG(check_geom(B, T, n_fft, hop, win_length), "unsupported STFT geometry");
+  if (B == 0) return ARTIC_OK;
+  FrameGeom g{T, n_fft, hop, win_length, (n_fft - win_length) / 2};
+  const size_t sb = smem_bytes(n_fft, 0);
+  int rc = ensure_smem(stft_loss_bwd_kernel, sb);
+  if (rc) return rc;
+  const int frames = 1 + T / hop;
+  const float inv_numel = 1.0f / ((float)B * (float)frames * (float)(n_fft / 2 + 1));
+  dim3 grid(frames, B);
+  stft_loss_bwd_kernel<<<grid, fft_threads(n_fft), sb, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, y, g, window, eps, sums, w_sc, w_mag, inv_numel, dx);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}
+
+extern "C" int artic_mel_loss_fwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft, int32_t hop,
+                                  int32_t win_length, const float* window, const float* melmat, int32_t n_mels,
+                                  float eps, float log_scale, float scale, float* slot, void* stream) {
+  ARTIC_CHECK_ARG(x && y && window && melmat && slot, "null pointer");
+  ARTIC_CHECK_ARG(check_geom(B, T, n_fft, hop, win_length), "unsupported STFT geometry");
+  ARTIC_CHECK_ARG(n_mels >= 1 && n_mels <= fft_threads(n_fft), "n_mels out of range");
+  if (B == 0) return ARTIC_OK;
+  FrameGeom g{T, n_fft, hop, win_length, (n_fft - win_length) / 2};
+  const size_t sb = smem_bytes(n_fft, n_mels);
+  int rc = ensure_smem(mel_loss_kernel<false>, sb);
+  if (rc) return rc;
+  dim3 grid(1 + T / hop, B);
+  mel_loss_kernel<false><<<grid, fft_threads(n_fft), sb, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, y, g, window, melmat, n_mels, eps, log_scale, scale, slot, nullptr);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}
+
+extern "C" int artic_mel_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft, int32_t hop,
+                                  int32_t win_length, const float* window, const float* melmat, int32_t n_mels,
+                                  float eps, float log_scale, float scale, float* dx, void* stream) {
+  ARTIC_CHECK_ARG(x && y && window && melmat && dx, "null pointer");
+  ARTIC_CHECK_ARG(check_geom(B, T, n_fft, hop, win_length), "unsupported STFT geometry");
+  ARTIC_CHECK_ARG(n_mels >= 1 && n_mels <= fft_threads(n_fft), "n_mels out of range");
+  if (B == 0) return ARTIC_OK;
+  FrameGeom g{T, n_fft, hop, win_length, (n_fft - win_length) / 2};
+  const size_t sb = smem_bytes(n_fft, n_mels);
+  int rc = ensure_smem(mel_loss_kernel<true>, sb);
+  if (rc) return rc;
+  dim3 grid(1 + T / hop, B);
+  mel_loss_kernel<true><<<grid, fft_threads(n_fft), sb, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, y, g, window, melmat, n_mels, eps, log_scale, scale, nullptr, dx);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}

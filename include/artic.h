@@ -1,0 +1,248 @@
+/*
+ * artic.h — C ABI of libartic_sm100.so, the B200 (sm_100a) kernels behind the
+ * HiFi-GAN / HiFi-CAR hot path of articulatory/articulatory.
+ *
+ * The reference is 100 % Python: every entry point below replaces a PyTorch library
+ * call site (cuDNN / cuBLAS / cuFFT / ATen) on the hot path; the call site is cited on
+ * each declaration (paths relative to /root/reference/articulatory).  The reference-side
+ * binding (a ctypes stub) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named h_*;
+ *   - `stream` is a cudaStream_t passed as void*; nothing here allocates, synchronises
+ *     or touches the host: every call is CUDA-graph capturable and re-entrant per stream;
+ *   - return value: 0 = ok, otherwise a negative ARTIC_E* code; artic_last_error() returns
+ *     a thread-local message;
+ *   - activations are CHANNELS-LAST: element (n, l, c) of a sequence batch lives at
+ *     base + (n / n_inner) * s_outer + (n % n_inner) * s_inner + l * s_row + c
+ *     (plain batch: n_inner = 1).  dtype codes: ARTIC_F32 / ARTIC_BF16 (storage type of
+ *     activations and prepared weights; accumulation is always fp32).
+ */
+#ifndef ARTIC_H_
+#define ARTIC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARTIC_F32 0
+#define ARTIC_BF16 1
+
+#define ARTIC_OK 0
+#define ARTIC_EINVAL (-1)  /* bad argument */
+#define ARTIC_ECUDA (-2)   /* CUDA runtime / launch error */
+#define ARTIC_ENOSUP (-3)  /* shape not supported by this kernel */
+
+#define ARTIC_ACT_NONE 0
+#define ARTIC_ACT_LRELU 1
+#define ARTIC_ACT_TANH 2
+
+#define ARTIC_MAX_TAPS 48
+
+int artic_version(void);          /* 100 * major + minor */
+const char* artic_arch(void);     /* "sm_100a" */
+const char* artic_last_error(void);
+
+/* Addressing of one channels-last sequence batch (see header comment). */
+typedef struct {
+  int64_t s_outer, s_inner, s_row; /* element strides */
+  int32_t n_inner;                 /* >= 1 */
+  int32_t len;                     /* rows per sequence */
+} artic_seq_t;
+
+/*
+ * Tap-gather GEMM: the one contraction behind Conv1d / ConvTranspose1d / Conv2d(k,1) /
+ * Linear, forward and data-gradient (torch.nn.Conv1d, ConvTranspose1d, Conv2d, Linear
+ * at models/hifigan.py:108-172,365-388,549-615; layers/residual_block.py:172-205;
+ * layers/pytorch_layers.py:437-449; and their cuDNN dgrad).
+ *
+ *   for n < N, q in [q0, q0+nq), g < G, co < Cog, row = q*so + ro (skipped unless 0 <= row < y.len):
+ *     acc = sum_{t < ntaps} sum_{ci < Cig} X[n, q*si + off[t], g*Cig+ci] * W[widx[t]][g][ci][co]
+ *           (X rows outside [0, x.len) read as zero)
+ *     v = alpha * acc + bias[g*Cog+co]
+ *     v += res_pre[n,row,c];  v *= (mask[n,row,c] > 0 ? 1 : mask_slope);  v += res[..] + res2[..]
+ *     Y[n,row,c] = v;   Y2[n,row,c] = act(v)        (any of bias/res_pre/mask/res/res2/Y/Y2 may be NULL)
+ *
+ * W is a PREPARED weight [K][G][Cig][Cog] (artic_weight_prep).  res_pre/mask/res/res2/Y2
+ * use Y's addressing.  Conv forward: si=stride, so=1, off[t]=t*dil-pad.  Conv dgrad /
+ * ConvTranspose forward: one call per output phase r with so=stride, si=1.
+ */
+typedef struct {
+  const void* X; const void* W; const float* bias;
+  const void* res_pre; const void* mask; const void* res; const void* res2;
+  void* Y; void* Y2;
+  artic_seq_t x, y;
+  int32_t N, G, Cig, Cog;
+  int32_t q0, nq, si, so, ro;
+  int32_t ntaps;
+  int32_t off[ARTIC_MAX_TAPS];
+  int32_t widx[ARTIC_MAX_TAPS];
+  float alpha, mask_slope, act_slope;
+  int32_t act;   /* ARTIC_ACT_* applied to Y2 */
+  int32_t dtype; /* ARTIC_F32 / ARTIC_BF16 */
+} artic_tapconv_t;
+
+int artic_tapconv(const artic_tapconv_t* p, void* stream);
+
+/*
+ * Weight gradient of the same contraction (cuDNN wgrad):
+ *   dW[widx[t]][g][ci][co] += sum_n sum_q X[n, q*si+off[t], g*Cig+ci] * dY[n, q*so+yoff[t], g*Cog+co]
+ * dW is fp32 [K][G][Cig][Cog] and is ACCUMULATED into (zero it first).  `ws` is an
+ * optional fp32 workspace (unused by the generic kernel; reserved).
+ */
+typedef struct {
+  const void* X; const void* dY; float* dW;
+  artic_seq_t x, y;
+  int32_t N, G, Cig, Cog;
+  int32_t q0, nq, si, so;
+  int32_t ntaps;
+  int32_t off[ARTIC_MAX_TAPS];
+  int32_t yoff[ARTIC_MAX_TAPS];
+  int32_t widx[ARTIC_MAX_TAPS];
+  int32_t dtype;
+} artic_tapwgrad_t;
+
+int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream);
+
+/* Bias gradient: out[c] += sum over all (n, row) of a channels-last batch (C channels). */
+int artic_colsum(const void* dY, const artic_seq_t* y, int32_t N, int32_t C, int32_t dtype,
+                 float* out, void* stream);
+
+/*
+ * Weight preparation (replaces the per-forward torch._weight_norm hook,
+ * models/hifigan.py:268-278,430-438 — w = g * v / ||v||, norm over all dims but 0 —
+ * plus the relayout the kernels want).  Source: a torch weight viewed as
+ * [rows][row_len] fp32 with logical dims (K taps, G groups, A in-channels, B out-channels)
+ * at element strides (sk, sg, sa, sb).  Output: [K][G][A][B] in `dtype`.
+ * g == NULL means a plain (un-normalised) weight.  `scale` (rows floats, may be NULL
+ * iff g == NULL) receives g/||v|| for the backward.
+ */
+int artic_weight_prep(const float* v, const float* g, float* scale, int32_t rows, int64_t row_len,
+                      int32_t K, int32_t G, int32_t A, int32_t B,
+                      int64_t sk, int64_t sg, int64_t sa, int64_t sb,
+                      void* out, int32_t dtype, void* stream);
+
+/*
+ * Backward of artic_weight_prep: dWp is fp32 [K][G][A][B].  Writes dv (torch layout,
+ * fp32) and dg (rows floats; NULL for a plain weight, in which case dv = permuted dWp).
+ * Results are ADDED to dv / dg (autograd accumulation semantics); zero them first.
+ */
+int artic_weight_unprep(const float* dWp, const float* v, const float* g, const float* scale,
+                        int32_t rows, int64_t row_len, int32_t K, int32_t G, int32_t A, int32_t B,
+                        int64_t sk, int64_t sg, int64_t sa, int64_t sb,
+                        float* dv, float* dg, void* stream);
+
+/* ---- small fused elementwise ops on the path ---------------------------------------- */
+
+/* Generator input assembly (models/hifigan.py:209-211): out[b,t,:] = cat(c[b,:,t], ar_feats[b,:])
+ * c is (B, Cc, T) channel-FIRST fp32 (the plugin boundary), ar_feats (B, Ca) in `dtype`
+ * (may be NULL with Ca = 0); out is channels-last (B, T, Cc+Ca) in `dtype`. */
+int artic_gen_input(const float* c, const void* ar_feats, void* out, int32_t B, int32_t Cc,
+                    int32_t Ca, int32_t T, int32_t dtype, void* stream);
+/* its backward wrt ar_feats: d_ar[b,a] = sum_t dX[b,t,Cc+a]  (fp32 out, overwritten) */
+int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int32_t Ca,
+                        int32_t T, int32_t dtype, void* stream);
+
+/* MRF average + activation (models/hifigan.py:226-230 and the LeakyReLU of the next
+ * layer): out_act = lrelu((a+b+c)/3, slope); n elements. */
+int artic_mean3_act(const void* a, const void* b, const void* c, void* out_act, int64_t n,
+                    float slope, int32_t dtype, void* stream);
+
+/* dpre = dy * (1 - y*y)  (torch.nn.Tanh backward, models/hifigan.py:158); fp32 dy/y in, `dtype` out. */
+int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64_t n, int32_t dtype, void* stream);
+
+/* dtype conversion helpers (n elements). */
+int artic_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+
+/* D input assembly (bin/train.py:345-346): out[b] = cat(ar[b] (La), y[b] (Ly)) rows, fp32 in,
+ * `dtype` out with row pitch `out_pitch` elements (>= La+Ly, rest untouched). */
+int artic_concat_time(const float* ar, const float* y, void* out, int32_t B, int32_t La, int32_t Ly,
+                      int64_t out_pitch, int32_t dtype, void* stream);
+
+/* AvgPool1d(kernel, stride, padding, count_include_pad=True) on (B, L) signals
+ * (models/hifigan.py:719-721,733-736). Lout = (L + 2*pad - k)/stride + 1. */
+int artic_avgpool1d(const void* x, void* y, int32_t B, int32_t L, int32_t Lout, int32_t k,
+                    int32_t stride, int32_t pad, int32_t dtype, void* stream);
+/* backward: dx[b,l] (+)= ... ; dx is overwritten unless accumulate != 0 */
+int artic_avgpool1d_bwd(const void* dy, void* dx, int32_t B, int32_t L, int32_t Lout, int32_t k,
+                        int32_t stride, int32_t pad, int32_t accumulate, int32_t dtype, void* stream);
+
+/* Right reflect pad of (B, L) -> (B, Lp) (F.pad(x,(0,n_pad),"reflect"), models/hifigan.py:413-416);
+ * bit-exact index map: out[l] = x[l] for l < L else x[2*(L-1) - l]. */
+int artic_reflect_pad_right(const void* x, void* y, int32_t B, int32_t L, int32_t Lp, int32_t dtype,
+                            void* stream);
+/* backward: dx[b,l] (+)= dy[b,l] + dy[b, 2(L-1)-l] (when that index is in [L, Lp)) */
+int artic_reflect_pad_right_bwd(const void* dy, void* dx, int32_t B, int32_t L, int32_t Lp,
+                                int32_t accumulate, int32_t dtype, void* stream);
+
+/* ---- loss reductions (losses/adversarial_loss.py:54-55,113-117; feat_match_loss.py:41-53) ---- */
+
+/* slot[0] += scale * sum_i (x_i - target)^2   (F.mse_loss against a constant; scale = w/numel) */
+int artic_sqerr_sum(const void* x, int64_t n, float target, float scale, float* slot, int32_t dtype,
+                    void* stream);
+/* dx_i (=|+=) 2 * scale * (x_i - target) */
+int artic_sqerr_bwd(const void* x, int64_t n, float target, float scale, void* dx, int32_t accumulate,
+                    int32_t dtype, void* stream);
+/* slot[0] += scale * sum_i |a_i - b_i|        (F.l1_loss; scale = w/numel) */
+int artic_l1_sum(const void* a, const void* b, int64_t n, float scale, float* slot, int32_t dtype,
+                 void* stream);
+/* da_i (=|+=) scale * sign(a_i - b_i) */
+int artic_l1_bwd(const void* a, const void* b, int64_t n, float scale, void* da, int32_t accumulate,
+                 int32_t dtype, void* stream);
+
+/* ---- spectral losses ------------------------------------------------------------------ */
+
+/*
+ * One resolution of MultiResolutionSTFTLoss (losses/stft_loss.py:16-40,50-61,71-82,101-118:
+ * torch.stft(center, reflect, hann(win) zero-padded to n_fft) -> sqrt(clamp(re^2+im^2,1e-7))
+ * -> Frobenius / log-L1 sums).  x = predicted, y = target, both (B, T) fp32.
+ * Forward accumulates into sums[0] += sum (Y-X)^2, sums[1] += sum Y^2, sums[2] += sum |ln Y - ln X|.
+ * window: win_length fp32 taps.  n_fft must be a power of two in [64, 4096].
+ */
+int artic_stft_loss_fwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft,
+                        int32_t hop, int32_t win_length, const float* window, float eps,
+                        float* sums, void* stream);
+/*
+ * Backward wrt x of  w_sc * sqrt(S0)/sqrt(S1) + w_mag * S2 / numel  with S* read from
+ * `sums` ON THE DEVICE (no host sync).  dx (B, T) fp32 is ACCUMULATED into.
+ * The spectrogram is recomputed (never stored in HBM).
+ */
+int artic_stft_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft,
+                        int32_t hop, int32_t win_length, const float* window, float eps,
+                        const float* sums, float w_sc, float w_mag, float* dx, void* stream);
+
+/*
+ * MelSpectrogramLoss (losses/mel_loss.py:82-111,151-166): STFT -> sqrt(clamp(power, eps))
+ * -> melmat (n_bins x n_mels, row-major fp32) -> clamp(eps) -> log (log_scale = 1 for ln,
+ * 1/ln2, 1/ln10) -> L1.  Forward: slot[0] += scale * sum |mel(x) - mel(y)|  (scale = w/numel).
+ */
+int artic_mel_loss_fwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft, int32_t hop,
+                       int32_t win_length, const float* window, const float* melmat, int32_t n_mels,
+                       float eps, float log_scale, float scale, float* slot, void* stream);
+/* dx (B,T) fp32 += d(scale * sum |mel(x) - mel(y)|)/dx */
+int artic_mel_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft, int32_t hop,
+                       int32_t win_length, const float* window, const float* melmat, int32_t n_mels,
+                       float eps, float log_scale, float scale, float* dx, void* stream);
+
+/* ---- optimiser (torch.optim.Adam + MultiStepLR, bin/train.py:372-383,424-435,1750-1789) ---- */
+
+/* Device-resident hyper-parameters so a captured graph can be replayed across steps. */
+typedef struct {
+  float lr0, beta1, beta2, eps, gamma;
+  int32_t step;           /* number of optimiser steps taken so far */
+  int32_t n_milestones;
+  int32_t milestones[8];
+} artic_adam_hyper_t;
+
+/* p, m, v updated in place from g over n fp32 elements; reads *hyper (device) for lr/step. */
+int artic_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
+                    const artic_adam_hyper_t* hyper, void* stream);
+/* hyper->step += 1 (device side; call once after all artic_adam_step of one optimiser step) */
+int artic_adam_tick(artic_adam_hyper_t* hyper, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARTIC_H_ */
