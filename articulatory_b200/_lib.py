@@ -33,7 +33,7 @@ class TapConv(C.Structure):
                 ("ntaps", C.c_int32),
                 ("off", C.c_int32 * MAX_TAPS), ("widx", C.c_int32 * MAX_TAPS),
                 ("alpha", C.c_float), ("mask_slope", C.c_float), ("act_slope", C.c_float),
-                ("act", C.c_int32), ("dtype", C.c_int32)]
+                ("act", C.c_int32), ("dtype", C.c_int32), ("out_dtype", C.c_int32)]
 
 
 class TapWgrad(C.Structure):
@@ -43,7 +43,7 @@ class TapWgrad(C.Structure):
                 ("q0", C.c_int32), ("nq", C.c_int32), ("si", C.c_int32), ("so", C.c_int32),
                 ("ntaps", C.c_int32),
                 ("off", C.c_int32 * MAX_TAPS), ("yoff", C.c_int32 * MAX_TAPS), ("widx", C.c_int32 * MAX_TAPS),
-                ("dtype", C.c_int32)]
+                ("dtype", C.c_int32), ("y_dtype", C.c_int32)]
 
 
 class AdamHyper(C.Structure):
@@ -66,7 +66,7 @@ SIGNATURES = {
     "artic_weight_unprep": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "artic_gen_input": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "artic_gen_input_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
-    "artic_mean3_act": (C.c_int, [_p, _p, _p, _p, _i64, _f, _i32, _p]),
+    "artic_mean3_act": (C.c_int, [_p, _p, _p, _p, _i64, _f, _i32, _i32, _p]),
     "artic_tanh_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "artic_cast": (C.c_int, [_p, _i32, _p, _i32, _i64, _p]),
     "artic_concat_time": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i64, _i32, _p]),
@@ -82,6 +82,8 @@ SIGNATURES = {
     "artic_stft_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _f, _f, _p, _p]),
     "artic_mel_loss_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _f, _f, _p, _p]),
     "artic_mel_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _f, _f, _p, _p]),
+    "artic_add_rows": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p]),
+    "artic_train_log": (C.c_int, [_p, _p, _p, _i32, _f, _f, _f, _p, _p, _p]),
     "artic_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
     "artic_adam_tick": (C.c_int, [_p, _p]),
 }

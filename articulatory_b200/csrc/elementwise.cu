@@ -44,9 +44,9 @@ __global__ void gen_input_bwd_kernel(const T* __restrict__ dX, float* __restrict
   }
 }
 
-template <typename T>
+template <typename T, typename TO>
 __global__ void mean3_act_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
-                                 T* __restrict__ out, int64_t n, float slope) {
+                                 TO* __restrict__ out, int64_t n, float slope) {
   GRID_STRIDE(i, n) {
     float v = (ld_f(a + i) + ld_f(b + i) + ld_f(c + i)) / 3.0f;
     st_f(out + i, v > 0.f ? v : slope * v);
@@ -181,6 +181,35 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
   }
 }
 
+__global__ void add_rows_kernel(const float* __restrict__ src, int64_t sp, float* __restrict__ dst, int64_t dp, int rows,
+                                int cols) {
+  const int64_t n = (int64_t)rows * cols;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % cols);
+    const int r = (int)(i / cols);
+    dst[(int64_t)r * dp + c] += src[(int64_t)r * sp + c];
+  }
+}
+
+__global__ void train_log_kernel(const float* __restrict__ slots, const float* __restrict__ sums,
+                                 const float* __restrict__ numel, int R, float la, float ladv, float lfm,
+                                 float* __restrict__ vals, float* __restrict__ running) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float sc = 0.f, mag = 0.f;
+  for (int r = 0; r < R; ++r) {
+    sc += sqrtf(sums[3 * r + 0]) / sqrtf(sums[3 * r + 1]);
+    mag += sums[3 * r + 2] / numel[r];
+  }
+  if (R > 0) { sc /= (float)R; mag /= (float)R; }
+  const float mel = slots[0], adv = slots[1], fm = slots[2], real = slots[3], fake = slots[4];
+  const float gen = la * (sc + mag + mel) + ladv * (adv + lfm * fm);
+  const float v[9] = {sc, mag, mel, adv, fm, gen, real, fake, real + fake};
+  for (int i = 0; i < 9; ++i) {
+    vals[i] = v[i];
+    running[i] += v[i];
+  }
+}
+
 }  // namespace artic
 
 using namespace artic;
@@ -214,11 +243,16 @@ extern "C" int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32
 }
 
 extern "C" int artic_mean3_act(const void* a, const void* b, const void* c, void* out_act, int64_t n, float slope,
-                               int32_t dtype, void* stream) {
+                               int32_t dtype, int32_t out_dtype, void* stream) {
   ARTIC_CHECK_ARG(a && b && c && out_act, "null pointer");
+  ARTIC_CHECK_ARG(out_dtype == ARTIC_F32 || out_dtype == ARTIC_BF16, "bad out dtype");
   if (n == 0) return ARTIC_OK;
-  DISPATCH(dtype, (mean3_act_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, (const float*)c, (float*)out_act, n, slope)),
-           (mean3_act_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out_act, n, slope)));
+  if (out_dtype == ARTIC_F32) {
+    DISPATCH(dtype, (mean3_act_kernel<float, float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, (const float*)c, (float*)out_act, n, slope)),
+             (mean3_act_kernel<bf16, float><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (float*)out_act, n, slope)));
+  }
+  DISPATCH(dtype, (mean3_act_kernel<float, bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, (const float*)c, (bf16*)out_act, n, slope)),
+           (mean3_act_kernel<bf16, bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out_act, n, slope)));
 }
 
 extern "C" int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64_t n, int32_t dtype, void* stream) {
@@ -321,4 +355,25 @@ extern "C" int artic_l1_bwd(const void* a, const void* b, int64_t n, float scale
   if (n == 0) return ARTIC_OK;
   DISPATCH(dtype, (l1_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, n, scale, (float*)da, accumulate)),
            (l1_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, n, scale, (bf16*)da, accumulate)));
+}
+
+extern "C" int artic_add_rows(const float* src, int64_t src_pitch, float* dst, int64_t dst_pitch, int32_t rows,
+                              int32_t cols, void* stream) {
+  ARTIC_CHECK_ARG(src && dst, "null pointer");
+  ARTIC_CHECK_ARG(rows >= 0 && cols >= 0 && src_pitch >= cols && dst_pitch >= cols, "bad geometry");
+  const int64_t n = (int64_t)rows * cols;
+  if (n == 0) return ARTIC_OK;
+  add_rows_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, src_pitch, dst, dst_pitch, rows, cols);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}
+
+extern "C" int artic_train_log(const float* slots, const float* stft_sums, const float* stft_numel, int32_t R,
+                               float lambda_aux, float lambda_adv, float lambda_fm, float* vals, float* running,
+                               void* stream) {
+  ARTIC_CHECK_ARG(slots && vals && running && (R == 0 || (stft_sums && stft_numel)), "null pointer");
+  train_log_kernel<<<1, 32, 0, ST(stream)>>>(slots, stft_sums, stft_numel, R, lambda_aux, lambda_adv, lambda_fm, vals,
+                                            running);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
 }

@@ -57,7 +57,7 @@ template <> struct Vec4<__nv_bfloat16> {
 // forward / dgrad
 // ------------------------------------------------------------------------------------
 // TNT = output channels per thread (TN = 16 * TNT); VEC = 4-wide loads/stores allowed.
-template <typename T, int TNT, bool VEC>
+template <typename T, typename TO, int TNT, bool VEC>
 __global__ void __launch_bounds__(NT) tapconv_kernel(const __grid_constant__ artic_tapconv_t p) {
   constexpr int TN = 16 * TNT;
   __shared__ __align__(16) float Xs[TK][TM];
@@ -176,12 +176,12 @@ __global__ void __launch_bounds__(NT) tapconv_kernel(const __grid_constant__ art
 
   // ---- epilogue
   const float* __restrict__ bias = p.bias;
-  const T* __restrict__ res_pre = reinterpret_cast<const T*>(p.res_pre);
-  const T* __restrict__ mask = reinterpret_cast<const T*>(p.mask);
-  const T* __restrict__ res = reinterpret_cast<const T*>(p.res);
-  const T* __restrict__ res2 = reinterpret_cast<const T*>(p.res2);
-  T* __restrict__ Y = reinterpret_cast<T*>(p.Y);
-  T* __restrict__ Y2 = reinterpret_cast<T*>(p.Y2);
+  const TO* __restrict__ res_pre = reinterpret_cast<const TO*>(p.res_pre);
+  const TO* __restrict__ mask = reinterpret_cast<const TO*>(p.mask);
+  const TO* __restrict__ res = reinterpret_cast<const TO*>(p.res);
+  const TO* __restrict__ res2 = reinterpret_cast<const TO*>(p.res2);
+  TO* __restrict__ Y = reinterpret_cast<TO*>(p.Y);
+  TO* __restrict__ Y2 = reinterpret_cast<TO*>(p.Y2);
   const int cbase = co0 + tx * TNT;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -197,17 +197,17 @@ __global__ void __launch_bounds__(NT) tapconv_kernel(const __grid_constant__ art
     if (VEC && TNT == 4 && cbase + 3 < p.Cog) {
       float t[4];
       float vv[4] = {v[0], v[1 % TNT], v[2 % TNT], v[3 % TNT]};
-      if (res_pre) { Vec4<T>::load(res_pre + o, t); for (int j = 0; j < 4; ++j) vv[j] += t[j]; }
-      if (mask) { Vec4<T>::load(mask + o, t); for (int j = 0; j < 4; ++j) vv[j] *= (t[j] > 0.f ? 1.f : p.mask_slope); }
-      if (res) { Vec4<T>::load(res + o, t); for (int j = 0; j < 4; ++j) vv[j] += t[j]; }
-      if (res2) { Vec4<T>::load(res2 + o, t); for (int j = 0; j < 4; ++j) vv[j] += t[j]; }
-      if (Y) Vec4<T>::store(Y + o, vv);
+      if (res_pre) { Vec4<TO>::load(res_pre + o, t); for (int j = 0; j < 4; ++j) vv[j] += t[j]; }
+      if (mask) { Vec4<TO>::load(mask + o, t); for (int j = 0; j < 4; ++j) vv[j] *= (t[j] > 0.f ? 1.f : p.mask_slope); }
+      if (res) { Vec4<TO>::load(res + o, t); for (int j = 0; j < 4; ++j) vv[j] += t[j]; }
+      if (res2) { Vec4<TO>::load(res2 + o, t); for (int j = 0; j < 4; ++j) vv[j] += t[j]; }
+      if (Y) Vec4<TO>::store(Y + o, vv);
       if (Y2) {
         for (int j = 0; j < 4; ++j) {
           if (p.act == ARTIC_ACT_LRELU) vv[j] = vv[j] > 0.f ? vv[j] : p.act_slope * vv[j];
           else if (p.act == ARTIC_ACT_TANH) vv[j] = tanhf(vv[j]);
         }
-        Vec4<T>::store(Y2 + o, vv);
+        Vec4<TO>::store(Y2 + o, vv);
       }
     } else {
 #pragma unroll
@@ -237,13 +237,13 @@ static bool ptr_vec_ok(const void* p, int esize) {
   return p == nullptr || (reinterpret_cast<uintptr_t>(p) % (4 * esize) == 0);
 }
 
-template <typename T>
+template <typename T, typename TO>
 static int launch_tapconv(const artic_tapconv_t& p, cudaStream_t st) {
-  const int es = (int)sizeof(T);
+  const int es = (int)sizeof(T), eo = (int)sizeof(TO);
   const bool vec_in = (p.Cig % 4 == 0) && seq_vec_ok(p.x, es) && ptr_vec_ok(p.X, es);
-  const bool vec_out = (p.Cog % 4 == 0) && seq_vec_ok(p.y, es) && ptr_vec_ok(p.Y, es) && ptr_vec_ok(p.Y2, es) &&
-                       ptr_vec_ok(p.res, es) && ptr_vec_ok(p.res2, es) && ptr_vec_ok(p.res_pre, es) &&
-                       ptr_vec_ok(p.mask, es);
+  const bool vec_out = (p.Cog % 4 == 0) && seq_vec_ok(p.y, eo) && ptr_vec_ok(p.Y, eo) && ptr_vec_ok(p.Y2, eo) &&
+                       ptr_vec_ok(p.res, eo) && ptr_vec_ok(p.res2, eo) && ptr_vec_ok(p.res_pre, eo) &&
+                       ptr_vec_ok(p.mask, eo);
   const bool vec = vec_in && vec_out;
   const int64_t Mtot = (int64_t)p.N * p.nq;
   const int tnt = p.Cog > 16 ? 4 : 1;
@@ -251,12 +251,12 @@ static int launch_tapconv(const artic_tapconv_t& p, cudaStream_t st) {
   dim3 grid((unsigned)((Mtot + TM - 1) / TM), (unsigned)(((p.Cog + TN - 1) / TN) * p.G), 1);
   if (grid.y > 65535) { set_error("artic_tapconv: too many channel tiles"); return ARTIC_ENOSUP; }
   if (tnt == 4) {
-    if (vec) tapconv_kernel<T, 4, true><<<grid, NT, 0, st>>>(p);
-    else tapconv_kernel<T, 4, false><<<grid, NT, 0, st>>>(p);
+    if (vec) tapconv_kernel<T, TO, 4, true><<<grid, NT, 0, st>>>(p);
+    else tapconv_kernel<T, TO, 4, false><<<grid, NT, 0, st>>>(p);
   } else {
     // narrow outputs: VEC epilogue is never used (TNT == 1); input vector loads still help
-    if (vec_in) tapconv_kernel<T, 1, true><<<grid, NT, 0, st>>>(p);
-    else tapconv_kernel<T, 1, false><<<grid, NT, 0, st>>>(p);
+    if (vec_in) tapconv_kernel<T, TO, 1, true><<<grid, NT, 0, st>>>(p);
+    else tapconv_kernel<T, TO, 1, false><<<grid, NT, 0, st>>>(p);
   }
   return ARTIC_OK;
 }
@@ -267,7 +267,7 @@ static int launch_tapconv(const artic_tapconv_t& p, cudaStream_t st) {
 constexpr int WT = 64;  // ci tile and co tile
 constexpr int WR = 16;  // rows per chunk
 
-template <typename T>
+template <typename T, typename TY>
 __global__ void __launch_bounds__(NT) tapwgrad_kernel(const __grid_constant__ artic_tapwgrad_t p, int rows_per_split) {
   __shared__ __align__(16) float Xs[WR][WT];
   __shared__ __align__(16) float Ys[WR][WT];
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(NT) tapwgrad_kernel(const __grid_constant__ ar
   const int64_t mb = (int64_t)blockIdx.z * rows_per_split;
   const int64_t me = min(Mtot, mb + rows_per_split);
   const T* __restrict__ X = reinterpret_cast<const T*>(p.X);
-  const T* __restrict__ dY = reinterpret_cast<const T*>(p.dY);
+  const TY* __restrict__ dY = reinterpret_cast<const TY*>(p.dY);
   const int xoff = p.off[tap], yoff = p.yoff[tap];
 
   float acc[4][4];
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(NT) tapwgrad_kernel(const __grid_constant__ ar
   }
 }
 
-template <typename T>
+template <typename T, typename TY>
 static int launch_tapwgrad(const artic_tapwgrad_t& p, cudaStream_t st) {
   const int n_ci_t = (p.Cig + WT - 1) / WT, n_co_t = (p.Cog + WT - 1) / WT;
   const int64_t Mtot = (int64_t)p.N * p.nq;
@@ -360,7 +360,7 @@ static int launch_tapwgrad(const artic_tapwgrad_t& p, cudaStream_t st) {
   splits = (Mtot + rps - 1) / rps;
   dim3 grid((unsigned)(n_ci_t * n_co_t), (unsigned)(p.ntaps * p.G), (unsigned)splits);
   if (grid.y > 65535) { set_error("artic_tapconv_wgrad: taps*groups too large"); return ARTIC_ENOSUP; }
-  tapwgrad_kernel<T><<<grid, NT, 0, st>>>(p, (int)rps);
+  tapwgrad_kernel<T, TY><<<grid, NT, 0, st>>>(p, (int)rps);
   return ARTIC_OK;
 }
 
@@ -416,16 +416,18 @@ extern "C" int artic_tapconv(const artic_tapconv_t* p, void* stream) {
   ARTIC_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= ARTIC_MAX_TAPS, "ntaps out of range");
   ARTIC_CHECK_ARG(p->si >= 1 && p->so >= 1 && p->nq >= 0, "bad q mapping");
   ARTIC_CHECK_ARG(p->dtype == ARTIC_F32 || p->dtype == ARTIC_BF16, "bad dtype");
+  ARTIC_CHECK_ARG(p->out_dtype == ARTIC_F32 || p->out_dtype == ARTIC_BF16, "bad out_dtype");
   if (p->N == 0 || p->nq == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
+  const bool ob = p->out_dtype == ARTIC_BF16;
   if (p->dtype == ARTIC_BF16) {
-    rc = artic_tapconv_tc_try(p, st);
+    rc = ob ? artic_tapconv_tc_try(p, st) : 0;
     if (rc < 0) return rc;
-    if (rc == 0) rc = launch_tapconv<__nv_bfloat16>(*p, st);
+    if (rc == 0) rc = ob ? launch_tapconv<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapconv<__nv_bfloat16, float>(*p, st);
     else rc = ARTIC_OK;
   } else {
-    rc = launch_tapconv<float>(*p, st);
+    rc = ob ? launch_tapconv<float, __nv_bfloat16>(*p, st) : launch_tapconv<float, float>(*p, st);
   }
   if (rc != ARTIC_OK) return rc;
   ARTIC_LAUNCH_CHECK();
@@ -440,9 +442,13 @@ extern "C" int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream) {
   ARTIC_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= ARTIC_MAX_TAPS, "ntaps out of range");
   ARTIC_CHECK_ARG(p->si >= 1 && p->so >= 1 && p->nq >= 0, "bad q mapping");
   ARTIC_CHECK_ARG(p->dtype == ARTIC_F32 || p->dtype == ARTIC_BF16, "bad dtype");
+  ARTIC_CHECK_ARG(p->y_dtype == ARTIC_F32 || p->y_dtype == ARTIC_BF16, "bad y_dtype");
   if (p->N == 0 || p->nq == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int rc = p->dtype == ARTIC_BF16 ? launch_tapwgrad<__nv_bfloat16>(*p, st) : launch_tapwgrad<float>(*p, st);
+  const bool yb = p->y_dtype == ARTIC_BF16;
+  int rc;
+  if (p->dtype == ARTIC_BF16) rc = yb ? launch_tapwgrad<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapwgrad<__nv_bfloat16, float>(*p, st);
+  else rc = yb ? launch_tapwgrad<float, __nv_bfloat16>(*p, st) : launch_tapwgrad<float, float>(*p, st);
   if (rc != ARTIC_OK) return rc;
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;

@@ -1,0 +1,622 @@
+"""Host-side execution engine: explicit forward / backward schedules of the HiFi-GAN
+generator and the multi-scale / multi-period discriminator over the C-ABI kernels.
+
+There is no autograd inside: every activation that the backward needs is kept on a
+tape by the forward, and the backward is a hand-written schedule of tap-gather GEMM
+dgrad / wgrad launches with the LeakyReLU masks, residual adds, MRF 1/3 scaling and
+feature-matching gradients fused into the GEMM epilogues.  All work is enqueued on the
+current CUDA stream with no host synchronisation, so a whole train step can be captured
+in one CUDA graph (trainer.py).
+
+Layouts: activations are channels-last (N, L, C); the period discriminators keep the
+reference's (B, H, p) element order with C innermost, i.e. (B, H, p, C), addressed as
+N = B*p interleaved sequences (artic_seq_t.n_inner = p) — so the reference's
+view(b, c, t//p, p) (models/hifigan.py:417) is a zero-copy reinterpretation.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH, BF16, F32, TORCH_DTYPE, call, ptr
+from .convspec import ConvSpec
+
+
+# --------------------------------------------------------------------------- #
+# tensors                                                                     #
+# --------------------------------------------------------------------------- #
+class SeqT:
+    """Channels-last sequence batch in a torch tensor (see include/artic.h artic_seq_t)."""
+    __slots__ = ("t", "N", "L", "C", "n_inner", "s_outer", "s_inner", "s_row", "code")
+
+    def __init__(self, t, N, L, C, n_inner=1, s_outer=None, s_inner=0, s_row=None):
+        self.t, self.N, self.L, self.C, self.n_inner = t, N, L, C, n_inner
+        self.s_row = C if s_row is None else s_row
+        self.s_outer = L * C if s_outer is None else s_outer
+        self.s_inner = s_inner
+        self.code = _lib.DTYPE_CODE[t.dtype]
+
+    @staticmethod
+    def empty(N, L, C, code, device, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return SeqT(f((N, L, C), dtype=TORCH_DTYPE[code], device=device), N, L, C)
+
+    @staticmethod
+    def period(B, H, p, C, code, device):
+        t = torch.empty((B, H, p, C), dtype=TORCH_DTYPE[code], device=device)
+        return SeqT(t, B * p, H, C, n_inner=p, s_outer=H * p * C, s_inner=C, s_row=p * C)
+
+    def like(self, code=None, C=None, L=None):
+        """New storage with the same batch structure (optionally other dtype / width / length)."""
+        code = self.code if code is None else code
+        C = self.C if C is None else C
+        L = self.L if L is None else L
+        if self.n_inner == 1:
+            return SeqT.empty(self.N, L, C, code, self.t.device)
+        return SeqT.period(self.N // self.n_inner, L, self.n_inner, C, code, self.t.device)
+
+    def seq(self):
+        return _lib.Seq(self.s_outer, self.s_inner, self.s_row, self.n_inner, self.L)
+
+    def numel(self):
+        return self.N * self.L * self.C
+
+
+def _fill_taps(dst_off, dst_idx, off, widx):
+    n = len(off)
+    for i in range(n):
+        dst_off[i] = off[i]
+        dst_idx[i] = widx[i]
+    return n
+
+
+def tapconv(launches, X: SeqT, W, G, Cig, Cog, Y: Optional[SeqT] = None, Y2: Optional[SeqT] = None,
+            bias=None, res_pre: Optional[SeqT] = None, mask: Optional[SeqT] = None,
+            res: Optional[SeqT] = None, res2: Optional[SeqT] = None, alpha=1.0, mask_slope=1.0,
+            act=ACT_NONE, act_slope=0.0):
+    """Issue the artic_tapconv launches of one layer direction."""
+    yref = Y if Y is not None else Y2
+    assert yref is not None and X.C == G * Cig and yref.C == G * Cog and X.N == yref.N
+    for o in (Y, Y2, res_pre, mask, res, res2):
+        assert o is None or (o.code == yref.code and o.s_row == yref.s_row and o.s_outer == yref.s_outer
+                             and o.L == yref.L and o.n_inner == yref.n_inner), "epilogue tensors must share Y's layout"
+    assert W.dtype == X.t.dtype
+    for L in launches:
+        p = _lib.TapConv()
+        p.X, p.W, p.bias = ptr(X.t), ptr(W), ptr(bias)
+        p.res_pre = ptr(res_pre.t) if res_pre is not None else None
+        p.mask = ptr(mask.t) if mask is not None else None
+        p.res = ptr(res.t) if res is not None else None
+        p.res2 = ptr(res2.t) if res2 is not None else None
+        p.Y = ptr(Y.t) if Y is not None else None
+        p.Y2 = ptr(Y2.t) if Y2 is not None else None
+        p.x, p.y = X.seq(), yref.seq()
+        p.N, p.G, p.Cig, p.Cog = X.N, G, Cig, Cog
+        p.q0, p.nq, p.si, p.so, p.ro = L.q0, L.nq, L.si, L.so, L.ro
+        p.ntaps = _fill_taps(p.off, p.widx, L.off, L.widx)
+        p.alpha, p.mask_slope, p.act_slope, p.act = alpha, mask_slope, act_slope, act
+        p.dtype, p.out_dtype = X.code, yref.code
+        call("artic_tapconv", p)
+
+
+# --------------------------------------------------------------------------- #
+# one conv-like layer                                                         #
+# --------------------------------------------------------------------------- #
+class ConvLayer:
+    """A conv / convT / linear layer bound to its torch parameters.
+
+    ``in_code`` is the storage dtype of the layer input (and of the forward weight),
+    ``out_code`` the dtype of its output (and of the dY / backward weight)."""
+
+    def __init__(self, spec: ConvSpec, name: str, in_code: int, out_code: int):
+        self.spec, self.name, self.in_code, self.out_code = spec, name, in_code, out_code
+        self.v = self.g = self.b = None          # torch parameters (fp32, device)
+        self.Wf = self.Wb = self.scale = None    # prepared weights
+        self.dWf = None                          # fp32 wgrad accumulator, 'fwd' layout
+
+    # ---- parameters ----------------------------------------------------------
+    def bind(self, params: Dict[str, torch.Tensor]):
+        """Bind to tensors from a name->tensor mapping with the reference's key names."""
+        n = self.name
+        if n + ".weight_v" in params:
+            self.v, self.g = params[n + ".weight_v"], params[n + ".weight_g"]
+        else:
+            self.v, self.g = params[n + ".weight"], None
+        self.b = params.get(n + ".bias")
+        for t in (self.v, self.g, self.b):
+            if t is not None:
+                _lib.require_cuda(t, f"parameter of {n}")
+                assert t.dtype == torch.float32 and t.is_contiguous()
+        shape = tuple(self.v.shape)
+        want = self.spec.weight_shape()
+        assert shape == want or shape == want + (1,), f"{n}: weight shape {shape} != {want}"
+
+    def param_names(self):
+        n = self.name
+        names = [n + ".weight_g", n + ".weight_v"] if self.g is not None else [n + ".weight"]
+        if self.b is not None:
+            names.append(n + ".bias")
+        return names
+
+    def prep(self, need_bwd=True):
+        """(Re)materialise the effective weights from the current parameters."""
+        s, dev = self.spec, self.v.device
+        rows, row_len = s.wn_rows()
+        if self.g is not None and self.scale is None:
+            self.scale = torch.empty(2 * rows, dtype=torch.float32, device=dev)
+        for direction in ("fwd", "bwd") if need_bwd else ("fwd",):
+            A, B, sk, sg, sa, sb = s.prep_strides(direction)
+            code = self.in_code if direction == "fwd" else self.out_code
+            buf = self.Wf if direction == "fwd" else self.Wb
+            if buf is None or buf.dtype != TORCH_DTYPE[code]:
+                buf = torch.empty((s.k, s.groups, A, B), dtype=TORCH_DTYPE[code], device=dev)
+                if direction == "fwd":
+                    self.Wf = buf
+                else:
+                    self.Wb = buf
+            call("artic_weight_prep", ptr(self.v), ptr(self.g), ptr(self.scale), rows, row_len,
+                 s.k, s.groups, A, B, sk, sg, sa, sb, ptr(buf), code)
+
+    # ---- compute -------------------------------------------------------------
+    def forward(self, X: SeqT, Y=None, Y2=None, **epi):
+        s = self.spec
+        tapconv(s.fwd_launches(X.L), X, self.Wf, s.groups, s.cig, s.cog, Y=Y, Y2=Y2, bias=self.b, **epi)
+
+    def dgrad(self, dY: SeqT, dX: Optional[SeqT] = None, dX2: Optional[SeqT] = None, **epi):
+        s = self.spec
+        lin = (dX if dX is not None else dX2).L
+        tapconv(s.dgrad_launches(lin), dY, self.Wb, s.groups, s.cog, s.cig, Y=dX, Y2=dX2, **epi)
+
+    def zero_wgrad(self):
+        if self.dWf is None:
+            s = self.spec
+            self.dWf = torch.zeros((s.k, s.groups, s.cig, s.cog), dtype=torch.float32, device=self.v.device)
+        else:
+            self.dWf.zero_()
+
+    def wgrad(self, X: SeqT, dY: SeqT, grads: Dict[str, torch.Tensor]):
+        """Accumulate dW (prepared layout) and the bias gradient (into grads[name.bias])."""
+        s = self.spec
+        L = s.wgrad_launch(X.L)
+        p = _lib.TapWgrad()
+        p.X, p.dY, p.dW = ptr(X.t), ptr(dY.t), ptr(self.dWf)
+        p.x, p.y = X.seq(), dY.seq()
+        p.N, p.G, p.Cig, p.Cog = X.N, s.groups, s.cig, s.cog
+        p.q0, p.nq, p.si, p.so = L.q0, L.nq, L.si, L.so
+        p.ntaps = len(L.off)
+        for i in range(p.ntaps):
+            p.off[i], p.yoff[i], p.widx[i] = L.off[i], L.yoff[i], L.widx[i]
+        p.dtype, p.y_dtype = X.code, dY.code
+        call("artic_tapconv_wgrad", p)
+        if self.b is not None:
+            call("artic_colsum", ptr(dY.t), dY.seq(), dY.N, dY.C, dY.code, ptr(grads[self.name + ".bias"]))
+
+    def finish_grads(self, grads: Dict[str, torch.Tensor]):
+        """dW (prepared layout) -> gradients of the torch parameters (weight-norm backward)."""
+        s = self.spec
+        rows, row_len = s.wn_rows()
+        A, B, sk, sg, sa, sb = s.prep_strides("fwd")
+        n = self.name
+        if self.g is not None:
+            dv, dg = grads[n + ".weight_v"], grads[n + ".weight_g"]
+        else:
+            dv, dg = grads[n + ".weight"], None
+        call("artic_weight_unprep", ptr(self.dWf), ptr(self.v), ptr(self.g), ptr(self.scale), rows, row_len,
+             s.k, s.groups, A, B, sk, sg, sa, sb, ptr(dv), ptr(dg))
+
+
+def _zero_grads_like(layers: List[ConvLayer]) -> Dict[str, torch.Tensor]:
+    out = {}
+    for l in layers:
+        for t, suffix in ((l.g, ".weight_g"), (l.v, ".weight_v" if l.g is not None else ".weight"), (l.b, ".bias")):
+            if t is not None:
+                out[l.name + suffix] = torch.zeros_like(t)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# generator                                                                   #
+# --------------------------------------------------------------------------- #
+class GeneratorEngine:
+    """HiFiGANGenerator.forward (reference models/hifigan.py:198-239) and its backward."""
+
+    def __init__(self, in_channels, out_channels, channels, kernel_size, upsample_scales,
+                 upsample_kernel_sizes, paddings, output_paddings, resblock_kernel_sizes,
+                 resblock_dilations, use_additional_convs, slope, use_weight_norm, use_ar, ar_input,
+                 ar_hidden, ar_output, use_tanh, code=F32):
+        assert use_additional_convs, "use_additional_convs=False is not on the hot path"
+        assert len(resblock_kernel_sizes) == 3, "the MRF mean kernel is written for 3 blocks"
+        self.code, self.slope, self.use_ar, self.use_tanh = code, slope, use_ar, use_tanh
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.ar_input, self.ar_output = ar_input, ar_output
+        self.scales = list(upsample_scales)
+        self.dilations = [list(d) for d in resblock_dilations]
+        wn = use_weight_norm
+        c = code
+        L = self.layers = {}
+
+        def add(name, spec, ic=c, oc=c):
+            spec.weight_norm = wn and spec.kind != "linear"
+            spec.name = name
+            L[name] = ConvLayer(spec, name, ic, oc)
+            return L[name]
+
+        add("input_conv", ConvSpec("conv", in_channels, channels, k=kernel_size, padding=(kernel_size - 1) // 2))
+        self.n_blocks = len(resblock_kernel_sizes)
+        for i, (s, k) in enumerate(zip(upsample_scales, upsample_kernel_sizes)):
+            add(f"upsamples.{i}.1", ConvSpec("convT", channels // 2 ** i, channels // 2 ** (i + 1), k=k, stride=s,
+                                             padding=paddings[i], output_padding=output_paddings[i]))
+            ch = channels // 2 ** (i + 1)
+            for j, rk in enumerate(resblock_kernel_sizes):
+                for di, d in enumerate(resblock_dilations[j]):
+                    b = i * self.n_blocks + j
+                    add(f"blocks.{b}.convs1.{di}.1", ConvSpec("conv", ch, ch, k=rk, dilation=d, padding=(rk - 1) // 2 * d))
+                    add(f"blocks.{b}.convs2.{di}.1", ConvSpec("conv", ch, ch, k=rk, padding=(rk - 1) // 2))
+        # the output conv reads a bf16/fp32 activation and writes the fp32 waveform
+        add("output_conv.1", ConvSpec("conv", channels // 2 ** len(upsample_scales), out_channels, k=kernel_size,
+                                      padding=(kernel_size - 1) // 2), ic=c, oc=F32)
+        if use_ar:
+            dims = [ar_input] + [ar_hidden] * 4 + [ar_output]
+            for li in range(5):
+                add(f"ar_model.model.{2 * li}", ConvSpec("linear", dims[li], dims[li + 1]))
+        self._prepped = False
+
+    # ---- parameters ----------------------------------------------------------
+    def bind(self, params):
+        for l in self.layers.values():
+            l.bind(params)
+        self._prepped = False
+
+    def prep_weights(self, need_bwd=True):
+        for l in self.layers.values():
+            l.prep(need_bwd)
+        self._prepped = True
+
+    def param_names(self):
+        return [n for l in self.layers.values() for n in l.param_names()]
+
+    # ---- forward -------------------------------------------------------------
+    def forward(self, c: torch.Tensor, ar: Optional[torch.Tensor], save=True):
+        """c (B, Cc, T') fp32 channel-first, ar (B, 1, ar_input) fp32 -> ((B, 1, T) fp32, tape)."""
+        _lib.require_cuda(c, "c")
+        assert self._prepped, "call prep_weights() after binding / updating parameters"
+        L, code, dev, slope = self.layers, self.code, c.device, self.slope
+        B, Cc, Tn = c.shape
+        c = c.contiguous().float()
+        tape = {"B": B, "Tn": Tn, "Cc": Cc} if save else None
+        ar_feats = None
+        Ca = 0
+        if self.use_ar:
+            Ca = self.ar_output
+            a0 = SeqT.empty(B, 1, self.ar_input, code, dev)
+            call("artic_cast", ptr(ar.contiguous().float()), F32, ptr(a0.t), code, B * self.ar_input)
+            acts = [a0]
+            h = a0
+            for li in range(5):
+                lay = L[f"ar_model.model.{2 * li}"]
+                o = SeqT.empty(B, 1, lay.spec.cout, code, dev)
+                if li < 4:
+                    lay.forward(h, Y2=o, act=ACT_LRELU, act_slope=0.1)   # pytorch_layers.py:440,446
+                else:
+                    lay.forward(h, Y=o)
+                acts.append(o)
+                h = o
+            ar_feats = h
+            if save:
+                tape["ar_acts"] = acts
+        assert Cc + Ca == self.in_channels, f"in_channels {self.in_channels} != {Cc} + {Ca}"
+        gin = SeqT.empty(B, Tn, Cc + Ca, code, dev)
+        call("artic_gen_input", ptr(c), ptr(ar_feats.t) if ar_feats is not None else None, ptr(gin.t),
+             B, Cc, Ca, Tn, code)
+        a = SeqT.empty(B, Tn, L["input_conv"].spec.cout, code, dev)
+        L["input_conv"].forward(gin, Y2=a, act=ACT_LRELU, act_slope=slope)
+        if save:
+            tape["gin"], tape["stages"] = gin, []
+        n_stage = len(self.scales)
+        for i in range(n_stage):
+            up = L[f"upsamples.{i}.1"]
+            lo = up.spec.out_len(a.L)
+            u = SeqT.empty(B, lo, up.spec.cout, code, dev)
+            au = u.like()
+            up.forward(a, Y=u, Y2=au, act=ACT_LRELU, act_slope=slope)
+            st = {"a_in": a, "a_u": au, "blocks": []}
+            outs = []
+            for j in range(self.n_blocks):
+                b = i * self.n_blocks + j
+                x, ax = u, au
+                pairs = []
+                nd = len(self.dilations[j])
+                for di in range(nd):
+                    at = u.like()
+                    L[f"blocks.{b}.convs1.{di}.1"].forward(ax, Y2=at, act=ACT_LRELU, act_slope=slope)
+                    xn = u.like()
+                    axn = u.like() if di < nd - 1 else None
+                    L[f"blocks.{b}.convs2.{di}.1"].forward(at, Y=xn, Y2=axn, res=x, act=ACT_LRELU, act_slope=slope)
+                    pairs.append((ax, at))
+                    x, ax = xn, axn
+                outs.append(x)
+                st["blocks"].append(pairs)
+            last = i == n_stage - 1
+            # LeakyReLU before the output conv uses torch's default slope 0.01 (hifigan.py:150)
+            st["slope_out"] = 0.01 if last else slope
+            a = u.like()
+            call("artic_mean3_act", ptr(outs[0].t), ptr(outs[1].t), ptr(outs[2].t), ptr(a.t), a.numel(),
+                 st["slope_out"], code, code)
+            st["a_c"] = a
+            if save:
+                tape["stages"].append(st)
+        y = SeqT.empty(B, a.L, self.out_channels, F32, dev)
+        if self.use_tanh:
+            L["output_conv.1"].forward(a, Y2=y, act=ACT_TANH)
+        else:
+            L["output_conv.1"].forward(a, Y=y)
+        if save:
+            tape["y"] = y
+        # (B, T, C_out) channels-last -> (B, C_out, T); zero-copy for out_channels == 1
+        out = y.t.permute(0, 2, 1) if self.out_channels > 1 else y.t.view(B, 1, a.L)
+        return out, tape
+
+    # ---- backward ------------------------------------------------------------
+    def backward(self, tape, dy: torch.Tensor, grads: Dict[str, torch.Tensor]):
+        """dy: (B, C_out, T) fp32 gradient of the waveform.  Accumulates parameter gradients
+        into ``grads`` (name -> fp32 tensor shaped like the parameter)."""
+        L, code, slope = self.layers, self.code, self.slope
+        B = tape["B"]
+        dev = dy.device
+        for l in L.values():
+            l.zero_wgrad()
+        y = tape["y"]
+        dyc = dy.permute(0, 2, 1).contiguous().float() if self.out_channels > 1 else dy.contiguous().float()
+        dpre = SeqT.empty(B, y.L, self.out_channels, F32, dev)
+        if self.use_tanh:
+            call("artic_tanh_bwd", ptr(dyc), ptr(y.t), ptr(dpre.t), dpre.numel(), F32)
+        else:
+            dpre.t.view(-1).copy_(dyc.reshape(-1))
+        stages = tape["stages"]
+        oc = L["output_conv.1"]
+        a_c = stages[-1]["a_c"]
+        oc.wgrad(a_c, dpre, grads)
+        # gradient wrt each MRF block output of the last stage: (1/3) * lrelu'(a_c) * dgrad
+        g = a_c.like()
+        oc.dgrad(dpre, dX=g, mask=a_c, mask_slope=stages[-1]["slope_out"], alpha=1.0 / self.n_blocks)
+        for i in range(len(stages) - 1, -1, -1):
+            st = stages[i]
+            du = None
+            for j in range(self.n_blocks):
+                b = i * self.n_blocks + j
+                gx = g
+                pairs = st["blocks"][j]
+                for di in range(len(pairs) - 1, -1, -1):
+                    ax, at = pairs[di]
+                    c2, c1 = L[f"blocks.{b}.convs2.{di}.1"], L[f"blocks.{b}.convs1.{di}.1"]
+                    c2.wgrad(at, gx, grads)
+                    dt = at.like()
+                    c2.dgrad(gx, dX=dt, mask=at, mask_slope=slope)
+                    c1.wgrad(ax, dt, grads)
+                    if di > 0:
+                        gn = ax.like()
+                        c1.dgrad(dt, dX=gn, mask=ax, mask_slope=slope, res=gx)
+                    else:  # block input: accumulate over the three blocks into du
+                        gn = ax.like() if du is None else du
+                        c1.dgrad(dt, dX=gn, mask=ax, mask_slope=slope, res=gx, res2=du)
+                        du = gn
+                    gx = gn
+            up = L[f"upsamples.{i}.1"]
+            a_in = st["a_in"]
+            up.wgrad(a_in, du, grads)
+            g = a_in.like()
+            if i > 0:
+                up.dgrad(du, dX=g, mask=a_in, mask_slope=stages[i - 1]["slope_out"], alpha=1.0 / self.n_blocks)
+            else:
+                up.dgrad(du, dX=g, mask=a_in, mask_slope=slope)
+        ic = L["input_conv"]
+        gin = tape["gin"]
+        ic.wgrad(gin, g, grads)
+        if self.use_ar:
+            dgin = gin.like()
+            ic.dgrad(g, dX=dgin)
+            Ca = self.ar_output
+            d_ar32 = torch.empty((B, Ca), dtype=torch.float32, device=dev)
+            call("artic_gen_input_bwd", ptr(dgin.t), ptr(d_ar32), B, tape["Cc"], Ca, tape["Tn"], code)
+            dz = SeqT.empty(B, 1, Ca, code, dev)
+            call("artic_cast", ptr(d_ar32), F32, ptr(dz.t), code, B * Ca)
+            acts = tape["ar_acts"]
+            for li in range(4, -1, -1):
+                lay = L[f"ar_model.model.{2 * li}"]
+                lay.wgrad(acts[li], dz, grads)
+                if li > 0:
+                    dn = acts[li].like()
+                    lay.dgrad(dz, dX=dn, mask=acts[li], mask_slope=0.1)
+                    dz = dn
+        for l in L.values():
+            l.finish_grads(grads)
+
+    def new_grads(self):
+        return _zero_grads_like(list(self.layers.values()))
+
+
+# --------------------------------------------------------------------------- #
+# discriminator                                                               #
+# --------------------------------------------------------------------------- #
+class _Chain:
+    """One sub-discriminator: a chain of conv layers, LeakyReLU after all but the last."""
+
+    def __init__(self, layers: List[ConvLayer], kind: str, period: int = 1, scale_index: int = 0):
+        self.layers, self.kind, self.period, self.scale_index = layers, kind, period, scale_index
+
+
+class DiscriminatorEngine:
+    """HiFiGANMultiScaleMultiPeriodDiscriminator (reference models/hifigan.py:741-825):
+    ``scales`` scale discriminators on an AvgPool1d pyramid followed by one period
+    discriminator per period.  Feature maps are stored in ``code`` dtype, the first conv of
+    every chain reads the fp32 signal and the logits are written in fp32."""
+
+    def __init__(self, scales, pool_params, scale_params, follow_official_norm, periods, period_params, code=F32):
+        from .convspec import ConvSpec as CS
+        self.code = code
+        self.pool = dict(pool_params)
+        self.slope_s = scale_params["nonlinear_activation_params"]["negative_slope"]
+        self.slope_p = period_params["nonlinear_activation_params"]["negative_slope"]
+        self.chains: List[_Chain] = []
+        sp, pp = scale_params, period_params
+        # NOTE reference quirk: the MSD norm hooks test isinstance(m, Conv2d) on
+        # Conv1d layers (hifigan.py:645-663), so NO weight/spectral norm is ever applied to MSD.
+        for s in range(scales):
+            ks = sp["kernel_sizes"]
+            specs = [CS("conv", sp["in_channels"], sp["channels"], k=ks[0], padding=(ks[0] - 1) // 2)]
+            in_chs = out_chs = sp["channels"]
+            groups = 4
+            for ds in sp["downsample_scales"]:
+                specs.append(CS("conv", in_chs, out_chs, k=ks[1], stride=ds, padding=(ks[1] - 1) // 2, groups=groups))
+                in_chs = out_chs
+                out_chs = min(in_chs * 2, sp["max_downsample_channels"])
+                groups = min(groups * 4, sp["max_groups"])
+            out_chs = min(in_chs * 2, sp["max_downsample_channels"])
+            specs.append(CS("conv", in_chs, out_chs, k=ks[2], padding=(ks[2] - 1) // 2))
+            specs.append(CS("conv", out_chs, sp["out_channels"], k=ks[3], padding=(ks[3] - 1) // 2))
+            layers = []
+            for li, spec in enumerate(specs):
+                last = li == len(specs) - 1
+                name = f"msd.discriminators.{s}.layers.{li}" + ("" if last else ".0")
+                layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code))
+            self.chains.append(_Chain(layers, "scale", scale_index=s))
+        for pi, period in enumerate(periods):
+            ks = pp["kernel_sizes"]
+            specs = []
+            in_chs, out_chs = pp["in_channels"], pp["channels"]
+            for ds in pp["downsample_scales"]:
+                specs.append(CS("conv", in_chs, out_chs, k=ks[0], stride=ds, padding=(ks[0] - 1) // 2))
+                in_chs = out_chs
+                out_chs = min(out_chs * 4, pp["max_downsample_channels"])
+            # reference: Conv2d(out_chs, out, (ks[1]-1, 1), 1, padding=((ks[1]-1)//2, 0)), hifigan.py:382-388
+            specs.append(CS("conv", out_chs, pp["out_channels"], k=ks[1] - 1, padding=(ks[1] - 1) // 2))
+            assert out_chs == in_chs, "output conv width must equal the last feature width (shipped configs)"
+            layers = []
+            for li, spec in enumerate(specs):
+                last = li == len(specs) - 1
+                name = f"mpd.discriminators.{pi}." + ("output_conv" if last else f"convs.{li}.0")
+                layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code))
+            self.chains.append(_Chain(layers, "period", period=period))
+        self.layers = {l.name: l for ch in self.chains for l in ch.layers}
+        self._prepped = False
+
+    def bind(self, params):
+        for l in self.layers.values():
+            l.bind(params)
+        self._prepped = False
+
+    def prep_weights(self, need_bwd=True):
+        for l in self.layers.values():
+            l.prep(need_bwd)
+        self._prepped = True
+
+    def param_names(self):
+        return [n for l in self.layers.values() for n in l.param_names()]
+
+    def new_grads(self):
+        return _zero_grads_like(list(self.layers.values()))
+
+    # ---- forward -------------------------------------------------------------
+    def forward(self, x: torch.Tensor, save=True):
+        """x (B, 1, T) fp32 -> (list of 8 lists of SeqT [feature maps..., logits], tape)."""
+        _lib.require_cuda(x, "x")
+        assert self._prepped and x.dim() == 3 and x.shape[1] == 1
+        B, _, T = x.shape
+        dev = x.device
+        x = x.contiguous().float()
+        outs, tape = [], {"B": B, "T": T, "chains": []}
+        # AvgPool pyramid (hifigan.py:733-736)
+        k, st, pd = self.pool["kernel_size"], self.pool["stride"], self.pool["padding"]
+        sigs = [SeqT(x.view(B, T, 1), B, T, 1)]
+        n_scales = sum(1 for c in self.chains if c.kind == "scale")
+        for s in range(1, n_scales):
+            lp = sigs[-1].L
+            lo = (lp + 2 * pd - k) // st + 1
+            t = torch.empty((B, lo, 1), dtype=torch.float32, device=dev)
+            call("artic_avgpool1d", ptr(sigs[-1].t), ptr(t), B, lp, lo, k, st, pd, F32)
+            sigs.append(SeqT(t, B, lo, 1))
+        for ch in self.chains:
+            if ch.kind == "scale":
+                h = sigs[ch.scale_index]
+                slope = self.slope_s
+            else:
+                p = ch.period
+                Tp = T if T % p == 0 else T + (p - T % p)                 # hifigan.py:413-416
+                if Tp != T:
+                    xp = torch.empty((B, Tp), dtype=torch.float32, device=dev)
+                    call("artic_reflect_pad_right", ptr(x), ptr(xp), B, T, Tp, F32)
+                else:
+                    xp = x.view(B, T)
+                H = Tp // p
+                h = SeqT(xp, B * p, H, 1, n_inner=p, s_outer=Tp, s_inner=1, s_row=p)
+                slope = self.slope_p
+            acts = [h]
+            n = len(ch.layers)
+            for li, lay in enumerate(ch.layers):
+                lo = lay.spec.out_len(h.L)
+                last = li == n - 1
+                o = h.like(code=F32 if last else self.code, C=lay.spec.cout, L=lo)
+                if last:
+                    lay.forward(h, Y=o)
+                else:
+                    lay.forward(h, Y2=o, act=ACT_LRELU, act_slope=slope)
+                acts.append(o)
+                h = o
+            outs.append(acts[1:])
+            tape["chains"].append(acts)
+        tape["sigs"] = sigs
+        return outs, (tape if save else None)
+
+    # ---- backward ------------------------------------------------------------
+    def backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True):
+        """douts: per chain a list (same length as the chain's outputs) of SeqT gradients or
+        None; the gradient wrt the logits must be present.  Accumulates parameter gradients
+        into ``grads`` when given (None = skip every wgrad, as in the generator phase) and
+        returns d x (B, 1, T) fp32 when ``need_dx``."""
+        B, T = tape["B"], tape["T"]
+        dev = tape["sigs"][0].t.device
+        if grads is not None:
+            for l in self.layers.values():
+                l.zero_wgrad()
+        dx = torch.zeros((B, 1, T), dtype=torch.float32, device=dev) if need_dx else None
+        n_scales = len(tape["sigs"])
+        dsig = [None] * n_scales
+        for ci, ch in enumerate(self.chains):
+            acts = tape["chains"][ci]           # acts[0] = input signal, acts[l+1] = output of layer l
+            dl = douts[ci]
+            slope = self.slope_s if ch.kind == "scale" else self.slope_p
+            n = len(ch.layers)
+            dz = dl[n - 1]                      # logits gradient (fp32 SeqT)
+            assert dz is not None
+            for li in range(n - 1, -1, -1):
+                lay = ch.layers[li]
+                if grads is not None:
+                    lay.wgrad(acts[li], dz, grads)
+                if li > 0:
+                    dn = acts[li].like()
+                    lay.dgrad(dz, dX=dn, res_pre=dl[li - 1], mask=acts[li], mask_slope=slope)
+                    dz = dn
+                elif need_dx:
+                    dn = acts[0].like(code=F32) if ch.kind == "scale" else None
+                    if ch.kind == "scale":
+                        lay.dgrad(dz, dX=dn)
+                        dsig[ch.scale_index] = dn
+                    else:
+                        h = acts[0]
+                        Tp = h.s_outer
+                        dxp = torch.empty((B, Tp), dtype=torch.float32, device=dev)
+                        dn = SeqT(dxp, h.N, h.L, 1, n_inner=h.n_inner, s_outer=Tp, s_inner=1, s_row=h.s_row)
+                        lay.dgrad(dz, dX=dn)
+                        call("artic_reflect_pad_right_bwd", ptr(dxp), ptr(dx), B, T, Tp, 1, F32)
+        if need_dx:
+            k, st, pd = self.pool["kernel_size"], self.pool["stride"], self.pool["padding"]
+            for s in range(n_scales - 1, 0, -1):
+                lp = tape["sigs"][s - 1].L
+                call("artic_avgpool1d_bwd", ptr(dsig[s].t), ptr(dsig[s - 1].t), B, lp, tape["sigs"][s].L,
+                     k, st, pd, 1, F32)
+            # dx += dsig[0]  (via the reflect-pad backward with Lp == L: plain accumulate)
+            call("artic_reflect_pad_right_bwd", ptr(dsig[0].t), ptr(dx), B, T, T, 1, F32)
+        if grads is not None:
+            for l in self.layers.values():
+                l.finish_grads(grads)
+        return dx

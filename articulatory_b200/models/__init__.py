@@ -1,0 +1,5 @@
+"""Plugin registry: class-name strings in YAML are resolved with
+``getattr(articulatory_b200.models, config["generator_type"])`` exactly like the
+reference does on ``articulatory.models`` (bin/train.py:1649-1662, utils/utils.py:325-334)."""
+from .hifigan import (HiFiGANGenerator, HiFiGANMultiScaleMultiPeriodDiscriminator,  # noqa: F401
+                      set_default_precision)

@@ -1,0 +1,273 @@
+"""The fused G + D + spectral-loss train step (reference Trainer._train_step,
+articulatory/bin/train.py:241-440), scheduled explicitly over the engines:
+
+  G phase   y_ = G(x, ar); aux = [MR-STFT] + [mel]; p_ = D(cat(ar, y_)); p = D(cat(ar, y))
+            gen_loss = l_aux*aux + l_adv*(adv(p_) + l_fm*fm(p_, p)); G <- Adam
+            (D's weight gradients are NOT computed here: the reference computes and then
+             discards them, bin/train.py:373 then :424)
+  D phase   y_ = G_new(x, ar) (no grad); D(real) is REUSED from the G phase (D is not updated
+            in between, so it is the same tensor the reference recomputes at :415);
+            dis_loss = real + fake; D <- Adam
+
+Differences from the reference that do not change results: no per-step ``.item()`` host
+syncs (the nine logged scalars are accumulated on the device and read at the log
+interval), one D(real) forward instead of two, no D wgrad in the G phase.  The steady-state
+step is captured once in a CUDA graph (per rank) and replayed.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import F32, call, ptr
+from .engine import SeqT
+from .losses.spectral import MelSpectrogramLoss, MultiResolutionSTFTLoss
+from .optim import FusedAdam
+
+LOG_KEYS = ["train/spectral_convergence_loss", "train/log_stft_magnitude_loss", "train/mel_loss",
+            "train/adversarial_loss", "train/feature_matching_loss", "train/generator_loss",
+            "train/real_loss", "train/fake_loss", "train/discriminator_loss"]
+_MEL, _ADV, _FM, _REAL, _FAKE = range(5)
+
+
+class TrainStep:
+    def __init__(self, generator, discriminator, config: Dict, device, world_size=1, all_reduce=None):
+        """``config`` uses the reference YAML keys (use_stft_loss, stft_loss_params, use_mel_loss,
+        mel_loss_params, lambda_aux, lambda_adv, lambda_feat_match, *_optimizer_params,
+        *_scheduler_params, *_train_start_steps).  ``all_reduce(flat_grad)`` (optional) sums a
+        flat gradient buffer over data-parallel ranks."""
+        self.G, self.D, self.cfg, self.dev = generator, discriminator, config, torch.device(device)
+        self.world, self.all_reduce = world_size, all_reduce
+        if config.get("generator_optimizer_type", "Adam") != "Adam" or \
+                config.get("discriminator_optimizer_type", "Adam") != "Adam":
+            raise NotImplementedError("the fused train step implements Adam (yaml default)")
+        for k in ("generator", "discriminator"):
+            if config.get(f"{k}_scheduler_type", "MultiStepLR") != "MultiStepLR":
+                raise NotImplementedError("the fused train step implements MultiStepLR (yaml default)")
+            if config.get(f"{k}_grad_norm", -1) > 0:
+                raise NotImplementedError("gradient clipping is off in the shipped yamls")
+        if not config.get("use_feat_match_loss", True):
+            raise NotImplementedError("use_feat_match_loss=false is not on the hot path")
+        self.use_stft = bool(config.get("use_stft_loss", False))
+        self.use_mel = bool(config.get("use_mel_loss", False))
+        self.stft = MultiResolutionSTFTLoss(**config.get("stft_loss_params", {})) if self.use_stft else None
+        self.mel = MelSpectrogramLoss(**config["mel_loss_params"]).to(self.dev) if self.use_mel else None
+        self.l_aux = float(config.get("lambda_aux", 1.0))
+        self.l_adv = float(config.get("lambda_adv", 1.0))
+        self.l_fm = float(config.get("lambda_feat_match", 1.0))
+        fm = config.get("feat_match_loss_params", {})
+        if fm.get("average_by_layers", True) or fm.get("average_by_discriminators", True) or \
+                fm.get("include_final_outputs", False) or \
+                config.get("generator_adv_loss_params", {}).get("average_by_discriminators", True) or \
+                config.get("discriminator_adv_loss_params", {}).get("average_by_discriminators", True):
+            raise NotImplementedError("only the yaml's un-averaged adversarial / feature-match sums are fused")
+        self.g_start = config.get("generator_train_start_steps", 0)
+        self.d_start = config.get("discriminator_train_start_steps", 0)
+
+        def opt(module, key):
+            op = dict(config.get(f"{key}_optimizer_params", {}))
+            sp = config.get(f"{key}_scheduler_params", {})
+            return FusedAdam(module, lr=op.get("lr", 1e-3), betas=tuple(op.get("betas", (0.9, 0.999))),
+                             eps=op.get("eps", 1e-8), weight_decay=op.get("weight_decay", 0.0),
+                             gamma=sp.get("gamma", 0.1), milestones=tuple(sp.get("milestones", ())))
+
+        self.optG, self.optD = opt(generator, "generator"), opt(discriminator, "discriminator")
+        R = len(self.stft.resolutions) if self.use_stft else 0
+        self.R = R
+        self.slots = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        self.stft_sums = torch.zeros((max(R, 1), 3), dtype=torch.float32, device=self.dev)
+        self.stft_numel = torch.zeros(max(R, 1), dtype=torch.float32, device=self.dev)
+        self.vals = torch.zeros(9, dtype=torch.float32, device=self.dev)
+        self.running = torch.zeros(9, dtype=torch.float32, device=self.dev)
+        self.steps = 0
+        self._graph = None
+        self._static = None
+        self.ar_len = generator._cfg["ar_input"] if generator.use_ar else 0
+
+    # ------------------------------------------------------------------------------
+    def _disc_input(self, ar, y):
+        B, _, T = y.shape
+        La = self.ar_len
+        out = torch.empty((B, 1, La + T), dtype=torch.float32, device=self.dev)
+        call("artic_concat_time", ptr(ar) if La else None, ptr(y), ptr(out), B, La, T, La + T, F32)
+        return out
+
+    def _adv_seed(self, outs, target, slot, scale_w, want_grad):
+        """sum over discriminators of mean((logits - target)^2) -> slots[slot]; returns per-chain
+        logits gradients (scaled by scale_w) when want_grad."""
+        grads = []
+        for lst in outs:
+            lg = lst[-1]
+            n = lg.numel()
+            call("artic_sqerr_sum", ptr(lg.t), n, float(target), 1.0 / n, ptr(self.slots[slot:]), lg.code)
+            if want_grad:
+                g = lg.like()
+                call("artic_sqerr_bwd", ptr(lg.t), n, float(target), scale_w / n, ptr(g.t), 0, lg.code)
+                grads.append(g)
+        return grads
+
+    def _phase_g(self, x, y, ar, train_d_active):
+        G, D = self.G, self.D
+        engG = G._ensure_ready()
+        B, _, T = y.shape
+        inv_w = 1.0 / self.world
+        y_, tapeG = engG.forward(x, ar, save=True)
+        y2d, t2d = y_.reshape(B, T), y.reshape(B, T)
+        dy = torch.zeros((B, 1, T), dtype=torch.float32, device=self.dev)
+        self.slots.zero_()
+        self.stft_sums.zero_()
+        if self.use_stft:                                                     # bin/train.py:289-297
+            for r, res in enumerate(self.stft.resolutions):
+                res.forward(y2d, t2d, self.stft_sums[r])
+                self.stft_numel[r] = float(res.numel(B, T))
+            for r, res in enumerate(self.stft.resolutions):
+                res.backward(y2d, t2d, self.stft_sums[r], self.l_aux * inv_w / self.R, self.l_aux * inv_w / self.R, dy)
+        if self.use_mel:                                                      # :313-316
+            n = self.mel.numel(B, T)
+            self.mel.accumulate(y2d, t2d, 1.0 / n, self.slots[_MEL:])
+            self.mel.backward_into(y2d, t2d, self.l_aux * inv_w / n, dy)
+        real = None
+        if train_d_active:                                                    # :350-364
+            engD = D._ensure_ready()
+            outs_f, tape_f = engD.forward(self._disc_input(ar, y_), save=True)
+            outs_r, tape_r = engD.forward(self._disc_input(ar, y), save=True)
+            real = (outs_r, tape_r)
+            douts = []
+            lg_grads = self._adv_seed(outs_f, 1.0, _ADV, self.l_adv * inv_w, True)
+            for ci, (lf, lr_) in enumerate(zip(outs_f, outs_r)):
+                dl = []
+                for a, b in zip(lf[:-1], lr_[:-1]):
+                    n = a.numel()
+                    call("artic_l1_sum", ptr(a.t), ptr(b.t), n, 1.0 / n, ptr(self.slots[_FM:]), a.code)
+                    g = a.like()
+                    call("artic_l1_bwd", ptr(a.t), ptr(b.t), n, self.l_adv * self.l_fm * inv_w / n, ptr(g.t), 0, a.code)
+                    dl.append(g)
+                dl.append(lg_grads[ci])
+                douts.append(dl)
+            d_in = engD.backward(tape_f, douts, grads=None, need_dx=True)    # dgrad only
+            La = self.ar_len
+            call("artic_add_rows", ptr(d_in) + 4 * La, La + T, ptr(dy), T, B, T)
+        self.optG.zero_grad()
+        engG.backward(tapeG, dy, self.optG.grad_views)
+        return real
+
+    def _phase_d(self, x, y, ar, real):
+        G, D = self.G, self.D
+        engG = G._ensure_ready()          # re-materialises the updated generator weights
+        engD = D._ensure_ready()
+        inv_w = 1.0 / self.world
+        y_, _ = engG.forward(x, ar, save=False)                               # bin/train.py:390-400
+        outs_f, tape_f = engD.forward(self._disc_input(ar, y_), save=True)
+        if real is None:
+            real = engD.forward(self._disc_input(ar, y), save=True)
+        outs_r, tape_r = real
+        g_r = self._adv_seed(outs_r, 1.0, _REAL, inv_w, True)                 # :415-418
+        g_f = self._adv_seed(outs_f, 0.0, _FAKE, inv_w, True)
+        self.optD.zero_grad()
+        for outs, tape, gl in ((outs_r, tape_r, g_r), (outs_f, tape_f, g_f)):
+            douts = [[None] * (len(lst) - 1) + [gl[ci]] for ci, lst in enumerate(outs)]
+            engD.backward(tape, douts, grads=self.optD.grad_views, need_dx=False)
+
+    # The step is cut into three segments so that the (optional) data-parallel gradient
+    # all-reduce can run between CUDA-graph replays:  seg1 = G phase up to dL/dθ_G,
+    # seg2 = Adam(G) + D phase up to dL/dθ_D,  seg3 = Adam(D) + log assembly.
+    def _seg1(self, x, y, ar, steps):
+        self._real = None
+        if steps > self.g_start:
+            self._real = self._phase_g(x, y, ar, steps > self.d_start)
+        else:
+            self.slots.zero_()
+            self.stft_sums.zero_()
+
+    def _seg2(self, x, y, ar, steps):
+        if steps > self.g_start:
+            self.optG.step()
+        if steps > self.d_start:
+            self._phase_d(x, y, ar, self._real)
+        self._real = None
+
+    def _seg3(self, steps):
+        if steps > self.d_start:
+            self.optD.step()
+        call("artic_train_log", ptr(self.slots), ptr(self.stft_sums), ptr(self.stft_numel),
+             self.R if steps > self.g_start else 0, self.l_aux, self.l_adv, self.l_fm, ptr(self.vals),
+             ptr(self.running))
+
+    def _step_impl(self, x, y, ar, steps):
+        """One reference train step at global step ``steps`` (gates as bin/train.py:268,350,388)."""
+        self._seg1(x, y, ar, steps)
+        if self.all_reduce is not None and steps > self.g_start:
+            self.all_reduce(self.optG.grad)
+        self._seg2(x, y, ar, steps)
+        if self.all_reduce is not None and steps > self.d_start:
+            self.all_reduce(self.optD.grad)
+        self._seg3(steps)
+
+    # ------------------------------------------------------------------------------
+    def step(self, x, y, ar, use_graph=True):
+        """One train step.  x (B, C, T'), y (B, 1, T), ar (B, 1, ar_len) fp32; CUDA tensors, or
+        (pinned) host tensors which are copied host->device inside the step."""
+        steady = self.steps > max(self.g_start, self.d_start)
+        if use_graph and steady:
+            if self._graph is None or self._static[0].shape != x.shape:
+                self._capture(x, y, ar)
+            for dst, src in zip(self._static, (x, y, ar)):
+                dst.copy_(src, non_blocking=True)
+            g1, g2, g3 = self._graph
+            g1.replay()
+            if self.all_reduce is not None:
+                self.all_reduce(self.optG.grad)
+            g2.replay()
+            if self.all_reduce is not None:
+                self.all_reduce(self.optD.grad)
+            g3.replay()
+        else:
+            x, y, ar = (t.to(self.dev, non_blocking=True).float().contiguous() for t in (x, y, ar))
+            self._step_impl(x, y, ar, self.steps)
+        self.steps += 1
+
+    def _capture(self, x, y, ar):
+        sx, sy, sa = (t.to(self.dev).clone().float().contiguous() for t in (x, y, ar))
+        torch.cuda.synchronize()
+        snap = self._snapshot()
+        # one eager steady-state step on a side stream (lazy allocations, smem attributes, ...)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        ar_fn, self.all_reduce = self.all_reduce, None
+        with torch.cuda.stream(s):
+            self._step_impl(sx, sy, sa, self.steps)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(snap)
+        pool = torch.cuda.graph_pool_handle()
+        graphs = []
+        for seg in (lambda: self._seg1(sx, sy, sa, self.steps), lambda: self._seg2(sx, sy, sa, self.steps),
+                    lambda: self._seg3(self.steps)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                seg()
+            graphs.append(g)
+        self.all_reduce = ar_fn
+        self._restore(snap)
+        self._graph, self._static = tuple(graphs), (sx, sy, sa)
+
+    def _snapshot(self):
+        return [t.clone() for t in (self.optG.flat, self.optG.m, self.optG.v, self.optG.hyper,
+                                    self.optD.flat, self.optD.m, self.optD.v, self.optD.hyper, self.running)]
+
+    def _restore(self, snap):
+        for dst, src in zip((self.optG.flat, self.optG.m, self.optG.v, self.optG.hyper,
+                             self.optD.flat, self.optD.m, self.optD.v, self.optD.hyper, self.running), snap):
+            dst.copy_(src)
+        self.G.mark_weights_dirty()
+        self.D.mark_weights_dirty()
+
+    def read_logs(self, reset=True):
+        """Device -> host read of the running sums (the reference's total_train_loss)."""
+        vals = self.running.cpu().tolist()
+        if reset:
+            self.running.zero_()
+        return dict(zip(LOG_KEYS, vals))
+
+    def last_values(self):
+        return dict(zip(LOG_KEYS, self.vals.cpu().tolist()))

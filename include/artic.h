@@ -80,8 +80,9 @@ typedef struct {
   int32_t off[ARTIC_MAX_TAPS];
   int32_t widx[ARTIC_MAX_TAPS];
   float alpha, mask_slope, act_slope;
-  int32_t act;   /* ARTIC_ACT_* applied to Y2 */
-  int32_t dtype; /* ARTIC_F32 / ARTIC_BF16 */
+  int32_t act;       /* ARTIC_ACT_* applied to Y2 */
+  int32_t dtype;     /* storage type of X and W */
+  int32_t out_dtype; /* storage type of Y, Y2, res_pre, mask, res, res2 */
 } artic_tapconv_t;
 
 int artic_tapconv(const artic_tapconv_t* p, void* stream);
@@ -89,8 +90,7 @@ int artic_tapconv(const artic_tapconv_t* p, void* stream);
 /*
  * Weight gradient of the same contraction (cuDNN wgrad):
  *   dW[widx[t]][g][ci][co] += sum_n sum_q X[n, q*si+off[t], g*Cig+ci] * dY[n, q*so+yoff[t], g*Cog+co]
- * dW is fp32 [K][G][Cig][Cog] and is ACCUMULATED into (zero it first).  `ws` is an
- * optional fp32 workspace (unused by the generic kernel; reserved).
+ * dW is fp32 [K][G][Cig][Cog] and is ACCUMULATED into (zero it first).
  */
 typedef struct {
   const void* X; const void* dY; float* dW;
@@ -101,7 +101,8 @@ typedef struct {
   int32_t off[ARTIC_MAX_TAPS];
   int32_t yoff[ARTIC_MAX_TAPS];
   int32_t widx[ARTIC_MAX_TAPS];
-  int32_t dtype;
+  int32_t dtype;   /* storage type of X */
+  int32_t y_dtype; /* storage type of dY */
 } artic_tapwgrad_t;
 
 int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream);
@@ -116,8 +117,8 @@ int artic_colsum(const void* dY, const artic_seq_t* y, int32_t N, int32_t C, int
  * plus the relayout the kernels want).  Source: a torch weight viewed as
  * [rows][row_len] fp32 with logical dims (K taps, G groups, A in-channels, B out-channels)
  * at element strides (sk, sg, sa, sb).  Output: [K][G][A][B] in `dtype`.
- * g == NULL means a plain (un-normalised) weight.  `scale` (rows floats, may be NULL
- * iff g == NULL) receives g/||v|| for the backward.
+ * g == NULL means a plain (un-normalised) weight.  `scale` (2*rows floats, may be NULL
+ * iff g == NULL) receives g/||v|| in [0,rows) and ||v|| in [rows,2*rows) for the backward.
  */
 int artic_weight_prep(const float* v, const float* g, float* scale, int32_t rows, int64_t row_len,
                       int32_t K, int32_t G, int32_t A, int32_t B,
@@ -146,9 +147,9 @@ int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int3
                         int32_t T, int32_t dtype, void* stream);
 
 /* MRF average + activation (models/hifigan.py:226-230 and the LeakyReLU of the next
- * layer): out_act = lrelu((a+b+c)/3, slope); n elements. */
+ * layer): out_act = lrelu((a+b+c)/3, slope); n elements; inputs in `dtype`, output in `out_dtype`. */
 int artic_mean3_act(const void* a, const void* b, const void* c, void* out_act, int64_t n,
-                    float slope, int32_t dtype, void* stream);
+                    float slope, int32_t dtype, int32_t out_dtype, void* stream);
 
 /* dpre = dy * (1 - y*y)  (torch.nn.Tanh backward, models/hifigan.py:158); fp32 dy/y in, `dtype` out. */
 int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64_t n, int32_t dtype, void* stream);
@@ -160,6 +161,11 @@ int artic_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype,
  * `dtype` out with row pitch `out_pitch` elements (>= La+Ly, rest untouched). */
 int artic_concat_time(const float* ar, const float* y, void* out, int32_t B, int32_t La, int32_t Ly,
                       int64_t out_pitch, int32_t dtype, void* stream);
+
+/* dst[r, 0:cols] += src[r, 0:cols] for r < rows (fp32; row pitches in elements): adds the
+ * waveform part of the discriminator-input gradient (bin/train.py:345-346 slices) to dL/dy_. */
+int artic_add_rows(const float* src, int64_t src_pitch, float* dst, int64_t dst_pitch, int32_t rows,
+                   int32_t cols, void* stream);
 
 /* AvgPool1d(kernel, stride, padding, count_include_pad=True) on (B, L) signals
  * (models/hifigan.py:719-721,733-736). Lout = (L + 2*pad - k)/stride + 1. */
@@ -191,6 +197,18 @@ int artic_l1_sum(const void* a, const void* b, int64_t n, float scale, float* sl
 /* da_i (=|+=) scale * sign(a_i - b_i) */
 int artic_l1_bwd(const void* a, const void* b, int64_t n, float scale, void* da, int32_t accumulate,
                  int32_t dtype, void* stream);
+
+/*
+ * Device-side assembly of the scalars the reference logs every step (bin/train.py:289-369,
+ * 415-421) from the raw accumulators, without a host sync:
+ *   slots = [mel, adv, fm, real, fake] (already normalised means / sums of means),
+ *   stft_sums = R x [sum (Y-X)^2, sum Y^2, sum |ln Y - ln X|], stft_numel = R element counts.
+ * vals[0..8] = [sc, mag, mel, adv, fm, gen, real, fake, dis] of this step, running[i] += vals[i].
+ * gen = lambda_aux*(sc+mag+mel) + lambda_adv*(adv + lambda_fm*fm);  R may be 0.
+ */
+int artic_train_log(const float* slots, const float* stft_sums, const float* stft_numel, int32_t R,
+                    float lambda_aux, float lambda_adv, float lambda_fm, float* vals, float* running,
+                    void* stream);
 
 /* ---- spectral losses ------------------------------------------------------------------ */
 

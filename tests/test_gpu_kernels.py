@@ -1,0 +1,259 @@
+"""GPU parity of the individual C-ABI kernels against the CPU oracle (torch fp32/fp64 ops
+that the reference itself calls).  Runs on the B200 box: `pytest -m gpu`."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from articulatory_b200 import _lib
+    from articulatory_b200.convspec import ConvSpec
+    from articulatory_b200.engine import ConvLayer, SeqT
+    from articulatory_b200._lib import call, ptr, F32, BF16
+
+DEV = "cuda:0"
+
+CONV_CASES = [
+    # (spec kwargs, N, Lin)
+    (dict(kind="conv", cin=32, cout=32, k=3, dilation=1, padding=1), 3, 500),
+    (dict(kind="conv", cin=64, cout=64, k=7, dilation=3, padding=9), 2, 333),
+    (dict(kind="conv", cin=32, cout=32, k=11, dilation=5, padding=25), 2, 1000),
+    (dict(kind="conv", cin=141, cout=96, k=7, padding=3), 2, 100),
+    (dict(kind="conv", cin=1, cout=32, k=15, padding=7), 2, 2129),
+    (dict(kind="conv", cin=32, cout=32, k=41, stride=4, padding=20, groups=4), 2, 517),
+    (dict(kind="conv", cin=32, cout=64, k=41, stride=4, padding=20, groups=16), 2, 133),
+    (dict(kind="conv", cin=64, cout=1, k=3, padding=1), 3, 34),
+    (dict(kind="conv", cin=4, cout=16, k=5, stride=3, padding=2), 6, 406),
+    (dict(kind="conv", cin=64, cout=64, k=5, stride=1, padding=2), 14, 10),
+    (dict(kind="conv", cin=64, cout=1, k=2, stride=1, padding=1), 4, 16),
+    (dict(kind="convT", cin=64, cout=32, k=10, stride=5, padding=3, output_padding=1), 2, 100),
+    (dict(kind="convT", cin=32, cout=16, k=8, stride=4, padding=2), 2, 125),
+    (dict(kind="convT", cin=16, cout=8, k=4, stride=2, padding=1), 3, 77),
+    (dict(kind="linear", cin=512, cout=256), 5, 1),
+]
+
+
+def _torch_fwd(spec, x, w, b):
+    if spec.kind == "conv":
+        return F.conv1d(x, w, b, stride=spec.stride, padding=spec.padding, dilation=spec.dilation, groups=spec.groups)
+    if spec.kind == "convT":
+        return F.conv_transpose1d(x, w, b, stride=spec.stride, padding=spec.padding, output_padding=spec.output_padding)
+    return F.linear(x.transpose(1, 2), w, b).transpose(1, 2)
+
+
+@pytest.mark.parametrize("case", range(len(CONV_CASES)))
+@pytest.mark.parametrize("wn", [False, True])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_conv_layer_fwd_dgrad_wgrad(case, wn, prec):
+    kw, N, lin = CONV_CASES[case]
+    spec = ConvSpec(**kw)
+    if spec.kind == "linear" and wn:
+        pytest.skip("no weight norm on Linear")
+    code = F32 if prec == "fp32" else BF16
+    tol = 2e-5 if prec == "fp32" else 2e-2
+    torch.manual_seed(case)
+    v = torch.randn(spec.weight_shape(), dtype=torch.float64) / math.sqrt(spec.cig * spec.k)
+    g = (torch.rand(spec.weight_shape()[0], *([1] * (v.dim() - 1)), dtype=torch.float64) + 0.5) if wn else None
+    b = torch.randn(spec.cout, dtype=torch.float64) * 0.1
+    x = torch.randn(N, spec.cin, lin, dtype=torch.float64)
+    v.requires_grad_(True)
+    x.requires_grad_(True)
+    if wn:
+        g.requires_grad_(True)
+        w = g * v / v.pow(2).sum(dim=tuple(range(1, v.dim())), keepdim=True).sqrt()
+    else:
+        w = v
+    b.requires_grad_(True)
+    y = _torch_fwd(spec, x, w, b)
+    dy = torch.randn_like(y)
+    ins = [x, v, b] + ([g] if wn else [])
+    gr = torch.autograd.grad(y, ins, dy)
+
+    lay = ConvLayer(spec, "l", code, code)
+    params = {"l.bias": b.detach().float().to(DEV)}
+    if wn:
+        params["l.weight_v"] = v.detach().float().to(DEV).contiguous()
+        params["l.weight_g"] = g.detach().float().to(DEV).contiguous()
+    else:
+        params["l.weight"] = v.detach().float().to(DEV).contiguous()
+    lay.bind(params)
+    lay.prep()
+    td = _lib.TORCH_DTYPE[code]
+    X = SeqT(x.detach().permute(0, 2, 1).contiguous().to(DEV, td), N, lin, spec.cin)
+    lout = spec.out_len(lin)
+    Y = SeqT.empty(N, lout, spec.cout, code, DEV)
+    Y2 = SeqT.empty(N, lout, spec.cout, code, DEV)
+    lay.forward(X, Y=Y, Y2=Y2, act=_lib.ACT_LRELU, act_slope=0.1)
+    torch.cuda.synchronize()
+    y_mine = Y.t.float().cpu().permute(0, 2, 1)
+    assert rel_err(y_mine, y) < tol
+    assert rel_err(Y2.t.float().cpu().permute(0, 2, 1), F.leaky_relu(y, 0.1)) < tol
+
+    dY = SeqT(dy.permute(0, 2, 1).contiguous().to(DEV, td), N, lout, spec.cout)
+    dX = SeqT.empty(N, lin, spec.cin, code, DEV)
+    lay.dgrad(dY, dX=dX)
+    torch.cuda.synchronize()
+    assert rel_err(dX.t.float().cpu().permute(0, 2, 1), gr[0]) < tol
+
+    grads = {k: torch.zeros_like(t) for k, t in params.items()}
+    lay.zero_wgrad()
+    lay.wgrad(X, dY, grads)
+    lay.finish_grads(grads)
+    torch.cuda.synchronize()
+    assert rel_err(grads["l.weight_v" if wn else "l.weight"].cpu(), gr[1]) < tol
+    assert rel_err(grads["l.bias"].cpu(), gr[2]) < tol
+    if wn:
+        assert rel_err(grads["l.weight_g"].cpu(), gr[3]) < tol
+
+
+def test_epilogue_mask_res_alpha():
+    """v = alpha*acc + bias; v += res_pre; v *= lrelu'(mask); v += res + res2."""
+    spec = ConvSpec("conv", 16, 24, k=3, padding=1)
+    torch.manual_seed(0)
+    N, L = 2, 50
+    w = torch.randn(spec.weight_shape()) * 0.2
+    x = torch.randn(N, 16, L)
+    res_pre, mask, res, res2 = (torch.randn(N, 24, L) for _ in range(4))
+    acc = F.conv1d(x, w, None, padding=1)
+    want = (0.25 * acc + res_pre) * torch.where(mask > 0, 1.0, 0.1) + res + res2
+    lay = ConvLayer(spec, "l", F32, F32)
+    lay.bind({"l.weight": w.to(DEV)})
+    lay.prep()
+    cl = lambda t: SeqT(t.permute(0, 2, 1).contiguous().to(DEV), N, L, t.shape[1])
+    Y = SeqT.empty(N, L, 24, F32, DEV)
+    lay.forward(cl(x), Y=Y, res_pre=cl(res_pre), mask=cl(mask), mask_slope=0.1, res=cl(res), res2=cl(res2), alpha=0.25)
+    torch.cuda.synchronize()
+    assert rel_err(Y.t.cpu().permute(0, 2, 1), want) < 1e-5
+
+
+def test_period_layout_matches_conv2d():
+    """n_inner = p addressing == the reference's view(b, c, t//p, p) + Conv2d((k,1),(s,1))."""
+    p, B, H, Ci, Co = 3, 2, 40, 8, 12
+    torch.manual_seed(1)
+    x = torch.randn(B, Ci, H, p)
+    w = torch.randn(Co, Ci, 5, 1) * 0.2
+    b = torch.randn(Co) * 0.1
+    want = F.conv2d(x, w, b, stride=(3, 1), padding=(2, 0))
+    spec = ConvSpec("conv", Ci, Co, k=5, stride=3, padding=2)
+    lay = ConvLayer(spec, "l", F32, F32)
+    lay.bind({"l.weight": w.to(DEV), "l.bias": b.to(DEV)})
+    lay.prep()
+    X = SeqT.period(B, H, p, Ci, F32, DEV)
+    X.t.copy_(x.permute(0, 2, 3, 1))
+    Ho = spec.out_len(H)
+    Y = SeqT.period(B, Ho, p, Co, F32, DEV)
+    lay.forward(X, Y=Y)
+    torch.cuda.synchronize()
+    assert rel_err(Y.t.cpu().permute(0, 3, 1, 2), want) < 1e-5
+
+
+def test_small_ops():
+    torch.manual_seed(0)
+    B, L = 3, 8512
+    x = torch.randn(B, 1, L)
+    xd = x.to(DEV)
+    # avg pool fwd/bwd
+    want = F.avg_pool1d(x, 4, 2, 2)
+    lo = want.shape[2]
+    y = torch.empty(B, lo, device=DEV)
+    call("artic_avgpool1d", ptr(xd), ptr(y), B, L, lo, 4, 2, 2, F32)
+    assert torch.allclose(y.cpu(), want[:, 0], atol=1e-6)
+    xr = x.clone().requires_grad_(True)
+    dy = torch.randn(B, 1, lo)
+    F.avg_pool1d(xr, 4, 2, 2).backward(dy)
+    dx = torch.zeros(B, L, device=DEV)
+    call("artic_avgpool1d_bwd", ptr(dy.to(DEV)), ptr(dx), B, L, lo, 4, 2, 2, 0, F32)
+    assert torch.allclose(dx.cpu(), xr.grad[:, 0], atol=1e-6)
+    # reflect pad fwd (bit exact) / bwd
+    for pd in (2, 3, 7):
+        want = F.pad(x, (0, pd), "reflect")
+        yp = torch.empty(B, L + pd, device=DEV)
+        call("artic_reflect_pad_right", ptr(xd), ptr(yp), B, L, L + pd, F32)
+        assert torch.equal(yp.cpu(), want[:, 0])
+        xr = x.clone().requires_grad_(True)
+        dyp = torch.randn(B, 1, L + pd)
+        F.pad(xr, (0, pd), "reflect").backward(dyp)
+        dx = torch.zeros(B, L, device=DEV)
+        call("artic_reflect_pad_right_bwd", ptr(dyp.to(DEV)), ptr(dx), B, L, L + pd, 0, F32)
+        assert torch.allclose(dx.cpu(), xr.grad[:, 0], atol=1e-6)
+    # losses
+    a, b = torch.randn(5, 7, 11), torch.randn(5, 7, 11)
+    slot = torch.zeros(2, device=DEV)
+    call("artic_sqerr_sum", ptr(a.to(DEV)), a.numel(), 1.0, 1.0 / a.numel(), ptr(slot), F32)
+    call("artic_l1_sum", ptr(a.to(DEV)), ptr(b.to(DEV)), a.numel(), 1.0 / a.numel(), ptr(slot[1:]), F32)
+    assert abs(slot[0].item() - F.mse_loss(a, torch.ones_like(a)).item()) < 1e-5
+    assert abs(slot[1].item() - F.l1_loss(a, b).item()) < 1e-5
+    # adam vs torch.optim.Adam + MultiStepLR
+    from articulatory_b200.optim import FusedAdam
+    lin = torch.nn.Linear(13, 7).to(DEV)
+    ref = torch.nn.Linear(13, 7)
+    ref.load_state_dict({k: v.cpu() for k, v in lin.state_dict().items()})
+    opt = FusedAdam(lin, lr=1e-3, betas=(0.5, 0.9), gamma=0.5, milestones=(3, 6))
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3, betas=(0.5, 0.9))
+    rs = torch.optim.lr_scheduler.MultiStepLR(ropt, gamma=0.5, milestones=[3, 6])
+    for it in range(8):
+        gw, gb = torch.randn(7, 13), torch.randn(7)
+        opt.grad_views["weight"].copy_(gw)
+        opt.grad_views["bias"].copy_(gb)
+        ref.weight.grad, ref.bias.grad = gw.clone(), gb.clone()
+        opt.step()
+        ropt.step()
+        rs.step()
+        assert torch.allclose(lin.weight.detach().cpu(), ref.weight.detach(), atol=1e-6), it
+    assert opt.step_count() == 8
+
+
+@pytest.mark.parametrize("res", [(1024, 120, 600), (2048, 240, 1200), (512, 50, 240), (1024, 80, 1024)])
+def test_stft_loss_single_resolution(res):
+    from oracle import torch_oracle as O
+    n_fft, hop, win = res
+    torch.manual_seed(0)
+    b = O.synthetic_batch(3, frames=25 if n_fft < 2048 else 100)
+    T = b["y"].shape[2]
+    y = b["y"][:, 0]
+    x = (0.3 * torch.randn(3, T) + 0.5 * y).contiguous()
+    window = torch.hann_window(win)
+    sums = torch.zeros(3, device=DEV)
+    call("artic_stft_loss_fwd", ptr(x.to(DEV)), ptr(y.to(DEV)), 3, T, n_fft, hop, win, ptr(window.to(DEV)), 1e-7, ptr(sums))
+    x64 = x.double().requires_grad_(True)
+    xm = O.stft_magnitude(x64, n_fft, hop, win, window.double())
+    ym = O.stft_magnitude(y.double(), n_fft, hop, win, window.double())
+    want = torch.stack([(ym - xm).pow(2).sum(), ym.pow(2).sum(), (ym.log() - xm.log()).abs().sum()])
+    got = sums.cpu().double()
+    assert torch.allclose(got, want.detach(), rtol=2e-4), (got, want)
+    sc = torch.norm(ym - xm, p="fro") / torch.norm(ym, p="fro")
+    mag = F.l1_loss(torch.log(ym), torch.log(xm))
+    (0.7 * sc + 1.3 * mag).backward()
+    dx = torch.zeros(3, T, device=DEV)
+    call("artic_stft_loss_bwd", ptr(x.to(DEV)), ptr(y.to(DEV)), 3, T, n_fft, hop, win, ptr(window.to(DEV)), 1e-7,
+         ptr(sums), 0.7, 1.3, ptr(dx))
+    # fp32 torch itself is ~5e-3 away from fp64 on this gradient (see tests/test_oracle_golden.py)
+    x32 = x.clone().requires_grad_(True)
+    xm32 = O.stft_magnitude(x32, n_fft, hop, win, window)
+    ym32 = O.stft_magnitude(y, n_fft, hop, win, window)
+    (0.7 * torch.norm(ym32 - xm32, p="fro") / torch.norm(ym32, p="fro") + 1.3 * F.l1_loss(ym32.log(), xm32.log())).backward()
+    ref_noise = rel_err(x32.grad, x64.grad)
+    assert rel_err(dx.cpu(), x64.grad) < max(1e-3, 3 * ref_noise), (rel_err(dx.cpu(), x64.grad), ref_noise)
+
+
+def test_mr_stft_and_mel_modules(golden):
+    from articulatory_b200.losses import MelSpectrogramLoss, MultiResolutionSTFTLoss
+    from oracle import torch_oracle as O
+    y_ = golden["g_out"].to(DEV).requires_grad_(True)
+    y = golden["batch"]["y"].to(DEV)
+    sc, mag = MultiResolutionSTFTLoss()(y_, y)
+    (sc + mag).backward()
+    assert abs(sc.item() - float(golden["stft"]["sc"])) < 1e-4 * float(golden["stft"]["sc"])
+    assert abs(mag.item() - float(golden["stft"]["mag"])) < 1e-4 * float(golden["stft"]["mag"])
+    assert rel_err(y_.grad.cpu(), golden["stft"]["grad"]) < 2e-2      # fp32-noise-limited, see above
+    y_ = golden["g_out"].to(DEV).requires_grad_(True)
+    ml = MelSpectrogramLoss(**O.E2W_MEL_LOSS_PARAMS).to(DEV)(y_, y)
+    ml.backward()
+    assert abs(ml.item() - float(golden["mel"]["loss"])) < 1e-4 * float(golden["mel"]["loss"])
+    assert rel_err(y_.grad.cpu(), golden["mel"]["grad"]) < 1e-3

@@ -1,0 +1,160 @@
+"""GPU parity of the plugin modules and the fused train step against the oracle and the
+reference-generated golden fixtures (tests/golden/small_e2w.pt).  `pytest -m gpu`."""
+import copy
+import warnings
+
+import pytest
+import torch
+
+from tests.helpers import check_digest, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _build(golden, precision="fp32"):
+    from articulatory_b200 import models as M
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = M.HiFiGANGenerator(**golden["generator_params"], precision=precision)
+        D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**golden["discriminator_params"], precision=precision)
+    G.load_state_dict(golden["gsd"])
+    D.load_state_dict(golden["dsd"])
+    return G.to(DEV), D.to(DEV)
+
+
+def test_generator_forward_golden(golden):
+    G, _ = _build(golden)
+    b = golden["batch"]
+    with torch.no_grad():
+        y = G(b["x"].to(DEV), ar=b["ar"].to(DEV))
+    assert y.shape == (2, 1, 2000)
+    assert rel_err(y.cpu(), golden["g_out"]) < 1e-4          # north_star: 1e-3 relative fp32
+
+
+def test_generator_forward_bf16_reported(golden):
+    """bf16 speed mode: error is REPORTED against the fp32 reference, gate is loose."""
+    G, _ = _build(golden, "bf16")
+    b = golden["batch"]
+    with torch.no_grad():
+        y = G(b["x"].to(DEV), ar=b["ar"].to(DEV))
+    e = rel_err(y.cpu(), golden["g_out"])
+    print(f"bf16 generator waveform rel err = {e:.3e}")
+    assert e < 5e-2
+
+
+def test_discriminator_forward_golden(golden):
+    _, D = _build(golden)
+    x = torch.cat([golden["batch"]["ar"], golden["g_out"]], dim=2).to(DEV)
+    with torch.no_grad():
+        outs = D(x)
+    assert len(outs) == 8
+    for i, (mine, ref) in enumerate(zip(outs, golden["d_out"])):
+        assert len(mine) == len(ref)
+        for j, (a, r) in enumerate(zip(mine[:-1], ref[:-1])):
+            check_digest(a.float().cpu(), r, 1e-4, f"D{i} fmap{j}")
+        assert mine[-1].shape == ref[-1].shape
+        assert rel_err(mine[-1].cpu(), ref[-1]) < 1e-4
+
+
+def test_autograd_gradients_golden(golden):
+    """Same losses as tests/golden/make_golden.py 'g_grads' / 'd_grads', through the plugin
+    modules + loss modules + torch autograd (the drop-in path)."""
+    from articulatory_b200 import losses as L
+    from oracle import torch_oracle as O
+    G, D = _build(golden)
+    b = {k: v.to(DEV) for k, v in golden["batch"].items()}
+    mel = L.MelSpectrogramLoss(**O.E2W_MEL_LOSS_PARAMS).to(DEV)
+    y_ = G(b["x"], ar=b["ar"])
+    for p in D.parameters():
+        p.requires_grad_(False)
+    p_ = D(torch.cat([b["ar"], y_], dim=2))
+    with torch.no_grad():
+        p = D(torch.cat([b["ar"], b["y"]], dim=2))
+    loss = 45.0 * mel(y_, b["y"]) + L.GeneratorAdversarialLoss(False)(p_) + 2.0 * L.FeatureMatchLoss(False, False, False)(p_, p)
+    assert abs(loss.item() - float(golden["gen_loss"])) < 1e-4 * float(golden["gen_loss"])
+    loss.backward()
+    for k, v in G.named_parameters():
+        check_digest(v.grad.cpu(), golden["g_grads"][k], 2e-3, f"G grad {k}")
+    for p_i in D.parameters():
+        p_i.requires_grad_(True)
+    pr = D(torch.cat([b["ar"], b["y"]], dim=2))
+    pf = D(torch.cat([b["ar"], y_.detach()], dim=2))
+    r, f = L.DiscriminatorAdversarialLoss(False)(pf, pr)
+    (r + f).backward()
+    for k, v in D.named_parameters():
+        check_digest(v.grad.cpu(), golden["d_grads"][k], 2e-3, f"D grad {k}")
+
+
+def _train_config(golden, stft=True):
+    from oracle import torch_oracle as O
+    return dict(use_stft_loss=stft, use_mel_loss=True, mel_loss_params=O.E2W_MEL_LOSS_PARAMS,
+                stft_loss_params=O.DEFAULT_STFT_LOSS_PARAMS, lambda_aux=45.0, lambda_adv=1.0, lambda_feat_match=2.0,
+                use_feat_match_loss=True,
+                feat_match_loss_params=dict(average_by_discriminators=False, average_by_layers=False, include_final_outputs=False),
+                generator_adv_loss_params=dict(average_by_discriminators=False),
+                discriminator_adv_loss_params=dict(average_by_discriminators=False),
+                generator_optimizer_params=dict(lr=1e-4, betas=[0.5, 0.9], weight_decay=0.0),
+                discriminator_optimizer_params=dict(lr=1e-4, betas=[0.5, 0.9], weight_decay=0.0),
+                generator_scheduler_params=dict(gamma=0.5, milestones=[80000, 160000, 240000, 320000]),
+                discriminator_scheduler_params=dict(gamma=0.5, milestones=[80000, 160000, 240000, 320000]),
+                generator_train_start_steps=1, discriminator_train_start_steps=0,
+                generator_grad_norm=-1, discriminator_grad_norm=-1)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_steps_golden(golden, use_graph):
+    """Four fused train steps == four reference Trainer._train_step calls (logged scalars)."""
+    from articulatory_b200.trainer import LOG_KEYS, TrainStep
+    G, D = _build(golden)
+    ts = TrainStep(G, D, _train_config(golden), DEV)
+    b = {k: v.to(DEV) for k, v in golden["batch"].items()}
+    for step, ref_logs in enumerate(golden["train_logs"]):
+        ts.step(b["x"], b["y"], b["ar"], use_graph=use_graph)
+        vals = ts.last_values()
+        for k, v in ref_logs.items():
+            assert abs(vals[k] - v) <= 1e-3 * abs(v), (step, k, vals[k], v)
+    # weight deltas: loose, see tests/test_oracle_golden.py::test_train_steps
+    gsd = {k: v.detach().cpu() for k, v in G.state_dict().items()}
+    for k, d in golden["gsd_delta"].items():
+        check_digest(gsd[k] - golden["gsd"][k], d, 0.9, f"G delta {k}", sum_rtol=0.3)
+    dsd = {k: v.detach().cpu() for k, v in D.state_dict().items()}
+    for k, d in golden["dsd_delta"].items():
+        check_digest(dsd[k] - golden["dsd"][k], d, 0.9, f"D delta {k}", sum_rtol=0.3)
+    # a 5th step replays the captured graph (when enabled) and must stay finite
+    ts.step(b["x"], b["y"], b["ar"], use_graph=use_graph)
+    assert all(map(lambda v: v == v and abs(v) < 1e6, ts.last_values().values()))
+
+
+def test_full_width_generator_and_discriminator_vs_oracle():
+    """e2w_hifigan.yaml widths, B=2: waveform and all 54 discriminator outputs vs the oracle."""
+    from articulatory_b200 import models as M
+    from oracle import torch_oracle as O
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = M.HiFiGANGenerator(**O.E2W_GENERATOR_PARAMS)
+        D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**O.E2W_DISCRIMINATOR_PARAMS)
+    gsd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    dsd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    G, D = G.to(DEV), D.to(DEV)
+    b = O.synthetic_batch(2)
+    with torch.no_grad():
+        y = G(b["x"].to(DEV), ar=b["ar"].to(DEV))
+        y_ref = O.generator_forward(gsd, O.E2W_GENERATOR_PARAMS, b["x"], b["ar"])
+        assert y.shape == (2, 1, 8000)
+        assert rel_err(y.cpu(), y_ref) < 1e-3
+        din = torch.cat([b["ar"], b["y"]], 2)
+        outs = D(din.to(DEV))
+        ref = O.discriminator_forward(dsd, O.E2W_DISCRIMINATOR_PARAMS, din)
+        for lo, lr_ in zip(outs, ref):
+            for a, r in zip(lo, lr_):
+                assert a.shape == r.shape
+                assert rel_err(a.float().cpu(), r) < 1e-3
+
+
+def test_cpu_input_fails_loudly(golden):
+    from articulatory_b200._lib import ArticError
+    G, _ = _build(golden)
+    with pytest.raises(ArticError):
+        G(golden["batch"]["x"], ar=golden["batch"]["ar"])
