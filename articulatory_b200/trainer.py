@@ -119,7 +119,6 @@ class TrainStep:
         if self.use_stft:                                                     # bin/train.py:289-297
             for r, res in enumerate(self.stft.resolutions):
                 res.forward(y2d, t2d, self.stft_sums[r])
-                self.stft_numel[r] = float(res.numel(B, T))
             for r, res in enumerate(self.stft.resolutions):
                 res.backward(y2d, t2d, self.stft_sums[r], self.l_aux * inv_w / self.R, self.l_aux * inv_w / self.R, dy)
         if self.use_mel:                                                      # :313-316
@@ -208,6 +207,7 @@ class TrainStep:
         """One train step.  x (B, C, T'), y (B, 1, T), ar (B, 1, ar_len) fp32; CUDA tensors, or
         (pinned) host tensors which are copied host->device inside the step."""
         steady = self.steps > max(self.g_start, self.d_start)
+        self._ensure_numel(y.shape[0], y.shape[2])
         if use_graph and steady:
             if self._graph is None or self._static[0].shape != x.shape:
                 self._capture(x, y, ar)
@@ -225,6 +225,13 @@ class TrainStep:
             x, y, ar = (t.to(self.dev, non_blocking=True).float().contiguous() for t in (x, y, ar))
             self._step_impl(x, y, ar, self.steps)
         self.steps += 1
+
+    def _ensure_numel(self, B, T):
+        """Element counts of the STFT magnitude tensors (log-magnitude mean), kept on the device."""
+        if self.use_stft and getattr(self, "_numel_for", None) != (B, T):
+            host = torch.tensor([float(r.numel(B, T)) for r in self.stft.resolutions], dtype=torch.float32)
+            self.stft_numel.copy_(host.to(self.dev))
+            self._numel_for = (B, T)
 
     def _capture(self, x, y, ar):
         sx, sy, sa = (t.to(self.dev).clone().float().contiguous() for t in (x, y, ar))

@@ -168,7 +168,8 @@ def test_small_ops():
     dy = torch.randn(B, 1, lo)
     F.avg_pool1d(xr, 4, 2, 2).backward(dy)
     dx = torch.zeros(B, L, device=DEV)
-    call("artic_avgpool1d_bwd", ptr(dy.to(DEV)), ptr(dx), B, L, lo, 4, 2, 2, 0, F32)
+    dyd = dy.to(DEV)
+    call("artic_avgpool1d_bwd", ptr(dyd), ptr(dx), B, L, lo, 4, 2, 2, 0, F32)
     assert torch.allclose(dx.cpu(), xr.grad[:, 0], atol=1e-6)
     # reflect pad fwd (bit exact) / bwd
     for pd in (2, 3, 7):
@@ -180,13 +181,15 @@ def test_small_ops():
         dyp = torch.randn(B, 1, L + pd)
         F.pad(xr, (0, pd), "reflect").backward(dyp)
         dx = torch.zeros(B, L, device=DEV)
-        call("artic_reflect_pad_right_bwd", ptr(dyp.to(DEV)), ptr(dx), B, L, L + pd, 0, F32)
+        dypd = dyp.to(DEV)
+        call("artic_reflect_pad_right_bwd", ptr(dypd), ptr(dx), B, L, L + pd, 0, F32)
         assert torch.allclose(dx.cpu(), xr.grad[:, 0], atol=1e-6)
     # losses
     a, b = torch.randn(5, 7, 11), torch.randn(5, 7, 11)
     slot = torch.zeros(2, device=DEV)
-    call("artic_sqerr_sum", ptr(a.to(DEV)), a.numel(), 1.0, 1.0 / a.numel(), ptr(slot), F32)
-    call("artic_l1_sum", ptr(a.to(DEV)), ptr(b.to(DEV)), a.numel(), 1.0 / a.numel(), ptr(slot[1:]), F32)
+    ad, bd = a.to(DEV), b.to(DEV)   # keep references: ptr() of a temporary would dangle
+    call("artic_sqerr_sum", ptr(ad), a.numel(), 1.0, 1.0 / a.numel(), ptr(slot), F32)
+    call("artic_l1_sum", ptr(ad), ptr(bd), a.numel(), 1.0 / a.numel(), ptr(slot[1:]), F32)
     assert abs(slot[0].item() - F.mse_loss(a, torch.ones_like(a)).item()) < 1e-5
     assert abs(slot[1].item() - F.l1_loss(a, b).item()) < 1e-5
     # adam vs torch.optim.Adam + MultiStepLR
@@ -220,7 +223,8 @@ def test_stft_loss_single_resolution(res):
     x = (0.3 * torch.randn(3, T) + 0.5 * y).contiguous()
     window = torch.hann_window(win)
     sums = torch.zeros(3, device=DEV)
-    call("artic_stft_loss_fwd", ptr(x.to(DEV)), ptr(y.to(DEV)), 3, T, n_fft, hop, win, ptr(window.to(DEV)), 1e-7, ptr(sums))
+    xd, yd, wd = x.to(DEV), y.contiguous().to(DEV), window.to(DEV)
+    call("artic_stft_loss_fwd", ptr(xd), ptr(yd), 3, T, n_fft, hop, win, ptr(wd), 1e-7, ptr(sums))
     x64 = x.double().requires_grad_(True)
     xm = O.stft_magnitude(x64, n_fft, hop, win, window.double())
     ym = O.stft_magnitude(y.double(), n_fft, hop, win, window.double())
@@ -231,8 +235,7 @@ def test_stft_loss_single_resolution(res):
     mag = F.l1_loss(torch.log(ym), torch.log(xm))
     (0.7 * sc + 1.3 * mag).backward()
     dx = torch.zeros(3, T, device=DEV)
-    call("artic_stft_loss_bwd", ptr(x.to(DEV)), ptr(y.to(DEV)), 3, T, n_fft, hop, win, ptr(window.to(DEV)), 1e-7,
-         ptr(sums), 0.7, 1.3, ptr(dx))
+    call("artic_stft_loss_bwd", ptr(xd), ptr(yd), 3, T, n_fft, hop, win, ptr(wd), 1e-7, ptr(sums), 0.7, 1.3, ptr(dx))
     # fp32 torch itself is ~5e-3 away from fp64 on this gradient (see tests/test_oracle_golden.py)
     x32 = x.clone().requires_grad_(True)
     xm32 = O.stft_magnitude(x32, n_fft, hop, win, window)
