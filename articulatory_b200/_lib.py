@@ -33,7 +33,8 @@ class TapConv(C.Structure):
                 ("ntaps", C.c_int32),
                 ("off", C.c_int32 * MAX_TAPS), ("widx", C.c_int32 * MAX_TAPS),
                 ("alpha", C.c_float), ("mask_slope", C.c_float), ("act_slope", C.c_float),
-                ("act", C.c_int32), ("dtype", C.c_int32), ("out_dtype", C.c_int32)]
+                ("act", C.c_int32), ("dtype", C.c_int32), ("out_dtype", C.c_int32),
+                ("Wt", C.c_void_p), ("Wt_taps", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class TapWgrad(C.Structure):
@@ -59,6 +60,7 @@ SIGNATURES = {
     "artic_version": (C.c_int, []),
     "artic_arch": (C.c_char_p, []),
     "artic_last_error": (C.c_char_p, []),
+    "artic_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
     "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),
@@ -111,6 +113,13 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # tuning / debugging knobs of the tensor-core path: ARTIC_TC=0 forces the CUDA-core kernel,
+    # ARTIC_DEBUG="k=v,k=v" sets raw artic_debug_set keys
+    if os.environ.get("ARTIC_TC", "1") == "0":
+        lib.artic_debug_set(1, 1)
+    for kv in filter(None, os.environ.get("ARTIC_DEBUG", "").split(",")):
+        k, v = kv.split("=")
+        lib.artic_debug_set(int(k), int(v))
     _lib = lib
     return lib
 

@@ -1,7 +1,577 @@
-// tcgen05 implicit-GEMM path for the dense bf16 contractions (placeholder until the kernel lands).
+// tcgen05 implicit-GEMM path of artic_tapconv for the dense bf16 contractions with unit
+// input stride (every generator conv / transposed-conv phase, every data-gradient phase,
+// the stride-1 discriminator convs).  sm_100a only.
+//
+//   D[m, co] (TMEM, fp32)  +=  A_t[m, ci] (smem, bf16, K-major)  x  B_t[co, ci] (smem, bf16, K-major)
+//
+// * M = 128-row sub-tiles of output positions, N = BN output channels, K = (tap, ci-chunk).
+// * The activation tile is staged ONCE per ci-chunk with its halo (rows q+min_off ..
+//   q+max_off) by TMA; every tap re-uses it through a row-shifted shared-memory matrix
+//   descriptor (im2col-free).  Out-of-range rows are zero-filled by TMA, which IS the
+//   convolution's zero padding (the row index is its own tensor-map dimension, so a tile
+//   never bleeds into the neighbouring sequence).
+// * Short sequences (discriminator tails, L <= 53) are packed: several zero-padded sequences
+//   are laid end to end in the staged tile, so a 128-row MMA still does useful work.
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+//   warps 2..5 = epilogue (TMEM -> registers -> fused bias / residual / LeakyReLU-mask /
+//   activation -> global).  Persistent over tiles; the accumulator is double-buffered in TMEM
+//   when it fits, so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
 #include "common.cuh"
 
-int artic_tapconv_tc_try(const artic_tapconv_t* p, cudaStream_t st) {
-  (void)p; (void)st;
-  return 0;  // not eligible -> generic kernel
+namespace artic {
+namespace tc {
+
+constexpr int NTHREADS = 192;
+constexpr int MAX_WS = 8;  // weight stages
+constexpr int MAX_AS = 3;  // activation stages
+
+struct Plan {
+  int32_t kch;        // channels per K chunk (64 / 32 / 16)
+  int32_t row_bytes;  // kch * 2 = swizzle span
+  int32_t n_kc;       // ci chunks
+  int32_t bn;         // output channels per tile
+  int32_t n_nt;       // channel tiles per group
+  int32_t mt;         // 128-row sub-tiles per CTA tile
+  int32_t packed;     // 1: several short sequences per tile
+  int32_t seg_per_tile, seg_pitch, seg_rows;  // packed: sequences per tile, smem row pitch, box rows
+  int32_t tiles_per_seq;                      // plain: tiles per sequence
+  int32_t boxr, nbox;                         // plain: box rows and boxes per activation stage
+  int32_t n_mt;       // row tiles in total
+  int32_t total_tiles;
+  int32_t a_stage_bytes, w_stage_bytes, n_as, n_ws;
+  int32_t acc_stages, tmem_cols;
+  int32_t min_off;
+  int32_t shift[ARTIC_MAX_TAPS];  // off[t] - min_off
+  int32_t layout_type;            // UMMA smem descriptor swizzle code
+  int32_t base_offset_mode;       // debug: 0 = address-based swizzle phase, 1 = explicit base offset
+};
+
+// ------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset,
+// [61,64) swizzle code.  Rows are `row_bytes` apart, 8-row groups SBO = 8*row_bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes, uint32_t layout_type, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;                                // LBO: unused for swizzled K-major layouts
+  d |= (uint64_t)(((8u * row_bytes) >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7) << 49;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+struct PipeState {
+  int stage, phase, n;
+  __device__ __forceinline__ PipeState(int n_) : stage(0), phase(0), n(n_) {}
+  __device__ __forceinline__ void next() {
+    if (++stage == n) { stage = 0; phase ^= 1; }
+  }
+};
+
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]);
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_constant__ Plan pl,
+                  const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[MAX_AS], a_empty[MAX_AS], w_full[MAX_WS], w_empty[MAX_WS];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 1024-byte aligned operand staging area
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem0;
+  const uint32_t w_base = smem0 + (uint32_t)pl.n_as * pl.a_stage_bytes;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_w);
+    for (int i = 0; i < pl.n_as; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < pl.n_ws; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)pl.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int ntaps = p.ntaps;
+  const int acc_cols = pl.mt * pl.bn;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      PipeState as(pl.n_as), ws(pl.n_ws);
+      const uint32_t w_bytes = (uint32_t)pl.bn * pl.row_bytes;
+      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+        const int nt = tile % pl.n_nt;
+        const int r = tile / pl.n_nt;
+        const int mtile = r % pl.n_mt;
+        const int g = r / pl.n_mt;
+        for (int kc = 0; kc < pl.n_kc; ++kc) {
+          const int c0 = g * p.Cig + kc * pl.kch;
+          mbar_wait(&a_empty[as.stage], as.phase ^ 1);
+          const uint32_t a_dst = a_base + (uint32_t)as.stage * pl.a_stage_bytes;
+          if (!pl.packed) {
+            const int n = mtile / pl.tiles_per_seq;
+            const int qt = mtile % pl.tiles_per_seq;
+            const int row0 = p.q0 + qt * pl.mt * 128 + pl.min_off;
+            mbar_expect_tx(&a_full[as.stage], (uint32_t)pl.nbox * pl.boxr * pl.row_bytes);
+            for (int b = 0; b < pl.nbox; ++b)
+              tma_load_4d(a_dst + (uint32_t)b * pl.boxr * pl.row_bytes, &map_x, &a_full[as.stage], c0, n % p.x.n_inner,
+                          row0 + b * pl.boxr, n / p.x.n_inner);
+          } else {
+            const int n0 = mtile * pl.seg_per_tile;
+            const int nseg = min(pl.seg_per_tile, p.N - n0);
+            mbar_expect_tx(&a_full[as.stage], (uint32_t)nseg * pl.seg_rows * pl.row_bytes);
+            for (int j = 0; j < nseg; ++j) {
+              const int n = n0 + j;
+              tma_load_4d(a_dst + (uint32_t)j * pl.seg_pitch * pl.row_bytes, &map_x, &a_full[as.stage], c0,
+                          n % p.x.n_inner, p.q0 + pl.min_off, n / p.x.n_inner);
+            }
+          }
+          as.next();
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(&w_empty[ws.stage], ws.phase ^ 1);
+            mbar_expect_tx(&w_full[ws.stage], w_bytes);
+            tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes, &map_w, &w_full[ws.stage], kc * pl.kch,
+                        (p.widx[t] * p.G + g) * p.Cog + nt * pl.bn);
+            ws.next();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      PipeState as(pl.n_as), ws(pl.n_ws), acc(pl.acc_stages);
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.bn >> 3) << 17) | ((128u >> 4) << 24);
+      const int ksteps = pl.kch / 16;
+      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc.stage], acc.phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)acc.stage * acc_cols;
+        for (int kc = 0; kc < pl.n_kc; ++kc) {
+          mbar_wait(&a_full[as.stage], as.phase);
+          const uint32_t a_st = a_base + (uint32_t)as.stage * pl.a_stage_bytes;
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(&w_full[ws.stage], ws.phase);
+            tc_fence_after();
+            const uint32_t w_st = w_base + (uint32_t)ws.stage * pl.w_stage_bytes;
+            for (int m = 0; m < pl.mt; ++m) {
+              const uint32_t a_row = (uint32_t)(m * 128 + pl.shift[t]);
+              const uint32_t a_addr = a_st + a_row * pl.row_bytes;
+              const uint32_t boff = pl.base_offset_mode ? ((a_addr >> 7) & 7u) : 0u;
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t ad = make_desc(a_addr + k * 32, pl.row_bytes, pl.layout_type, boff);
+                const uint64_t bd = make_desc(w_st + k * 32, pl.row_bytes, pl.layout_type, 0);
+                umma_bf16(d_base + (uint32_t)m * pl.bn, ad, bd, idesc, (kc | t | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&w_empty[ws.stage]);
+            ws.next();
+          }
+          umma_commit(&a_empty[as.stage]);
+          as.next();
+        }
+        umma_commit(&acc_full[acc.stage]);
+        acc.next();
+      }
+    }
+  } else {
+    // =============================== epilogue ===================================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    PipeState acc(pl.acc_stages);
+    using TO = __nv_bfloat16;
+    const TO* __restrict__ res_pre = reinterpret_cast<const TO*>(p.res_pre);
+    const TO* __restrict__ mask = reinterpret_cast<const TO*>(p.mask);
+    const TO* __restrict__ res = reinterpret_cast<const TO*>(p.res);
+    const TO* __restrict__ res2 = reinterpret_cast<const TO*>(p.res2);
+    TO* __restrict__ Y = reinterpret_cast<TO*>(p.Y);
+    TO* __restrict__ Y2 = reinterpret_cast<TO*>(p.Y2);
+    for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+      const int nt = tile % pl.n_nt;
+      const int r = tile / pl.n_nt;
+      const int mtile = r % pl.n_mt;
+      const int g = r / pl.n_mt;
+      mbar_wait(&acc_full[acc.stage], acc.phase);
+      tc_fence_after();
+      const int cbase = g * p.Cog + nt * pl.bn;
+      for (int m = 0; m < pl.mt; ++m) {
+        const int mrow = m * 128 + ew * 32 + lane;
+        int n, q;
+        bool valid;
+        if (!pl.packed) {
+          n = mtile / pl.tiles_per_seq;
+          q = (mtile % pl.tiles_per_seq) * pl.mt * 128 + mrow;
+          valid = q < p.nq;
+        } else {
+          const int j = mrow / pl.seg_pitch;
+          q = mrow - j * pl.seg_pitch;
+          n = mtile * pl.seg_per_tile + j;
+          valid = j < pl.seg_per_tile && q < p.nq && n < p.N;
+        }
+        int64_t o = 0;
+        if (valid) {
+          const int row = (p.q0 + q) * p.so + p.ro;
+          valid = row >= 0 && row < p.y.len;
+          o = seq_base(p.y, n) + (int64_t)row * p.y.s_row + cbase;
+        }
+        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc.stage * acc_cols + (uint32_t)m * pl.bn;
+        for (int c0 = 0; c0 < pl.bn; c0 += 32) {
+          uint32_t acc_r[32];
+          tmem_ld32(t_row + c0, acc_r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int v8 = 0; v8 < 4; ++v8) {
+              float v[8], tmp[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[i] = p.alpha * __uint_as_float(acc_r[v8 * 8 + i]);
+                if (p.bias != nullptr) v[i] += __ldg(p.bias + cbase + c0 + v8 * 8 + i);
+              }
+              const int64_t oo = o + c0 + v8 * 8;
+              if (res_pre) {
+                unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(res_pre + oo)), tmp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+              }
+              if (mask) {
+                unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(mask + oo)), tmp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= (tmp[i] > 0.f ? 1.f : p.mask_slope);
+              }
+              if (res) {
+                unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(res + oo)), tmp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+              }
+              if (res2) {
+                unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(res2 + oo)), tmp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+              }
+              if (Y) *reinterpret_cast<uint4*>(Y + oo) = pack8(v);
+              if (Y2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (p.act == ARTIC_ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : p.act_slope * v[i];
+                  else if (p.act == ARTIC_ACT_TANH) v[i] = tanhf(v[i]);
+                }
+                *reinterpret_cast<uint4*>(Y2 + oo) = pack8(v);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc.stage]);
+      acc.next();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static int g_smem_optin = 0;
+
+// Largest dynamic shared-memory size the kernel may be launched with (opt-in limit minus the
+// kernel's static shared memory); sets the function attribute once.
+static int max_smem() {
+  if (g_smem_optin == 0) {
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (optin <= 0) optin = 227 * 1024;
+    cudaFuncAttributes fa;
+    int stat = 2048;
+    if (cudaFuncGetAttributes(&fa, tapconv_tc_kernel) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+    int dyn = optin - stat;
+    if (cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) {
+      cudaGetLastError();
+      dyn = 48 * 1024;
+    }
+    g_smem_optin = dyn;
+  }
+  return g_smem_optin;
+}
+
+static CUtensorMapSwizzle swizzle_of(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+}  // namespace tc
+}  // namespace artic
+
+using namespace artic;
+
+extern "C" int artic_debug_set(int key, int value) {
+  if (key < 0 || key >= 8) return ARTIC_EINVAL;
+  tc::g_debug[key] = value;
+  return ARTIC_OK;
+}
+
+// returns 1 if the launch was taken, 0 if the shape is not eligible, <0 on error.
+int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
+  const artic_tapconv_t& p = *pp;
+  if (tc::g_debug[1]) return 0;                       // debug: force the generic kernel
+  if (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16) return 0;
+  if (p.si != 1) return 0;
+  if (p.Cig % 16 != 0 || p.Cog % 32 != 0) return 0;
+  if ((p.x.s_row % 8) || (p.x.s_outer % 8) || (p.x.n_inner > 1 && (p.x.s_inner % 8))) return 0;
+  if ((p.y.s_row % 8) || (p.y.s_outer % 8) || (p.y.n_inner > 1 && (p.y.s_inner % 8))) return 0;
+  const void* ptrs[] = {p.X, p.Wt, p.res_pre, p.mask, p.res, p.res2, p.Y, p.Y2};
+  for (const void* q : ptrs)
+    if (q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15)) return 0;
+  tc::EncodeTiledFn enc = tc::encode_fn();
+  if (enc == nullptr) return 0;
+
+  tc::Plan pl;
+  memset(&pl, 0, sizeof(pl));
+  int min_off = p.off[0], max_off = p.off[0];
+  for (int t = 1; t < p.ntaps; ++t) { min_off = min(min_off, p.off[t]); max_off = max(max_off, p.off[t]); }
+  const int span = max_off - min_off;
+  if (span > 160 || min_off < -(1 << 20)) return 0;   // also rejects the "no tap on this phase" marker
+  pl.min_off = min_off;
+  for (int t = 0; t < p.ntaps; ++t) pl.shift[t] = p.off[t] - min_off;
+  pl.kch = (p.Cig % 64 == 0) ? 64 : (p.Cig % 32 == 0) ? 32 : 16;
+  pl.row_bytes = pl.kch * 2;
+  pl.n_kc = p.Cig / pl.kch;
+  pl.layout_type = pl.row_bytes == 128 ? 2 : pl.row_bytes == 64 ? 4 : 6;
+  pl.bn = (p.Cog % 256 == 0) ? 256 : (p.Cog % 128 == 0) ? 128 : (p.Cog % 64 == 0) ? 64 : 32;
+  if (tc::g_debug[2] > 0 && p.Cog % tc::g_debug[2] == 0) pl.bn = tc::g_debug[2];
+  pl.n_nt = p.Cog / pl.bn;
+  int mt = 512 / (2 * pl.bn);
+  if (mt < 1) mt = 1;
+  if (mt > 4) mt = 4;
+  if (tc::g_debug[3] > 0) mt = tc::g_debug[3];
+  const int rows_align = 128 / pl.row_bytes;          // TMA shared-memory destinations are 128-byte aligned
+  const int lpad = p.nq + span;
+  pl.packed = (p.N >= 2 && lpad <= 256 && 2 * lpad <= mt * 128) ? 1 : 0;
+  if (tc::g_debug[4] == 1) pl.packed = 0;
+  int a_rows;
+  if (pl.packed) {
+    pl.seg_rows = lpad;
+    pl.seg_pitch = ((lpad + rows_align - 1) / rows_align) * rows_align;
+    pl.seg_per_tile = (mt * 128) / pl.seg_pitch;
+    if (pl.seg_per_tile > p.N) {
+      pl.seg_per_tile = p.N;
+      mt = (pl.seg_per_tile * pl.seg_pitch + 127) / 128;
+    }
+    pl.n_mt = (p.N + pl.seg_per_tile - 1) / pl.seg_per_tile;
+    a_rows = mt * 128 + span + 8;
+  } else {
+    while (mt > 1 && (mt - 1) * 128 >= p.nq) --mt;
+    pl.tiles_per_seq = (p.nq + mt * 128 - 1) / (mt * 128);
+    pl.n_mt = p.N * pl.tiles_per_seq;
+    pl.boxr = 64;
+    pl.nbox = (mt * 128 + span + pl.boxr - 1) / pl.boxr;
+    a_rows = pl.nbox * pl.boxr;
+  }
+  pl.mt = mt;
+  pl.acc_stages = (2 * mt * pl.bn <= 512) ? 2 : 1;
+  int cols = pl.acc_stages * mt * pl.bn;
+  pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  if (cols > 512) return 0;
+  pl.a_stage_bytes = ((a_rows * pl.row_bytes + 1023) / 1024) * 1024;
+  pl.w_stage_bytes = ((pl.bn * pl.row_bytes + 1023) / 1024) * 1024;
+  const int budget = tc::max_smem() - 1024 /*alignment slack*/;
+  pl.n_as = 2;
+  int rem = budget - pl.n_as * pl.a_stage_bytes;
+  if (rem < 2 * pl.w_stage_bytes) {
+    pl.n_as = 1;
+    rem = budget - pl.a_stage_bytes;
+    if (rem < 2 * pl.w_stage_bytes) return 0;
+  }
+  pl.n_ws = rem / pl.w_stage_bytes;
+  if (pl.n_ws > tc::MAX_WS) pl.n_ws = tc::MAX_WS;
+  if (pl.n_ws > 2 && pl.n_as < tc::MAX_AS && pl.n_kc > 2 && rem - pl.n_ws * pl.w_stage_bytes >= pl.a_stage_bytes) pl.n_as += 1;
+  const int64_t total = (int64_t)pl.n_mt * pl.n_nt * p.G;
+  if (total > (1 << 30)) return 0;
+  pl.total_tiles = (int)total;
+  pl.base_offset_mode = tc::g_debug[0];
+
+  // ---- tensor maps
+  CUtensorMap map_x, map_w;
+  {
+    const int ni = p.x.n_inner;
+    cuuint64_t dims[4] = {(cuuint64_t)p.G * p.Cig, (cuuint64_t)ni, (cuuint64_t)p.x.len, (cuuint64_t)((p.N + ni - 1) / ni)};
+    cuuint64_t strides[3] = {(cuuint64_t)(ni > 1 ? p.x.s_inner : p.x.s_row) * 2, (cuuint64_t)p.x.s_row * 2,
+                             (cuuint64_t)p.x.s_outer * 2};
+    if (dims[3] == 1 && strides[2] == 0) strides[2] = strides[1] * dims[2];
+    cuuint32_t box[4] = {(cuuint32_t)pl.kch, 1, (cuuint32_t)(pl.packed ? pl.seg_rows : pl.boxr), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult rc = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.X), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swizzle_of(pl.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { set_error("artic_tapconv: cuTensorMapEncodeTiled(X) failed (%d)", (int)rc); return ARTIC_ECUDA; }
+  }
+  {
+    int wmax = 0;
+    for (int t = 0; t < p.ntaps; ++t) wmax = max(wmax, p.widx[t]);
+    const int rows_total = p.Wt_taps > 0 ? p.Wt_taps : (wmax + 1);
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cig, (cuuint64_t)rows_total * p.G * p.Cog};
+    cuuint64_t strides[1] = {(cuuint64_t)p.Cig * 2};
+    cuuint32_t box[2] = {(cuuint32_t)pl.kch, (cuuint32_t)pl.bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult rc = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.Wt), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swizzle_of(pl.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { set_error("artic_tapconv: cuTensorMapEncodeTiled(W) failed (%d)", (int)rc); return ARTIC_ECUDA; }
+  }
+  const int smem_bytes = pl.n_as * pl.a_stage_bytes + pl.n_ws * pl.w_stage_bytes + 1024;
+  int grid = num_sms();
+  if (grid > pl.total_tiles) grid = pl.total_tiles;
+  tc::tapconv_tc_kernel<<<grid, tc::NTHREADS, smem_bytes, st>>>(p, pl, map_x, map_w);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    set_error("artic_tapconv(tc): launch failed: %s (grid %d, smem %d of %d, bn %d mt %d as %d ws %d packed %d)",
+              cudaGetErrorString(le), grid, smem_bytes, tc::max_smem(), pl.bn, pl.mt, pl.n_as, pl.n_ws, pl.packed);
+    return ARTIC_ECUDA;
+  }
+  return 1;
 }

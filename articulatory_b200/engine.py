@@ -73,8 +73,9 @@ def _fill_taps(dst_off, dst_idx, off, widx):
 def tapconv(launches, X: SeqT, W, G, Cig, Cog, Y: Optional[SeqT] = None, Y2: Optional[SeqT] = None,
             bias=None, res_pre: Optional[SeqT] = None, mask: Optional[SeqT] = None,
             res: Optional[SeqT] = None, res2: Optional[SeqT] = None, alpha=1.0, mask_slope=1.0,
-            act=ACT_NONE, act_slope=0.0):
-    """Issue the artic_tapconv launches of one layer direction."""
+            act=ACT_NONE, act_slope=0.0, Wt=None):
+    """Issue the artic_tapconv launches of one layer direction.  ``Wt`` is the same weight
+    in the transposed prepared layout [K][G][Cog][Cig] (enables the tcgen05 kernel)."""
     yref = Y if Y is not None else Y2
     assert yref is not None and X.C == G * Cig and yref.C == G * Cog and X.N == yref.N
     for o in (Y, Y2, res_pre, mask, res, res2):
@@ -96,6 +97,8 @@ def tapconv(launches, X: SeqT, W, G, Cig, Cog, Y: Optional[SeqT] = None, Y2: Opt
         p.ntaps = _fill_taps(p.off, p.widx, L.off, L.widx)
         p.alpha, p.mask_slope, p.act_slope, p.act = alpha, mask_slope, act_slope, act
         p.dtype, p.out_dtype = X.code, yref.code
+        if Wt is not None and Wt.dtype == W.dtype:
+            p.Wt, p.Wt_taps = ptr(Wt), Wt.shape[0]
         call("artic_tapconv", p)
 
 
@@ -160,12 +163,12 @@ class ConvLayer:
     # ---- compute -------------------------------------------------------------
     def forward(self, X: SeqT, Y=None, Y2=None, **epi):
         s = self.spec
-        tapconv(s.fwd_launches(X.L), X, self.Wf, s.groups, s.cig, s.cog, Y=Y, Y2=Y2, bias=self.b, **epi)
+        tapconv(s.fwd_launches(X.L), X, self.Wf, s.groups, s.cig, s.cog, Y=Y, Y2=Y2, bias=self.b, Wt=self.Wb, **epi)
 
     def dgrad(self, dY: SeqT, dX: Optional[SeqT] = None, dX2: Optional[SeqT] = None, **epi):
         s = self.spec
         lin = (dX if dX is not None else dX2).L
-        tapconv(s.dgrad_launches(lin), dY, self.Wb, s.groups, s.cog, s.cig, Y=dX, Y2=dX2, **epi)
+        tapconv(s.dgrad_launches(lin), dY, self.Wb, s.groups, s.cog, s.cig, Y=dX, Y2=dX2, Wt=self.Wf, **epi)
 
     def zero_wgrad(self):
         if self.dWf is None:

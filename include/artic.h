@@ -44,6 +44,8 @@ extern "C" {
 int artic_version(void);          /* 100 * major + minor */
 const char* artic_arch(void);     /* "sm_100a" */
 const char* artic_last_error(void);
+/* Debug / tuning knobs of the tensor-core path (key 0..7); not part of the reference surface. */
+int artic_debug_set(int key, int value);
 
 /* Addressing of one channels-last sequence batch (see header comment). */
 typedef struct {
@@ -65,8 +67,11 @@ typedef struct {
  *     v += res_pre[n,row,c];  v *= (mask[n,row,c] > 0 ? 1 : mask_slope);  v += res[..] + res2[..]
  *     Y[n,row,c] = v;   Y2[n,row,c] = act(v)        (any of bias/res_pre/mask/res/res2/Y/Y2 may be NULL)
  *
- * W is a PREPARED weight [K][G][Cig][Cog] (artic_weight_prep).  res_pre/mask/res/res2/Y2
- * use Y's addressing.  Conv forward: si=stride, so=1, off[t]=t*dil-pad.  Conv dgrad /
+ * W is a PREPARED weight [K][G][Cig][Cog] (artic_weight_prep).  Wt (optional) is the SAME
+ * weight in the transposed prepared layout [Wt_taps][G][Cog][Cig]; when it is given and the
+ * shape is eligible (bf16 in/out, si == 1, Cig % 16 == 0, Cog % 32 == 0) the contraction
+ * runs on the tcgen05 tensor-core kernel, otherwise on the CUDA-core kernel (same results
+ * up to fp32 summation order).  res_pre/mask/res/res2/Y2 use Y's addressing.  Conv forward: si=stride, so=1, off[t]=t*dil-pad.  Conv dgrad /
  * ConvTranspose forward: one call per output phase r with so=stride, si=1.
  */
 typedef struct {
@@ -83,6 +88,9 @@ typedef struct {
   int32_t act;       /* ARTIC_ACT_* applied to Y2 */
   int32_t dtype;     /* storage type of X and W */
   int32_t out_dtype; /* storage type of Y, Y2, res_pre, mask, res, res2 */
+  const void* Wt;    /* optional transposed prepared weight [Wt_taps][G][Cog][Cig] (same dtype as W) */
+  int32_t Wt_taps;   /* number of taps K stored in Wt */
+  int32_t reserved_;
 } artic_tapconv_t;
 
 int artic_tapconv(const artic_tapconv_t* p, void* stream);
