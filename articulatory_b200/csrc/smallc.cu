@@ -1,0 +1,186 @@
+// Channel-1 ends of the networks, where the tap-gather contraction degenerates and the GEMM
+// tilings waste the machine (these launches are HBM / latency bound):
+//
+//   * Cog == 1  (logit convs 1024->1, the generator's output conv 32->1 + tanh, and the
+//     data gradient of every first layer): one warp per output row, lanes across the
+//     (tap, channel) reduction with 128-bit loads, warp-shuffle reduction, fused epilogue.
+//   * Cig == 1 weight gradient (first layers on the raw fp32 signal, k = 15 / 5):
+//     dW[t][co] = sum_{n,q} x[n, q*si + off_t] * dY[n, q, co]; threads own output channels
+//     (coalesced dY rows), the taps live in registers, one atomicAdd per (tap, co) per CTA.
+#include "common.cuh"
+
+namespace artic {
+
+// ------------------------------------------------------------------------------------
+// Cog == 1 forward / dgrad
+// ------------------------------------------------------------------------------------
+template <typename T> struct Ld8;
+template <> struct Ld8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+template <> struct Ld8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+
+// One warp per output row.  VEC: Cig % 8 == 0 and 16/32-byte aligned rows -> 8-wide loads.
+template <typename T, typename TO, bool VEC>
+__global__ void __launch_bounds__(256) tapconv_co1_kernel(const __grid_constant__ artic_tapconv_t p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t Mtot = (int64_t)p.N * p.nq;
+  const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= Mtot) return;
+  const int n = (int)(m / p.nq);
+  const int q = p.q0 + (int)(m % p.nq);
+  const int row = q * p.so + p.ro;
+  if (row < 0 || row >= p.y.len) return;
+  const T* __restrict__ X = reinterpret_cast<const T*>(p.X) + seq_base(p.x, n);
+  const T* __restrict__ W = reinterpret_cast<const T*>(p.W);
+  float acc = 0.f;
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int pos = q * p.si + p.off[t];
+    if (pos < 0 || pos >= p.x.len) continue;
+    const T* xr = X + (int64_t)pos * p.x.s_row;
+    const T* wr = W + (int64_t)p.widx[t] * p.Cig;   // [K][G=1][Cig][Cog=1]
+    if (VEC) {
+      for (int c = lane * 8; c < p.Cig; c += 256) {
+        float a[8], b[8];
+        Ld8<T>::load(xr + c, a);
+        Ld8<T>::load(wr + c, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
+      }
+    } else {
+      for (int c = lane; c < p.Cig; c += 32) acc = fmaf(ld_f(xr + c), ld_f(wr + c), acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane != 0) return;
+  const int64_t o = seq_base(p.y, n) + (int64_t)row * p.y.s_row;
+  float v = p.alpha * acc;
+  if (p.bias) v += __ldg(p.bias);
+  if (p.res_pre) v += ld_f(reinterpret_cast<const TO*>(p.res_pre) + o);
+  if (p.mask) v *= (ld_f(reinterpret_cast<const TO*>(p.mask) + o) > 0.f ? 1.f : p.mask_slope);
+  if (p.res) v += ld_f(reinterpret_cast<const TO*>(p.res) + o);
+  if (p.res2) v += ld_f(reinterpret_cast<const TO*>(p.res2) + o);
+  if (p.Y) st_f(reinterpret_cast<TO*>(p.Y) + o, v);
+  if (p.Y2) {
+    if (p.act == ARTIC_ACT_LRELU) v = v > 0.f ? v : p.act_slope * v;
+    else if (p.act == ARTIC_ACT_TANH) v = tanhf(v);
+    st_f(reinterpret_cast<TO*>(p.Y2) + o, v);
+  }
+}
+
+template <typename T, typename TO>
+static void launch_co1(const artic_tapconv_t& p, cudaStream_t st) {
+  const int64_t Mtot = (int64_t)p.N * p.nq;
+  const unsigned grid = (unsigned)((Mtot + 7) / 8);
+  const int es = (int)sizeof(T);
+  const bool vec = (p.Cig % 8 == 0) && (p.x.s_row % 8 == 0) && (p.x.s_outer % 8 == 0) && (p.x.s_inner % 8 == 0) &&
+                   (reinterpret_cast<uintptr_t>(p.X) % (8 * es) == 0) && (reinterpret_cast<uintptr_t>(p.W) % (8 * es) == 0);
+  if (vec) tapconv_co1_kernel<T, TO, true><<<grid, 256, 0, st>>>(p);
+  else tapconv_co1_kernel<T, TO, false><<<grid, 256, 0, st>>>(p);
+}
+
+// ------------------------------------------------------------------------------------
+// Cig == 1 weight gradient
+// ------------------------------------------------------------------------------------
+constexpr int CI1_TAPS = 16;   // taps per pass (registers)
+constexpr int CI1_ROWS = 512;  // positions per CTA
+
+template <typename T, typename TY>
+__global__ void __launch_bounds__(256) tapwgrad_ci1_kernel(const __grid_constant__ artic_tapwgrad_t p, int cw, int tap0) {
+  // threads: cw channel lanes x (256 / cw) position lanes
+  __shared__ float red[256];
+  const int cl = threadIdx.x % cw;
+  const int pl = threadIdx.x / cw;
+  const int npl = 256 / cw;
+  const int c = blockIdx.y * cw + cl;
+  const int64_t Mtot = (int64_t)p.N * p.nq;
+  const int64_t m0 = (int64_t)blockIdx.x * CI1_ROWS;
+  const int64_t m1 = min(Mtot, m0 + CI1_ROWS);
+  const T* __restrict__ X = reinterpret_cast<const T*>(p.X);
+  const TY* __restrict__ dY = reinterpret_cast<const TY*>(p.dY);
+  const int nt = min(CI1_TAPS, p.ntaps - tap0);
+  float acc[CI1_TAPS];
+#pragma unroll
+  for (int t = 0; t < CI1_TAPS; ++t) acc[t] = 0.f;
+  if (c < p.Cog) {
+    for (int64_t m = m0 + pl; m < m1; m += npl) {
+      const int n = (int)(m / p.nq);
+      const int q = p.q0 + (int)(m % p.nq);
+      const T* xs = X + seq_base(p.x, n);
+      const TY* ys = dY + seq_base(p.y, n);
+#pragma unroll
+      for (int t = 0; t < CI1_TAPS; ++t) {
+        if (t < nt) {
+          const int xpos = q * p.si + p.off[tap0 + t];
+          const int ypos = q * p.so + p.yoff[tap0 + t];
+          if (xpos >= 0 && xpos < p.x.len && ypos >= 0 && ypos < p.y.len)
+            acc[t] = fmaf(ld_f(xs + (int64_t)xpos * p.x.s_row), ld_f(ys + (int64_t)ypos * p.y.s_row + c), acc[t]);
+        }
+      }
+    }
+  }
+  // reduce over position lanes, one atomic per (tap, channel) per CTA
+  for (int t = 0; t < nt; ++t) {
+    __syncthreads();
+    red[threadIdx.x] = acc[t];
+    __syncthreads();
+    if (pl == 0 && c < p.Cog) {
+      float s = 0.f;
+      for (int i = 0; i < npl; ++i) s += red[i * cw + cl];
+      atomicAdd(p.dW + (int64_t)p.widx[tap0 + t] * p.Cog + c, s);   // [K][G=1][Cig=1][Cog]
+    }
+  }
+}
+
+}  // namespace artic
+
+using namespace artic;
+
+// returns 1 if taken, 0 if not eligible
+int artic_tapconv_co1_try(const artic_tapconv_t* pp, cudaStream_t st) {
+  const artic_tapconv_t& p = *pp;
+  if (p.Cog != 1 || p.G != 1 || p.Cig < 32) return 0;
+  const bool ob = p.out_dtype == ARTIC_BF16;
+  if (p.dtype == ARTIC_BF16) {
+    if (ob) launch_co1<__nv_bfloat16, __nv_bfloat16>(p, st);
+    else launch_co1<__nv_bfloat16, float>(p, st);
+  } else {
+    if (ob) launch_co1<float, __nv_bfloat16>(p, st);
+    else launch_co1<float, float>(p, st);
+  }
+  return 1;
+}
+
+int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
+  const artic_tapwgrad_t& p = *pp;
+  if (p.Cig != 1 || p.G != 1) return 0;
+  int cw = 32;
+  while (cw < 256 && cw < p.Cog) cw <<= 1;
+  const int64_t Mtot = (int64_t)p.N * p.nq;
+  dim3 grid((unsigned)((Mtot + CI1_ROWS - 1) / CI1_ROWS), (unsigned)((p.Cog + cw - 1) / cw));
+  const bool yb = p.y_dtype == ARTIC_BF16;
+  for (int tap0 = 0; tap0 < p.ntaps; tap0 += CI1_TAPS) {
+    if (p.dtype == ARTIC_BF16) {
+      if (yb) tapwgrad_ci1_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(p, cw, tap0);
+      else tapwgrad_ci1_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(p, cw, tap0);
+    } else {
+      if (yb) tapwgrad_ci1_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(p, cw, tap0);
+      else tapwgrad_ci1_kernel<float, float><<<grid, 256, 0, st>>>(p, cw, tap0);
+    }
+  }
+  return 1;
+}

@@ -407,6 +407,9 @@ static int check_seq(const artic_seq_t& s) { return s.n_inner >= 1 && s.len >= 0
 // implemented in tapconv_tc.cu: returns 1 if it took the launch, 0 if the shape is not
 // eligible (fall through to the generic kernel), <0 on error.
 int artic_tapconv_tc_try(const artic_tapconv_t* p, cudaStream_t st);
+int artic_tapwgrad_tc_try(const artic_tapwgrad_t* p, cudaStream_t st);  // tapwgrad_tc.cu, same convention
+int artic_tapconv_co1_try(const artic_tapconv_t* p, cudaStream_t st);    // smallc.cu
+int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* p, cudaStream_t st);  // smallc.cu
 
 extern "C" int artic_tapconv(const artic_tapconv_t* p, void* stream) {
   ARTIC_CHECK_ARG(p != nullptr, "null params");
@@ -421,6 +424,10 @@ extern "C" int artic_tapconv(const artic_tapconv_t* p, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
   const bool ob = p->out_dtype == ARTIC_BF16;
+  if (artic_tapconv_co1_try(p, st) == 1) {
+    ARTIC_LAUNCH_CHECK();
+    return ARTIC_OK;
+  }
   if (p->dtype == ARTIC_BF16) {
     rc = ob ? artic_tapconv_tc_try(p, st) : 0;
     if (rc < 0) return rc;
@@ -446,7 +453,13 @@ extern "C" int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream) {
   if (p->N == 0 || p->nq == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool yb = p->y_dtype == ARTIC_BF16;
-  int rc;
+  if (artic_tapwgrad_ci1_try(p, st) == 1) {
+    ARTIC_LAUNCH_CHECK();
+    return ARTIC_OK;
+  }
+  int rc = artic_tapwgrad_tc_try(p, st);
+  if (rc < 0) return rc;
+  if (rc == 1) return ARTIC_OK;
   if (p->dtype == ARTIC_BF16) rc = yb ? launch_tapwgrad<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapwgrad<__nv_bfloat16, float>(*p, st);
   else rc = yb ? launch_tapwgrad<float, __nv_bfloat16>(*p, st) : launch_tapwgrad<float, float>(*p, st);
   if (rc != ARTIC_OK) return rc;

@@ -16,9 +16,7 @@
 //   warps 2..5 = epilogue (TMEM -> registers -> fused bias / residual / LeakyReLU-mask /
 //   activation -> global).  Persistent over tiles; the accumulator is double-buffered in TMEM
 //   when it fits, so the epilogue of tile i overlaps the main loop of tile i+1.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace artic {
 namespace tc {
@@ -43,99 +41,12 @@ struct Plan {
   int32_t a_stage_bytes, w_stage_bytes, n_as, n_ws;
   int32_t acc_stages, tmem_cols;
   int32_t min_off;
-  int32_t shift[ARTIC_MAX_TAPS];  // off[t] - min_off
+  int32_t n_ph, panel_bytes;      // input-stride phases (= si) and bytes of one phase panel
+  int32_t shift[ARTIC_MAX_TAPS];  // (off[t] - min_off) / si : row shift inside the tap's phase panel
+  int32_t phase[ARTIC_MAX_TAPS];  // (off[t] - min_off) % si : which phase panel the tap reads
   int32_t layout_type;            // UMMA smem descriptor swizzle code
   int32_t base_offset_mode;       // debug: 0 = address-based swizzle phase, 1 = explicit base offset
 };
-
-// ------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a pipeline bug traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset,
@@ -149,33 +60,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
   d |= (uint64_t)(base_off & 7) << 49;
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
-}
-
-struct PipeState {
-  int stage, phase, n;
-  __device__ __forceinline__ PipeState(int n_) : stage(0), phase(0), n(n_) {}
-  __device__ __forceinline__ void next() {
-    if (++stage == n) { stage = 0; phase ^= 1; }
-  }
-};
-
-template <typename T> __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]);
-template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& u, float (&f)[8]) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  uint32_t w[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    w[i] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // ------------------------------------------------------------------------------------
@@ -229,19 +113,22 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
           if (!pl.packed) {
             const int n = mtile / pl.tiles_per_seq;
             const int qt = mtile % pl.tiles_per_seq;
-            const int row0 = p.q0 + qt * pl.mt * 128 + pl.min_off;
-            mbar_expect_tx(&a_full[as.stage], (uint32_t)pl.nbox * pl.boxr * pl.row_bytes);
-            for (int b = 0; b < pl.nbox; ++b)
-              tma_load_4d(a_dst + (uint32_t)b * pl.boxr * pl.row_bytes, &map_x, &a_full[as.stage], c0, n % p.x.n_inner,
-                          row0 + b * pl.boxr, n / p.x.n_inner);
+            const int qrow0 = p.q0 + qt * pl.mt * 128;
+            mbar_expect_tx(&a_full[as.stage], (uint32_t)pl.n_ph * pl.nbox * pl.boxr * pl.row_bytes);
+            for (int ph = 0; ph < pl.n_ph; ++ph)
+              for (int b = 0; b < pl.nbox; ++b)
+                tma_load_4d(a_dst + (uint32_t)ph * pl.panel_bytes + (uint32_t)b * pl.boxr * pl.row_bytes, &map_x,
+                            &a_full[as.stage], c0, n % p.x.n_inner, (qrow0 + b * pl.boxr) * p.si + pl.min_off + ph,
+                            n / p.x.n_inner);
           } else {
             const int n0 = mtile * pl.seg_per_tile;
             const int nseg = min(pl.seg_per_tile, p.N - n0);
-            mbar_expect_tx(&a_full[as.stage], (uint32_t)nseg * pl.seg_rows * pl.row_bytes);
+            mbar_expect_tx(&a_full[as.stage], (uint32_t)nseg * pl.n_ph * pl.seg_rows * pl.row_bytes);
             for (int j = 0; j < nseg; ++j) {
               const int n = n0 + j;
-              tma_load_4d(a_dst + (uint32_t)j * pl.seg_pitch * pl.row_bytes, &map_x, &a_full[as.stage], c0,
-                          n % p.x.n_inner, p.q0 + pl.min_off, n / p.x.n_inner);
+              for (int ph = 0; ph < pl.n_ph; ++ph)
+                tma_load_4d(a_dst + (uint32_t)ph * pl.panel_bytes + (uint32_t)j * pl.seg_pitch * pl.row_bytes, &map_x,
+                            &a_full[as.stage], c0, n % p.x.n_inner, p.q0 * p.si + pl.min_off + ph, n / p.x.n_inner);
             }
           }
           as.next();
@@ -275,7 +162,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
             const uint32_t w_st = w_base + (uint32_t)ws.stage * pl.w_stage_bytes;
             for (int m = 0; m < pl.mt; ++m) {
               const uint32_t a_row = (uint32_t)(m * 128 + pl.shift[t]);
-              const uint32_t a_addr = a_st + a_row * pl.row_bytes;
+              const uint32_t a_addr = a_st + (uint32_t)pl.phase[t] * pl.panel_bytes + a_row * pl.row_bytes;
               const uint32_t boff = pl.base_offset_mode ? ((a_addr >> 7) & 7u) : 0u;
 #pragma unroll 4
               for (int k = 0; k < ksteps; ++k) {
@@ -398,11 +285,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
 // ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -416,7 +299,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 static int g_smem_optin = 0;
 
 // Largest dynamic shared-memory size the kernel may be launched with (opt-in limit minus the
@@ -440,10 +323,6 @@ static int max_smem() {
   return g_smem_optin;
 }
 
-static CUtensorMapSwizzle swizzle_of(int row_bytes) {
-  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-}
-
 }  // namespace tc
 }  // namespace artic
 
@@ -460,7 +339,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   const artic_tapconv_t& p = *pp;
   if (tc::g_debug[1]) return 0;                       // debug: force the generic kernel
   if (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16) return 0;
-  if (p.si != 1) return 0;
+  if (p.si < 1 || p.si > 8) return 0;
   if (p.Cig % 16 != 0 || p.Cog % 32 != 0) return 0;
   if ((p.x.s_row % 8) || (p.x.s_outer % 8) || (p.x.n_inner > 1 && (p.x.s_inner % 8))) return 0;
   if ((p.y.s_row % 8) || (p.y.s_outer % 8) || (p.y.n_inner > 1 && (p.y.s_inner % 8))) return 0;
@@ -474,10 +353,15 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   memset(&pl, 0, sizeof(pl));
   int min_off = p.off[0], max_off = p.off[0];
   for (int t = 1; t < p.ntaps; ++t) { min_off = min(min_off, p.off[t]); max_off = max(max_off, p.off[t]); }
-  const int span = max_off - min_off;
-  if (span > 160 || min_off < -(1 << 20)) return 0;   // also rejects the "no tap on this phase" marker
+  if (max_off - min_off > 160 * p.si || min_off < -(1 << 20)) return 0;   // also rejects the "no tap on this phase" marker
   pl.min_off = min_off;
-  for (int t = 0; t < p.ntaps; ++t) pl.shift[t] = p.off[t] - min_off;
+  pl.n_ph = p.si;
+  int span = 0;                                       // largest row shift inside a phase panel
+  for (int t = 0; t < p.ntaps; ++t) {
+    pl.shift[t] = (p.off[t] - min_off) / p.si;
+    pl.phase[t] = (p.off[t] - min_off) % p.si;
+    span = max(span, pl.shift[t]);
+  }
   pl.kch = (p.Cig % 64 == 0) ? 64 : (p.Cig % 32 == 0) ? 32 : 16;
   pl.row_bytes = pl.kch * 2;
   pl.n_kc = p.Cig / pl.kch;
@@ -489,9 +373,15 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   if (mt < 1) mt = 1;
   if (mt > 4) mt = 4;
   if (tc::g_debug[3] > 0) mt = tc::g_debug[3];
+  pl.w_stage_bytes = ((pl.bn * pl.row_bytes + 1023) / 1024) * 1024;
+  const int budget = tc::max_smem() - 1024 /*alignment slack*/;
+  {  // keep two activation stages + a few weight stages within shared memory
+    auto a_bytes = [&](int m) { return p.si * ((((m * 128 + span + 64) * pl.row_bytes + 1023) / 1024) * 1024); };
+    while (mt > 1 && 2 * a_bytes(mt) + 3 * pl.w_stage_bytes > budget) --mt;
+  }
   const int rows_align = 128 / pl.row_bytes;          // TMA shared-memory destinations are 128-byte aligned
   const int lpad = p.nq + span;
-  pl.packed = (p.N >= 2 && lpad <= 256 && 2 * lpad <= mt * 128) ? 1 : 0;
+  pl.packed = (p.N >= 2 && lpad * p.si <= 256 && 2 * lpad <= mt * 128) ? 1 : 0;
   if (tc::g_debug[4] == 1) pl.packed = 0;
   int a_rows;
   if (pl.packed) {
@@ -508,7 +398,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
     while (mt > 1 && (mt - 1) * 128 >= p.nq) --mt;
     pl.tiles_per_seq = (p.nq + mt * 128 - 1) / (mt * 128);
     pl.n_mt = p.N * pl.tiles_per_seq;
-    pl.boxr = 64;
+    pl.boxr = p.si == 1 ? 64 : 32;                     // TMA box extent (rows * si) must stay <= 256
     pl.nbox = (mt * 128 + span + pl.boxr - 1) / pl.boxr;
     a_rows = pl.nbox * pl.boxr;
   }
@@ -517,9 +407,8 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   int cols = pl.acc_stages * mt * pl.bn;
   pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   if (cols > 512) return 0;
-  pl.a_stage_bytes = ((a_rows * pl.row_bytes + 1023) / 1024) * 1024;
-  pl.w_stage_bytes = ((pl.bn * pl.row_bytes + 1023) / 1024) * 1024;
-  const int budget = tc::max_smem() - 1024 /*alignment slack*/;
+  pl.panel_bytes = ((a_rows * pl.row_bytes + 1023) / 1024) * 1024;
+  pl.a_stage_bytes = pl.n_ph * pl.panel_bytes;
   pl.n_as = 2;
   int rem = budget - pl.n_as * pl.a_stage_bytes;
   if (rem < 2 * pl.w_stage_bytes) {
@@ -543,8 +432,9 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
     cuuint64_t strides[3] = {(cuuint64_t)(ni > 1 ? p.x.s_inner : p.x.s_row) * 2, (cuuint64_t)p.x.s_row * 2,
                              (cuuint64_t)p.x.s_outer * 2};
     if (dims[3] == 1 && strides[2] == 0) strides[2] = strides[1] * dims[2];
-    cuuint32_t box[4] = {(cuuint32_t)pl.kch, 1, (cuuint32_t)(pl.packed ? pl.seg_rows : pl.boxr), 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // rows are traversed with stride si: a box of rows*si elements loads `rows` rows (one phase)
+    cuuint32_t box[4] = {(cuuint32_t)pl.kch, 1, (cuuint32_t)((pl.packed ? pl.seg_rows : pl.boxr) * p.si), 1};
+    cuuint32_t es[4] = {1, 1, (cuuint32_t)p.si, 1};
     CUresult rc = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.X), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swizzle_of(pl.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -1,0 +1,389 @@
+// tcgen05 weight-gradient kernel of the tap-gather contraction (artic_tapconv_wgrad) for the
+// dense bf16 stride-1 convolutions:
+//
+//   dW[t][ci][co] += sum_{n,q} X[n, q + off[t], ci] * dY[n, q + yoff, co]
+//
+// GEMM view: M = input channels (TMEM lanes), N = output channels, K = positions.  Both
+// operands are staged by TMA exactly as they sit in HBM (channels-last rows), i.e. "MN-major"
+// for the tensor core: the X tile [positions + halo][ci] is loaded ONCE per position chunk and
+// every tap reads it through a row-shifted shared-memory descriptor; each tap owns its own
+// fp32 accumulator in TMEM (n_acc * BN <= 512 columns).
+// Narrow layers (Cig = 64 / 32) put 2 / 4 TAPS side by side in the 128 MMA rows: the leading
+// byte offset of the A descriptor is the byte distance between consecutive taps (dil rows),
+// so the second/third/fourth 64/32-row block of A is the same tile shifted by one more tap.
+// Positions are split over CTAs (split-K); partial sums are reduced into the fp32 dW with
+// vector red.global.add.
+//
+// Zero padding / sequence boundaries: rows outside [0, len) are zero-filled by TMA; short
+// sequences are packed back to back with their halos (pitch = L + span), the padding rows of
+// dY being zero so that they contribute nothing.  The staging area is zeroed once so that rows
+// no TMA ever writes are exact zeros rather than stale bits.
+#include "tc_common.cuh"
+
+namespace artic {
+namespace tc {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_STAGES = 8;
+
+struct WPlan {
+  int32_t xrb, yrb;            // row bytes (= swizzle span) of the X / dY panels
+  int32_t x_layout, y_layout;  // UMMA swizzle codes
+  int32_t mci;                 // input channels per CTA (128, 64 or 32)
+  int32_t slots;               // taps side by side in the 128 MMA rows (1, 2 or 4)
+  int32_t nxp, nyp;            // panels per stage for X / dY
+  int32_t x_rows, kp;          // staged X rows per panel, positions per chunk
+  int32_t x_panel_bytes, y_panel_bytes, stage_bytes, n_stages;
+  int32_t bn, n_nt, n_mb, n_tg, tpc;  // co tile, #co tiles, #ci blocks, #tap groups, taps per group
+  int32_t n_acc;               // accumulators per CTA (= ceil(tpc / slots))
+  int32_t tmem_cols;
+  int32_t packed, seg_per_chunk, seg_pitch, chunks_per_seq, n_chunks, chunks_per_split, n_splits;
+  int32_t boxr, nxb;           // plain: rows per X box, X boxes per panel
+  int32_t min_off;             // first tap offset
+  int32_t a_lbo;               // leading byte offset of the A descriptor
+  int32_t n_ph;                // input-stride phases (= si); X panels per stage = n_ph * nxp
+  int32_t tap_stride;          // tap-index distance between side-by-side slots
+  int32_t n_acc_total, apc;    // accumulators over all CTAs of a (ci, co) tile; accumulators per CTA
+  // per accumulator: phase panel, row shift of slot 0, tap index of slot 0, number of valid slots
+  int8_t acc_panel[ARTIC_MAX_TAPS];
+  int16_t acc_shift[ARTIC_MAX_TAPS];
+  int8_t acc_tap0[ARTIC_MAX_TAPS];
+  int8_t acc_cnt[ARTIC_MAX_TAPS];
+};
+
+// MN-major shared-memory matrix descriptor: 64-element (SW128) / 32-element (SW64) channel blocks
+// LBO bytes apart, 8-position groups SBO = 8 * row_bytes apart.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t row_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(((8u * row_bytes) >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_constant__ WPlan pl,
+                   const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[WG_MAX_STAGES], empty[WG_MAX_STAGES];
+  __shared__ __align__(8) uint64_t acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  // ---- work decode: blockIdx.x -> (split z, co tile nt, ci block mb, tap group tg, group g)
+  int w = blockIdx.x;
+  const int z = w % pl.n_splits; w /= pl.n_splits;
+  const int nt = w % pl.n_nt; w /= pl.n_nt;
+  const int mb = w % pl.n_mb; w /= pl.n_mb;
+  const int tg = w % pl.n_tg;
+  const int g = w / pl.n_tg;
+  const int c_begin = z * pl.chunks_per_split;
+  const int c_end = min(pl.n_chunks, c_begin + pl.chunks_per_split);
+  const int acc0 = tg * pl.apc;
+  const int n_acc = min(pl.apc, pl.n_acc_total - acc0);
+
+  // ---- one-time setup: zero the staging area, barriers, TMEM
+  {
+    uint4* z4 = reinterpret_cast<uint4*>(smem_raw + (smem0 - smem_u32(smem_raw)));
+    const int n16 = pl.n_stages * pl.stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += WG_THREADS) z4[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_y);
+    for (int i = 0; i < pl.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)pl.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      PipeState ps(pl.n_stages);
+      const int cx0 = g * p.Cig + mb * pl.mci;
+      const int cy0 = g * p.Cog + nt * pl.bn;
+      const int xch = pl.xrb / 2, ych = pl.yrb / 2;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+        const uint32_t xs = smem0 + (uint32_t)ps.stage * pl.stage_bytes;
+        const uint32_t ys = xs + (uint32_t)(pl.n_ph * pl.nxp) * pl.x_panel_bytes;
+        if (!pl.packed) {
+          const int n = c / pl.chunks_per_seq;
+          const int qc = p.q0 + (c % pl.chunks_per_seq) * pl.kp;
+          mbar_expect_tx(&full[ps.stage],
+                         (uint32_t)(pl.n_ph * pl.nxp * pl.nxb * pl.boxr * pl.xrb + pl.nyp * pl.kp * pl.yrb));
+          for (int ph = 0; ph < pl.n_ph; ++ph)
+            for (int pn = 0; pn < pl.nxp; ++pn)
+              for (int b = 0; b < pl.nxb; ++b)
+                tma_load_4d(xs + (uint32_t)(ph * pl.nxp + pn) * pl.x_panel_bytes + (uint32_t)b * pl.boxr * pl.xrb, &map_x,
+                            &full[ps.stage], cx0 + pn * xch, n % p.x.n_inner, (qc + b * pl.boxr) * p.si + pl.min_off + ph,
+                            n / p.x.n_inner);
+          for (int pn = 0; pn < pl.nyp; ++pn)
+            tma_load_4d(ys + (uint32_t)pn * pl.y_panel_bytes, &map_y, &full[ps.stage], cy0 + pn * ych, n % p.y.n_inner,
+                        qc + p.yoff[0], n / p.y.n_inner);
+        } else {
+          const int n0 = c * pl.seg_per_chunk;
+          mbar_expect_tx(&full[ps.stage],
+                         (uint32_t)(pl.seg_per_chunk * pl.seg_pitch * (pl.n_ph * pl.nxp * pl.xrb + pl.nyp * pl.yrb)));
+          for (int j = 0; j < pl.seg_per_chunk; ++j) {
+            const int n = n0 + j;  // n >= N: fully out of bounds -> zero fill
+            for (int ph = 0; ph < pl.n_ph; ++ph)
+              for (int pn = 0; pn < pl.nxp; ++pn)
+                tma_load_4d(xs + (uint32_t)(ph * pl.nxp + pn) * pl.x_panel_bytes + (uint32_t)j * pl.seg_pitch * pl.xrb,
+                            &map_x, &full[ps.stage], cx0 + pn * xch, n % p.x.n_inner, p.q0 * p.si + pl.min_off + ph,
+                            n / p.x.n_inner);
+            for (int pn = 0; pn < pl.nyp; ++pn)
+              tma_load_4d(ys + (uint32_t)pn * pl.y_panel_bytes + (uint32_t)j * pl.seg_pitch * pl.yrb, &map_y,
+                          &full[ps.stage], cy0 + pn * ych, n % p.y.n_inner, p.q0 + p.yoff[0], n / p.y.n_inner);
+          }
+        }
+        ps.next();
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      PipeState ps(pl.n_stages);
+      // D fp32, A/B bf16, both MN-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(pl.bn >> 3) << 17) | ((128u >> 4) << 24);
+      const int ksteps = pl.kp / 16;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full[ps.stage], ps.phase);
+        tc_fence_after();
+        const uint32_t xs = smem0 + (uint32_t)ps.stage * pl.stage_bytes;
+        const uint32_t ys = xs + (uint32_t)(pl.n_ph * pl.nxp) * pl.x_panel_bytes;
+        for (int a = 0; a < n_acc; ++a) {
+          const uint32_t shift = (uint32_t)pl.acc_shift[acc0 + a];   // rows inside the phase panel
+          const uint32_t xp = xs + (uint32_t)(pl.acc_panel[acc0 + a] * pl.nxp) * pl.x_panel_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_desc_mn(xp + (shift + k * 16) * pl.xrb, pl.a_lbo, pl.xrb, pl.x_layout);
+            const uint64_t bd = make_desc_mn(ys + (uint32_t)(k * 16) * pl.yrb, pl.y_panel_bytes, pl.yrb, pl.y_layout);
+            umma_bf16(tmem_base + (uint32_t)a * pl.bn, ad, bd, idesc, (c > c_begin || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[ps.stage]);
+        ps.next();
+      }
+      umma_commit(&acc_full);
+    }
+  } else {
+    // =============================== epilogue ===================================
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;           // MMA row = TMEM lane
+    const int slot = row / pl.mci;            // which tap of the side-by-side group (0 when mci == 128)
+    const int ci = mb * pl.mci + (row - slot * pl.mci);
+    if (c_end > c_begin) {
+      mbar_wait(&acc_full, 0);
+      tc_fence_after();
+      for (int a = 0; a < n_acc; ++a) {
+        const bool valid = slot < pl.acc_cnt[acc0 + a] && ci < p.Cig;
+        float* dst = nullptr;
+        if (valid) {
+          const int tap = pl.acc_tap0[acc0 + a] + slot * pl.tap_stride;
+          dst = p.dW + (((int64_t)p.widx[tap] * p.G + g) * p.Cig + ci) * p.Cog + nt * pl.bn;
+        }
+        for (int c0 = 0; c0 < pl.bn; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * pl.bn + c0, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              red_add_v4(dst + c0 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                         __uint_as_float(r[i + 3]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
+  }
+}
+
+static int g_wg_smem = 0;
+static int wg_max_smem() {
+  if (g_wg_smem == 0) {
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (optin <= 0) optin = 227 * 1024;
+    cudaFuncAttributes fa;
+    int stat = 2048;
+    if (cudaFuncGetAttributes(&fa, tapwgrad_tc_kernel) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+    int dyn = optin - stat;
+    if (cudaFuncSetAttribute(tapwgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) {
+      cudaGetLastError();
+      dyn = 48 * 1024;
+    }
+    g_wg_smem = dyn;
+  }
+  return g_wg_smem;
+}
+
+static CUresult encode_seq_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, const artic_seq_t& s, int N,
+                               int channels, int box_ch, int box_rows, int row_bytes, int row_stride) {
+  const int ni = s.n_inner;
+  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)ni, (cuuint64_t)s.len, (cuuint64_t)((N + ni - 1) / ni)};
+  cuuint64_t strides[3] = {(cuuint64_t)(ni > 1 ? s.s_inner : s.s_row) * 2, (cuuint64_t)s.s_row * 2, (cuuint64_t)s.s_outer * 2};
+  if (dims[3] == 1 && strides[2] == 0) strides[2] = strides[1] * dims[2];
+  // rows traversed with stride row_stride: a box extent of rows*stride loads `rows` rows
+  cuuint32_t box[4] = {(cuuint32_t)box_ch, 1, (cuuint32_t)(box_rows * row_stride), 1};
+  cuuint32_t es[4] = {1, 1, (cuuint32_t)row_stride, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace tc
+}  // namespace artic
+
+using namespace artic;
+
+// returns 1 if the launch was taken, 0 if the shape is not eligible, <0 on error.
+int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
+  const artic_tapwgrad_t& p = *pp;
+  if (tc::g_debug[1] || tc::g_debug[5]) return 0;
+  if (p.dtype != ARTIC_BF16 || p.y_dtype != ARTIC_BF16) return 0;
+  if (p.si < 1 || p.si > 8 || p.so != 1) return 0;
+  if (!(p.Cig == 32 || p.Cig == 64 || p.Cig % 128 == 0) || p.Cog % 32 != 0) return 0;
+  if ((p.x.s_row % 8) || (p.x.s_outer % 8) || (p.x.n_inner > 1 && (p.x.s_inner % 8))) return 0;
+  if ((p.y.s_row % 8) || (p.y.s_outer % 8) || (p.y.n_inner > 1 && (p.y.s_inner % 8))) return 0;
+  if ((reinterpret_cast<uintptr_t>(p.X) & 15) || (reinterpret_cast<uintptr_t>(p.dY) & 15) ||
+      (reinterpret_cast<uintptr_t>(p.dW) & 15))
+    return 0;
+  for (int t = 1; t < p.ntaps; ++t)
+    if (p.yoff[t] != p.yoff[0]) return 0;
+  // positions past nq (chunk overrun) must fall outside dY so that TMA zero-fills them
+  if (p.q0 + p.yoff[0] + p.nq < p.y.len) return 0;
+  // taps must be uniformly spaced and ascending (conv: off[t] = t*dil - pad)
+  const int step = p.ntaps > 1 ? p.off[1] - p.off[0] : 1;
+  if (step < 1) return 0;
+  for (int t = 1; t < p.ntaps; ++t)
+    if (p.off[t] - p.off[t - 1] != step) return 0;
+  if (p.ntaps > 127) return 0;
+  tc::EncodeTiledFn enc = tc::encode_fn();
+  if (enc == nullptr) return 0;
+
+  tc::WPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  const int si = p.si;
+  pl.min_off = p.off[0];
+  pl.n_ph = si;
+  pl.mci = p.Cig >= 128 ? 128 : p.Cig;
+  pl.slots = 128 / pl.mci;
+  pl.n_mb = p.Cig / pl.mci;
+  pl.xrb = p.Cig >= 64 ? 128 : 64;
+  pl.x_layout = pl.xrb == 128 ? 2 : 4;
+  pl.nxp = pl.mci == 128 ? 2 : 1;
+  // taps t and t + u read the same phase panel, slot_rows rows apart (u = si / gcd(step, si))
+  int gcd = step, tmp = si;
+  while (tmp) { const int r = gcd % tmp; gcd = tmp; tmp = r; }
+  const int u = si / gcd, slot_rows = step / gcd;
+  pl.tap_stride = u;
+  // accumulators: for every residue class r < u, the taps r, r+u, r+2u, ... in groups of `slots`
+  int n_acc_total = 0, span_rows = 0, ext = 0;
+  for (int r = 0; r < u && r < p.ntaps; ++r) {
+    const int cnt = (p.ntaps - r + u - 1) / u;
+    for (int j = 0; j * pl.slots < cnt; ++j) {
+      const int t0 = r + u * (j * pl.slots);
+      const int a = n_acc_total++;
+      if (a >= ARTIC_MAX_TAPS) return 0;
+      pl.acc_panel[a] = (int8_t)((t0 * step) % si);
+      pl.acc_shift[a] = (int16_t)((t0 * step) / si);
+      pl.acc_tap0[a] = (int8_t)t0;
+      pl.acc_cnt[a] = (int8_t)min(pl.slots, cnt - j * pl.slots);
+      span_rows = max(span_rows, (int)pl.acc_shift[a] + (pl.acc_cnt[a] - 1) * slot_rows);
+      ext = max(ext, (int)pl.acc_shift[a] + (pl.slots - 1) * slot_rows);
+    }
+  }
+  pl.n_acc_total = n_acc_total;
+  // co tile: accumulators per CTA * bn <= 512 TMEM columns
+  if (p.Cog % 64 != 0) pl.bn = 32;
+  else if (p.Cog % 128 == 0 && n_acc_total <= 4) pl.bn = 128;
+  else pl.bn = 64;
+  if (tc::g_debug[6] > 0 && p.Cog % tc::g_debug[6] == 0) pl.bn = tc::g_debug[6];
+  pl.yrb = pl.bn >= 64 ? 128 : 64;
+  pl.y_layout = pl.yrb == 128 ? 2 : 4;
+  pl.nyp = pl.bn >= 64 ? pl.bn / 64 : 1;
+  pl.n_nt = p.Cog / pl.bn;
+  const int max_acc = 512 / pl.bn;
+  pl.n_tg = (n_acc_total + max_acc - 1) / max_acc;
+  pl.apc = (n_acc_total + pl.n_tg - 1) / pl.n_tg;
+  pl.n_acc = pl.apc;
+  const int cols = pl.apc * pl.bn;
+  pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  const int align = 2;  // keeps every TMA destination 128-byte aligned for 64-byte rows
+  const int lpad = ((p.nq + span_rows + align - 1) / align) * align;
+  pl.packed = (p.N >= 2 && lpad <= 64 && lpad * si <= 256) ? 1 : 0;
+  if (pl.packed) {
+    pl.seg_pitch = lpad;
+    pl.seg_per_chunk = 128 / lpad;
+    if (pl.seg_per_chunk > p.N) pl.seg_per_chunk = p.N;
+    pl.kp = ((pl.seg_per_chunk * lpad + 15) / 16) * 16;
+    pl.n_chunks = (p.N + pl.seg_per_chunk - 1) / pl.seg_per_chunk;
+    pl.x_rows = pl.kp + ext + 8;
+  } else {
+    pl.kp = 64;
+    pl.chunks_per_seq = (p.nq + pl.kp - 1) / pl.kp;
+    pl.n_chunks = p.N * pl.chunks_per_seq;
+    pl.boxr = si == 1 ? 64 : 32;
+    pl.nxb = (pl.kp + span_rows + pl.boxr - 1) / pl.boxr;
+    pl.x_rows = max(pl.nxb * pl.boxr, pl.kp + ext + 8);
+  }
+  if (ext > 1024) return 0;
+  pl.x_panel_bytes = ((pl.x_rows * pl.xrb + 1023) / 1024) * 1024;
+  pl.y_panel_bytes = ((pl.kp * pl.yrb + 1023) / 1024) * 1024;
+  pl.stage_bytes = pl.n_ph * pl.nxp * pl.x_panel_bytes + pl.nyp * pl.y_panel_bytes;
+  pl.a_lbo = pl.mci == 128 ? pl.x_panel_bytes : slot_rows * pl.xrb;
+  if ((pl.a_lbo >> 4) > 0x3fff || (pl.y_panel_bytes >> 4) > 0x3fff) return 0;
+  const int budget = tc::wg_max_smem() - 1024;
+  pl.n_stages = budget / pl.stage_bytes;
+  if (pl.n_stages < 2) return 0;
+  if (pl.n_stages > tc::WG_MAX_STAGES) pl.n_stages = tc::WG_MAX_STAGES;
+  const int64_t base = (int64_t)pl.n_nt * pl.n_mb * pl.n_tg * p.G;
+  int64_t splits = num_sms() / base;
+  if (splits > pl.n_chunks) splits = pl.n_chunks;
+  if (splits < 1) splits = 1;
+  pl.chunks_per_split = (int)((pl.n_chunks + splits - 1) / splits);
+  pl.n_splits = (pl.n_chunks + pl.chunks_per_split - 1) / pl.chunks_per_split;
+  if (pl.n_stages > pl.chunks_per_split + 1) pl.n_stages = pl.chunks_per_split + 1;
+  if (pl.n_stages < 2) pl.n_stages = 2;
+  const int64_t grid = base * pl.n_splits;
+  if (grid > (1 << 30)) return 0;
+
+  CUtensorMap map_x, map_y;
+  CUresult rc = tc::encode_seq_map(enc, &map_x, p.X, p.x, p.N, p.G * p.Cig, pl.xrb / 2,
+                                   pl.packed ? pl.seg_pitch : pl.boxr, pl.xrb, si);
+  if (rc != CUDA_SUCCESS) { set_error("artic_tapconv_wgrad: cuTensorMapEncodeTiled(X) failed (%d)", (int)rc); return ARTIC_ECUDA; }
+  rc = tc::encode_seq_map(enc, &map_y, p.dY, p.y, p.N, p.G * p.Cog, pl.yrb / 2, pl.packed ? pl.seg_pitch : pl.kp, pl.yrb, 1);
+  if (rc != CUDA_SUCCESS) { set_error("artic_tapconv_wgrad: cuTensorMapEncodeTiled(dY) failed (%d)", (int)rc); return ARTIC_ECUDA; }
+  const int smem_bytes = pl.n_stages * pl.stage_bytes + 1024;
+  tc::tapwgrad_tc_kernel<<<(unsigned)grid, tc::WG_THREADS, smem_bytes, st>>>(p, pl, map_x, map_y);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    set_error("artic_tapconv_wgrad(tc): launch failed: %s (grid %lld, smem %d of %d, bn %d acc %d stages %d packed %d)",
+              cudaGetErrorString(le), (long long)grid, smem_bytes, tc::wg_max_smem(), pl.bn, pl.n_acc, pl.n_stages, pl.packed);
+    return ARTIC_ECUDA;
+  }
+  return 1;
+}

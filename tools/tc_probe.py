@@ -32,7 +32,21 @@ CASES = [
     (dict(kind="convT", cin=512, cout=256, k=10, stride=5, padding=3, output_padding=1), 2, 100, 1),
     (dict(kind="convT", cin=64, cout=32, k=4, stride=2, padding=1), 2, 4000, 1),
     (dict(kind="conv", cin=96, cout=160, k=5, padding=2), 2, 300, 1),
+    (dict(kind="conv", cin=64, cout=64, k=11, dilation=1, padding=5), 16, 4000, 1),
+    (dict(kind="conv", cin=32, cout=32, k=7, dilation=3, padding=9), 16, 8000, 1),
+    (dict(kind="conv", cin=256, cout=256, k=3, dilation=1, padding=1), 16, 500, 1),
+    (dict(kind="conv", cin=128, cout=128, k=11, dilation=1, padding=5), 16, 2000, 1),
+    (dict(kind="conv", cin=1024, cout=1024, k=5, stride=1, padding=2), 32, 53, 2),
+    (dict(kind="conv", cin=32, cout=32, k=41, stride=1, padding=20, groups=1), 2, 517, 1),
     (dict(kind="conv", cin=48, cout=96, k=3, padding=1), 2, 300, 1),
+    (dict(kind="conv", cin=32, cout=128, k=5, stride=3, padding=2), 6, 473, 3),
+    (dict(kind="conv", cin=512, cout=1024, k=5, stride=3, padding=2), 4, 158, 2),
+    (dict(kind="conv", cin=512, cout=1024, k=5, stride=3, padding=2), 22, 29, 11),
+    (dict(kind="conv", cin=128, cout=128, k=41, stride=4, padding=20, groups=4), 2, 8512, 1),
+    (dict(kind="conv", cin=256, cout=512, k=41, stride=4, padding=20, groups=16), 2, 532, 1),
+    (dict(kind="conv", cin=512, cout=1024, k=41, stride=4, padding=20, groups=16), 3, 133, 1),
+    (dict(kind="conv", cin=1024, cout=1024, k=41, stride=1, padding=20, groups=16), 4, 34, 1),
+    (dict(kind="conv", cin=64, cout=64, k=7, stride=2, dilation=3, padding=9), 3, 1001, 1),
 ]
 
 
@@ -74,9 +88,13 @@ def run(case, mode):
     x = torch.randn(N, spec.cin, lin, dtype=torch.float64).to(torch.bfloat16).double()
     w = w.to(torch.bfloat16).double()
     x.requires_grad_(True)
+    x.requires_grad_(True)
     y = torch_fwd(spec, x, w, b)
     dy = torch.randn_like(y).to(torch.bfloat16).double()
-    gx, = torch.autograd.grad(y, [x], dy)
+    w.requires_grad_(True)
+    y = torch_fwd(spec, x, w, b)
+    gx, gw = torch.autograd.grad(y, [x, w], dy)
+    w = w.detach()
     lib = _lib.load()
     lib.artic_debug_set(1, 1 if mode == "generic" else 0)
     lib.artic_debug_set(0, 1 if mode == "tc1" else 0)
@@ -97,6 +115,22 @@ def run(case, mode):
     lay.dgrad(dY, dX=dX)
     torch.cuda.synchronize()
     e_d = rel(seq_to(dX), gx)
+    params = {"l.weight": lay.v, "l.bias": lay.b}
+    grads = {k: torch.zeros_like(t) for k, t in params.items()}
+    lay.zero_wgrad()
+    lay.wgrad(X, dY, grads)
+    lay.finish_grads(grads)
+    torch.cuda.synchronize()
+    e_w = rel(grads["l.weight"].cpu(), gw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        lay.wgrad(X, dY, grads)
+    e0.record()
+    for _ in range(10):
+        lay.wgrad(X, dY, grads)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_w = e0.elapsed_time(e1) / 10
     # timing of the forward
     for _ in range(3):
         lay.forward(X, Y=Y, Y2=Y2, act=_lib.ACT_LRELU, act_slope=0.1)
@@ -109,7 +143,7 @@ def run(case, mode):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     flops = 2.0 * N * lout * spec.cout * spec.cig * spec.k / (spec.stride if spec.kind == "convT" else 1)
-    return e_f, e_a, e_d, ms, flops / ms / 1e9
+    return e_f, e_a, e_d, e_w, ms, flops / ms / 1e9, ms_w, flops / ms_w / 1e9
 
 
 def main():
@@ -118,8 +152,9 @@ def main():
         for mode in modes:
             t0 = time.time()
             try:
-                e_f, e_a, e_d, ms, tf = run(case, mode)
-                print(f"case {ci:2d} {mode:8s} fwd {e_f:.2e} act {e_a:.2e} dgrad {e_d:.2e}  fwd {ms:.4f} ms {tf:8.2f} TFLOP/s  "
+                e_f, e_a, e_d, e_w, ms, tf, ms_w, tf_w = run(case, mode)
+                print(f"case {ci:2d} {mode:8s} fwd {e_f:.2e} act {e_a:.2e} dgrad {e_d:.2e} wgrad {e_w:.2e} | fwd {ms:.4f} ms {tf:7.2f} TF/s "
+                      f"wgrad {ms_w:.4f} ms {tf_w:7.2f} TF/s  "
                       f"{case[0]} N={case[1]} L={case[2]} ni={case[3]}", flush=True)
             except Exception as ex:  # noqa: BLE001
                 print(f"case {ci:2d} {mode:8s} FAILED after {time.time() - t0:.1f}s: {ex}", flush=True)
