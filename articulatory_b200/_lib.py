@@ -64,8 +64,8 @@ SIGNATURES = {
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
     "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),
-    "artic_weight_prep": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _i32, _p]),
-    "artic_weight_unprep": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "artic_weight_prep": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _p, _i32, _p]),
+    "artic_weight_unprep": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _p, _p, _p]),
     "artic_gen_input": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "artic_gen_input_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "artic_mean3_act": (C.c_int, [_p, _p, _p, _p, _i64, _f, _i32, _i32, _p]),

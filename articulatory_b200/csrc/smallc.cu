@@ -94,46 +94,49 @@ static void launch_co1(const artic_tapconv_t& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------
-// Cig == 1 weight gradient
+// Cig == 1 and Cog == 1 weight gradients
 // ------------------------------------------------------------------------------------
-constexpr int CI1_TAPS = 16;   // taps per pass (registers)
-constexpr int CI1_ROWS = 512;  // positions per CTA
+constexpr int C1_TAPS = 16;   // taps per pass (registers)
+constexpr int C1_ROWS = 512;  // positions per CTA
+constexpr int C1_SMEM = 2304; // staged single-channel samples per CTA
 
+// dW[t][co] = sum_q x[q*si + off_t] * dY[q*so + yoff_t][co]   (x single channel, staged in smem).
+// grid = (chunks per sequence, N, channel tiles); threads = cw channel lanes x 256/cw position lanes.
 template <typename T, typename TY>
-__global__ void __launch_bounds__(256) tapwgrad_ci1_kernel(const __grid_constant__ artic_tapwgrad_t p, int cw, int tap0) {
-  // threads: cw channel lanes x (256 / cw) position lanes
+__global__ void __launch_bounds__(256) tapwgrad_ci1_kernel(const __grid_constant__ artic_tapwgrad_t p, int cw, int tap0,
+                                                           int min_off, int span) {
+  __shared__ float xs[C1_SMEM];
   __shared__ float red[256];
-  const int cl = threadIdx.x % cw;
-  const int pl = threadIdx.x / cw;
-  const int npl = 256 / cw;
-  const int c = blockIdx.y * cw + cl;
-  const int64_t Mtot = (int64_t)p.N * p.nq;
-  const int64_t m0 = (int64_t)blockIdx.x * CI1_ROWS;
-  const int64_t m1 = min(Mtot, m0 + CI1_ROWS);
-  const T* __restrict__ X = reinterpret_cast<const T*>(p.X);
-  const TY* __restrict__ dY = reinterpret_cast<const TY*>(p.dY);
-  const int nt = min(CI1_TAPS, p.ntaps - tap0);
-  float acc[CI1_TAPS];
+  const int cl = threadIdx.x % cw, pl = threadIdx.x / cw, npl = 256 / cw;
+  const int c = blockIdx.z * cw + cl;
+  const int n = blockIdx.y;
+  const int qa = blockIdx.x * C1_ROWS;                 // relative to q0
+  const int qb = min(p.nq, qa + C1_ROWS);
+  const T* __restrict__ X = reinterpret_cast<const T*>(p.X) + seq_base(p.x, n);
+  const TY* __restrict__ dY = reinterpret_cast<const TY*>(p.dY) + seq_base(p.y, n);
+  const int x0 = (p.q0 + qa) * p.si + min_off;         // first staged sample
+  const int nx = (qb - qa - 1) * p.si + span + 1;
+  for (int i = threadIdx.x; i < nx; i += 256) {
+    const int pos = x0 + i;
+    xs[i] = (pos >= 0 && pos < p.x.len) ? ld_f(X + (int64_t)pos * p.x.s_row) : 0.f;
+  }
+  __syncthreads();
+  const int nt = min(C1_TAPS, p.ntaps - tap0);
+  float acc[C1_TAPS];
 #pragma unroll
-  for (int t = 0; t < CI1_TAPS; ++t) acc[t] = 0.f;
+  for (int t = 0; t < C1_TAPS; ++t) acc[t] = 0.f;
+  const int yo = p.yoff[tap0];
   if (c < p.Cog) {
-    for (int64_t m = m0 + pl; m < m1; m += npl) {
-      const int n = (int)(m / p.nq);
-      const int q = p.q0 + (int)(m % p.nq);
-      const T* xs = X + seq_base(p.x, n);
-      const TY* ys = dY + seq_base(p.y, n);
+    for (int q = qa + pl; q < qb; q += npl) {
+      const int ypos = (p.q0 + q) * p.so + yo;
+      if (ypos < 0 || ypos >= p.y.len) continue;
+      const float dy = ld_f(dY + (int64_t)ypos * p.y.s_row + c);
+      const int xb = (q - qa) * p.si - min_off;
 #pragma unroll
-      for (int t = 0; t < CI1_TAPS; ++t) {
-        if (t < nt) {
-          const int xpos = q * p.si + p.off[tap0 + t];
-          const int ypos = q * p.so + p.yoff[tap0 + t];
-          if (xpos >= 0 && xpos < p.x.len && ypos >= 0 && ypos < p.y.len)
-            acc[t] = fmaf(ld_f(xs + (int64_t)xpos * p.x.s_row), ld_f(ys + (int64_t)ypos * p.y.s_row + c), acc[t]);
-        }
-      }
+      for (int t = 0; t < C1_TAPS; ++t)
+        if (t < nt) acc[t] = fmaf(xs[xb + p.off[tap0 + t]], dy, acc[t]);
     }
   }
-  // reduce over position lanes, one atomic per (tap, channel) per CTA
   for (int t = 0; t < nt; ++t) {
     __syncthreads();
     red[threadIdx.x] = acc[t];
@@ -142,6 +145,56 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_kernel(const __grid_constant
       float s = 0.f;
       for (int i = 0; i < npl; ++i) s += red[i * cw + cl];
       atomicAdd(p.dW + (int64_t)p.widx[tap0 + t] * p.Cog + c, s);   // [K][G=1][Cig=1][Cog]
+    }
+  }
+}
+
+// dW[t][ci] = sum_q X[q + off_t][ci] * dy[q + yoff]   (dy single channel, staged in smem; si = so = 1).
+// Every X element is read once and feeds all taps.
+template <typename T, typename TY>
+__global__ void __launch_bounds__(256) tapwgrad_co1_kernel(const __grid_constant__ artic_tapwgrad_t p, int cw, int tap0,
+                                                           int min_off, int span) {
+  __shared__ float ys[C1_SMEM];
+  __shared__ float red[256];
+  const int cl = threadIdx.x % cw, pl = threadIdx.x / cw, npl = 256 / cw;
+  const int c = blockIdx.z * cw + cl;
+  const int n = blockIdx.y;
+  // this CTA owns X rows [ra, rb) and needs dy[q] for q = r - off_t, i.e. q in [ra - max_off, rb - 1 - min_off]
+  const int ra = p.q0 + min_off + blockIdx.x * C1_ROWS;
+  const int rb = min(p.q0 + p.nq + min_off + span, ra + C1_ROWS);
+  const T* __restrict__ X = reinterpret_cast<const T*>(p.X) + seq_base(p.x, n);
+  const TY* __restrict__ dY = reinterpret_cast<const TY*>(p.dY) + seq_base(p.y, n);
+  const int y0 = ra - (min_off + span);                // first staged q
+  const int ny = (rb - ra) + span;
+  const int yo = p.yoff[tap0];
+  for (int i = threadIdx.x; i < ny; i += 256) {
+    const int q = y0 + i;
+    const int ypos = q + yo;
+    ys[i] = (q >= p.q0 && q < p.q0 + p.nq && ypos >= 0 && ypos < p.y.len) ? ld_f(dY + (int64_t)ypos * p.y.s_row) : 0.f;
+  }
+  __syncthreads();
+  const int nt = min(C1_TAPS, p.ntaps - tap0);
+  float acc[C1_TAPS];
+#pragma unroll
+  for (int t = 0; t < C1_TAPS; ++t) acc[t] = 0.f;
+  if (c < p.Cig) {
+    for (int r = ra + pl; r < rb; r += npl) {
+      if (r < 0 || r >= p.x.len) continue;
+      const float x = ld_f(X + (int64_t)r * p.x.s_row + c);
+      const int yb = r - y0;                           // index of q = r in ys
+#pragma unroll
+      for (int t = 0; t < C1_TAPS; ++t)
+        if (t < nt) acc[t] = fmaf(x, ys[yb - p.off[tap0 + t]], acc[t]);
+    }
+  }
+  for (int t = 0; t < nt; ++t) {
+    __syncthreads();
+    red[threadIdx.x] = acc[t];
+    __syncthreads();
+    if (pl == 0 && c < p.Cig) {
+      float s = 0.f;
+      for (int i = 0; i < npl; ++i) s += red[i * cw + cl];
+      atomicAdd(p.dW + (int64_t)p.widx[tap0 + t] * p.Cig + c, s);   // [K][G=1][Cig][Cog=1]
     }
   }
 }
@@ -167,20 +220,35 @@ int artic_tapconv_co1_try(const artic_tapconv_t* pp, cudaStream_t st) {
 
 int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   const artic_tapwgrad_t& p = *pp;
-  if (p.Cig != 1 || p.G != 1) return 0;
+  if (p.G != 1 || p.N > 65535 || p.ntaps < 1) return 0;
+  const bool ci1 = p.Cig == 1;
+  const bool co1 = !ci1 && p.Cog == 1 && p.si == 1 && p.so == 1;
+  if (!ci1 && !co1) return 0;
+  int min_off = p.off[0], max_off = p.off[0];
+  for (int t = 0; t < p.ntaps; ++t) {
+    min_off = min(min_off, p.off[t]);
+    max_off = max(max_off, p.off[t]);
+    if (p.yoff[t] != p.yoff[0]) return 0;
+  }
+  const int span = max_off - min_off;
+  if ((C1_ROWS - 1) * p.si + span + 1 > C1_SMEM || C1_ROWS + span > C1_SMEM) return 0;
+  const int C = ci1 ? p.Cog : p.Cig;
   int cw = 32;
-  while (cw < 256 && cw < p.Cog) cw <<= 1;
-  const int64_t Mtot = (int64_t)p.N * p.nq;
-  dim3 grid((unsigned)((Mtot + CI1_ROWS - 1) / CI1_ROWS), (unsigned)((p.Cog + cw - 1) / cw));
-  const bool yb = p.y_dtype == ARTIC_BF16;
-  for (int tap0 = 0; tap0 < p.ntaps; tap0 += CI1_TAPS) {
-    if (p.dtype == ARTIC_BF16) {
-      if (yb) tapwgrad_ci1_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(p, cw, tap0);
-      else tapwgrad_ci1_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(p, cw, tap0);
-    } else {
-      if (yb) tapwgrad_ci1_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(p, cw, tap0);
-      else tapwgrad_ci1_kernel<float, float><<<grid, 256, 0, st>>>(p, cw, tap0);
-    }
+  while (cw < 256 && cw < C) cw <<= 1;
+  const int rows = ci1 ? p.nq : p.nq + span;
+  dim3 grid((unsigned)((rows + C1_ROWS - 1) / C1_ROWS), (unsigned)p.N, (unsigned)((C + cw - 1) / cw));
+  const bool yb = p.y_dtype == ARTIC_BF16, xb = p.dtype == ARTIC_BF16;
+  for (int tap0 = 0; tap0 < p.ntaps; tap0 += C1_TAPS) {
+#define ARTIC_C1_LAUNCH(K)                                                                                        \
+  do {                                                                                                            \
+    if (xb && yb) K<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(p, cw, tap0, min_off, span);               \
+    else if (xb) K<__nv_bfloat16, float><<<grid, 256, 0, st>>>(p, cw, tap0, min_off, span);                        \
+    else if (yb) K<float, __nv_bfloat16><<<grid, 256, 0, st>>>(p, cw, tap0, min_off, span);                        \
+    else K<float, float><<<grid, 256, 0, st>>>(p, cw, tap0, min_off, span);                                        \
+  } while (0)
+    if (ci1) ARTIC_C1_LAUNCH(tapwgrad_ci1_kernel);
+    else ARTIC_C1_LAUNCH(tapwgrad_co1_kernel);
+#undef ARTIC_C1_LAUNCH
   }
   return 1;
 }

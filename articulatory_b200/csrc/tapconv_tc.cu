@@ -349,11 +349,12 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   tc::EncodeTiledFn enc = tc::encode_fn();
   if (enc == nullptr) return 0;
 
-  tc::Plan pl;
-  memset(&pl, 0, sizeof(pl));
+  const int budget = tc::max_smem() - 1024 /*alignment slack*/;
+  auto make_plan = [&](tc::Plan& pl, int bn_req, int mt_req) -> bool {
+    memset(&pl, 0, sizeof(pl));
   int min_off = p.off[0], max_off = p.off[0];
   for (int t = 1; t < p.ntaps; ++t) { min_off = min(min_off, p.off[t]); max_off = max(max_off, p.off[t]); }
-  if (max_off - min_off > 160 * p.si || min_off < -(1 << 20)) return 0;   // also rejects the "no tap on this phase" marker
+  if (max_off - min_off > 160 * p.si || min_off < -(1 << 20)) return false;   // also rejects the "no tap on this phase" marker
   pl.min_off = min_off;
   pl.n_ph = p.si;
   int span = 0;                                       // largest row shift inside a phase panel
@@ -366,15 +367,13 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   pl.row_bytes = pl.kch * 2;
   pl.n_kc = p.Cig / pl.kch;
   pl.layout_type = pl.row_bytes == 128 ? 2 : pl.row_bytes == 64 ? 4 : 6;
-  pl.bn = (p.Cog % 256 == 0) ? 256 : (p.Cog % 128 == 0) ? 128 : (p.Cog % 64 == 0) ? 64 : 32;
-  if (tc::g_debug[2] > 0 && p.Cog % tc::g_debug[2] == 0) pl.bn = tc::g_debug[2];
+  pl.bn = bn_req;
   pl.n_nt = p.Cog / pl.bn;
-  int mt = 512 / (2 * pl.bn);
+  int mt = 512 / pl.bn;   // up to the whole TMEM (single-buffered accumulator when > 256 columns)
   if (mt < 1) mt = 1;
   if (mt > 4) mt = 4;
-  if (tc::g_debug[3] > 0) mt = tc::g_debug[3];
+  if (mt_req > 0 && mt_req < mt) mt = mt_req;
   pl.w_stage_bytes = ((pl.bn * pl.row_bytes + 1023) / 1024) * 1024;
-  const int budget = tc::max_smem() - 1024 /*alignment slack*/;
   {  // keep two activation stages + a few weight stages within shared memory
     auto a_bytes = [&](int m) { return p.si * ((((m * 128 + span + 64) * pl.row_bytes + 1023) / 1024) * 1024); };
     while (mt > 1 && 2 * a_bytes(mt) + 3 * pl.w_stage_bytes > budget) --mt;
@@ -406,7 +405,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   pl.acc_stages = (2 * mt * pl.bn <= 512) ? 2 : 1;
   int cols = pl.acc_stages * mt * pl.bn;
   pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-  if (cols > 512) return 0;
+  if (cols > 512) return false;
   pl.panel_bytes = ((a_rows * pl.row_bytes + 1023) / 1024) * 1024;
   pl.a_stage_bytes = pl.n_ph * pl.panel_bytes;
   pl.n_as = 2;
@@ -414,14 +413,35 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   if (rem < 2 * pl.w_stage_bytes) {
     pl.n_as = 1;
     rem = budget - pl.a_stage_bytes;
-    if (rem < 2 * pl.w_stage_bytes) return 0;
+    if (rem < 2 * pl.w_stage_bytes) return false;
   }
   pl.n_ws = rem / pl.w_stage_bytes;
   if (pl.n_ws > tc::MAX_WS) pl.n_ws = tc::MAX_WS;
   if (pl.n_ws > 2 && pl.n_as < tc::MAX_AS && pl.n_kc > 2 && rem - pl.n_ws * pl.w_stage_bytes >= pl.a_stage_bytes) pl.n_as += 1;
   const int64_t total = (int64_t)pl.n_mt * pl.n_nt * p.G;
-  if (total > (1 << 30)) return 0;
+  if (total > (1 << 30)) return false;
   pl.total_tiles = (int)total;
+    return true;
+  };
+  // Tile shape: minimise (waves over the SMs) x (MMA work per tile), lightly penalising narrow
+  // channel tiles (they re-stage the activation tile more often).
+  tc::Plan pl, cand;
+  double best = -1.0;
+  const int bns[4] = {256, 128, 64, 32};
+  for (int bi = 0; bi < 4; ++bi) {
+    const int bn = bns[bi];
+    if (p.Cog % bn != 0) continue;
+    if (tc::g_debug[2] > 0 && bn != tc::g_debug[2]) continue;
+    for (int mt_req = 4; mt_req >= 1; --mt_req) {
+      if (tc::g_debug[3] > 0 && mt_req != tc::g_debug[3]) continue;
+      if (!make_plan(cand, bn, mt_req)) continue;
+      if (cand.mt != mt_req && mt_req != 4) continue;   // already evaluated at a larger request
+      const double waves = (double)((cand.total_tiles + num_sms() - 1) / num_sms());
+      const double cost = waves * cand.mt * bn * (1.0 + 24.0 / bn) * (cand.acc_stages == 2 ? 1.0 : 1.15);
+      if (best < 0 || cost < best) { best = cost; pl = cand; }
+    }
+  }
+  if (best < 0) return 0;
   pl.base_offset_mode = tc::g_debug[0];
 
   // ---- tensor maps

@@ -335,29 +335,35 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   const int align = 2;  // keeps every TMA destination 128-byte aligned for 64-byte rows
   const int lpad = ((p.nq + span_rows + align - 1) / align) * align;
   pl.packed = (p.N >= 2 && lpad <= 64 && lpad * si <= 256) ? 1 : 0;
-  if (pl.packed) {
-    pl.seg_pitch = lpad;
-    pl.seg_per_chunk = 128 / lpad;
-    if (pl.seg_per_chunk > p.N) pl.seg_per_chunk = p.N;
-    pl.kp = ((pl.seg_per_chunk * lpad + 15) / 16) * 16;
-    pl.n_chunks = (p.N + pl.seg_per_chunk - 1) / pl.seg_per_chunk;
-    pl.x_rows = pl.kp + ext + 8;
-  } else {
-    pl.kp = 64;
-    pl.chunks_per_seq = (p.nq + pl.kp - 1) / pl.kp;
-    pl.n_chunks = p.N * pl.chunks_per_seq;
-    pl.boxr = si == 1 ? 64 : 32;
-    pl.nxb = (pl.kp + span_rows + pl.boxr - 1) / pl.boxr;
-    pl.x_rows = max(pl.nxb * pl.boxr, pl.kp + ext + 8);
-  }
   if (ext > 1024) return 0;
-  pl.x_panel_bytes = ((pl.x_rows * pl.xrb + 1023) / 1024) * 1024;
-  pl.y_panel_bytes = ((pl.kp * pl.yrb + 1023) / 1024) * 1024;
-  pl.stage_bytes = pl.n_ph * pl.nxp * pl.x_panel_bytes + pl.nyp * pl.y_panel_bytes;
+  const int budget = tc::wg_max_smem() - 1024;
+  // positions per chunk: shrink until at least 3 stages fit in shared memory
+  int kp_cap = 128;
+  for (;;) {
+    if (pl.packed) {
+      pl.seg_pitch = lpad;
+      pl.seg_per_chunk = max(1, kp_cap / lpad);
+      if (pl.seg_per_chunk > p.N) pl.seg_per_chunk = p.N;
+      pl.kp = ((pl.seg_per_chunk * lpad + 15) / 16) * 16;
+      pl.n_chunks = (p.N + pl.seg_per_chunk - 1) / pl.seg_per_chunk;
+      pl.x_rows = pl.kp + ext + 8;
+    } else {
+      pl.kp = min(kp_cap, 64);
+      pl.chunks_per_seq = (p.nq + pl.kp - 1) / pl.kp;
+      pl.n_chunks = p.N * pl.chunks_per_seq;
+      pl.boxr = si == 1 ? min(64, pl.kp) : 32;
+      pl.nxb = (pl.kp + span_rows + pl.boxr - 1) / pl.boxr;
+      pl.x_rows = max(pl.nxb * pl.boxr, pl.kp + ext + 8);
+    }
+    pl.x_panel_bytes = ((pl.x_rows * pl.xrb + 1023) / 1024) * 1024;
+    pl.y_panel_bytes = ((pl.kp * pl.yrb + 1023) / 1024) * 1024;
+    pl.stage_bytes = pl.n_ph * pl.nxp * pl.x_panel_bytes + pl.nyp * pl.y_panel_bytes;
+    pl.n_stages = budget / pl.stage_bytes;
+    if (pl.n_stages >= 3 || kp_cap <= 32) break;
+    kp_cap /= 2;
+  }
   pl.a_lbo = pl.mci == 128 ? pl.x_panel_bytes : slot_rows * pl.xrb;
   if ((pl.a_lbo >> 4) > 0x3fff || (pl.y_panel_bytes >> 4) > 0x3fff) return 0;
-  const int budget = tc::wg_max_smem() - 1024;
-  pl.n_stages = budget / pl.stage_bytes;
   if (pl.n_stages < 2) return 0;
   if (pl.n_stages > tc::WG_MAX_STAGES) pl.n_stages = tc::WG_MAX_STAGES;
   const int64_t base = (int64_t)pl.n_nt * pl.n_mb * pl.n_tg * p.G;

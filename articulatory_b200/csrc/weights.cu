@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) prep_permute_kernel(const float* __restrict__ v, const float* __restrict__ scale,
                                                            int64_t row_len, int K, int G, int A, int B, int64_t sk,
-                                                           int64_t sg, int64_t sa, int64_t sb, T* __restrict__ out) {
+                                                           int64_t sg, int64_t sa, int64_t sb, int mg,
+                                                           T* __restrict__ out) {
   const int64_t total = (int64_t)K * G * A * B;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(o % B);
@@ -37,7 +38,11 @@ __global__ void __launch_bounds__(256) prep_permute_kernel(const float* __restri
     const int64_t src = k * sk + g * sg + a * sa + b * sb;
     float w = v[src];
     if (scale != nullptr) w *= scale[src / row_len];
-    st_f(out + o, w);
+    // merge > 1: block-diagonal layout [K][G/mg][mg*A][mg*B] (off-diagonal blocks stay zero)
+    const int64_t oo = mg == 1 ? o
+                               : ((((int64_t)k * (G / mg) + g / mg) * (mg * A) + (g % mg) * A + a) * (int64_t)(mg * B) +
+                                  (g % mg) * B + b);
+    st_f(out + oo, w);
   }
 }
 
@@ -51,7 +56,7 @@ struct Unperm {
 
 __global__ void __launch_bounds__(256) unprep_kernel(const float* __restrict__ dWp, const float* __restrict__ v,
                                                      const float* __restrict__ scale, int rows, int64_t row_len, int G,
-                                                     int A, int B, Unperm up, float* __restrict__ dv,
+                                                     int A, int B, int mg, Unperm up, float* __restrict__ dv,
                                                      float* __restrict__ dg) {
   __shared__ float red[32];
   __shared__ float s_dot;
@@ -64,7 +69,9 @@ __global__ void __launch_bounds__(256) unprep_kernel(const float* __restrict__ d
       idx[up.dim_id[i]] = (int)(rem / up.stride[i]);
       rem -= (int64_t)idx[up.dim_id[i]] * up.stride[i];
     }
-    return (((int64_t)idx[0] * G + idx[1]) * A + idx[2]) * B + idx[3];
+    if (mg == 1) return (((int64_t)idx[0] * G + idx[1]) * A + idx[2]) * B + idx[3];
+    return (((int64_t)idx[0] * (G / mg) + idx[1] / mg) * (mg * A) + (idx[1] % mg) * A + idx[2]) * (int64_t)(mg * B) +
+           (idx[1] % mg) * B + idx[3];
   };
   if (scale == nullptr) {
     for (int64_t e = threadIdx.x; e < row_len; e += blockDim.x) dv[e0 + e] += dWp[perm(e0 + e)];
@@ -113,8 +120,9 @@ using namespace artic;
 
 extern "C" int artic_weight_prep(const float* v, const float* g, float* scale, int32_t rows, int64_t row_len,
                                  int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sg, int64_t sa,
-                                 int64_t sb, void* out, int32_t dtype, void* stream) {
+                                 int64_t sb, int32_t merge, void* out, int32_t dtype, void* stream) {
   ARTIC_CHECK_ARG(v && out, "null pointer");
+  ARTIC_CHECK_ARG(merge >= 1 && G % merge == 0, "merge must divide the group count");
   ARTIC_CHECK_ARG(g == nullptr || scale != nullptr, "scale buffer required with weight norm");
   ARTIC_CHECK_ARG(rows >= 1 && row_len >= 1 && K >= 1 && G >= 1 && A >= 1 && B >= 1, "bad dims");
   ARTIC_CHECK_ARG((int64_t)rows * row_len == (int64_t)K * G * A * B, "element count mismatch");
@@ -126,10 +134,10 @@ extern "C" int artic_weight_prep(const float* v, const float* g, float* scale, i
   if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
   const float* sc = g != nullptr ? scale : nullptr;
   if (dtype == ARTIC_BF16)
-    prep_permute_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(v, sc, row_len, K, G, A, B, sk, sg, sa, sb,
+    prep_permute_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(v, sc, row_len, K, G, A, B, sk, sg, sa, sb, merge,
                                                                 reinterpret_cast<__nv_bfloat16*>(out));
   else
-    prep_permute_kernel<float><<<blocks, 256, 0, st>>>(v, sc, row_len, K, G, A, B, sk, sg, sa, sb,
+    prep_permute_kernel<float><<<blocks, 256, 0, st>>>(v, sc, row_len, K, G, A, B, sk, sg, sa, sb, merge,
                                                         reinterpret_cast<float*>(out));
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
@@ -137,8 +145,9 @@ extern "C" int artic_weight_prep(const float* v, const float* g, float* scale, i
 
 extern "C" int artic_weight_unprep(const float* dWp, const float* v, const float* g, const float* scale, int32_t rows,
                                    int64_t row_len, int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sg,
-                                   int64_t sa, int64_t sb, float* dv, float* dg, void* stream) {
+                                   int64_t sa, int64_t sb, int32_t merge, float* dv, float* dg, void* stream) {
   ARTIC_CHECK_ARG(dWp && v && dv, "null pointer");
+  ARTIC_CHECK_ARG(merge >= 1 && G % merge == 0, "merge must divide the group count");
   ARTIC_CHECK_ARG(g == nullptr || (scale != nullptr && dg != nullptr), "scale and dg required with weight norm");
   ARTIC_CHECK_ARG((int64_t)rows * row_len == (int64_t)K * G * A * B, "element count mismatch");
   Unperm up;
@@ -161,7 +170,7 @@ extern "C" int artic_weight_unprep(const float* dWp, const float* v, const float
     expect *= ext[up.dim_id[i]];
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  unprep_kernel<<<rows, 256, 0, st>>>(dWp, v, g != nullptr ? scale : nullptr, rows, row_len, G, A, B, up, dv, dg);
+  unprep_kernel<<<rows, 256, 0, st>>>(dWp, v, g != nullptr ? scale : nullptr, rows, row_len, G, A, B, merge, up, dv, dg);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
 }

@@ -113,6 +113,16 @@ class ConvLayer:
 
     def __init__(self, spec: ConvSpec, name: str, in_code: int, out_code: int):
         self.spec, self.name, self.in_code, self.out_code = spec, name, in_code, out_code
+        # Narrow grouped convs (< 32 channels per group, e.g. the scale discriminator's 128->256
+        # g16 layer with 8 -> 16 channels per group) would starve the tensor-core tiles: in the
+        # bf16 mode `mg` groups are merged into one super-group whose weight is block-diagonal
+        # (artic_weight_prep `merge`), trading mg x redundant MACs for full MMA tiles.
+        mg = 1
+        if in_code == BF16 and out_code == BF16 and spec.groups > 1:
+            while (spec.cig * mg < 32 or spec.cog * mg < 32) and spec.groups % (2 * mg) == 0:
+                mg *= 2
+        self.mg = mg
+        self.kG, self.kcig, self.kcog = spec.groups // mg, spec.cig * mg, spec.cog * mg   # kernel-facing dims
         self.v = self.g = self.b = None          # torch parameters (fp32, device)
         self.Wf = self.Wb = self.scale = None    # prepared weights
         self.dWf = None                          # fp32 wgrad accumulator, 'fwd' layout
@@ -152,28 +162,28 @@ class ConvLayer:
             code = self.in_code if direction == "fwd" else self.out_code
             buf = self.Wf if direction == "fwd" else self.Wb
             if buf is None or buf.dtype != TORCH_DTYPE[code]:
-                buf = torch.empty((s.k, s.groups, A, B), dtype=TORCH_DTYPE[code], device=dev)
+                buf = torch.zeros((s.k, self.kG, A * self.mg, B * self.mg), dtype=TORCH_DTYPE[code], device=dev)
                 if direction == "fwd":
                     self.Wf = buf
                 else:
                     self.Wb = buf
             call("artic_weight_prep", ptr(self.v), ptr(self.g), ptr(self.scale), rows, row_len,
-                 s.k, s.groups, A, B, sk, sg, sa, sb, ptr(buf), code)
+                 s.k, s.groups, A, B, sk, sg, sa, sb, self.mg, ptr(buf), code)
 
     # ---- compute -------------------------------------------------------------
     def forward(self, X: SeqT, Y=None, Y2=None, **epi):
         s = self.spec
-        tapconv(s.fwd_launches(X.L), X, self.Wf, s.groups, s.cig, s.cog, Y=Y, Y2=Y2, bias=self.b, Wt=self.Wb, **epi)
+        tapconv(s.fwd_launches(X.L), X, self.Wf, self.kG, self.kcig, self.kcog, Y=Y, Y2=Y2, bias=self.b, Wt=self.Wb, **epi)
 
     def dgrad(self, dY: SeqT, dX: Optional[SeqT] = None, dX2: Optional[SeqT] = None, **epi):
         s = self.spec
         lin = (dX if dX is not None else dX2).L
-        tapconv(s.dgrad_launches(lin), dY, self.Wb, s.groups, s.cog, s.cig, Y=dX, Y2=dX2, Wt=self.Wf, **epi)
+        tapconv(s.dgrad_launches(lin), dY, self.Wb, self.kG, self.kcog, self.kcig, Y=dX, Y2=dX2, Wt=self.Wf, **epi)
 
     def zero_wgrad(self):
         if self.dWf is None:
             s = self.spec
-            self.dWf = torch.zeros((s.k, s.groups, s.cig, s.cog), dtype=torch.float32, device=self.v.device)
+            self.dWf = torch.zeros((s.k, self.kG, self.kcig, self.kcog), dtype=torch.float32, device=self.v.device)
         else:
             self.dWf.zero_()
 
@@ -184,7 +194,7 @@ class ConvLayer:
         p = _lib.TapWgrad()
         p.X, p.dY, p.dW = ptr(X.t), ptr(dY.t), ptr(self.dWf)
         p.x, p.y = X.seq(), dY.seq()
-        p.N, p.G, p.Cig, p.Cog = X.N, s.groups, s.cig, s.cog
+        p.N, p.G, p.Cig, p.Cog = X.N, self.kG, self.kcig, self.kcog
         p.q0, p.nq, p.si, p.so = L.q0, L.nq, L.si, L.so
         p.ntaps = len(L.off)
         for i in range(p.ntaps):
@@ -205,7 +215,7 @@ class ConvLayer:
         else:
             dv, dg = grads[n + ".weight"], None
         call("artic_weight_unprep", ptr(self.dWf), ptr(self.v), ptr(self.g), ptr(self.scale), rows, row_len,
-             s.k, s.groups, A, B, sk, sg, sa, sb, ptr(dv), ptr(dg))
+             s.k, s.groups, A, B, sk, sg, sa, sb, self.mg, ptr(dv), ptr(dg))
 
 
 def _zero_grads_like(layers: List[ConvLayer]) -> Dict[str, torch.Tensor]:

@@ -124,23 +124,27 @@ int artic_colsum(const void* dY, const artic_seq_t* y, int32_t N, int32_t C, int
  * models/hifigan.py:268-278,430-438 — w = g * v / ||v||, norm over all dims but 0 —
  * plus the relayout the kernels want).  Source: a torch weight viewed as
  * [rows][row_len] fp32 with logical dims (K taps, G groups, A in-channels, B out-channels)
- * at element strides (sk, sg, sa, sb).  Output: [K][G][A][B] in `dtype`.
+ * at element strides (sk, sg, sa, sb).  Output: [K][G][A][B] in `dtype`; with merge = m > 1
+ * (m divides G) the output is the BLOCK-DIAGONAL layout [K][G/m][m*A][m*B] in which m narrow
+ * groups form one super-group (only the diagonal blocks are written: zero the buffer once),
+ * so that grouped convs with < 32 channels per group still fill tensor-core tiles.
  * g == NULL means a plain (un-normalised) weight.  `scale` (2*rows floats, may be NULL
  * iff g == NULL) receives g/||v|| in [0,rows) and ||v|| in [rows,2*rows) for the backward.
  */
 int artic_weight_prep(const float* v, const float* g, float* scale, int32_t rows, int64_t row_len,
                       int32_t K, int32_t G, int32_t A, int32_t B,
-                      int64_t sk, int64_t sg, int64_t sa, int64_t sb,
+                      int64_t sk, int64_t sg, int64_t sa, int64_t sb, int32_t merge,
                       void* out, int32_t dtype, void* stream);
 
 /*
- * Backward of artic_weight_prep: dWp is fp32 [K][G][A][B].  Writes dv (torch layout,
+ * Backward of artic_weight_prep: dWp is fp32 [K][G][A][B] (or the block-diagonal layout for
+ * merge > 1, of which only the diagonal blocks are read).  Writes dv (torch layout,
  * fp32) and dg (rows floats; NULL for a plain weight, in which case dv = permuted dWp).
  * Results are ADDED to dv / dg (autograd accumulation semantics); zero them first.
  */
 int artic_weight_unprep(const float* dWp, const float* v, const float* g, const float* scale,
                         int32_t rows, int64_t row_len, int32_t K, int32_t G, int32_t A, int32_t B,
-                        int64_t sk, int64_t sg, int64_t sa, int64_t sb,
+                        int64_t sk, int64_t sg, int64_t sa, int64_t sb, int32_t merge,
                         float* dv, float* dg, void* stream);
 
 /* ---- small fused elementwise ops on the path ---------------------------------------- */
