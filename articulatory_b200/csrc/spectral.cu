@@ -18,25 +18,25 @@ __device__ __forceinline__ int reflect_index(int t, int T) {
 
 // Radix-2 Stockham autosort FFT (forward, e^{-i...}), natural-order in and out.
 // Source is (r0,i0); returns 0 if the result ends in (r0,i0), 1 if in (r1,i1).
-__device__ __forceinline__ int fft_stockham(float* r0, float* i0, float* r1, float* i1, const float* twr,
-                                            const float* twi, int N) {
+template <typename T, typename TW>
+__device__ __forceinline__ int fft_stockham(T* r0, T* i0, T* r1, T* i1, const TW* twr, const TW* twi, int N) {
   int cur = 0;
   const int half = N >> 1;
   for (int s = 1; s < N; s <<= 1) {
-    const float* xr = cur ? r1 : r0;
-    const float* xi = cur ? i1 : i0;
-    float* yr = cur ? r0 : r1;
-    float* yi = cur ? i0 : i1;
+    const T* xr = cur ? r1 : r0;
+    const T* xi = cur ? i1 : i0;
+    T* yr = cur ? r0 : r1;
+    T* yi = cur ? i0 : i1;
     for (int b = threadIdx.x; b < half; b += blockDim.x) {
       const int q = b & (s - 1);
       const int ps = b - q;
-      const float ar = xr[b], ai = xi[b];
-      const float br = xr[b + half], bi = xi[b + half];
-      const float wr = twr[ps], wi = twi[ps];
+      const T ar = xr[b], ai = xi[b];
+      const T br = xr[b + half], bi = xi[b + half];
+      const T wr = (T)twr[ps], wi = (T)twi[ps];
       const int o = q + 2 * ps;
       yr[o] = ar + br;
       yi[o] = ai + bi;
-      const float dr = ar - br, di = ai - bi;
+      const T dr = ar - br, di = ai - bi;
       yr[o + s] = dr * wr - di * wi;
       yi[o + s] = dr * wi + di * wr;
     }
@@ -46,6 +46,14 @@ __device__ __forceinline__ int fft_stockham(float* r0, float* i0, float* r1, flo
   return cur;
 }
 
+__device__ __forceinline__ void make_twiddles(double* twr, double* twi, int N) {
+  for (int k = threadIdx.x; k < (N >> 1); k += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * (double)k / (double)N, &s, &c);
+    twr[k] = c;
+    twi[k] = -s;
+  }
+}
 __device__ __forceinline__ void make_twiddles(float* twr, float* twi, int N) {
   for (int k = threadIdx.x; k < (N >> 1); k += blockDim.x) {
     float s, c;
@@ -56,18 +64,19 @@ __device__ __forceinline__ void make_twiddles(float* twr, float* twi, int N) {
 }
 
 // Load frame f of (x, y) into (re, im) with window and reflect padding.
+template <typename T>
 __device__ __forceinline__ void load_frame(const float* __restrict__ x, const float* __restrict__ y,
-                                           const float* __restrict__ window, const FrameGeom& g, int f, float* re,
-                                           float* im) {
+                                           const float* __restrict__ window, const FrameGeom& g, int f, T* re,
+                                           T* im) {
   const int start = f * g.hop - (g.N >> 1);
   for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
-    float a = 0.f, b = 0.f;
+    T a = 0, b = 0;
     const int wn = n - g.lpad;
     if (wn >= 0 && wn < g.win) {
-      const float w = __ldg(window + wn);
+      const T w = (T)__ldg(window + wn);
       const int t = reflect_index(start + n, g.T);
-      a = w * __ldg(x + t);
-      b = w * __ldg(y + t);
+      a = w * (T)__ldg(x + t);
+      b = w * (T)__ldg(y + t);
     }
     re[n] = a;
     im[n] = b;
@@ -75,14 +84,14 @@ __device__ __forceinline__ void load_frame(const float* __restrict__ x, const fl
 }
 
 // Split Z = FFT(x + i y) into the two Hermitian spectra at bin k (0 <= k <= N/2).
-__device__ __forceinline__ void split_bin(const float* zr, const float* zi, int k, int N, float& xr, float& xi,
-                                          float& yr, float& yi) {
+template <typename T>
+__device__ __forceinline__ void split_bin(const T* zr, const T* zi, int k, int N, T& xr, T& xi, T& yr, T& yi) {
   const int k2 = (N - k) & (N - 1);
-  const float ar = zr[k], ai = zi[k], br = zr[k2], bi = zi[k2];
-  xr = 0.5f * (ar + br);
-  xi = 0.5f * (ai - bi);
-  yr = 0.5f * (ai + bi);
-  yi = -0.5f * (ar - br);
+  const T ar = zr[k], ai = zi[k], br = zr[k2], bi = zi[k2];
+  xr = (T)0.5 * (ar + br);
+  xi = (T)0.5 * (ai - bi);
+  yr = (T)0.5 * (ai + bi);
+  yi = (T)-0.5 * (ar - br);
 }
 
 // smem layout (floats): r0[N] i0[N] r1[N] i1[N] twr[N/2] twi[N/2] red[32] extra[...]
@@ -129,10 +138,11 @@ __global__ void __launch_bounds__(512) stft_loss_fwd_kernel(const float* __restr
 
 // Adjoint of the framing + rFFT: the caller has written conj(G[k]) for k <= N/2 (zeros above)
 // into (gr, gi); result dx_frame[n] = w[n] * Re(FFT(conj G))[n] is overlap-added into dx.
-__device__ __forceinline__ void adjoint_to_dx(float* gr, float* gi, float* orr, float* oi, const Smem& sm,
+template <typename TW>
+__device__ __forceinline__ void adjoint_to_dx(float* gr, float* gi, float* orr, float* oi, const TW* twr, const TW* twi,
                                               const FrameGeom& g, const float* __restrict__ window, int f,
                                               float* __restrict__ dx) {
-  const int cur = fft_stockham(gr, gi, orr, oi, sm.twr, sm.twi, g.N);
+  const int cur = fft_stockham(gr, gi, orr, oi, twr, twi, g.N);
   const float* rr = cur ? orr : gr;
   const int start = f * g.hop - (g.N >> 1);
   for (int wn = threadIdx.x; wn < g.win; wn += blockDim.x) {
@@ -142,45 +152,52 @@ __device__ __forceinline__ void adjoint_to_dx(float* gr, float* gi, float* orr, 
   }
 }
 
+// The forward transform of the backward pass runs in fp64: the log-magnitude gradient scales
+// like 1/|X_k|^2, so the absolute rounding error of an fp32 FFT (~1e-7 * ||frame||) at the few
+// near-silent bins dominates the whole gradient (measured 1.9e-3 relative vs 2e-4 with an fp64
+// forward transform; torch's fp32 path sits at ~1e-4).  The adjoint transform stays fp32.
+// smem (doubles): r0[N] i0[N] r1[N] i1[N] twr[N/2] twi[N/2]; the idle double pair is re-used as
+// four fp32 arrays for the adjoint.
 __global__ void __launch_bounds__(512) stft_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                             FrameGeom g, const float* __restrict__ window, float eps,
                                                             const float* __restrict__ sums, float w_sc, float w_mag,
                                                             float inv_numel, float* __restrict__ dx) {
-  extern __shared__ __align__(16) float smem_f[];
-  Smem sm(smem_f, g.N);
+  extern __shared__ __align__(16) double smem_d[];
+  const int N = g.N;
+  double *r0 = smem_d, *i0 = r0 + N, *r1 = i0 + N, *i1 = r1 + N, *twr = i1 + N, *twi = twr + (N >> 1);
   const int f = blockIdx.x, b = blockIdx.y;
-  make_twiddles(sm.twr, sm.twi, g.N);
-  load_frame(x + (int64_t)b * g.T, y + (int64_t)b * g.T, window, g, f, sm.r0, sm.i0);
+  make_twiddles(twr, twi, N);
+  load_frame(x + (int64_t)b * g.T, y + (int64_t)b * g.T, window, g, f, r0, i0);
   __syncthreads();
-  const int cur = fft_stockham(sm.r0, sm.i0, sm.r1, sm.i1, sm.twr, sm.twi, g.N);
-  const float* zr = cur ? sm.r1 : sm.r0;
-  const float* zi = cur ? sm.i1 : sm.i0;
-  float* gr = cur ? sm.r0 : sm.r1;  // the other buffer
-  float* gi = cur ? sm.i0 : sm.i1;
+  const int cur = fft_stockham(r0, i0, r1, i1, twr, twi, N);
+  const double* zr = cur ? r1 : r0;
+  const double* zi = cur ? i1 : i0;
+  float* fbuf = reinterpret_cast<float*>(cur ? r0 : r1);  // the idle pair: 2N doubles = 4N floats
+  float *gr = fbuf, *gi = fbuf + N, *orr = fbuf + 2 * N, *oi = fbuf + 3 * N;
   const float S0 = sums[0], S1 = sums[1];
   const float c_sc = (S0 > 0.f && S1 > 0.f) ? w_sc * rsqrtf(S0) * rsqrtf(S1) : 0.f;
   const float c_mag = w_mag * inv_numel;
-  const int half = g.N >> 1;
+  const int half = N >> 1;
   for (int k = threadIdx.x; k <= half; k += blockDim.x) {
-    float xr, xi, yr, yi;
-    split_bin(zr, zi, k, g.N, xr, xi, yr, yi);
-    const float px = xr * xr + xi * xi;
-    const float xm = sqrtf(fmaxf(px, eps));
-    const float ym = sqrtf(fmaxf(yr * yr + yi * yi, eps));
+    double xr, xi, yr, yi;
+    split_bin(zr, zi, k, N, xr, xi, yr, yi);
+    const double px = xr * xr + xi * xi;
+    const float xm = (float)sqrt(fmax(px, (double)eps));
+    const float ym = (float)sqrt(fmax(yr * yr + yi * yi, (double)eps));
     // d/dxm [ w_sc * sqrt(S0)/sqrt(S1) + w_mag/numel * |ln ym - ln xm| ]
     const float dl = logf(ym) - logf(xm);
     float gk = c_sc * (xm - ym) - c_mag * (dl > 0.f ? 1.f : (dl < 0.f ? -1.f : 0.f)) / xm;
-    if (!(px >= eps)) gk = 0.f;  // clamp(min=eps) passes gradient only where px >= eps
+    if (!(px >= (double)eps)) gk = 0.f;  // clamp(min=eps) passes gradient only where px >= eps
     const float sc = gk / xm;
-    gr[k] = sc * xr;
-    gi[k] = -sc * xi;  // conj
+    gr[k] = sc * (float)xr;
+    gi[k] = -sc * (float)xi;  // conj
     if (k > 0 && k < half) {
-      gr[g.N - k] = 0.f;
-      gi[g.N - k] = 0.f;
+      gr[N - k] = 0.f;
+      gi[N - k] = 0.f;
     }
   }
   __syncthreads();
-  adjoint_to_dx(gr, gi, const_cast<float*>(zr), const_cast<float*>(zi), sm, g, window, f, dx + (int64_t)b * g.T);
+  adjoint_to_dx(gr, gi, orr, oi, twr, twi, g, window, f, dx + (int64_t)b * g.T);
 }
 
 // ---- mel ---------------------------------------------------------------------------
@@ -280,7 +297,7 @@ __global__ void __launch_bounds__(512) mel_loss_kernel(const float* __restrict__
       }
     }
     __syncthreads();
-    adjoint_to_dx(ax, ay, const_cast<float*>(zr), const_cast<float*>(zi), sm, g, window, f, dx + (int64_t)b * g.T);
+    adjoint_to_dx(ax, ay, const_cast<float*>(zr), const_cast<float*>(zi), sm.twr, sm.twi, g, window, f, dx + (int64_t)b * g.T);
   }
 }
 
@@ -336,7 +353,7 @@ extern "C" int artic_stft_loss_bwd(const float* x, const float* y, int32_t B, in
   ARTIC_CHECK_ARG(check_geom(B, T, n_fft, hop, win_length), "unsupported STFT geometry");
   if (B == 0) return ARTIC_OK;
   FrameGeom g{T, n_fft, hop, win_length, (n_fft - win_length) / 2};
-  const size_t sb = smem_bytes(n_fft, 0);
+  const size_t sb = sizeof(double) * (size_t)5 * n_fft;
   int rc = ensure_smem(stft_loss_bwd_kernel, sb);
   if (rc) return rc;
   const int frames = 1 + T / hop;
