@@ -53,6 +53,23 @@ class AdamHyper(C.Structure):
                 ("milestones", C.c_int32 * 8)]
 
 
+class WDesc(C.Structure):
+    _fields_ = [("v", C.c_void_p), ("g", C.c_void_p), ("scale", C.c_void_p),
+                ("out_f", C.c_void_p), ("out_b", C.c_void_p),
+                ("dWp", C.c_void_p), ("dv", C.c_void_p), ("dg", C.c_void_p),
+                ("row_len", C.c_int64), ("sk", C.c_int64), ("sg", C.c_int64), ("sa", C.c_int64), ("sb", C.c_int64),
+                ("rows", C.c_int32), ("K", C.c_int32), ("G", C.c_int32), ("A", C.c_int32), ("B", C.c_int32),
+                ("merge", C.c_int32), ("a_pad", C.c_int32), ("b_pad", C.c_int32),
+                ("dtype_f", C.c_int32), ("dtype_b", C.c_int32)]
+
+
+def upload_structs(items, device):
+    """Array of ctypes structs -> device uint8 tensor (descriptor tables of the batched kernels)."""
+    arr = (type(items[0]) * len(items))(*items)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device)
+
+
 _i32, _i64, _f, _p = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 #: every exported symbol of include/artic.h: name -> (restype, argtypes)
@@ -61,13 +78,14 @@ SIGNATURES = {
     "artic_arch": (C.c_char_p, []),
     "artic_last_error": (C.c_char_p, []),
     "artic_debug_set": (C.c_int, [C.c_int, C.c_int]),
+    "artic_debug_buffer": (C.c_int, [_p]),
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
     "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),
-    "artic_weight_prep": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _p, _i32, _p]),
-    "artic_weight_unprep": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _p, _p, _p]),
-    "artic_gen_input": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
-    "artic_gen_input_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "artic_weights_prep": (C.c_int, [_p, _i32, _i32, _p]),
+    "artic_weights_unprep": (C.c_int, [_p, _i32, _i32, _p]),
+    "artic_gen_input": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "artic_gen_input_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "artic_mean3_act": (C.c_int, [_p, _p, _p, _p, _i64, _f, _i32, _i32, _p]),
     "artic_tanh_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "artic_cast": (C.c_int, [_p, _i32, _p, _i32, _i64, _p]),

@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Decode with a trained HiFi-GAN / HiFi-CAR generator (reference bin/decode.py).
+
+Same flags as ``articulatory-decode`` (--feats-scp/--scp, --dumpdir, --outdir, --checkpoint,
+--config, --normalize-before, --verbose), same ``config.yml`` discovery next to the checkpoint,
+same per-utterance RTF report; the generator runs on the sm_100a kernels.  ``ar_loop`` keeps the
+reference signature and semantics (bin/decode.py:31-83); ``--batch N`` additionally decodes N
+utterances in lock-step (articulatory_b200.decode.BatchedARDecoder), which the reference cannot.
+"""
+import argparse
+import glob
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+import yaml
+
+from articulatory_b200.decode import BatchedARDecoder
+from articulatory_b200.utils import load_model
+
+
+def ar_loop(model, x, config, do_wsola=False, modality=None, generator2=False):
+    """Chunked autoregressive synthesis of ONE utterance (reference bin/decode.py:31-83).
+
+    x: (art_len, num_feats) tensor on the model's device.  Returns the (art_len * hop,) signal."""
+    if generator2 or modality is not None or do_wsola or config.get("dataset_mode", "a2w") == "w2a":
+        raise NotImplementedError("generator2 / multi-modality / WSOLA / w2a decoding are outside the B200 hot path")
+    gp = config["generator_params"]
+    audio_chunk_len = config["batch_max_steps"]
+    in_chunk_len = int(audio_chunk_len / config["hop_size"])                       # :50
+    past_out_len = gp["ar_input"]                                                   # :51
+    ins = [x[i:i + in_chunk_len] for i in range(0, len(x), in_chunk_len)]           # :56
+    prev_samples = torch.zeros((1, gp["out_channels"], past_out_len), dtype=x.dtype, device=x.device)
+    outs = []
+    for cin in ins:
+        if cin.dim() == 1:
+            cin = cin.unsqueeze(1)
+        cin = cin.unsqueeze(0).permute(0, 2, 1)                                     # (1, num_feats, in_chunk_len)
+        cout = model(cin, ar=prev_samples)                                          # (1, 1, audio_chunk_len)
+        outs.append(cout[0][0])
+        if past_out_len <= audio_chunk_len:                                         # :77-78
+            prev_samples = cout[:, :, -past_out_len:]
+        else:                                                                       # :79-81
+            prev_samples[:, :, :-in_chunk_len] = prev_samples[:, :, in_chunk_len:].clone()
+            prev_samples[:, :, -in_chunk_len:] = cout
+    return torch.cat(outs, dim=0)
+
+
+def _load_feature_files(args, config):
+    """(utt_id, (T', C) float array) pairs from --dumpdir (npy / hdf5) or a kaldi-style scp of npy paths."""
+    items = []
+    if args.dumpdir is not None:
+        fmt = config.get("format", "npy")
+        if fmt == "npy":
+            for path in sorted(glob.glob(os.path.join(args.dumpdir, "**", "*-feats.npy"), recursive=True)):
+                items.append((os.path.basename(path).replace("-feats.npy", ""), np.load(path)))
+        elif fmt == "hdf5":
+            import h5py  # optional dependency, as in the reference
+            for path in sorted(glob.glob(os.path.join(args.dumpdir, "**", "*.h5"), recursive=True)):
+                with h5py.File(path, "r") as f:
+                    items.append((os.path.splitext(os.path.basename(path))[0], f["feats"][()]))
+        else:
+            raise ValueError("Support only hdf5 or npy format.")
+    else:
+        with open(args.feats_scp) as f:
+            for line in f:
+                utt_id, path = line.split(None, 1)
+                items.append((utt_id, np.load(path.strip())))
+    return items
+
+
+def _write_wav(path, y, fs):
+    """PCM-16 WAV (the reference uses soundfile; the stdlib wave module writes the same container)."""
+    import wave
+    pcm = (np.clip(y, -1.0, 1.0) * 32767.0).astype("<i2")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(int(fs))
+        w.writeframes(pcm.tobytes())
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="Decode dumped features with trained HiFi-GAN / HiFi-CAR Generator "
+                                                 "(See detail in articulatory_b200/bin/decode.py).")
+    parser.add_argument("--feats-scp", "--scp", default=None, type=str, help="kaldi-style feats.scp file (npy paths).")
+    parser.add_argument("--dumpdir", default=None, type=str, help="directory including feature files.")
+    parser.add_argument("--outdir", type=str, required=True, help="directory to save generated speech.")
+    parser.add_argument("--checkpoint", type=str, required=True, help="checkpoint file to be loaded.")
+    parser.add_argument("--config", default=None, type=str, help="yaml format configuration file.")
+    parser.add_argument("--normalize-before", default=False, action="store_true")
+    parser.add_argument("--verbose", type=int, default=1)
+    parser.add_argument("--batch", type=int, default=1, help="utterances decoded in lock-step (B200 extension)")
+    parser.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    args = parser.parse_args(argv)
+    logging.basicConfig(level=logging.INFO if args.verbose > 0 else logging.WARN,
+                        format="%(asctime)s (%(module)s:%(lineno)d) %(levelname)s: %(message)s")
+    os.makedirs(args.outdir, exist_ok=True)
+    if args.config is None:
+        args.config = os.path.join(os.path.dirname(args.checkpoint), "config.yml")
+    with open(args.config) as f:
+        config = yaml.load(f, Loader=yaml.Loader)
+    config.update(vars(args))
+    if (args.feats_scp is not None) == (args.dumpdir is not None):
+        raise ValueError("Please specify either --dumpdir or --feats-scp.")
+    if config.get("dataset_mode", "a2w") not in ("a2w", "default"):
+        raise NotImplementedError("only articulatory -> waveform decoding is on the B200 hot path")
+    if not torch.cuda.is_available():
+        raise RuntimeError("articulatory_b200 decodes on a CUDA device (sm_100a); there is no CPU path")
+    device = torch.device("cuda")
+    items = _load_feature_files(args, config)
+    logging.info(f"The number of features to be decoded = {len(items)}.")
+    model = load_model(args.checkpoint, config, precision=args.precision)
+    logging.info(f"Loaded model parameters from {args.checkpoint}.")
+    model.remove_weight_norm()
+    model = model.eval().to(device)
+    use_ar = config["generator_params"].get("use_ar", False)
+    fs = config["sampling_rate"]
+    total_rtf, n_done = 0.0, 0
+    with torch.no_grad():
+        if use_ar and args.batch > 1:
+            dec = BatchedARDecoder(model, config)
+            for i in range(0, len(items), args.batch):
+                group = items[i:i + args.batch]
+                start = time.time()
+                ys = dec.decode([torch.tensor(c, dtype=torch.float) for _, c in group])
+                torch.cuda.synchronize()
+                el = time.time() - start
+                for (utt_id, _), y in zip(group, ys):
+                    total_rtf += el / len(group) / (len(y) / fs)
+                    n_done += 1
+                    _write_wav(os.path.join(args.outdir, f"{utt_id}_gen.wav"), y.cpu().numpy(), fs)
+        else:
+            for utt_id, c in items:
+                c = torch.tensor(c, dtype=torch.float).to(device)
+                start = time.time()
+                if use_ar:
+                    y = ar_loop(model, c, config)
+                else:
+                    y = model.inference(c, normalize_before=args.normalize_before).view(-1)
+                y = y.cpu().numpy()
+                total_rtf += (time.time() - start) / (len(y) / fs)
+                n_done += 1
+                _write_wav(os.path.join(args.outdir, f"{utt_id}_gen.wav"), y, fs)
+    logging.info(f"Finished generation of {n_done} utterances (RTF = {total_rtf / max(n_done, 1):.03f}).")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+#!/usr/bin/env python
+"""Train a HiFi-GAN / HiFi-CAR vocoder on the B200 hot path (reference bin/train.py).
+
+Same flags as ``articulatory-train`` (--train-dumpdir, --dev-dumpdir, --outdir, --config,
+--pretrain, --resume, --verbose, --rank, --local_rank), same YAML keys
+(``egs/ema/voc1/conf/e2w_hifigan*.yaml`` run unchanged), same plugin lookup by class name,
+same checkpoint layout (``{"model": {"generator", "discriminator"}, "optimizer", "scheduler",
+"steps", "epochs"}``), same schedule gates and logged scalars.  The loop body is the fused
+``TrainStep`` (three CUDA graphs per step, no per-step host sync); distributed training — disabled
+in the reference (bin/train.py:1790-1801) — is one process per GPU with an NCCL gradient all-reduce.
+
+Data: ``--train-dumpdir`` with ``*-wave.npy`` / ``*-feats.npy`` pairs (the reference's ``format:
+npy`` dump layout) or ``*.h5`` with ``wave`` / ``feats`` datasets when h5py is installed;
+``--synthetic N`` trains on N generated MNGU0-shaped utterances (no dataset needed).
+"""
+import argparse
+import glob
+import logging
+import os
+import sys
+
+import numpy as np
+import torch
+import yaml
+
+import articulatory_b200
+import articulatory_b200.models
+from articulatory_b200.data import SpeechCollater, synthetic_utterances
+from articulatory_b200.parallel import DataParallel
+from articulatory_b200.trainer import LOG_KEYS, TrainStep
+
+
+def _load_items(dumpdir, config):
+    """[{'audio': (T,), 'art': (T', C)}] from a dump directory (reference SpeechDataset, npy / hdf5 layouts)."""
+    items = []
+    fmt = config.get("format", "hdf5")
+    if fmt == "npy":
+        for wav in sorted(glob.glob(os.path.join(dumpdir, "**", "*-wave.npy"), recursive=True)):
+            feats = wav.replace("-wave.npy", "-feats.npy")
+            if os.path.exists(feats):
+                items.append({"audio": np.load(wav).astype(np.float32), "art": np.load(feats).astype(np.float32)})
+    elif fmt == "hdf5":
+        import h5py  # optional dependency, as in the reference
+        for path in sorted(glob.glob(os.path.join(dumpdir, "**", "*.h5"), recursive=True)):
+            with h5py.File(path, "r") as f:
+                items.append({"audio": f["wave"][()].astype(np.float32), "art": f["feats"][()].astype(np.float32)})
+    else:
+        raise ValueError("support only hdf5 or npy format.")
+    return items
+
+
+class Trainer(object):
+    """Epoch / step loop, logging and checkpointing around ``TrainStep`` (reference Trainer, bin/train.py:60-780)."""
+
+    def __init__(self, steps, epochs, items, collater, model, step_fn, config, dp, device):
+        self.steps, self.epochs = steps, epochs
+        self.items, self.collater, self.model, self.ts = items, collater, model, step_fn
+        self.config, self.dp, self.device = config, dp, device
+        self.finish_train = False
+
+    def save_checkpoint(self, path):
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        torch.save({"model": {"generator": self.model["generator"].state_dict(),
+                              "discriminator": self.model["discriminator"].state_dict()},
+                    "optimizer": {"generator": self.ts.optG.state_dict(), "discriminator": self.ts.optD.state_dict()},
+                    "scheduler": {"generator": {"last_epoch": self.ts.optG.step_count()},
+                                  "discriminator": {"last_epoch": self.ts.optD.step_count()}},
+                    "steps": self.steps, "epochs": self.epochs}, path)
+
+    def load_checkpoint(self, path, load_only_params=False):
+        sd = torch.load(path, map_location="cpu", weights_only=False)
+        self.model["generator"].load_state_dict(sd["model"]["generator"])
+        self.model["discriminator"].load_state_dict(sd["model"]["discriminator"])
+        for m in self.model.values():
+            m.mark_weights_dirty()
+        if not load_only_params:
+            self.steps, self.epochs = sd["steps"], sd["epochs"]
+            self.ts.steps = self.steps
+            if "exp_avg" in sd["optimizer"]["generator"]:
+                self.ts.optG.load_state_dict(sd["optimizer"]["generator"])
+                self.ts.optD.load_state_dict(sd["optimizer"]["discriminator"])
+
+    def run(self):
+        bs = self.config["batch_size"]
+        while not self.finish_train:
+            idx = self.dp.sampler_indices(len(self.items), self.epochs, shuffle=True)
+            for lo in range(0, len(idx) - bs + 1, bs):
+                batch = self.collater([self.items[i] for i in idx[lo:lo + bs]])
+                if batch["y"].shape[0] != bs:
+                    continue          # an utterance shorter than the window was dropped: keep shapes static
+                self.ts.step(batch["x"][0].pin_memory(), batch["y"].pin_memory(), batch["ar"].pin_memory())
+                self.steps += 1
+                if self.steps % self.config["log_interval_steps"] == 0:
+                    n = self.config["log_interval_steps"]
+                    vals = self.dp.mean_scalars(self.ts.running.clone()).cpu().tolist()
+                    self.ts.running.zero_()
+                    if self.dp.rank == 0:
+                        for k, v in zip(LOG_KEYS, vals):
+                            logging.info(f"(Steps: {self.steps}) {k} = {v / n:.4f}.")
+                if self.steps % self.config["save_interval_steps"] == 0 and self.dp.rank == 0:
+                    self.save_checkpoint(os.path.join(self.config["outdir"], f"checkpoint-{self.steps}steps.pkl"))
+                if self.steps >= self.config["train_max_steps"]:
+                    self.finish_train = True
+                    break
+            self.epochs += 1
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="Train HiFi-GAN / HiFi-CAR (See detail in articulatory_b200/bin/train.py).")
+    for name in ("--train-wav-scp", "--train-feats-scp", "--train-segments", "--train-dumpdir", "--train-dumpdirs",
+                 "--dev-wav-scp", "--dev-feats-scp", "--dev-segments", "--dev-dumpdir", "--dev-dumpdirs"):
+        parser.add_argument(name, default=None, type=str)
+    parser.add_argument("--outdir", type=str, required=True, help="directory to save checkpoints.")
+    parser.add_argument("--config", type=str, required=True, help="yaml format configuration file.")
+    parser.add_argument("--pretrain", default="", type=str, help='checkpoint file path to load pretrained params. (default="")')
+    parser.add_argument("--pretrain2", default="", type=str)
+    parser.add_argument("--resume", default="", type=str, help='checkpoint file path to resume training. (default="")')
+    parser.add_argument("--verbose", type=int, default=1)
+    parser.add_argument("--rank", "--local_rank", default=0, type=int)
+    parser.add_argument("--synthetic", type=int, default=0, help="train on N synthetic utterances (B200 extension)")
+    parser.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    args = parser.parse_args(argv)
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("articulatory_b200 trains on a CUDA device (sm_100a); there is no CPU path")
+    dp_probe = int(os.environ.get("LOCAL_RANK", args.rank))
+    torch.cuda.set_device(dp_probe)
+    device = torch.device("cuda", dp_probe)
+    dp = DataParallel(device=device)
+    args.distributed = dp.world > 1
+    if dp.rank != 0:
+        sys.stdout = open(os.devnull, "w")                                   # reference :1462-1463
+    logging.basicConfig(level=logging.INFO if args.verbose > 0 else logging.WARN, stream=sys.stdout,
+                        format="%(asctime)s (%(module)s:%(lineno)d) %(levelname)s: %(message)s")
+    os.makedirs(args.outdir, exist_ok=True)
+    with open(args.config) as f:
+        config = yaml.load(f, Loader=yaml.Loader)
+    config.update(vars(args))
+    config["version"] = articulatory_b200.__version__
+    if dp.rank == 0:
+        with open(os.path.join(args.outdir, "config.yml"), "w") as f:
+            yaml.dump(config, f, Dumper=yaml.Dumper)
+    if args.pretrain2 or "generator2_type" in config:
+        raise NotImplementedError("two-stage generator cascades are outside the B200 hot path")
+
+    if args.synthetic:
+        hop = config["hop_size"]
+        frames = 4 * config["batch_max_steps"] // hop
+        n_feats = config["generator_params"]["in_channels"] - (config["generator_params"].get("ar_output", 0)
+                                                               if config["generator_params"].get("use_ar") else 0)
+        items = synthetic_utterances(args.synthetic, frames, n_feats, hop, seed=dp.rank)
+    elif args.train_dumpdir is not None:
+        items = _load_items(args.train_dumpdir, config)
+    else:
+        raise ValueError("Please specify --train-dumpdir or --synthetic.")
+    logging.info(f"The number of training files = {len(items)}.")
+    collater = SpeechCollater(batch_max_steps=config["batch_max_steps"], hop_size=config["hop_size"],
+                              aux_context_window=config["generator_params"].get("aux_context_window", 0),
+                              dataset_mode=config.get("dataset_mode", "a2w"), config=config)
+
+    # plugin lookup by class name (reference :1649-1662)
+    generator_class = getattr(articulatory_b200.models, config.get("generator_type", "HiFiGANGenerator"))
+    discriminator_class = getattr(articulatory_b200.models,
+                                  config.get("discriminator_type", "HiFiGANMultiScaleMultiPeriodDiscriminator"))
+    model = {"generator": generator_class(**config["generator_params"], precision=args.precision).to(device),
+             "discriminator": discriminator_class(**config["discriminator_params"], precision=args.precision).to(device)}
+    dp.broadcast_parameters(model["generator"], model["discriminator"])
+    ts = TrainStep(model["generator"], model["discriminator"], config, device, world_size=dp.world,
+                   all_reduce=dp.all_reduce if dp.world > 1 else None)
+    trainer = Trainer(0, 0, items, collater, model, ts, config, dp, device)
+    if args.pretrain:
+        trainer.load_checkpoint(args.pretrain, load_only_params=True)
+    if args.resume:
+        trainer.load_checkpoint(args.resume)
+    try:
+        trainer.run()
+    finally:
+        if dp.rank == 0:
+            trainer.save_checkpoint(os.path.join(config["outdir"], f"checkpoint-{trainer.steps}steps.pkl"))
+            logging.info(f"Successfully saved checkpoint @ {trainer.steps}steps.")
+        dp.close()
+
+
+if __name__ == "__main__":
+    main()

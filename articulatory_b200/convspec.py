@@ -52,6 +52,7 @@ class ConvSpec:
     groups: int = 1
     weight_norm: bool = False
     name: str = ""
+    trim_right: int = 0       # output samples dropped at the end (causal convs, layers/causal_conv.py:42,66)
     # derived
     cig: int = field(init=False)
     cog: int = field(init=False)
@@ -70,8 +71,8 @@ class ConvSpec:
     # ---- geometry ----------------------------------------------------------------
     def out_len(self, lin: int) -> int:
         if self.kind == "convT":
-            return (lin - 1) * self.stride - 2 * self.padding + self.k + self.output_padding
-        return (lin + 2 * self.padding - self.dilation * (self.k - 1) - 1) // self.stride + 1
+            return (lin - 1) * self.stride - 2 * self.padding + self.k + self.output_padding - self.trim_right
+        return (lin + 2 * self.padding - self.dilation * (self.k - 1) - 1) // self.stride + 1 - self.trim_right
 
     # ---- torch weight layout -----------------------------------------------------
     def weight_shape(self) -> Tuple[int, ...]:

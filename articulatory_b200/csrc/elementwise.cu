@@ -16,30 +16,29 @@ static inline int grid_for(int64_t n, int per_block = 256) {
 
 template <typename T>
 __global__ void gen_input_kernel(const float* __restrict__ c, const T* __restrict__ ar, T* __restrict__ out, int B,
-                                 int Cc, int Ca, int Tn) {
-  const int C = Cc + Ca;
+                                 int Cc, int Ca, int C, int Tn) {
   const int64_t n = (int64_t)B * Tn * C;
   GRID_STRIDE(i, n) {
     const int ch = (int)(i % C);
     const int64_t r = i / C;
     const int t = (int)(r % Tn);
     const int b = (int)(r / Tn);
-    float v;
+    float v = 0.f;   // channels >= Cc + Ca are zero padding
     if (ch < Cc) v = c[((int64_t)b * Cc + ch) * Tn + t];
-    else v = ld_f(ar + (int64_t)b * Ca + (ch - Cc));
+    else if (ch < Cc + Ca) v = ld_f(ar + (int64_t)b * Ca + (ch - Cc));
     st_f(out + i, v);
   }
 }
 
 template <typename T>
-__global__ void gen_input_bwd_kernel(const T* __restrict__ dX, float* __restrict__ d_ar, int B, int Cc, int Ca, int Tn) {
+__global__ void gen_input_bwd_kernel(const T* __restrict__ dX, float* __restrict__ d_ar, int B, int Cc, int Ca, int C, int Tn) {
   // one thread per (b, a); Tn is small (<= a few hundred frames)
   const int64_t n = (int64_t)B * Ca;
   GRID_STRIDE(i, n) {
     const int a = (int)(i % Ca);
     const int b = (int)(i / Ca);
     float s = 0.f;
-    for (int t = 0; t < Tn; ++t) s += ld_f(dX + ((int64_t)b * Tn + t) * (Cc + Ca) + Cc + a);
+    for (int t = 0; t < Tn; ++t) s += ld_f(dX + ((int64_t)b * Tn + t) * C + Cc + a);
     d_ar[i] = s;
   }
 }
@@ -225,21 +224,23 @@ typedef __nv_bfloat16 bf16;
   } while (0)
 
 extern "C" int artic_gen_input(const float* c, const void* ar_feats, void* out, int32_t B, int32_t Cc, int32_t Ca,
-                               int32_t T, int32_t dtype, void* stream) {
+                               int32_t Cpad, int32_t T, int32_t dtype, void* stream) {
   ARTIC_CHECK_ARG(c && out && (ar_feats || Ca == 0), "null pointer");
-  const int64_t n = (int64_t)B * T * (Cc + Ca);
+  ARTIC_CHECK_ARG(Cpad >= Cc + Ca, "row pitch smaller than the channel count");
+  const int64_t n = (int64_t)B * T * Cpad;
   if (n == 0) return ARTIC_OK;
-  DISPATCH(dtype, (gen_input_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(c, (const float*)ar_feats, (float*)out, B, Cc, Ca, T)),
-           (gen_input_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(c, (const bf16*)ar_feats, (bf16*)out, B, Cc, Ca, T)));
+  DISPATCH(dtype, (gen_input_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(c, (const float*)ar_feats, (float*)out, B, Cc, Ca, Cpad, T)),
+           (gen_input_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(c, (const bf16*)ar_feats, (bf16*)out, B, Cc, Ca, Cpad, T)));
 }
 
-extern "C" int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int32_t Ca, int32_t T,
-                                   int32_t dtype, void* stream) {
+extern "C" int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int32_t Ca, int32_t Cpad,
+                                   int32_t T, int32_t dtype, void* stream) {
   ARTIC_CHECK_ARG(dX && d_ar, "null pointer");
+  ARTIC_CHECK_ARG(Cpad >= Cc + Ca, "row pitch smaller than the channel count");
   const int64_t n = (int64_t)B * Ca;
   if (n == 0) return ARTIC_OK;
-  DISPATCH(dtype, (gen_input_bwd_kernel<float><<<grid_for(n, 64), 64, 0, ST(stream)>>>((const float*)dX, d_ar, B, Cc, Ca, T)),
-           (gen_input_bwd_kernel<bf16><<<grid_for(n, 64), 64, 0, ST(stream)>>>((const bf16*)dX, d_ar, B, Cc, Ca, T)));
+  DISPATCH(dtype, (gen_input_bwd_kernel<float><<<grid_for(n, 64), 64, 0, ST(stream)>>>((const float*)dX, d_ar, B, Cc, Ca, Cpad, T)),
+           (gen_input_bwd_kernel<bf16><<<grid_for(n, 64), 64, 0, ST(stream)>>>((const bf16*)dX, d_ar, B, Cc, Ca, Cpad, T)));
 }
 
 extern "C" int artic_mean3_act(const void* a, const void* b, const void* c, void* out_act, int64_t n, float slope,

@@ -149,6 +149,84 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_kernel(const __grid_constant
   }
 }
 
+// Vector variant of the above for bf16 dY rows (Cog % 8 == 0): Cog/8 threads cover one dY row with
+// 128-bit loads, each thread keeps [taps][8 channels] partial sums in registers, the position loop
+// is unrolled 4x so that four independent row loads are in flight (the scalar kernel above is
+// latency-bound: one 2-byte load per thread per iteration).
+template <typename T>
+__global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_constant__ artic_tapwgrad_t p, int tap0,
+                                                               int min_off, int span) {
+  __shared__ float xs[C1_SMEM];
+  __shared__ float red[256][9];
+  const int tpr = p.Cog >> 3, rpp = 256 / tpr;
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const int n = blockIdx.y;
+  const int qa = blockIdx.x * C1_ROWS;
+  const int qb = min(p.nq, qa + C1_ROWS);
+  const T* __restrict__ X = reinterpret_cast<const T*>(p.X) + seq_base(p.x, n);
+  const __nv_bfloat16* __restrict__ dY = reinterpret_cast<const __nv_bfloat16*>(p.dY) + seq_base(p.y, n);
+  const int x0 = (p.q0 + qa) * p.si + min_off;
+  const int nx = (qb - qa - 1) * p.si + span + 1;
+  for (int i = threadIdx.x; i < nx; i += 256) {
+    const int pos = x0 + i;
+    xs[i] = (pos >= 0 && pos < p.x.len) ? ld_f(X + (int64_t)pos * p.x.s_row) : 0.f;
+  }
+  __syncthreads();
+  const int nt = min(C1_TAPS, p.ntaps - tap0);
+  float acc[C1_TAPS][8];
+#pragma unroll
+  for (int t = 0; t < C1_TAPS; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  const int yo = p.yoff[tap0];
+  for (int q = qa + rl; q < qb; q += 4 * rpp) {
+    uint4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int qq = q + j * rpp;
+      const int ypos = (p.q0 + qq) * p.so + yo;
+      u[j] = (qq < qb && ypos >= 0 && ypos < p.y.len)
+                 ? __ldg(reinterpret_cast<const uint4*>(dY + (int64_t)ypos * p.y.s_row) + cg)
+                 : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int qq = q + j * rpp;
+      if (qq >= qb) break;
+      float dy[8];
+      const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        dy[2 * i] = __uint_as_float(w[i] << 16);
+        dy[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      }
+      const int xb = (qq - qa) * p.si - min_off;
+#pragma unroll
+      for (int t = 0; t < C1_TAPS; ++t) {
+        if (t < nt) {
+          const float xv = xs[xb + p.off[tap0 + t]];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(xv, dy[i], acc[t][i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < C1_TAPS; ++t) {
+    if (t < nt) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[t][i];
+      __syncthreads();
+      for (int c = threadIdx.x; c < p.Cog; c += 256) {
+        float sum = 0.f;
+        for (int r = 0; r < rpp; ++r) sum += red[r * tpr + (c >> 3)][c & 7];
+        atomicAdd(p.dW + (int64_t)p.widx[tap0 + t] * p.Cog + c, sum);   // [K][G=1][Cig=1][Cog]
+      }
+    }
+  }
+}
+
 // dW[t][ci] = sum_q X[q + off_t][ci] * dy[q + yoff]   (dy single channel, staged in smem; si = so = 1).
 // Every X element is read once and feeds all taps.
 template <typename T, typename TY>
@@ -246,7 +324,15 @@ int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
     else if (yb) K<float, __nv_bfloat16><<<grid, 256, 0, st>>>(p, cw, tap0, min_off, span);                        \
     else K<float, float><<<grid, 256, 0, st>>>(p, cw, tap0, min_off, span);                                        \
   } while (0)
-    if (ci1) ARTIC_C1_LAUNCH(tapwgrad_ci1_kernel);
+    const int tpr = p.Cog / 8;
+    const bool vec = ci1 && yb && p.Cog % 8 == 0 && tpr <= 256 && 256 % tpr == 0 && p.y.s_row % 8 == 0 &&
+                     p.y.s_outer % 8 == 0 && (p.y.n_inner == 1 || p.y.s_inner % 8 == 0) &&
+                     (reinterpret_cast<uintptr_t>(p.dY) & 15) == 0;
+    if (vec) {
+      dim3 vgrid(grid.x, grid.y, 1);
+      if (xb) tapwgrad_ci1_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span);
+      else tapwgrad_ci1_vec_kernel<float><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span);
+    } else if (ci1) ARTIC_C1_LAUNCH(tapwgrad_ci1_kernel);
     else ARTIC_C1_LAUNCH(tapwgrad_co1_kernel);
 #undef ARTIC_C1_LAUNCH
   }

@@ -44,8 +44,9 @@ struct Plan {
   int32_t n_ph, panel_bytes;      // input-stride phases (= si) and bytes of one phase panel
   int32_t shift[ARTIC_MAX_TAPS];  // (off[t] - min_off) / si : row shift inside the tap's phase panel
   int32_t phase[ARTIC_MAX_TAPS];  // (off[t] - min_off) % si : which phase panel the tap reads
+  int32_t a_off16[ARTIC_MAX_TAPS];  // (phase * panel_bytes + shift * row_bytes) / 16 : descriptor offset of the tap
   int32_t layout_type;            // UMMA smem descriptor swizzle code
-  int32_t base_offset_mode;       // debug: 0 = address-based swizzle phase, 1 = explicit base offset
+  long long* dbg;                 // debug timeline buffer (artic_debug_buffer) or nullptr
 };
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100):
@@ -60,6 +61,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
   d |= (uint64_t)(base_off & 7) << 49;
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
+}
+
+// Debug timeline: CTA 0 appends (tag, clock64) pairs; slot 0 is the write cursor.
+__device__ __forceinline__ void dbg_mark(long long* dbg, int tag) {
+  if (dbg != nullptr && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(dbg), 1ULL);
+    if (i < 2000) { dbg[1 + 2 * i] = tag; dbg[2 + 2 * i] = clock64(); }
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -79,6 +88,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
   const uint32_t a_base = smem0;
   const uint32_t w_base = smem0 + (uint32_t)pl.n_as * pl.a_stage_bytes;
 
+  if (threadIdx.x == 0) dbg_mark(pl.dbg, 1);
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_x);
     prefetch_tmap(&map_w);
@@ -92,6 +102,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) dbg_mark(pl.dbg, 2);
 
   const int ntaps = p.ntaps;
   const int acc_cols = pl.mt * pl.bn;
@@ -109,6 +120,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
         for (int kc = 0; kc < pl.n_kc; ++kc) {
           const int c0 = g * p.Cig + kc * pl.kch;
           mbar_wait(&a_empty[as.stage], as.phase ^ 1);
+          dbg_mark(pl.dbg, 10);
           const uint32_t a_dst = a_base + (uint32_t)as.stage * pl.a_stage_bytes;
           if (!pl.packed) {
             const int n = mtile / pl.tiles_per_seq;
@@ -134,6 +146,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
           as.next();
           for (int t = 0; t < ntaps; ++t) {
             mbar_wait(&w_empty[ws.stage], ws.phase ^ 1);
+            dbg_mark(pl.dbg, 11);
             mbar_expect_tx(&w_full[ws.stage], w_bytes);
             tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes, &map_w, &w_full[ws.stage], kc * pl.kch,
                         (p.widx[t] * p.G + g) * p.Cog + nt * pl.bn);
@@ -144,32 +157,56 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
+    // One thread issues every MMA, so the instructions between two tcgen05.mma are the kernel's
+    // critical path for narrow tiles: the shared-memory descriptors are reduced to one 32-bit add
+    // per operand (constant high word; the low word is the 16-byte address, to which the tap's
+    // precomputed row shift, the sub-tile offset and the k-step are added).
     if (lane == 0) {
       PipeState as(pl.n_as), ws(pl.n_ws), acc(pl.acc_stages);
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.bn >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t desc_hi = (((8u * (uint32_t)pl.row_bytes) >> 4) & 0x3fffu) | (1u << 14) | ((uint32_t)(pl.layout_type & 7) << 29);
+      const uint32_t desc_lo = 1u << 16;                      // LBO field (unused for swizzled K-major)
+      const uint32_t m_step16 = (128u * (uint32_t)pl.row_bytes) >> 4;
       const int ksteps = pl.kch / 16;
+      const int mt = pl.mt;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[acc.stage], acc.phase ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)acc.stage * acc_cols;
+        uint32_t accum = 0;
         for (int kc = 0; kc < pl.n_kc; ++kc) {
           mbar_wait(&a_full[as.stage], as.phase);
-          const uint32_t a_st = a_base + (uint32_t)as.stage * pl.a_stage_bytes;
+          dbg_mark(pl.dbg, 20);
+          const uint32_t a16 = desc_lo | (((a_base + (uint32_t)as.stage * pl.a_stage_bytes) >> 4) & 0x3fffu);
           for (int t = 0; t < ntaps; ++t) {
             mbar_wait(&w_full[ws.stage], ws.phase);
+            dbg_mark(pl.dbg, 21);
             tc_fence_after();
-            const uint32_t w_st = w_base + (uint32_t)ws.stage * pl.w_stage_bytes;
-            for (int m = 0; m < pl.mt; ++m) {
-              const uint32_t a_row = (uint32_t)(m * 128 + pl.shift[t]);
-              const uint32_t a_addr = a_st + (uint32_t)pl.phase[t] * pl.panel_bytes + a_row * pl.row_bytes;
-              const uint32_t boff = pl.base_offset_mode ? ((a_addr >> 7) & 7u) : 0u;
-#pragma unroll 4
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t ad = make_desc(a_addr + k * 32, pl.row_bytes, pl.layout_type, boff);
-                const uint64_t bd = make_desc(w_st + k * 32, pl.row_bytes, pl.layout_type, 0);
-                umma_bf16(d_base + (uint32_t)m * pl.bn, ad, bd, idesc, (kc | t | k) != 0 ? 1u : 0u);
+            const uint32_t b16 = desc_lo | (((w_base + (uint32_t)ws.stage * pl.w_stage_bytes) >> 4) & 0x3fffu);
+            uint32_t at16 = a16 + (uint32_t)pl.a_off16[t];
+            uint32_t dcol = d_base;
+            for (int m = 0; m < mt; ++m) {
+              if (ksteps == 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
+                  accum = 1;
+                }
+              } else if (ksteps == 2) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
+                  accum = 1;
+                }
+              } else {
+                umma_bf16(dcol, ((uint64_t)desc_hi << 32) | at16, ((uint64_t)desc_hi << 32) | b16, idesc, accum);
+                accum = 1;
               }
+              // the accumulate flag must stay 0 for the first k-step of EVERY sub-tile of the tile
+              if (kc == 0 && t == 0 && m + 1 < mt) accum = 0;
+              at16 += m_step16;
+              dcol += (uint32_t)pl.bn;
             }
             umma_commit(&w_empty[ws.stage]);
             ws.next();
@@ -178,6 +215,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
           as.next();
         }
         umma_commit(&acc_full[acc.stage]);
+        dbg_mark(pl.dbg, 22);
         acc.next();
       }
     }
@@ -198,6 +236,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
       const int mtile = r % pl.n_mt;
       const int g = r / pl.n_mt;
       mbar_wait(&acc_full[acc.stage], acc.phase);
+      if (threadIdx.x == 64) dbg_mark(pl.dbg, 30);
       tc_fence_after();
       const int cbase = g * p.Cog + nt * pl.bn;
       for (int m = 0; m < pl.mt; ++m) {
@@ -269,6 +308,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
         }
       }
       tc_fence_before();
+      if (threadIdx.x == 64) dbg_mark(pl.dbg, 31);
       mbar_arrive(&acc_empty[acc.stage]);
       acc.next();
     }
@@ -300,6 +340,7 @@ EncodeTiledFn encode_fn() {
 }
 
 int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+long long* g_dbg_buf = nullptr;
 static int g_smem_optin = 0;
 
 // Largest dynamic shared-memory size the kernel may be launched with (opt-in limit minus the
@@ -327,6 +368,11 @@ static int max_smem() {
 }  // namespace artic
 
 using namespace artic;
+
+extern "C" int artic_debug_buffer(void* dev_buf) {
+  tc::g_dbg_buf = reinterpret_cast<long long*>(dev_buf);
+  return ARTIC_OK;
+}
 
 extern "C" int artic_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return ARTIC_EINVAL;
@@ -442,7 +488,8 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
     }
   }
   if (best < 0) return 0;
-  pl.base_offset_mode = tc::g_debug[0];
+  pl.dbg = tc::g_dbg_buf;
+  for (int t = 0; t < p.ntaps; ++t) pl.a_off16[t] = (pl.phase[t] * pl.panel_bytes + pl.shift[t] * pl.row_bytes) >> 4;
 
   // ---- tensor maps
   CUtensorMap map_x, map_w;

@@ -162,20 +162,34 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(pl.bn >> 3) << 17) | ((128u >> 4) << 24);
       const int ksteps = pl.kp / 16;
+      // descriptors: constant high words, low word = 16-byte address | LBO << 16 (one add per k-step)
+      const uint32_t a_hi = (((8u * (uint32_t)pl.xrb) >> 4) & 0x3fffu) | (1u << 14) | ((uint32_t)(pl.x_layout & 7) << 29);
+      const uint32_t b_hi = (((8u * (uint32_t)pl.yrb) >> 4) & 0x3fffu) | (1u << 14) | ((uint32_t)(pl.y_layout & 7) << 29);
+      const uint32_t a_lo0 = (((uint32_t)pl.a_lbo >> 4) & 0x3fffu) << 16;
+      const uint32_t b_lo0 = (((uint32_t)pl.y_panel_bytes >> 4) & 0x3fffu) << 16;
+      uint32_t accum = 0;
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&full[ps.stage], ps.phase);
         tc_fence_after();
         const uint32_t xs = smem0 + (uint32_t)ps.stage * pl.stage_bytes;
         const uint32_t ys = xs + (uint32_t)(pl.n_ph * pl.nxp) * pl.x_panel_bytes;
+        const uint32_t b16 = b_lo0 | ((ys >> 4) & 0x3fffu);
         for (int a = 0; a < n_acc; ++a) {
-          const uint32_t shift = (uint32_t)pl.acc_shift[acc0 + a];   // rows inside the phase panel
-          const uint32_t xp = xs + (uint32_t)(pl.acc_panel[acc0 + a] * pl.nxp) * pl.x_panel_bytes;
+          const uint32_t xa = xs + (uint32_t)(pl.acc_panel[acc0 + a] * pl.nxp) * pl.x_panel_bytes +
+                              (uint32_t)pl.acc_shift[acc0 + a] * pl.xrb;
+          uint32_t ad = a_lo0 | ((xa >> 4) & 0x3fffu);
+          uint32_t bd = b16;
+          const uint32_t dcol = tmem_base + (uint32_t)a * pl.bn;
+          uint32_t acc_k = accum;
+#pragma unroll 4
           for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_desc_mn(xp + (shift + k * 16) * pl.xrb, pl.a_lbo, pl.xrb, pl.x_layout);
-            const uint64_t bd = make_desc_mn(ys + (uint32_t)(k * 16) * pl.yrb, pl.y_panel_bytes, pl.yrb, pl.y_layout);
-            umma_bf16(tmem_base + (uint32_t)a * pl.bn, ad, bd, idesc, (c > c_begin || k > 0) ? 1u : 0u);
+            umma_bf16(dcol, ((uint64_t)a_hi << 32) | ad, ((uint64_t)b_hi << 32) | bd, idesc, acc_k);
+            acc_k = 1;
+            ad += (uint32_t)pl.xrb;    // 16 positions * xrb bytes / 16
+            bd += (uint32_t)pl.yrb;
           }
         }
+        accum = 1;
         umma_commit(&empty[ps.stage]);
         ps.next();
       }

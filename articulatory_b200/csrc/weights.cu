@@ -3,91 +3,131 @@
 
 namespace artic {
 
+// ---- batched ("multi-tensor") weight preparation ----------------------------------------
+// One launch handles every layer of a network: blockIdx.y = layer, blockIdx.x strides over the
+// layer's rows / tiles.  The descriptor table lives in device memory (uploaded once).
+
 // scale[row] = g[row] / ||v[row]||, scale[rows + row] = ||v[row]||
-__global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g,
-                                                       float* __restrict__ scale, int rows, int64_t row_len) {
+__global__ void __launch_bounds__(256) wn_scale_kernel(const artic_wdesc_t* __restrict__ descs) {
   __shared__ float red[32];
-  const int row = blockIdx.x;
-  const float* vr = v + (int64_t)row * row_len;
-  float s = 0.f;
-  for (int64_t e = threadIdx.x; e < row_len; e += blockDim.x) {
-    const float x = vr[e];
-    s = fmaf(x, x, s);
-  }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) {
-    const float nrm = sqrtf(s);
-    scale[row] = g[row] / nrm;
-    scale[rows + row] = nrm;
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) prep_permute_kernel(const float* __restrict__ v, const float* __restrict__ scale,
-                                                           int64_t row_len, int K, int G, int A, int B, int64_t sk,
-                                                           int64_t sg, int64_t sa, int64_t sb, int mg,
-                                                           T* __restrict__ out) {
-  const int64_t total = (int64_t)K * G * A * B;
-  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(o % B);
-    int64_t r = o / B;
-    const int a = (int)(r % A);
-    r /= A;
-    const int g = (int)(r % G);
-    const int k = (int)(r / G);
-    const int64_t src = k * sk + g * sg + a * sa + b * sb;
-    float w = v[src];
-    if (scale != nullptr) w *= scale[src / row_len];
-    // merge > 1: block-diagonal layout [K][G/mg][mg*A][mg*B] (off-diagonal blocks stay zero)
-    const int64_t oo = mg == 1 ? o
-                               : ((((int64_t)k * (G / mg) + g / mg) * (mg * A) + (g % mg) * A + a) * (int64_t)(mg * B) +
-                                  (g % mg) * B + b);
-    st_f(out + oo, w);
+  const artic_wdesc_t& d = descs[blockIdx.y];
+  if (d.g == nullptr) return;
+  for (int row = blockIdx.x; row < d.rows; row += gridDim.x) {
+    const float* vr = d.v + (int64_t)row * d.row_len;
+    float s = 0.f;
+    for (int64_t e = threadIdx.x; e < d.row_len; e += blockDim.x) {
+      const float x = vr[e];
+      s = fmaf(x, x, s);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+      const float nrm = sqrtf(s);
+      d.scale[row] = d.g[row] / nrm;
+      d.scale[d.rows + row] = nrm;
+    }
+    __syncthreads();
   }
 }
 
-// One block per torch row. dWp is [K][G][A][B]; (k,g,a,b) are recovered from the source
-// element index by mixed-radix decomposition over the dims sorted by decreasing stride.
-struct Unperm {
-  int64_t stride[4];  // sorted descending
-  int32_t dim_id[4];  // 0=k 1=g 2=a 3=b
-  int32_t n;          // number of dims with extent > 1
-};
+// Tiled permutation between the torch weight and a prepared layout, through shared memory so
+// that BOTH sides move in contiguous runs (torch side: runs of inner-dim x taps; prepared side:
+// runs of 32 columns).  MODE 0: torch -> 'fwd' layout [K][G/m][a_pad][b_pad] (rows = A, cols = B)
+//                        MODE 1: torch -> 'bwd' layout [K][G/m][b_pad][a_pad] (rows = B, cols = A)
+//                        MODE 2: fp32 dWp ('fwd' layout) -> dv (torch layout), overwriting
+constexpr int PT = 32;   // tile edge
+constexpr int PK = 8;    // taps per tile
+template <int MODE>
+__global__ void __launch_bounds__(256) wperm_kernel(const artic_wdesc_t* __restrict__ descs) {
+  __shared__ float tile[PK][PT][PT + 1];
+  const artic_wdesc_t& d = descs[blockIdx.y];
+  void* outp = MODE == 0 ? d.out_f : MODE == 1 ? d.out_b : (void*)d.dv;
+  if (outp == nullptr || (MODE == 2 && d.dWp == nullptr)) return;
+  const bool swap = MODE == 1;
+  const int Rn = swap ? d.B : d.A, Cn = swap ? d.A : d.B;          // rows / cols of the prepared matrix
+  const int64_t sr = swap ? d.sb : d.sa, sc = swap ? d.sa : d.sb;  // their strides in the torch weight
+  const int r_pad = swap ? d.b_pad : d.a_pad, c_pad = swap ? d.a_pad : d.b_pad;
+  const int m = d.merge, Gs = d.G / m;
+  const int kc = d.K < PK ? d.K : PK;
+  const int n_rt = (Rn + PT - 1) / PT, n_ct = (Cn + PT - 1) / PT, n_kt = (d.K + kc - 1) / kc;
+  const int64_t n_tiles = (int64_t)n_rt * n_ct * n_kt * d.G;
+  const bool r_inner = sr < sc;                                      // which matrix dim is contiguous-ish in torch
+  const int dtype = MODE == 0 ? d.dtype_f : d.dtype_b;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int64_t w = t;
+    const int ct = (int)(w % n_ct); w /= n_ct;
+    const int rt = (int)(w % n_rt); w /= n_rt;
+    const int kt = (int)(w % n_kt);
+    const int g = (int)(w / n_kt);
+    const int r0 = rt * PT, c0 = ct * PT, k0 = kt * kc;
+    const int kn = min(kc, d.K - k0);
+    const int64_t tbase = (int64_t)g * d.sg + (int64_t)k0 * d.sk;
+    // prepared-side offset of element (kk, r, c)
+    auto poff = [&](int kk, int r, int c) -> int64_t {
+      return (((int64_t)(k0 + kk) * Gs + g / m) * r_pad + (g % m) * Rn + r0 + r) * (int64_t)c_pad + (g % m) * Cn + c0 + c;
+    };
+    const int n_el = PT * PT * kn;
+    if (MODE != 2) {
+      // torch -> smem (taps fastest, then the torch-inner matrix dim)
+      for (int e = threadIdx.x; e < n_el; e += 256) {
+        const int kk = e % kn;
+        const int i = (e / kn) % PT, o = e / (kn * PT);
+        const int r = r_inner ? i : o, c = r_inner ? o : i;
+        float val = 0.f;
+        if (r0 + r < Rn && c0 + c < Cn) {
+          const int64_t src = tbase + (int64_t)kk * d.sk + (int64_t)(r0 + r) * sr + (int64_t)(c0 + c) * sc;
+          val = d.v[src];
+          if (d.g != nullptr) val *= d.scale[src / d.row_len];
+        }
+        tile[kk][r][c] = val;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < n_el; e += 256) {
+        const int c = e % PT, r = (e / PT) % PT, kk = e / (PT * PT);
+        if (r0 + r < Rn && c0 + c < Cn) {
+          const int64_t o = poff(kk, r, c);
+          if (dtype == ARTIC_BF16) reinterpret_cast<__nv_bfloat16*>(outp)[o] = __float2bfloat16_rn(tile[kk][r][c]);
+          else reinterpret_cast<float*>(outp)[o] = tile[kk][r][c];
+        }
+      }
+    } else {
+      for (int e = threadIdx.x; e < n_el; e += 256) {
+        const int c = e % PT, r = (e / PT) % PT, kk = e / (PT * PT);
+        tile[kk][r][c] = (r0 + r < Rn && c0 + c < Cn) ? d.dWp[poff(kk, r, c)] : 0.f;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < n_el; e += 256) {
+        const int kk = e % kn;
+        const int i = (e / kn) % PT, o = e / (kn * PT);
+        const int r = r_inner ? i : o, c = r_inner ? o : i;
+        if (r0 + r < Rn && c0 + c < Cn)
+          d.dv[tbase + (int64_t)kk * d.sk + (int64_t)(r0 + r) * sr + (int64_t)(c0 + c) * sc] = tile[kk][r][c];
+      }
+    }
+    __syncthreads();
+  }
+}
 
-__global__ void __launch_bounds__(256) unprep_kernel(const float* __restrict__ dWp, const float* __restrict__ v,
-                                                     const float* __restrict__ scale, int rows, int64_t row_len, int G,
-                                                     int A, int B, int mg, Unperm up, float* __restrict__ dv,
-                                                     float* __restrict__ dg) {
+// Weight-norm backward, in place on dv (which holds dL/dw in torch layout):
+//   dot = <dw_row, v_row>;  dv = s * dw - (s * dot / nrm^2) * v;  dg = dot / nrm     (s = g / nrm)
+__global__ void __launch_bounds__(256) wn_bwd_kernel(const artic_wdesc_t* __restrict__ descs) {
   __shared__ float red[32];
   __shared__ float s_dot;
-  const int row = blockIdx.x;
-  const int64_t e0 = (int64_t)row * row_len;
-  auto perm = [&](int64_t e) -> int64_t {
-    int idx[4] = {0, 0, 0, 0};
-    int64_t rem = e;
-    for (int i = 0; i < up.n; ++i) {
-      idx[up.dim_id[i]] = (int)(rem / up.stride[i]);
-      rem -= (int64_t)idx[up.dim_id[i]] * up.stride[i];
-    }
-    if (mg == 1) return (((int64_t)idx[0] * G + idx[1]) * A + idx[2]) * B + idx[3];
-    return (((int64_t)idx[0] * (G / mg) + idx[1] / mg) * (mg * A) + (idx[1] % mg) * A + idx[2]) * (int64_t)(mg * B) +
-           (idx[1] % mg) * B + idx[3];
-  };
-  if (scale == nullptr) {
-    for (int64_t e = threadIdx.x; e < row_len; e += blockDim.x) dv[e0 + e] += dWp[perm(e0 + e)];
-    return;
+  const artic_wdesc_t& d = descs[blockIdx.y];
+  if (d.g == nullptr || d.dv == nullptr) return;
+  for (int row = blockIdx.x; row < d.rows; row += gridDim.x) {
+    const int64_t e0 = (int64_t)row * d.row_len;
+    float dot = 0.f;
+    for (int64_t e = threadIdx.x; e < d.row_len; e += blockDim.x) dot = fmaf(d.dv[e0 + e], d.v[e0 + e], dot);
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) s_dot = dot;
+    __syncthreads();
+    dot = s_dot;
+    const float s = d.scale[row], nrm = d.scale[d.rows + row];
+    const float coef = s * dot / (nrm * nrm);
+    for (int64_t e = threadIdx.x; e < d.row_len; e += blockDim.x) d.dv[e0 + e] = s * d.dv[e0 + e] - coef * d.v[e0 + e];
+    if (threadIdx.x == 0) d.dg[row] = dot / nrm;
+    __syncthreads();
   }
-  float dot = 0.f;
-  for (int64_t e = threadIdx.x; e < row_len; e += blockDim.x) dot = fmaf(dWp[perm(e0 + e)], v[e0 + e], dot);
-  dot = block_sum(dot, red);
-  if (threadIdx.x == 0) s_dot = dot;
-  __syncthreads();
-  dot = s_dot;
-  const float s = scale[row], nrm = scale[rows + row];
-  const float coef = s * dot / (nrm * nrm);
-  for (int64_t e = threadIdx.x; e < row_len; e += blockDim.x)
-    dv[e0 + e] += s * dWp[perm(e0 + e)] - coef * v[e0 + e];
-  if (threadIdx.x == 0) dg[row] += dot / nrm;
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -118,59 +158,23 @@ __global__ void adam_tick_kernel(artic_adam_hyper_t* hyper) { hyper->step += 1; 
 
 using namespace artic;
 
-extern "C" int artic_weight_prep(const float* v, const float* g, float* scale, int32_t rows, int64_t row_len,
-                                 int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sg, int64_t sa,
-                                 int64_t sb, int32_t merge, void* out, int32_t dtype, void* stream) {
-  ARTIC_CHECK_ARG(v && out, "null pointer");
-  ARTIC_CHECK_ARG(merge >= 1 && G % merge == 0, "merge must divide the group count");
-  ARTIC_CHECK_ARG(g == nullptr || scale != nullptr, "scale buffer required with weight norm");
-  ARTIC_CHECK_ARG(rows >= 1 && row_len >= 1 && K >= 1 && G >= 1 && A >= 1 && B >= 1, "bad dims");
-  ARTIC_CHECK_ARG((int64_t)rows * row_len == (int64_t)K * G * A * B, "element count mismatch");
-  ARTIC_CHECK_ARG(dtype == ARTIC_F32 || dtype == ARTIC_BF16, "bad dtype");
+extern "C" int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, void* stream) {
+  ARTIC_CHECK_ARG(descs != nullptr && n >= 0, "bad descriptor table");
+  if (n == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (g != nullptr) wn_scale_kernel<<<rows, 256, 0, st>>>(v, g, scale, rows, row_len);
-  const int64_t total = (int64_t)K * G * A * B;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
-  const float* sc = g != nullptr ? scale : nullptr;
-  if (dtype == ARTIC_BF16)
-    prep_permute_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(v, sc, row_len, K, G, A, B, sk, sg, sa, sb, merge,
-                                                                reinterpret_cast<__nv_bfloat16*>(out));
-  else
-    prep_permute_kernel<float><<<blocks, 256, 0, st>>>(v, sc, row_len, K, G, A, B, sk, sg, sa, sb, merge,
-                                                        reinterpret_cast<float*>(out));
+  if (any_norm) wn_scale_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
+  wperm_kernel<0><<<dim3(64, (unsigned)n), 256, 0, st>>>(descs);
+  wperm_kernel<1><<<dim3(64, (unsigned)n), 256, 0, st>>>(descs);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
 }
 
-extern "C" int artic_weight_unprep(const float* dWp, const float* v, const float* g, const float* scale, int32_t rows,
-                                   int64_t row_len, int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sg,
-                                   int64_t sa, int64_t sb, int32_t merge, float* dv, float* dg, void* stream) {
-  ARTIC_CHECK_ARG(dWp && v && dv, "null pointer");
-  ARTIC_CHECK_ARG(merge >= 1 && G % merge == 0, "merge must divide the group count");
-  ARTIC_CHECK_ARG(g == nullptr || (scale != nullptr && dg != nullptr), "scale and dg required with weight norm");
-  ARTIC_CHECK_ARG((int64_t)rows * row_len == (int64_t)K * G * A * B, "element count mismatch");
-  Unperm up;
-  const int64_t strides[4] = {sk, sg, sa, sb};
-  const int32_t ext[4] = {K, G, A, B};
-  up.n = 0;
-  for (int d = 0; d < 4; ++d)
-    if (ext[d] > 1) { up.stride[up.n] = strides[d]; up.dim_id[up.n] = d; ++up.n; }
-  for (int i = 0; i < up.n; ++i)       // sort by decreasing stride
-    for (int j = i + 1; j < up.n; ++j)
-      if (up.stride[j] > up.stride[i]) {
-        int64_t ts = up.stride[i]; up.stride[i] = up.stride[j]; up.stride[j] = ts;
-        int32_t td = up.dim_id[i]; up.dim_id[i] = up.dim_id[j]; up.dim_id[j] = td;
-      }
-  for (int i = up.n; i < 4; ++i) { up.stride[i] = 1; up.dim_id[i] = 0; }
-  // nestedness check: each stride must be the product of the extents of the smaller-stride dims
-  int64_t expect = 1;
-  for (int i = up.n - 1; i >= 0; --i) {
-    ARTIC_CHECK_ARG(up.stride[i] == expect, "source layout is not a permutation of a contiguous tensor");
-    expect *= ext[up.dim_id[i]];
-  }
+extern "C" int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, void* stream) {
+  ARTIC_CHECK_ARG(descs != nullptr && n >= 0, "bad descriptor table");
+  if (n == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  unprep_kernel<<<rows, 256, 0, st>>>(dWp, v, g != nullptr ? scale : nullptr, rows, row_len, G, A, B, merge, up, dv, dg);
+  wperm_kernel<2><<<dim3(64, (unsigned)n), 256, 0, st>>>(descs);
+  if (any_norm) wn_bwd_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
 }

@@ -1,0 +1,95 @@
+"""Host-side batch assembly on the hot path's input side.
+
+``SpeechCollater`` mirrors reference bin/train.py:865-1098 for the configuration the voc1 EMA
+recipes run (``dataset_mode: a2w``, ``package_mode: random_window``, optional CAR past-sample
+slice): same constructor keywords, same use of ``np.random.randint`` (so a seeded numpy RNG
+yields the same windows as the reference), same integer indexing — checked bit-exactly against
+the reference's own output in tests/golden/collater.npz.  Pure numpy / host work: the batch it
+returns is what ``TrainStep.step`` copies host->device.
+"""
+import numpy as np
+import torch
+
+
+class SpeechCollater(object):
+    """Customized collater for the PyTorch DataLoader in training (reference bin/train.py:865)."""
+
+    def __init__(self, batch_max_steps=20480, hop_size=256, aux_context_window=0, use_noise_input=False,
+                 dataset_mode="a2w", use_spk_id=False, use_ph=False, config=None):
+        assert batch_max_steps % hop_size == 0
+        if dataset_mode != "a2w":
+            raise NotImplementedError("only dataset_mode 'a2w' (articulatory -> waveform) is on the B200 hot path")
+        if use_spk_id or use_ph:
+            raise NotImplementedError("speaker / phoneme conditioning is outside the B200 hot path")
+        config = config or {}
+        if config.get("package_mode", "random_window") != "random_window":
+            raise NotImplementedError("only package_mode 'random_window' (the reference default) is implemented")
+        if "generator2_params" in config or "generator2_type" in config:
+            raise NotImplementedError("two-stage generator cascades are outside the B200 hot path")
+        self.batch_max_steps = batch_max_steps
+        self.batch_max_frames = batch_max_steps // hop_size
+        self.hop_size = hop_size
+        self.aux_context_window = aux_context_window
+        self.use_noise_input = use_noise_input
+        self.dataset_mode = dataset_mode
+        gp = config.get("generator_params", {})
+        self.use_ar = gp.get("use_ar", False)
+        # a2w: the AR context is past WAVEFORM samples (reference :897-905, ar2_len)
+        self.ar_len = int(gp.get("ar_input", 512) / gp.get("out_channels", 1)) if self.use_ar else None
+        self.start_offset = aux_context_window                                   # :919
+        self.end_offset = -(self.batch_max_frames + aux_context_window)          # :920
+        self.config = config
+
+    def window_plan(self, audio_len, art_len, start_frame):
+        """Integer index plan of one item for a given start frame (reference :1009-1027, :1082-1097)."""
+        w0 = start_frame * self.hop_size
+        plan = dict(art=(start_frame - self.aux_context_window,
+                         start_frame + self.batch_max_frames + self.aux_context_window),
+                    wav=(w0, w0 + self.batch_max_steps))
+        if self.use_ar:
+            lo = w0 - self.ar_len
+            plan["ar"] = (max(lo, 0), w0)
+            plan["ar_left_zero_pad"] = max(-lo, 0)
+        return plan
+
+    def __call__(self, batch):
+        """batch: list of dicts with 'audio' (T,) and 'art' (T', C) numpy arrays.
+        Returns dict with 'x' = ((B, C, T') float,), 'y' = (B, 1, T) float [, 'ar' = (B, 1, ar_len)]."""
+        audios, arts = [], []
+        for d in batch:
+            audio, art = d["audio"], d["art"]
+            art = art[:int(len(audio) / self.hop_size)]                          # :983
+            if len(art) + self.end_offset > self.start_offset:                   # :984
+                audios.append(audio)
+                arts.append(art)
+        # one np.random.randint per kept item, in order (reference :1013)
+        starts = np.array([np.random.randint(self.start_offset, len(c) + self.end_offset) for c in arts])
+        plans = [self.window_plan(len(a), len(c), int(s)) for a, c, s in zip(audios, arts, starts)]
+        audio_batch = np.stack([a[p["wav"][0]:p["wav"][1]] for a, p in zip(audios, plans)], axis=0)
+        art_batch = np.stack([c[p["art"][0]:p["art"][1]] for c, p in zip(arts, plans)], axis=0)
+        out = {"audio": torch.tensor(audio_batch, dtype=torch.float).unsqueeze(1),          # (B, 1, T)
+               "art": torch.tensor(art_batch, dtype=torch.float).transpose(2, 1)}           # (B, C, T')
+        out["x"] = (out["art"],)
+        out["y"] = out["audio"]
+        if self.use_ar:
+            ars = []
+            for a, p in zip(audios, plans):
+                ar = a[p["ar"][0]:p["ar"][1]]
+                if p["ar_left_zero_pad"]:
+                    ar = np.pad(ar, (p["ar_left_zero_pad"], 0), "constant", constant_values=0)
+                ars.append(ar)
+            out["ar"] = torch.tensor(np.stack(ars, axis=0), dtype=torch.float).unsqueeze(1)  # (B, 1, ar_len)
+        return out
+
+
+def synthetic_utterances(n_items, n_frames=400, n_feats=13, hop_size=80, seed=0):
+    """Synthetic MNGU0-shaped items ({'audio', 'art'}) for smoke runs without a dataset."""
+    rng = np.random.RandomState(seed)
+    items = []
+    for _ in range(n_items):
+        t = np.arange(n_frames * hop_size)
+        f0 = rng.uniform(80, 300)
+        audio = (0.5 * np.sin(2 * np.pi * f0 * t / 16000.0 + rng.uniform(0, 6.28)) + 0.05 * rng.randn(len(t)))
+        items.append({"audio": np.clip(audio, -1, 1).astype(np.float32),
+                      "art": rng.randn(n_frames, n_feats).astype(np.float32)})
+    return items

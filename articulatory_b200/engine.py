@@ -105,27 +105,37 @@ def tapconv(launches, X: SeqT, W, G, Cig, Cog, Y: Optional[SeqT] = None, Y2: Opt
 # --------------------------------------------------------------------------- #
 # one conv-like layer                                                         #
 # --------------------------------------------------------------------------- #
+def slice_seq(s: SeqT, lo: int, hi: int) -> SeqT:
+    """View of batch items [lo, hi) (the batch is the leading tensor dim in every layout)."""
+    return SeqT(s.t[lo:hi], (hi - lo) * s.n_inner, s.L, s.C, s.n_inner, s.s_outer, s.s_inner, s.s_row)
+
+
 class ConvLayer:
     """A conv / convT / linear layer bound to its torch parameters.
 
     ``in_code`` is the storage dtype of the layer input (and of the forward weight),
     ``out_code`` the dtype of its output (and of the dY / backward weight)."""
 
-    def __init__(self, spec: ConvSpec, name: str, in_code: int, out_code: int):
+    def __init__(self, spec: ConvSpec, name: str, in_code: int, out_code: int, pad_in: bool = False):
         self.spec, self.name, self.in_code, self.out_code = spec, name, in_code, out_code
         # Narrow grouped convs (< 32 channels per group, e.g. the scale discriminator's 128->256
         # g16 layer with 8 -> 16 channels per group) would starve the tensor-core tiles: in the
         # bf16 mode `mg` groups are merged into one super-group whose weight is block-diagonal
-        # (artic_weight_prep `merge`), trading mg x redundant MACs for full MMA tiles.
+        # (artic_wdesc_t.merge), trading mg x redundant MACs for full MMA tiles.
         mg = 1
         if in_code == BF16 and out_code == BF16 and spec.groups > 1:
             while (spec.cig * mg < 32 or spec.cog * mg < 32) and spec.groups % (2 * mg) == 0:
                 mg *= 2
         self.mg = mg
         self.kG, self.kcig, self.kcog = spec.groups // mg, spec.cig * mg, spec.cog * mg   # kernel-facing dims
+        # Odd input widths (the generator's 13 + 128 = 141-channel input conv) are zero-padded to a
+        # multiple of 32 channels so that the layer runs on the tensor-core kernel.
+        if pad_in and in_code == BF16 and out_code == BF16 and spec.groups == 1 and spec.cin >= 32 and spec.cin % 16:
+            self.kcig = (spec.cin + 31) // 32 * 32
         self.v = self.g = self.b = None          # torch parameters (fp32, device)
         self.Wf = self.Wb = self.scale = None    # prepared weights
         self.dWf = None                          # fp32 wgrad accumulator, 'fwd' layout
+        self._own = None                         # single-layer WeightSet (tests / stand-alone use)
 
     # ---- parameters ----------------------------------------------------------
     def bind(self, params: Dict[str, torch.Tensor]):
@@ -143,6 +153,7 @@ class ConvLayer:
         shape = tuple(self.v.shape)
         want = self.spec.weight_shape()
         assert shape == want or shape == want + (1,), f"{n}: weight shape {shape} != {want}"
+        self._own = None
 
     def param_names(self):
         n = self.name
@@ -151,24 +162,21 @@ class ConvLayer:
             names.append(n + ".bias")
         return names
 
+    def _single(self):
+        if self._own is None:
+            self._own = WeightSet([self])
+        return self._own
+
     def prep(self, need_bwd=True):
         """(Re)materialise the effective weights from the current parameters."""
-        s, dev = self.spec, self.v.device
-        rows, row_len = s.wn_rows()
-        if self.g is not None and self.scale is None:
-            self.scale = torch.empty(2 * rows, dtype=torch.float32, device=dev)
-        for direction in ("fwd", "bwd") if need_bwd else ("fwd",):
-            A, B, sk, sg, sa, sb = s.prep_strides(direction)
-            code = self.in_code if direction == "fwd" else self.out_code
-            buf = self.Wf if direction == "fwd" else self.Wb
-            if buf is None or buf.dtype != TORCH_DTYPE[code]:
-                buf = torch.zeros((s.k, self.kG, A * self.mg, B * self.mg), dtype=TORCH_DTYPE[code], device=dev)
-                if direction == "fwd":
-                    self.Wf = buf
-                else:
-                    self.Wb = buf
-            call("artic_weight_prep", ptr(self.v), ptr(self.g), ptr(self.scale), rows, row_len,
-                 s.k, s.groups, A, B, sk, sg, sa, sb, self.mg, ptr(buf), code)
+        self._single().prep()
+
+    def zero_wgrad(self):
+        self._single().zero()
+
+    def finish_grads(self, grads: Dict[str, torch.Tensor]):
+        """dW (prepared layout) -> gradients of the torch parameters (weight-norm backward)."""
+        self._single().unprep(grads)
 
     # ---- compute -------------------------------------------------------------
     def forward(self, X: SeqT, Y=None, Y2=None, **epi):
@@ -179,13 +187,6 @@ class ConvLayer:
         s = self.spec
         lin = (dX if dX is not None else dX2).L
         tapconv(s.dgrad_launches(lin), dY, self.Wb, self.kG, self.kcog, self.kcig, Y=dX, Y2=dX2, Wt=self.Wf, **epi)
-
-    def zero_wgrad(self):
-        if self.dWf is None:
-            s = self.spec
-            self.dWf = torch.zeros((s.k, self.kG, self.kcig, self.kcog), dtype=torch.float32, device=self.v.device)
-        else:
-            self.dWf.zero_()
 
     def wgrad(self, X: SeqT, dY: SeqT, grads: Dict[str, torch.Tensor]):
         """Accumulate dW (prepared layout) and the bias gradient (into grads[name.bias])."""
@@ -204,18 +205,78 @@ class ConvLayer:
         if self.b is not None:
             call("artic_colsum", ptr(dY.t), dY.seq(), dY.N, dY.C, dY.code, ptr(grads[self.name + ".bias"]))
 
-    def finish_grads(self, grads: Dict[str, torch.Tensor]):
-        """dW (prepared layout) -> gradients of the torch parameters (weight-norm backward)."""
-        s = self.spec
-        rows, row_len = s.wn_rows()
-        A, B, sk, sg, sa, sb = s.prep_strides("fwd")
-        n = self.name
-        if self.g is not None:
-            dv, dg = grads[n + ".weight_v"], grads[n + ".weight_g"]
-        else:
-            dv, dg = grads[n + ".weight"], None
-        call("artic_weight_unprep", ptr(self.dWf), ptr(self.v), ptr(self.g), ptr(self.scale), rows, row_len,
-             s.k, s.groups, A, B, sk, sg, sa, sb, self.mg, ptr(dv), ptr(dg))
+class WeightSet:
+    """The prepared weights and weight-gradient accumulators of a set of layers, handled by the
+    batched kernels (artic_weights_prep / artic_weights_unprep: one launch per pass for the
+    whole network instead of three per layer)."""
+
+    def __init__(self, layers: List[ConvLayer]):
+        self.layers = list(layers)
+        dev = self.layers[0].v.device
+        self.dev = dev
+        self.any_norm = int(any(l.g is not None for l in self.layers))
+        sizes = []
+        for l in self.layers:
+            s = l.spec
+            shape_f = (s.k, l.kG, l.kcig, l.kcog)
+            l.Wf = torch.zeros(shape_f, dtype=TORCH_DTYPE[l.in_code], device=dev)
+            l.Wb = torch.zeros((s.k, l.kG, l.kcog, l.kcig), dtype=TORCH_DTYPE[l.out_code], device=dev)
+            l.scale = torch.empty(2 * s.wn_rows()[0], dtype=torch.float32, device=dev) if l.g is not None else None
+            sizes.append(s.k * l.kG * l.kcig * l.kcog)
+        # one flat fp32 accumulator for all weight gradients: a single memset per backward
+        self.dW = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        o = 0
+        for l, n in zip(self.layers, sizes):
+            s = l.spec
+            l.dWf = self.dW[o:o + n].view(s.k, l.kG, l.kcig, l.kcog)
+            o += n
+        self._bufs = [(l.Wf, l.Wb, l.scale, l.dWf) for l in self.layers]
+        self._tables = {}
+
+    def _table(self, grads):
+        key = None if grads is None else tuple(ptr(grads[n]) for l in self.layers for n in l.param_names()[:1])
+        tab = self._tables.get(key)
+        if tab is None:
+            descs = []
+            for l in self.layers:
+                s = l.spec
+                rows, row_len = s.wn_rows()
+                A, B, sk, sg, sa, sb = s.prep_strides("fwd")
+                d = _lib.WDesc()
+                d.v, d.g, d.scale = ptr(l.v), ptr(l.g), ptr(l.scale)
+                d.out_f, d.out_b, d.dWp = ptr(l.Wf), ptr(l.Wb), ptr(l.dWf)
+                if grads is not None:
+                    n = l.name
+                    if l.g is not None:
+                        d.dv, d.dg = ptr(grads[n + ".weight_v"]), ptr(grads[n + ".weight_g"])
+                    else:
+                        d.dv, d.dg = ptr(grads[n + ".weight"]), None
+                d.row_len, d.sk, d.sg, d.sa, d.sb = row_len, sk, sg, sa, sb
+                d.rows, d.K, d.G, d.A, d.B = rows, s.k, s.groups, A, B
+                d.merge, d.a_pad, d.b_pad = l.mg, l.kcig, l.kcog
+                d.dtype_f, d.dtype_b = l.in_code, l.out_code
+                descs.append(d)
+            tab = _lib.upload_structs(descs, self.dev)
+            if len(self._tables) > 4:       # the autograd path hands in fresh grads every backward
+                self._tables = {k: v for k, v in self._tables.items() if k is None}
+            self._tables[key] = tab
+        return tab
+
+    def rebind(self):
+        """Re-attach the buffers to the layers after ConvLayer.bind() (same parameter storage)."""
+        for l, (wf, wb, sc, dw) in zip(self.layers, self._bufs):
+            l.Wf, l.Wb, l.scale, l.dWf = wf, wb, sc, dw
+
+    def prep(self):
+        call("artic_weights_prep", ptr(self._table(None)), len(self.layers), self.any_norm)
+
+    def zero(self):
+        self.dW.zero_()
+
+    def unprep(self, grads: Dict[str, torch.Tensor]):
+        """dW (prepared layout) -> dv / dg of the torch parameters (OVERWRITES those entries of
+        ``grads``; bias gradients were accumulated by ConvLayer.wgrad)."""
+        call("artic_weights_unprep", ptr(self._table(grads)), len(self.layers), self.any_norm)
 
 
 def _zero_grads_like(layers: List[ConvLayer]) -> Dict[str, torch.Tensor]:
@@ -248,13 +309,14 @@ class GeneratorEngine:
         c = code
         L = self.layers = {}
 
-        def add(name, spec, ic=c, oc=c):
+        def add(name, spec, ic=c, oc=c, pad_in=False):
             spec.weight_norm = wn and spec.kind != "linear"
             spec.name = name
-            L[name] = ConvLayer(spec, name, ic, oc)
+            L[name] = ConvLayer(spec, name, ic, oc, pad_in=pad_in)
             return L[name]
 
-        add("input_conv", ConvSpec("conv", in_channels, channels, k=kernel_size, padding=(kernel_size - 1) // 2))
+        add("input_conv", ConvSpec("conv", in_channels, channels, k=kernel_size, padding=(kernel_size - 1) // 2),
+            pad_in=True)
         self.n_blocks = len(resblock_kernel_sizes)
         for i, (s, k) in enumerate(zip(upsample_scales, upsample_kernel_sizes)):
             add(f"upsamples.{i}.1", ConvSpec("convT", channels // 2 ** i, channels // 2 ** (i + 1), k=k, stride=s,
@@ -278,11 +340,18 @@ class GeneratorEngine:
     def bind(self, params):
         for l in self.layers.values():
             l.bind(params)
+        # keep the prepared-weight buffers and descriptor tables while the parameters stay in place
+        # (re-binding happens after every optimizer update; CUDA-graph capture must not see uploads)
+        sig = tuple(ptr(t) for l in self.layers.values() for t in (l.v, l.g, l.b))
+        if getattr(self, "_bind_sig", None) != sig:
+            self.wset = WeightSet(list(self.layers.values()))
+            self._bind_sig = sig
+        else:
+            self.wset.rebind()
         self._prepped = False
 
     def prep_weights(self, need_bwd=True):
-        for l in self.layers.values():
-            l.prep(need_bwd)
+        self.wset.prep()
         self._prepped = True
 
     def param_names(self):
@@ -318,9 +387,10 @@ class GeneratorEngine:
             if save:
                 tape["ar_acts"] = acts
         assert Cc + Ca == self.in_channels, f"in_channels {self.in_channels} != {Cc} + {Ca}"
-        gin = SeqT.empty(B, Tn, Cc + Ca, code, dev)
+        Cpad = L["input_conv"].kcig                      # >= Cc + Ca (zero-padded for the tensor-core path)
+        gin = SeqT.empty(B, Tn, Cpad, code, dev)
         call("artic_gen_input", ptr(c), ptr(ar_feats.t) if ar_feats is not None else None, ptr(gin.t),
-             B, Cc, Ca, Tn, code)
+             B, Cc, Ca, Cpad, Tn, code)
         a = SeqT.empty(B, Tn, L["input_conv"].spec.cout, code, dev)
         L["input_conv"].forward(gin, Y2=a, act=ACT_LRELU, act_slope=slope)
         if save:
@@ -376,8 +446,7 @@ class GeneratorEngine:
         L, code, slope = self.layers, self.code, self.slope
         B = tape["B"]
         dev = dy.device
-        for l in L.values():
-            l.zero_wgrad()
+        self.wset.zero()
         y = tape["y"]
         dyc = dy.permute(0, 2, 1).contiguous().float() if self.out_channels > 1 else dy.contiguous().float()
         dpre = SeqT.empty(B, y.L, self.out_channels, F32, dev)
@@ -430,7 +499,7 @@ class GeneratorEngine:
             ic.dgrad(g, dX=dgin)
             Ca = self.ar_output
             d_ar32 = torch.empty((B, Ca), dtype=torch.float32, device=dev)
-            call("artic_gen_input_bwd", ptr(dgin.t), ptr(d_ar32), B, tape["Cc"], Ca, tape["Tn"], code)
+            call("artic_gen_input_bwd", ptr(dgin.t), ptr(d_ar32), B, tape["Cc"], Ca, gin.C, tape["Tn"], code)
             dz = SeqT.empty(B, 1, Ca, code, dev)
             call("artic_cast", ptr(d_ar32), F32, ptr(dz.t), code, B * Ca)
             acts = tape["ar_acts"]
@@ -441,8 +510,7 @@ class GeneratorEngine:
                     dn = acts[li].like()
                     lay.dgrad(dz, dX=dn, mask=acts[li], mask_slope=0.1)
                     dz = dn
-        for l in L.values():
-            l.finish_grads(grads)
+        self.wset.unprep(grads)
 
     def new_grads(self):
         return _zero_grads_like(list(self.layers.values()))
@@ -464,12 +532,17 @@ class DiscriminatorEngine:
     discriminator per period.  Feature maps are stored in ``code`` dtype, the first conv of
     every chain reads the fp32 signal and the logits are written in fp32."""
 
-    def __init__(self, scales, pool_params, scale_params, follow_official_norm, periods, period_params, code=F32):
+    def __init__(self, scales, pool_params, scale_params, follow_official_norm, periods, period_params, code=F32,
+                 scale_prefix="msd.discriminators.{i}.", period_prefix="mpd.discriminators.{i}."):
+        """``scale_prefix`` / ``period_prefix`` name the parameters of sub-discriminator ``i`` (the
+        stand-alone classes use "discriminators.{i}." or ""); ``scales`` may be 0 and ``periods`` empty."""
         from .convspec import ConvSpec as CS
         self.code = code
-        self.pool = dict(pool_params)
-        self.slope_s = scale_params["nonlinear_activation_params"]["negative_slope"]
-        self.slope_p = period_params["nonlinear_activation_params"]["negative_slope"]
+        self.pool = dict(pool_params or {"kernel_size": 4, "stride": 2, "padding": 2})
+        scale_params = scale_params or {}
+        period_params = period_params or {}
+        self.slope_s = scale_params.get("nonlinear_activation_params", {}).get("negative_slope", 0.1)
+        self.slope_p = period_params.get("nonlinear_activation_params", {}).get("negative_slope", 0.1)
         self.chains: List[_Chain] = []
         sp, pp = scale_params, period_params
         # NOTE reference quirk (SURVEY.md §7): the MSD norm hooks test isinstance(m, Conv2d) on
@@ -490,7 +563,7 @@ class DiscriminatorEngine:
             layers = []
             for li, spec in enumerate(specs):
                 last = li == len(specs) - 1
-                name = f"msd.discriminators.{s}.layers.{li}" + ("" if last else ".0")
+                name = scale_prefix.format(i=s) + f"layers.{li}" + ("" if last else ".0")
                 layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code))
             self.chains.append(_Chain(layers, "scale", scale_index=s))
         for pi, period in enumerate(periods):
@@ -507,7 +580,7 @@ class DiscriminatorEngine:
             layers = []
             for li, spec in enumerate(specs):
                 last = li == len(specs) - 1
-                name = f"mpd.discriminators.{pi}." + ("output_conv" if last else f"convs.{li}.0")
+                name = period_prefix.format(i=pi) + ("output_conv" if last else f"convs.{li}.0")
                 layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code))
             self.chains.append(_Chain(layers, "period", period=period))
         self.layers = {l.name: l for ch in self.chains for l in ch.layers}
@@ -516,11 +589,18 @@ class DiscriminatorEngine:
     def bind(self, params):
         for l in self.layers.values():
             l.bind(params)
+        # keep the prepared-weight buffers and descriptor tables while the parameters stay in place
+        # (re-binding happens after every optimizer update; CUDA-graph capture must not see uploads)
+        sig = tuple(ptr(t) for l in self.layers.values() for t in (l.v, l.g, l.b))
+        if getattr(self, "_bind_sig", None) != sig:
+            self.wset = WeightSet(list(self.layers.values()))
+            self._bind_sig = sig
+        else:
+            self.wset.rebind()
         self._prepped = False
 
     def prep_weights(self, need_bwd=True):
-        for l in self.layers.values():
-            l.prep(need_bwd)
+        self.wset.prep()
         self._prepped = True
 
     def param_names(self):
@@ -530,25 +610,39 @@ class DiscriminatorEngine:
         return _zero_grads_like(list(self.layers.values()))
 
     # ---- forward -------------------------------------------------------------
-    def forward(self, x: torch.Tensor, save=True):
-        """x (B, 1, T) fp32 -> (list of 8 lists of SeqT [feature maps..., logits], tape)."""
+    def forward(self, x: torch.Tensor, save=True, into=None, lo=0):
+        """x (B, 1, T) fp32 -> (list of 8 lists of SeqT [feature maps..., logits], tape).
+
+        ``into`` (a tape of an earlier forward over a batch of >= lo + B items) makes this call
+        write its activations into batch items [lo, lo + B) of that tape's buffers instead of
+        allocating: the train step keeps [fake | real] in ONE 2B batch so that the discriminator
+        backward (and every weight gradient) runs once over both halves."""
         _lib.require_cuda(x, "x")
         assert self._prepped and x.dim() == 3 and x.shape[1] == 1
         B, _, T = x.shape
         dev = x.device
-        x = x.contiguous().float()
-        outs, tape = [], {"B": B, "T": T, "chains": []}
+        if into is not None:
+            assert into["T"] == T and lo + B <= into["B"]
+            x2d = into["x"][lo:lo + B]
+            x2d.copy_(x.reshape(B, T))
+        else:
+            x2d = x.contiguous().float().view(B, T)
+
+        def take(full: SeqT):
+            return slice_seq(full, lo, lo + B)
+
+        outs, tape = [], {"B": B, "T": T, "x": x2d, "chains": [], "xp": {}}
         # AvgPool pyramid (hifigan.py:733-736)
         k, st, pd = self.pool["kernel_size"], self.pool["stride"], self.pool["padding"]
-        sigs = [SeqT(x.view(B, T, 1), B, T, 1)]
+        sigs = [SeqT(x2d.view(B, T, 1), B, T, 1)]
         n_scales = sum(1 for c in self.chains if c.kind == "scale")
         for s in range(1, n_scales):
             lp = sigs[-1].L
-            lo = (lp + 2 * pd - k) // st + 1
-            t = torch.empty((B, lo, 1), dtype=torch.float32, device=dev)
-            call("artic_avgpool1d", ptr(sigs[-1].t), ptr(t), B, lp, lo, k, st, pd, F32)
-            sigs.append(SeqT(t, B, lo, 1))
-        for ch in self.chains:
+            lo_ = (lp + 2 * pd - k) // st + 1
+            nxt = take(into["sigs"][s]) if into is not None else SeqT.empty(B, lo_, 1, F32, dev)
+            call("artic_avgpool1d", ptr(sigs[-1].t), ptr(nxt.t), B, lp, lo_, k, st, pd, F32)
+            sigs.append(nxt)
+        for ci, ch in enumerate(self.chains):
             if ch.kind == "scale":
                 h = sigs[ch.scale_index]
                 slope = self.slope_s
@@ -556,19 +650,23 @@ class DiscriminatorEngine:
                 p = ch.period
                 Tp = T if T % p == 0 else T + (p - T % p)                 # hifigan.py:413-416
                 if Tp != T:
-                    xp = torch.empty((B, Tp), dtype=torch.float32, device=dev)
-                    call("artic_reflect_pad_right", ptr(x), ptr(xp), B, T, Tp, F32)
+                    xp = into["xp"][ci][lo:lo + B] if into is not None else torch.empty((B, Tp), dtype=torch.float32, device=dev)
+                    call("artic_reflect_pad_right", ptr(x2d), ptr(xp), B, T, Tp, F32)
                 else:
-                    xp = x.view(B, T)
+                    xp = x2d
+                tape["xp"][ci] = xp
                 H = Tp // p
                 h = SeqT(xp, B * p, H, 1, n_inner=p, s_outer=Tp, s_inner=1, s_row=p)
                 slope = self.slope_p
             acts = [h]
             n = len(ch.layers)
             for li, lay in enumerate(ch.layers):
-                lo = lay.spec.out_len(h.L)
+                lo_ = lay.spec.out_len(h.L)
                 last = li == n - 1
-                o = h.like(code=F32 if last else self.code, C=lay.spec.cout, L=lo)
+                if into is not None:
+                    o = take(into["chains"][ci][li + 1])
+                else:
+                    o = h.like(code=F32 if last else self.code, C=lay.spec.cout, L=lo_)
                 if last:
                     lay.forward(h, Y=o)
                 else:
@@ -580,6 +678,14 @@ class DiscriminatorEngine:
         tape["sigs"] = sigs
         return outs, (tape if save else None)
 
+    @staticmethod
+    def slice_tape(tape, lo, hi):
+        """The tape of batch items [lo, hi) of a larger forward (views, no copies)."""
+        return {"B": hi - lo, "T": tape["T"], "x": tape["x"][lo:hi],
+                "xp": {ci: t[lo:hi] for ci, t in tape["xp"].items()},
+                "sigs": [slice_seq(s, lo, hi) for s in tape["sigs"]],
+                "chains": [[slice_seq(a, lo, hi) for a in acts] for acts in tape["chains"]]}
+
     # ---- backward ------------------------------------------------------------
     def backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True):
         """douts: per chain a list (same length as the chain's outputs) of SeqT gradients or
@@ -589,8 +695,7 @@ class DiscriminatorEngine:
         B, T = tape["B"], tape["T"]
         dev = tape["sigs"][0].t.device
         if grads is not None:
-            for l in self.layers.values():
-                l.zero_wgrad()
+            self.wset.zero()
         dx = torch.zeros((B, 1, T), dtype=torch.float32, device=dev) if need_dx else None
         n_scales = len(tape["sigs"])
         dsig = [None] * n_scales
@@ -630,6 +735,5 @@ class DiscriminatorEngine:
             # dx += dsig[0]  (via the reflect-pad backward with Lp == L: plain accumulate)
             call("artic_reflect_pad_right_bwd", ptr(dsig[0].t), ptr(dx), B, T, T, 1, F32)
         if grads is not None:
-            for l in self.layers.values():
-                l.finish_grads(grads)
+            self.wset.unprep(grads)
         return dx

@@ -337,77 +337,83 @@ class _DiscFn(torch.autograd.Function):
         return (None, None, None, dx) + pg
 
 
-class HiFiGANMultiScaleMultiPeriodDiscriminator(_EngineModule):
-    """HiFi-GAN multi-scale + multi-period discriminator (reference models/hifigan.py:741-825).
+_DEFAULT_SCALE_PARAMS = {
+    "in_channels": 1, "out_channels": 1, "kernel_sizes": [15, 41, 5, 3], "channels": 128,
+    "max_downsample_channels": 1024, "max_groups": 16, "bias": True,
+    "downsample_scales": [2, 2, 4, 4, 1], "nonlinear_activation": "LeakyReLU",
+    "nonlinear_activation_params": {"negative_slope": 0.1}}
+_DEFAULT_PERIOD_PARAMS = {
+    "in_channels": 1, "out_channels": 1, "kernel_sizes": [5, 3], "channels": 32,
+    "downsample_scales": [3, 3, 3, 3, 1], "max_downsample_channels": 1024, "bias": True,
+    "nonlinear_activation": "LeakyReLU", "nonlinear_activation_params": {"negative_slope": 0.1},
+    "use_weight_norm": True, "use_spectral_norm": False}
+_DEFAULT_POOL_PARAMS = {"kernel_size": 4, "stride": 2, "padding": 2}
 
-    ``forward(x (B,1,T))`` returns 8 lists (3 scales, then 5 periods); each inner list holds
-    the per-layer feature maps followed by the logits, with the reference's shapes."""
 
-    def __init__(self, scales=3, scale_downsample_pooling="AvgPool1d",
-                 scale_downsample_pooling_params={"kernel_size": 4, "stride": 2, "padding": 2},
-                 scale_discriminator_params={
-                     "in_channels": 1, "out_channels": 1, "kernel_sizes": [15, 41, 5, 3], "channels": 128,
-                     "max_downsample_channels": 1024, "max_groups": 16, "bias": True,
-                     "downsample_scales": [2, 2, 4, 4, 1], "nonlinear_activation": "LeakyReLU",
-                     "nonlinear_activation_params": {"negative_slope": 0.1}},
-                 follow_official_norm=True, periods=[2, 3, 5, 7, 11],
-                 period_discriminator_params={
-                     "in_channels": 1, "out_channels": 1, "kernel_sizes": [5, 3], "channels": 32,
-                     "downsample_scales": [3, 3, 3, 3, 1], "max_downsample_channels": 1024, "bias": True,
-                     "nonlinear_activation": "LeakyReLU", "nonlinear_activation_params": {"negative_slope": 0.1},
-                     "use_weight_norm": True, "use_spectral_norm": False},
-                 precision=None):
-        super().__init__()
-        if scale_downsample_pooling != "AvgPool1d":
+class _DiscriminatorBase(_EngineModule):
+    """Shared body of the five discriminator plugin classes: validates the reference keywords,
+    builds the engine topology once on the host to enumerate the layers, and mirrors it with
+    torch parameter containers named like the reference's modules (``layers.N[.0]``,
+    ``convs.N.0``, ``output_conv``, under ``scale_prefix`` / ``period_prefix``)."""
+
+    def _setup(self, scales, pool, pool_params, scale_params, follow_official_norm, periods, period_params,
+               scale_prefix, period_prefix, precision):
+        if pool != "AvgPool1d":
             raise NotImplementedError("only AvgPool1d pooling is implemented")
-        if period_discriminator_params.get("use_spectral_norm", False):
-            raise NotImplementedError("spectral norm is not on the hot path (yaml: use_spectral_norm false)")
-        for prm in (scale_discriminator_params, period_discriminator_params):
+        scale_params = copy.deepcopy(scale_params) if scale_params else None
+        period_params = copy.deepcopy(period_params) if period_params else None
+        if period_params is not None:
+            period_params = dict(_DEFAULT_PERIOD_PARAMS, **period_params)
+            period_params.pop("period", None)
+            if period_params.get("use_spectral_norm", False):
+                raise NotImplementedError("spectral norm is not on the hot path (yaml: use_spectral_norm false)")
+            ks = period_params["kernel_sizes"]
+            assert len(ks) == 2 and ks[0] % 2 == 1 and ks[1] % 2 == 1, "Kernel size must be odd number."
+        if scale_params is not None:
+            scale_params = dict(_DEFAULT_SCALE_PARAMS, **scale_params)
+            ks = scale_params["kernel_sizes"]
+            assert len(ks) == 4 and all(k % 2 == 1 for k in ks)
+        for prm in (scale_params, period_params):
+            if prm is None:
+                continue
             if prm.get("nonlinear_activation", "LeakyReLU") != "LeakyReLU":
                 raise NotImplementedError("only LeakyReLU is implemented on the B200 path")
             assert prm.get("bias", True), "bias=False is not on the hot path"
         self.precision = DEFAULT_PRECISION if precision is None else precision
-        self._cfg = dict(scales=scales, pool_params=copy.deepcopy(scale_downsample_pooling_params),
-                         scale_params=copy.deepcopy(scale_discriminator_params),
+        self._cfg = dict(scales=scales, pool_params=copy.deepcopy(pool_params), scale_params=scale_params,
                          follow_official_norm=follow_official_norm, periods=list(periods),
-                         period_params=copy.deepcopy(period_discriminator_params))
-        # Build the engine topology once on the host to enumerate layers, then mirror it with
-        # torch containers named like the reference (msd.discriminators.N.layers.M[.0], ...).
+                         period_params=period_params, scale_prefix=scale_prefix, period_prefix=period_prefix)
         topo = DiscriminatorEngine(code=_lib.F32, **self._cfg)
-        self.msd = torch.nn.Module()
-        self.msd.discriminators = torch.nn.ModuleList()
-        self.mpd = torch.nn.Module()
-        self.mpd.discriminators = torch.nn.ModuleList()
-        use_wn_p = period_discriminator_params.get("use_weight_norm", True)
+        use_wn_p = (period_params or {}).get("use_weight_norm", True)
         for ch in topo.chains:
-            d = torch.nn.Module()
             n = len(ch.layers)
-            if ch.kind == "scale":
-                d.layers = torch.nn.ModuleList()
-                for li, lay in enumerate(ch.layers):
-                    s = lay.spec
+            for li, lay in enumerate(ch.layers):
+                s = lay.spec
+                if ch.kind == "scale":
+                    # reference quirk (hifigan.py:645-663): the norm hooks test isinstance(m, Conv2d) on
+                    # Conv1d layers, so no weight / spectral norm is ever applied to a scale discriminator
                     conv = torch.nn.Conv1d(s.cin, s.cout, s.k, stride=s.stride, padding=s.padding, groups=s.groups)
-                    # reference quirk: no norm is ever applied to the scale discriminators
-                    d.layers.append(conv if li == n - 1 else torch.nn.Sequential(conv, torch.nn.LeakyReLU(0.1)))
-                self.msd.discriminators.append(d)
-            else:
-                d.convs = torch.nn.ModuleList()
-                for li, lay in enumerate(ch.layers):
-                    s = lay.spec
+                else:
                     conv = torch.nn.Conv2d(s.cin, s.cout, (s.k, 1), (s.stride, 1), padding=(s.padding, 0))
                     if use_wn_p:
                         conv = _wn(conv)
-                    if li == n - 1:
-                        d.output_conv = conv
-                    else:
-                        d.convs.append(torch.nn.Sequential(conv, torch.nn.LeakyReLU(0.1)))
-                self.mpd.discriminators.append(d)
+                self._place(lay.name, conv)
         self._init_engine_state()
+
+    def _place(self, dotted, module):
+        """Register ``module`` under a dotted path, creating plain container modules on the way."""
+        parts = dotted.split(".")
+        node = self
+        for part in parts[:-1]:
+            if part not in node._modules:
+                node.add_module(part, torch.nn.Module())
+            node = node._modules[part]
+        node.add_module(parts[-1], module)
 
     def _build_engine(self):
         return DiscriminatorEngine(code=_PRECISIONS[self.precision], **self._cfg)
 
-    def forward(self, x):
+    def _forward_lists(self, x):
         params = [p for _, p in self.named_parameters()]
         need_w = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         need_x = torch.is_grad_enabled() and x.requires_grad
@@ -418,3 +424,87 @@ class HiFiGANMultiScaleMultiPeriodDiscriminator(_EngineModule):
             outs.append(list(flat[i:i + n]))
             i += n
         return outs
+
+    def forward(self, x):
+        return self._forward_lists(x)
+
+
+class HiFiGANPeriodDiscriminator(_DiscriminatorBase):
+    """HiFiGAN period discriminator (reference models/hifigan.py:317-440): ``forward(x (B,1,T))`` returns
+    the list of the 5 feature maps (B, C, T/p', p) followed by the flattened logits."""
+
+    def __init__(self, in_channels=1, out_channels=1, period=3, kernel_sizes=[5, 3], channels=32,
+                 downsample_scales=[3, 3, 3, 3, 1], max_downsample_channels=1024, bias=True,
+                 nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
+                 use_weight_norm=True, use_spectral_norm=False, precision=None):
+        super().__init__()
+        if use_weight_norm and use_spectral_norm:
+            raise ValueError("Either use use_weight_norm or use_spectral_norm.")
+        self.period = period
+        pp = dict(in_channels=in_channels, out_channels=out_channels, kernel_sizes=kernel_sizes, channels=channels,
+                  downsample_scales=downsample_scales, max_downsample_channels=max_downsample_channels, bias=bias,
+                  nonlinear_activation=nonlinear_activation, nonlinear_activation_params=nonlinear_activation_params,
+                  use_weight_norm=use_weight_norm, use_spectral_norm=use_spectral_norm)
+        self._setup(0, "AvgPool1d", None, None, False, [period], pp, "", "", precision)
+
+    def forward(self, x):
+        return self._forward_lists(x)[0]
+
+
+class HiFiGANMultiPeriodDiscriminator(_DiscriminatorBase):
+    """HiFiGAN multi-period discriminator (reference models/hifigan.py:443-500): list of per-period lists."""
+
+    def __init__(self, periods=[2, 3, 5, 7, 11], discriminator_params=_DEFAULT_PERIOD_PARAMS, precision=None):
+        super().__init__()
+        self._setup(0, "AvgPool1d", None, None, False, periods, discriminator_params, "", "discriminators.{i}.",
+                    precision)
+
+
+class HiFiGANScaleDiscriminator(_DiscriminatorBase):
+    """HiFi-GAN scale discriminator (reference models/hifigan.py:503-663): list of the 7 feature maps
+    followed by the logits (B, 1, T')."""
+
+    def __init__(self, in_channels=1, out_channels=1, kernel_sizes=[15, 41, 5, 3], channels=128,
+                 max_downsample_channels=1024, max_groups=16, bias=True, downsample_scales=[2, 2, 4, 4, 1],
+                 nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
+                 use_weight_norm=True, use_spectral_norm=False, precision=None):
+        super().__init__()
+        if use_weight_norm and use_spectral_norm:
+            raise ValueError("Either use use_weight_norm or use_spectral_norm.")
+        sp = dict(in_channels=in_channels, out_channels=out_channels, kernel_sizes=kernel_sizes, channels=channels,
+                  max_downsample_channels=max_downsample_channels, max_groups=max_groups, bias=bias,
+                  downsample_scales=downsample_scales, nonlinear_activation=nonlinear_activation,
+                  nonlinear_activation_params=nonlinear_activation_params)
+        self._setup(1, "AvgPool1d", None, sp, False, [], None, "", "", precision)
+
+    def forward(self, x):
+        return self._forward_lists(x)[0]
+
+
+class HiFiGANMultiScaleDiscriminator(_DiscriminatorBase):
+    """HiFi-GAN multi-scale discriminator (reference models/hifigan.py:666-738): list of per-scale lists,
+    scale i seeing the input pooled i times."""
+
+    def __init__(self, scales=3, downsample_pooling="AvgPool1d", downsample_pooling_params=_DEFAULT_POOL_PARAMS,
+                 discriminator_params=_DEFAULT_SCALE_PARAMS, follow_official_norm=False, precision=None):
+        super().__init__()
+        self._setup(scales, downsample_pooling, downsample_pooling_params, discriminator_params,
+                    follow_official_norm, [], None, "discriminators.{i}.", "", precision)
+
+
+class HiFiGANMultiScaleMultiPeriodDiscriminator(_DiscriminatorBase):
+    """HiFi-GAN multi-scale + multi-period discriminator (reference models/hifigan.py:741-825).
+
+    ``forward(x (B,1,T))`` returns 8 lists (3 scales, then 5 periods); each inner list holds
+    the per-layer feature maps followed by the logits, with the reference's shapes."""
+
+    def __init__(self, scales=3, scale_downsample_pooling="AvgPool1d",
+                 scale_downsample_pooling_params=_DEFAULT_POOL_PARAMS,
+                 scale_discriminator_params=_DEFAULT_SCALE_PARAMS,
+                 follow_official_norm=True, periods=[2, 3, 5, 7, 11],
+                 period_discriminator_params=_DEFAULT_PERIOD_PARAMS,
+                 precision=None):
+        super().__init__()
+        self._setup(scales, scale_downsample_pooling, scale_downsample_pooling_params, scale_discriminator_params,
+                    follow_official_norm, periods, period_discriminator_params,
+                    "msd.discriminators.{i}.", "mpd.discriminators.{i}.", precision)

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from ._lib import F32, call, ptr
-from .engine import SeqT
+from .engine import SeqT, slice_seq
 from .losses.spectral import MelSpectrogramLoss, MultiResolutionSTFTLoss
 from .optim import FusedAdam
 
@@ -85,27 +85,29 @@ class TrainStep:
         self.ar_len = generator._cfg["ar_input"] if generator.use_ar else 0
 
     # ------------------------------------------------------------------------------
-    def _disc_input(self, ar, y):
-        B, _, T = y.shape
+    def _disc_input(self, ar, ys):
+        """cat([ar, y], dim=2) for every y in ``ys`` stacked along the batch (bin/train.py:345-346):
+        (len(ys) * B, 1, La + T) fp32."""
+        B, _, T = ys[0].shape
         La = self.ar_len
-        out = torch.empty((B, 1, La + T), dtype=torch.float32, device=self.dev)
-        call("artic_concat_time", ptr(ar) if La else None, ptr(y), ptr(out), B, La, T, La + T, F32)
+        out = torch.empty((len(ys) * B, 1, La + T), dtype=torch.float32, device=self.dev)
+        for i, y in enumerate(ys):
+            call("artic_concat_time", ptr(ar) if La else None, ptr(y), ptr(out[i * B:]), B, La, T, La + T, F32)
         return out
 
-    def _adv_seed(self, outs, target, slot, scale_w, want_grad):
-        """sum over discriminators of mean((logits - target)^2) -> slots[slot]; returns per-chain
-        logits gradients (scaled by scale_w) when want_grad."""
-        grads = []
-        for lst in outs:
+    def _adv_seed(self, outs, target, slot, scale_w, grads=None, lo=0):
+        """sum over discriminators of mean((logits - target)^2) -> slots[slot]; writes the logits
+        gradients (scaled by scale_w) into batch items [lo, lo + B) of ``grads`` when given."""
+        for ci, lst in enumerate(outs):
             lg = lst[-1]
             n = lg.numel()
             call("artic_sqerr_sum", ptr(lg.t), n, float(target), 1.0 / n, ptr(self.slots[slot:]), lg.code)
-            if want_grad:
-                g = lg.like()
+            if grads is not None:
+                g = slice_seq(grads[ci], lo, lo + lg.N // lg.n_inner)
                 call("artic_sqerr_bwd", ptr(lg.t), n, float(target), scale_w / n, ptr(g.t), 0, lg.code)
-                grads.append(g)
-        return grads
 
+    # Both discriminator inputs of a phase travel as ONE batch [fake | real] (2B items): one set
+    # of launches per layer, and in the D phase one backward / one weight gradient over both.
     def _phase_g(self, x, y, ar, train_d_active):
         G, D = self.G, self.D
         engG = G._ensure_ready()
@@ -125,14 +127,15 @@ class TrainStep:
             n = self.mel.numel(B, T)
             self.mel.accumulate(y2d, t2d, 1.0 / n, self.slots[_MEL:])
             self.mel.backward_into(y2d, t2d, self.l_aux * inv_w / n, dy)
-        real = None
+        tape2 = None
         if train_d_active:                                                    # :350-364
             engD = D._ensure_ready()
-            outs_f, tape_f = engD.forward(self._disc_input(ar, y_), save=True)
-            outs_r, tape_r = engD.forward(self._disc_input(ar, y), save=True)
-            real = (outs_r, tape_r)
+            outs2, tape2 = engD.forward(self._disc_input(ar, (y_, y)), save=True)
+            outs_f = [[slice_seq(o, 0, B) for o in lst] for lst in outs2]
+            outs_r = [[slice_seq(o, B, 2 * B) for o in lst] for lst in outs2]
+            lg_grads = [lst[-1].like() for lst in outs_f]
+            self._adv_seed(outs_f, 1.0, _ADV, self.l_adv * inv_w, lg_grads)
             douts = []
-            lg_grads = self._adv_seed(outs_f, 1.0, _ADV, self.l_adv * inv_w, True)
             for ci, (lf, lr_) in enumerate(zip(outs_f, outs_r)):
                 dl = []
                 for a, b in zip(lf[:-1], lr_[:-1]):
@@ -143,29 +146,34 @@ class TrainStep:
                     dl.append(g)
                 dl.append(lg_grads[ci])
                 douts.append(dl)
-            d_in = engD.backward(tape_f, douts, grads=None, need_dx=True)    # dgrad only
+            d_in = engD.backward(engD.slice_tape(tape2, 0, B), douts, grads=None, need_dx=True)    # dgrad only
             La = self.ar_len
             call("artic_add_rows", ptr(d_in) + 4 * La, La + T, ptr(dy), T, B, T)
         self.optG.zero_grad()
         engG.backward(tapeG, dy, self.optG.grad_views)
-        return real
+        return tape2
 
-    def _phase_d(self, x, y, ar, real):
+    def _phase_d(self, x, y, ar, tape2):
         G, D = self.G, self.D
         engG = G._ensure_ready()          # re-materialises the updated generator weights
         engD = D._ensure_ready()
+        B = y.shape[0]
         inv_w = 1.0 / self.world
         y_, _ = engG.forward(x, ar, save=False)                               # bin/train.py:390-400
-        outs_f, tape_f = engD.forward(self._disc_input(ar, y_), save=True)
-        if real is None:
-            real = engD.forward(self._disc_input(ar, y), save=True)
-        outs_r, tape_r = real
-        g_r = self._adv_seed(outs_r, 1.0, _REAL, inv_w, True)                 # :415-418
-        g_f = self._adv_seed(outs_f, 0.0, _FAKE, inv_w, True)
+        if tape2 is None:
+            _, tape2 = engD.forward(self._disc_input(ar, (y_, y)), save=True)
+        else:
+            # D(real) is REUSED from the G phase; D(fake) overwrites the stale fake half in place
+            engD.forward(self._disc_input(ar, (y_,)), save=True, into=tape2, lo=0)
+        outs2 = [acts[1:] for acts in tape2["chains"]]
+        outs_f = [[slice_seq(lst[-1], 0, B)] for lst in outs2]
+        outs_r = [[slice_seq(lst[-1], B, 2 * B)] for lst in outs2]
+        lg_grads = [lst[-1].like() for lst in outs2]
+        self._adv_seed(outs_r, 1.0, _REAL, inv_w, lg_grads, lo=B)             # :415-418
+        self._adv_seed(outs_f, 0.0, _FAKE, inv_w, lg_grads, lo=0)
         self.optD.zero_grad()
-        for outs, tape, gl in ((outs_r, tape_r, g_r), (outs_f, tape_f, g_f)):
-            douts = [[None] * (len(lst) - 1) + [gl[ci]] for ci, lst in enumerate(outs)]
-            engD.backward(tape, douts, grads=self.optD.grad_views, need_dx=False)
+        douts = [[None] * (len(lst) - 1) + [lg_grads[ci]] for ci, lst in enumerate(outs2)]
+        engD.backward(tape2, douts, grads=self.optD.grad_views, need_dx=False)
 
     # The step is cut into three segments so that the (optional) data-parallel gradient
     # all-reduce can run between CUDA-graph replays:  seg1 = G phase up to dL/dθ_G,

@@ -46,6 +46,9 @@ const char* artic_arch(void);     /* "sm_100a" */
 const char* artic_last_error(void);
 /* Debug / tuning knobs of the tensor-core path (key 0..7); not part of the reference surface. */
 int artic_debug_set(int key, int value);
+/* Debug: device buffer (>= 4001 int64, zeroed) into which CTA 0 of the tensor-core conv kernel records a
+ * (tag, clock64) timeline; NULL disables. */
+int artic_debug_buffer(void* dev_buf);
 
 /* Addressing of one channels-last sequence batch (see header comment). */
 typedef struct {
@@ -122,40 +125,45 @@ int artic_colsum(const void* dY, const artic_seq_t* y, int32_t N, int32_t C, int
 /*
  * Weight preparation (replaces the per-forward torch._weight_norm hook,
  * models/hifigan.py:268-278,430-438 — w = g * v / ||v||, norm over all dims but 0 —
- * plus the relayout the kernels want).  Source: a torch weight viewed as
- * [rows][row_len] fp32 with logical dims (K taps, G groups, A in-channels, B out-channels)
- * at element strides (sk, sg, sa, sb).  Output: [K][G][A][B] in `dtype`; with merge = m > 1
- * (m divides G) the output is the BLOCK-DIAGONAL layout [K][G/m][m*A][m*B] in which m narrow
- * groups form one super-group (only the diagonal blocks are written: zero the buffer once),
- * so that grouped convs with < 32 channels per group still fill tensor-core tiles.
- * g == NULL means a plain (un-normalised) weight.  `scale` (2*rows floats, may be NULL
- * iff g == NULL) receives g/||v|| in [0,rows) and ||v|| in [rows,2*rows) for the backward.
+ * plus the relayout the kernels want), batched over all layers of a network in ONE launch
+ * per pass.  One descriptor per layer, the table lives in DEVICE memory:
+ *
+ *   v      torch weight, fp32, viewed as [rows][row_len] for the norm and through the element
+ *          strides (sk, sg, sa, sb) of its logical dims (K taps, G groups, A in-ch/group,
+ *          B out-ch/group) for the relayout;  g = weight_g (rows floats) or NULL (plain weight)
+ *   scale  2*rows floats (NULL iff g == NULL): g/||v|| in [0,rows), ||v|| in [rows,2*rows)
+ *   out_f  'fwd' layout [K][G/m][a_pad][b_pad] in dtype_f          (NULL = skip)
+ *   out_b  'bwd' (transposed) layout [K][G/m][b_pad][a_pad] in dtype_b  (NULL = skip)
+ *          m = merge > 1 packs m narrow groups into one BLOCK-DIAGONAL super-group (a_pad >= m*A,
+ *          b_pad >= m*B) so that grouped convs with < 32 channels per group still fill
+ *          tensor-core tiles; a_pad / b_pad > m*A / m*B zero-pads odd channel counts (141 -> 144).
+ *          Only the live entries are written: zero the buffers once.
+ *   dWp    fp32 gradient in the 'fwd' layout (written by artic_tapconv_wgrad)
+ *   dv,dg  gradients of v and g in torch layout, OVERWRITTEN by artic_weights_unprep
  */
-int artic_weight_prep(const float* v, const float* g, float* scale, int32_t rows, int64_t row_len,
-                      int32_t K, int32_t G, int32_t A, int32_t B,
-                      int64_t sk, int64_t sg, int64_t sa, int64_t sb, int32_t merge,
-                      void* out, int32_t dtype, void* stream);
+typedef struct {
+  const float* v; const float* g; float* scale;
+  void* out_f; void* out_b;
+  const float* dWp; float* dv; float* dg;
+  int64_t row_len, sk, sg, sa, sb;
+  int32_t rows, K, G, A, B, merge, a_pad, b_pad, dtype_f, dtype_b;
+} artic_wdesc_t;
 
-/*
- * Backward of artic_weight_prep: dWp is fp32 [K][G][A][B] (or the block-diagonal layout for
- * merge > 1, of which only the diagonal blocks are read).  Writes dv (torch layout,
- * fp32) and dg (rows floats; NULL for a plain weight, in which case dv = permuted dWp).
- * Results are ADDED to dv / dg (autograd accumulation semantics); zero them first.
- */
-int artic_weight_unprep(const float* dWp, const float* v, const float* g, const float* scale,
-                        int32_t rows, int64_t row_len, int32_t K, int32_t G, int32_t A, int32_t B,
-                        int64_t sk, int64_t sg, int64_t sa, int64_t sb, int32_t merge,
-                        float* dv, float* dg, void* stream);
+/* scale + out_f + out_b of every descriptor (any_norm = 0 skips the norm pass). */
+int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, void* stream);
+/* Backward of artic_weights_prep: dWp -> dv (and dg, through the weight-norm Jacobian). */
+int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, void* stream);
 
 /* ---- small fused elementwise ops on the path ---------------------------------------- */
 
 /* Generator input assembly (models/hifigan.py:209-211): out[b,t,:] = cat(c[b,:,t], ar_feats[b,:])
  * c is (B, Cc, T) channel-FIRST fp32 (the plugin boundary), ar_feats (B, Ca) in `dtype`
- * (may be NULL with Ca = 0); out is channels-last (B, T, Cc+Ca) in `dtype`. */
+ * (may be NULL with Ca = 0); out is channels-last (B, T, Cpad) in `dtype`, Cpad >= Cc+Ca, the
+ * extra channels written as zeros (pads 141 channels to a tensor-core friendly 160). */
 int artic_gen_input(const float* c, const void* ar_feats, void* out, int32_t B, int32_t Cc,
-                    int32_t Ca, int32_t T, int32_t dtype, void* stream);
+                    int32_t Ca, int32_t Cpad, int32_t T, int32_t dtype, void* stream);
 /* its backward wrt ar_feats: d_ar[b,a] = sum_t dX[b,t,Cc+a]  (fp32 out, overwritten) */
-int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int32_t Ca,
+int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int32_t Ca, int32_t Cpad,
                         int32_t T, int32_t dtype, void* stream);
 
 /* MRF average + activation (models/hifigan.py:226-230 and the LeakyReLU of the next

@@ -1,0 +1,182 @@
+"""GPU parity of the remaining plugin surface: the stand-alone discriminator classes, the causal
+conv layers, chunked AR decoding (ar_loop / BatchedARDecoder), load_model and the train CLI."""
+import copy
+import os
+import warnings
+
+import pytest
+import torch
+import torch.nn.functional as F
+import yaml
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _small_disc_params(golden):
+    dp = golden["discriminator_params"]
+    return copy.deepcopy(dp["scale_discriminator_params"]), copy.deepcopy(dp["period_discriminator_params"])
+
+
+def test_standalone_discriminators_vs_oracle(golden):
+    from articulatory_b200 import models as M
+    from oracle import torch_oracle as O
+    sp, pp = _small_disc_params(golden)
+    x = torch.cat([golden["batch"]["ar"], golden["batch"]["y"]], dim=2)       # (2, 1, 2512)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(3)
+        pd = M.HiFiGANPeriodDiscriminator(period=5, **pp)
+        mpd = M.HiFiGANMultiPeriodDiscriminator(periods=[2, 3], discriminator_params=pp)
+        sd_ = M.HiFiGANScaleDiscriminator(**sp)
+        msd = M.HiFiGANMultiScaleDiscriminator(scales=2, discriminator_params=sp,
+                                               downsample_pooling_params={"kernel_size": 4, "stride": 2, "padding": 2})
+    with torch.no_grad():
+        # single period discriminator
+        ref = O.period_discriminator_forward({"d." + k: v for k, v in pd.state_dict().items()}, "d", pp, 5, x)
+        got = pd.to(DEV)(x.to(DEV))
+        assert len(got) == len(ref) == 6
+        for a, r in zip(got, ref):
+            assert a.shape == r.shape and rel_err(a.float().cpu(), r) < 1e-4
+        # multi period
+        got = mpd.to(DEV)(x.to(DEV))
+        sdm = mpd.state_dict()
+        for i, p in enumerate((2, 3)):
+            ref = O.period_discriminator_forward({k: v.cpu() for k, v in sdm.items()}, f"discriminators.{i}", pp, p, x)
+            for a, r in zip(got[i], ref):
+                assert a.shape == r.shape and rel_err(a.float().cpu(), r) < 1e-4
+        # single scale
+        ref = O.scale_discriminator_forward({"d." + k: v for k, v in sd_.state_dict().items()}, "d", sp, x)
+        got = sd_.to(DEV)(x.to(DEV))
+        assert len(got) == len(ref) == 8
+        for a, r in zip(got, ref):
+            assert a.shape == r.shape and rel_err(a.float().cpu(), r) < 1e-4
+        # multi scale: scale 1 sees the AvgPool1d(4, 2, 2) of the input
+        got = msd.to(DEV)(x.to(DEV))
+        sdm = {k: v.cpu() for k, v in msd.state_dict().items()}
+        xs = x
+        for i in range(2):
+            ref = O.scale_discriminator_forward(sdm, f"discriminators.{i}", sp, xs)
+            for a, r in zip(got[i], ref):
+                assert a.shape == r.shape and rel_err(a.float().cpu(), r) < 1e-4
+            xs = F.avg_pool1d(xs, 4, 2, 2)
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+def test_causal_convs_vs_torch(prec, tol):
+    """CausalConv1d / CausalConvTranspose1d == reference layers/causal_conv.py semantics (pad-left + trim)."""
+    from articulatory_b200.layers import CausalConv1d, CausalConvTranspose1d
+    torch.manual_seed(0)
+    for k, d in ((3, 1), (5, 2), (7, 3)):
+        m = CausalConv1d(32, 64, k, dilation=d)
+        m.precision = prec
+        x = torch.randn(2, 32, 101, requires_grad=True)
+        ref = F.conv1d(F.pad(x, ((k - 1) * d, 0)), m.conv.weight, m.conv.bias, dilation=d)[:, :, :101]
+        dy = torch.randn_like(ref)
+        gx, gw, gb = torch.autograd.grad(ref, [x, m.conv.weight, m.conv.bias], dy)
+        m = m.to(DEV)
+        xd = x.detach().to(DEV).requires_grad_(True)
+        y = m(xd)
+        assert y.shape == ref.shape and rel_err(y.cpu(), ref) < tol
+        y.backward(dy.to(DEV))
+        assert rel_err(xd.grad.cpu(), gx) < tol
+        assert rel_err(m.conv.weight.grad.cpu(), gw) < tol and rel_err(m.conv.bias.grad.cpu(), gb) < tol
+        # causality: output sample t must not depend on inputs after t
+        x2 = x.detach().clone()
+        x2[:, :, 60:] = 0.0
+        y2 = m(x2.to(DEV))
+        assert torch.equal(y2[:, :, :60].cpu(), m(x.detach().to(DEV))[:, :, :60].cpu())
+    for k, s in ((8, 4), (4, 2), (16, 8)):
+        m = CausalConvTranspose1d(32, 16, k, s)
+        m.precision = prec
+        x = torch.randn(2, 32, 50, requires_grad=True)
+        ref = F.conv_transpose1d(x, m.deconv.weight, m.deconv.bias, stride=s)[:, :, :-s]
+        dy = torch.randn_like(ref)
+        gx, gw, gb = torch.autograd.grad(ref, [x, m.deconv.weight, m.deconv.bias], dy)
+        m = m.to(DEV)
+        xd = x.detach().to(DEV).requires_grad_(True)
+        y = m(xd)
+        assert y.shape == ref.shape and rel_err(y.cpu(), ref) < tol
+        y.backward(dy.to(DEV))
+        assert rel_err(xd.grad.cpu(), gx) < tol
+        assert rel_err(m.deconv.weight.grad.cpu(), gw) < tol and rel_err(m.deconv.bias.grad.cpu(), gb) < tol
+
+
+def _car_model(golden, precision="fp32"):
+    from articulatory_b200 import models as M
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = M.HiFiGANGenerator(**golden["generator_params"], precision=precision)
+    G.load_state_dict(golden["gsd"])
+    return G
+
+
+def test_ar_loop_matches_reference_fixture(golden):
+    """bin/decode.py ar_loop on the CUDA generator == the reference's ar_loop output (57 frames -> 4560
+    samples, last chunk short), with and without weight norm removed."""
+    from articulatory_b200.bin.decode import ar_loop
+    a = golden["ar_loop"]
+    cfg = {"generator_params": golden["generator_params"], "batch_max_steps": a["batch_max_steps"],
+           "hop_size": a["hop_size"], "dataset_mode": "a2w"}
+    G = _car_model(golden).to(DEV).eval()
+    with torch.no_grad():
+        wav = ar_loop(G, a["art"].to(DEV), cfg)
+        assert wav.shape == a["wav"].shape
+        assert rel_err(wav.cpu(), a["wav"]) < 1e-4
+        G.remove_weight_norm()
+        assert "input_conv.weight" in G.state_dict() and "input_conv.weight_g" not in G.state_dict()
+        wav2 = ar_loop(G, a["art"].to(DEV), cfg)
+        assert rel_err(wav2.cpu(), a["wav"]) < 1e-4
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_batched_decoder_equals_per_utterance_loop(golden, use_graph):
+    from articulatory_b200.bin.decode import ar_loop
+    from articulatory_b200.decode import BatchedARDecoder
+    a = golden["ar_loop"]
+    cfg = {"generator_params": golden["generator_params"], "batch_max_steps": a["batch_max_steps"],
+           "hop_size": a["hop_size"], "dataset_mode": "a2w"}
+    G = _car_model(golden).to(DEV).eval()
+    G.remove_weight_norm()
+    g = torch.Generator().manual_seed(5)
+    feats = [a["art"], torch.randn(75, a["art"].shape[1], generator=g), torch.randn(25, a["art"].shape[1], generator=g),
+             torch.randn(3, a["art"].shape[1], generator=g), a["art"].flip(0)]
+    dec = BatchedARDecoder(G, cfg, use_graph=use_graph)
+    outs = dec.decode(feats)
+    assert rel_err(outs[0].cpu(), a["wav"]) < 1e-4                           # reference fixture
+    with torch.no_grad():
+        for f, o in zip(feats, outs):
+            want = ar_loop(G, f.to(DEV), cfg)
+            assert o.shape == want.shape == (len(f) * a["hop_size"],)
+            assert rel_err(o.cpu(), want.cpu()) < 1e-5
+    # a second call replays the captured graphs
+    outs2 = dec.decode(feats)
+    for o, o2 in zip(outs, outs2):
+        assert torch.equal(o, o2)
+
+
+def test_load_model_and_train_cli(golden, tmp_path):
+    """Checkpoint written by the train entry point loads through utils.load_model (reference key names)."""
+    from articulatory_b200.bin import train as train_cli
+    from articulatory_b200.utils import load_model
+    from tests.test_gpu_models import _train_config
+    cfg = _train_config(golden, stft=True)
+    cfg.update(generator_type="HiFiGANGenerator", discriminator_type="HiFiGANMultiScaleMultiPeriodDiscriminator",
+               generator_params=golden["generator_params"], discriminator_params=golden["discriminator_params"],
+               batch_max_steps=2000, hop_size=80, batch_size=2, sampling_rate=16000, format="npy",
+               log_interval_steps=2, save_interval_steps=1000, train_max_steps=4, dataset_mode="a2w")
+    conf = tmp_path / "conf.yaml"
+    conf.write_text(yaml.dump(cfg))
+    out = tmp_path / "exp"
+    train_cli.main(["--config", str(conf), "--outdir", str(out), "--synthetic", "6", "--precision", "fp32"])
+    ckpt = out / "checkpoint-4steps.pkl"
+    assert ckpt.exists() and (out / "config.yml").exists()
+    sd = torch.load(ckpt, map_location="cpu", weights_only=False)
+    assert sd["steps"] == 4 and set(sd["model"]["generator"].keys()) == set(golden["gsd"].keys())
+    assert set(sd["model"]["discriminator"].keys()) == set(golden["dsd"].keys())
+    model = load_model(str(ckpt))                       # config.yml discovered beside the checkpoint
+    model.remove_weight_norm()
+    y = model.eval().to(DEV)(golden["batch"]["x"].to(DEV), ar=golden["batch"]["ar"].to(DEV))
+    assert y.shape == (2, 1, 2000) and torch.isfinite(y).all()

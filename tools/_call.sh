@@ -1,5 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 > gpurun_out/r1_pytest_gpu_6.log
-timeout 300 python tools/layer_times.py --top 80 > gpurun_out/r1_layer_times_6.log 2>&1
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_6.log 2>&1
-timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r1_launches_6.csv python tools/profile_step.py > gpurun_out/r1_profile_step_6.log 2>&1
-tail -5 gpurun_out/r1_pytest_gpu_6.log; tail -3 gpurun_out/r1_bench_6.log
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r1_pytest_gpu_9.log
+timeout 300 python tools/tc_timeline.py > gpurun_out/r1_tc_timeline_9.log 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_9.log 2>&1
+tail -12 gpurun_out/r1_pytest_gpu_9.log; tail -1 gpurun_out/r1_bench_9.log | cut -c1-300
