@@ -53,6 +53,12 @@ __global__ void mean3_act_kernel(const T* __restrict__ a, const T* __restrict__ 
 }
 
 template <typename T>
+__global__ void sum3_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, T* __restrict__ out,
+                            int64_t n) {
+  GRID_STRIDE(i, n) { st_f(out + i, ld_f(a + i) + ld_f(b + i) + ld_f(c + i)); }
+}
+
+template <typename T>
 __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, T* __restrict__ dpre, int64_t n) {
   GRID_STRIDE(i, n) { st_f(dpre + i, dy[i] * (1.f - y[i] * y[i])); }
 }
@@ -254,6 +260,13 @@ extern "C" int artic_mean3_act(const void* a, const void* b, const void* c, void
   }
   DISPATCH(dtype, (mean3_act_kernel<float, bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, (const float*)c, (bf16*)out_act, n, slope)),
            (mean3_act_kernel<bf16, bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out_act, n, slope)));
+}
+
+extern "C" int artic_sum3(const void* a, const void* b, const void* c, void* out, int64_t n, int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(a && b && c && out, "null pointer");
+  if (n == 0) return ARTIC_OK;
+  DISPATCH(dtype, (sum3_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, (const float*)c, (float*)out, n)),
+           (sum3_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out, n)));
 }
 
 extern "C" int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64_t n, int32_t dtype, void* stream) {

@@ -94,6 +94,73 @@ static void launch_co1(const artic_tapconv_t& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------
+// Cig == 1 forward (first layer of every discriminator chain: raw fp32 signal -> C channels)
+// ------------------------------------------------------------------------------------
+// HBM-bound on the output write: the CTA stages its input window and the whole [taps][C] weight in
+// shared memory; Cog/8 threads produce one output row with a single 128-bit store each.
+constexpr int CI1_ROWS = 128;     // output positions per CTA
+constexpr int CI1_XS = 1280;      // staged input samples
+constexpr int CI1_WS = 4096;      // staged weights (taps * Cog)
+
+template <typename T>
+__global__ void __launch_bounds__(256) tapconv_ci1_kernel(const __grid_constant__ artic_tapconv_t p, int min_off, int span) {
+  __shared__ float xs[CI1_XS];
+  __shared__ __align__(16) float wsm[CI1_WS];
+  __shared__ __align__(16) float bsm[256];
+  const int tpr = p.Cog >> 3, rpp = 256 / tpr;
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const int n = blockIdx.y;
+  const int qa = blockIdx.x * CI1_ROWS;
+  const int qb = min(p.nq, qa + CI1_ROWS);
+  const T* __restrict__ X = reinterpret_cast<const T*>(p.X) + seq_base(p.x, n);
+  const float* __restrict__ W = reinterpret_cast<const float*>(p.W);      // [K][1][1][Cog] fp32
+  const int x0 = (p.q0 + qa) * p.si + min_off;
+  const int nx = (qb - qa - 1) * p.si + span + 1;
+  for (int i = threadIdx.x; i < nx; i += 256) {
+    const int pos = x0 + i;
+    xs[i] = (pos >= 0 && pos < p.x.len) ? ld_f(X + (int64_t)pos * p.x.s_row) : 0.f;
+  }
+  for (int i = threadIdx.x; i < p.ntaps * p.Cog; i += 256)
+    wsm[i] = __ldg(W + (int64_t)p.widx[i / p.Cog] * p.Cog + (i % p.Cog));
+  for (int i = threadIdx.x; i < p.Cog; i += 256) bsm[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+  __syncthreads();
+  __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(p.Y);
+  __nv_bfloat16* __restrict__ Y2 = reinterpret_cast<__nv_bfloat16*>(p.Y2);
+  const int64_t ybase = seq_base(p.y, n);
+  for (int q = qa + rl; q < qb; q += rpp) {
+    const int row = p.q0 + q;                       // so == 1, ro == 0
+    if (row < 0 || row >= p.y.len) continue;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int xb = (q - qa) * p.si - min_off;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const float xv = xs[xb + p.off[t]];
+      const float4 w0 = *reinterpret_cast<const float4*>(&wsm[t * p.Cog + cg * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&wsm[t * p.Cog + cg * 8 + 4]);
+      acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+      acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+      acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+      acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+    }
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = p.alpha * acc[2 * i] + bsm[cg * 8 + 2 * i], b = p.alpha * acc[2 * i + 1] + bsm[cg * 8 + 2 * i + 1];
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      o1[i] = *reinterpret_cast<uint32_t*>(&h);
+      if (p.act == ARTIC_ACT_LRELU) { a = a > 0.f ? a : p.act_slope * a; b = b > 0.f ? b : p.act_slope * b; }
+      else if (p.act == ARTIC_ACT_TANH) { a = tanhf(a); b = tanhf(b); }
+      h = __floats2bfloat162_rn(a, b);
+      o2[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    const int64_t o = ybase + (int64_t)row * p.y.s_row + cg * 8;
+    if (Y) *reinterpret_cast<uint4*>(Y + o) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    if (Y2) *reinterpret_cast<uint4*>(Y2 + o) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Cig == 1 and Cog == 1 weight gradients
 // ------------------------------------------------------------------------------------
 constexpr int C1_TAPS = 16;   // taps per pass (registers)
@@ -282,6 +349,23 @@ __global__ void __launch_bounds__(256) tapwgrad_co1_kernel(const __grid_constant
 using namespace artic;
 
 // returns 1 if taken, 0 if not eligible
+int artic_tapconv_ci1_try(const artic_tapconv_t* pp, cudaStream_t st) {
+  const artic_tapconv_t& p = *pp;
+  if (p.Cig != 1 || p.G != 1 || p.dtype != ARTIC_F32 || p.out_dtype != ARTIC_BF16) return 0;
+  if (p.so != 1 || p.ro != 0 || p.res_pre || p.mask || p.res || p.res2 || p.N > 65535) return 0;
+  const int tpr = p.Cog / 8;
+  if (p.Cog % 8 != 0 || tpr < 1 || tpr > 256 || 256 % tpr != 0 || p.ntaps * p.Cog > CI1_WS) return 0;
+  if ((p.y.s_row % 8) || (p.y.s_outer % 8) || (p.y.n_inner > 1 && (p.y.s_inner % 8))) return 0;
+  if ((p.Y && (reinterpret_cast<uintptr_t>(p.Y) & 15)) || (p.Y2 && (reinterpret_cast<uintptr_t>(p.Y2) & 15))) return 0;
+  int min_off = p.off[0], max_off = p.off[0];
+  for (int t = 1; t < p.ntaps; ++t) { min_off = min(min_off, p.off[t]); max_off = max(max_off, p.off[t]); }
+  const int span = max_off - min_off;
+  if ((CI1_ROWS - 1) * p.si + span + 1 > CI1_XS) return 0;
+  dim3 grid((unsigned)((p.nq + CI1_ROWS - 1) / CI1_ROWS), (unsigned)p.N);
+  tapconv_ci1_kernel<float><<<grid, 256, 0, st>>>(p, min_off, span);
+  return 1;
+}
+
 int artic_tapconv_co1_try(const artic_tapconv_t* pp, cudaStream_t st) {
   const artic_tapconv_t& p = *pp;
   if (p.Cog != 1 || p.G != 1 || p.Cig < 32) return 0;

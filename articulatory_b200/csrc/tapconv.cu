@@ -456,6 +456,7 @@ static int check_seq(const artic_seq_t& s) { return s.n_inner >= 1 && s.len >= 0
 int artic_tapconv_tc_try(const artic_tapconv_t* p, cudaStream_t st);
 int artic_tapwgrad_tc_try(const artic_tapwgrad_t* p, cudaStream_t st);  // tapwgrad_tc.cu, same convention
 int artic_tapconv_co1_try(const artic_tapconv_t* p, cudaStream_t st);    // smallc.cu
+int artic_tapconv_ci1_try(const artic_tapconv_t* p, cudaStream_t st);    // smallc.cu
 int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* p, cudaStream_t st);  // smallc.cu
 
 extern "C" int artic_tapconv(const artic_tapconv_t* p, void* stream) {
@@ -471,7 +472,7 @@ extern "C" int artic_tapconv(const artic_tapconv_t* p, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
   const bool ob = p->out_dtype == ARTIC_BF16;
-  if (artic_tapconv_co1_try(p, st) == 1) {
+  if (artic_tapconv_co1_try(p, st) == 1 || artic_tapconv_ci1_try(p, st) == 1) {
     ARTIC_LAUNCH_CHECK();
     return ARTIC_OK;
   }

@@ -21,9 +21,11 @@
 namespace artic {
 namespace tc {
 
-constexpr int NTHREADS = 192;
-constexpr int MAX_WS = 8;  // weight stages
-constexpr int MAX_AS = 3;  // activation stages
+constexpr int NTHREADS = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int MAX_WS = 10;  // weight stages (streaming mode)
+constexpr int MAX_AS = 8;   // activation stages
+constexpr int EPI_STAGE_BYTES = 8 * 32 * 8 * 16;   // 8 epilogue warps x [32 rows][32 channels] fp32
+constexpr int EPI_BYTES = EPI_STAGE_BYTES + 8 * 4 * 32 * 8;  // + per-warp row offsets of up to 4 sub-tiles
 
 struct Plan {
   int32_t kch;        // channels per K chunk (64 / 32 / 16)
@@ -39,6 +41,7 @@ struct Plan {
   int32_t n_mt;       // row tiles in total
   int32_t total_tiles;
   int32_t a_stage_bytes, w_stage_bytes, n_as, n_ws;
+  int32_t w_resident;   // 1: the whole weight [n_kc][ntaps][bn x kch] stays in shared memory for the CTA's lifetime
   int32_t acc_stages, tmem_cols;
   int32_t min_off;
   int32_t n_ph, panel_bytes;      // input-stride phases (= si) and bytes of one phase panel
@@ -79,7 +82,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
                   const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_AS], a_empty[MAX_AS], w_full[MAX_WS], w_empty[MAX_WS];
-  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], w_res_full;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,22 +90,32 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem0;
   const uint32_t w_base = smem0 + (uint32_t)pl.n_as * pl.a_stage_bytes;
+  const uint32_t epi_base = w_base + (uint32_t)(pl.w_resident ? pl.n_kc * p.ntaps : pl.n_ws) * pl.w_stage_bytes;   // 4 x 8 KB transpose stages + row offsets
 
   if (threadIdx.x == 0) dbg_mark(pl.dbg, 1);
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&map_x);
-    prefetch_tmap(&map_w);
-    for (int i = 0; i < pl.n_as; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < pl.n_ws; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // Setup rendezvous on named barrier 1: the producer warp initialises the mbarriers, ARRIVES and goes
+  // straight to its first TMA loads; the other warps (TMEM allocation in warp 1) SYNC on it.
+  uint32_t tmem_base = 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&map_x);
+      prefetch_tmap(&map_w);
+      for (int i = 0; i < pl.n_as; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+      for (int i = 0; i < pl.n_ws; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
+      mbar_init(&w_res_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("bar.arrive 1, %0;" ::"r"(NTHREADS) : "memory");
+  } else {
+    if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)pl.tmem_cols);
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"r"(NTHREADS) : "memory");
+    tc_fence_after();
+    tmem_base = tmem_base_s;
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)pl.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  if (threadIdx.x == 0) dbg_mark(pl.dbg, 2);
+  if (threadIdx.x == 32) dbg_mark(pl.dbg, 2);
 
   const int ntaps = p.ntaps;
   const int acc_cols = pl.mt * pl.bn;
@@ -112,6 +125,14 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
     if (lane == 0) {
       PipeState as(pl.n_as), ws(pl.n_ws);
       const uint32_t w_bytes = (uint32_t)pl.bn * pl.row_bytes;
+      if (pl.w_resident) {
+        // small layers (n_nt == 1, G == 1): every tile uses the same weights; load them once
+        mbar_expect_tx(&w_res_full, (uint32_t)(pl.n_kc * ntaps) * w_bytes);
+        for (int kc = 0; kc < pl.n_kc; ++kc)
+          for (int t = 0; t < ntaps; ++t)
+            tma_load_2d(w_base + (uint32_t)(kc * ntaps + t) * pl.w_stage_bytes, &map_w, &w_res_full, kc * pl.kch,
+                        p.widx[t] * p.Cog);
+      }
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         const int nt = tile % pl.n_nt;
         const int r = tile / pl.n_nt;
@@ -120,7 +141,6 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
         for (int kc = 0; kc < pl.n_kc; ++kc) {
           const int c0 = g * p.Cig + kc * pl.kch;
           mbar_wait(&a_empty[as.stage], as.phase ^ 1);
-          dbg_mark(pl.dbg, 10);
           const uint32_t a_dst = a_base + (uint32_t)as.stage * pl.a_stage_bytes;
           if (!pl.packed) {
             const int n = mtile / pl.tiles_per_seq;
@@ -144,9 +164,9 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
             }
           }
           as.next();
+          if (pl.w_resident) continue;
           for (int t = 0; t < ntaps; ++t) {
             mbar_wait(&w_empty[ws.stage], ws.phase ^ 1);
-            dbg_mark(pl.dbg, 11);
             mbar_expect_tx(&w_full[ws.stage], w_bytes);
             tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes, &map_w, &w_full[ws.stage], kc * pl.kch,
                         (p.widx[t] * p.G + g) * p.Cog + nt * pl.bn);
@@ -170,6 +190,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
       const uint32_t m_step16 = (128u * (uint32_t)pl.row_bytes) >> 4;
       const int ksteps = pl.kch / 16;
       const int mt = pl.mt;
+      if (pl.w_resident) mbar_wait(&w_res_full, 0);
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[acc.stage], acc.phase ^ 1);
         tc_fence_after();
@@ -180,10 +201,11 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
           dbg_mark(pl.dbg, 20);
           const uint32_t a16 = desc_lo | (((a_base + (uint32_t)as.stage * pl.a_stage_bytes) >> 4) & 0x3fffu);
           for (int t = 0; t < ntaps; ++t) {
-            mbar_wait(&w_full[ws.stage], ws.phase);
-            dbg_mark(pl.dbg, 21);
+            const uint32_t w_slot = pl.w_resident ? (uint32_t)(kc * ntaps + t) : (uint32_t)ws.stage;
+            if (!pl.w_resident) mbar_wait(&w_full[ws.stage], ws.phase);
+            if (kc == 0 && t == 0) dbg_mark(pl.dbg, 21);
             tc_fence_after();
-            const uint32_t b16 = desc_lo | (((w_base + (uint32_t)ws.stage * pl.w_stage_bytes) >> 4) & 0x3fffu);
+            const uint32_t b16 = desc_lo | (((w_base + w_slot * pl.w_stage_bytes) >> 4) & 0x3fffu);
             uint32_t at16 = a16 + (uint32_t)pl.a_off16[t];
             uint32_t dcol = d_base;
             for (int m = 0; m < mt; ++m) {
@@ -208,8 +230,10 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
               at16 += m_step16;
               dcol += (uint32_t)pl.bn;
             }
-            umma_commit(&w_empty[ws.stage]);
-            ws.next();
+            if (!pl.w_resident) {
+              umma_commit(&w_empty[ws.stage]);
+              ws.next();
+            }
           }
           umma_commit(&a_empty[as.stage]);
           as.next();
@@ -221,7 +245,17 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
     }
   } else {
     // =============================== epilogue ===================================
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    // TMEM hands every lane one accumulator ROW; stored as is, a warp-wide 16-byte access would touch
+    // 32 different cache lines (measured: ~12k cycles per 128x128 tile).  Each warp therefore
+    // transposes [32 rows][32 channels] chunks through a private XOR-swizzled shared-memory stage
+    // and runs the fused epilogue with lanes along the CHANNELS (4 lanes x 8 channels per row, 8
+    // rows per instruction: full 64-byte row segments).  Eight warps work on a tile: two per TMEM
+    // lane quarter, on alternating channel chunks.  Everything that does not depend on the
+    // accumulator — output row offsets, the bias, the residual / mask operands of the chunk — is
+    // fetched BEFORE the accumulator is waited for / read, so its latency is paid once per chunk.
+    const int ew = warp & 3;            // TMEM lane quarter this warp may access
+    const int ewarp = warp - 2;         // 0..7
+    const int eh = ewarp >> 2;          // channel-chunk parity
     PipeState acc(pl.acc_stages);
     using TO = __nv_bfloat16;
     const TO* __restrict__ res_pre = reinterpret_cast<const TO*>(p.res_pre);
@@ -230,16 +264,17 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
     const TO* __restrict__ res2 = reinterpret_cast<const TO*>(p.res2);
     TO* __restrict__ Y = reinterpret_cast<TO*>(p.Y);
     TO* __restrict__ Y2 = reinterpret_cast<TO*>(p.Y2);
+    uint8_t* epi = smem_raw + (epi_base - smem_u32(smem_raw));
+    float4* stage = reinterpret_cast<float4*>(epi) + ewarp * (32 * 8);                        // [32 rows][8 units]
+    long long* rowoff = reinterpret_cast<long long*>(epi + EPI_STAGE_BYTES) + ewarp * (4 * 32);   // [sub-tile][32 rows]
+    const int g8 = lane & 3, rsub = lane >> 2;
     for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
       const int nt = tile % pl.n_nt;
       const int r = tile / pl.n_nt;
       const int mtile = r % pl.n_mt;
       const int g = r / pl.n_mt;
-      mbar_wait(&acc_full[acc.stage], acc.phase);
-      if (threadIdx.x == 64) dbg_mark(pl.dbg, 30);
-      tc_fence_after();
       const int cbase = g * p.Cog + nt * pl.bn;
-      for (int m = 0; m < pl.mt; ++m) {
+      for (int m = 0; m < pl.mt; ++m) {   // output offset of this lane's row in every sub-tile (-1: not stored)
         const int mrow = m * 128 + ew * 32 + lane;
         int n, q;
         bool valid;
@@ -253,59 +288,101 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
           n = mtile * pl.seg_per_tile + j;
           valid = j < pl.seg_per_tile && q < p.nq && n < p.N;
         }
-        int64_t o = 0;
+        long long o = -1;
         if (valid) {
           const int row = (p.q0 + q) * p.so + p.ro;
-          valid = row >= 0 && row < p.y.len;
-          o = seq_base(p.y, n) + (int64_t)row * p.y.s_row + cbase;
+          if (row >= 0 && row < p.y.len) o = seq_base(p.y, n) + (int64_t)row * p.y.s_row + cbase;
         }
+        rowoff[m * 32 + lane] = o;
+      }
+      __syncwarp();
+      bool waited = false;
+      for (int m = 0; m < pl.mt; ++m) {
         const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc.stage * acc_cols + (uint32_t)m * pl.bn;
-        for (int c0 = 0; c0 < pl.bn; c0 += 32) {
-          uint32_t acc_r[32];
-          tmem_ld32(t_row + c0, acc_r);
-          tmem_ld_wait();
-          if (valid) {
+        for (int c0 = eh * 32; c0 < pl.bn; c0 += 64) {
+          // ---- (1) everything independent of the accumulator
+          long long oo[4];
+          uint4 q_rp[4], q_mk[4], q_rs[4], q_r2[4];
+          float bv[8];
 #pragma unroll
-            for (int v8 = 0; v8 < 4; ++v8) {
-              float v[8], tmp[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                v[i] = p.alpha * __uint_as_float(acc_r[v8 * 8 + i]);
-                if (p.bias != nullptr) v[i] += __ldg(p.bias + cbase + c0 + v8 * 8 + i);
-              }
-              const int64_t oo = o + c0 + v8 * 8;
-              if (res_pre) {
-                unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(res_pre + oo)), tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += tmp[i];
-              }
-              if (mask) {
-                unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(mask + oo)), tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= (tmp[i] > 0.f ? 1.f : p.mask_slope);
-              }
-              if (res) {
-                unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(res + oo)), tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += tmp[i];
-              }
-              if (res2) {
-                unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(res2 + oo)), tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += tmp[i];
-              }
-              if (Y) *reinterpret_cast<uint4*>(Y + oo) = pack8(v);
-              if (Y2) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  if (p.act == ARTIC_ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : p.act_slope * v[i];
-                  else if (p.act == ARTIC_ACT_TANH) v[i] = tanhf(v[i]);
-                }
-                *reinterpret_cast<uint4*>(Y2 + oo) = pack8(v);
-              }
+          for (int it = 0; it < 4; ++it) {
+            const long long o = rowoff[m * 32 + it * 8 + rsub];
+            oo[it] = o < 0 ? -1 : o + c0 + g8 * 8;
+            q_rp[it] = q_mk[it] = q_rs[it] = q_r2[it] = make_uint4(0, 0, 0, 0);
+            if (oo[it] >= 0) {
+              if (res_pre) q_rp[it] = __ldg(reinterpret_cast<const uint4*>(res_pre + oo[it]));
+              if (mask) q_mk[it] = __ldg(reinterpret_cast<const uint4*>(mask + oo[it]));
+              if (res) q_rs[it] = __ldg(reinterpret_cast<const uint4*>(res + oo[it]));
+              if (res2) q_r2[it] = __ldg(reinterpret_cast<const uint4*>(res2 + oo[it]));
             }
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = p.bias != nullptr ? __ldg(p.bias + cbase + c0 + g8 * 8 + i) : 0.f;
+          if (!waited) {
+            mbar_wait(&acc_full[acc.stage], acc.phase);
+            if (threadIdx.x == 64) dbg_mark(pl.dbg, 30);
+            tc_fence_after();
+            waited = true;
+          }
+          // ---- (2) TMEM -> registers -> swizzled smem (lane = row)
+          {
+            uint32_t acc_r[32];
+            tmem_ld32(t_row + c0, acc_r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              stage[lane * 8 + (u ^ (lane & 7))] =
+                  make_float4(__uint_as_float(acc_r[4 * u]), __uint_as_float(acc_r[4 * u + 1]),
+                              __uint_as_float(acc_r[4 * u + 2]), __uint_as_float(acc_r[4 * u + 3]));
+          }
+          __syncwarp();
+          // ---- (3) transposed pass (lanes along channels)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + rsub;
+            const float4 f0 = stage[rr * 8 + ((2 * g8) ^ (rr & 7))];
+            const float4 f1 = stage[rr * 8 + ((2 * g8 + 1) ^ (rr & 7))];
+            if (oo[it] < 0) continue;
+            float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            float tmp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(p.alpha, v[i], bv[i]);
+            if (res_pre) {
+              unpack8<TO>(q_rp[it], tmp);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+            }
+            if (mask) {
+              unpack8<TO>(q_mk[it], tmp);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= (tmp[i] > 0.f ? 1.f : p.mask_slope);
+            }
+            if (res) {
+              unpack8<TO>(q_rs[it], tmp);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+            }
+            if (res2) {
+              unpack8<TO>(q_r2[it], tmp);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+            }
+            if (Y) *reinterpret_cast<uint4*>(Y + oo[it]) = pack8(v);
+            if (Y2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (p.act == ARTIC_ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : p.act_slope * v[i];
+                else if (p.act == ARTIC_ACT_TANH) v[i] = tanhf(v[i]);
+              }
+              *reinterpret_cast<uint4*>(Y2 + oo[it]) = pack8(v);
+            }
+          }
+          __syncwarp();
         }
+      }
+      if (!waited) {   // bn == 32: the odd-chunk warps have no channels, but still own a share of the barrier
+        mbar_wait(&acc_full[acc.stage], acc.phase);
+        tc_fence_after();
       }
       tc_fence_before();
       if (threadIdx.x == 64) dbg_mark(pl.dbg, 31);
@@ -395,7 +472,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   tc::EncodeTiledFn enc = tc::encode_fn();
   if (enc == nullptr) return 0;
 
-  const int budget = tc::max_smem() - 1024 /*alignment slack*/;
+  const int budget = tc::max_smem() - 1024 /*alignment slack*/ - tc::EPI_BYTES;
   auto make_plan = [&](tc::Plan& pl, int bn_req, int mt_req) -> bool {
     memset(&pl, 0, sizeof(pl));
   int min_off = p.off[0], max_off = p.off[0];
@@ -454,23 +531,44 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   if (cols > 512) return false;
   pl.panel_bytes = ((a_rows * pl.row_bytes + 1023) / 1024) * 1024;
   pl.a_stage_bytes = pl.n_ph * pl.panel_bytes;
-  pl.n_as = 2;
-  int rem = budget - pl.n_as * pl.a_stage_bytes;
-  if (rem < 2 * pl.w_stage_bytes) {
-    pl.n_as = 1;
-    rem = budget - pl.a_stage_bytes;
-    if (rem < 2 * pl.w_stage_bytes) return false;
+  // Shared memory: weights either RESIDENT (single channel tile, single group, <= 96 KB: the C = 32 / 64
+  // generator stages — their per-tile weight traffic would otherwise serialise the producer) or
+  // streamed through up to MAX_WS stages; the rest goes to activation stages, because the bytes in
+  // flight per SM (x ~2 us TMA latency) are what bounds the operand bandwidth.
+  const int w_all = pl.n_kc * p.ntaps * pl.w_stage_bytes;
+  pl.w_resident = (pl.n_nt == 1 && p.G == 1 && w_all <= 96 * 1024 && budget - w_all >= 2 * pl.a_stage_bytes &&
+                   tc::g_debug[7] != 1) ? 1 : 0;
+  if (pl.w_resident) {
+    pl.n_ws = 1;   // unused
+    pl.n_as = (budget - w_all) / pl.a_stage_bytes;
+    if (pl.n_as > tc::MAX_AS) pl.n_as = tc::MAX_AS;
+  } else {
+    const int steps = pl.n_kc * p.ntaps;
+    int want_ws = steps < tc::MAX_WS ? steps : tc::MAX_WS;
+    if (want_ws < 2) want_ws = 2;
+    pl.n_as = 2;
+    if (budget - pl.n_as * pl.a_stage_bytes < 2 * pl.w_stage_bytes) {
+      pl.n_as = 1;
+      if (budget - pl.a_stage_bytes < 2 * pl.w_stage_bytes) return false;
+    }
+    int rem = budget - pl.n_as * pl.a_stage_bytes;
+    pl.n_ws = rem / pl.w_stage_bytes;
+    if (pl.n_ws > want_ws) pl.n_ws = want_ws;
+    rem -= pl.n_ws * pl.w_stage_bytes;
+    while (pl.n_as < tc::MAX_AS && pl.n_as < 2 * pl.n_kc + 1 && rem >= pl.a_stage_bytes) { ++pl.n_as; rem -= pl.a_stage_bytes; }
+    int more = rem / pl.w_stage_bytes;     // leftover: deepen the weight pipeline
+    while (more-- > 0 && pl.n_ws < tc::MAX_WS) ++pl.n_ws;
   }
-  pl.n_ws = rem / pl.w_stage_bytes;
-  if (pl.n_ws > tc::MAX_WS) pl.n_ws = tc::MAX_WS;
-  if (pl.n_ws > 2 && pl.n_as < tc::MAX_AS && pl.n_kc > 2 && rem - pl.n_ws * pl.w_stage_bytes >= pl.a_stage_bytes) pl.n_as += 1;
   const int64_t total = (int64_t)pl.n_mt * pl.n_nt * p.G;
   if (total > (1 << 30)) return false;
   pl.total_tiles = (int)total;
     return true;
   };
-  // Tile shape: minimise (waves over the SMs) x (MMA work per tile), lightly penalising narrow
-  // channel tiles (they re-stage the activation tile more often).
+  // Tile shape: a small clock model per candidate (bn, mt), fitted to tools/tc_sweep.py on B200:
+  //   per MMA (M=128, K=16): max(tensor time bn/2, operand smem reads 32 + bn/4) clocks;
+  //   epilogue ~700 clocks per [128 x 64] chunk pair, overlapped with the next main loop when the
+  //   accumulator is double-buffered; every tile pays a ~600-clock hand-over bubble;
+  //   all CTAs together cannot pull operands from L2 faster than ~2500 B/clk.
   tc::Plan pl, cand;
   double best = -1.0;
   const int bns[4] = {256, 128, 64, 32};
@@ -483,7 +581,21 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
       if (!make_plan(cand, bn, mt_req)) continue;
       if (cand.mt != mt_req && mt_req != 4) continue;   // already evaluated at a larger request
       const double waves = (double)((cand.total_tiles + num_sms() - 1) / num_sms());
-      const double cost = waves * cand.mt * bn * (1.0 + 24.0 / bn) * (cand.acc_stages == 2 ? 1.0 : 1.15);
+      const double per_mma = bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0;
+      const double main_clk = (double)cand.n_kc * p.ntaps * (cand.kch / 16) * cand.mt * per_mma;
+      const double epi_clk = cand.mt * ((bn + 63) / 64) * 700.0;
+      // operand streaming: bytes per tile over min(bytes in flight / ~3000-clock TMA latency, fair share of L2)
+      const double w_tile = cand.w_resident ? 0.0 : (double)cand.n_kc * p.ntaps * bn * cand.row_bytes;
+      const double tile_bytes = (double)cand.n_kc * cand.a_stage_bytes + w_tile;
+      const double inflight = (double)cand.n_as * cand.a_stage_bytes + (cand.w_resident ? 0.0 : (double)cand.n_ws * cand.w_stage_bytes);
+      const double active = cand.total_tiles < num_sms() ? cand.total_tiles : num_sms();
+      double bw = inflight / 3000.0;
+      if (bw > 6000.0 / active) bw = 6000.0 / active;
+      const double mem_clk = tile_bytes / bw;
+      double tile_clk = main_clk > mem_clk ? main_clk : mem_clk;
+      if (cand.acc_stages == 2) tile_clk = tile_clk > epi_clk ? tile_clk : epi_clk;
+      else tile_clk += epi_clk;
+      const double cost = waves * (tile_clk + 600.0) + (cand.acc_stages == 2 ? epi_clk : 0.0);
       if (best < 0 || cost < best) { best = cost; pl = cand; }
     }
   }
@@ -520,7 +632,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("artic_tapconv: cuTensorMapEncodeTiled(W) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   }
-  const int smem_bytes = pl.n_as * pl.a_stage_bytes + pl.n_ws * pl.w_stage_bytes + 1024;
+  const int smem_bytes = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? pl.n_kc * p.ntaps : pl.n_ws) * pl.w_stage_bytes + 1024 + tc::EPI_BYTES;
   int grid = num_sms();
   if (grid > pl.total_tiles) grid = pl.total_tiles;
   tc::tapconv_tc_kernel<<<grid, tc::NTHREADS, smem_bytes, st>>>(p, pl, map_x, map_w);

@@ -36,24 +36,32 @@ __global__ void __launch_bounds__(256) wn_scale_kernel(const artic_wdesc_t* __re
 //                        MODE 2: fp32 dWp ('fwd' layout) -> dv (torch layout), overwriting
 constexpr int PT = 32;   // tile edge
 constexpr int PK = 8;    // taps per tile
+// Tiles of ALL layers form one flat index space (descs[i].tile_begin = exclusive prefix of the per-layer
+// tile counts, computed by the host with wperm_tiles()), so the grid is balanced over the big layers.
 template <int MODE>
-__global__ void __launch_bounds__(256) wperm_kernel(const artic_wdesc_t* __restrict__ descs) {
+__global__ void __launch_bounds__(256) wperm_kernel(const artic_wdesc_t* __restrict__ descs, int n_layers,
+                                                    long long total_tiles) {
   __shared__ float tile[PK][PT][PT + 1];
-  const artic_wdesc_t& d = descs[blockIdx.y];
+  for (long long gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+  int lo = 0, hi = n_layers - 1;                       // last layer with tile_begin <= gt
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].tile_begin <= gt) lo = mid; else hi = mid - 1;
+  }
+  const artic_wdesc_t& d = descs[lo];
   void* outp = MODE == 0 ? d.out_f : MODE == 1 ? d.out_b : (void*)d.dv;
-  if (outp == nullptr || (MODE == 2 && d.dWp == nullptr)) return;
-  const bool swap = MODE == 1;
+  if (outp == nullptr || (MODE == 2 && d.dWp == nullptr)) continue;
+  const bool swap = MODE == 1 || (MODE == 2 && d.dw_swapped != 0);
   const int Rn = swap ? d.B : d.A, Cn = swap ? d.A : d.B;          // rows / cols of the prepared matrix
   const int64_t sr = swap ? d.sb : d.sa, sc = swap ? d.sa : d.sb;  // their strides in the torch weight
   const int r_pad = swap ? d.b_pad : d.a_pad, c_pad = swap ? d.a_pad : d.b_pad;
   const int m = d.merge, Gs = d.G / m;
   const int kc = d.K < PK ? d.K : PK;
   const int n_rt = (Rn + PT - 1) / PT, n_ct = (Cn + PT - 1) / PT, n_kt = (d.K + kc - 1) / kc;
-  const int64_t n_tiles = (int64_t)n_rt * n_ct * n_kt * d.G;
   const bool r_inner = sr < sc;                                      // which matrix dim is contiguous-ish in torch
   const int dtype = MODE == 0 ? d.dtype_f : d.dtype_b;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    int64_t w = t;
+  {
+    int64_t w = gt - d.tile_begin;
     const int ct = (int)(w % n_ct); w /= n_ct;
     const int rt = (int)(w % n_rt); w /= n_rt;
     const int kt = (int)(w % n_kt);
@@ -104,6 +112,7 @@ __global__ void __launch_bounds__(256) wperm_kernel(const artic_wdesc_t* __restr
       }
     }
     __syncthreads();
+  }
   }
 }
 
@@ -158,22 +167,34 @@ __global__ void adam_tick_kernel(artic_adam_hyper_t* hyper) { hyper->step += 1; 
 
 using namespace artic;
 
-extern "C" int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, void* stream) {
-  ARTIC_CHECK_ARG(descs != nullptr && n >= 0, "bad descriptor table");
+static unsigned wperm_grid(int64_t total_tiles) {
+  const int64_t cap = 8LL * num_sms();
+  return (unsigned)(total_tiles < cap ? (total_tiles > 0 ? total_tiles : 1) : cap);
+}
+
+extern "C" int64_t artic_wperm_tiles(int32_t K, int32_t G, int32_t A, int32_t B) {
+  const int kc = K < PK ? K : PK;
+  return (int64_t)((A + PT - 1) / PT) * ((B + PT - 1) / PT) * ((K + kc - 1) / kc) * G;
+}
+
+extern "C" int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles,
+                                  void* stream) {
+  ARTIC_CHECK_ARG(descs != nullptr && n >= 0 && total_tiles >= 0, "bad descriptor table");
   if (n == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (any_norm) wn_scale_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
-  wperm_kernel<0><<<dim3(64, (unsigned)n), 256, 0, st>>>(descs);
-  wperm_kernel<1><<<dim3(64, (unsigned)n), 256, 0, st>>>(descs);
+  wperm_kernel<0><<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
+  wperm_kernel<1><<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
 }
 
-extern "C" int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, void* stream) {
-  ARTIC_CHECK_ARG(descs != nullptr && n >= 0, "bad descriptor table");
+extern "C" int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles,
+                                    void* stream) {
+  ARTIC_CHECK_ARG(descs != nullptr && n >= 0 && total_tiles >= 0, "bad descriptor table");
   if (n == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  wperm_kernel<2><<<dim3(64, (unsigned)n), 256, 0, st>>>(descs);
+  wperm_kernel<2><<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
   if (any_norm) wn_bwd_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;

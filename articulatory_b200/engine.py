@@ -105,6 +105,37 @@ def tapconv(launches, X: SeqT, W, G, Cig, Cog, Y: Optional[SeqT] = None, Y2: Opt
 # --------------------------------------------------------------------------- #
 # one conv-like layer                                                         #
 # --------------------------------------------------------------------------- #
+_SIDE_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
+
+
+def fork_join(branches, device=None):
+    """Run independent branches concurrently: branch 0 on the current stream, the others on side
+    streams forked from it, all joined back before returning (capturable in a CUDA graph: the
+    fork / join become graph edges).  The layers of this network are small enough that a single
+    kernel leaves SMs idle and pays its launch / pipeline-fill latency serially; the three MRF
+    blocks of a generator stage and the eight sub-discriminators are independent, so their kernels
+    overlap.  ARTIC_STREAMS=0 runs the branches one after the other."""
+    import os
+    if len(branches) == 1 or os.environ.get("ARTIC_STREAMS", "1") == "0":
+        return [b() for b in branches]
+    main = torch.cuda.current_stream()
+    dev = main.device_index
+    pool = _SIDE_STREAMS.setdefault(dev, [])
+    while len(pool) < len(branches) - 1:
+        pool.append(torch.cuda.Stream(device=dev))
+    side = pool[:len(branches) - 1]
+    for st in side:
+        st.wait_stream(main)
+    out = [None] * len(branches)
+    for i in range(1, len(branches)):
+        with torch.cuda.stream(side[i - 1]):
+            out[i] = branches[i]()
+    out[0] = branches[0]()
+    for st in side:
+        main.wait_stream(st)
+    return out
+
+
 def slice_seq(s: SeqT, lo: int, hi: int) -> SeqT:
     """View of batch items [lo, hi) (the batch is the leading tensor dim in every layout)."""
     return SeqT(s.t[lo:hi], (hi - lo) * s.n_inner, s.L, s.C, s.n_inner, s.s_outer, s.s_inner, s.s_row)
@@ -132,6 +163,10 @@ class ConvLayer:
         # multiple of 32 channels so that the layer runs on the tensor-core kernel.
         if pad_in and in_code == BF16 and out_code == BF16 and spec.groups == 1 and spec.cin >= 32 and spec.cin % 16:
             self.kcig = (spec.cin + 31) // 32 * 32
+        # Transposed convs get their weight gradient as the weight gradient of the equivalent strided conv
+        # with X and dY exchanged (dW^T, i.e. the 'bwd' layout): that contraction has unit output stride,
+        # which the tcgen05 wgrad kernel requires.
+        self.dw_swapped = spec.kind == "convT" and in_code == BF16 and out_code == BF16
         self.v = self.g = self.b = None          # torch parameters (fp32, device)
         self.Wf = self.Wb = self.scale = None    # prepared weights
         self.dWf = None                          # fp32 wgrad accumulator, 'fwd' layout
@@ -191,16 +226,27 @@ class ConvLayer:
     def wgrad(self, X: SeqT, dY: SeqT, grads: Dict[str, torch.Tensor]):
         """Accumulate dW (prepared layout) and the bias gradient (into grads[name.bias])."""
         s = self.spec
-        L = s.wgrad_launch(X.L)
         p = _lib.TapWgrad()
-        p.X, p.dY, p.dW = ptr(X.t), ptr(dY.t), ptr(self.dWf)
-        p.x, p.y = X.seq(), dY.seq()
-        p.N, p.G, p.Cig, p.Cog = X.N, self.kG, self.kcig, self.kcog
-        p.q0, p.nq, p.si, p.so = L.q0, L.nq, L.si, L.so
-        p.ntaps = len(L.off)
-        for i in range(p.ntaps):
-            p.off[i], p.yoff[i], p.widx[i] = L.off[i], L.yoff[i], L.widx[i]
-        p.dtype, p.y_dtype = X.code, dY.code
+        if self.dw_swapped:
+            # dW^T[j][co][ci] = sum_q dY[q*s + j - pad][co] * X[q][ci]
+            p.X, p.dY, p.dW = ptr(dY.t), ptr(X.t), ptr(self.dWf)
+            p.x, p.y = dY.seq(), X.seq()
+            p.N, p.G, p.Cig, p.Cog = X.N, self.kG, self.kcog, self.kcig
+            p.q0, p.nq, p.si, p.so = 0, X.L, s.stride, 1
+            p.ntaps = s.k
+            for j in range(s.k):
+                p.off[j], p.yoff[j], p.widx[j] = j - s.padding, 0, j
+            p.dtype, p.y_dtype = dY.code, X.code
+        else:
+            L = s.wgrad_launch(X.L)
+            p.X, p.dY, p.dW = ptr(X.t), ptr(dY.t), ptr(self.dWf)
+            p.x, p.y = X.seq(), dY.seq()
+            p.N, p.G, p.Cig, p.Cog = X.N, self.kG, self.kcig, self.kcog
+            p.q0, p.nq, p.si, p.so = L.q0, L.nq, L.si, L.so
+            p.ntaps = len(L.off)
+            for i in range(p.ntaps):
+                p.off[i], p.yoff[i], p.widx[i] = L.off[i], L.yoff[i], L.widx[i]
+            p.dtype, p.y_dtype = X.code, dY.code
         call("artic_tapconv_wgrad", p)
         if self.b is not None:
             call("artic_colsum", ptr(dY.t), dY.seq(), dY.N, dY.C, dY.code, ptr(grads[self.name + ".bias"]))
@@ -228,7 +274,7 @@ class WeightSet:
         o = 0
         for l, n in zip(self.layers, sizes):
             s = l.spec
-            l.dWf = self.dW[o:o + n].view(s.k, l.kG, l.kcig, l.kcog)
+            l.dWf = self.dW[o:o + n].view(*((s.k, l.kG, l.kcog, l.kcig) if l.dw_swapped else (s.k, l.kG, l.kcig, l.kcog)))
             o += n
         self._bufs = [(l.Wf, l.Wb, l.scale, l.dWf) for l in self.layers]
         self._tables = {}
@@ -238,6 +284,8 @@ class WeightSet:
         tab = self._tables.get(key)
         if tab is None:
             descs = []
+            tiles = 0
+            lib = _lib.load()
             for l in self.layers:
                 s = l.spec
                 rows, row_len = s.wn_rows()
@@ -255,7 +303,11 @@ class WeightSet:
                 d.rows, d.K, d.G, d.A, d.B = rows, s.k, s.groups, A, B
                 d.merge, d.a_pad, d.b_pad = l.mg, l.kcig, l.kcog
                 d.dtype_f, d.dtype_b = l.in_code, l.out_code
+                d.dw_swapped = int(l.dw_swapped)
+                d.tile_begin = tiles
+                tiles += lib.artic_wperm_tiles(s.k, s.groups, A, B)
                 descs.append(d)
+            self.total_tiles = tiles
             tab = _lib.upload_structs(descs, self.dev)
             if len(self._tables) > 4:       # the autograd path hands in fresh grads every backward
                 self._tables = {k: v for k, v in self._tables.items() if k is None}
@@ -268,7 +320,8 @@ class WeightSet:
             l.Wf, l.Wb, l.scale, l.dWf = wf, wb, sc, dw
 
     def prep(self):
-        call("artic_weights_prep", ptr(self._table(None)), len(self.layers), self.any_norm)
+        tab = self._table(None)
+        call("artic_weights_prep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
 
     def zero(self):
         self.dW.zero_()
@@ -276,7 +329,8 @@ class WeightSet:
     def unprep(self, grads: Dict[str, torch.Tensor]):
         """dW (prepared layout) -> dv / dg of the torch parameters (OVERWRITES those entries of
         ``grads``; bias gradients were accumulated by ConvLayer.wgrad)."""
-        call("artic_weights_unprep", ptr(self._table(grads)), len(self.layers), self.any_norm)
+        tab = self._table(grads)
+        call("artic_weights_unprep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
 
 
 def _zero_grads_like(layers: List[ConvLayer]) -> Dict[str, torch.Tensor]:
@@ -403,8 +457,8 @@ class GeneratorEngine:
             au = u.like()
             up.forward(a, Y=u, Y2=au, act=ACT_LRELU, act_slope=slope)
             st = {"a_in": a, "a_u": au, "blocks": []}
-            outs = []
-            for j in range(self.n_blocks):
+
+            def block_fwd(j, i=i, u=u, au=au):
                 b = i * self.n_blocks + j
                 x, ax = u, au
                 pairs = []
@@ -417,8 +471,11 @@ class GeneratorEngine:
                     L[f"blocks.{b}.convs2.{di}.1"].forward(at, Y=xn, Y2=axn, res=x, act=ACT_LRELU, act_slope=slope)
                     pairs.append((ax, at))
                     x, ax = xn, axn
-                outs.append(x)
-                st["blocks"].append(pairs)
+                return x, pairs
+
+            res_j = fork_join([lambda j=j: block_fwd(j) for j in range(self.n_blocks)])
+            outs = [r[0] for r in res_j]
+            st["blocks"] = [r[1] for r in res_j]
             last = i == n_stage - 1
             # LeakyReLU before the output conv uses torch's default slope 0.01 (hifigan.py:150)
             st["slope_out"] = 0.01 if last else slope
@@ -463,8 +520,8 @@ class GeneratorEngine:
         oc.dgrad(dpre, dX=g, mask=a_c, mask_slope=stages[-1]["slope_out"], alpha=1.0 / self.n_blocks)
         for i in range(len(stages) - 1, -1, -1):
             st = stages[i]
-            du = None
-            for j in range(self.n_blocks):
+
+            def block_bwd(j, i=i, st=st, g=g):
                 b = i * self.n_blocks + j
                 gx = g
                 pairs = st["blocks"][j]
@@ -475,14 +532,14 @@ class GeneratorEngine:
                     dt = at.like()
                     c2.dgrad(gx, dX=dt, mask=at, mask_slope=slope)
                     c1.wgrad(ax, dt, grads)
-                    if di > 0:
-                        gn = ax.like()
-                        c1.dgrad(dt, dX=gn, mask=ax, mask_slope=slope, res=gx)
-                    else:  # block input: accumulate over the three blocks into du
-                        gn = ax.like() if du is None else du
-                        c1.dgrad(dt, dX=gn, mask=ax, mask_slope=slope, res=gx, res2=du)
-                        du = gn
+                    gn = ax.like()
+                    c1.dgrad(dt, dX=gn, mask=ax, mask_slope=slope, res=gx)
                     gx = gn
+                return gx        # gradient wrt the block input (pre-activation u)
+
+            dus = fork_join([lambda j=j: block_bwd(j) for j in range(self.n_blocks)])
+            du = dus[0].like()
+            call("artic_sum3", ptr(dus[0].t), ptr(dus[1].t), ptr(dus[2].t), ptr(du.t), du.numel(), code)
             up = L[f"upsamples.{i}.1"]
             a_in = st["a_in"]
             up.wgrad(a_in, du, grads)
@@ -642,21 +699,30 @@ class DiscriminatorEngine:
             nxt = take(into["sigs"][s]) if into is not None else SeqT.empty(B, lo_, 1, F32, dev)
             call("artic_avgpool1d", ptr(sigs[-1].t), ptr(nxt.t), B, lp, lo_, k, st, pd, F32)
             sigs.append(nxt)
-        for ci, ch in enumerate(self.chains):
+        xps = {}
+        for ci, ch in enumerate(self.chains):          # reflect-padded period inputs (hifigan.py:413-416)
+            if ch.kind != "period":
+                continue
+            p = ch.period
+            Tp = T if T % p == 0 else T + (p - T % p)
+            if Tp != T:
+                xp = into["xp"][ci][lo:lo + B] if into is not None else torch.empty((B, Tp), dtype=torch.float32, device=dev)
+                call("artic_reflect_pad_right", ptr(x2d), ptr(xp), B, T, Tp, F32)
+            else:
+                xp = x2d
+            xps[ci] = xp
+        tape["xp"] = xps
+
+        def chain_fwd(ci):
+            ch = self.chains[ci]
             if ch.kind == "scale":
                 h = sigs[ch.scale_index]
                 slope = self.slope_s
             else:
                 p = ch.period
-                Tp = T if T % p == 0 else T + (p - T % p)                 # hifigan.py:413-416
-                if Tp != T:
-                    xp = into["xp"][ci][lo:lo + B] if into is not None else torch.empty((B, Tp), dtype=torch.float32, device=dev)
-                    call("artic_reflect_pad_right", ptr(x2d), ptr(xp), B, T, Tp, F32)
-                else:
-                    xp = x2d
-                tape["xp"][ci] = xp
-                H = Tp // p
-                h = SeqT(xp, B * p, H, 1, n_inner=p, s_outer=Tp, s_inner=1, s_row=p)
+                xp = xps[ci]
+                Tp = xp.shape[1]
+                h = SeqT(xp, B * p, Tp // p, 1, n_inner=p, s_outer=Tp, s_inner=1, s_row=p)
                 slope = self.slope_p
             acts = [h]
             n = len(ch.layers)
@@ -673,6 +739,10 @@ class DiscriminatorEngine:
                     lay.forward(h, Y2=o, act=ACT_LRELU, act_slope=slope)
                 acts.append(o)
                 h = o
+            return acts
+
+        all_acts = fork_join([lambda ci=ci: chain_fwd(ci) for ci in range(len(self.chains))])
+        for acts in all_acts:
             outs.append(acts[1:])
             tape["chains"].append(acts)
         tape["sigs"] = sigs
@@ -699,13 +769,16 @@ class DiscriminatorEngine:
         dx = torch.zeros((B, 1, T), dtype=torch.float32, device=dev) if need_dx else None
         n_scales = len(tape["sigs"])
         dsig = [None] * n_scales
-        for ci, ch in enumerate(self.chains):
+
+        def chain_bwd(ci):
+            ch = self.chains[ci]
             acts = tape["chains"][ci]           # acts[0] = input signal, acts[l+1] = output of layer l
             dl = douts[ci]
             slope = self.slope_s if ch.kind == "scale" else self.slope_p
             n = len(ch.layers)
             dz = dl[n - 1]                      # logits gradient (fp32 SeqT)
             assert dz is not None
+            d_in = None
             for li in range(n - 1, -1, -1):
                 lay = ch.layers[li]
                 if grads is not None:
@@ -715,17 +788,24 @@ class DiscriminatorEngine:
                     lay.dgrad(dz, dX=dn, res_pre=dl[li - 1], mask=acts[li], mask_slope=slope)
                     dz = dn
                 elif need_dx:
-                    dn = acts[0].like(code=F32) if ch.kind == "scale" else None
                     if ch.kind == "scale":
-                        lay.dgrad(dz, dX=dn)
-                        dsig[ch.scale_index] = dn
+                        d_in = acts[0].like(code=F32)
+                        lay.dgrad(dz, dX=d_in)
                     else:
                         h = acts[0]
                         Tp = h.s_outer
                         dxp = torch.empty((B, Tp), dtype=torch.float32, device=dev)
-                        dn = SeqT(dxp, h.N, h.L, 1, n_inner=h.n_inner, s_outer=Tp, s_inner=1, s_row=h.s_row)
-                        lay.dgrad(dz, dX=dn)
-                        call("artic_reflect_pad_right_bwd", ptr(dxp), ptr(dx), B, T, Tp, 1, F32)
+                        d_in = SeqT(dxp, h.N, h.L, 1, n_inner=h.n_inner, s_outer=Tp, s_inner=1, s_row=h.s_row)
+                        lay.dgrad(dz, dX=d_in)
+            return d_in
+
+        d_ins = fork_join([lambda ci=ci: chain_bwd(ci) for ci in range(len(self.chains))])
+        if need_dx:     # the chains' input gradients meet in dx on the main stream
+            for ch, d_in in zip(self.chains, d_ins):
+                if ch.kind == "scale":
+                    dsig[ch.scale_index] = d_in
+                else:
+                    call("artic_reflect_pad_right_bwd", ptr(d_in.t), ptr(dx), B, T, d_in.s_outer, 1, F32)
         if need_dx:
             k, st, pd = self.pool["kernel_size"], self.pool["stride"], self.pool["padding"]
             for s in range(n_scales - 1, 0, -1):

@@ -138,16 +138,14 @@ def run_ours(args):
 
     from articulatory_b200 import _lib
     from articulatory_b200 import models as M
+    from articulatory_b200.parallel import DataParallel, env_world
     from articulatory_b200.trainer import TrainStep
     from oracle import torch_oracle as O  # synthetic workload generator + yaml constants
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    dp = DataParallel(backend="nccl", device=dev)      # one process per GPU; NCCL over NVLink / NVSwitch
     _lib.load()
 
     torch.manual_seed(0)
@@ -155,12 +153,9 @@ def run_ours(args):
         warnings.simplefilter("ignore")
         G = M.HiFiGANGenerator(**O.E2W_GENERATOR_PARAMS, precision=args.precision).to(dev)
         D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**O.E2W_DISCRIMINATOR_PARAMS, precision=args.precision).to(dev)
-    all_reduce = None
-    if world > 1:
-        for p in list(G.parameters()) + list(D.parameters()):
-            dist.broadcast(p.data, 0)
-        all_reduce = lambda flat: dist.all_reduce(flat)  # noqa: E731  (sum; 1/world folded into loss seeds)
-    ts = TrainStep(G, D, train_config(), dev, world_size=world, all_reduce=all_reduce)
+    dp.broadcast_parameters(G, D)
+    # gradient exchange: sum of the flat fp32 gradient buffers (1/world is folded into the loss seeds)
+    ts = TrainStep(G, D, train_config(), dev, world_size=world, all_reduce=dp.all_reduce if world > 1 else None)
     B = BATCH_PER_GPU
     host = O.synthetic_batch(B, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}

@@ -138,7 +138,9 @@ int artic_colsum(const void* dY, const artic_seq_t* y, int32_t N, int32_t C, int
  *          b_pad >= m*B) so that grouped convs with < 32 channels per group still fill
  *          tensor-core tiles; a_pad / b_pad > m*A / m*B zero-pads odd channel counts (141 -> 144).
  *          Only the live entries are written: zero the buffers once.
- *   dWp    fp32 gradient in the 'fwd' layout (written by artic_tapconv_wgrad)
+ *   dWp    fp32 gradient in the 'fwd' layout (written by artic_tapconv_wgrad), or in the 'bwd' layout
+ *          when dw_swapped != 0 (transposed-conv layers compute dW^T as a strided-conv weight gradient
+ *          with the roles of X and dY exchanged)
  *   dv,dg  gradients of v and g in torch layout, OVERWRITTEN by artic_weights_unprep
  */
 typedef struct {
@@ -146,13 +148,17 @@ typedef struct {
   void* out_f; void* out_b;
   const float* dWp; float* dv; float* dg;
   int64_t row_len, sk, sg, sa, sb;
-  int32_t rows, K, G, A, B, merge, a_pad, b_pad, dtype_f, dtype_b;
+  int64_t tile_begin;   /* exclusive prefix sum of artic_wperm_tiles() over the table */
+  int32_t rows, K, G, A, B, merge, a_pad, b_pad, dtype_f, dtype_b, dw_swapped, reserved_;
 } artic_wdesc_t;
 
-/* scale + out_f + out_b of every descriptor (any_norm = 0 skips the norm pass). */
-int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, void* stream);
+/* Number of relayout tiles of one layer (host helper: fills tile_begin / total_tiles). */
+int64_t artic_wperm_tiles(int32_t K, int32_t G, int32_t A, int32_t B);
+/* scale + out_f + out_b of every descriptor (any_norm = 0 skips the norm pass); total_tiles = sum of
+ * artic_wperm_tiles over the table. */
+int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles, void* stream);
 /* Backward of artic_weights_prep: dWp -> dv (and dg, through the weight-norm Jacobian). */
-int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, void* stream);
+int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles, void* stream);
 
 /* ---- small fused elementwise ops on the path ---------------------------------------- */
 
@@ -170,6 +176,10 @@ int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int3
  * layer): out_act = lrelu((a+b+c)/3, slope); n elements; inputs in `dtype`, output in `out_dtype`. */
 int artic_mean3_act(const void* a, const void* b, const void* c, void* out_act, int64_t n,
                     float slope, int32_t dtype, int32_t out_dtype, void* stream);
+
+/* out = a + b + c (n elements of `dtype`): joins the input gradients of the three MRF blocks, which
+ * run on concurrent streams (models/hifigan.py:226-228 backward). */
+int artic_sum3(const void* a, const void* b, const void* c, void* out, int64_t n, int32_t dtype, void* stream);
 
 /* dpre = dy * (1 - y*y)  (torch.nn.Tanh backward, models/hifigan.py:158); fp32 dy/y in, `dtype` out. */
 int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64_t n, int32_t dtype, void* stream);
