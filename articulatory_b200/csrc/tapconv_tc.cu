@@ -24,6 +24,9 @@ namespace tc {
 constexpr int NTHREADS = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int MAX_WS = 10;  // weight stages (streaming mode)
 constexpr int MAX_AS = 8;   // activation stages
+#ifndef ARTIC_TC_TRACE
+#define ARTIC_TC_TRACE 0
+#endif
 constexpr int EPI_STAGE_BYTES = 8 * 32 * 8 * 16;   // 8 epilogue warps x [32 rows][32 channels] fp32
 constexpr int EPI_BYTES = EPI_STAGE_BYTES + 8 * 4 * 32 * 8;  // + per-warp row offsets of up to 4 sub-tiles
 
@@ -41,6 +44,8 @@ struct Plan {
   int32_t n_mt;       // row tiles in total
   int32_t total_tiles;
   int32_t a_stage_bytes, w_stage_bytes, n_as, n_ws;
+  int32_t w_tile_bytes;  // one tap's [bn x kch] weight tile (1024-byte multiple)
+  int32_t tps;           // taps per weight stage: one barrier hand-shake feeds tps * mt * kch/16 MMAs
   int32_t w_resident;   // 1: the whole weight [n_kc][ntaps][bn x kch] stays in shared memory for the CTA's lifetime
   int32_t acc_stages, tmem_cols;
   int32_t min_off;
@@ -84,19 +89,23 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
   __shared__ __align__(8) uint64_t a_full[MAX_AS], a_empty[MAX_AS], w_full[MAX_WS], w_empty[MAX_WS];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], w_res_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ long long tr_issue[64], tr_seen[64], tr_done[64];   // debug: per-W-load clocks (CTA 0)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1024-byte aligned operand staging area
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem0;
   const uint32_t w_base = smem0 + (uint32_t)pl.n_as * pl.a_stage_bytes;
-  const uint32_t epi_base = w_base + (uint32_t)(pl.w_resident ? pl.n_kc * p.ntaps : pl.n_ws) * pl.w_stage_bytes;   // 4 x 8 KB transpose stages + row offsets
+  const uint32_t epi_base = w_base + (pl.w_resident ? (uint32_t)(pl.n_kc * p.ntaps) * pl.w_tile_bytes : (uint32_t)pl.n_ws * pl.w_stage_bytes);   // 4 x 8 KB transpose stages + row offsets
 
   if (threadIdx.x == 0) dbg_mark(pl.dbg, 1);
   // Setup rendezvous on named barrier 1: the producer warp initialises the mbarriers, ARRIVES and goes
   // straight to its first TMA loads; the other warps (TMEM allocation in warp 1) SYNC on it.
   uint32_t tmem_base = 0;
   if (warp == 0) {
+    if (pl.dbg != nullptr) {
+      tr_issue[lane] = tr_issue[lane + 32] = tr_seen[lane] = tr_seen[lane + 32] = tr_done[lane] = tr_done[lane + 32] = 0;
+    }
     if (lane == 0) {
       prefetch_tmap(&map_x);
       prefetch_tmap(&map_w);
@@ -124,13 +133,16 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
     // =============================== TMA producer ===============================
     if (lane == 0) {
       PipeState as(pl.n_as), ws(pl.n_ws);
+#if ARTIC_TC_TRACE
+      int n_wl = 0;
+#endif
       const uint32_t w_bytes = (uint32_t)pl.bn * pl.row_bytes;
       if (pl.w_resident) {
         // small layers (n_nt == 1, G == 1): every tile uses the same weights; load them once
         mbar_expect_tx(&w_res_full, (uint32_t)(pl.n_kc * ntaps) * w_bytes);
         for (int kc = 0; kc < pl.n_kc; ++kc)
           for (int t = 0; t < ntaps; ++t)
-            tma_load_2d(w_base + (uint32_t)(kc * ntaps + t) * pl.w_stage_bytes, &map_w, &w_res_full, kc * pl.kch,
+            tma_load_2d(w_base + (uint32_t)(kc * ntaps + t) * pl.w_tile_bytes, &map_w, &w_res_full, kc * pl.kch,
                         p.widx[t] * p.Cog);
       }
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
@@ -165,11 +177,16 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
           }
           as.next();
           if (pl.w_resident) continue;
-          for (int t = 0; t < ntaps; ++t) {
+          for (int t0 = 0; t0 < ntaps; t0 += pl.tps) {
+            const int nt_g = min(pl.tps, ntaps - t0);
             mbar_wait(&w_empty[ws.stage], ws.phase ^ 1);
-            mbar_expect_tx(&w_full[ws.stage], w_bytes);
-            tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes, &map_w, &w_full[ws.stage], kc * pl.kch,
-                        (p.widx[t] * p.G + g) * p.Cog + nt * pl.bn);
+#if ARTIC_TC_TRACE
+            if (pl.dbg != nullptr && n_wl < 64) tr_issue[n_wl++] = clock64();
+#endif
+            mbar_expect_tx(&w_full[ws.stage], (uint32_t)nt_g * w_bytes);
+            for (int j = 0; j < nt_g; ++j)
+              tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes, &map_w,
+                          &w_full[ws.stage], kc * pl.kch, (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn);
             ws.next();
           }
         }
@@ -181,65 +198,87 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
     // critical path for narrow tiles: the shared-memory descriptors are reduced to one 32-bit add
     // per operand (constant high word; the low word is the 16-byte address, to which the tap's
     // precomputed row shift, the sub-tile offset and the k-step are added).
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       PipeState as(pl.n_as), ws(pl.n_ws), acc(pl.acc_stages);
+#if ARTIC_TC_TRACE
+      int n_ws_seen = 0;
+#endif
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.bn >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t desc_hi = (((8u * (uint32_t)pl.row_bytes) >> 4) & 0x3fffu) | (1u << 14) | ((uint32_t)(pl.layout_type & 7) << 29);
       const uint32_t desc_lo = 1u << 16;                      // LBO field (unused for swizzled K-major)
       const uint32_t m_step16 = (128u * (uint32_t)pl.row_bytes) >> 4;
       const int ksteps = pl.kch / 16;
-      const int mt = pl.mt;
+      const int mt = pl.mt, tps = pl.tps;
+      const bool w_res = pl.w_resident != 0;
+      const uint32_t bn = (uint32_t)pl.bn;
+      const uint32_t w_base16 = w_base >> 4, wt16 = (uint32_t)pl.w_tile_bytes >> 4, ws16 = (uint32_t)pl.w_stage_bytes >> 4;
       if (pl.w_resident) mbar_wait(&w_res_full, 0);
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[acc.stage], acc.phase ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)acc.stage * acc_cols;
         uint32_t accum = 0;
+        bool first_tap = true;
         for (int kc = 0; kc < pl.n_kc; ++kc) {
           mbar_wait(&a_full[as.stage], as.phase);
-          dbg_mark(pl.dbg, 20);
+          if (lane == 0) dbg_mark(pl.dbg, 20);
           const uint32_t a16 = desc_lo | (((a_base + (uint32_t)as.stage * pl.a_stage_bytes) >> 4) & 0x3fffu);
-          for (int t = 0; t < ntaps; ++t) {
-            const uint32_t w_slot = pl.w_resident ? (uint32_t)(kc * ntaps + t) : (uint32_t)ws.stage;
-            if (!pl.w_resident) mbar_wait(&w_full[ws.stage], ws.phase);
-            if (kc == 0 && t == 0) dbg_mark(pl.dbg, 21);
-            tc_fence_after();
-            const uint32_t b16 = desc_lo | (((w_base + w_slot * pl.w_stage_bytes) >> 4) & 0x3fffu);
-            uint32_t at16 = a16 + (uint32_t)pl.a_off16[t];
-            uint32_t dcol = d_base;
-            for (int m = 0; m < mt; ++m) {
-              if (ksteps == 4) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
-                  accum = 1;
-                }
-              } else if (ksteps == 2) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
-                  accum = 1;
-                }
-              } else {
-                umma_bf16(dcol, ((uint64_t)desc_hi << 32) | at16, ((uint64_t)desc_hi << 32) | b16, idesc, accum);
-                accum = 1;
-              }
-              // the accumulate flag must stay 0 for the first k-step of EVERY sub-tile of the tile
-              if (kc == 0 && t == 0 && m + 1 < mt) accum = 0;
-              at16 += m_step16;
-              dcol += (uint32_t)pl.bn;
+          for (int t0 = 0; t0 < ntaps; t0 += tps) {
+            const int nt_g = min(tps, ntaps - t0);
+            uint32_t w16;
+            if (w_res) {
+              w16 = w_base16 + (uint32_t)(kc * ntaps + t0) * wt16;
+            } else {
+              mbar_wait(&w_full[ws.stage], ws.phase);
+              w16 = w_base16 + (uint32_t)ws.stage * ws16;
             }
-            if (!pl.w_resident) {
-              umma_commit(&w_empty[ws.stage]);
+#if ARTIC_TC_TRACE
+            if (lane == 0 && pl.dbg != nullptr && n_ws_seen < 64) tr_seen[n_ws_seen] = clock64();
+#endif
+            tc_fence_after();
+            for (int j = 0; j < nt_g; ++j) {
+              const uint32_t b16 = desc_lo | ((w16 + (uint32_t)j * wt16) & 0x3fffu);
+              uint32_t at16 = a16 + (uint32_t)pl.a_off16[t0 + j];
+              uint32_t dcol = d_base;
+              for (int m = 0; m < mt; ++m) {
+                if (ksteps == 4) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    if (leader) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
+                    accum = 1;
+                  }
+                } else if (ksteps == 2) {
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) {
+                    if (leader) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
+                    accum = 1;
+                  }
+                } else {
+                  if (leader) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | at16, ((uint64_t)desc_hi << 32) | b16, idesc, accum);
+                  accum = 1;
+                }
+                // the accumulate flag must stay 0 for the first k-step of EVERY sub-tile of the tile
+                if (first_tap && m + 1 < mt) accum = 0;
+                at16 += m_step16;
+                dcol += bn;
+              }
+              first_tap = false;
+            }
+#if ARTIC_TC_TRACE
+            if (pl.dbg != nullptr && n_ws_seen < 64) { if (lane == 0) tr_done[n_ws_seen] = clock64(); ++n_ws_seen; }
+#endif
+            if (!w_res) {
+              if (leader) umma_commit(&w_empty[ws.stage]);
               ws.next();
             }
           }
-          umma_commit(&a_empty[as.stage]);
+          if (leader) umma_commit(&a_empty[as.stage]);
           as.next();
         }
-        umma_commit(&acc_full[acc.stage]);
-        dbg_mark(pl.dbg, 22);
+        if (leader) umma_commit(&acc_full[acc.stage]);
+        if (lane == 0) dbg_mark(pl.dbg, 22);
         acc.next();
       }
     }
@@ -393,6 +432,11 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (pl.dbg != nullptr && blockIdx.x == 0 && threadIdx.x < 64) {   // debug trace: slots [3000 + 3*i ..]
+    pl.dbg[3000 + 3 * threadIdx.x] = tr_issue[threadIdx.x];
+    pl.dbg[3001 + 3 * threadIdx.x] = tr_seen[threadIdx.x];
+    pl.dbg[3002 + 3 * threadIdx.x] = tr_done[threadIdx.x];
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
@@ -496,7 +540,13 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   if (mt < 1) mt = 1;
   if (mt > 4) mt = 4;
   if (mt_req > 0 && mt_req < mt) mt = mt_req;
-  pl.w_stage_bytes = ((pl.bn * pl.row_bytes + 1023) / 1024) * 1024;
+  pl.w_tile_bytes = ((pl.bn * pl.row_bytes + 1023) / 1024) * 1024;
+  pl.tps = 32 * 1024 / pl.w_tile_bytes;                  // stages of <= 32 KB
+  if (pl.tps > 4) pl.tps = 4;
+  if (pl.tps > p.ntaps) pl.tps = p.ntaps;
+  if (pl.tps < 1) pl.tps = 1;
+  if (tc::g_debug[0] > 0) pl.tps = tc::g_debug[0] < p.ntaps ? tc::g_debug[0] : p.ntaps;   // debug: force taps per stage
+  pl.w_stage_bytes = pl.tps * pl.w_tile_bytes;
   {  // keep two activation stages + a few weight stages within shared memory
     auto a_bytes = [&](int m) { return p.si * ((((m * 128 + span + 64) * pl.row_bytes + 1023) / 1024) * 1024); };
     while (mt > 1 && 2 * a_bytes(mt) + 3 * pl.w_stage_bytes > budget) --mt;
@@ -535,7 +585,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   // generator stages — their per-tile weight traffic would otherwise serialise the producer) or
   // streamed through up to MAX_WS stages; the rest goes to activation stages, because the bytes in
   // flight per SM (x ~2 us TMA latency) are what bounds the operand bandwidth.
-  const int w_all = pl.n_kc * p.ntaps * pl.w_stage_bytes;
+  const int w_all = pl.n_kc * p.ntaps * pl.w_tile_bytes;
   pl.w_resident = (pl.n_nt == 1 && p.G == 1 && w_all <= 96 * 1024 && budget - w_all >= 2 * pl.a_stage_bytes &&
                    tc::g_debug[7] != 1) ? 1 : 0;
   if (pl.w_resident) {
@@ -543,7 +593,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
     pl.n_as = (budget - w_all) / pl.a_stage_bytes;
     if (pl.n_as > tc::MAX_AS) pl.n_as = tc::MAX_AS;
   } else {
-    const int steps = pl.n_kc * p.ntaps;
+    const int steps = pl.n_kc * ((p.ntaps + pl.tps - 1) / pl.tps);
     int want_ws = steps < tc::MAX_WS ? steps : tc::MAX_WS;
     if (want_ws < 2) want_ws = 2;
     pl.n_as = 2;
@@ -632,7 +682,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("artic_tapconv: cuTensorMapEncodeTiled(W) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   }
-  const int smem_bytes = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? pl.n_kc * p.ntaps : pl.n_ws) * pl.w_stage_bytes + 1024 + tc::EPI_BYTES;
+  const int smem_bytes = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? pl.n_kc * p.ntaps * pl.w_tile_bytes : pl.n_ws * pl.w_stage_bytes) + 1024 + tc::EPI_BYTES;
   int grid = num_sms();
   if (grid > pl.total_tiles) grid = pl.total_tiles;
   tc::tapconv_tc_kernel<<<grid, tc::NTHREADS, smem_bytes, st>>>(p, pl, map_x, map_w);

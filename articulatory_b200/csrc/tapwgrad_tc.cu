@@ -158,7 +158,8 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
+    {   // whole warp runs the loop (uniform registers); one elected lane issues the tcgen05 instructions
+      const bool leader = elect_one();
       PipeState ps(pl.n_stages);
       // D fp32, A/B bf16, both MN-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
@@ -185,17 +186,17 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
           uint32_t acc_k = accum;
 #pragma unroll 4
           for (int k = 0; k < ksteps; ++k) {
-            umma_bf16(dcol, ((uint64_t)a_hi << 32) | ad, ((uint64_t)b_hi << 32) | bd, idesc, acc_k);
+            if (leader) umma_bf16(dcol, ((uint64_t)a_hi << 32) | ad, ((uint64_t)b_hi << 32) | bd, idesc, acc_k);
             acc_k = 1;
             ad += (uint32_t)pl.xrb;    // 16 positions * xrb bytes / 16
             bd += (uint32_t)pl.yrb;
           }
         }
         accum = 1;
-        umma_commit(&empty[ps.stage]);
+        if (leader) umma_commit(&empty[ps.stage]);
         ps.next();
       }
-      umma_commit(&acc_full);
+      if (leader) umma_commit(&acc_full);
     }
   } else {
     // =============================== epilogue ===================================

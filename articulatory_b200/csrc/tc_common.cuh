@@ -96,6 +96,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a converged warp (elect.sync): lets the whole warp run the issue loop, so that the
+// compiler keeps descriptors / addresses in UNIFORM registers and the single tcgen05 / TMA
+// instruction takes them directly (a loop under `if (lane == 0)` is divergent code: every MMA then
+// pays ~5 R2UR moves and an ELECT loop, measured ~190 clocks per MMA instead of 64).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 struct PipeState {
   int stage, phase, n;
   __device__ __forceinline__ PipeState(int n_) : stage(0), phase(0), n(n_) {}

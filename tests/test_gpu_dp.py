@@ -1,0 +1,89 @@
+"""Data-parallel train step on two GPUs (NCCL): two ranks with half the batch each must take the same
+optimizer steps as one GPU with the whole batch (losses that are plain batch means: mel + adversarial +
+feature matching; spectral convergence is a per-rank ratio by design).
+Skipped unless two CUDA devices are visible (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_dp.py -m gpu`)."""
+import os
+import socket
+import warnings
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(golden):
+    from tests.test_gpu_models import _train_config
+    return _train_config(golden, stft=False)
+
+
+def _build(golden, dev):
+    from articulatory_b200 import models as M
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = M.HiFiGANGenerator(**golden["generator_params"])
+        D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**golden["discriminator_params"])
+    G.load_state_dict(golden["gsd"])
+    D.load_state_dict(golden["dsd"])
+    return G.to(dev), D.to(dev)
+
+
+def _batch(golden):
+    b = golden["batch"]          # 2 items -> 4 items (second pair time-reversed) so each rank gets 2
+    return {"x": torch.cat([b["x"], b["x"].flip(2)]), "y": torch.cat([b["y"], b["y"].flip(2)]),
+            "ar": torch.cat([b["ar"], b["ar"].flip(2)])}
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    from articulatory_b200.parallel import DataParallel
+    from articulatory_b200.trainer import TrainStep
+    golden = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_e2w.pt"),
+                        weights_only=False)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dp = DataParallel(backend="nccl", device=dev)
+    G, D = _build(golden, dev)
+    dp.broadcast_parameters(G, D)
+    ts = TrainStep(G, D, _cfg(golden), dev, world_size=world, all_reduce=dp.all_reduce)
+    shard = {k: v.to(dev) for k, v in dp.shard(_batch(golden)).items()}
+    for _ in range(4):
+        ts.step(shard["x"], shard["y"], shard["ar"], use_graph=True)
+    torch.cuda.synchronize()
+    torch.save({"g": {k: v.cpu() for k, v in G.state_dict().items()}, "vals": ts.last_values()},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dp.barrier()
+    dp.close()
+
+
+def test_two_gpu_step_matches_single_gpu(golden, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from articulatory_b200.trainer import TrainStep
+    from tests.helpers import rel_err
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "r0.pt", weights_only=False)
+    r1 = torch.load(tmp_path / "r1.pt", weights_only=False)
+    for k in r0["g"]:
+        assert torch.equal(r0["g"][k], r1["g"][k]), f"ranks diverged on {k}"
+    dev = torch.device("cuda", 0)
+    G, D = _build(golden, dev)
+    ts = TrainStep(G, D, _cfg(golden), dev)
+    full = {k: v.to(dev) for k, v in _batch(golden).items()}
+    for _ in range(4):
+        ts.step(full["x"], full["y"], full["ar"], use_graph=False)
+    for k, v in G.state_dict().items():
+        d_ref = v.cpu() - golden["gsd"][k]
+        d_dp = r0["g"][k] - golden["gsd"][k]
+        if d_ref.abs().max() > 0:
+            assert rel_err(d_dp, d_ref) < 0.1, (k, rel_err(d_dp, d_ref))     # Adam's sign-like first steps amplify fp noise
+    one = ts.last_values()
+    for k in ("train/mel_loss", "train/adversarial_loss", "train/feature_matching_loss"):
+        both = 0.5 * (r0["vals"][k] + r1["vals"][k])
+        assert abs(both - one[k]) <= 2e-3 * abs(one[k]), (k, both, one[k])

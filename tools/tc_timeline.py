@@ -18,8 +18,8 @@ from tools.tc_sweep import SHAPES, seq  # noqa: E402
 
 def main():
     lib = _lib.load()
-    buf = torch.zeros(4096, dtype=torch.int64, device="cuda:0")
-    for i in (0, 2, 6, 12, 14, 24):
+    buf = torch.zeros(8192, dtype=torch.int64, device="cuda:0")
+    for i in (0, 2, 6, 24):
         kw, N, lin, ni = SHAPES[i]
         spec = ConvSpec(**kw)
         lay = ConvLayer(spec, "l", BF16, BF16)
@@ -40,6 +40,11 @@ def main():
         t0 = ev[0][0]
         print(f"== {kw} N={N} L={lin}: {n} events")
         print("   " + " ".join(f"{tag}@{t - t0}" for t, tag in ev[:160]))
+        tr = [(h[3000 + 3 * j], h[3001 + 3 * j], h[3002 + 3 * j]) for j in range(48)]
+        tr = [x for x in tr if x[0] > 0 and x[1] > 0]
+        if tr:
+            print("   W loads (issue, seen-by-MMA, mma-issued; latency): " +
+                  " ".join(f"[{a - t0},{b - t0},{c - t0};{b - a}]" for a, b, c in tr))
 
 
 if __name__ == "__main__":
