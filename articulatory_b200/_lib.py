@@ -100,6 +100,7 @@ SIGNATURES = {
     "artic_sqerr_sum": (C.c_int, [_p, _i64, _f, _f, _p, _i32, _p]),
     "artic_sqerr_bwd": (C.c_int, [_p, _i64, _f, _f, _p, _i32, _i32, _p]),
     "artic_l1_sum": (C.c_int, [_p, _p, _i64, _f, _p, _i32, _p]),
+    "artic_l1_sum_bwd": (C.c_int, [_p, _p, _i64, _f, _p, _f, _p, _i32, _p]),
     "artic_l1_bwd": (C.c_int, [_p, _p, _i64, _f, _p, _i32, _i32, _p]),
     "artic_stft_loss_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _p]),
     "artic_stft_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _f, _f, _p, _p]),

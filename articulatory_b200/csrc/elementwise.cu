@@ -186,6 +186,45 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
   }
 }
 
+// Fused feature-matching term: slot += sum_scale * sum |a - b| and da = grad_scale * sign(a - b) in one
+// pass over the two feature maps (8 bf16 per thread and iteration when VEC).
+template <bool VEC>
+__global__ void __launch_bounds__(256) l1_fused_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, int64_t n,
+                                                            float sum_scale, float* __restrict__ slot, float grad_scale,
+                                                            __nv_bfloat16* __restrict__ da) {
+  __shared__ float red[32];
+  float s = 0.f;
+  if (VEC) {
+    const int64_t n8 = n >> 3;
+    const uint4* a4 = reinterpret_cast<const uint4*>(a);
+    const uint4* b4 = reinterpret_cast<const uint4*>(b);
+    uint4* d4 = reinterpret_cast<uint4*>(da);
+    GRID_STRIDE(i, n8) {
+      const uint4 ua = __ldg(a4 + i), ub = __ldg(b4 + i);
+      const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+      uint32_t wo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d0 = __uint_as_float(wa[j] << 16) - __uint_as_float(wb[j] << 16);
+        const float d1 = __uint_as_float(wa[j] & 0xffff0000u) - __uint_as_float(wb[j] & 0xffff0000u);
+        s += fabsf(d0) + fabsf(d1);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(d0 > 0.f ? grad_scale : (d0 < 0.f ? -grad_scale : 0.f),
+                                                       d1 > 0.f ? grad_scale : (d1 < 0.f ? -grad_scale : 0.f));
+        wo[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      d4[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+    }
+  } else {
+    GRID_STRIDE(i, n) {
+      const float d = ld_f(a + i) - ld_f(b + i);
+      s += fabsf(d);
+      st_f(da + i, d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f));
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(slot, s * sum_scale);
+}
+
 __global__ void add_rows_kernel(const float* __restrict__ src, int64_t sp, float* __restrict__ dst, int64_t dp, int rows,
                                 int cols) {
   const int64_t n = (int64_t)rows * cols;
@@ -369,6 +408,18 @@ extern "C" int artic_l1_bwd(const void* a, const void* b, int64_t n, float scale
   if (n == 0) return ARTIC_OK;
   DISPATCH(dtype, (l1_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>((const float*)a, (const float*)b, n, scale, (float*)da, accumulate)),
            (l1_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, n, scale, (bf16*)da, accumulate)));
+}
+
+extern "C" int artic_l1_sum_bwd(const void* a, const void* b, int64_t n, float sum_scale, float* slot, float grad_scale,
+                                void* da, int32_t dtype, void* stream) {
+  ARTIC_CHECK_ARG(a && b && slot && da, "null pointer");
+  ARTIC_CHECK_ARG(dtype == ARTIC_BF16, "the fused kernel is bf16-only (use artic_l1_sum + artic_l1_bwd for fp32)");
+  if (n == 0) return ARTIC_OK;
+  const bool vec = (n % 8 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(da)) & 15) == 0;
+  if (vec) l1_fused_bf16_kernel<true><<<grid_for(n / 8, 1024), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, n, sum_scale, slot, grad_scale, (bf16*)da);
+  else l1_fused_bf16_kernel<false><<<grid_for(n, 1024), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, n, sum_scale, slot, grad_scale, (bf16*)da);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
 }
 
 extern "C" int artic_add_rows(const float* src, int64_t src_pitch, float* dst, int64_t dst_pitch, int32_t rows,

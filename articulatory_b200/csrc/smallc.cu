@@ -48,20 +48,26 @@ __global__ void __launch_bounds__(256) tapconv_co1_kernel(const __grid_constant_
   const T* __restrict__ X = reinterpret_cast<const T*>(p.X) + seq_base(p.x, n);
   const T* __restrict__ W = reinterpret_cast<const T*>(p.W);
   float acc = 0.f;
-  for (int t = 0; t < p.ntaps; ++t) {
-    const int pos = q * p.si + p.off[t];
-    if (pos < 0 || pos >= p.x.len) continue;
-    const T* xr = X + (int64_t)pos * p.x.s_row;
-    const T* wr = W + (int64_t)p.widx[t] * p.Cig;   // [K][G=1][Cig][Cog=1]
-    if (VEC) {
-      for (int c = lane * 8; c < p.Cig; c += 256) {
-        float a[8], b[8];
-        Ld8<T>::load(xr + c, a);
-        Ld8<T>::load(wr + c, b);
+  if (VEC) {
+    // lanes run over the flattened (tap, 8-channel chunk) index, so narrow layers (the generator's
+    // 32 -> 1 output conv: 7 taps x 4 chunks) still use 28 of 32 lanes
+    const int cpt = p.Cig >> 3;
+    for (int e = lane; e < p.ntaps * cpt; e += 32) {
+      const int t = e / cpt, c = (e - t * cpt) << 3;
+      const int pos = q * p.si + p.off[t];
+      if (pos < 0 || pos >= p.x.len) continue;
+      float a[8], b[8];
+      Ld8<T>::load(X + (int64_t)pos * p.x.s_row + c, a);
+      Ld8<T>::load(W + (int64_t)p.widx[t] * p.Cig + c, b);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
-      }
-    } else {
+      for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
+    }
+  } else {
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int pos = q * p.si + p.off[t];
+      if (pos < 0 || pos >= p.x.len) continue;
+      const T* xr = X + (int64_t)pos * p.x.s_row;
+      const T* wr = W + (int64_t)p.widx[t] * p.Cig;   // [K][G=1][Cig][Cog=1]
       for (int c = lane; c < p.Cig; c += 32) acc = fmaf(ld_f(xr + c), ld_f(wr + c), acc);
     }
   }

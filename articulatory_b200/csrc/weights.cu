@@ -73,42 +73,39 @@ __global__ void __launch_bounds__(256) wperm_kernel(const artic_wdesc_t* __restr
     auto poff = [&](int kk, int r, int c) -> int64_t {
       return (((int64_t)(k0 + kk) * Gs + g / m) * r_pad + (g % m) * Rn + r0 + r) * (int64_t)c_pad + (g % m) * Cn + c0 + c;
     };
-    const int n_el = PT * PT * kn;
+    // thread mapping without divisions: lane l = tid % 32 runs along the contiguous side of each phase
+    // (torch side: the torch-inner matrix dim, each thread walking the kn contiguous taps; prepared
+    // side: the column), w8 = tid / 32 strides the other matrix dim in steps of 8.
+    const int l = threadIdx.x & 31, w8 = threadIdx.x >> 5;
     if (MODE != 2) {
-      // torch -> smem (taps fastest, then the torch-inner matrix dim)
-      for (int e = threadIdx.x; e < n_el; e += 256) {
-        const int kk = e % kn;
-        const int i = (e / kn) % PT, o = e / (kn * PT);
-        const int r = r_inner ? i : o, c = r_inner ? o : i;
-        float val = 0.f;
-        if (r0 + r < Rn && c0 + c < Cn) {
-          const int64_t src = tbase + (int64_t)kk * d.sk + (int64_t)(r0 + r) * sr + (int64_t)(c0 + c) * sc;
-          val = d.v[src];
-          if (d.g != nullptr) val *= d.scale[src / d.row_len];
-        }
-        tile[kk][r][c] = val;
+      for (int o = w8; o < PT; o += 8) {
+        const int r = r_inner ? l : o, c = r_inner ? o : l;
+        const bool ok = r0 + r < Rn && c0 + c < Cn;
+        const int64_t src = tbase + (int64_t)(r0 + r) * sr + (int64_t)(c0 + c) * sc;
+        const float sc_row = (ok && d.g != nullptr) ? d.scale[src / d.row_len] : 1.f;
+        for (int kk = 0; kk < kn; ++kk) tile[kk][r][c] = ok ? d.v[src + (int64_t)kk * d.sk] * sc_row : 0.f;
       }
       __syncthreads();
-      for (int e = threadIdx.x; e < n_el; e += 256) {
-        const int c = e % PT, r = (e / PT) % PT, kk = e / (PT * PT);
-        if (r0 + r < Rn && c0 + c < Cn) {
-          const int64_t o = poff(kk, r, c);
-          if (dtype == ARTIC_BF16) reinterpret_cast<__nv_bfloat16*>(outp)[o] = __float2bfloat16_rn(tile[kk][r][c]);
-          else reinterpret_cast<float*>(outp)[o] = tile[kk][r][c];
-        }
+      if (c0 + l < Cn) {
+        for (int kk = 0; kk < kn; ++kk)
+          for (int r = w8; r < PT && r0 + r < Rn; r += 8) {
+            const int64_t o = poff(kk, r, l);
+            if (dtype == ARTIC_BF16) reinterpret_cast<__nv_bfloat16*>(outp)[o] = __float2bfloat16_rn(tile[kk][r][l]);
+            else reinterpret_cast<float*>(outp)[o] = tile[kk][r][l];
+          }
       }
     } else {
-      for (int e = threadIdx.x; e < n_el; e += 256) {
-        const int c = e % PT, r = (e / PT) % PT, kk = e / (PT * PT);
-        tile[kk][r][c] = (r0 + r < Rn && c0 + c < Cn) ? d.dWp[poff(kk, r, c)] : 0.f;
+      if (c0 + l < Cn) {
+        for (int kk = 0; kk < kn; ++kk)
+          for (int r = w8; r < PT && r0 + r < Rn; r += 8) tile[kk][r][l] = d.dWp[poff(kk, r, l)];
       }
       __syncthreads();
-      for (int e = threadIdx.x; e < n_el; e += 256) {
-        const int kk = e % kn;
-        const int i = (e / kn) % PT, o = e / (kn * PT);
-        const int r = r_inner ? i : o, c = r_inner ? o : i;
-        if (r0 + r < Rn && c0 + c < Cn)
-          d.dv[tbase + (int64_t)kk * d.sk + (int64_t)(r0 + r) * sr + (int64_t)(c0 + c) * sc] = tile[kk][r][c];
+      for (int o = w8; o < PT; o += 8) {
+        const int r = r_inner ? l : o, c = r_inner ? o : l;
+        if (r0 + r < Rn && c0 + c < Cn) {
+          const int64_t dst = tbase + (int64_t)(r0 + r) * sr + (int64_t)(c0 + c) * sc;
+          for (int kk = 0; kk < kn; ++kk) d.dv[dst + (int64_t)kk * d.sk] = tile[kk][r][c];
+        }
       }
     }
     __syncthreads();
@@ -150,14 +147,32 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   const float bc1 = (float)(1.0 - pow((double)h.beta1, t));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)h.beta2, t));
   const float step_size = lr / bc1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i];
-    const float mi = m[i] + (gi - m[i]) * (1.f - h.beta1);      // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * h.beta2 + (1.f - h.beta2) * gi * gi; // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + h.eps;
-    p[i] -= step_size * (mi / denom);
+  // 128-bit accesses over the 16-byte aligned body (the flat buffers come from the torch allocator), scalar tail
+  const int64_t n4 = (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                        reinterpret_cast<uintptr_t>(v)) & 15) == 0) ? (n >> 2) : 0;
+  const float b1 = h.beta1, b2 = h.beta2, eps = h.eps;
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    mi = mi + (gi - mi) * (1.f - b1);              // exp_avg.lerp_(grad, 1 - beta1)
+    vi = vi * b2 + (1.f - b2) * gi * gi;           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  };
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    upd(pp.x, gg.x, mm.x, vv.x);
+    upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z);
+    upd(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 
@@ -205,7 +220,7 @@ extern "C" int artic_adam_step(float* p, const float* g, float* m, float* v, int
   ARTIC_CHECK_ARG(p && g && m && v && hyper, "null pointer");
   if (n == 0) return ARTIC_OK;
   int64_t blocks = (n + 1023) / 1024;
-  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
   adam_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, hyper);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;

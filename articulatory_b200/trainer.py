@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from ._lib import F32, call, ptr
-from .engine import SeqT, slice_seq
+from .engine import SeqT, fork_join, slice_seq
 from .losses.spectral import MelSpectrogramLoss, MultiResolutionSTFTLoss
 from .optim import FusedAdam
 
@@ -134,18 +134,26 @@ class TrainStep:
             outs_f = [[slice_seq(o, 0, B) for o in lst] for lst in outs2]
             outs_r = [[slice_seq(o, B, 2 * B) for o in lst] for lst in outs2]
             lg_grads = [lst[-1].like() for lst in outs_f]
-            self._adv_seed(outs_f, 1.0, _ADV, self.l_adv * inv_w, lg_grads)
-            douts = []
-            for ci, (lf, lr_) in enumerate(zip(outs_f, outs_r)):
+
+            def seed_chain(ci):
+                # adversarial seed of the logits + feature-matching term of every feature map of one
+                # sub-discriminator (its own stream: ~6 small kernels per chain overlap across chains)
+                self._adv_seed(outs_f[ci:ci + 1], 1.0, _ADV, self.l_adv * inv_w, lg_grads[ci:ci + 1])
                 dl = []
-                for a, b in zip(lf[:-1], lr_[:-1]):
+                for a, b in zip(outs_f[ci][:-1], outs_r[ci][:-1]):
                     n = a.numel()
-                    call("artic_l1_sum", ptr(a.t), ptr(b.t), n, 1.0 / n, ptr(self.slots[_FM:]), a.code)
                     g = a.like()
-                    call("artic_l1_bwd", ptr(a.t), ptr(b.t), n, self.l_adv * self.l_fm * inv_w / n, ptr(g.t), 0, a.code)
+                    if a.code == _lib.BF16:
+                        call("artic_l1_sum_bwd", ptr(a.t), ptr(b.t), n, 1.0 / n, ptr(self.slots[_FM:]),
+                             self.l_adv * self.l_fm * inv_w / n, ptr(g.t), a.code)
+                    else:
+                        call("artic_l1_sum", ptr(a.t), ptr(b.t), n, 1.0 / n, ptr(self.slots[_FM:]), a.code)
+                        call("artic_l1_bwd", ptr(a.t), ptr(b.t), n, self.l_adv * self.l_fm * inv_w / n, ptr(g.t), 0, a.code)
                     dl.append(g)
                 dl.append(lg_grads[ci])
-                douts.append(dl)
+                return dl
+
+            douts = fork_join([lambda ci=ci: seed_chain(ci) for ci in range(len(outs_f))])
             d_in = engD.backward(engD.slice_tape(tape2, 0, B), douts, grads=None, need_dx=True)    # dgrad only
             La = self.ar_len
             call("artic_add_rows", ptr(d_in) + 4 * La, La + T, ptr(dy), T, B, T)
@@ -169,8 +177,11 @@ class TrainStep:
         outs_f = [[slice_seq(lst[-1], 0, B)] for lst in outs2]
         outs_r = [[slice_seq(lst[-1], B, 2 * B)] for lst in outs2]
         lg_grads = [lst[-1].like() for lst in outs2]
-        self._adv_seed(outs_r, 1.0, _REAL, inv_w, lg_grads, lo=B)             # :415-418
-        self._adv_seed(outs_f, 0.0, _FAKE, inv_w, lg_grads, lo=0)
+        def seed_chain(ci):                                                   # :415-418, one stream per chain
+            self._adv_seed(outs_r[ci:ci + 1], 1.0, _REAL, inv_w, lg_grads[ci:ci + 1], lo=B)
+            self._adv_seed(outs_f[ci:ci + 1], 0.0, _FAKE, inv_w, lg_grads[ci:ci + 1], lo=0)
+
+        fork_join([lambda ci=ci: seed_chain(ci) for ci in range(len(outs2))])
         self.optD.zero_grad()
         douts = [[None] * (len(lst) - 1) + [lg_grads[ci]] for ci, lst in enumerate(outs2)]
         engD.backward(tape2, douts, grads=self.optD.grad_views, need_dx=False)

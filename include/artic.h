@@ -228,6 +228,11 @@ int artic_l1_sum(const void* a, const void* b, int64_t n, float scale, float* sl
 int artic_l1_bwd(const void* a, const void* b, int64_t n, float scale, void* da, int32_t accumulate,
                  int32_t dtype, void* stream);
 
+/* Fused feature-matching term (bf16): slot[0] += sum_scale * sum_i |a_i - b_i| and da_i = grad_scale *
+ * sign(a_i - b_i) in one pass (losses/feat_match_loss.py:41-53 and its backward). */
+int artic_l1_sum_bwd(const void* a, const void* b, int64_t n, float sum_scale, float* slot, float grad_scale,
+                     void* da, int32_t dtype, void* stream);
+
 /*
  * Device-side assembly of the scalars the reference logs every step (bin/train.py:289-369,
  * 415-421) from the raw accumulators, without a host sync:
