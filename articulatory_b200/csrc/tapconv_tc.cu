@@ -21,14 +21,13 @@
 namespace artic {
 namespace tc {
 
-constexpr int NTHREADS = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int NTHREADS = 320;   // max: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (4 or 8 of them)
 constexpr int MAX_WS = 10;  // weight stages (streaming mode)
 constexpr int MAX_AS = 8;   // activation stages
 #ifndef ARTIC_TC_TRACE
 #define ARTIC_TC_TRACE 0
 #endif
-constexpr int EPI_STAGE_BYTES = 8 * 32 * 8 * 16;   // 8 epilogue warps x [32 rows][32 channels] fp32
-constexpr int EPI_BYTES = EPI_STAGE_BYTES + 8 * 4 * 32 * 8;  // + per-warp row offsets of up to 4 sub-tiles
+constexpr int EPI_WARP_BYTES = 32 * 8 * 16 + 4 * 32 * 8;   // per epilogue warp: [32 rows][32 channels] fp32 stage + row offsets of 4 sub-tiles
 
 struct Plan {
   int32_t kch;        // channels per K chunk (64 / 32 / 16)
@@ -111,16 +110,16 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
       prefetch_tmap(&map_w);
       for (int i = 0; i < pl.n_as; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < pl.n_ws; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], blockDim.x - 64); }
       mbar_init(&w_res_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("bar.arrive 1, %0;" ::"r"(NTHREADS) : "memory");
+    asm volatile("bar.arrive 1, %0;" ::"r"(blockDim.x) : "memory");
   } else {
     if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)pl.tmem_cols);
     tc_fence_before();
-    asm volatile("bar.sync 1, %0;" ::"r"(NTHREADS) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x) : "memory");
     tc_fence_after();
     tmem_base = tmem_base_s;
   }
@@ -304,8 +303,9 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
     TO* __restrict__ Y = reinterpret_cast<TO*>(p.Y);
     TO* __restrict__ Y2 = reinterpret_cast<TO*>(p.Y2);
     uint8_t* epi = smem_raw + (epi_base - smem_u32(smem_raw));
-    float4* stage = reinterpret_cast<float4*>(epi) + ewarp * (32 * 8);                        // [32 rows][8 units]
-    long long* rowoff = reinterpret_cast<long long*>(epi + EPI_STAGE_BYTES) + ewarp * (4 * 32);   // [sub-tile][32 rows]
+    const int n_ew = (int)(blockDim.x >> 5) - 2;            // 4 or 8 epilogue warps
+    float4* stage = reinterpret_cast<float4*>(epi + ewarp * EPI_WARP_BYTES);                  // [32 rows][8 units]
+    long long* rowoff = reinterpret_cast<long long*>(epi + ewarp * EPI_WARP_BYTES + 32 * 8 * 16);   // [sub-tile][32 rows]
     const int g8 = lane & 3, rsub = lane >> 2;
     for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
       const int nt = tile % pl.n_nt;
@@ -338,7 +338,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
       bool waited = false;
       for (int m = 0; m < pl.mt; ++m) {
         const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc.stage * acc_cols + (uint32_t)m * pl.bn;
-        for (int c0 = eh * 32; c0 < pl.bn; c0 += 64) {
+        for (int c0 = eh * 32; c0 < pl.bn; c0 += 8 * n_ew) {
           // ---- (1) everything independent of the accumulator
           long long oo[4];
           uint4 q_rp[4], q_mk[4], q_rs[4], q_r2[4];
@@ -460,7 +460,7 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_debug[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 long long* g_dbg_buf = nullptr;
 static int g_smem_optin = 0;
 
@@ -496,7 +496,7 @@ extern "C" int artic_debug_buffer(void* dev_buf) {
 }
 
 extern "C" int artic_debug_set(int key, int value) {
-  if (key < 0 || key >= 8) return ARTIC_EINVAL;
+  if (key < 0 || key >= 16) return ARTIC_EINVAL;
   tc::g_debug[key] = value;
   return ARTIC_OK;
 }
@@ -516,7 +516,15 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   tc::EncodeTiledFn enc = tc::encode_fn();
   if (enc == nullptr) return 0;
 
-  const int budget = tc::max_smem() - 1024 /*alignment slack*/ - tc::EPI_BYTES;
+  // "compact" CTAs (debug key 8 = shared-memory cap in KB, e.g. 110): <= half of the SM's shared memory,
+  // <= 256 TMEM columns and 4 epilogue warps, so that TWO CTAs (usually of different kernels running on
+  // concurrent streams) share an SM and one's prologue / epilogue tail overlaps the other's main loop.
+  const int smem_cap = tc::g_debug[8] > 0 ? tc::g_debug[8] * 1024 : tc::max_smem();
+  const bool compact = smem_cap < tc::max_smem();
+  const int n_ew = compact ? 4 : 8;
+  const int tmem_cap = compact ? 256 : 512;
+  const int epi_bytes = n_ew * tc::EPI_WARP_BYTES;
+  const int budget = (smem_cap < tc::max_smem() ? smem_cap : tc::max_smem()) - 1024 /*alignment slack*/ - epi_bytes;
   auto make_plan = [&](tc::Plan& pl, int bn_req, int mt_req) -> bool {
     memset(&pl, 0, sizeof(pl));
   int min_off = p.off[0], max_off = p.off[0];
@@ -536,7 +544,7 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
   pl.layout_type = pl.row_bytes == 128 ? 2 : pl.row_bytes == 64 ? 4 : 6;
   pl.bn = bn_req;
   pl.n_nt = p.Cog / pl.bn;
-  int mt = 512 / pl.bn;   // up to the whole TMEM (single-buffered accumulator when > 256 columns)
+  int mt = tmem_cap / pl.bn;   // up to the whole TMEM budget (single-buffered accumulator when > half of it)
   if (mt < 1) mt = 1;
   if (mt > 4) mt = 4;
   if (mt_req > 0 && mt_req < mt) mt = mt_req;
@@ -575,10 +583,10 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
     a_rows = pl.nbox * pl.boxr;
   }
   pl.mt = mt;
-  pl.acc_stages = (2 * mt * pl.bn <= 512) ? 2 : 1;
+  pl.acc_stages = (2 * mt * pl.bn <= tmem_cap) ? 2 : 1;
   int cols = pl.acc_stages * mt * pl.bn;
   pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-  if (cols > 512) return false;
+  if (cols > tmem_cap) return false;
   pl.panel_bytes = ((a_rows * pl.row_bytes + 1023) / 1024) * 1024;
   pl.a_stage_bytes = pl.n_ph * pl.panel_bytes;
   // Shared memory: weights either RESIDENT (single channel tile, single group, <= 96 KB: the C = 32 / 64
@@ -682,10 +690,10 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("artic_tapconv: cuTensorMapEncodeTiled(W) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   }
-  const int smem_bytes = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? pl.n_kc * p.ntaps * pl.w_tile_bytes : pl.n_ws * pl.w_stage_bytes) + 1024 + tc::EPI_BYTES;
+  const int smem_bytes = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? pl.n_kc * p.ntaps * pl.w_tile_bytes : pl.n_ws * pl.w_stage_bytes) + 1024 + epi_bytes;
   int grid = num_sms();
   if (grid > pl.total_tiles) grid = pl.total_tiles;
-  tc::tapconv_tc_kernel<<<grid, tc::NTHREADS, smem_bytes, st>>>(p, pl, map_x, map_w);
+  tc::tapconv_tc_kernel<<<grid, 64 + 32 * n_ew, smem_bytes, st>>>(p, pl, map_x, map_w);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     set_error("artic_tapconv(tc): launch failed: %s (grid %d, smem %d of %d, bn %d mt %d as %d ws %d packed %d)",

@@ -138,7 +138,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn();           // cuTensorMapEncodeTiled via the runtime's driver entry point (tapconv_tc.cu)
-extern int g_debug[8];               // artic_debug_set knobs
+extern int g_debug[16];              // artic_debug_set knobs
 
 inline CUtensorMapSwizzle swizzle_of(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;

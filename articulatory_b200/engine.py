@@ -106,6 +106,7 @@ def tapconv(launches, X: SeqT, W, G, Cig, Cog, Y: Optional[SeqT] = None, Y2: Opt
 # one conv-like layer                                                         #
 # --------------------------------------------------------------------------- #
 _SIDE_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
+_FORK_DEPTH: Dict[int, int] = {}
 
 
 def fork_join(branches, device=None):
@@ -121,19 +122,61 @@ def fork_join(branches, device=None):
     main = torch.cuda.current_stream()
     dev = main.device_index
     pool = _SIDE_STREAMS.setdefault(dev, [])
-    while len(pool) < len(branches) - 1:
+    base = _FORK_DEPTH.get(dev, 0)                 # nested fork_join calls take fresh side streams
+    while len(pool) < base + len(branches) - 1:
         pool.append(torch.cuda.Stream(device=dev))
-    side = pool[:len(branches) - 1]
-    for st in side:
-        st.wait_stream(main)
-    out = [None] * len(branches)
-    for i in range(1, len(branches)):
-        with torch.cuda.stream(side[i - 1]):
-            out[i] = branches[i]()
-    out[0] = branches[0]()
-    for st in side:
-        main.wait_stream(st)
+    side = pool[base:base + len(branches) - 1]
+    _FORK_DEPTH[dev] = base + len(branches) - 1
+    try:
+        for st in side:
+            st.wait_stream(main)
+        out = [None] * len(branches)
+        for i in range(1, len(branches)):
+            with torch.cuda.stream(side[i - 1]):
+                out[i] = branches[i]()
+        out[0] = branches[0]()
+        for st in side:
+            main.wait_stream(st)
+    finally:
+        _FORK_DEPTH[dev] = base
     return out
+
+
+_QUEUE_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
+_QUEUE_NEXT: Dict[int, int] = {}
+
+
+class SideQueue:
+    """A side stream for work that hangs OFF the critical path of the current stream: the weight
+    gradients of a backward chain only feed the final weight-norm backward, so they are queued here
+    and the data-gradient chain does not wait for them.  Every submission first waits for the work
+    already enqueued on the submitting stream (its inputs); ``join`` makes the current stream wait
+    for the queue.  Tensors handed to queued kernels must stay referenced until ``join`` (``keep``)."""
+
+    def __init__(self):
+        import os
+        self.inline = os.environ.get("ARTIC_STREAMS", "1") == "0"
+        self.keep = []
+        if not self.inline:
+            dev = torch.cuda.current_stream().device_index
+            pool = _QUEUE_STREAMS.setdefault(dev, [torch.cuda.Stream(device=dev) for _ in range(12)])
+            i = _QUEUE_NEXT.get(dev, 0)
+            _QUEUE_NEXT[dev] = (i + 1) % len(pool)
+            self.s = pool[i]
+
+    def run(self, fn, *tensors):
+        if self.inline:
+            return fn()
+        self.keep.extend(tensors)
+        self.s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.s):
+            fn()
+
+    def join(self):
+        if not self.inline:
+            torch.cuda.current_stream().wait_stream(self.s)
+        keep, self.keep = self.keep, []
+        return keep
 
 
 def slice_seq(s: SeqT, lo: int, hi: int) -> SeqT:
@@ -525,19 +568,22 @@ class GeneratorEngine:
                 b = i * self.n_blocks + j
                 gx = g
                 pairs = st["blocks"][j]
+                wq = SideQueue()                 # weight gradients run beside the data-gradient chain
                 for di in range(len(pairs) - 1, -1, -1):
                     ax, at = pairs[di]
                     c2, c1 = L[f"blocks.{b}.convs2.{di}.1"], L[f"blocks.{b}.convs1.{di}.1"]
-                    c2.wgrad(at, gx, grads)
+                    wq.run(lambda c2=c2, at=at, gx=gx: c2.wgrad(at, gx, grads), at, gx)
                     dt = at.like()
                     c2.dgrad(gx, dX=dt, mask=at, mask_slope=slope)
-                    c1.wgrad(ax, dt, grads)
+                    wq.run(lambda c1=c1, ax=ax, dt=dt: c1.wgrad(ax, dt, grads), ax, dt)
                     gn = ax.like()
                     c1.dgrad(dt, dX=gn, mask=ax, mask_slope=slope, res=gx)
                     gx = gn
-                return gx        # gradient wrt the block input (pre-activation u)
+                return gx, wq        # gradient wrt the block input (pre-activation u); queue joined by the caller
 
-            dus = fork_join([lambda j=j: block_bwd(j) for j in range(self.n_blocks)])
+            res_b = fork_join([lambda j=j: block_bwd(j) for j in range(self.n_blocks)])
+            dus = [r[0] for r in res_b]
+            held = [r[1].join() for r in res_b]      # noqa: F841  (tensors of queued wgrads stay alive until joined)
             du = dus[0].like()
             call("artic_sum3", ptr(dus[0].t), ptr(dus[1].t), ptr(dus[2].t), ptr(du.t), du.numel(), code)
             up = L[f"upsamples.{i}.1"]
@@ -779,10 +825,11 @@ class DiscriminatorEngine:
             dz = dl[n - 1]                      # logits gradient (fp32 SeqT)
             assert dz is not None
             d_in = None
+            wq = SideQueue() if grads is not None else None
             for li in range(n - 1, -1, -1):
                 lay = ch.layers[li]
                 if grads is not None:
-                    lay.wgrad(acts[li], dz, grads)
+                    wq.run(lambda lay=lay, a=acts[li], dz=dz: lay.wgrad(a, dz, grads), acts[li], dz)
                 if li > 0:
                     dn = acts[li].like()
                     lay.dgrad(dz, dX=dn, res_pre=dl[li - 1], mask=acts[li], mask_slope=slope)
@@ -797,9 +844,11 @@ class DiscriminatorEngine:
                         dxp = torch.empty((B, Tp), dtype=torch.float32, device=dev)
                         d_in = SeqT(dxp, h.N, h.L, 1, n_inner=h.n_inner, s_outer=Tp, s_inner=1, s_row=h.s_row)
                         lay.dgrad(dz, dX=d_in)
-            return d_in
+            return d_in, wq
 
-        d_ins = fork_join([lambda ci=ci: chain_bwd(ci) for ci in range(len(self.chains))])
+        res_c = fork_join([lambda ci=ci: chain_bwd(ci) for ci in range(len(self.chains))])
+        d_ins = [r[0] for r in res_c]
+        held = [r[1].join() for r in res_c if r[1] is not None]      # noqa: F841
         if need_dx:     # the chains' input gradients meet in dx on the main stream
             for ch, d_in in zip(self.chains, d_ins):
                 if ch.kind == "scale":

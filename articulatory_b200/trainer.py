@@ -113,24 +113,53 @@ class TrainStep:
         engG = G._ensure_ready()
         B, _, T = y.shape
         inv_w = 1.0 / self.world
-        y_, tapeG = engG.forward(x, ar, save=True)
+        # the discriminator's weights (updated at the end of the previous step) are re-materialised on a
+        # side stream while the generator forward runs
+        (y_, tapeG), engD = fork_join([lambda: engG.forward(x, ar, save=True),
+                                       lambda: D._ensure_ready() if train_d_active else None])
         y2d, t2d = y_.reshape(B, T), y.reshape(B, T)
         dy = torch.zeros((B, 1, T), dtype=torch.float32, device=self.dev)
         self.slots.zero_()
         self.stft_sums.zero_()
-        if self.use_stft:                                                     # bin/train.py:289-297
-            for r, res in enumerate(self.stft.resolutions):
-                res.forward(y2d, t2d, self.stft_sums[r])
-            for r, res in enumerate(self.stft.resolutions):
-                res.backward(y2d, t2d, self.stft_sums[r], self.l_aux * inv_w / self.R, self.l_aux * inv_w / self.R, dy)
-        if self.use_mel:                                                      # :313-316
-            n = self.mel.numel(B, T)
-            self.mel.accumulate(y2d, t2d, 1.0 / n, self.slots[_MEL:])
-            self.mel.backward_into(y2d, t2d, self.l_aux * inv_w / n, dy)
+
+        def spectral():
+            # the STFT resolutions and the mel loss are independent of each other (dy is accumulated atomically)
+            jobs = []
+            if self.use_stft:                                                 # bin/train.py:289-297
+                for r, res in enumerate(self.stft.resolutions):
+                    def job(r=r, res=res):
+                        res.forward(y2d, t2d, self.stft_sums[r])
+                        res.backward(y2d, t2d, self.stft_sums[r], self.l_aux * inv_w / self.R,
+                                     self.l_aux * inv_w / self.R, dy)
+                    jobs.append(job)
+            if self.use_mel:                                                  # :313-316
+                def mel_job():
+                    n = self.mel.numel(B, T)
+                    self.mel.accumulate(y2d, t2d, 1.0 / n, self.slots[_MEL:])
+                    self.mel.backward_into(y2d, t2d, self.l_aux * inv_w / n, dy)
+                jobs.append(mel_job)
+            if jobs:
+                fork_join(jobs)
+
         tape2 = None
-        if train_d_active:                                                    # :350-364
-            engD = D._ensure_ready()
+        if not train_d_active:
+            spectral()
+        else:                                                                 # :350-364
+            return self._phase_g_adv(x, y, ar, y_, tapeG, engG, engD, dy, spectral)
+        self.optG.zero_grad()
+        engG.backward(tapeG, dy, self.optG.grad_views)
+        return tape2
+
+    def _phase_g_adv(self, x, y, ar, y_, tapeG, engG, engD, dy, spectral):
+        """Adversarial + feature-matching part of the generator phase; runs concurrently with the
+        spectral losses (both only read y_; they meet in dy)."""
+        B, _, T = y.shape
+        inv_w = 1.0 / self.world
+        state = {}
+
+        def adversarial():
             outs2, tape2 = engD.forward(self._disc_input(ar, (y_, y)), save=True)
+            state["tape2"] = tape2
             outs_f = [[slice_seq(o, 0, B) for o in lst] for lst in outs2]
             outs_r = [[slice_seq(o, B, 2 * B) for o in lst] for lst in outs2]
             lg_grads = [lst[-1].like() for lst in outs_f]
@@ -154,9 +183,12 @@ class TrainStep:
                 return dl
 
             douts = fork_join([lambda ci=ci: seed_chain(ci) for ci in range(len(outs_f))])
-            d_in = engD.backward(engD.slice_tape(tape2, 0, B), douts, grads=None, need_dx=True)    # dgrad only
-            La = self.ar_len
-            call("artic_add_rows", ptr(d_in) + 4 * La, La + T, ptr(dy), T, B, T)
+            state["d_in"] = engD.backward(engD.slice_tape(tape2, 0, B), douts, grads=None, need_dx=True)    # dgrad only
+
+        fork_join([adversarial, spectral])
+        La = self.ar_len
+        call("artic_add_rows", ptr(state["d_in"]) + 4 * La, La + T, ptr(dy), T, B, T)
+        tape2 = state["tape2"]
         self.optG.zero_grad()
         engG.backward(tapeG, dy, self.optG.grad_views)
         return tape2
