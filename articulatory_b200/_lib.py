@@ -81,6 +81,7 @@ SIGNATURES = {
     "artic_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "artic_debug_buffer": (C.c_int, [_p]),
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
+    "artic_tapconv_multi": (C.c_int, [C.POINTER(TapConv), _i32, _p]),
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
     "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),
     "artic_wperm_tiles": (C.c_int64, [_i32, _i32, _i32, _i32]),

@@ -453,13 +453,13 @@ static int check_seq(const artic_seq_t& s) { return s.n_inner >= 1 && s.len >= 0
 
 // implemented in tapconv_tc.cu: returns 1 if it took the launch, 0 if the shape is not
 // eligible (fall through to the generic kernel), <0 on error.
-int artic_tapconv_tc_try(const artic_tapconv_t* p, cudaStream_t st);
+int artic_tapconv_tc_multi(const artic_tapconv_t* ps, int n, int* taken, cudaStream_t st);   // tapconv_tc.cu
 int artic_tapwgrad_tc_try(const artic_tapwgrad_t* p, cudaStream_t st);  // tapwgrad_tc.cu, same convention
 int artic_tapconv_co1_try(const artic_tapconv_t* p, cudaStream_t st);    // smallc.cu
 int artic_tapconv_ci1_try(const artic_tapconv_t* p, cudaStream_t st);    // smallc.cu
 int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* p, cudaStream_t st);  // smallc.cu
 
-extern "C" int artic_tapconv(const artic_tapconv_t* p, void* stream) {
+static int check_tapconv(const artic_tapconv_t* p) {
   ARTIC_CHECK_ARG(p != nullptr, "null params");
   ARTIC_CHECK_ARG(p->X && p->W && (p->Y || p->Y2), "X, W and one of Y/Y2 are required");
   ARTIC_CHECK_ARG(check_seq(p->x) && check_seq(p->y), "bad sequence descriptor");
@@ -468,26 +468,54 @@ extern "C" int artic_tapconv(const artic_tapconv_t* p, void* stream) {
   ARTIC_CHECK_ARG(p->si >= 1 && p->so >= 1 && p->nq >= 0, "bad q mapping");
   ARTIC_CHECK_ARG(p->dtype == ARTIC_F32 || p->dtype == ARTIC_BF16, "bad dtype");
   ARTIC_CHECK_ARG(p->out_dtype == ARTIC_F32 || p->out_dtype == ARTIC_BF16, "bad out_dtype");
+  return ARTIC_OK;
+}
+
+// one problem on the CUDA-core kernels (channel-1 special cases first)
+static int tapconv_fallback(const artic_tapconv_t* p, cudaStream_t st) {
   if (p->N == 0 || p->nq == 0) return ARTIC_OK;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int rc;
-  const bool ob = p->out_dtype == ARTIC_BF16;
   if (artic_tapconv_co1_try(p, st) == 1 || artic_tapconv_ci1_try(p, st) == 1) {
     ARTIC_LAUNCH_CHECK();
     return ARTIC_OK;
   }
-  if (p->dtype == ARTIC_BF16) {
-    rc = ob ? artic_tapconv_tc_try(p, st) : 0;
-    if (rc < 0) return rc;
-    if (rc == 0) rc = ob ? launch_tapconv<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapconv<__nv_bfloat16, float>(*p, st);
-    else rc = ARTIC_OK;
-  } else {
-    rc = ob ? launch_tapconv<float, __nv_bfloat16>(*p, st) : launch_tapconv<float, float>(*p, st);
-  }
+  const bool ob = p->out_dtype == ARTIC_BF16;
+  int rc;
+  if (p->dtype == ARTIC_BF16) rc = ob ? launch_tapconv<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapconv<__nv_bfloat16, float>(*p, st);
+  else rc = ob ? launch_tapconv<float, __nv_bfloat16>(*p, st) : launch_tapconv<float, float>(*p, st);
   if (rc != ARTIC_OK) return rc;
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
 }
+
+extern "C" int artic_tapconv_multi(const artic_tapconv_t* ps, int32_t n, void* stream) {
+  ARTIC_CHECK_ARG(ps != nullptr && n >= 0 && n <= 64, "bad problem list");
+  for (int i = 0; i < n; ++i) {
+    const int rc = check_tapconv(&ps[i]);
+    if (rc != ARTIC_OK) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int taken[64];
+  bool cand[64];
+  artic_tapconv_t tcp[64];
+  int map[64], m = 0;
+  for (int i = 0; i < n; ++i) {     // channel-1 problems never go to the tensor cores
+    cand[i] = !(ps[i].Cog == 1 && ps[i].G == 1 && ps[i].Cig >= 32) && ps[i].Cig != 1;
+    if (cand[i]) { tcp[m] = ps[i]; map[m++] = i; }
+  }
+  int tk[64];
+  int rc = artic_tapconv_tc_multi(tcp, m, tk, st);
+  if (rc != ARTIC_OK) return rc;
+  for (int i = 0; i < n; ++i) taken[i] = 0;
+  for (int k = 0; k < m; ++k) taken[map[k]] = tk[k];
+  for (int i = 0; i < n; ++i) {
+    if (taken[i]) continue;
+    rc = tapconv_fallback(&ps[i], st);
+    if (rc != ARTIC_OK) return rc;
+  }
+  return ARTIC_OK;
+}
+
+extern "C" int artic_tapconv(const artic_tapconv_t* p, void* stream) { return artic_tapconv_multi(p, 1, stream); }
 
 extern "C" int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream) {
   ARTIC_CHECK_ARG(p != nullptr, "null params");

@@ -56,6 +56,23 @@ struct Plan {
   long long* dbg;                 // debug timeline buffer (artic_debug_buffer) or nullptr
 };
 
+// Several independent problems (the phases of a strided data gradient / transposed conv, the three MRF
+// blocks of a generator stage, the sub-discriminators at one depth) share ONE launch: the grid is the
+// concatenation of per-problem persistent CTA ranges, each CTA works on its own problem only.
+struct Prob {
+  artic_tapconv_t p;
+  Plan pl;
+  CUtensorMap map_x, map_w;
+};
+constexpr int MAXP = 8;
+struct Multi {
+  int32_t n;
+  int32_t cta_begin[MAXP + 1];
+  Prob prob[MAXP];
+};
+
+static_assert(sizeof(Multi) <= 32000, "kernel parameter space");
+
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset,
 // [61,64) swizzle code.  Rows are `row_bytes` apart, 8-row groups SBO = 8*row_bytes apart.
@@ -82,8 +99,15 @@ __device__ __forceinline__ void dbg_mark(long long* dbg, int tag) {
 // kernel
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
-tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_constant__ Plan pl,
-                  const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w) {
+tapconv_tc_kernel(const __grid_constant__ Multi mp) {
+  int prob_j = 0;
+  while (prob_j + 1 < mp.n && (int)blockIdx.x >= mp.cta_begin[prob_j + 1]) ++prob_j;
+  const artic_tapconv_t& p = mp.prob[prob_j].p;
+  const Plan& pl = mp.prob[prob_j].pl;
+  const CUtensorMap& map_x = mp.prob[prob_j].map_x;
+  const CUtensorMap& map_w = mp.prob[prob_j].map_w;
+  const int cta = (int)blockIdx.x - mp.cta_begin[prob_j];                 // this CTA's index / count inside its problem
+  const int ncta = mp.cta_begin[prob_j + 1] - mp.cta_begin[prob_j];
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_AS], a_empty[MAX_AS], w_full[MAX_WS], w_empty[MAX_WS];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], w_res_full;
@@ -144,7 +168,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
             tma_load_2d(w_base + (uint32_t)(kc * ntaps + t) * pl.w_tile_bytes, &map_w, &w_res_full, kc * pl.kch,
                         p.widx[t] * p.Cog);
       }
-      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
         const int nt = tile % pl.n_nt;
         const int r = tile / pl.n_nt;
         const int mtile = r % pl.n_mt;
@@ -214,7 +238,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
       const uint32_t bn = (uint32_t)pl.bn;
       const uint32_t w_base16 = w_base >> 4, wt16 = (uint32_t)pl.w_tile_bytes >> 4, ws16 = (uint32_t)pl.w_stage_bytes >> 4;
       if (pl.w_resident) mbar_wait(&w_res_full, 0);
-      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
         mbar_wait(&acc_empty[acc.stage], acc.phase ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)acc.stage * acc_cols;
@@ -307,7 +331,7 @@ tapconv_tc_kernel(const __grid_constant__ artic_tapconv_t p, const __grid_consta
     float4* stage = reinterpret_cast<float4*>(epi + ewarp * EPI_WARP_BYTES);                  // [32 rows][8 units]
     long long* rowoff = reinterpret_cast<long long*>(epi + ewarp * EPI_WARP_BYTES + 32 * 8 * 16);   // [sub-tile][32 rows]
     const int g8 = lane & 3, rsub = lane >> 2;
-    for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
       const int nt = tile % pl.n_nt;
       const int r = tile / pl.n_nt;
       const int mtile = r % pl.n_mt;
@@ -501,8 +525,9 @@ extern "C" int artic_debug_set(int key, int value) {
   return ARTIC_OK;
 }
 
-// returns 1 if the launch was taken, 0 if the shape is not eligible, <0 on error.
-int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
+// Plans one problem for the tensor-core kernel: returns 1 (pr filled: parameters, plan, tensor maps,
+// pr_smem / pr_cost set), 0 if the shape is not eligible, <0 on error.
+static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem, double& pr_cost) {
   const artic_tapconv_t& p = *pp;
   if (tc::g_debug[1]) return 0;                       // debug: force the generic kernel
   if (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16) return 0;
@@ -658,11 +683,13 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
     }
   }
   if (best < 0) return 0;
+  pr_cost = best;
   pl.dbg = tc::g_dbg_buf;
   for (int t = 0; t < p.ntaps; ++t) pl.a_off16[t] = (pl.phase[t] * pl.panel_bytes + pl.shift[t] * pl.row_bytes) >> 4;
 
   // ---- tensor maps
-  CUtensorMap map_x, map_w;
+  CUtensorMap& map_x = pr.map_x;
+  CUtensorMap& map_w = pr.map_w;
   {
     const int ni = p.x.n_inner;
     cuuint64_t dims[4] = {(cuuint64_t)p.G * p.Cig, (cuuint64_t)ni, (cuuint64_t)p.x.len, (cuuint64_t)((p.N + ni - 1) / ni)};
@@ -690,15 +717,67 @@ int artic_tapconv_tc_try(const artic_tapconv_t* pp, cudaStream_t st) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("artic_tapconv: cuTensorMapEncodeTiled(W) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   }
-  const int smem_bytes = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? pl.n_kc * p.ntaps * pl.w_tile_bytes : pl.n_ws * pl.w_stage_bytes) + 1024 + epi_bytes;
-  int grid = num_sms();
-  if (grid > pl.total_tiles) grid = pl.total_tiles;
-  tc::tapconv_tc_kernel<<<grid, 64 + 32 * n_ew, smem_bytes, st>>>(p, pl, map_x, map_w);
+  pr_smem = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? pl.n_kc * p.ntaps * pl.w_tile_bytes : pl.n_ws * pl.w_stage_bytes) + 1024 + epi_bytes;
+  pr.p = p;
+  pr.pl = pl;
+  return 1;
+}
+
+// Launches up to MAXP planned problems as ONE grid of per-problem persistent CTA ranges.
+static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, cudaStream_t st) {
+  const int n = mp.n;
+  const int n_ew = (tc::g_debug[8] > 0 && tc::g_debug[8] * 1024 < tc::max_smem()) ? 4 : 8;
+  int64_t tiles = 0;
+  double work = 0.0;
+  for (int j = 0; j < n; ++j) { tiles += mp.prob[j].pl.total_tiles; work += cost[j]; }
+  int smem_bytes = 0;
+  mp.cta_begin[0] = 0;
+  for (int j = 0; j < n; ++j) {
+    const int t = mp.prob[j].pl.total_tiles;
+    int c = t;
+    if (tiles > num_sms()) {   // share the SMs in proportion to the planner's time estimate of each problem
+      c = (int)(num_sms() * (cost[j] / work) + 0.5);
+      if (c < 1) c = 1;
+      if (c > t) c = t;
+    }
+    mp.cta_begin[j + 1] = mp.cta_begin[j] + c;
+    if (smem[j] > smem_bytes) smem_bytes = smem[j];
+  }
+  const int grid = mp.cta_begin[n];
+  tc::tapconv_tc_kernel<<<grid, 64 + 32 * n_ew, smem_bytes, st>>>(mp);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
-    set_error("artic_tapconv(tc): launch failed: %s (grid %d, smem %d of %d, bn %d mt %d as %d ws %d packed %d)",
-              cudaGetErrorString(le), grid, smem_bytes, tc::max_smem(), pl.bn, pl.mt, pl.n_as, pl.n_ws, pl.packed);
+    const tc::Plan& pl = mp.prob[0].pl;
+    set_error("artic_tapconv(tc): launch failed: %s (%d problems, grid %d, smem %d of %d, bn %d mt %d as %d ws %d packed %d)",
+              cudaGetErrorString(le), n, grid, smem_bytes, tc::max_smem(), pl.bn, pl.mt, pl.n_as, pl.n_ws, pl.packed);
     return ARTIC_ECUDA;
   }
-  return 1;
+  return ARTIC_OK;
+}
+
+// Multi-problem front end used by artic_tapconv / artic_tapconv_multi (tapconv.cu): tries to plan every problem
+// for the tensor-core kernel; taken[i] = 1 for those launched here (in groups of <= MAXP), 0 for the rest.
+int artic_tapconv_tc_multi(const artic_tapconv_t* ps, int n, int* taken, cudaStream_t st) {
+  static thread_local tc::Multi mp;       // ~13 KB: keep it off the stack
+  int smem[tc::MAXP];
+  double cost[tc::MAXP];
+  mp.n = 0;
+  for (int i = 0; i < n; ++i) {
+    taken[i] = 0;
+    if (ps[i].N == 0 || ps[i].nq == 0) continue;
+    const int rc = tc_plan_problem(&ps[i], mp.prob[mp.n], smem[mp.n], cost[mp.n]);
+    if (rc < 0) return rc;
+    if (rc == 0) continue;
+    taken[i] = 1;
+    if (++mp.n == tc::MAXP) {
+      const int lrc = tc_launch_group(mp, smem, cost, st);
+      if (lrc != ARTIC_OK) return lrc;
+      mp.n = 0;
+    }
+  }
+  if (mp.n > 0) {
+    const int lrc = tc_launch_group(mp, smem, cost, st);
+    if (lrc != ARTIC_OK) return lrc;
+  }
+  return ARTIC_OK;
 }

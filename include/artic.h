@@ -97,6 +97,11 @@ typedef struct {
 } artic_tapconv_t;
 
 int artic_tapconv(const artic_tapconv_t* p, void* stream);
+/* n (<= 64) INDEPENDENT problems (no output of one is an input of another) in as few launches as possible:
+ * tensor-core eligible problems share grids of per-problem persistent CTA ranges (the phases of a strided
+ * data gradient or transposed conv, the three MRF blocks of a generator stage, the sub-discriminators at
+ * one depth), the others run one by one. */
+int artic_tapconv_multi(const artic_tapconv_t* ps, int32_t n, void* stream);
 
 /*
  * Weight gradient of the same contraction (cuDNN wgrad):
