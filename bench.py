@@ -53,6 +53,16 @@ def train_config():
         generator_grad_norm=-1, discriminator_grad_norm=-1)
 
 
+def measured_traffic():
+    """DRAM bytes per step of the tcgen05 kernels (ncu dram__bytes_{read,write}.sum over one step,
+    profiles/r1_traffic.json written by tools/traffic_summary.py); None when not captured."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(path))["tensor_core_kernels"]["dram_bytes_per_step"]
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -231,8 +241,11 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "audio-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 36},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None,
-                     "note": f"algorithmic 194.70 GFLOP/window x {B} windows / step time, per GPU; peak = {peak_src}"},
+                     "frac": achieved_tf / peak_tf, "traffic": measured_traffic(),
+                     "kernel": "tc::tapconv_tc_kernel + tc::tapwgrad_tc_kernel (tcgen05 implicit-GEMM conv, data and weight gradients)",
+                     "note": f"algorithmic 194.70 GFLOP/window (SURVEY 8d: 4 F_G + 8 F_D) x {B} windows / step time, per GPU, "
+                             f"timed with CUDA events over the whole step; peak = {peak_src}; traffic = DRAM bytes per step of the "
+                             "tensor-core kernels (ncu, profiles/r1_traffic.json)"},
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

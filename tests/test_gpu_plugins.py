@@ -180,3 +180,44 @@ def test_load_model_and_train_cli(golden, tmp_path):
     model.remove_weight_norm()
     y = model.eval().to(DEV)(golden["batch"]["x"].to(DEV), ar=golden["batch"]["ar"].to(DEV))
     assert y.shape == (2, 1, 2000) and torch.isfinite(y).all()
+
+
+def test_inference_and_register_stats(golden, tmp_path):
+    """HiFiGANGenerator.inference / register_stats (reference models/hifigan.py:280-314) on a non-AR model:
+    (T', C) features, normalised with the registered stats, -> (T, 1) waveform."""
+    import numpy as np
+    from articulatory_b200 import models as M
+    from oracle import torch_oracle as O
+    gp = dict(golden["generator_params"], use_ar=False, in_channels=13)
+    torch.manual_seed(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = M.HiFiGANGenerator(**gp)
+    gsd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    rng = np.random.RandomState(0)
+    stats = np.stack([rng.randn(13), rng.rand(13) + 0.5]).astype(np.float32)
+    np.save(tmp_path / "stats.npy", stats)
+    G.register_stats(str(tmp_path / "stats.npy"))
+    G = G.to(DEV).eval()
+    c = torch.randn(37, 13)
+    y = G.inference(c.to(DEV), normalize_before=True)
+    assert y.shape == (37 * 80, 1)
+    cn = (c - torch.from_numpy(stats[0])) / torch.from_numpy(stats[1])
+    ref = O.generator_forward(gsd, gp, cn.T[None])
+    assert rel_err(y.cpu().T[None], ref) < 1e-4
+    # numpy input path (reference accepts ndarray)
+    y2 = G.inference(c.numpy(), normalize_before=True)
+    assert torch.equal(y2, y)
+    with pytest.raises(ValueError):
+        _car_model(golden).to(DEV)(golden["batch"]["x"].to(DEV))      # use_ar model without `ar`
+
+
+def test_off_path_options_fail_loudly():
+    from articulatory_b200 import losses as L
+    from articulatory_b200 import models as M
+    with pytest.raises(NotImplementedError):
+        L.GeneratorAdversarialLoss(loss_type="hinge")
+    with pytest.raises(NotImplementedError):
+        M.HiFiGANGenerator(use_spk_id=True, num_spk=4)
+    with pytest.raises(NotImplementedError):
+        M.HiFiGANPeriodDiscriminator(use_weight_norm=False, use_spectral_norm=True)

@@ -11,6 +11,8 @@ def main(path, top=30):
         lines = [l for l in f if not l.startswith("==")]
     tot, cnt = collections.Counter(), collections.Counter()
     for row in csv.DictReader(lines):
+        if not row["Metric Name"].startswith("gpu__time_duration"):
+            continue
         v = float(row["Metric Value"].replace(",", ""))
         unit = row["Metric Unit"]
         v = v / 1e3 if unit in ("ns", "nsecond") else v * 1e3 if unit in ("ms", "msecond") else v
