@@ -54,6 +54,7 @@ struct Plan {
   int32_t a_off16[ARTIC_MAX_TAPS];  // (phase * panel_bytes + shift * row_bytes) / 16 : descriptor offset of the tap
   int32_t layout_type;            // UMMA smem descriptor swizzle code
   long long* dbg;                 // debug timeline buffer (artic_debug_buffer) or nullptr
+  int32_t dbg_flags;              // debug: 1 = skip epilogue stores, 2 = skip operand use
 };
 
 // Several independent problems (the phases of a strided data gradient / transposed conv, the three MRF
@@ -87,11 +88,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
   return d;
 }
 
-// Debug timeline: CTA 0 appends (tag, clock64) pairs; slot 0 is the write cursor.
+// Debug timeline (artic_debug_buffer): CTA 0 records clock64 of the FIRST occurrence of each tag in a
+// shared-memory slot (no atomics, ~20 clocks) and of the LAST occurrence in a second slot; dumped at exit.
+__shared__ long long g_ev_first[40], g_ev_last[40];
 __device__ __forceinline__ void dbg_mark(long long* dbg, int tag) {
   if (dbg != nullptr && blockIdx.x == 0) {
-    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(dbg), 1ULL);
-    if (i < 2000) { dbg[1 + 2 * i] = tag; dbg[2 + 2 * i] = clock64(); }
+    const long long t = clock64();
+    if (g_ev_first[tag] == 0) g_ev_first[tag] = t;
+    g_ev_last[tag] = t;
   }
 }
 
@@ -121,14 +125,17 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
   const uint32_t w_base = smem0 + (uint32_t)pl.n_as * pl.a_stage_bytes;
   const uint32_t epi_base = w_base + (pl.w_resident ? (uint32_t)(pl.n_kc * p.ntaps) * pl.w_tile_bytes : (uint32_t)pl.n_ws * pl.w_stage_bytes);   // 4 x 8 KB transpose stages + row offsets
 
-  if (threadIdx.x == 0) dbg_mark(pl.dbg, 1);
+  const long long t_start = clock64();
   // Setup rendezvous on named barrier 1: the producer warp initialises the mbarriers, ARRIVES and goes
   // straight to its first TMA loads; the other warps (TMEM allocation in warp 1) SYNC on it.
   uint32_t tmem_base = 0;
   if (warp == 0) {
     if (pl.dbg != nullptr) {
+      g_ev_first[lane] = g_ev_last[lane] = 0;
+      if (lane < 8) g_ev_first[32 + lane] = g_ev_last[32 + lane] = 0;
       tr_issue[lane] = tr_issue[lane + 32] = tr_seen[lane] = tr_seen[lane + 32] = tr_done[lane] = tr_done[lane + 32] = 0;
     }
+    if (lane == 0 && pl.dbg != nullptr && blockIdx.x == 0) g_ev_first[1] = g_ev_last[1] = t_start;
     if (lane == 0) {
       prefetch_tmap(&map_x);
       prefetch_tmap(&map_w);
@@ -331,6 +338,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     float4* stage = reinterpret_cast<float4*>(epi + ewarp * EPI_WARP_BYTES);                  // [32 rows][8 units]
     long long* rowoff = reinterpret_cast<long long*>(epi + ewarp * EPI_WARP_BYTES + 32 * 8 * 16);   // [sub-tile][32 rows]
     const int g8 = lane & 3, rsub = lane >> 2;
+    const float neg_slope = p.act == ARTIC_ACT_LRELU ? p.act_slope : 1.f;
     for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
       const int nt = tile % pl.n_nt;
       const int r = tile / pl.n_nt;
@@ -381,6 +389,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) bv[i] = p.bias != nullptr ? __ldg(p.bias + cbase + c0 + g8 * 8 + i) : 0.f;
+          if (threadIdx.x == 64) dbg_mark(pl.dbg, 32);
           if (!waited) {
             mbar_wait(&acc_full[acc.stage], acc.phase);
             if (threadIdx.x == 64) dbg_mark(pl.dbg, 30);
@@ -392,6 +401,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
             uint32_t acc_r[32];
             tmem_ld32(t_row + c0, acc_r);
             tmem_ld_wait();
+            if (threadIdx.x == 64) dbg_mark(pl.dbg, 33);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
               stage[lane * 8 + (u ^ (lane & 7))] =
@@ -399,6 +409,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
                               __uint_as_float(acc_r[4 * u + 2]), __uint_as_float(acc_r[4 * u + 3]));
           }
           __syncwarp();
+          if (threadIdx.x == 64) dbg_mark(pl.dbg, 34);
           // ---- (3) transposed pass (lanes along channels)
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
@@ -430,17 +441,16 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += tmp[i];
             }
-            if (Y) *reinterpret_cast<uint4*>(Y + oo[it]) = pack8(v);
-            if (Y2) {
+            if (Y && !(pl.dbg_flags & 1)) *reinterpret_cast<uint4*>(Y + oo[it]) = pack8(v);
+            if (Y2) {   // second output: LeakyReLU (or identity: neg_slope = 1); tanh layers never reach this kernel
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (p.act == ARTIC_ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : p.act_slope * v[i];
-                else if (p.act == ARTIC_ACT_TANH) v[i] = tanhf(v[i]);
-              }
-              *reinterpret_cast<uint4*>(Y2 + oo[it]) = pack8(v);
+              for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : neg_slope * v[i];
+              if (!(pl.dbg_flags & 1)) *reinterpret_cast<uint4*>(Y2 + oo[it]) = pack8(v);
+              else if (v[0] == 12345.678f) Y2[0] = __float2bfloat16(v[1]);
             }
           }
           __syncwarp();
+          if (threadIdx.x == 64) dbg_mark(pl.dbg, 35);
         }
       }
       if (!waited) {   // bn == 32: the odd-chunk warps have no channels, but still own a share of the barrier
@@ -456,6 +466,11 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
 
   tc_fence_before();
   __syncthreads();
+  if (pl.dbg != nullptr && blockIdx.x == 0 && threadIdx.x < 40) {
+    pl.dbg[1 + 2 * threadIdx.x] = g_ev_first[threadIdx.x];
+    pl.dbg[2 + 2 * threadIdx.x] = g_ev_last[threadIdx.x];
+    if (threadIdx.x == 0) { pl.dbg[0] = 40; pl.dbg[90] = clock64(); }
+  }
   if (pl.dbg != nullptr && blockIdx.x == 0 && threadIdx.x < 64) {   // debug trace: slots [3000 + 3*i ..]
     pl.dbg[3000 + 3 * threadIdx.x] = tr_issue[threadIdx.x];
     pl.dbg[3001 + 3 * threadIdx.x] = tr_seen[threadIdx.x];
@@ -530,7 +545,7 @@ extern "C" int artic_debug_set(int key, int value) {
 static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem, double& pr_cost) {
   const artic_tapconv_t& p = *pp;
   if (tc::g_debug[1]) return 0;                       // debug: force the generic kernel
-  if (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16) return 0;
+  if (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16 || p.act == ARTIC_ACT_TANH) return 0;
   if (p.si < 1 || p.si > 8) return 0;
   if (p.Cig % 16 != 0 || p.Cog % 32 != 0) return 0;
   if ((p.x.s_row % 8) || (p.x.s_outer % 8) || (p.x.n_inner > 1 && (p.x.s_inner % 8))) return 0;
@@ -685,6 +700,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
   if (best < 0) return 0;
   pr_cost = best;
   pl.dbg = tc::g_dbg_buf;
+  pl.dbg_flags = tc::g_debug[9];
   for (int t = 0; t < p.ntaps; ++t) pl.a_off16[t] = (pl.phase[t] * pl.panel_bytes + pl.shift[t] * pl.row_bytes) >> 4;
 
   // ---- tensor maps

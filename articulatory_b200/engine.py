@@ -206,6 +206,16 @@ def slice_seq(s: SeqT, lo: int, hi: int) -> SeqT:
     return SeqT(s.t[lo:hi], (hi - lo) * s.n_inner, s.L, s.C, s.n_inner, s.s_outer, s.s_inner, s.s_row)
 
 
+def flat_period(s: SeqT) -> SeqT:
+    """(B, H, p, C) period storage seen as B plain sequences of H*p rows (zero-copy).  A stride-1
+    Conv2d (k,1) over (H, p) is exactly a Conv1d over that flattened length with dilation p and padding
+    pad*p: one dense tile per batch item instead of p short interleaved sequences."""
+    if s.n_inner == 1:
+        return s
+    B = s.N // s.n_inner
+    return SeqT(s.t, B, s.L * s.n_inner, s.C, n_inner=1, s_outer=s.s_outer, s_inner=0, s_row=s.s_inner)
+
+
 class ConvLayer:
     """A conv / convT / linear layer bound to its torch parameters.
 
@@ -279,16 +289,16 @@ class ConvLayer:
         self._single().unprep(grads)
 
     # ---- compute -------------------------------------------------------------
-    def forward_params(self, X: SeqT, Y=None, Y2=None, **epi):
-        s = self.spec
+    def forward_params(self, X: SeqT, Y=None, Y2=None, spec=None, **epi):
+        s = spec or self.spec
         return tapconv_params(s.fwd_launches(X.L), X, self.Wf, self.kG, self.kcig, self.kcog, Y=Y, Y2=Y2, bias=self.b,
                               Wt=self.Wb, **epi)
 
     def forward(self, X: SeqT, Y=None, Y2=None, **epi):
         launch_tapconvs(self.forward_params(X, Y=Y, Y2=Y2, **epi))
 
-    def dgrad_params(self, dY: SeqT, dX: Optional[SeqT] = None, dX2: Optional[SeqT] = None, **epi):
-        s = self.spec
+    def dgrad_params(self, dY: SeqT, dX: Optional[SeqT] = None, dX2: Optional[SeqT] = None, spec=None, **epi):
+        s = spec or self.spec
         lin = (dX if dX is not None else dX2).L
         return tapconv_params(s.dgrad_launches(lin), dY, self.Wb, self.kG, self.kcog, self.kcig, Y=dX, Y2=dX2,
                               Wt=self.Wf, **epi)
@@ -296,9 +306,9 @@ class ConvLayer:
     def dgrad(self, dY: SeqT, dX: Optional[SeqT] = None, dX2: Optional[SeqT] = None, **epi):
         launch_tapconvs(self.dgrad_params(dY, dX=dX, dX2=dX2, **epi))
 
-    def wgrad(self, X: SeqT, dY: SeqT, grads: Dict[str, torch.Tensor]):
+    def wgrad(self, X: SeqT, dY: SeqT, grads: Dict[str, torch.Tensor], spec=None):
         """Accumulate dW (prepared layout) and the bias gradient (into grads[name.bias])."""
-        s = self.spec
+        s = spec or self.spec
         p = _lib.TapWgrad()
         if self.dw_swapped:
             # dW^T[j][co][ci] = sum_q dY[q*s + j - pad][co] * X[q][ci]
@@ -769,6 +779,7 @@ class DiscriminatorEngine:
                 layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code))
             self.chains.append(_Chain(layers, "period", period=period))
         self.layers = {l.name: l for ch in self.chains for l in ch.layers}
+        self._flat_specs = {}
         self._prepped = False
 
     def bind(self, params):
@@ -793,6 +804,20 @@ class DiscriminatorEngine:
 
     def new_grads(self):
         return _zero_grads_like(list(self.layers.values()))
+
+    def _flat_spec(self, ch, lay):
+        """Dilated-conv restatement of a stride-1 period layer (see flat_period), or None."""
+        s = lay.spec
+        if ch.kind != "period" or s.stride != 1 or s.k == 1 or s.kind != "conv" or s.cin < 32 or s.cout < 32 \
+                or _os.environ.get("ARTIC_FLAT_PERIOD", "1") == "0":
+            return None
+        key = (lay.name, ch.period)
+        fs = self._flat_specs.get(key)
+        if fs is None:
+            from .convspec import ConvSpec as CS
+            fs = CS("conv", s.cin, s.cout, k=s.k, dilation=ch.period, padding=s.padding * ch.period, groups=s.groups)
+            self._flat_specs[key] = fs
+        return fs
 
     # ---- forward -------------------------------------------------------------
     def forward(self, x: torch.Tensor, save=True, into=None, lo=0):
@@ -861,8 +886,11 @@ class DiscriminatorEngine:
                     o = take(into["chains"][ci][li + 1])
                 else:
                     o = h.like(code=F32 if last else self.code, C=lay.spec.cout, L=lo_)
+                fs = self._flat_spec(ch, lay)
                 if last:
                     lay.forward(h, Y=o)
+                elif fs is not None:
+                    launch_tapconvs(lay.forward_params(flat_period(h), Y2=flat_period(o), act=ACT_LRELU, act_slope=slope, spec=fs))
                 else:
                     lay.forward(h, Y2=o, act=ACT_LRELU, act_slope=slope)
                 acts.append(o)
@@ -910,11 +938,21 @@ class DiscriminatorEngine:
             wq = SideQueue() if grads is not None else None
             for li in range(n - 1, -1, -1):
                 lay = ch.layers[li]
+                fs = self._flat_spec(ch, lay) if li < n - 1 else None
                 if grads is not None:
-                    wq.run(lambda lay=lay, a=acts[li], dz=dz: lay.wgrad(a, dz, grads), acts[li], dz)
+                    if fs is not None:
+                        wq.run(lambda lay=lay, a=acts[li], dz=dz, fs=fs: lay.wgrad(flat_period(a), flat_period(dz), grads, spec=fs),
+                               acts[li], dz)
+                    else:
+                        wq.run(lambda lay=lay, a=acts[li], dz=dz: lay.wgrad(a, dz, grads), acts[li], dz)
                 if li > 0:
                     dn = acts[li].like()
-                    lay.dgrad(dz, dX=dn, res_pre=dl[li - 1], mask=acts[li], mask_slope=slope)
+                    if fs is not None:
+                        rp = flat_period(dl[li - 1]) if dl[li - 1] is not None else None
+                        launch_tapconvs(lay.dgrad_params(flat_period(dz), dX=flat_period(dn), res_pre=rp, mask=flat_period(acts[li]),
+                                                         mask_slope=slope, spec=fs))
+                    else:
+                        lay.dgrad(dz, dX=dn, res_pre=dl[li - 1], mask=acts[li], mask_slope=slope)
                     dz = dn
                 elif need_dx:
                     if ch.kind == "scale":

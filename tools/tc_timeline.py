@@ -19,7 +19,9 @@ from tools.tc_sweep import SHAPES, seq  # noqa: E402
 def main():
     lib = _lib.load()
     buf = torch.zeros(8192, dtype=torch.int64, device="cuda:0")
-    for i in (0, 2, 6, 24):
+    import os
+    lib.artic_debug_set(9, int(os.environ.get('EPI_DBG', '0')))
+    for i in (0, 2, 6, 12, 24):
         kw, N, lin, ni = SHAPES[i]
         spec = ConvSpec(**kw)
         lay = ConvLayer(spec, "l", BF16, BF16)
@@ -35,11 +37,13 @@ def main():
             torch.cuda.synchronize()
             lib.artic_debug_buffer(None)
         h = buf.cpu().tolist()
-        n = min(h[0], 2000)
-        ev = sorted(((h[2 + 2 * j], h[1 + 2 * j]) for j in range(n)))
-        t0 = ev[0][0]
-        print(f"== {kw} N={N} L={lin}: {n} events")
-        print("   " + " ".join(f"{tag}@{t - t0}" for t, tag in ev[:160]))
+        ev = {j: (h[1 + 2 * j], h[2 + 2 * j]) for j in range(40) if h[1 + 2 * j] > 0}
+        t0 = ev[1][0]
+        names = {1: "start", 2: "setup done", 20: "A seen (first/last kc)", 22: "tile committed (first/last)",
+                 30: "epilogue saw acc (first/last)", 31: "epilogue done (first/last)",
+                 32: "chunk prefetch issued", 33: "chunk tmem loaded", 34: "chunk staged", 35: "chunk stored"}
+        print(f"== {kw} N={N} L={lin}")
+        print("   " + "; ".join(f"{names.get(j, j)}: {a - t0}/{b - t0}" for j, (a, b) in sorted(ev.items())) + f"; exit: {h[90] - t0}")
         tr = [(h[3000 + 3 * j], h[3001 + 3 * j], h[3002 + 3 * j]) for j in range(48)]
         tr = [x for x in tr if x[0] > 0 and x[1] > 0]
         if tr:
