@@ -260,3 +260,25 @@ def test_mr_stft_and_mel_modules(golden):
     ml.backward()
     assert abs(ml.item() - float(golden["mel"]["loss"])) < 1e-4 * float(golden["mel"]["loss"])
     assert rel_err(y_.grad.cpu(), golden["mel"]["grad"]) < 1e-3
+
+
+def test_tc_conv_with_unaligned_bias_and_views():
+    """Parameters live in ONE flat buffer in the train step (FusedAdam), so bias pointers are only 4-byte
+    aligned: the tensor-core epilogue must not assume 16-byte aligned bias (regression: misaligned address)."""
+    torch.manual_seed(0)
+    spec = ConvSpec(kind="conv", cin=64, cout=128, k=3, padding=1)
+    w = torch.randn(spec.weight_shape()) * 0.05
+    flat = torch.zeros(1 + spec.cout + 3, device=DEV)
+    bias = flat[1:1 + spec.cout]                       # data_ptr % 16 == 4
+    bias.copy_(torch.randn(spec.cout) * 0.1)
+    assert bias.data_ptr() % 16 != 0
+    x = torch.randn(3, spec.cin, 300)
+    ref = F.leaky_relu(F.conv1d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias.cpu(), padding=1), 0.1)
+    lay = ConvLayer(spec, "l", BF16, BF16)
+    lay.bind({"l.weight": w.to(DEV).contiguous(), "l.bias": bias})
+    lay.prep()
+    X = SeqT(x.permute(0, 2, 1).contiguous().to(DEV, torch.bfloat16), 3, 300, spec.cin)
+    Y = SeqT.empty(3, 300, spec.cout, BF16, DEV)
+    lay.forward(X, Y2=Y, act=_lib.ACT_LRELU, act_slope=0.1)
+    torch.cuda.synchronize()
+    assert rel_err(Y.t.float().cpu().permute(0, 2, 1), ref) < 2e-2
