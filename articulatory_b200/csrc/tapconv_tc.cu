@@ -27,7 +27,7 @@ constexpr int MAX_AS = 8;   // activation stages
 #ifndef ARTIC_TC_TRACE
 #define ARTIC_TC_TRACE 0
 #endif
-constexpr int EPI_WARP_BYTES = 4 * 32 * 8 + 32 * 4;   // per epilogue warp: row offsets of 4 sub-tiles + the chunk's 32 bias values
+constexpr int EPI_WARP_BYTES = 4 * 32 * 8 + 8 * 32 * 4;   // per epilogue warp: row offsets of 4 sub-tiles + bias of its (<= 8) channel chunks
 
 struct Plan {
   int32_t kch;        // channels per K chunk (64 / 32 / 16)
@@ -330,7 +330,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     uint8_t* epi = smem_raw + (epi_base - smem_u32(smem_raw));
     const int n_ew = (int)(blockDim.x >> 5) - 2;            // 4 or 8 epilogue warps
     long long* rowoff = reinterpret_cast<long long*>(epi + ewarp * EPI_WARP_BYTES);          // [sub-tile][32 rows]
-    float* bias_s = reinterpret_cast<float*>(epi + ewarp * EPI_WARP_BYTES + 4 * 32 * 8);       // [32]
+    float* bias_s = reinterpret_cast<float*>(epi + ewarp * EPI_WARP_BYTES + 4 * 32 * 8);       // [chunk][32]
     const float neg_slope = p.act == ARTIC_ACT_LRELU ? p.act_slope : 1.f;
     for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
       const int nt = tile % pl.n_nt;
@@ -359,11 +359,17 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
         }
         rowoff[m * 32 + lane] = o;
       }
+      {  // bias of this warp's channel chunks (same for every sub-tile): loaded before the accumulator is ready
+        int j = 0;
+        for (int c0 = eh * 32; c0 < pl.bn; c0 += 8 * n_ew, ++j)
+          bias_s[j * 32 + lane] = p.bias != nullptr ? __ldg(p.bias + cbase + c0 + lane) : 0.f;
+      }
       __syncwarp();
       bool waited = false;
       for (int m = 0; m < pl.mt; ++m) {
         const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc.stage * acc_cols + (uint32_t)m * pl.bn;
-        for (int c0 = eh * 32; c0 < pl.bn; c0 += 8 * n_ew) {
+        int cj = 0;
+        for (int c0 = eh * 32; c0 < pl.bn; c0 += 8 * n_ew, ++cj) {
           // Fused epilogue in the TMEM row-per-lane layout: lane = output row, 32 channels per chunk as
           // four 16-byte pieces.  (A shared-memory transposed variant with lanes along the channels
           // coalesces better but costs ~5x the instructions; the epilogue of these small tiles is
@@ -380,9 +386,6 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
               if (res) q_rs[u] = __ldg(reinterpret_cast<const uint4*>(res + o + c0 + 8 * u));
             }
           }
-          __syncwarp();
-          bias_s[lane] = p.bias != nullptr ? __ldg(p.bias + cbase + c0 + lane) : 0.f;   // one coalesced load, broadcast below
-          __syncwarp();
           if (!waited) {
             mbar_wait(&acc_full[acc.stage], acc.phase);
             if (threadIdx.x == 64) dbg_mark(pl.dbg, 30);
@@ -397,7 +400,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
           if (o >= 0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float4 b0 = reinterpret_cast<const float4*>(bias_s)[2 * u], b1 = reinterpret_cast<const float4*>(bias_s)[2 * u + 1];
+              const float4 b0 = reinterpret_cast<const float4*>(bias_s + cj * 32)[2 * u], b1 = reinterpret_cast<const float4*>(bias_s + cj * 32)[2 * u + 1];
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float v[8], tmp[8];
 #pragma unroll

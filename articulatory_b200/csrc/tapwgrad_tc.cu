@@ -25,7 +25,7 @@ namespace tc {
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 8;
-constexpr int WG_EPI_BYTES = 4 * 32 * 8 * 16 + 4 * 32 * 8;   // epilogue transpose stages + row pointers
+constexpr int WG_EPI_BYTES = 0;
 
 struct WPlan {
   int32_t xrb, yrb;            // row bytes (= swizzle span) of the X / dY panels
@@ -78,7 +78,6 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem0 + (uint32_t)pl.n_stages * pl.stage_bytes;   // 4 x 4 KB transpose stages + row pointers
 
   // ---- work decode: blockIdx.x -> (split z, co tile nt, ci block mb, tap group tg, group g)
   int w = blockIdx.x;
@@ -200,16 +199,11 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
     }
   } else {
     // =============================== epilogue ===================================
-    // Split-K partial sums are reduced into dW with red.global.add.v4.f32.  TMEM gives each lane one
-    // ci ROW; the slab is transposed through a swizzled per-warp smem stage so that 8 lanes cover one
-    // row's 32 output channels and every red instruction adds whole 128-byte row segments.
+    // Split-K partial sums are reduced into dW with red.global.add.v4.f32, one dW row (= TMEM lane) per lane.
     const int ew = warp & 3;
     const int row = ew * 32 + lane;           // MMA row = TMEM lane
     const int slot = row / pl.mci;            // which tap of the side-by-side group (0 when mci == 128)
     const int ci = mb * pl.mci + (row - slot * pl.mci);
-    float4* stage = reinterpret_cast<float4*>(smem_raw + (epi_base - smem_u32(smem_raw))) + ew * (32 * 8);   // [32 rows][8 units]
-    float** rowdst = reinterpret_cast<float**>(smem_raw + (epi_base + 4 * 32 * 8 * 16 - smem_u32(smem_raw))) + ew * 32;
-    const int g8 = lane & 7, rsub = lane >> 3;
     if (c_end > c_begin) {
       mbar_wait(&acc_full, 0);
       tc_fence_after();
@@ -220,24 +214,18 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
           const int tap = pl.acc_tap0[acc0 + a] + slot * pl.tap_stride;
           dst = p.dW + (((int64_t)p.widx[tap] * p.G + g) * p.Cig + ci) * p.Cog + nt * pl.bn;
         }
-        rowdst[lane] = dst;
         for (int c0 = 0; c0 < pl.bn; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * pl.bn + c0, r);
           tmem_ld_wait();
+          if (valid) {
+            // posted reductions straight from the TMEM row-per-lane layout (one dW row per lane); the
+            // smem-transposed variant coalesces better but is issue-latency bound on these small tiles
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            stage[lane * 8 + (u ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]),
-                                                             __uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3]));
-          __syncwarp();
-#pragma unroll
-          for (int it = 0; it < 32; it += 4) {
-            const int rr = it + rsub;
-            float* d = rowdst[rr];
-            const float4 f = stage[rr * 8 + (g8 ^ (rr & 7))];
-            if (d != nullptr) red_add_v4(d + c0 + g8 * 4, f.x, f.y, f.z, f.w);
+            for (int i = 0; i < 32; i += 4)
+              red_add_v4(dst + c0 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                         __uint_as_float(r[i + 3]));
           }
-          __syncwarp();
         }
       }
     }
