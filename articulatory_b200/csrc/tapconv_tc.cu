@@ -16,6 +16,8 @@
 //   warps 2..5 = epilogue (TMEM -> registers -> fused bias / residual / LeakyReLU-mask /
 //   activation -> global).  Persistent over tiles; the accumulator is double-buffered in TMEM
 //   when it fits, so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <mutex>
+
 #include "tc_common.cuh"
 
 namespace artic {
@@ -30,6 +32,7 @@ constexpr int MAX_AS = 8;   // activation stages
 constexpr int EPI_WARP_BYTES = 4 * 32 * 8 + 8 * 32 * 4;   // per epilogue warp: row offsets of 4 sub-tiles + bias of its (<= 8) channel chunks
 
 struct Plan {
+  int32_t w_early;    // 1: the first weight stages may be loaded before the grid-dependency wait
   int32_t kch;        // channels per K chunk (64 / 32 / 16)
   int32_t row_bytes;  // kch * 2 = swizzle span
   int32_t n_kc;       // ci chunks
@@ -126,6 +129,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
   const uint32_t epi_base = w_base + (pl.w_resident ? (uint32_t)(pl.n_kc * p.ntaps) * pl.w_tile_bytes : (uint32_t)pl.n_ws * pl.w_stage_bytes);   // 4 x 8 KB transpose stages + row offsets
 
   const long long t_start = clock64();
+  pdl_launch_dependents();   // the next conv of the stream may start its prologue (and weight prefetch) under this one
   // Setup rendezvous on named barrier 1: the producer warp initialises the mbarriers, ARRIVES and goes
   // straight to its first TMA loads; the other warps (TMEM allocation in warp 1) SYNC on it.
   uint32_t tmem_base = 0;
@@ -167,6 +171,8 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
       int n_wl = 0;
 #endif
       const uint32_t w_bytes = (uint32_t)pl.bn * pl.row_bytes;
+      int w_pre = 0;   // weight stages of the first tile issued ahead of the grid-dependency wait
+      if (!pl.w_early) pdl_wait();   // the predecessor may have written the weights
       if (pl.w_resident) {
         // small layers (n_nt == 1, G == 1): every tile uses the same weights; load them once
         mbar_expect_tx(&w_res_full, (uint32_t)(pl.n_kc * ntaps) * w_bytes);
@@ -174,7 +180,24 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
           for (int t = 0; t < ntaps; ++t)
             tma_load_2d(w_base + (uint32_t)(kc * ntaps + t) * pl.w_tile_bytes, &map_w, &w_res_full, kc * pl.kch,
                         p.widx[t] * p.Cog);
+      } else if (cta < pl.total_tiles) {
+        // the weights are not written by the predecessor kernel (tc::note_weights_written): fill the
+        // weight pipeline with the first tile's stages while the predecessor is still finishing
+        const int nt = cta % pl.n_nt;
+        const int g = (cta / pl.n_nt) / pl.n_mt;
+        const int spk = (ntaps + pl.tps - 1) / pl.tps;
+        const int npre = min(pl.n_ws, pl.n_kc * spk);
+        for (; w_pre < npre; ++w_pre) {
+          const int kc = w_pre / spk, t0 = (w_pre % spk) * pl.tps;
+          const int nt_g = min(pl.tps, ntaps - t0);
+          mbar_expect_tx(&w_full[ws.stage], (uint32_t)nt_g * w_bytes);
+          for (int j = 0; j < nt_g; ++j)
+            tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes, &map_w,
+                        &w_full[ws.stage], kc * pl.kch, (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn);
+          ws.next();
+        }
       }
+      pdl_wait();   // activations (and everything the epilogue touches) come from the predecessor
       for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
         const int nt = tile % pl.n_nt;
         const int r = tile / pl.n_nt;
@@ -208,6 +231,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
           as.next();
           if (pl.w_resident) continue;
           for (int t0 = 0; t0 < ntaps; t0 += pl.tps) {
+            if (w_pre > 0) { --w_pre; continue; }
             const int nt_g = min(pl.tps, ntaps - t0);
             mbar_wait(&w_empty[ws.stage], ws.phase ^ 1);
 #if ARTIC_TC_TRACE
@@ -317,6 +341,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     // Eight warps work on a tile: two per TMEM lane quarter, on alternating 32-channel chunks.  Everything
     // that does not depend on the accumulator — output row offsets, the bias, the residual / mask operands
     // of the chunk — is fetched BEFORE the accumulator is waited for / read.
+    pdl_wait();
     const int ew = warp & 3;            // TMEM lane quarter this warp may access
     const int ewarp = warp - 2;         // 0..7
     const int eh = ewarp >> 2;          // channel-chunk parity
@@ -501,6 +526,26 @@ static int max_smem() {
   return g_smem_optin;
 }
 
+// Streams whose prepared weights were rewritten since their last tensor-core conv launch.
+static std::mutex g_wfence_mu;
+static cudaStream_t g_wfence[256];
+static int g_wfence_n = 0;
+static bool g_wfence_overflow = false;   // list full once: early weight prefetch stays off for good
+void note_weights_written(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_wfence_mu);
+  for (int i = 0; i < g_wfence_n; ++i)
+    if (g_wfence[i] == st) return;
+  if (g_wfence_n < 256) g_wfence[g_wfence_n++] = st;
+  else g_wfence_overflow = true;
+}
+static bool consume_weight_fence(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_wfence_mu);
+  if (g_wfence_overflow) return true;
+  for (int i = 0; i < g_wfence_n; ++i)
+    if (g_wfence[i] == st) { g_wfence[i] = g_wfence[--g_wfence_n]; return true; }
+  return false;
+}
+
 }  // namespace tc
 }  // namespace artic
 
@@ -519,7 +564,8 @@ extern "C" int artic_debug_set(int key, int value) {
 
 // Plans one problem for the tensor-core kernel: returns 1 (pr filled: parameters, plan, tensor maps,
 // pr_smem / pr_cost set), 0 if the shape is not eligible, <0 on error.
-static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem, double& pr_cost) {
+// n_share = number of problems that will share the grid (each gets ~1/n_share of the SMs).
+static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem, double& pr_cost, int n_share) {
   const artic_tapconv_t& p = *pp;
   if (tc::g_debug[1]) return 0;                       // debug: force the generic kernel
   if (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16 || p.act == ARTIC_ACT_TANH || p.res2 != nullptr) return 0;
@@ -647,6 +693,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
   tc::Plan pl, cand;
   double best = -1.0;
   const int bns[4] = {256, 128, 64, 32};
+  const int sms_avail = n_share > 1 ? (num_sms() / n_share > 0 ? num_sms() / n_share : 1) : num_sms();
   for (int bi = 0; bi < 4; ++bi) {
     const int bn = bns[bi];
     if (p.Cog % bn != 0) continue;
@@ -655,7 +702,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
       if (tc::g_debug[3] > 0 && mt_req != tc::g_debug[3]) continue;
       if (!make_plan(cand, bn, mt_req)) continue;
       if (cand.mt != mt_req && mt_req != 4) continue;   // already evaluated at a larger request
-      const double waves = (double)((cand.total_tiles + num_sms() - 1) / num_sms());
+      const double waves = (double)((cand.total_tiles + sms_avail - 1) / sms_avail);
       const double per_mma = bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0;
       const double main_clk = (double)cand.n_kc * p.ntaps * (cand.kch / 16) * cand.mt * per_mma;
       const double epi_clk = cand.mt * ((bn + 63) / 64) * 700.0;
@@ -663,7 +710,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
       const double w_tile = cand.w_resident ? 0.0 : (double)cand.n_kc * p.ntaps * bn * cand.row_bytes;
       const double tile_bytes = (double)cand.n_kc * cand.a_stage_bytes + w_tile;
       const double inflight = (double)cand.n_as * cand.a_stage_bytes + (cand.w_resident ? 0.0 : (double)cand.n_ws * cand.w_stage_bytes);
-      const double active = cand.total_tiles < num_sms() ? cand.total_tiles : num_sms();
+      const double active = n_share > 1 ? num_sms() : cand.total_tiles < num_sms() ? cand.total_tiles : num_sms();
       double bw = inflight / 3000.0;
       if (bw > 6000.0 / active) bw = 6000.0 / active;
       const double mem_clk = tile_bytes / bw;
@@ -737,8 +784,23 @@ static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, c
     if (smem[j] > smem_bytes) smem_bytes = smem[j];
   }
   const int grid = mp.cta_begin[n];
-  tc::tapconv_tc_kernel<<<grid, 64 + 32 * n_ew, smem_bytes, st>>>(mp);
-  cudaError_t le = cudaGetLastError();
+  // Programmatic dependent launch (debug key 11 = 1 disables): the kernel may start under its predecessor
+  // in the stream; it prefetches weights before its grid-dependency wait unless they were just rewritten.
+  const bool pdl = tc::g_debug[11] != 1;
+  const bool w_early = pdl && !tc::consume_weight_fence(st);
+  for (int j = 0; j < n; ++j) mp.prob[j].pl.w_early = w_early ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)(64 + 32 * n_ew));
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = w_early ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tc::tapconv_tc_kernel, mp);
+  if (le == cudaSuccess) le = cudaGetLastError();
   if (le != cudaSuccess) {
     const tc::Plan& pl = mp.prob[0].pl;
     set_error("artic_tapconv(tc): launch failed: %s (%d problems, grid %d, smem %d of %d, bn %d mt %d as %d ws %d packed %d)",
@@ -755,10 +817,13 @@ int artic_tapconv_tc_multi(const artic_tapconv_t* ps, int n, int* taken, cudaStr
   int smem[tc::MAXP];
   double cost[tc::MAXP];
   mp.n = 0;
+  int n_live = 0;
+  for (int i = 0; i < n; ++i) n_live += (ps[i].N != 0 && ps[i].nq != 0) ? 1 : 0;
+  const int n_share = tc::g_debug[10] == 1 ? 1 : n_live < tc::MAXP ? n_live : tc::MAXP;   // debug key 10 = 1: plan as if alone
   for (int i = 0; i < n; ++i) {
     taken[i] = 0;
     if (ps[i].N == 0 || ps[i].nq == 0) continue;
-    const int rc = tc_plan_problem(&ps[i], mp.prob[mp.n], smem[mp.n], cost[mp.n]);
+    const int rc = tc_plan_problem(&ps[i], mp.prob[mp.n], smem[mp.n], cost[mp.n], n_share);
     if (rc < 0) return rc;
     if (rc == 0) continue;
     taken[i] = 1;

@@ -96,6 +96,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute
+// may START while its predecessor in the stream is still running; `pdl_wait` blocks until the predecessor
+// has completed and its writes are visible (no-op for a normally launched kernel).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // One lane of a converged warp (elect.sync): lets the whole warp run the issue loop, so that the
 // compiler keeps descriptors / addresses in UNIFORM registers and the single tcgen05 / TMA
 // instruction takes them directly (a loop under `if (lane == 0)` is divergent code: every MMA then
@@ -139,6 +145,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn();           // cuTensorMapEncodeTiled via the runtime's driver entry point (tapconv_tc.cu)
 extern int g_debug[16];              // artic_debug_set knobs
+// Prepared weights were (re)written by a kernel on stream `st`: the next tensor-core conv on that stream
+// is launched with full stream serialization (it prefetches weights BEFORE its grid-dependency wait).
+void note_weights_written(cudaStream_t st);
 
 inline CUtensorMapSwizzle swizzle_of(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;

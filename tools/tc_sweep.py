@@ -112,7 +112,15 @@ def main():
     if what == ["ncu"]:
         return ncu_mode()
     lib = _lib.load()
-    for kw, N, lin, ni in SHAPES:
+    sel = os.environ.get("SWEEP_SHAPES")          # e.g. "16-19,22-29": indices into SHAPES
+    shapes = SHAPES
+    if sel:
+        idx = []
+        for part in sel.split(","):
+            a, _, b = part.partition("-")
+            idx += list(range(int(a), int(b or a) + 1))
+        shapes = [SHAPES[i] for i in idx]
+    for kw, N, lin, ni in shapes:
         spec = ConvSpec(**kw)
         lay = ConvLayer(spec, "l", BF16, BF16)
         w = torch.randn(spec.weight_shape(), device=DEV) * 0.05
