@@ -80,6 +80,7 @@ SIGNATURES = {
     "artic_last_error": (C.c_char_p, []),
     "artic_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "artic_debug_buffer": (C.c_int, [_p]),
+    "artic_trace_buffer": (C.c_int, [_p, C.c_longlong]),
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
     "artic_tapconv_multi": (C.c_int, [C.POINTER(TapConv), _i32, _p]),
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),

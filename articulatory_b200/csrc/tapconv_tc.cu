@@ -70,6 +70,9 @@ struct Prob {
 };
 constexpr int MAXP = 8;
 struct Multi {
+  long long* trace;       // SM-occupancy trace buffer or nullptr
+  long long trace_cap;
+  int32_t launch_id;
   int32_t n;
   int32_t cta_begin[MAXP + 1];
   Prob prob[MAXP];
@@ -129,6 +132,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
   const uint32_t epi_base = w_base + (pl.w_resident ? (uint32_t)(pl.n_kc * p.ntaps) * pl.w_tile_bytes : (uint32_t)pl.n_ws * pl.w_stage_bytes);   // 4 x 8 KB transpose stages + row offsets
 
   const long long t_start = clock64();
+  const long long t_trace = (mp.trace != nullptr && threadIdx.x == 0) ? global_timer() : 0;
   pdl_launch_dependents();   // the next conv of the stream may start its prologue (and weight prefetch) under this one
   // Setup rendezvous on named barrier 1: the producer warp initialises the mbarriers, ARRIVES and goes
   // straight to its first TMA loads; the other warps (TMEM allocation in warp 1) SYNC on it.
@@ -482,6 +486,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
   }
+  if (mp.trace != nullptr && threadIdx.x == 0) trace_cta(mp.trace, mp.trace_cap, mp.launch_id, prob_j & 7, t_trace);
 }
 
 // ------------------------------------------------------------------------------------
@@ -503,6 +508,9 @@ EncodeTiledFn encode_fn() {
 
 int g_debug[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 long long* g_dbg_buf = nullptr;
+long long* g_trace_buf = nullptr;
+long long g_trace_cap = 0;
+int g_trace_launch = 0;
 static int g_smem_optin = 0;
 
 // Largest dynamic shared-memory size the kernel may be launched with (opt-in limit minus the
@@ -553,6 +561,13 @@ using namespace artic;
 
 extern "C" int artic_debug_buffer(void* dev_buf) {
   tc::g_dbg_buf = reinterpret_cast<long long*>(dev_buf);
+  return ARTIC_OK;
+}
+
+extern "C" int artic_trace_buffer(void* dev_buf, long long capacity_records) {
+  tc::g_trace_buf = reinterpret_cast<long long*>(dev_buf);
+  tc::g_trace_cap = dev_buf != nullptr ? capacity_records : 0;
+  tc::g_trace_launch = 0;
   return ARTIC_OK;
 }
 
@@ -789,6 +804,9 @@ static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, c
   const bool pdl = tc::g_debug[11] != 1;
   const bool w_early = pdl && !tc::consume_weight_fence(st);
   for (int j = 0; j < n; ++j) mp.prob[j].pl.w_early = w_early ? 1 : 0;
+  mp.trace = tc::g_trace_buf;
+  mp.trace_cap = tc::g_trace_cap;
+  mp.launch_id = tc::g_trace_buf != nullptr ? tc::g_trace_launch++ : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)(64 + 32 * n_ew));

@@ -45,6 +45,10 @@ struct WPlan {
   int32_t n_ph;                // input-stride phases (= si); X panels per stage = n_ph * nxp
   int32_t tap_stride;          // tap-index distance between side-by-side slots
   int32_t n_acc_total, apc;    // accumulators over all CTAs of a (ci, co) tile; accumulators per CTA
+  long long* trace;            // SM-occupancy trace buffer or nullptr
+  long long trace_cap;
+  int32_t launch_id;
+  int32_t dbg_flags;           // debug key 13: 1 = skip the reductions, 2 = skip the staging-area zeroing (timing experiments)
   // per accumulator: phase panel, row shift of slot 0, tap index of slot 0, number of valid slots
   int8_t acc_panel[ARTIC_MAX_TAPS];
   int16_t acc_shift[ARTIC_MAX_TAPS];
@@ -78,6 +82,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const long long t_trace = (pl.trace != nullptr && threadIdx.x == 0) ? global_timer() : 0;
 
   // ---- work decode: blockIdx.x -> (split z, co tile nt, ci block mb, tap group tg, group g)
   int w = blockIdx.x;
@@ -92,7 +97,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
   const int n_acc = min(pl.apc, pl.n_acc_total - acc0);
 
   // ---- one-time setup: zero the staging area, barriers, TMEM
-  {
+  if (!(pl.dbg_flags & 2)) {
     uint4* z4 = reinterpret_cast<uint4*>(smem_raw + (smem0 - smem_u32(smem_raw)));
     const int n16 = pl.n_stages * pl.stage_bytes / 16;
     for (int i = threadIdx.x; i < n16; i += WG_THREADS) z4[i] = make_uint4(0, 0, 0, 0);
@@ -218,7 +223,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * pl.bn + c0, r);
           tmem_ld_wait();
-          if (valid) {
+          if (valid && !(pl.dbg_flags & 1)) {
             // posted reductions straight from the TMEM row-per-lane layout (one dW row per lane); the
             // smem-transposed variant coalesces better but is issue-latency bound on these small tiles
 #pragma unroll
@@ -237,6 +242,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
   }
+  if (pl.trace != nullptr && threadIdx.x == 0) trace_cta(pl.trace, pl.trace_cap, pl.launch_id, 8, t_trace);
 }
 
 static int g_wg_smem = 0;
@@ -388,6 +394,19 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   const int64_t base = (int64_t)pl.n_nt * pl.n_mb * pl.n_tg * p.G;
   int64_t splits = num_sms() / base;
   if (splits > pl.n_chunks) splits = pl.n_chunks;
+  {
+    // Every CTA pays ~6 us of fixed cost (launch, staging, first-load latency, the split-K reduction of its
+    // whole accumulator) while it holds an SM that the concurrent streams could use: give each split a main
+    // loop of at least `min_clk` tensor-core clocks (debug key 14, in units of 1000 clocks; default 12) rather
+    // than spreading a small layer over all SMs.
+    const double per_mma = pl.bn / 2.0 > 32.0 + pl.bn / 4.0 ? pl.bn / 2.0 : 32.0 + pl.bn / 4.0;
+    const double chunk_clk = (double)pl.apc * (pl.kp / 16) * per_mma;
+    const double min_clk = 1000.0 * (tc::g_debug[14] > 0 ? tc::g_debug[14] : tc::g_debug[14] < 0 ? 0 : 12);
+    int64_t min_chunks = (int64_t)(min_clk / chunk_clk + 0.999);
+    if (min_chunks < 1) min_chunks = 1;
+    const int64_t cap = (pl.n_chunks + min_chunks - 1) / min_chunks;
+    if (splits > cap) splits = cap;
+  }
   if (splits < 1) splits = 1;
   pl.chunks_per_split = (int)((pl.n_chunks + splits - 1) / splits);
   pl.n_splits = (pl.n_chunks + pl.chunks_per_split - 1) / pl.chunks_per_split;
@@ -402,6 +421,10 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   if (rc != CUDA_SUCCESS) { set_error("artic_tapconv_wgrad: cuTensorMapEncodeTiled(X) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   rc = tc::encode_seq_map(enc, &map_y, p.dY, p.y, p.N, p.G * p.Cog, pl.yrb / 2, pl.packed ? pl.seg_pitch : pl.kp, pl.yrb, 1);
   if (rc != CUDA_SUCCESS) { set_error("artic_tapconv_wgrad: cuTensorMapEncodeTiled(dY) failed (%d)", (int)rc); return ARTIC_ECUDA; }
+  pl.dbg_flags = tc::g_debug[13];
+  pl.trace = tc::g_trace_buf;
+  pl.trace_cap = tc::g_trace_cap;
+  pl.launch_id = tc::g_trace_buf != nullptr ? tc::g_trace_launch++ : 0;
   const int smem_bytes = pl.n_stages * pl.stage_bytes + 1024 + tc::WG_EPI_BYTES;
   tc::tapwgrad_tc_kernel<<<(unsigned)grid, tc::WG_THREADS, smem_bytes, st>>>(p, pl, map_x, map_y);
   cudaError_t le = cudaGetLastError();

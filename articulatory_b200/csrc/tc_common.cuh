@@ -102,6 +102,24 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+__device__ __forceinline__ long long global_timer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_cta(long long* trace, long long cap, int launch_id, int kind, long long t0) {
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(trace), 1ULL);
+  if ((long long)slot < cap) {
+    long long* r = trace + 1 + 4 * slot;
+    r[0] = ((long long)launch_id << 32) | ((long long)kind << 28) | (long long)blockIdx.x;
+    r[1] = smid;
+    r[2] = t0;
+    r[3] = global_timer();
+  }
+}
+
 // One lane of a converged warp (elect.sync): lets the whole warp run the issue loop, so that the
 // compiler keeps descriptors / addresses in UNIFORM registers and the single tcgen05 / TMA
 // instruction takes them directly (a loop under `if (lane == 0)` is divergent code: every MMA then
@@ -145,6 +163,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn();           // cuTensorMapEncodeTiled via the runtime's driver entry point (tapconv_tc.cu)
 extern int g_debug[16];              // artic_debug_set knobs
+// SM-occupancy trace (artic_trace_buffer): every CTA of the tensor-core kernels appends one record
+// {launch id << 32 | kind << 28 | blockIdx, smid, globaltimer at start, at exit}; slot 0 = record count.
+extern long long* g_trace_buf;
+extern long long g_trace_cap;
+extern int g_trace_launch;
 // Prepared weights were (re)written by a kernel on stream `st`: the next tensor-core conv on that stream
 // is launched with full stream serialization (it prefetches weights BEFORE its grid-dependency wait).
 void note_weights_written(cudaStream_t st);

@@ -189,6 +189,14 @@ __device__ __forceinline__ void store_out(void* out, int dtype, uint32_t o, floa
   else reinterpret_cast<float*>(out)[o] = x;
 }
 
+// Fast path of both kernels (a tile holds all K <= 8 taps and the taps are the torch-inner index): the torch side
+// of the tile is 32 runs of n_in * K CONTIGUOUS floats; they are copied to / from shared memory as they are
+// (row pitch 32 * K + 1 floats), and the prepared side addresses element (a, b, kk) at a * sA + b * sB + kk.
+__device__ __forceinline__ bool tile_is_runs(const artic_wdesc_t& d, const TileGeom& t, uint32_t s_in, uint32_t s_out) {
+  return t.kn == (uint32_t)d.K && d.sk == 1 && s_in == (uint32_t)d.K &&
+         (d.g == nullptr || (uint32_t)d.row_len % s_out == 0);   // a run stays inside ONE weight-norm row
+}
+
 __global__ void __launch_bounds__(256) wprep_kernel(const artic_wdesc_t* __restrict__ descs, int n_layers,
                                                     long long total_tiles) {
   __shared__ float tile[PK * (TS_K + 32)];
@@ -203,32 +211,66 @@ __global__ void __launch_bounds__(256) wprep_kernel(const artic_wdesc_t* __restr
     const uint32_t in0 = a_inner ? t.a0 : t.b0, out0 = a_inner ? t.b0 : t.a0;
     const uint32_t n_in = min((uint32_t)PT, (a_inner ? A : B) - in0), n_out = min((uint32_t)PT, (a_inner ? B : A) - out0);
     const uint32_t row_len = (uint32_t)d.row_len;
-    // smem strides of the (inner, outer) matrix dims
-    const uint32_t sm_in = a_inner ? TS_A : 1, sm_out = a_inner ? 1 : TS_A;
+    const bool runs = tile_is_runs(d, t, s_in, s_out);
+    uint32_t sA, sB, sK;            // smem strides of (a, b, kk)
     // ---- torch -> smem (weight-norm scale applied)
-    if (t.kn == K && d.sk == 1 && s_in == K && (d.g == nullptr || row_len % s_out == 0)) {
-      // every outer index owns one contiguous run of n_in * K floats (inside ONE weight-norm row)
-      const uint32_t run = n_in * K;
-      const uint32_t q32 = 32 / K, r32 = 32 % K;
-      for (uint32_t o = w8; o < PT; o += 8) {
-        if (o < n_out) {
+    if (runs) {
+      const uint32_t pitch = PT * K + 1, run = n_in * K;
+      sA = a_inner ? K : pitch; sB = a_inner ? pitch : K; sK = 1;
+      // all of a warp's loads (4 rows x <= 2 vectors per lane) are issued before the first use: the pass is
+      // bound by the bytes in flight per SM, not by instruction issue
+      const bool vec = (run & 3) == 0 && (reinterpret_cast<uintptr_t>(d.v + t.tb + in0 * K + out0 * s_out) & 15) == 0 && (s_out & 3) == 0;
+      if (vec) {
+        float4 x[4][2];
+        float sc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t o = w8 + 8 * i;
+          const uint32_t src0 = t.tb + in0 * K + (out0 + o) * s_out;
+          sc[i] = (o < n_out && d.g != nullptr) ? d.scale[src0 / row_len] : 1.f;
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const uint32_t e = 4 * l + 128 * it;
+            x[i][it] = (o < n_out && e < run) ? __ldg(reinterpret_cast<const float4*>(d.v + src0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t o = w8 + 8 * i;
+          float* dst = tile + o * pitch;
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const uint32_t e = 4 * l + 128 * it;
+            if (o < n_out && e < run) {
+              dst[e] = x[i][it].x * sc[i]; dst[e + 1] = x[i][it].y * sc[i]; dst[e + 2] = x[i][it].z * sc[i]; dst[e + 3] = x[i][it].w * sc[i];
+            }
+          }
+        }
+      } else {
+        for (uint32_t o = w8; o < n_out; o += 8) {
           const uint32_t src0 = t.tb + in0 * K + (out0 + o) * s_out;
           const float sc = d.g != nullptr ? d.scale[src0 / row_len] : 1.f;
-          uint32_t in = l / K, kk = l % K;
-          for (uint32_t e = l; e < run; e += 32) {
-            tile[kk * t.ks + in * sm_in + o * sm_out] = __ldg(d.v + src0 + e) * sc;
-            kk += r32; in += q32;
-            if (kk >= K) { kk -= K; ++in; }
-          }
+          const float* src = d.v + src0;
+          float* dst = tile + o * pitch;
+#pragma unroll 4
+          for (uint32_t e = l; e < run; e += 32) dst[e] = __ldg(src + e) * sc;
         }
       }
     } else {
+      sA = TS_A; sB = 1; sK = t.ks;
+      const uint32_t sm_in = a_inner ? TS_A : 1, sm_out = a_inner ? 1 : TS_A;
       for (uint32_t o = w8; o < PT; o += 8) {
-        if (o < n_out && l < n_in) {
+        if (o < n_out && (uint32_t)l < n_in) {
           const uint32_t src = t.tb + (in0 + l) * s_in + (out0 + o) * s_out;
           const float sc = d.g != nullptr ? d.scale[src / row_len] : 1.f;
-          for (uint32_t kk = 0; kk < t.kn; ++kk)
-            tile[kk * t.ks + l * sm_in + o * sm_out] = __ldg(d.v + src + kk * (uint32_t)d.sk) * sc;
+          const float* vp = d.v + src;
+          float* tp = tile + l * sm_in + o * sm_out;
+          float xv[PK];
+#pragma unroll
+          for (uint32_t kk = 0; kk < PK; ++kk) xv[kk] = kk < t.kn ? __ldg(vp + kk * (uint32_t)d.sk) : 0.f;
+#pragma unroll
+          for (uint32_t kk = 0; kk < PK; ++kk)
+            if (kk < t.kn) tp[kk * t.ks] = xv[kk] * sc;
         }
       }
     }
@@ -239,50 +281,50 @@ __global__ void __launch_bounds__(256) wprep_kernel(const artic_wdesc_t* __restr
     if (d.out_f != nullptr) {
       const bool pairs = d.dtype_f == ARTIC_BF16 && !(d.b_pad & 1) && !(t.base_f & 1);
       if (pairs) {
-        for (uint32_t kk = 0; kk < t.kn; ++kk)
+        const uint32_t b = 2 * j;
+        if (b < nb) {
+          const bool two = b + 1 < nb;
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out_f) + t.base_f + b;
           for (uint32_t a = rr; a < na; a += 16) {
-            const uint32_t b = 2 * j;
-            if (b < nb) {
-              const float x0 = tile[kk * t.ks + a * TS_A + b];
-              const uint32_t o = t.base_f + kk * t.kstride + a * d.b_pad + b;
-              if (b + 1 < nb) {
-                const float x1 = tile[kk * t.ks + a * TS_A + b + 1];
-                *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(d.out_f) + o) = __floats2bfloat162_rn(x0, x1);
-              } else {
-                reinterpret_cast<__nv_bfloat16*>(d.out_f)[o] = __float2bfloat16_rn(x0);
-              }
+            const float* s0 = tile + a * sA + b * sB;
+            __nv_bfloat16* o = out + a * d.b_pad;
+#pragma unroll 4
+            for (uint32_t kk = 0; kk < t.kn; ++kk, s0 += sK, o += t.kstride) {
+              if (two) *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(s0[0], s0[sB]);
+              else *o = __float2bfloat16_rn(s0[0]);
             }
           }
+        }
       } else {
         for (uint32_t kk = 0; kk < t.kn; ++kk)
           for (uint32_t a = w8; a < na; a += 8)
             if ((uint32_t)l < nb)
-              store_out(d.out_f, d.dtype_f, t.base_f + kk * t.kstride + a * d.b_pad + l, tile[kk * t.ks + a * TS_A + l]);
+              store_out(d.out_f, d.dtype_f, t.base_f + kk * t.kstride + a * d.b_pad + l, tile[kk * sK + a * sA + l * sB]);
       }
     }
     // ---- 'bwd' layout: rows b, runs along a
     if (d.out_b != nullptr) {
       const bool pairs = d.dtype_b == ARTIC_BF16 && !(d.a_pad & 1) && !(t.base_b & 1);
       if (pairs) {
-        for (uint32_t kk = 0; kk < t.kn; ++kk)
+        const uint32_t a = 2 * j;
+        if (a < na) {
+          const bool two = a + 1 < na;
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out_b) + t.base_b + a;
           for (uint32_t b = rr; b < nb; b += 16) {
-            const uint32_t a = 2 * j;
-            if (a < na) {
-              const float x0 = tile[kk * t.ks + a * TS_A + b];
-              const uint32_t o = t.base_b + kk * t.kstride + b * d.a_pad + a;
-              if (a + 1 < na) {
-                const float x1 = tile[kk * t.ks + (a + 1) * TS_A + b];
-                *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(d.out_b) + o) = __floats2bfloat162_rn(x0, x1);
-              } else {
-                reinterpret_cast<__nv_bfloat16*>(d.out_b)[o] = __float2bfloat16_rn(x0);
-              }
+            const float* s0 = tile + a * sA + b * sB;
+            __nv_bfloat16* o = out + b * d.a_pad;
+#pragma unroll 4
+            for (uint32_t kk = 0; kk < t.kn; ++kk, s0 += sK, o += t.kstride) {
+              if (two) *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(s0[0], s0[sA]);
+              else *o = __float2bfloat16_rn(s0[0]);
             }
           }
+        }
       } else {
         for (uint32_t kk = 0; kk < t.kn; ++kk)
           for (uint32_t b = w8; b < nb; b += 8)
             if ((uint32_t)l < na)
-              store_out(d.out_b, d.dtype_b, t.base_b + kk * t.kstride + b * d.a_pad + l, tile[kk * t.ks + l * TS_A + b]);
+              store_out(d.out_b, d.dtype_b, t.base_b + kk * t.kstride + b * d.a_pad + l, tile[kk * sK + l * sA + b * sB]);
       }
     }
     __syncthreads();
@@ -299,40 +341,80 @@ __global__ void __launch_bounds__(256) wunprep_kernel(const artic_wdesc_t* __res
     const TileGeom t = tile_geom(d, gt);
     const uint32_t A = d.A, B = d.B, K = d.K;
     const uint32_t na = min((uint32_t)PT, A - t.a0), nb = min((uint32_t)PT, B - t.b0);
-    // ---- prepared gradient -> smem
-    if (!d.dw_swapped) {
-      for (uint32_t kk = 0; kk < t.kn; ++kk)
-        for (uint32_t a = w8; a < na; a += 8)
-          if ((uint32_t)l < nb) tile[kk * t.ks + a * TS_A + l] = __ldg(d.dWp + t.base_f + kk * t.kstride + a * d.b_pad + l);
-    } else {
-      for (uint32_t kk = 0; kk < t.kn; ++kk)
-        for (uint32_t b = w8; b < nb; b += 8)
-          if ((uint32_t)l < na) tile[kk * t.ks + l * TS_A + b] = __ldg(d.dWp + t.base_b + kk * t.kstride + b * d.a_pad + l);
-    }
-    __syncthreads();
-    // ---- smem -> torch layout
-    const bool a_inner = d.sa < d.sb || (d.sa == d.sb && d.A == 1);   // tie (one channel): keep the other dim outer
+    const bool a_inner = d.sa < d.sb || (d.sa == d.sb && d.A == 1);
     const uint32_t s_in = (uint32_t)(a_inner ? d.sa : d.sb), s_out = (uint32_t)(a_inner ? d.sb : d.sa);
     const uint32_t in0 = a_inner ? t.a0 : t.b0, out0 = a_inner ? t.b0 : t.a0;
     const uint32_t n_in = a_inner ? na : nb, n_out = a_inner ? nb : na;
-    const uint32_t sm_in = a_inner ? TS_A : 1, sm_out = a_inner ? 1 : TS_A;
-    if (t.kn == K && d.sk == 1 && s_in == K) {
-      const uint32_t run = n_in * K;
-      const uint32_t q32 = 32 / K, r32 = 32 % K;
-      for (uint32_t o = w8; o < n_out; o += 8) {
-        const uint32_t dst0 = t.tb + in0 * K + (out0 + o) * s_out;
-        uint32_t in = l / K, kk = l % K;
-        for (uint32_t e = l; e < run; e += 32) {
-          d.dv[dst0 + e] = tile[kk * t.ks + in * sm_in + o * sm_out];
-          kk += r32; in += q32;
-          if (kk >= K) { kk -= K; ++in; }
+    const bool runs = t.kn == K && d.sk == 1 && s_in == K;
+    const uint32_t pitch = PT * K + 1;
+    const uint32_t sA = runs ? (a_inner ? K : pitch) : TS_A, sB = runs ? (a_inner ? pitch : K) : 1, sK = runs ? 1 : t.ks;
+    // ---- prepared gradient -> smem
+    if (!d.dw_swapped) {
+      if ((uint32_t)l < nb) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {      // 2 rows x 8 taps of loads in flight per lane
+          float xv[2][PK];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t a = w8 + 8 * (2 * half + i);
+            const float* src = d.dWp + t.base_f + a * d.b_pad + l;
+#pragma unroll
+            for (uint32_t kk = 0; kk < PK; ++kk) xv[i][kk] = (a < na && kk < t.kn) ? __ldg(src + kk * t.kstride) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t a = w8 + 8 * (2 * half + i);
+            float* tp = tile + a * sA + l * sB;
+#pragma unroll
+            for (uint32_t kk = 0; kk < PK; ++kk)
+              if (a < na && kk < t.kn) tp[kk * sK] = xv[i][kk];
+          }
         }
       }
     } else {
+      if ((uint32_t)l < na) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float xv[2][PK];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t b = w8 + 8 * (2 * half + i);
+            const float* src = d.dWp + t.base_b + b * d.a_pad + l;
+#pragma unroll
+            for (uint32_t kk = 0; kk < PK; ++kk) xv[i][kk] = (b < nb && kk < t.kn) ? __ldg(src + kk * t.kstride) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t b = w8 + 8 * (2 * half + i);
+            float* tp = tile + l * sA + b * sB;
+#pragma unroll
+            for (uint32_t kk = 0; kk < PK; ++kk)
+              if (b < nb && kk < t.kn) tp[kk * sK] = xv[i][kk];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- smem -> torch layout
+    if (runs) {
+      const uint32_t run = n_in * K;
+      for (uint32_t o = w8; o < n_out; o += 8) {
+        float* dst = d.dv + t.tb + in0 * K + (out0 + o) * s_out;
+        const float* src = tile + o * pitch;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (run & 3) == 0) {
+          for (uint32_t e = 4 * l; e < run; e += 128)
+            *reinterpret_cast<float4*>(dst + e) = make_float4(src[e], src[e + 1], src[e + 2], src[e + 3]);
+        } else {
+          for (uint32_t e = l; e < run; e += 32) dst[e] = src[e];
+        }
+      }
+    } else {
+      const uint32_t sm_in = a_inner ? TS_A : 1, sm_out = a_inner ? 1 : TS_A;
       for (uint32_t o = w8; o < n_out; o += 8)
         if ((uint32_t)l < n_in) {
-          const uint32_t dst = t.tb + (in0 + l) * s_in + (out0 + o) * s_out;
-          for (uint32_t kk = 0; kk < t.kn; ++kk) d.dv[dst + kk * (uint32_t)d.sk] = tile[kk * t.ks + l * sm_in + o * sm_out];
+          float* dst = d.dv + t.tb + (in0 + l) * s_in + (out0 + o) * s_out;
+          const float* tp = tile + l * sm_in + o * sm_out;
+          for (uint32_t kk = 0; kk < t.kn; ++kk) dst[kk * (uint32_t)d.sk] = tp[kk * t.ks];
         }
     }
     __syncthreads();
@@ -473,8 +555,10 @@ __global__ void adam_tick_kernel(artic_adam_hyper_t* hyper) { hyper->step += 1; 
 
 using namespace artic;
 
+// One tile per block up to a generous cap: short-lived blocks let a low-priority weight prep yield SMs to the
+// critical-path kernels it runs under (persistent blocks would hold them for the whole pass).
 static unsigned wperm_grid(int64_t total_tiles) {
-  const int64_t cap = 8LL * num_sms();
+  const int64_t cap = 1LL << 20;
   return (unsigned)(total_tiles < cap ? (total_tiles > 0 ? total_tiles : 1) : cap);
 }
 

@@ -133,10 +133,29 @@ _SIDE_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
 _FORK_DEPTH: Dict[int, int] = {}
 
 
-def fork_join(branches, device=None):
+#: Stream priorities: everything on the critical path runs on HIGH-priority streams (the capture stream
+#: of trainer.TrainStep, fork_join side streams, weight-gradient queues); "background" branches — the
+#: discriminator's weight re-materialisation under the generator forward, the spectral losses under the
+#: discriminator forward — run on LOW-priority streams, so that their thread blocks only take SMs the
+#: critical-path kernels do not want (measured with tools/kernel_trace.py: without this the 1184 blocks of
+#: the weight prep / the 1600 frame-FFT blocks of the mel loss fill every SM and the chain they should
+#: overlap with starts 300-500 us late).
+PRIO_HIGH, PRIO_LOW = -1, 0
+_BG_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
+_BG_DEPTH: Dict[int, int] = {}
+_IN_BACKGROUND = [False]
+
+
+def critical_stream(device=None):
+    """A new high-priority stream (for graph capture / the eager step)."""
+    return torch.cuda.Stream(device=device, priority=PRIO_HIGH)
+
+
+def fork_join(branches, device=None, background=()):
     """Run independent branches concurrently: branch 0 on the current stream, the others on side
     streams forked from it, all joined back before returning (capturable in a CUDA graph: the
-    fork / join become graph edges).  The layers of this network are small enough that a single
+    fork / join become graph edges).  Branch indices listed in ``background`` (and every fork_join
+    nested inside them) use low-priority streams.  The layers of this network are small enough that a single
     kernel leaves SMs idle and pays its launch / pipeline-fill latency serially; the three MRF
     blocks of a generator stage and the eight sub-discriminators are independent, so their kernels
     overlap.  ARTIC_STREAMS=0 runs the branches one after the other."""
@@ -145,24 +164,40 @@ def fork_join(branches, device=None):
         return [b() for b in branches]
     main = torch.cuda.current_stream()
     dev = main.device_index
+    use_prio = os.environ.get("ARTIC_PRIORITIES", "1") != "0"
     pool = _SIDE_STREAMS.setdefault(dev, [])
-    base = _FORK_DEPTH.get(dev, 0)                 # nested fork_join calls take fresh side streams
-    while len(pool) < base + len(branches) - 1:
-        pool.append(torch.cuda.Stream(device=dev))
-    side = pool[base:base + len(branches) - 1]
-    _FORK_DEPTH[dev] = base + len(branches) - 1
+    bg_pool = _BG_STREAMS.setdefault(dev, [])
+    base, bg_base = _FORK_DEPTH.get(dev, 0), _BG_DEPTH.get(dev, 0)   # nested fork_join calls take fresh side streams
+    side = []
+    n_hi = n_bg = 0
+    for i in range(1, len(branches)):
+        if use_prio and (_IN_BACKGROUND[0] or i in background):
+            if len(bg_pool) <= bg_base + n_bg:
+                bg_pool.append(torch.cuda.Stream(device=dev, priority=PRIO_LOW))
+            side.append(bg_pool[bg_base + n_bg])
+            n_bg += 1
+        else:
+            if len(pool) <= base + n_hi:
+                pool.append(torch.cuda.Stream(device=dev, priority=PRIO_HIGH if use_prio else 0))
+            side.append(pool[base + n_hi])
+            n_hi += 1
+    _FORK_DEPTH[dev], _BG_DEPTH[dev] = base + n_hi, bg_base + n_bg
+    was_bg = _IN_BACKGROUND[0]
     try:
         for st in side:
             st.wait_stream(main)
         out = [None] * len(branches)
         for i in range(1, len(branches)):
+            _IN_BACKGROUND[0] = was_bg or i in background
             with torch.cuda.stream(side[i - 1]):
                 out[i] = branches[i]()
+        _IN_BACKGROUND[0] = was_bg or 0 in background
         out[0] = branches[0]()
         for st in side:
             main.wait_stream(st)
     finally:
-        _FORK_DEPTH[dev] = base
+        _FORK_DEPTH[dev], _BG_DEPTH[dev] = base, bg_base
+        _IN_BACKGROUND[0] = was_bg
     return out
 
 
@@ -183,7 +218,8 @@ class SideQueue:
         self.keep = []
         if not self.inline:
             dev = torch.cuda.current_stream().device_index
-            pool = _QUEUE_STREAMS.setdefault(dev, [torch.cuda.Stream(device=dev) for _ in range(12)])
+            prio = PRIO_HIGH if os.environ.get("ARTIC_PRIORITIES", "1") != "0" else 0
+            pool = _QUEUE_STREAMS.setdefault(dev, [torch.cuda.Stream(device=dev, priority=prio) for _ in range(12)])
             i = _QUEUE_NEXT.get(dev, 0)
             _QUEUE_NEXT[dev] = (i + 1) % len(pool)
             self.s = pool[i]
@@ -240,6 +276,8 @@ class ConvLayer:
         # multiple of 32 channels so that the layer runs on the tensor-core kernel.
         if pad_in and in_code == BF16 and out_code == BF16 and spec.groups == 1 and spec.cin >= 32 and spec.cin % 16:
             self.kcig = (spec.cin + 31) // 32 * 32
+            if self.kcig > 128:      # the tcgen05 weight-gradient kernel wants 32 / 64 / k * 128 input channels
+                self.kcig = (spec.cin + 127) // 128 * 128
         # Transposed convs get their weight gradient as the weight gradient of the equivalent strided conv
         # with X and dY exchanged (dW^T, i.e. the 'bwd' layout): that contraction has unit output stride,
         # which the tcgen05 wgrad kernel requires.
@@ -919,14 +957,15 @@ class DiscriminatorEngine:
                 "chains": [[slice_seq(a, lo, hi) for a in acts] for acts in tape["chains"]]}
 
     # ---- backward ------------------------------------------------------------
-    def backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True):
+    def backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True, pre_zeroed=False):
         """douts: per chain a list (same length as the chain's outputs) of SeqT gradients or
         None; the gradient wrt the logits must be present.  Accumulates parameter gradients
         into ``grads`` when given (None = skip every wgrad, as in the generator phase) and
-        returns d x (B, 1, T) fp32 when ``need_dx``."""
+        returns d x (B, 1, T) fp32 when ``need_dx``.  ``pre_zeroed``: the caller already cleared the
+        weight-gradient accumulators (``wset.zero()``) off the critical path."""
         B, T = tape["B"], tape["T"]
         dev = tape["sigs"][0].t.device
-        if grads is not None:
+        if grads is not None and not pre_zeroed:
             self.wset.zero()
         dx = torch.zeros((B, 1, T), dtype=torch.float32, device=dev) if need_dx else None
         n_scales = len(tape["sigs"])

@@ -20,9 +20,16 @@ import torch
 
 from . import _lib
 from ._lib import F32, call, ptr
-from .engine import SeqT, fork_join, slice_seq
+from .engine import SeqT, critical_stream, fork_join, slice_seq
 from .losses.spectral import MelSpectrogramLoss, MultiResolutionSTFTLoss
 from .optim import FusedAdam
+
+import os as _os
+#: ARTIC_BG="prep,spectral,order": which branches run on low-priority streams / in which order (see
+#: engine.fork_join).  Measured on B200 (gpurun_out/r1_bg_45.log): every variant lands within 0.1 ms of the
+#: default (nothing in the background) — the step is bound by total SM time, not by the order the scheduler
+#: picks — so the default keeps everything at one priority.
+_BG = set(filter(None, _os.environ.get("ARTIC_BG", "").split(",")))
 
 LOG_KEYS = ["train/spectral_convergence_loss", "train/log_stft_magnitude_loss", "train/mel_loss",
             "train/adversarial_loss", "train/feature_matching_loss", "train/generator_loss",
@@ -116,7 +123,8 @@ class TrainStep:
         # the discriminator's weights (updated at the end of the previous step) are re-materialised on a
         # side stream while the generator forward runs
         (y_, tapeG), engD = fork_join([lambda: engG.forward(x, ar, save=True),
-                                       lambda: D._ensure_ready() if train_d_active else None])
+                                       lambda: D._ensure_ready() if train_d_active else None],
+                                      background=(1,) if "prep" in _BG else ())
         y2d, t2d = y_.reshape(B, T), y.reshape(B, T)
         dy = torch.zeros((B, 1, T), dtype=torch.float32, device=self.dev)
         self.slots.zero_()
@@ -185,7 +193,12 @@ class TrainStep:
             douts = fork_join([lambda ci=ci: seed_chain(ci) for ci in range(len(outs_f))])
             state["d_in"] = engD.backward(engD.slice_tape(tape2, 0, B), douts, grads=None, need_dx=True)    # dgrad only
 
-        fork_join([adversarial, spectral])
+        # the discriminator chain is enqueued FIRST (side stream), the losses after it: the ~1600 frame-FFT
+        # blocks of the mel loss otherwise fill every SM before the chain's first kernels get one
+        if "order" in _BG:
+            _, res = fork_join([spectral, adversarial], background=(0,) if "spectral" in _BG else ())
+        else:
+            fork_join([adversarial, spectral], background=(1,) if "spectral" in _BG else ())
         La = self.ar_len
         call("artic_add_rows", ptr(state["d_in"]) + 4 * La, La + T, ptr(dy), T, B, T)
         tape2 = state["tape2"]
@@ -199,7 +212,11 @@ class TrainStep:
         engD = D._ensure_ready()
         B = y.shape[0]
         inv_w = 1.0 / self.world
-        y_, _ = engG.forward(x, ar, save=False)                               # bin/train.py:390-400
+        def clear_d_grads():      # two 283 MB fills: under the generator forward instead of in front of the D backward
+            self.optD.zero_grad()
+            engD.wset.zero()
+
+        (y_, _), _ = fork_join([lambda: engG.forward(x, ar, save=False), clear_d_grads])   # bin/train.py:390-400
         if tape2 is None:
             _, tape2 = engD.forward(self._disc_input(ar, (y_, y)), save=True)
         else:
@@ -214,9 +231,8 @@ class TrainStep:
             self._adv_seed(outs_f[ci:ci + 1], 0.0, _FAKE, inv_w, lg_grads[ci:ci + 1], lo=0)
 
         fork_join([lambda ci=ci: seed_chain(ci) for ci in range(len(outs2))])
-        self.optD.zero_grad()
         douts = [[None] * (len(lst) - 1) + [lg_grads[ci]] for ci, lst in enumerate(outs2)]
-        engD.backward(tape2, douts, grads=self.optD.grad_views, need_dx=False)
+        engD.backward(tape2, douts, grads=self.optD.grad_views, need_dx=False, pre_zeroed=True)
 
     # The step is cut into three segments so that the (optional) data-parallel gradient
     # all-reduce can run between CUDA-graph replays:  seg1 = G phase up to dL/dθ_G,
@@ -299,10 +315,11 @@ class TrainStep:
         self._restore(snap)
         pool = torch.cuda.graph_pool_handle()
         graphs = []
+        cap = critical_stream(self.dev)         # high priority: see engine.fork_join
         for seg in (lambda: self._seg1(sx, sy, sa, self.steps), lambda: self._seg2(sx, sy, sa, self.steps),
                     lambda: self._seg3(self.steps)):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pool, stream=cap):
                 seg()
             graphs.append(g)
         self.all_reduce = ar_fn

@@ -49,6 +49,12 @@ int artic_debug_set(int key, int value);
 /* Debug: device buffer (>= 4001 int64, zeroed) into which CTA 0 of the tensor-core conv kernel records a
  * (tag, clock64) timeline; NULL disables. */
 int artic_debug_buffer(void* dev_buf);
+/* Debug: SM-occupancy trace.  Every CTA of the tensor-core kernels appends one record of four int64
+ * {launch id << 32 | kind << 28 | blockIdx.x, smid, globaltimer ns at start, at exit} after slot 0
+ * (= record count, zero it before the traced region); kind 0..7 = problem index of a conv launch,
+ * 8 = weight gradient.  dev_buf holds 1 + 4 * capacity_records int64; NULL disables.  The pointer is
+ * baked into launches when they are enqueued (CUDA graphs: set it before capture). */
+int artic_trace_buffer(void* dev_buf, long long capacity_records);
 
 /* Addressing of one channels-last sequence batch (see header comment). */
 typedef struct {

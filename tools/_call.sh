@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r1_pytest_gpu_39.log
-tail -3 gpurun_out/r1_pytest_gpu_39.log
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+ARTIC_BG=none timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-250
