@@ -280,13 +280,34 @@ __global__ void __launch_bounds__(512) mel_loss_kernel(const float* __restrict__
       dm[threadIdx.x] = gm;
     }
     __syncthreads();
+    // da[k] = sum_m dm[m] * melmat[k][m].  One WARP per bin (lanes along the mel index: coalesced rows, a
+    // shuffle reduction) when the scratch area can hold da[]; a thread per bin walking its own row touches
+    // 32 different cache lines per load instruction and made this loop the bulk of the kernel.
+    const int ngroups = max(1, (int)blockDim.x / n_mels);
+    const bool warp_rows = 2 * ngroups * n_mels >= n_mels + n_bins;
+    float* da_s = dm + n_mels;
+    if (warp_rows) {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+      for (int k = warp; k <= half; k += nwarp) {
+        const float* mrow = melmat + (int64_t)k * n_mels;
+        float acc = 0.f;
+        for (int m = lane; m < n_mels; m += 32) acc = fmaf(dm[m], __ldg(mrow + m), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) da_s[k] = acc;
+      }
+      __syncthreads();
+    }
     for (int k = threadIdx.x; k <= half; k += blockDim.x) {
       float xr, xi, yr, yi;
       split_bin(zr, zi, k, g.N, xr, xi, yr, yi);
       const float px = xr * xr + xi * xi;
       float da = 0.f;
-      const float* mrow = melmat + (int64_t)k * n_mels;
-      for (int m = 0; m < n_mels; ++m) da = fmaf(dm[m], __ldg(mrow + m), da);
+      if (warp_rows) {
+        da = da_s[k];
+      } else {
+        const float* mrow = melmat + (int64_t)k * n_mels;
+        for (int m = 0; m < n_mels; ++m) da = fmaf(dm[m], __ldg(mrow + m), da);
+      }
       if (!(px >= eps)) da = 0.f;
       const float sc = da / ax[k];
       ax[k] = sc * xr;
