@@ -340,16 +340,17 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_kernel(const __grid_constant
 // 128-bit loads, each thread keeps [taps][8 channels] partial sums in registers, the position loop
 // is unrolled 4x so that four independent row loads are in flight (the scalar kernel above is
 // latency-bound: one 2-byte load per thread per iteration).
+constexpr int C1V_ROWS = 256;   // positions per CTA of the vector kernel (twice the CTAs of the scalar ones)
 template <typename T>
 __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_constant__ artic_tapwgrad_t p, int tap0,
                                                                int min_off, int span) {
   __shared__ float xs[C1_SMEM];
-  __shared__ float red[256][9];
+  __shared__ float red[256][17];
   const int tpr = p.Cog >> 3, rpp = 256 / tpr;
   const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
   const int n = blockIdx.y;
-  const int qa = blockIdx.x * C1_ROWS;
-  const int qb = min(p.nq, qa + C1_ROWS);
+  const int qa = blockIdx.x * C1V_ROWS;
+  const int qb = min(p.nq, qa + C1V_ROWS);
   const T* __restrict__ X = reinterpret_cast<const T*>(p.X) + seq_base(p.x, n);
   const __nv_bfloat16* __restrict__ dY = reinterpret_cast<const __nv_bfloat16*>(p.dY) + seq_base(p.y, n);
   const int x0 = (p.q0 + qa) * p.si + min_off;
@@ -399,16 +400,19 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
     }
   }
 #pragma unroll
-  for (int t = 0; t < C1_TAPS; ++t) {
+  for (int t = 0; t < C1_TAPS; t += 2) {       // two taps per reduction round
     if (t < nt) {
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[t][i];
+      for (int i = 0; i < 8; ++i) { red[threadIdx.x][i] = acc[t][i]; red[threadIdx.x][8 + i] = acc[t + 1][i]; }
       __syncthreads();
-      for (int c = threadIdx.x; c < p.Cog; c += 256) {
-        float sum = 0.f;
-        for (int r = 0; r < rpp; ++r) sum += red[r * tpr + (c >> 3)][c & 7];
-        atomicAdd(p.dW + (int64_t)p.widx[tap0 + t] * p.Cog + c, sum);   // [K][G=1][Cig=1][Cog]
+      for (int e = threadIdx.x; e < 2 * p.Cog; e += 256) {
+        const int tt = e / p.Cog, c = e - tt * p.Cog;
+        if (t + tt < nt) {
+          float sum = 0.f;
+          for (int r = 0; r < rpp; ++r) sum += red[r * tpr + (c >> 3)][8 * tt + (c & 7)];
+          atomicAdd(p.dW + (int64_t)p.widx[tap0 + t + tt] * p.Cog + c, sum);   // [K][G=1][Cig=1][Cog]
+        }
       }
     }
   }
@@ -443,23 +447,37 @@ __global__ void __launch_bounds__(256) tapwgrad_co1_kernel(const __grid_constant
 #pragma unroll
   for (int t = 0; t < C1_TAPS; ++t) acc[t] = 0.f;
   if (c < p.Cig) {
-    for (int r = ra + pl; r < rb; r += npl) {
-      if (r < 0 || r >= p.x.len) continue;
-      const float x = ld_f(X + (int64_t)r * p.x.s_row + c);
-      const int yb = r - y0;                           // index of q = r in ys
+    // four independent row loads in flight per thread (one 2-byte load per iteration is latency-bound)
+    for (int r = ra + pl; r < rb; r += 4 * npl) {
+      float x[4];
 #pragma unroll
-      for (int t = 0; t < C1_TAPS; ++t)
-        if (t < nt) acc[t] = fmaf(x, ys[yb - p.off[tap0 + t]], acc[t]);
+      for (int j = 0; j < 4; ++j) {
+        const int rr = r + j * npl;
+        x[j] = (rr < rb && rr >= 0 && rr < p.x.len) ? ld_f(X + (int64_t)rr * p.x.s_row + c) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = r + j * npl;
+        if (rr < rb) {
+          const int yb = rr - y0;                      // index of q = r in ys
+#pragma unroll
+          for (int t = 0; t < C1_TAPS; ++t)
+            if (t < nt) acc[t] = fmaf(x[j], ys[yb - p.off[tap0 + t]], acc[t]);
+        }
+      }
     }
   }
-  for (int t = 0; t < nt; ++t) {
-    __syncthreads();
-    red[threadIdx.x] = acc[t];
-    __syncthreads();
-    if (pl == 0 && c < p.Cig) {
-      float s = 0.f;
-      for (int i = 0; i < npl; ++i) s += red[i * cw + cl];
-      atomicAdd(p.dW + (int64_t)p.widx[tap0 + t] * p.Cig + c, s);   // [K][G=1][Cig][Cog=1]
+#pragma unroll
+  for (int t = 0; t < C1_TAPS; ++t) {      // static indexing: acc[] stays in registers
+    if (t < nt) {
+      __syncthreads();
+      red[threadIdx.x] = acc[t];
+      __syncthreads();
+      if (pl == 0 && c < p.Cig) {
+        float s = 0.f;
+        for (int i = 0; i < npl; ++i) s += red[i * cw + cl];
+        atomicAdd(p.dW + (int64_t)p.widx[tap0 + t] * p.Cig + c, s);   // [K][G=1][Cig][Cog=1]
+      }
     }
   }
 }
@@ -535,7 +553,7 @@ int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
                      p.y.s_outer % 8 == 0 && (p.y.n_inner == 1 || p.y.s_inner % 8 == 0) &&
                      (reinterpret_cast<uintptr_t>(p.dY) & 15) == 0;
     if (vec) {
-      dim3 vgrid(grid.x, grid.y, 1);
+      dim3 vgrid((unsigned)((p.nq + C1V_ROWS - 1) / C1V_ROWS), grid.y, 1);
       if (xb) tapwgrad_ci1_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span);
       else tapwgrad_ci1_vec_kernel<float><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span);
     } else if (ci1) ARTIC_C1_LAUNCH(tapwgrad_ci1_kernel);
