@@ -506,7 +506,7 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int g_debug[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+int g_debug[32] = {0};
 long long* g_dbg_buf = nullptr;
 long long* g_trace_buf = nullptr;
 long long g_trace_cap = 0;
@@ -572,7 +572,7 @@ extern "C" int artic_trace_buffer(void* dev_buf, long long capacity_records) {
 }
 
 extern "C" int artic_debug_set(int key, int value) {
-  if (key < 0 || key >= 16) return ARTIC_EINVAL;
+  if (key < 0 || key >= 32) return ARTIC_EINVAL;
   tc::g_debug[key] = value;
   return ARTIC_OK;
 }
@@ -725,14 +725,28 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
       const double w_tile = cand.w_resident ? 0.0 : (double)cand.n_kc * p.ntaps * bn * cand.row_bytes;
       const double tile_bytes = (double)cand.n_kc * cand.a_stage_bytes + w_tile;
       const double inflight = (double)cand.n_as * cand.a_stage_bytes + (cand.w_resident ? 0.0 : (double)cand.n_ws * cand.w_stage_bytes);
-      const double active = n_share > 1 ? num_sms() : cand.total_tiles < num_sms() ? cand.total_tiles : num_sms();
+      // every SM is busy with some stream's CTA: the L2 share of a CTA is 1 / #SMs (debug key 17 = 1: of this launch only)
+      const double active = (n_share > 1 || tc::g_debug[17] != 1) ? num_sms() : cand.total_tiles < num_sms() ? cand.total_tiles : num_sms();
       double bw = inflight / 3000.0;
       if (bw > 6000.0 / active) bw = 6000.0 / active;
       const double mem_clk = tile_bytes / bw;
       double tile_clk = main_clk > mem_clk ? main_clk : mem_clk;
       if (cand.acc_stages == 2) tile_clk = tile_clk > epi_clk ? tile_clk : epi_clk;
       else tile_clk += epi_clk;
-      const double cost = waves * (tile_clk + 600.0) + (cand.acc_stages == 2 ? epi_clk : 0.0);
+      double cost = waves * (tile_clk + 600.0) + (cand.acc_stages == 2 ? epi_clk : 0.0);
+      {
+        // Objective: the SM TIME of the launch, not its stand-alone latency.  The train step runs 3..8 independent
+        // chains on concurrent streams, every CTA owns an SM (shared memory), and the SM-occupancy trace
+        // (tools/sm_timeline.py) shows the step bound by the sum of CTA lifetimes: a plan with fewer, fuller CTAs
+        // that is slower alone leaves SMs to the other streams.  Measured: 14.4 -> 13.5 ms per step.
+        // Debug key 15 = percentage of the SM-time term (default 100; -1 = pure latency), key 16 = fixed cost per
+        // CTA in units of 500 clocks (default 6: launch, barrier / TMEM setup, first TMA round trip).
+        const double a = tc::g_debug[15] > 0 ? tc::g_debug[15] / 100.0 : tc::g_debug[15] < 0 ? 0.0 : 1.0;
+        const double fixed = tc::g_debug[16] > 0 ? 500.0 * tc::g_debug[16] : 3000.0;
+        const double ctas = cand.total_tiles < sms_avail ? cand.total_tiles : sms_avail;
+        const double sm_time = ctas * (fixed + waves * (tile_clk + 600.0)) / sms_avail;
+        cost = (1.0 - a) * cost + a * sm_time;
+      }
       if (best < 0 || cost < best) { best = cost; pl = cand; }
     }
   }

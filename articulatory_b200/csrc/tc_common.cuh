@@ -162,7 +162,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn();           // cuTensorMapEncodeTiled via the runtime's driver entry point (tapconv_tc.cu)
-extern int g_debug[16];              // artic_debug_set knobs
+extern int g_debug[32];              // artic_debug_set knobs
 // SM-occupancy trace (artic_trace_buffer): every CTA of the tensor-core kernels appends one record
 // {launch id << 32 | kind << 28 | blockIdx, smid, globaltimer at start, at exit}; slot 0 = record count.
 extern long long* g_trace_buf;
