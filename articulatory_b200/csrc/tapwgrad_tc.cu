@@ -48,6 +48,7 @@ struct WPlan {
   long long* trace;            // SM-occupancy trace buffer or nullptr
   long long trace_cap;
   int32_t launch_id;
+  int32_t epi_transposed;      // 1: coalesced reductions through a shared-memory transpose (debug key 18 = 1 turns it off)
   int32_t dbg_flags;           // debug key 13: 1 = skip the reductions, 2 = skip the staging-area zeroing (timing experiments)
   // per accumulator: phase panel, row shift of slot 0, tap index of slot 0, number of valid slots
   int8_t acc_panel[ARTIC_MAX_TAPS];
@@ -209,6 +210,9 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
     const int row = ew * 32 + lane;           // MMA row = TMEM lane
     const int slot = row / pl.mci;            // which tap of the side-by-side group (0 when mci == 128)
     const int ci = mb * pl.mci + (row - slot * pl.mci);
+    float4* stage = reinterpret_cast<float4*>(smem_raw + (smem0 - smem_u32(smem_raw))) + ew * (32 * 8);   // [32 rows][8 units]
+    float** rowdst = reinterpret_cast<float**>(smem_raw + (smem0 + 4 * 32 * 8 * 16 - smem_u32(smem_raw))) + ew * 32;
+    const int g8 = lane & 7, rsub = lane >> 3;
     if (c_end > c_begin) {
       mbar_wait(&acc_full, 0);
       tc_fence_after();
@@ -219,13 +223,32 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
           const int tap = pl.acc_tap0[acc0 + a] + slot * pl.tap_stride;
           dst = p.dW + (((int64_t)p.widx[tap] * p.G + g) * p.Cig + ci) * p.Cog + nt * pl.bn;
         }
+        if (pl.epi_transposed) rowdst[lane] = dst;
         for (int c0 = 0; c0 < pl.bn; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * pl.bn + c0, r);
           tmem_ld_wait();
-          if (valid && !(pl.dbg_flags & 1)) {
-            // posted reductions straight from the TMEM row-per-lane layout (one dW row per lane); the
-            // smem-transposed variant coalesces better but is issue-latency bound on these small tiles
+          if (pl.epi_transposed) {
+            // the slab goes through a swizzled per-warp stage (the operand staging area is free once acc_full has
+            // fired) so that 8 lanes cover one dW row's 32 channels: whole 128-byte segments per reduction
+            // instruction, half the L2 atomic operations of the row-per-lane form
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              stage[lane * 8 + (u ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]),
+                                                               __uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3]));
+            __syncwarp();
+            if (!(pl.dbg_flags & 1)) {
+#pragma unroll
+              for (int it = 0; it < 32; it += 4) {
+                const int rr = it + rsub;
+                float* d = rowdst[rr];
+                const float4 f = stage[rr * 8 + (g8 ^ (rr & 7))];
+                if (d != nullptr) red_add_v4(d + c0 + g8 * 4, f.x, f.y, f.z, f.w);
+              }
+            }
+            __syncwarp();
+          } else if (valid && !(pl.dbg_flags & 1)) {
+            // posted reductions straight from the TMEM row-per-lane layout (one dW row per lane)
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
               red_add_v4(dst + c0 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
@@ -422,10 +445,12 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   rc = tc::encode_seq_map(enc, &map_y, p.dY, p.y, p.N, p.G * p.Cog, pl.yrb / 2, pl.packed ? pl.seg_pitch : pl.kp, pl.yrb, 1);
   if (rc != CUDA_SUCCESS) { set_error("artic_tapconv_wgrad: cuTensorMapEncodeTiled(dY) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   pl.dbg_flags = tc::g_debug[13];
+  pl.epi_transposed = tc::g_debug[18] == 1 ? 0 : 1;
   pl.trace = tc::g_trace_buf;
   pl.trace_cap = tc::g_trace_cap;
   pl.launch_id = tc::g_trace_buf != nullptr ? tc::g_trace_launch++ : 0;
-  const int smem_bytes = pl.n_stages * pl.stage_bytes + 1024 + tc::WG_EPI_BYTES;
+  const int epi_need = 4 * 32 * 8 * 16 + 4 * 32 * 8;    // transpose stages + row pointers (overlaid on the operand stages)
+  const int smem_bytes = (pl.n_stages * pl.stage_bytes > epi_need ? pl.n_stages * pl.stage_bytes : epi_need) + 1024 + tc::WG_EPI_BYTES;
   tc::tapwgrad_tc_kernel<<<(unsigned)grid, tc::WG_THREADS, smem_bytes, st>>>(p, pl, map_x, map_y);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
