@@ -44,7 +44,9 @@ struct WPlan {
   int32_t a_lbo;               // leading byte offset of the A descriptor
   int32_t n_ph;                // input-stride phases (= si); X panels per stage = n_ph * nxp
   int32_t tap_stride;          // tap-index distance between side-by-side slots
-  int32_t n_acc_total, apc;    // accumulators over all CTAs of a (ci, co) tile; accumulators per CTA
+  int32_t n_acc_total, apc;    // accumulators over all CTAs of a (ci, co) tile; (max) accumulators per CTA
+  int16_t tg_begin[ARTIC_MAX_TAPS + 1];   // tap group g owns accumulators [tg_begin[g], tg_begin[g + 1]); with an input
+                                          // stride a group never mixes phases, so its CTAs load ONE phase panel of X
   long long* trace;            // SM-occupancy trace buffer or nullptr
   long long trace_cap;
   int32_t launch_id;
@@ -94,8 +96,11 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
   const int g = w / pl.n_tg;
   const int c_begin = z * pl.chunks_per_split;
   const int c_end = min(pl.n_chunks, c_begin + pl.chunks_per_split);
-  const int acc0 = tg * pl.apc;
-  const int n_acc = min(pl.apc, pl.n_acc_total - acc0);
+  const int acc0 = pl.tg_begin[tg];
+  const int n_acc = pl.tg_begin[tg + 1] - acc0;
+  uint32_t ph_mask = 0;                     // phase panels this CTA's accumulators read
+  for (int a = 0; a < n_acc; ++a) ph_mask |= 1u << pl.acc_panel[acc0 + a];
+  const int n_ph_used = __popc(ph_mask);
 
   // ---- one-time setup: zero the staging area, barriers, TMEM
   if (!(pl.dbg_flags & 2)) {
@@ -132,9 +137,9 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
           const int n = c / pl.chunks_per_seq;
           const int qc = p.q0 + (c % pl.chunks_per_seq) * pl.kp;
           mbar_expect_tx(&full[ps.stage],
-                         (uint32_t)(pl.n_ph * pl.nxp * pl.nxb * pl.boxr * pl.xrb + pl.nyp * pl.kp * pl.yrb));
+                         (uint32_t)(n_ph_used * pl.nxp * pl.nxb * pl.boxr * pl.xrb + pl.nyp * pl.kp * pl.yrb));
           for (int ph = 0; ph < pl.n_ph; ++ph)
-            for (int pn = 0; pn < pl.nxp; ++pn)
+            for (int pn = 0; pn < pl.nxp && ((ph_mask >> ph) & 1u); ++pn)
               for (int b = 0; b < pl.nxb; ++b)
                 tma_load_4d(xs + (uint32_t)(ph * pl.nxp + pn) * pl.x_panel_bytes + (uint32_t)b * pl.boxr * pl.xrb, &map_x,
                             &full[ps.stage], cx0 + pn * xch, n % p.x.n_inner, (qc + b * pl.boxr) * p.si + pl.min_off + ph,
@@ -145,11 +150,11 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
         } else {
           const int n0 = c * pl.seg_per_chunk;
           mbar_expect_tx(&full[ps.stage],
-                         (uint32_t)(pl.seg_per_chunk * pl.seg_pitch * (pl.n_ph * pl.nxp * pl.xrb + pl.nyp * pl.yrb)));
+                         (uint32_t)(pl.seg_per_chunk * pl.seg_pitch * (n_ph_used * pl.nxp * pl.xrb + pl.nyp * pl.yrb)));
           for (int j = 0; j < pl.seg_per_chunk; ++j) {
             const int n = n0 + j;  // n >= N: fully out of bounds -> zero fill
             for (int ph = 0; ph < pl.n_ph; ++ph)
-              for (int pn = 0; pn < pl.nxp; ++pn)
+              for (int pn = 0; pn < pl.nxp && ((ph_mask >> ph) & 1u); ++pn)
                 tma_load_4d(xs + (uint32_t)(ph * pl.nxp + pn) * pl.x_panel_bytes + (uint32_t)j * pl.seg_pitch * pl.xrb,
                             &map_x, &full[ps.stage], cx0 + pn * xch, n % p.x.n_inner, p.q0 * p.si + pl.min_off + ph,
                             n / p.x.n_inner);
@@ -350,8 +355,10 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   pl.tap_stride = u;
   // accumulators: for every residue class r < u, the taps r, r+u, r+2u, ... in groups of `slots`
   int n_acc_total = 0, span_rows = 0, ext = 0;
+  int class_begin[ARTIC_MAX_TAPS + 1], n_class = 0;      // accumulators of one residue class (= one phase panel) are contiguous
   for (int r = 0; r < u && r < p.ntaps; ++r) {
     const int cnt = (p.ntaps - r + u - 1) / u;
+    class_begin[n_class++] = n_acc_total;
     for (int j = 0; j * pl.slots < cnt; ++j) {
       const int t0 = r + u * (j * pl.slots);
       const int a = n_acc_total++;
@@ -365,18 +372,53 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
     }
   }
   pl.n_acc_total = n_acc_total;
+  class_begin[n_class] = n_acc_total;
+  const int class_max = n_class > 0 ? class_begin[1] - class_begin[0] : 1;   // class 0 is the largest
   // co tile: accumulators per CTA * bn <= 512 TMEM columns
   if (p.Cog % 64 != 0) pl.bn = 32;
   else if (p.Cog % 128 == 0 && n_acc_total <= 4) pl.bn = 128;
   else pl.bn = 64;
+  bool per_phase = false;
+  if (u > 1 && tc::g_debug[19] != 1) {
+    // Input stride: cutting the tap groups per phase (below) lets a CTA load ONE phase panel of X instead of all
+    // `si`, and the widest co tile that still holds one phase's accumulators in TMEM re-reads X the fewest times —
+    // but it multiplies the CTAs that stream dY.  Operand bytes per position decide.
+    int bn_pp = 0;
+    for (int bn = 256; bn >= 64; bn >>= 1)
+      if (p.Cog % bn == 0 && class_max * bn <= 512) { bn_pp = bn; break; }
+    if (bn_pp > 0) {
+      const int x_phase = (p.Cig >= 128 ? 2 : 1) * (p.Cig >= 64 ? 128 : 64);          // bytes per position of one phase panel set
+      const int tg_old = (n_acc_total + 512 / pl.bn - 1) / (512 / pl.bn);
+      int tg_pp = 0;
+      for (int c = 0; c < n_class; ++c) tg_pp += (class_begin[c + 1] - class_begin[c] + 512 / bn_pp - 1) / (512 / bn_pp);
+      const long long cost_old = (long long)(p.Cog / pl.bn) * tg_old * (si * x_phase + 2 * pl.bn);
+      const long long cost_pp = (long long)(p.Cog / bn_pp) * tg_pp * (x_phase + 2 * bn_pp);
+      if (cost_pp < cost_old) { per_phase = true; pl.bn = bn_pp; }
+    }
+  }
   if (tc::g_debug[6] > 0 && p.Cog % tc::g_debug[6] == 0) pl.bn = tc::g_debug[6];
   pl.yrb = pl.bn >= 64 ? 128 : 64;
   pl.y_layout = pl.yrb == 128 ? 2 : 4;
   pl.nyp = pl.bn >= 64 ? pl.bn / 64 : 1;
   pl.n_nt = p.Cog / pl.bn;
   const int max_acc = 512 / pl.bn;
-  pl.n_tg = (n_acc_total + max_acc - 1) / max_acc;
-  pl.apc = (n_acc_total + pl.n_tg - 1) / pl.n_tg;
+  pl.n_tg = 0;
+  pl.apc = 0;
+  if (per_phase && !(tc::g_debug[6] > 0)) {
+    for (int c = 0; c < n_class; ++c) {               // every class in equal chunks of <= max_acc accumulators
+      const int cnt = class_begin[c + 1] - class_begin[c];
+      const int parts = (cnt + max_acc - 1) / max_acc, per = (cnt + parts - 1) / parts;
+      for (int a = class_begin[c]; a < class_begin[c + 1]; a += per) {
+        pl.tg_begin[pl.n_tg++] = (int16_t)a;
+        pl.apc = max(pl.apc, min(per, class_begin[c + 1] - a));
+      }
+    }
+  } else {
+    const int n_tg = (n_acc_total + max_acc - 1) / max_acc, per = (n_acc_total + n_tg - 1) / n_tg;
+    for (int a = 0; a < n_acc_total; a += per) pl.tg_begin[pl.n_tg++] = (int16_t)a;
+    pl.apc = per;
+  }
+  pl.tg_begin[pl.n_tg] = (int16_t)n_acc_total;
   pl.n_acc = pl.apc;
   const int cols = pl.apc * pl.bn;
   pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
