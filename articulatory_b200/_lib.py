@@ -108,6 +108,7 @@ SIGNATURES = {
     "artic_stft_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _f, _f, _p, _p]),
     "artic_mel_loss_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _f, _f, _p, _p]),
     "artic_mel_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _f, _f, _p, _p]),
+    "artic_mel_loss_fwd_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _f, _f, _f, _p, _f, _p, _p]),
     "artic_add_rows": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p]),
     "artic_train_log": (C.c_int, [_p, _p, _p, _i32, _f, _f, _f, _p, _p, _p]),
     "artic_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),

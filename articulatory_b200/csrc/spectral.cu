@@ -203,14 +203,17 @@ __global__ void __launch_bounds__(512) stft_loss_bwd_kernel(const float* __restr
 // ---- mel ---------------------------------------------------------------------------
 // Mel projection of the two amplitude spectra held in (ax, ay)[0..N/2] -> extra[0..2*n_mels):
 // mel_x at extra[m], mel_y at extra[n_mels + m].  Uses extra[2*n_mels ...] as scratch.
+// rng (optional): the filters are narrow triangles — rng[2m], rng[2m+1] = first / one-past-last bin with a non-zero
+// weight in filter m; rng[2*n_mels + 2k], [.. + 1] = the filters touching bin k.
 __device__ __forceinline__ void mel_project(const float* ax, const float* ay, const float* __restrict__ melmat,
-                                            int n_bins, int n_mels, float* extra) {
+                                            int n_bins, int n_mels, float* extra, const int* __restrict__ rng = nullptr) {
   const int ngroups = max(1, (int)blockDim.x / n_mels);
   float* part = extra + 2 * n_mels;  // [ngroups][2][n_mels]
   const int gi = threadIdx.x / n_mels, m = threadIdx.x % n_mels;
   if (gi < ngroups) {
     float sx = 0.f, sy = 0.f;
-    for (int k = gi; k < n_bins; k += ngroups) {
+    const int k_lo = rng != nullptr ? __ldg(rng + 2 * m) : 0, k_hi = rng != nullptr ? __ldg(rng + 2 * m + 1) : n_bins;
+    for (int k = k_lo + gi; k < k_hi; k += ngroups) {
       const float w = __ldg(melmat + (int64_t)k * n_mels + m);
       sx = fmaf(ax[k], w, sx);
       sy = fmaf(ay[k], w, sy);
@@ -236,7 +239,10 @@ __global__ void __launch_bounds__(512) mel_loss_kernel(const float* __restrict__
                                                        FrameGeom g, const float* __restrict__ window,
                                                        const float* __restrict__ melmat, int n_mels, float eps,
                                                        float log_scale, float scale, float* __restrict__ slot,
-                                                       float* __restrict__ dx) {
+                                                       float* __restrict__ dx, const int* __restrict__ rng = nullptr,
+                                                       float loss_scale = 0.f) {
+  // BWD: dx += scale * d(sum |..|)/dx and, when slot != nullptr, slot[0] += loss_scale * sum |..| (the backward
+  // recomputes the whole forward, so the separate forward launch is redundant in a train step)
   extern __shared__ __align__(16) float smem_f[];
   Smem sm(smem_f, g.N);
   const int f = blockIdx.x, b = blockIdx.y;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(512) mel_loss_kernel(const float* __restrict__
     ay[k] = sqrtf(fmaxf(yr * yr + yi * yi, eps));
   }
   __syncthreads();
-  mel_project(ax, ay, melmat, n_bins, n_mels, sm.extra);
+  mel_project(ax, ay, melmat, n_bins, n_mels, sm.extra, rng);
   if (!BWD) {
     float s = 0.f;
     if (threadIdx.x < n_mels) {
@@ -270,21 +276,27 @@ __global__ void __launch_bounds__(512) mel_loss_kernel(const float* __restrict__
   } else {
     // d/dmel_x of scale * |log(clamp(mel_x)) - log(clamp(mel_y))| * log_scale
     float* dm = sm.extra + 2 * n_mels;  // overwrite the (now dead) partial-sum scratch
+    float labs = 0.f;
     if (threadIdx.x < n_mels) {
       const float mx = sm.extra[threadIdx.x], my = sm.extra[n_mels + threadIdx.x];
       const float lx = logf(fmaxf(mx, eps)) * log_scale;
       const float ly = logf(fmaxf(my, eps)) * log_scale;
       const float d = lx - ly;
+      labs = fabsf(d);
       float gm = (d > 0.f ? scale : (d < 0.f ? -scale : 0.f)) * log_scale / fmaxf(mx, eps);
       if (!(mx >= eps)) gm = 0.f;
       dm[threadIdx.x] = gm;
+    }
+    if (slot != nullptr) {      // uniform branch
+      labs = block_sum(labs, sm.red);
+      if (threadIdx.x == 0) atomicAdd(slot, labs * loss_scale);
     }
     __syncthreads();
     // da[k] = sum_m dm[m] * melmat[k][m].  One WARP per bin (lanes along the mel index: coalesced rows, a
     // shuffle reduction) when the scratch area can hold da[]; a thread per bin walking its own row touches
     // 32 different cache lines per load instruction and made this loop the bulk of the kernel.
     const int ngroups = max(1, (int)blockDim.x / n_mels);
-    const bool warp_rows = 2 * ngroups * n_mels >= n_mels + n_bins;
+    const bool warp_rows = rng == nullptr && 2 * ngroups * n_mels >= n_mels + n_bins;
     float* da_s = dm + n_mels;
     if (warp_rows) {
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -304,6 +316,10 @@ __global__ void __launch_bounds__(512) mel_loss_kernel(const float* __restrict__
       float da = 0.f;
       if (warp_rows) {
         da = da_s[k];
+      } else if (rng != nullptr) {
+        const float* mrow = melmat + (int64_t)k * n_mels;
+        const int m_hi = __ldg(rng + 2 * n_mels + 2 * k + 1);
+        for (int m = __ldg(rng + 2 * n_mels + 2 * k); m < m_hi; ++m) da = fmaf(dm[m], __ldg(mrow + m), da);
       } else {
         const float* mrow = melmat + (int64_t)k * n_mels;
         for (int m = 0; m < n_mels; ++m) da = fmaf(dm[m], __ldg(mrow + m), da);
@@ -400,6 +416,25 @@ extern "C" int artic_mel_loss_fwd(const float* x, const float* y, int32_t B, int
   dim3 grid(1 + T / hop, B);
   mel_loss_kernel<false><<<grid, fft_threads(n_fft), sb, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, y, g, window, melmat, n_mels, eps, log_scale, scale, slot, nullptr);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}
+
+extern "C" int artic_mel_loss_fwd_bwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft, int32_t hop,
+                                      int32_t win_length, const float* window, const float* melmat,
+                                      const int32_t* mel_ranges, int32_t n_mels, float eps, float log_scale,
+                                      float loss_scale, float* slot, float grad_scale, float* dx, void* stream) {
+  ARTIC_CHECK_ARG(x && y && window && melmat && dx, "null pointer");
+  ARTIC_CHECK_ARG(check_geom(B, T, n_fft, hop, win_length), "unsupported STFT geometry");
+  ARTIC_CHECK_ARG(n_mels >= 1 && n_mels <= fft_threads(n_fft), "n_mels out of range");
+  if (B == 0) return ARTIC_OK;
+  FrameGeom g{T, n_fft, hop, win_length, (n_fft - win_length) / 2};
+  const size_t sb = smem_bytes(n_fft, n_mels);
+  int rc = ensure_smem(mel_loss_kernel<true>, sb);
+  if (rc) return rc;
+  dim3 grid(1 + T / hop, B);
+  mel_loss_kernel<true><<<grid, fft_threads(n_fft), sb, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, y, g, window, melmat, n_mels, eps, log_scale, grad_scale, slot, dx, mel_ranges, loss_scale);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
 }

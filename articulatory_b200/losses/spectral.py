@@ -120,6 +120,14 @@ class MelSpectrogramLoss(torch.nn.Module):
         self.register_buffer("window", w.float(), persistent=False)
         melmat = slaney_mel_basis(fs, fft_size, num_mels, fmin, fmax)            # (mels, bins)
         self.register_buffer("melmat", torch.from_numpy(np.ascontiguousarray(melmat.T)).float())  # (bins, mels)
+        # non-zero ranges of the (triangular, ~97 % zero) filters: per filter the bins, per bin the filters
+        nz = np.asarray(melmat) != 0
+        rng = []
+        for rows in (nz, nz.T):
+            for r in rows:
+                idx = np.nonzero(r)[0]
+                rng += [int(idx[0]), int(idx[-1]) + 1] if idx.size else [0, 0]
+        self.register_buffer("mel_ranges", torch.tensor(rng, dtype=torch.int32), persistent=False)
 
     def numel(self, B, T):
         return B * self.num_mels * (1 + T // self.hop)
@@ -133,6 +141,13 @@ class MelSpectrogramLoss(torch.nn.Module):
         B, T = x.shape
         call("artic_mel_loss_bwd", ptr(x), ptr(y), B, T, self.fft_size, self.hop, self.win_length,
              ptr(self.window), ptr(self.melmat), self.num_mels, self.eps, self.log_scale, float(scale), ptr(dx))
+
+    def loss_and_grad(self, x, y, loss_scale, slot, grad_scale, dx):
+        """slot[0] += loss_scale * sum |..| and dx += grad_scale * d(sum |..|)/dx in one launch."""
+        B, T = x.shape
+        call("artic_mel_loss_fwd_bwd", ptr(x), ptr(y), B, T, self.fft_size, self.hop, self.win_length,
+             ptr(self.window), ptr(self.melmat), ptr(self.mel_ranges), self.num_mels, self.eps, self.log_scale,
+             float(loss_scale), ptr(slot), float(grad_scale), ptr(dx))
 
     def forward(self, y_hat, y):
         return _MelFn.apply(y_hat, y, self)

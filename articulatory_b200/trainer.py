@@ -143,8 +143,7 @@ class TrainStep:
             if self.use_mel:                                                  # :313-316
                 def mel_job():
                     n = self.mel.numel(B, T)
-                    self.mel.accumulate(y2d, t2d, 1.0 / n, self.slots[_MEL:])
-                    self.mel.backward_into(y2d, t2d, self.l_aux * inv_w / n, dy)
+                    self.mel.loss_and_grad(y2d, t2d, 1.0 / n, self.slots[_MEL:], self.l_aux * inv_w / n, dy)
                 jobs.append(mel_job)
             if jobs:
                 fork_join(jobs)

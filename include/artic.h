@@ -290,6 +290,15 @@ int artic_mel_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, int
                        int32_t win_length, const float* window, const float* melmat, int32_t n_mels,
                        float eps, float log_scale, float scale, float* dx, void* stream);
 
+/* Loss and gradient in ONE launch (the backward recomputes the forward): slot[0] += loss_scale * sum |..| when
+ * slot != NULL, dx += grad_scale * d(sum |..|)/dx.  mel_ranges (optional, int32 [2 * n_mels + 2 * n_bins], device):
+ * [2m], [2m+1] = first / one-past-last bin with a non-zero weight in filter m, then per bin k the first /
+ * one-past-last filter touching it — the triangular filters make melmat ~97 % zeros. */
+int artic_mel_loss_fwd_bwd(const float* x, const float* y, int32_t B, int32_t T, int32_t n_fft, int32_t hop,
+                           int32_t win_length, const float* window, const float* melmat,
+                           const int32_t* mel_ranges, int32_t n_mels, float eps, float log_scale,
+                           float loss_scale, float* slot, float grad_scale, float* dx, void* stream);
+
 /* ---- optimiser (torch.optim.Adam + MultiStepLR, bin/train.py:372-383,424-435,1750-1789) ---- */
 
 /* Device-resident hyper-parameters so a captured graph can be replayed across steps. */

@@ -262,6 +262,32 @@ def test_mr_stft_and_mel_modules(golden):
     assert rel_err(y_.grad.cpu(), golden["mel"]["grad"]) < 1e-3
 
 
+def test_mel_loss_and_grad_fused(golden):
+    """artic_mel_loss_fwd_bwd (one launch, sparse filter ranges) == the golden loss and gradient of the
+    reference MelSpectrogramLoss (tests/golden/make_golden.py), and the ranges cover every non-zero weight."""
+    from articulatory_b200.losses import MelSpectrogramLoss
+    from oracle import torch_oracle as O
+    mod = MelSpectrogramLoss(**O.E2W_MEL_LOSS_PARAMS).to(DEV)
+    mm = mod.melmat.cpu().numpy()                                  # (bins, mels)
+    rng = mod.mel_ranges.cpu().numpy()
+    n_bins, n_mels = mm.shape
+    for m in range(n_mels):
+        lo, hi = rng[2 * m], rng[2 * m + 1]
+        assert not mm[:lo, m].any() and not mm[hi:, m].any()
+    for k in range(n_bins):
+        lo, hi = rng[2 * n_mels + 2 * k], rng[2 * n_mels + 2 * k + 1]
+        assert not mm[k, :lo].any() and not mm[k, hi:].any()
+    x = golden["g_out"].to(DEV).reshape(golden["g_out"].shape[0], -1).contiguous()
+    y = golden["batch"]["y"].to(DEV).reshape(x.shape).contiguous()
+    slot = torch.zeros(1, device=DEV)
+    dx = torch.zeros_like(x)
+    n = mod.numel(*x.shape)
+    mod.loss_and_grad(x, y, 1.0 / n, slot, 1.0 / n, dx)
+    torch.cuda.synchronize()
+    assert abs(slot.item() - float(golden["mel"]["loss"])) < 1e-4 * float(golden["mel"]["loss"])
+    assert rel_err(dx.cpu().view_as(golden["mel"]["grad"]), golden["mel"]["grad"]) < 1e-3
+
+
 def test_tc_conv_with_unaligned_bias_and_views():
     """Parameters live in ONE flat buffer in the train step (FusedAdam), so bias pointers are only 4-byte
     aligned: the tensor-core epilogue must not assume 16-byte aligned bias (regression: misaligned address)."""

@@ -1,3 +1,2 @@
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-250
-SWEEP_SHAPES="21-23,25-27,29-32" timeout 300 python tools/tc_sweep.py wgrad 2>&1 | grep wgrad | cut -c1-50

@@ -73,8 +73,7 @@ def main():
         if ts.use_mel:
             def mel_job():
                 n = ts.mel.numel(B, T)
-                ts.mel.accumulate(y2d, t2d, 1.0 / n, ts.slots[0:])
-                ts.mel.backward_into(y2d, t2d, 1.0 / n, dy)
+                ts.mel.loss_and_grad(y2d, t2d, 1.0 / n, ts.slots[0:], 1.0 / n, dy)
             jobs.append(mel_job)
         fork_join(jobs)
 
