@@ -8,6 +8,7 @@
 //     dW[t][co] = sum_{n,q} x[n, q*si + off_t] * dY[n, q, co]; threads own output channels
 //     (coalesced dY rows), the taps live in registers, one atomicAdd per (tap, co) per CTA.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace artic {
 
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_kernel(const __grid_constant
 constexpr int C1V_ROWS = 256;   // positions per CTA of the vector kernel (twice the CTAs of the scalar ones)
 template <typename T>
 __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_constant__ artic_tapwgrad_t p, int tap0,
-                                                               int min_off, int span) {
+                                                               int min_off, int span, int dbg) {
   __shared__ float xs[C1_SMEM];
   __shared__ float red[256][17];
   const int tpr = p.Cog >> 3, rpp = 256 / tpr;
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
   const int yo = p.yoff[tap0];
-  for (int q = qa + rl; q < qb; q += 4 * rpp) {
+  for (int q = qa + rl; q < qb && !(dbg & 2); q += 4 * rpp) {
     uint4 u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
         if (t + tt < nt) {
           float sum = 0.f;
           for (int r = 0; r < rpp; ++r) sum += red[r * tpr + (c >> 3)][8 * tt + (c & 7)];
-          atomicAdd(p.dW + (int64_t)p.widx[tap0 + t + tt] * p.Cog + c, sum);   // [K][G=1][Cig=1][Cog]
+          if (!(dbg & 1)) atomicAdd(p.dW + (int64_t)p.widx[tap0 + t + tt] * p.Cog + c, sum);   // [K][G=1][Cig=1][Cog]
         }
       }
     }
@@ -554,8 +555,8 @@ int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
                      (reinterpret_cast<uintptr_t>(p.dY) & 15) == 0;
     if (vec) {
       dim3 vgrid((unsigned)((p.nq + C1V_ROWS - 1) / C1V_ROWS), grid.y, 1);
-      if (xb) tapwgrad_ci1_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span);
-      else tapwgrad_ci1_vec_kernel<float><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span);
+      if (xb) tapwgrad_ci1_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span, tc::g_debug[20]);
+      else tapwgrad_ci1_vec_kernel<float><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span, tc::g_debug[20]);
     } else if (ci1) ARTIC_C1_LAUNCH(tapwgrad_ci1_kernel);
     else ARTIC_C1_LAUNCH(tapwgrad_co1_kernel);
 #undef ARTIC_C1_LAUNCH

@@ -1,2 +1,3 @@
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-250
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-250
+ARTIC_DEFER_D=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-250
