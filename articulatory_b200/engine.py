@@ -472,6 +472,26 @@ def _zero_grads_like(layers: List[ConvLayer]) -> Dict[str, torch.Tensor]:
 # --------------------------------------------------------------------------- #
 # generator                                                                   #
 # --------------------------------------------------------------------------- #
+import contextlib
+
+
+@contextlib.contextmanager
+def planner_objective(sm_time_pct: int):
+    """Tile-planner objective for the launches enqueued inside: percentage of the SM-time term against
+    stand-alone latency (artic_debug_set key 15; 0 restores the default = 100).  The discriminator runs eight
+    chains at once and wants small SM time per launch; the generator has three, so part of the machine is
+    idle anyway and latency counts."""
+    lib = _lib.load()
+    lib.artic_debug_set(15, int(sm_time_pct))
+    try:
+        yield
+    finally:
+        lib.artic_debug_set(15, 0)
+
+
+_G_OBJECTIVE = int(_os.environ.get("ARTIC_G_OBJECTIVE", "60"))   # measured: 100 -> 12.93, 60 -> 12.82, 30 -> 13.15 ms
+
+
 class GeneratorEngine:
     """HiFiGANGenerator.forward (reference models/hifigan.py:198-239) and its backward."""
 
@@ -541,6 +561,10 @@ class GeneratorEngine:
     # ---- forward -------------------------------------------------------------
     def forward(self, c: torch.Tensor, ar: Optional[torch.Tensor], save=True):
         """c (B, Cc, T') fp32 channel-first, ar (B, 1, ar_input) fp32 -> ((B, 1, T) fp32, tape)."""
+        with planner_objective(_G_OBJECTIVE):
+            return self._forward(c, ar, save)
+
+    def _forward(self, c, ar, save):
         _lib.require_cuda(c, "c")
         assert self._prepped, "call prep_weights() after binding / updating parameters"
         L, code, dev, slope = self.layers, self.code, c.device, self.slope
@@ -653,6 +677,10 @@ class GeneratorEngine:
     def backward(self, tape, dy: torch.Tensor, grads: Dict[str, torch.Tensor]):
         """dy: (B, C_out, T) fp32 gradient of the waveform.  Accumulates parameter gradients
         into ``grads`` (name -> fp32 tensor shaped like the parameter)."""
+        with planner_objective(_G_OBJECTIVE):
+            return self._backward(tape, dy, grads)
+
+    def _backward(self, tape, dy, grads):
         L, code, slope = self.layers, self.code, self.slope
         B = tape["B"]
         dev = dy.device

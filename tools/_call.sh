@@ -1,5 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_dp.py -m gpu -q 2>&1 | tail -3 > gpurun_out/r1_pytest_dp2_62.log
-tail -2 gpurun_out/r1_pytest_dp2_62.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_2gpu_62.log 2>&1
-tail -1 gpurun_out/r1_bench_2gpu_62.log | cut -c1-300
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-200
+for v in 100 60 30 -1; do
+ARTIC_G_OBJECTIVE=$v timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('G objective $v', d['ms_per_step'])" | tee -a gpurun_out/r1_gobj_64.log
+done
