@@ -26,10 +26,11 @@ from .optim import FusedAdam
 
 import os as _os
 #: ARTIC_BG="prep,spectral,order": which branches run on low-priority streams / in which order (see
-#: engine.fork_join).  Measured on B200 (gpurun_out/r1_bg_45.log): every variant lands within 0.1 ms of the
-#: default (nothing in the background) — the step is bound by total SM time, not by the order the scheduler
-#: picks — so the default keeps everything at one priority.
-_BG = set(filter(None, _os.environ.get("ARTIC_BG", "").split(",")))
+#: engine.fork_join).  Measured on B200, 20-step runs, repeatable to +-0.02 ms (gpurun_out/r1_bg_66.log):
+#: none 12.87, order 12.81 / 12.85, order+spectral 12.75 ms — the discriminator chain is enqueued before the
+#: spectral losses and those run at low priority, so the ~1600 frame-FFT blocks no longer sit in front of the
+#: chain's first (tiny) kernels.  "prep" (weight re-materialisation in the background) does not pay.
+_BG = set(filter(None, _os.environ.get("ARTIC_BG", "order,spectral").split(",")))
 
 LOG_KEYS = ["train/spectral_convergence_loss", "train/log_stft_magnitude_loss", "train/mel_loss",
             "train/adversarial_loss", "train/feature_matching_loss", "train/generator_loss",
