@@ -29,8 +29,9 @@ import os as _os
 #: engine.fork_join).  Measured on B200, 20-step runs, repeatable to +-0.02 ms (gpurun_out/r1_bg_66.log):
 #: none 12.87, order 12.81 / 12.85, order+spectral 12.75 ms — the discriminator chain is enqueued before the
 #: spectral losses and those run at low priority, so the ~1600 frame-FFT blocks no longer sit in front of the
-#: chain's first (tiny) kernels.  "prep" (weight re-materialisation in the background) does not pay.
-_BG = set(filter(None, _os.environ.get("ARTIC_BG", "order,spectral").split(",")))
+#: chain's first (tiny) kernels.  "order2" (12.70): the generator forward is enqueued ahead of the big-grid weight
+#: prep / gradient clears it overlaps with.  "prep" (weight re-materialisation in the background) does not pay.
+_BG = set(filter(None, _os.environ.get("ARTIC_BG", "order,spectral,order2").split(",")))
 
 LOG_KEYS = ["train/spectral_convergence_loss", "train/log_stft_magnitude_loss", "train/mel_loss",
             "train/adversarial_loss", "train/feature_matching_loss", "train/generator_loss",
@@ -123,9 +124,13 @@ class TrainStep:
         inv_w = 1.0 / self.world
         # the discriminator's weights (updated at the end of the previous step) are re-materialised on a
         # side stream while the generator forward runs
-        (y_, tapeG), engD = fork_join([lambda: engG.forward(x, ar, save=True),
-                                       lambda: D._ensure_ready() if train_d_active else None],
-                                      background=(1,) if "prep" in _BG else ())
+        if "order2" in _BG:      # generator forward enqueued first (side stream), the big-grid weight prep after it
+            engD, (y_, tapeG) = fork_join([lambda: D._ensure_ready() if train_d_active else None,
+                                           lambda: engG.forward(x, ar, save=True)])
+        else:
+            (y_, tapeG), engD = fork_join([lambda: engG.forward(x, ar, save=True),
+                                           lambda: D._ensure_ready() if train_d_active else None],
+                                          background=(1,) if "prep" in _BG else ())
         y2d, t2d = y_.reshape(B, T), y.reshape(B, T)
         dy = torch.zeros((B, 1, T), dtype=torch.float32, device=self.dev)
         self.slots.zero_()
@@ -216,7 +221,10 @@ class TrainStep:
             self.optD.zero_grad()
             engD.wset.zero()
 
-        (y_, _), _ = fork_join([lambda: engG.forward(x, ar, save=False), clear_d_grads])   # bin/train.py:390-400
+        if "order2" in _BG:
+            _, (y_, _) = fork_join([clear_d_grads, lambda: engG.forward(x, ar, save=False)])
+        else:
+            (y_, _), _ = fork_join([lambda: engG.forward(x, ar, save=False), clear_d_grads])   # bin/train.py:390-400
         if tape2 is None:
             _, tape2 = engD.forward(self._disc_input(ar, (y_, y)), save=True)
         else:
