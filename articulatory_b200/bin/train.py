@@ -52,11 +52,38 @@ def _load_items(dumpdir, config):
 class Trainer(object):
     """Epoch / step loop, logging and checkpointing around ``TrainStep`` (reference Trainer, bin/train.py:60-780)."""
 
-    def __init__(self, steps, epochs, items, collater, model, step_fn, config, dp, device):
+    def __init__(self, steps, epochs, items, collater, model, step_fn, config, dp, device, dev_items=None):
         self.steps, self.epochs = steps, epochs
         self.items, self.collater, self.model, self.ts = items, collater, model, step_fn
         self.config, self.dp, self.device = config, dp, device
+        self.dev_items = dev_items or []
+        self.best_mel_loss = float("inf")
         self.finish_train = False
+
+    def eval_epoch(self):
+        """Reference Trainer._eval_epoch (bin/train.py:605-648): average the eval losses over the dev set, keep the
+        checkpoint with the best mel loss (best_mel_ckpt.pkl + best_mel_step.txt).  Returns the averages."""
+        bs = self.config["batch_size"]
+        n = 0
+        for lo in range(0, len(self.dev_items) - bs + 1, bs):
+            batch = self.collater(self.dev_items[lo:lo + bs])
+            if batch["y"].shape[0] != bs:
+                continue
+            self.ts.eval_step(batch["x"][0], batch["y"], batch["ar"])
+            n += 1
+        if n == 0:
+            return {}
+        logs = self.ts.read_eval_logs(n)
+        if self.dp.rank == 0:
+            logging.info(f"(Steps: {self.steps}) Finished evaluation ({n} steps per epoch).")
+            for k, v in logs.items():
+                logging.info(f"(Steps: {self.steps}) {k} = {v:.4f}.")
+            if logs["eval/mel_loss"] < self.best_mel_loss:
+                with open(os.path.join(self.config["outdir"], "best_mel_step.txt"), "w+") as ouf:
+                    ouf.write("%d\n" % self.steps)
+                self.save_checkpoint(os.path.join(self.config["outdir"], "best_mel_ckpt.pkl"))
+                self.best_mel_loss = logs["eval/mel_loss"]
+        return logs
 
     def save_checkpoint(self, path):
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
@@ -97,6 +124,8 @@ class Trainer(object):
                     if self.dp.rank == 0:
                         for k, v in zip(LOG_KEYS, vals):
                             logging.info(f"(Steps: {self.steps}) {k} = {v / n:.4f}.")
+                if self.dev_items and self.steps % self.config.get("eval_interval_steps", 1000) == 0:
+                    self.eval_epoch()                                          # reference :766-768
                 if self.steps % self.config["save_interval_steps"] == 0 and self.dp.rank == 0:
                     self.save_checkpoint(os.path.join(self.config["outdir"], f"checkpoint-{self.steps}steps.pkl"))
                 if self.steps >= self.config["train_max_steps"]:
@@ -154,6 +183,9 @@ def main(argv=None):
     else:
         raise ValueError("Please specify --train-dumpdir or --synthetic.")
     logging.info(f"The number of training files = {len(items)}.")
+    dev_items = _load_items(args.dev_dumpdir, config) if args.dev_dumpdir is not None else \
+        (synthetic_utterances(max(config["batch_size"], 2), frames, n_feats, hop, seed=10_000 + dp.rank) if args.synthetic else [])
+    logging.info(f"The number of development files = {len(dev_items)}.")
     collater = SpeechCollater(batch_max_steps=config["batch_max_steps"], hop_size=config["hop_size"],
                               aux_context_window=config["generator_params"].get("aux_context_window", 0),
                               dataset_mode=config.get("dataset_mode", "a2w"), config=config)
@@ -167,7 +199,7 @@ def main(argv=None):
     dp.broadcast_parameters(model["generator"], model["discriminator"])
     ts = TrainStep(model["generator"], model["discriminator"], config, device, world_size=dp.world,
                    all_reduce=dp.all_reduce if dp.world > 1 else None)
-    trainer = Trainer(0, 0, items, collater, model, ts, config, dp, device)
+    trainer = Trainer(0, 0, items, collater, model, ts, config, dp, device, dev_items=dev_items)
     if args.pretrain:
         trainer.load_checkpoint(args.pretrain, load_only_params=True)
     if args.resume:

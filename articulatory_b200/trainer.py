@@ -345,6 +345,52 @@ class TrainStep:
         self.G.mark_weights_dirty()
         self.D.mark_weights_dirty()
 
+    # ------------------------------------------------------------------------------
+    EVAL_KEYS = [k.replace("train/", "eval/") for k in LOG_KEYS]
+
+    @torch.no_grad()
+    def eval_step(self, x, y, ar):
+        """One evaluation step (reference Trainer._eval_step, bin/train.py:470-603): the nine losses of the train
+        step on a dev batch, no gradients, no updates.  Returns a dict with the reference's ``eval/*`` keys
+        (one host read); ``eval_running`` accumulates them for ``_eval_epoch``-style averaging.  D(real) and
+        D(fake) are evaluated once and feed both the generator-side and the discriminator-side terms (the
+        reference evaluates each twice, :572-587, with identical results under no_grad)."""
+        x, y, ar = (t.to(self.dev, non_blocking=True).float().contiguous() for t in (x, y, ar))
+        self._ensure_numel(y.shape[0], y.shape[2])
+        if not hasattr(self, "eval_vals"):
+            self.eval_vals = torch.zeros(9, dtype=torch.float32, device=self.dev)
+            self.eval_running = torch.zeros(9, dtype=torch.float32, device=self.dev)
+        engG, engD = self.G._ensure_ready(), self.D._ensure_ready()
+        B, _, T = y.shape
+        y_, _ = engG.forward(x, ar, save=False)
+        y2d, t2d = y_.reshape(B, T), y.reshape(B, T)
+        self.slots.zero_()
+        self.stft_sums.zero_()
+        if self.use_stft:                                                     # :515-520
+            for r, res in enumerate(self.stft.resolutions):
+                res.forward(y2d, t2d, self.stft_sums[r])
+        if self.use_mel:                                                      # :536-540
+            self.mel.accumulate(y2d, t2d, 1.0 / self.mel.numel(B, T), self.slots[_MEL:])
+        outs2, _ = engD.forward(self._disc_input(ar, (y_, y)), save=False)    # :572-587, [fake | real]
+        outs_f = [[slice_seq(o, 0, B) for o in lst] for lst in outs2]
+        outs_r = [[slice_seq(o, B, 2 * B) for o in lst] for lst in outs2]
+        self._adv_seed(outs_f, 1.0, _ADV, 0.0)                                # gen_adv(p_)
+        for lf, lr in zip(outs_f, outs_r):                                    # feat_match(p_, p)
+            for a, b in zip(lf[:-1], lr[:-1]):
+                call("artic_l1_sum", ptr(a.t), ptr(b.t), a.numel(), 1.0 / a.numel(), ptr(self.slots[_FM:]), a.code)
+        self._adv_seed(outs_r, 1.0, _REAL, 0.0)                               # dis_adv(p_, p)
+        self._adv_seed(outs_f, 0.0, _FAKE, 0.0)
+        call("artic_train_log", ptr(self.slots), ptr(self.stft_sums), ptr(self.stft_numel), self.R, self.l_aux,
+             self.l_adv, self.l_fm, ptr(self.eval_vals), ptr(self.eval_running))
+        return dict(zip(self.EVAL_KEYS, self.eval_vals.cpu().tolist()))
+
+    def read_eval_logs(self, n_steps, reset=True):
+        """Averages of the accumulated eval losses over ``n_steps`` eval steps (bin/train.py:624-629)."""
+        vals = (self.eval_running / max(n_steps, 1)).cpu().tolist()
+        if reset:
+            self.eval_running.zero_()
+        return dict(zip(self.EVAL_KEYS, vals))
+
     def read_logs(self, reset=True):
         """Device -> host read of the running sums (the reference's total_train_loss)."""
         vals = self.running.cpu().tolist()

@@ -126,6 +126,39 @@ def test_train_steps_golden(golden, use_graph):
     assert all(map(lambda v: v == v and abs(v) < 1e6, ts.last_values().values()))
 
 
+def test_eval_step_vs_oracle(golden):
+    """TrainStep.eval_step == the reference Trainer._eval_step arithmetic (bin/train.py:470-603), restated with the
+    oracle's functions on the golden weights / batch: nine eval/* losses, no parameter change."""
+    from articulatory_b200.trainer import TrainStep
+    from oracle import torch_oracle as O
+    G, D = _build(golden)
+    cfg = _train_config(golden)
+    ts = TrainStep(G, D, cfg, DEV)
+    b = golden["batch"]
+    before = {k: v.detach().clone() for k, v in list(G.state_dict().items()) + list(D.state_dict().items())}
+    got = ts.eval_step(b["x"].to(DEV), b["y"].to(DEV), b["ar"].to(DEV))
+    gsd, dsd = golden["gsd"], golden["dsd"]
+    with torch.no_grad():
+        y_ = O.generator_forward(gsd, golden["generator_params"], b["x"], b["ar"])
+        sc, mag = O.mr_stft_loss(y_.squeeze(1), b["y"].squeeze(1))
+        mel = O.mel_loss(y_, b["y"], **O.E2W_MEL_LOSS_PARAMS)
+        p_ = O.discriminator_forward(dsd, golden["discriminator_params"], torch.cat([b["ar"], y_], dim=2))
+        p = O.discriminator_forward(dsd, golden["discriminator_params"], torch.cat([b["ar"], b["y"]], dim=2))
+        adv = O.generator_adv_loss(p_)
+        fm = O.feat_match_loss(p_, p)
+        real, fake = O.discriminator_adv_loss(p_, p)
+        gen = 45.0 * (sc + mag + mel) + 1.0 * adv + 1.0 * 2.0 * fm
+    want = {"eval/spectral_convergence_loss": sc, "eval/log_stft_magnitude_loss": mag, "eval/mel_loss": mel,
+            "eval/adversarial_loss": adv, "eval/feature_matching_loss": fm, "eval/generator_loss": gen,
+            "eval/real_loss": real, "eval/fake_loss": fake, "eval/discriminator_loss": real + fake}
+    for k, v in want.items():
+        assert abs(got[k] - float(v)) <= 1e-3 * abs(float(v)), (k, got[k], float(v))
+    after = dict(list(G.state_dict().items()) + list(D.state_dict().items()))
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    avg = ts.read_eval_logs(1)
+    assert abs(avg["eval/mel_loss"] - got["eval/mel_loss"]) < 1e-6
+
+
 def test_full_width_generator_and_discriminator_vs_oracle():
     """e2w_hifigan.yaml widths, B=2: waveform and all 54 discriminator outputs vs the oracle."""
     from articulatory_b200 import models as M
