@@ -246,12 +246,13 @@ __global__ void __launch_bounds__(256) tapconv_ci1_kernel(const __grid_constant_
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     if (NT > 0) {
       const float* xp = xs + (q - qa) * p.si;
+      float xv[NT > 0 ? NT : 1];
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const float xv = xp[offr[t]];               // padded taps: weight 0, offset 0
+      for (int t = 0; t < NT; ++t) xv[t] = xp[offr[t]];      // all tap samples in flight first; padded taps: weight 0, offset 0
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, wr[t][i], acc[i]);
-      }
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv[t], wr[t][i], acc[i]);
     } else {
       const int xb = (q - qa) * p.si - min_off;
       for (int t = 0; t < p.ntaps; ++t) {
@@ -368,8 +369,13 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
   const int yo = p.yoff[tap0];
-  for (int q = qa + rl; q < qb && !(dbg & 2); q += 4 * rpp) {
-    uint4 u[4];
+  // tap offsets in registers (padded taps read offset 0 and are skipped), and the dY rows double-buffered:
+  // the next four row loads are in flight while the current four are consumed (eight warps per SM cannot
+  // hide a global-load round trip per batch otherwise; the loop was 125 of the kernel's 174 us)
+  int offr[C1_TAPS];
+#pragma unroll
+  for (int t = 0; t < C1_TAPS; ++t) offr[t] = t < nt ? p.off[tap0 + t] - min_off : 0;
+  auto load4 = [&](uint4 (&u)[4], int q) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int qq = q + j * rpp;
@@ -378,6 +384,11 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
                  ? __ldg(reinterpret_cast<const uint4*>(dY + (int64_t)ypos * p.y.s_row) + cg)
                  : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 u[4], un[4];
+  if (!(dbg & 2)) load4(u, qa + rl);
+  for (int q = qa + rl; q < qb && !(dbg & 2); q += 4 * rpp) {
+    load4(un, q + 4 * rpp);                      // rows past qb load zeros
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int qq = q + j * rpp;
@@ -389,16 +400,20 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
         dy[2 * i] = __uint_as_float(w[i] << 16);
         dy[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
       }
-      const int xb = (qq - qa) * p.si - min_off;
+      // all tap samples first (16 independent shared-memory loads in flight: with two warps per scheduler a
+      // load -> 8 dependent FMAs chain per tap stalls on the shared-memory latency), padded taps read offset 0
+      // into accumulators that are never written out
+      const float* xp = xs + (qq - qa) * p.si;
+      float xv[C1_TAPS];
 #pragma unroll
-      for (int t = 0; t < C1_TAPS; ++t) {
-        if (t < nt) {
-          const float xv = xs[xb + p.off[tap0 + t]];
+      for (int t = 0; t < C1_TAPS; ++t) xv[t] = xp[offr[t]];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(xv, dy[i], acc[t][i]);
-        }
-      }
+      for (int t = 0; t < C1_TAPS; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(xv[t], dy[i], acc[t][i]);
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = un[j];
   }
 #pragma unroll
   for (int t = 0; t < C1_TAPS; t += 2) {       // two taps per reduction round
