@@ -1,3 +1,2 @@
-timeout 200 python tools/c1_bench.py 2>&1 | tail -3
-timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-220
+timeout 600 python bench.py > gpurun_out/r1_bench_73.log 2>&1
+tail -1 gpurun_out/r1_bench_73.log | cut -c1-260
