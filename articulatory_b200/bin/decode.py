@@ -53,6 +53,14 @@ def _load_feature_files(args, config):
     items = []
     if args.dumpdir is not None:
         fmt = config.get("format", "npy")
+        parts = args.dumpdir.split("/")
+        if len(parts) > 1 and os.path.exists(os.path.join("data", parts[1], "feats.scp")):
+            # the recipe's layout: utterance ids from the dump, features from data/<stage>/feats.scp
+            # (reference ArtDataset, bin/decode.py:221-236)
+            from articulatory_b200.datasets import ArtDataset
+            ds = ArtDataset(args.dumpdir, mel_query="*-feats.npy" if fmt == "npy" else "*.h5", return_utt_id=True,
+                            transform=config.get("transform"))
+            return [ds[i] for i in range(len(ds))]
         if fmt == "npy":
             for path in sorted(glob.glob(os.path.join(args.dumpdir, "**", "*-feats.npy"), recursive=True)):
                 items.append((os.path.basename(path).replace("-feats.npy", ""), np.load(path)))

@@ -14,7 +14,6 @@ npy`` dump layout) or ``*.h5`` with ``wave`` / ``feats`` datasets when h5py is i
 ``--synthetic N`` trains on N generated MNGU0-shaped utterances (no dataset needed).
 """
 import argparse
-import glob
 import logging
 import os
 import sys
@@ -31,21 +30,30 @@ from articulatory_b200.trainer import LOG_KEYS, TrainStep
 
 
 def _load_items(dumpdir, config):
-    """[{'audio': (T,), 'art': (T', C)}] from a dump directory (reference SpeechDataset, npy / hdf5 layouts)."""
-    items = []
+    """[{'audio': (T,), 'art': (T', C)}] from a dump directory.  With the recipe's ``data/<stage>/feats.scp`` in the
+    working directory this is the reference ``SpeechDataset`` (wave from the dump, articulatory features from the
+    scp, bin/train.py:1571-1582); without it, ``*-wave.npy`` / ``*-feats.npy`` (or ``wave`` / ``feats`` of each
+    ``*.h5``) pairs of the dump itself."""
+    from articulatory_b200.datasets import SpeechDataset, find_files, read_hdf5
     fmt = config.get("format", "hdf5")
-    if fmt == "npy":
-        for wav in sorted(glob.glob(os.path.join(dumpdir, "**", "*-wave.npy"), recursive=True)):
-            feats = wav.replace("-wave.npy", "-feats.npy")
-            if os.path.exists(feats):
-                items.append({"audio": np.load(wav).astype(np.float32), "art": np.load(feats).astype(np.float32)})
-    elif fmt == "hdf5":
-        import h5py  # optional dependency, as in the reference
-        for path in sorted(glob.glob(os.path.join(dumpdir, "**", "*.h5"), recursive=True)):
-            with h5py.File(path, "r") as f:
-                items.append({"audio": f["wave"][()].astype(np.float32), "art": f["feats"][()].astype(np.float32)})
+    if fmt == "hdf5":
+        audio_query, mel_query = "*.h5", "*.h5"
+        audio_load_fn, mel_load_fn = (lambda x: read_hdf5(x, "wave")), (lambda x: read_hdf5(x, "feats"))
+    elif fmt == "npy":
+        audio_query, mel_query = "*-wave.npy", "*-feats.npy"
+        audio_load_fn = mel_load_fn = np.load
     else:
         raise ValueError("support only hdf5 or npy format.")
+    parts = dumpdir.split("/")
+    if len(parts) > 1 and os.path.exists(os.path.join("data", parts[1], "feats.scp")):
+        ds = SpeechDataset(dumpdir, audio_query=audio_query, mel_query=mel_query, audio_load_fn=audio_load_fn,
+                           mel_load_fn=mel_load_fn, dataset_mode=config.get("dataset_mode", "a2w"))
+        return [{"audio": np.asarray(it["audio"], dtype=np.float32), "art": np.asarray(it["art"], dtype=np.float32)}
+                for it in (ds[i] for i in range(len(ds)))]
+    items = []
+    for wav, feats in zip(sorted(find_files(dumpdir, audio_query)), sorted(find_files(dumpdir, mel_query))):
+        items.append({"audio": np.asarray(audio_load_fn(wav), dtype=np.float32),
+                      "art": np.asarray(mel_load_fn(feats), dtype=np.float32)})
     return items
 
 
