@@ -127,8 +127,6 @@ import os as _os
 #: launches instead of on three concurrent streams (measured on B200: 17.8 vs 17.7 ms per step, i.e. no
 #: better — the step is bound by SM time, not by launch count — so the stream schedule stays the default)
 _GROUPED = _os.environ.get("ARTIC_GROUP", "0") == "1"
-#: ARTIC_WHATIF="nowgrad,nocolsum,...": profiling experiments that SKIP work (results are wrong)
-_WHATIF = set(filter(None, _os.environ.get("ARTIC_WHATIF", "").split(",")))
 _SIDE_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
 _FORK_DEPTH: Dict[int, int] = {}
 
@@ -370,9 +368,8 @@ class ConvLayer:
             for i in range(p.ntaps):
                 p.off[i], p.yoff[i], p.widx[i] = L.off[i], L.yoff[i], L.widx[i]
             p.dtype, p.y_dtype = X.code, dY.code
-        if "nowgrad" not in _WHATIF:
-            call("artic_tapconv_wgrad", p)
-        if self.b is not None and "nocolsum" not in _WHATIF:
+        call("artic_tapconv_wgrad", p)
+        if self.b is not None:
             call("artic_colsum", ptr(dY.t), dY.seq(), dY.N, dY.C, dY.code, ptr(grads[self.name + ".bias"]))
 
 class WeightSet:
@@ -445,9 +442,7 @@ class WeightSet:
 
     def prep(self):
         tab = self._table(None)
-        if "noprep" not in _WHATIF or not getattr(self, "_prepped_once", False):
-            call("artic_weights_prep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
-            self._prepped_once = True
+        call("artic_weights_prep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
 
     def zero(self):
         self.dW.zero_()
@@ -456,8 +451,7 @@ class WeightSet:
         """dW (prepared layout) -> dv / dg of the torch parameters (OVERWRITES those entries of
         ``grads``; bias gradients were accumulated by ConvLayer.wgrad)."""
         tab = self._table(grads)
-        if "nounprep" not in _WHATIF:
-            call("artic_weights_unprep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
+        call("artic_weights_unprep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
 
 
 def _zero_grads_like(layers: List[ConvLayer]) -> Dict[str, torch.Tensor]:
