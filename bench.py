@@ -121,6 +121,57 @@ def cpu_oracle_steps(batch_items, steps, warmup, threads):
     return times
 
 
+def stft_loss_gpu_ms(dev, reps=50):
+    """BASELINE metric, second half: MR-STFT loss forward + backward (three resolutions), B = 16, T = 8000, device
+    resident, CUDA events on the launching stream.  Algorithmic bytes = read x, y + write dL/dx = 3 * B * T * 4
+    (SURVEY 8d): the figure is launch / latency bound, GB/s is reported against that."""
+    from articulatory_b200.losses import MultiResolutionSTFTLoss
+    from oracle import torch_oracle as O
+    mod = MultiResolutionSTFTLoss(**O.DEFAULT_STFT_LOSS_PARAMS)
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(BATCH_PER_GPU, T, generator=g) * 0.1).to(dev)
+    y = (torch.randn(BATCH_PER_GPU, T, generator=g) * 0.1).to(dev)
+    R = len(mod.resolutions)
+    sums = torch.zeros((R, 3), dtype=torch.float32, device=dev)
+    dx = torch.zeros((BATCH_PER_GPU, T), dtype=torch.float32, device=dev)
+
+    def once():
+        sums.zero_()
+        for r, res in enumerate(mod.resolutions):
+            res.forward(x, y, sums[r])
+        for r, res in enumerate(mod.resolutions):
+            res.backward(x, y, sums[r], 1.0 / R, 1.0 / R, dx)
+
+    for _ in range(5):
+        once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def stft_loss_cpu_ms(threads, reps=3):
+    """The same loss through the reference's arithmetic (oracle, torch CPU autograd) on the host cores."""
+    from oracle import torch_oracle as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(BATCH_PER_GPU, T, generator=g) * 0.1).requires_grad_(True)
+    y = torch.randn(BATCH_PER_GPU, T, generator=g) * 0.1
+    times = []
+    for it in range(reps + 1):
+        t0 = time.perf_counter()
+        sc, mag = O.mr_stft_loss(x, y)
+        (sc + mag).backward()
+        x.grad = None
+        if it > 0:
+            times.append(time.perf_counter() - t0)
+    return 1e3 * sum(times) / len(times)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -247,6 +298,17 @@ def run_ours(args):
                              f"timed with CUDA events over the whole step; peak = {peak_src}; traffic = DRAM bytes per step of the "
                              "tensor-core kernels (ncu, profiles/r1_traffic.json)"},
     }
+    try:        # second half of BASELINE's metric; never allowed to break the headline line
+        sms = stft_loss_gpu_ms(dev)
+        nbytes = 3 * B * T * 4
+        line["stft_loss"] = {"ms": sms, "shape": f"B={B}, T={T}, 3 resolutions (1024/2048/512), fwd + bwd",
+                             "algorithmic_bytes": nbytes, "achieved_GBps": nbytes / (sms * 1e-3) / 1e9,
+                             "peak_GBps": peak_gbs, "note": "six launches + one 36-byte memset: latency bound, not HBM bound"}
+        if world == 1 and not args.no_cpu_baseline:
+            line["stft_loss"]["cpu_ms"] = stft_loss_cpu_ms(os.cpu_count() or 1)
+            line["stft_loss"]["cpu_cores"] = os.cpu_count() or 1
+    except Exception as ex:  # noqa: BLE001
+        line["stft_loss"] = {"error": str(ex)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         times = cpu_oracle_steps(2, 2, 1, threads)
