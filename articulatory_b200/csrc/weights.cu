@@ -140,10 +140,12 @@ __global__ void __launch_bounds__(256) wn_bwd_kernel(const artic_wdesc_t* __rest
 // ---- lean versions (the default) ----------------------------------------------------------
 // wprep_kernel: ONE pass over the torch weight writes BOTH prepared layouts ('fwd' [K][G/m][a_pad][b_pad]
 // and 'bwd' [K][G/m][b_pad][a_pad]); wunprep_kernel: the prepared fp32 gradient back to the torch layout.
-// Same flat tile space as wperm_kernel ([<= 8 taps][32 a][32 b] per tile).  What makes them ~5x faster:
-// 32-bit index arithmetic with per-tile bases (no 64-bit multiplies / divisions per element), the
-// torch side of a tile moved as CONTIGUOUS runs of 32 * K floats whenever a tile holds all taps (K <= 8),
-// bf16 pairs stored as 32-bit words, and the descriptor read once per tile.
+// Same flat tile space as wperm_kernel ([<= 8 taps][32 a][32 b] per tile).  Against the generic three-pass
+// version (debug key 12): 32-bit index arithmetic with per-tile bases (no 64-bit multiplies / divisions per
+// element), the torch side of a tile moved as CONTIGUOUS runs of 32 * K floats whenever a tile holds all taps
+// (K <= 8), bf16 pairs stored as 32-bit words, the descriptor read once per tile.  Measured on the
+// discriminator (70.7 M parameters, tools/weights_bench.py): prep 705 -> 315 us, unprep + weight-norm backward
+// 626 -> 480 us; still instruction- rather than HBM-bound (1.8 / 2.9 TB/s, profiles/r1_weights_bench_final.log).
 constexpr int TS_A = PT + 1;                    // smem row pitch (floats)
 constexpr int TS_K = PT * TS_A;                 // tap pitch, plus a per-layer skew (below)
 
