@@ -78,3 +78,51 @@ def test_car_yaml_extra_keys(ref):
     sd = O.init_generator_state(gp)
     b = O.synthetic_batch(1, frames=25)
     assert O.generator_forward(sd, gp, b["x"], b["ar"]).shape == (1, 1, 2000)
+
+
+def test_eval_step_arithmetic_vs_reference_trainer():
+    """The nine eval/* losses as TrainStep.eval_step composes them (tests/test_gpu_models.py::test_eval_step_vs_oracle
+    uses the same oracle formulas) == the reference Trainer._eval_step (bin/train.py:470-603) on the golden
+    reduced-width networks."""
+    import os
+
+    ref_shim.install()
+    import articulatory.bin.train as ref_train
+    import articulatory.losses as L
+    import articulatory.models as M
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "small_e2w.pt"), map_location="cpu",
+                      weights_only=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = M.HiFiGANGenerator(**gold["generator_params"])
+        D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**gold["discriminator_params"])
+    G.load_state_dict(gold["gsd"])
+    D.load_state_dict(gold["dsd"])
+    config = dict(outdir="/tmp", generator_params=gold["generator_params"], use_stft_loss=True,
+                  use_subband_stft_loss=False, use_mel_loss=True, use_inter_loss=False, use_ph_loss=False,
+                  lambda_aux=45.0, lambda_adv=1.0, lambda_feat_match=2.0, use_feat_match_loss=True,
+                  generator_train_start_steps=1, discriminator_train_start_steps=0, generator_grad_norm=-1,
+                  discriminator_grad_norm=-1, train_max_steps=100)
+    criterion = {"gen_adv": L.GeneratorAdversarialLoss(average_by_discriminators=False),
+                 "dis_adv": L.DiscriminatorAdversarialLoss(average_by_discriminators=False),
+                 "stft": L.MultiResolutionSTFTLoss(), "mel": L.MelSpectrogramLoss(**O.E2W_MEL_LOSS_PARAMS),
+                 "feat_match": L.FeatureMatchLoss(False, False, False)}
+    tr = ref_train.Trainer(0, 0, None, None, {"generator": G, "discriminator": D}, criterion, {}, {}, config)
+    b = gold["batch"]
+    tr._eval_step({"x": (b["x"],), "y": b["y"], "ar": b["ar"]})
+    want = dict(tr.total_eval_loss)
+    with torch.no_grad():
+        y_ = O.generator_forward(gold["gsd"], gold["generator_params"], b["x"], b["ar"])
+        sc, mag = O.mr_stft_loss(y_.squeeze(1), b["y"].squeeze(1))
+        mel = O.mel_loss(y_, b["y"], **O.E2W_MEL_LOSS_PARAMS)
+        p_ = O.discriminator_forward(gold["dsd"], gold["discriminator_params"], torch.cat([b["ar"], y_], dim=2))
+        p = O.discriminator_forward(gold["dsd"], gold["discriminator_params"], torch.cat([b["ar"], b["y"]], dim=2))
+        adv, fm = O.generator_adv_loss(p_), O.feat_match_loss(p_, p)
+        real, fake = O.discriminator_adv_loss(p_, p)
+        gen = 45.0 * (sc + mag + mel) + 1.0 * adv + 1.0 * 2.0 * fm
+    got = {"eval/spectral_convergence_loss": sc, "eval/log_stft_magnitude_loss": mag, "eval/mel_loss": mel,
+           "eval/adversarial_loss": adv, "eval/feature_matching_loss": fm, "eval/generator_loss": gen,
+           "eval/real_loss": real, "eval/fake_loss": fake, "eval/discriminator_loss": real + fake}
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert abs(float(got[k]) - v) <= 1e-4 * abs(v), (k, float(got[k]), v)
