@@ -25,6 +25,7 @@ CASES = [
     ConvSpec("convT", 4, 2, k=8, stride=4, padding=2),
     ConvSpec("convT", 4, 2, k=4, stride=2, padding=1),
     ConvSpec("convT", 3, 2, k=16, stride=8, padding=4),
+    ConvSpec("convT", 4, 2, k=6, stride=3, padding=2, output_padding=1),   # egs/mri/voc1 (scales [8, 5, 3, 2])
     ConvSpec("linear", 7, 5),
 ]
 
