@@ -308,3 +308,72 @@ def test_tc_conv_with_unaligned_bias_and_views():
     lay.forward(X, Y2=Y, act=_lib.ACT_LRELU, act_slope=0.1)
     torch.cuda.synchronize()
     assert rel_err(Y.t.float().cpu().permute(0, 2, 1), ref) < 2e-2
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float64)
+
+
+MIXED_CASES = [
+    # (spec kwargs, N, Lin, in dtype): the shapes whose bf16-mode kernels the uniform-precision cases above do not reach
+    (dict(kind="conv", cin=1, cout=128, k=15, padding=7), 3, 1500, "f32"),               # Cin = 1 kernels (MSD first layer)
+    (dict(kind="conv", cin=1, cout=32, k=5, stride=3, padding=2), 4, 901, "f32"),        # Cin = 1, strided (MPD first layer)
+    (dict(kind="conv", cin=128, cout=256, k=5, stride=3, padding=2), 4, 301, "bf16"),    # strided tcgen05 wgrad (per-phase groups)
+    (dict(kind="conv", cin=256, cout=256, k=5, stride=1, padding=2), 3, 200, "bf16"),
+    (dict(kind="convT", cin=128, cout=64, k=8, stride=4, padding=2), 2, 200, "bf16"),    # transposed: wgrad with X / dY exchanged
+    (dict(kind="conv", cin=141, cout=256, k=7, padding=3), 2, 100, "bf16"),              # padded input width (141 -> 256)
+]
+
+
+@pytest.mark.parametrize("case", range(len(MIXED_CASES)))
+def test_bf16_mode_layers_fwd_dgrad_wgrad(case):
+    """The bf16-mode kernels of the discriminator's first layers (fp32 signal in, bf16 features out: register-
+    weight Cin = 1 forward, shared-memory-staged Cout = 1 data gradient into fp32, vector Cin = 1 weight gradient)
+    and of the strided / transposed / padded tensor-core layers, against torch on the SAME rounded operands
+    (so only the accumulation order differs)."""
+    kw, N, lin, in_dt = MIXED_CASES[case]
+    spec = ConvSpec(**kw)
+    in_code = F32 if in_dt == "f32" else BF16
+    torch.manual_seed(100 + case)
+    w = torch.randn(spec.weight_shape(), dtype=torch.float64) / math.sqrt(spec.cig * spec.k)
+    b = torch.randn(spec.cout, dtype=torch.float64) * 0.1
+    x = torch.randn(N, spec.cin, lin, dtype=torch.float64)
+    if in_code == BF16:
+        x, w_eff = _bf16_round(x), _bf16_round(w)          # the layer computes with bf16 weights and activations
+    else:
+        w_eff = w.float().double()                          # Cin = 1 layers keep fp32 weights
+    x.requires_grad_(True)
+    w_eff.requires_grad_(True)
+    b.requires_grad_(True)
+    y = _torch_fwd(spec, x, w_eff, b)
+    dy = _bf16_round(torch.randn_like(y))
+    gx, gw, gb = torch.autograd.grad(y, [x, w_eff, b], dy)
+
+    lay = ConvLayer(spec, "l", in_code, BF16, pad_in=True)
+    params = {"l.weight": w.float().to(DEV).contiguous(), "l.bias": b.detach().float().to(DEV)}
+    lay.bind(params)
+    lay.prep()
+    xin = x.detach().permute(0, 2, 1).contiguous()
+    if spec.groups == 1 and lay.kcig > spec.cin:
+        xin = F.pad(xin, (0, lay.kcig - spec.cin))          # zero-padded channels (the generator's input assembly does this)
+    X = SeqT(xin.to(DEV, _lib.TORCH_DTYPE[in_code]), N, lin, xin.shape[2])
+    lout = spec.out_len(lin)
+    Y = SeqT.empty(N, lout, spec.cout, BF16, DEV)
+    lay.forward(X, Y2=Y, act=_lib.ACT_LRELU, act_slope=0.1)
+    torch.cuda.synchronize()
+    assert rel_err(Y.t.float().cpu().permute(0, 2, 1), F.leaky_relu(y.detach(), 0.1)) < 6e-3      # bf16 output rounding
+
+    dY = SeqT(dy.permute(0, 2, 1).contiguous().to(DEV, torch.bfloat16), N, lout, spec.cout)
+    dX = SeqT.empty(N, lin, xin.shape[2], F32 if in_code == F32 else BF16, DEV)
+    lay.dgrad(dY, dX=dX)
+    torch.cuda.synchronize()
+    got = dX.t.float().cpu()[:, :, :spec.cin].permute(0, 2, 1)
+    assert rel_err(got, gx) < 6e-3          # bf16 'bwd' weights (also for the fp32-input layers) / bf16 dX
+
+    grads = {k: torch.zeros_like(t) for k, t in params.items()}
+    lay.zero_wgrad()
+    lay.wgrad(X, dY, grads)
+    lay.finish_grads(grads)
+    torch.cuda.synchronize()
+    assert rel_err(grads["l.weight"].cpu(), gw) < 2e-3
+    assert rel_err(grads["l.bias"].cpu(), gb) < 2e-3
