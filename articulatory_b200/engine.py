@@ -13,6 +13,8 @@ reference's (B, H, p) element order with C innermost, i.e. (B, H, p, C), address
 N = B*p interleaved sequences (artic_seq_t.n_inner = p) — so the reference's
 view(b, c, t//p, p) (models/hifigan.py:417) is a zero-copy reinterpretation.
 """
+import contextlib
+import os as _os
 from typing import Dict, List, Optional
 
 import torch
@@ -121,7 +123,6 @@ def tapconv(launches, X: SeqT, W, G, Cig, Cog, **kw):
 # --------------------------------------------------------------------------- #
 # one conv-like layer                                                         #
 # --------------------------------------------------------------------------- #
-import os as _os
 
 #: ARTIC_GROUP=1: the three MRF blocks of a generator stage advance in lock-step through multi-problem
 #: launches instead of on three concurrent streams (measured on B200: 17.8 vs 17.7 ms per step, i.e. no
@@ -157,7 +158,7 @@ def fork_join(branches, device=None, background=()):
     kernel leaves SMs idle and pays its launch / pipeline-fill latency serially; the three MRF
     blocks of a generator stage and the eight sub-discriminators are independent, so their kernels
     overlap.  ARTIC_STREAMS=0 runs the branches one after the other."""
-    import os
+    os = _os
     if len(branches) == 1 or os.environ.get("ARTIC_STREAMS", "1") == "0":
         return [b() for b in branches]
     main = torch.cuda.current_stream()
@@ -466,8 +467,6 @@ def _zero_grads_like(layers: List[ConvLayer]) -> Dict[str, torch.Tensor]:
 # --------------------------------------------------------------------------- #
 # generator                                                                   #
 # --------------------------------------------------------------------------- #
-import contextlib
-
 
 @contextlib.contextmanager
 def planner_objective(sm_time_pct: int):

@@ -14,6 +14,7 @@ syncs (the nine logged scalars are accumulated on the device and read at the log
 interval), one D(real) forward instead of two, no D wgrad in the G phase.  The steady-state
 step is captured once in a CUDA graph (per rank) and replayed.
 """
+import os as _os
 from typing import Dict, Optional
 
 import torch
@@ -24,7 +25,6 @@ from .engine import SeqT, critical_stream, fork_join, slice_seq
 from .losses.spectral import MelSpectrogramLoss, MultiResolutionSTFTLoss
 from .optim import FusedAdam
 
-import os as _os
 #: ARTIC_BG="prep,spectral,order": which branches run on low-priority streams / in which order (see
 #: engine.fork_join).  Measured on B200, 20-step runs, repeatable to +-0.02 ms (gpurun_out/r1_bg_66.log):
 #: none 12.87, order 12.81 / 12.85, order+spectral 12.75 ms — the discriminator chain is enqueued before the
