@@ -1,5 +1,5 @@
 // tcgen05 weight-gradient kernel of the tap-gather contraction (artic_tapconv_wgrad) for the
-// dense bf16 stride-1 convolutions:
+// bf16 convolutions (unit or strided input, groups, period layout):
 //
 //   dW[t][ci][co] += sum_{n,q} X[n, q + off[t], ci] * dY[n, q + yoff, co]
 //
@@ -12,7 +12,11 @@
 // byte offset of the A descriptor is the byte distance between consecutive taps (dil rows),
 // so the second/third/fourth 64/32-row block of A is the same tile shifted by one more tap.
 // Positions are split over CTAs (split-K); partial sums are reduced into the fp32 dW with
-// vector red.global.add.
+// vector red.global.add, coalesced through a per-warp shared-memory transpose that overlays
+// the (by then idle) operand stages.
+// Input stride si > 1: X is staged as si phase panels (row r of phase ph = input row r * si + ph);
+// the tap groups are cut per phase when that moves fewer operand bytes, so a CTA loads only the
+// ONE panel its accumulators read and the co tile widens (up to 256).
 //
 // Zero padding / sequence boundaries: rows outside [0, len) are zero-filled by TMA; short
 // sequences are packed back to back with their halos (pitch = L + span), the padding rows of
@@ -25,7 +29,7 @@ namespace tc {
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 8;
-constexpr int WG_EPI_BYTES = 0;
+constexpr int WG_EPI_BYTES = 0;   // the epilogue's transpose stages overlay the operand stages
 
 struct WPlan {
   int32_t xrb, yrb;            // row bytes (= swizzle span) of the X / dY panels
