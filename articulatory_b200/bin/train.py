@@ -24,7 +24,7 @@ import yaml
 
 import articulatory_b200
 import articulatory_b200.models
-from articulatory_b200.data import SpeechCollater, synthetic_utterances
+from articulatory_b200.data import BatchPrefetcher, SpeechCollater, synthetic_utterances
 from articulatory_b200.parallel import DataParallel
 from articulatory_b200.trainer import LOG_KEYS, TrainStep
 
@@ -119,11 +119,12 @@ class Trainer(object):
         bs = self.config["batch_size"]
         while not self.finish_train:
             idx = self.dp.sampler_indices(len(self.items), self.epochs, shuffle=True)
-            for lo in range(0, len(idx) - bs + 1, bs):
-                batch = self.collater([self.items[i] for i in idx[lo:lo + bs]])
+            groups = [idx[lo:lo + bs] for lo in range(0, len(idx) - bs + 1, bs)]
+            # window cutting + pinning of the next two batches run on a host thread under the current step
+            for batch in BatchPrefetcher(lambda g: self.collater([self.items[i] for i in g]), groups, depth=2):
                 if batch["y"].shape[0] != bs:
                     continue          # an utterance shorter than the window was dropped: keep shapes static
-                self.ts.step(batch["x"][0].pin_memory(), batch["y"].pin_memory(), batch["ar"].pin_memory())
+                self.ts.step(batch["x"][0], batch["y"], batch["ar"])
                 self.steps += 1
                 if self.steps % self.config["log_interval_steps"] == 0:
                     n = self.config["log_interval_steps"]

@@ -7,6 +7,9 @@ yields the same windows as the reference), same integer indexing — checked bit
 the reference's own output in tests/golden/collater.npz.  Pure numpy / host work: the batch it
 returns is what ``TrainStep.step`` copies host->device.
 """
+import queue
+import threading
+
 import numpy as np
 import torch
 
@@ -80,6 +83,72 @@ class SpeechCollater(object):
                 ars.append(ar)
             out["ar"] = torch.tensor(np.stack(ars, axis=0), dtype=torch.float).unsqueeze(1)  # (B, 1, ar_len)
         return out
+
+
+class BatchPrefetcher(object):
+    """Assemble (and pin) the next batches on ONE host thread while the GPU runs the current step.
+
+    ``make_batch(job)`` is called for every job in order on the worker thread — a single worker, so a seeded
+    ``np.random`` (the collater's window draws) yields exactly the batches of the synchronous loop — and its
+    results are handed over through a bounded queue (``depth`` batches ahead).  With ``pin=True`` every tensor of a
+    dict result is moved to pinned memory, ready for the non-blocking host->device copy inside ``TrainStep.step``.
+    Exceptions of the worker are re-raised by the iterator; ``close()`` (also called when iteration ends or is
+    abandoned) stops the worker."""
+
+    _END = object()
+
+    def __init__(self, make_batch, jobs, depth=2, pin=True):
+        self._q = queue.Queue(maxsize=max(int(depth), 1))
+        self._stop = threading.Event()
+        self._pin = pin
+
+        def work():
+            try:
+                for job in jobs:
+                    if self._stop.is_set():
+                        return
+                    b = make_batch(job)
+                    if self._pin and isinstance(b, dict):
+                        b = {k: (v.pin_memory() if torch.is_tensor(v) else
+                                 tuple(t.pin_memory() for t in v) if isinstance(v, tuple) else v) for k, v in b.items()}
+                    if not self._put((None, b)):
+                        return
+                self._put((None, self._END))
+            except BaseException as ex:                                    # noqa: BLE001 — handed to the consumer
+                self._put((ex, None))
+
+        self._t = threading.Thread(target=work, name="artic-batch-prefetch", daemon=True)
+        self._t.start()
+
+    def _put(self, item):
+        while not self._stop.is_set():
+            try:
+                self._q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def __iter__(self):
+        try:
+            while True:
+                ex, b = self._q.get()
+                if ex is not None:
+                    raise ex
+                if b is self._END:
+                    return
+                yield b
+        finally:
+            self.close()
+
+    def close(self):
+        self._stop.set()
+        try:
+            while True:
+                self._q.get_nowait()
+        except queue.Empty:
+            pass
+        self._t.join(timeout=5.0)
 
 
 def synthetic_utterances(n_items, n_frames=400, n_feats=13, hop_size=80, seed=0):
