@@ -34,7 +34,9 @@ class TapConv(C.Structure):
                 ("off", C.c_int32 * MAX_TAPS), ("widx", C.c_int32 * MAX_TAPS),
                 ("alpha", C.c_float), ("mask_slope", C.c_float), ("act_slope", C.c_float),
                 ("act", C.c_int32), ("dtype", C.c_int32), ("out_dtype", C.c_int32),
-                ("Wt", C.c_void_p), ("Wt_taps", C.c_int32), ("reserved_", C.c_int32)]
+                ("Wt", C.c_void_p), ("Wt_taps", C.c_int32), ("reserved_", C.c_int32),
+                ("X_sp", C.c_void_p), ("Wt_sp", C.c_void_p), ("Y_sp", C.c_void_p), ("Y2_sp", C.c_void_p),
+                ("x_plane", C.c_int64), ("w_plane", C.c_int64), ("y_plane", C.c_int64)]
 
 
 class TapWgrad(C.Structure):
@@ -44,7 +46,8 @@ class TapWgrad(C.Structure):
                 ("q0", C.c_int32), ("nq", C.c_int32), ("si", C.c_int32), ("so", C.c_int32),
                 ("ntaps", C.c_int32),
                 ("off", C.c_int32 * MAX_TAPS), ("yoff", C.c_int32 * MAX_TAPS), ("widx", C.c_int32 * MAX_TAPS),
-                ("dtype", C.c_int32), ("y_dtype", C.c_int32)]
+                ("dtype", C.c_int32), ("y_dtype", C.c_int32),
+                ("X_sp", C.c_void_p), ("dY_sp", C.c_void_p), ("x_plane", C.c_int64), ("y_plane", C.c_int64)]
 
 
 class AdamHyper(C.Structure):
@@ -94,6 +97,8 @@ SIGNATURES = {
     "artic_sum3": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p]),
     "artic_tanh_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "artic_cast": (C.c_int, [_p, _i32, _p, _i32, _i64, _p]),
+    "artic_split": (C.c_int, [_p, _p, _i64, _i64, _p]),
+    "artic_path_counts": (C.c_int, [C.POINTER(C.c_int64), _i32]),
     "artic_concat_time": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i64, _i32, _p]),
     "artic_avgpool1d": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "artic_avgpool1d_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
@@ -161,6 +166,16 @@ def call(name, *args):
     launch_count += 1
     if rc != 0:
         raise ArticError(f"{name} failed ({rc}): {lib.artic_last_error().decode()}")
+
+
+PATH_NAMES = ("conv_tc", "conv_tc_x3", "conv_generic", "conv_c1", "wgrad_tc", "wgrad_tc_x3", "wgrad_generic", "wgrad_c1")
+
+
+def path_counts(reset=False):
+    """Which kernel family took each contraction since the last reset (artic_path_counts)."""
+    buf = (C.c_int64 * 10)()
+    load().artic_path_counts(buf, int(reset))
+    return dict(zip(PATH_NAMES, list(buf)[:8]))
 
 
 def ptr(t):

@@ -5,7 +5,8 @@ Same flags as ``articulatory-train`` (--train-dumpdir, --dev-dumpdir, --outdir, 
 --pretrain, --resume, --verbose, --rank, --local_rank), same YAML keys
 (``egs/ema/voc1/conf/e2w_hifigan*.yaml`` run unchanged), same plugin lookup by class name,
 same checkpoint layout (``{"model": {"generator", "discriminator"}, "optimizer", "scheduler",
-"steps", "epochs"}``), same schedule gates and logged scalars.  The loop body is the fused
+"steps", "epochs"}`` with ``torch.optim.Adam`` / ``MultiStepLR`` state dicts, so checkpoints resume across the two
+code bases), same schedule gates and logged scalars.  The loop body is the fused
 ``TrainStep`` (three CUDA graphs per step, no per-step host sync); distributed training — disabled
 in the reference (bin/train.py:1790-1801) — is one process per GPU with an NCCL gradient all-reduce.
 
@@ -45,24 +46,33 @@ def _load_items(dumpdir, config):
     else:
         raise ValueError("support only hdf5 or npy format.")
     parts = dumpdir.split("/")
+    # reference bin/train.py:1511-1516,1547: utterances not longer than the training window are dropped up front
+    mel_thr = None
+    if config.get("remove_short_samples", False):
+        mel_thr = config["batch_max_steps"] // config["hop_size"] + 2 * config["generator_params"].get("aux_context_window", 0)
     if len(parts) > 1 and os.path.exists(os.path.join("data", parts[1], "feats.scp")):
         ds = SpeechDataset(dumpdir, audio_query=audio_query, mel_query=mel_query, audio_load_fn=audio_load_fn,
-                           mel_load_fn=mel_load_fn, dataset_mode=config.get("dataset_mode", "a2w"))
+                           mel_load_fn=mel_load_fn, dataset_mode=config.get("dataset_mode", "a2w"),
+                           mel_length_threshold=mel_thr)
         return [{"audio": np.asarray(it["audio"], dtype=np.float32), "art": np.asarray(it["art"], dtype=np.float32)}
                 for it in (ds[i] for i in range(len(ds)))]
     items = []
     for wav, feats in zip(sorted(find_files(dumpdir, audio_query)), sorted(find_files(dumpdir, mel_query))):
-        items.append({"audio": np.asarray(audio_load_fn(wav), dtype=np.float32),
-                      "art": np.asarray(mel_load_fn(feats), dtype=np.float32)})
+        audio, art = np.asarray(audio_load_fn(wav), dtype=np.float32), np.asarray(mel_load_fn(feats), dtype=np.float32)
+        if mel_thr is not None and len(art) <= mel_thr:
+            continue
+        items.append({"audio": audio, "art": art})
     return items
 
 
 class Trainer(object):
     """Epoch / step loop, logging and checkpointing around ``TrainStep`` (reference Trainer, bin/train.py:60-780)."""
 
-    def __init__(self, steps, epochs, items, collater, model, step_fn, config, dp, device, dev_items=None):
+    def __init__(self, steps, epochs, items, collater, model, step_fn, config, dp, device, dev_items=None,
+                 dev_collater=None):
         self.steps, self.epochs = steps, epochs
         self.items, self.collater, self.model, self.ts = items, collater, model, step_fn
+        self.dev_collater = dev_collater or collater
         self.config, self.dp, self.device = config, dp, device
         self.dev_items = dev_items or []
         self.best_mel_loss = float("inf")
@@ -74,10 +84,10 @@ class Trainer(object):
         bs = self.config["batch_size"]
         n = 0
         for lo in range(0, len(self.dev_items) - bs + 1, bs):
-            batch = self.collater(self.dev_items[lo:lo + bs])
+            batch = self.dev_collater(self.dev_items[lo:lo + bs])
             if batch["y"].shape[0] != bs:
                 continue
-            self.ts.eval_step(batch["x"][0], batch["y"], batch["ar"])
+            self.ts.eval_step(batch["x"][0], batch["y"], batch.get("ar"))
             n += 1
         if n == 0:
             return {}
@@ -98,8 +108,8 @@ class Trainer(object):
         torch.save({"model": {"generator": self.model["generator"].state_dict(),
                               "discriminator": self.model["discriminator"].state_dict()},
                     "optimizer": {"generator": self.ts.optG.state_dict(), "discriminator": self.ts.optD.state_dict()},
-                    "scheduler": {"generator": {"last_epoch": self.ts.optG.step_count()},
-                                  "discriminator": {"last_epoch": self.ts.optD.step_count()}},
+                    "scheduler": {"generator": self.ts.optG.scheduler_state_dict(),
+                                  "discriminator": self.ts.optD.scheduler_state_dict()},
                     "steps": self.steps, "epochs": self.epochs}, path)
 
     def load_checkpoint(self, path, load_only_params=False):
@@ -111,20 +121,25 @@ class Trainer(object):
         if not load_only_params:
             self.steps, self.epochs = sd["steps"], sd["epochs"]
             self.ts.steps = self.steps
-            if "exp_avg" in sd["optimizer"]["generator"]:
-                self.ts.optG.load_state_dict(sd["optimizer"]["generator"])
-                self.ts.optD.load_state_dict(sd["optimizer"]["discriminator"])
+            sch = sd.get("scheduler", {})
+            self.ts.optG.load_state_dict(sd["optimizer"]["generator"], sch.get("generator"))
+            self.ts.optD.load_state_dict(sd["optimizer"]["discriminator"], sch.get("discriminator"))
 
     def run(self):
         bs = self.config["batch_size"]
         while not self.finish_train:
             idx = self.dp.sampler_indices(len(self.items), self.epochs, shuffle=True)
             groups = [idx[lo:lo + bs] for lo in range(0, len(idx) - bs + 1, bs)]
+            if not groups:
+                raise ValueError(f"{len(idx)} training utterances on this rank cannot fill one batch of {bs}")
+            stepped = False
             # window cutting + pinning of the next two batches run on a host thread under the current step
-            for batch in BatchPrefetcher(lambda g: self.collater([self.items[i] for i in g]), groups, depth=2):
+            for batch in BatchPrefetcher(lambda g: self.collater([self.items[i] for i in g]), groups, depth=2,
+                                         device=self.device):
                 if batch["y"].shape[0] != bs:
                     continue          # an utterance shorter than the window was dropped: keep shapes static
-                self.ts.step(batch["x"][0], batch["y"], batch["ar"])
+                stepped = True
+                self.ts.step(batch["x"][0], batch["y"], batch.get("ar"))
                 self.steps += 1
                 if self.steps % self.config["log_interval_steps"] == 0:
                     n = self.config["log_interval_steps"]
@@ -140,6 +155,9 @@ class Trainer(object):
                 if self.steps >= self.config["train_max_steps"]:
                     self.finish_train = True
                     break
+            if not stepped:
+                raise ValueError("every batch of the epoch lost an utterance shorter than the training window; set "
+                                 "remove_short_samples: true (the yaml default) or lower batch_max_steps")
             self.epochs += 1
 
 
@@ -156,7 +174,10 @@ def main(argv=None):
     parser.add_argument("--verbose", type=int, default=1)
     parser.add_argument("--rank", "--local_rank", default=0, type=int)
     parser.add_argument("--synthetic", type=int, default=0, help="train on N synthetic utterances (B200 extension)")
-    parser.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    parser.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
+                        help="bf16x3 (default): fp32 storage, error-compensated split-bf16 tcgen05 contraction — the mode "
+                             "that meets the 1e-3 parity gate against the fp32 reference; bf16: bf16 storage, plain "
+                             "tcgen05 (fastest, ~1e-2 waveform error); fp32: CUDA-core kernels (debug)")
     args = parser.parse_args(argv)
 
     if not torch.cuda.is_available():
@@ -208,7 +229,11 @@ def main(argv=None):
     dp.broadcast_parameters(model["generator"], model["discriminator"])
     ts = TrainStep(model["generator"], model["discriminator"], config, device, world_size=dp.world,
                    all_reduce=dp.all_reduce if dp.world > 1 else None)
-    trainer = Trainer(0, 0, items, collater, model, ts, config, dp, device, dev_items=dev_items)
+    dev_collater = SpeechCollater(batch_max_steps=config["batch_max_steps"], hop_size=config["hop_size"],
+                                  aux_context_window=config["generator_params"].get("aux_context_window", 0),
+                                  dataset_mode=config.get("dataset_mode", "a2w"), config=config,
+                                  rng=np.random.RandomState(777 + dp.rank))   # own stream: the prefetch thread owns np.random
+    trainer = Trainer(0, 0, items, collater, model, ts, config, dp, device, dev_items=dev_items, dev_collater=dev_collater)
     if args.pretrain:
         trainer.load_checkpoint(args.pretrain, load_only_params=True)
     if args.resume:

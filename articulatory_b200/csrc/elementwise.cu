@@ -63,6 +63,27 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __res
   GRID_STRIDE(i, n) { st_f(dpre + i, dy[i] * (1.f - y[i] * y[i])); }
 }
 
+// bf16x3 operand split, 4 elements per thread (128-bit load, two 64-bit stores)
+__global__ void split4_kernel(const float4* __restrict__ s, uint2* __restrict__ hi, uint2* __restrict__ lo, int64_t n4) {
+  GRID_STRIDE(i, n4) {
+    const float4 v = __ldg(s + i);
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+    const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+    hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
+}
+__global__ void split1_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                              int64_t n) {
+  GRID_STRIDE(i, n) {
+    const float v = __ldg(s + i);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
   GRID_STRIDE(i, n) { st_f(d + i, ld_f(s + i)); }
@@ -313,6 +334,19 @@ extern "C" int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64
   if (n == 0) return ARTIC_OK;
   DISPATCH(dtype, (tanh_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(dy, y, (float*)dpre, n)),
            (tanh_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(dy, y, (bf16*)dpre, n)));
+}
+
+extern "C" int artic_split(const float* src, void* hi, int64_t plane, int64_t n, void* stream) {
+  ARTIC_CHECK_ARG(src && hi && plane >= n && n >= 0, "bad arguments");
+  if (n == 0) return ARTIC_OK;
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
+  if (n % 4 == 0 && plane % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 7) == 0)
+    split4_kernel<<<grid_for(n / 4), 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(h),
+                                                          reinterpret_cast<uint2*>(h + plane), n / 4);
+  else
+    split1_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, h, h + plane, n);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
 }
 
 extern "C" int artic_cast(const void* src, int32_t sd, void* dst, int32_t dd, int64_t n, void* stream) {

@@ -446,6 +446,14 @@ __global__ void __launch_bounds__(256) colsum_dense_bf16_kernel(const __nv_bfloa
 using namespace artic;
 
 extern "C" const char* artic_last_error(void) { return artic::g_err; }
+
+namespace artic { long long g_path_counts[10] = {0}; }
+extern "C" int artic_path_counts(int64_t* h_out, int32_t reset) {
+  ARTIC_CHECK_ARG(h_out != nullptr, "null pointer");
+  for (int i = 0; i < 10; ++i) h_out[i] = artic::g_path_counts[i];
+  if (reset) for (int i = 0; i < 10; ++i) artic::g_path_counts[i] = 0;
+  return ARTIC_OK;
+}
 extern "C" int artic_version(void) { return 100; }
 extern "C" const char* artic_arch(void) { return "sm_100a"; }
 
@@ -476,8 +484,10 @@ static int tapconv_fallback(const artic_tapconv_t* p, cudaStream_t st) {
   if (p->N == 0 || p->nq == 0) return ARTIC_OK;
   if (artic_tapconv_co1_try(p, st) == 1 || artic_tapconv_ci1_try(p, st) == 1) {
     ARTIC_LAUNCH_CHECK();
+    ++g_path_counts[PATH_CONV_C1];
     return ARTIC_OK;
   }
+  ++g_path_counts[PATH_CONV_GENERIC];
   const bool ob = p->out_dtype == ARTIC_BF16;
   int rc;
   if (p->dtype == ARTIC_BF16) rc = ob ? launch_tapconv<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapconv<__nv_bfloat16, float>(*p, st);
@@ -512,6 +522,24 @@ extern "C" int artic_tapconv_multi(const artic_tapconv_t* ps, int32_t n, void* s
     rc = tapconv_fallback(&ps[i], st);
     if (rc != ARTIC_OK) return rc;
   }
+  // bf16x3 mode: split copies requested from a problem that ran on a CUDA-core kernel (the tcgen05 epilogue
+  // writes them itself).  The phases of one layer share their output tensor: split it once, after the last.
+  for (int i = 0; i < n; ++i) {
+    if (taken[i] || ps[i].N == 0 || ps[i].nq == 0 || ps[i].out_dtype != ARTIC_F32) continue;
+    const void* outs[2] = {ps[i].Y, ps[i].Y2};
+    void* sps[2] = {ps[i].Y_sp, ps[i].Y2_sp};
+    for (int k = 0; k < 2; ++k) {
+      if (outs[k] == nullptr || sps[k] == nullptr) continue;
+      bool later = false;
+      for (int j = i + 1; j < n && !later; ++j)
+        later = !taken[j] && ps[j].N != 0 && ps[j].nq != 0 && (ps[j].Y == outs[k] || ps[j].Y2 == outs[k]);
+      if (later) continue;
+      const artic_seq_t& y = ps[i].y;
+      const int64_t total = (int64_t)((ps[i].N + y.n_inner - 1) / y.n_inner) * y.s_outer;
+      rc = artic_split(reinterpret_cast<const float*>(outs[k]), sps[k], ps[i].y_plane, total, stream);
+      if (rc != ARTIC_OK) return rc;
+    }
+  }
   return ARTIC_OK;
 }
 
@@ -531,11 +559,13 @@ extern "C" int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream) {
   const bool yb = p->y_dtype == ARTIC_BF16;
   if (artic_tapwgrad_ci1_try(p, st) == 1) {
     ARTIC_LAUNCH_CHECK();
+    ++g_path_counts[PATH_WGRAD_C1];
     return ARTIC_OK;
   }
   int rc = artic_tapwgrad_tc_try(p, st);
   if (rc < 0) return rc;
   if (rc == 1) return ARTIC_OK;
+  ++g_path_counts[PATH_WGRAD_GENERIC];
   if (p->dtype == ARTIC_BF16) rc = yb ? launch_tapwgrad<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapwgrad<__nv_bfloat16, float>(*p, st);
   else rc = yb ? launch_tapwgrad<float, __nv_bfloat16>(*p, st) : launch_tapwgrad<float, float>(*p, st);
   if (rc != ARTIC_OK) return rc;

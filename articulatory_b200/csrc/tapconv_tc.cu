@@ -12,10 +12,18 @@
 //   never bleeds into the neighbouring sequence).
 // * Short sequences (discriminator tails, L <= 53) are packed: several zero-padded sequences
 //   are laid end to end in the staged tile, so a 128-row MMA still does useful work.
-// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-//   warps 2..5 = epilogue (TMEM -> registers -> fused bias / residual / LeakyReLU-mask /
-//   activation -> global).  Persistent over tiles; the accumulator is double-buffered in TMEM
-//   when it fits, so the epilogue of tile i overlaps the main loop of tile i+1.
+// * Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+//   warps 2..9 = epilogue (TMEM -> registers -> fused bias / residual / LeakyReLU-mask /
+//   activation -> global; two warps per TMEM lane quarter on alternating 32-channel chunks).
+//   Persistent over tiles; the accumulator is double-buffered in TMEM when it fits, so the
+//   epilogue of tile i overlaps the main loop of tile i+1.
+// * bf16x3 mode (template X3): fp32 activations and weights live in HBM next to SPLIT COPIES
+//   (bf16 hi = rn(x), lo = rn(x - hi); artic_split / this kernel's epilogue).  Every K chunk is
+//   issued three times — (x_hi, w_hi), (x_hi, w_lo), (x_lo, w_hi) — into the same fp32 TMEM
+//   accumulator, i.e. the classic error-compensated product with ~2^-16 relative operand error
+//   (the dropped x_lo * w_lo term is 2^-16 of the result as well).  The epilogue reads fp32
+//   residual / mask operands and writes the fp32 result plus, on request, its split copy for
+//   the next tensor-core consumer.
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -56,6 +64,7 @@ struct Plan {
   int32_t phase[ARTIC_MAX_TAPS];  // (off[t] - min_off) % si : which phase panel the tap reads
   int32_t a_off16[ARTIC_MAX_TAPS];  // (phase * panel_bytes + shift * row_bytes) / 16 : descriptor offset of the tap
   int32_t layout_type;            // UMMA smem descriptor swizzle code
+  int32_t n_kcl;                  // logical ci chunks (n_kc = 3 * n_kcl in the bf16x3 mode)
   long long* dbg;                 // debug timeline buffer (artic_debug_buffer) or nullptr
   int32_t dbg_flags;              // debug: 1 = skip epilogue stores, 2 = skip operand use
 };
@@ -67,6 +76,7 @@ struct Prob {
   artic_tapconv_t p;
   Plan pl;
   CUtensorMap map_x, map_w;
+  CUtensorMap map_x_lo, map_w_lo;   // bf16x3 mode: the `lo` planes
 };
 constexpr int MAXP = 8;
 struct Multi {
@@ -108,6 +118,7 @@ __device__ __forceinline__ void dbg_mark(long long* dbg, int tag) {
 // ------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------
+template <bool X3>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tapconv_tc_kernel(const __grid_constant__ Multi mp) {
   int prob_j = 0;
@@ -116,6 +127,10 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
   const Plan& pl = mp.prob[prob_j].pl;
   const CUtensorMap& map_x = mp.prob[prob_j].map_x;
   const CUtensorMap& map_w = mp.prob[prob_j].map_w;
+  const CUtensorMap& map_x_lo = mp.prob[prob_j].map_x_lo;
+  const CUtensorMap& map_w_lo = mp.prob[prob_j].map_w_lo;
+  // bf16x3: K chunk kc = 3 * kcl + part; part 0 = (x_hi, w_hi), 1 = (x_hi, w_lo), 2 = (x_lo, w_hi)
+  const int n_wres = X3 ? 2 * pl.n_kcl : pl.n_kc;      // resident weight chunks: [w_hi chunks | w_lo chunks]
   const int cta = (int)blockIdx.x - mp.cta_begin[prob_j];                 // this CTA's index / count inside its problem
   const int ncta = mp.cta_begin[prob_j + 1] - mp.cta_begin[prob_j];
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -129,7 +144,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem0;
   const uint32_t w_base = smem0 + (uint32_t)pl.n_as * pl.a_stage_bytes;
-  const uint32_t epi_base = w_base + (pl.w_resident ? (uint32_t)(pl.n_kc * p.ntaps) * pl.w_tile_bytes : (uint32_t)pl.n_ws * pl.w_stage_bytes);   // 4 x 8 KB transpose stages + row offsets
+  const uint32_t epi_base = w_base + (pl.w_resident ? (uint32_t)(n_wres * p.ntaps) * pl.w_tile_bytes : (uint32_t)pl.n_ws * pl.w_stage_bytes);   // 4 x 8 KB transpose stages + row offsets
 
   const long long t_start = clock64();
   const long long t_trace = (mp.trace != nullptr && threadIdx.x == 0) ? global_timer() : 0;
@@ -147,6 +162,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     if (lane == 0) {
       prefetch_tmap(&map_x);
       prefetch_tmap(&map_w);
+      if (X3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
       for (int i = 0; i < pl.n_as; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < pl.n_ws; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], blockDim.x - 64); }
@@ -179,11 +195,13 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
       if (!pl.w_early) pdl_wait();   // the predecessor may have written the weights
       if (pl.w_resident) {
         // small layers (n_nt == 1, G == 1): every tile uses the same weights; load them once
-        mbar_expect_tx(&w_res_full, (uint32_t)(pl.n_kc * ntaps) * w_bytes);
-        for (int kc = 0; kc < pl.n_kc; ++kc)
+        mbar_expect_tx(&w_res_full, (uint32_t)(n_wres * ntaps) * w_bytes);
+        for (int kc = 0; kc < n_wres; ++kc) {
+          const bool lo = X3 && kc >= pl.n_kcl;
           for (int t = 0; t < ntaps; ++t)
-            tma_load_2d(w_base + (uint32_t)(kc * ntaps + t) * pl.w_tile_bytes, &map_w, &w_res_full, kc * pl.kch,
-                        p.widx[t] * p.Cog);
+            tma_load_2d(w_base + (uint32_t)(kc * ntaps + t) * pl.w_tile_bytes, lo ? &map_w_lo : &map_w, &w_res_full,
+                        (lo ? kc - pl.n_kcl : kc) * pl.kch, p.widx[t] * p.Cog);
+        }
       } else if (cta < pl.total_tiles) {
         // the weights are not written by the predecessor kernel (tc::note_weights_written): fill the
         // weight pipeline with the first tile's stages while the predecessor is still finishing
@@ -193,11 +211,13 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
         const int npre = min(pl.n_ws, pl.n_kc * spk);
         for (; w_pre < npre; ++w_pre) {
           const int kc = w_pre / spk, t0 = (w_pre % spk) * pl.tps;
+          const int kcl = X3 ? kc / 3 : kc;
+          const CUtensorMap* mw = (X3 && kc % 3 == 1) ? &map_w_lo : &map_w;
           const int nt_g = min(pl.tps, ntaps - t0);
           mbar_expect_tx(&w_full[ws.stage], (uint32_t)nt_g * w_bytes);
           for (int j = 0; j < nt_g; ++j)
-            tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes, &map_w,
-                        &w_full[ws.stage], kc * pl.kch, (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn);
+            tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes, mw,
+                        &w_full[ws.stage], kcl * pl.kch, (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn);
           ws.next();
         }
       }
@@ -208,7 +228,10 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
         const int mtile = r % pl.n_mt;
         const int g = r / pl.n_mt;
         for (int kc = 0; kc < pl.n_kc; ++kc) {
-          const int c0 = g * p.Cig + kc * pl.kch;
+          const int kcl = X3 ? kc / 3 : kc;
+          const CUtensorMap* mx = (X3 && kc % 3 == 2) ? &map_x_lo : &map_x;
+          const CUtensorMap* mw = (X3 && kc % 3 == 1) ? &map_w_lo : &map_w;
+          const int c0 = g * p.Cig + kcl * pl.kch;
           mbar_wait(&a_empty[as.stage], as.phase ^ 1);
           const uint32_t a_dst = a_base + (uint32_t)as.stage * pl.a_stage_bytes;
           if (!pl.packed) {
@@ -218,7 +241,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
             mbar_expect_tx(&a_full[as.stage], (uint32_t)pl.n_ph * pl.nbox * pl.boxr * pl.row_bytes);
             for (int ph = 0; ph < pl.n_ph; ++ph)
               for (int b = 0; b < pl.nbox; ++b)
-                tma_load_4d(a_dst + (uint32_t)ph * pl.panel_bytes + (uint32_t)b * pl.boxr * pl.row_bytes, &map_x,
+                tma_load_4d(a_dst + (uint32_t)ph * pl.panel_bytes + (uint32_t)b * pl.boxr * pl.row_bytes, mx,
                             &a_full[as.stage], c0, n % p.x.n_inner, (qrow0 + b * pl.boxr) * p.si + pl.min_off + ph,
                             n / p.x.n_inner);
           } else {
@@ -228,7 +251,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
             for (int j = 0; j < nseg; ++j) {
               const int n = n0 + j;
               for (int ph = 0; ph < pl.n_ph; ++ph)
-                tma_load_4d(a_dst + (uint32_t)ph * pl.panel_bytes + (uint32_t)j * pl.seg_pitch * pl.row_bytes, &map_x,
+                tma_load_4d(a_dst + (uint32_t)ph * pl.panel_bytes + (uint32_t)j * pl.seg_pitch * pl.row_bytes, mx,
                             &a_full[as.stage], c0, n % p.x.n_inner, p.q0 * p.si + pl.min_off + ph, n / p.x.n_inner);
             }
           }
@@ -243,8 +266,8 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
 #endif
             mbar_expect_tx(&w_full[ws.stage], (uint32_t)nt_g * w_bytes);
             for (int j = 0; j < nt_g; ++j)
-              tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes, &map_w,
-                          &w_full[ws.stage], kc * pl.kch, (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn);
+              tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes, mw,
+                          &w_full[ws.stage], kcl * pl.kch, (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn);
             ws.next();
           }
         }
@@ -287,7 +310,8 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
             const int nt_g = min(tps, ntaps - t0);
             uint32_t w16;
             if (w_res) {
-              w16 = w_base16 + (uint32_t)(kc * ntaps + t0) * wt16;
+              const int wkc = X3 ? (kc % 3 == 1 ? pl.n_kcl + kc / 3 : kc / 3) : kc;
+              w16 = w_base16 + (uint32_t)(wkc * ntaps + t0) * wt16;
             } else {
               mbar_wait(&w_full[ws.stage], ws.phase);
               w16 = w_base16 + (uint32_t)ws.stage * ws16;
@@ -404,56 +428,130 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
           // coalesces better but costs ~5x the instructions; the epilogue of these small tiles is
           // issue-latency bound, not bandwidth bound: measured 5.6k vs 11.7k clocks per 256x128 tile.)
           const long long o = rowoff[m * 32 + lane];
-          // ---- (1) everything independent of the accumulator: operands of this lane's row, bias of the chunk
-          uint4 q_rp[4], q_mk[4], q_rs[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            q_rp[u] = q_mk[u] = q_rs[u] = make_uint4(0, 0, 0, 0);
-            if (o >= 0) {
-              if (res_pre) q_rp[u] = __ldg(reinterpret_cast<const uint4*>(res_pre + o + c0 + 8 * u));
-              if (mask) q_mk[u] = __ldg(reinterpret_cast<const uint4*>(mask + o + c0 + 8 * u));
-              if (res) q_rs[u] = __ldg(reinterpret_cast<const uint4*>(res + o + c0 + 8 * u));
+          if constexpr (X3) {
+            // bf16x3 mode: fp32 epilogue operands / outputs, optional split copies of the outputs
+            const float* __restrict__ res_pre32 = reinterpret_cast<const float*>(p.res_pre);
+            const float* __restrict__ mask32 = reinterpret_cast<const float*>(p.mask);
+            const float* __restrict__ res32 = reinterpret_cast<const float*>(p.res);
+            float* __restrict__ Y32 = reinterpret_cast<float*>(p.Y);
+            float* __restrict__ Y2_32 = reinterpret_cast<float*>(p.Y2);
+            TO* __restrict__ Ysp = reinterpret_cast<TO*>(p.Y_sp);
+            TO* __restrict__ Y2sp = reinterpret_cast<TO*>(p.Y2_sp);
+            if (!waited) {
+              mbar_wait(&acc_full[acc.stage], acc.phase);
+              tc_fence_after();
+              waited = true;
             }
-          }
-          if (!waited) {
-            mbar_wait(&acc_full[acc.stage], acc.phase);
-            if (threadIdx.x == 64) dbg_mark(pl.dbg, 30);
-            tc_fence_after();
-            waited = true;
-          }
-          // ---- (2) accumulator chunk
-          uint32_t acc_r[32];
-          tmem_ld32(t_row + c0, acc_r);
-          tmem_ld_wait();
-          // ---- (3) bias / residual / mask / activation, stores
-          if (o >= 0) {
+            uint32_t acc_r[32];
+            tmem_ld32(t_row + c0, acc_r);
+            tmem_ld_wait();
+            if (o >= 0) {
 #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 b0 = reinterpret_cast<const float4*>(bias_s + cj * 32)[2 * u], b1 = reinterpret_cast<const float4*>(bias_s + cj * 32)[2 * u + 1];
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const long long oc = o + c0 + 8 * u;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaf(p.alpha, __uint_as_float(acc_r[8 * u + i]), bb[i]);
+                if (res_pre32) {
+                  const float4 t0 = __ldg(reinterpret_cast<const float4*>(res_pre32 + oc)), t1 = __ldg(reinterpret_cast<const float4*>(res_pre32 + oc + 4));
+                  v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+                }
+                if (mask32) {
+                  const float4 t0 = __ldg(reinterpret_cast<const float4*>(mask32 + oc)), t1 = __ldg(reinterpret_cast<const float4*>(mask32 + oc + 4));
+                  const float mk[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] *= (mk[i] > 0.f ? 1.f : p.mask_slope);
+                }
+                if (res32) {
+                  const float4 t0 = __ldg(reinterpret_cast<const float4*>(res32 + oc)), t1 = __ldg(reinterpret_cast<const float4*>(res32 + oc + 4));
+                  v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+                }
+                if (Y32) {
+                  *reinterpret_cast<float4*>(Y32 + oc) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(Y32 + oc + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                if (Ysp) {
+                  const uint4 h = pack8(v);
+                  float hv[8], lv[8];
+                  unpack8<TO>(h, hv);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) lv[i] = v[i] - hv[i];
+                  *reinterpret_cast<uint4*>(Ysp + oc) = h;
+                  *reinterpret_cast<uint4*>(Ysp + p.y_plane + oc) = pack8(lv);
+                }
+                if (Y2_32 || Y2sp) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : neg_slope * v[i];
+                  if (Y2_32) {
+                    *reinterpret_cast<float4*>(Y2_32 + oc) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(Y2_32 + oc + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                  }
+                  if (Y2sp) {
+                    const uint4 h = pack8(v);
+                    float hv[8], lv[8];
+                    unpack8<TO>(h, hv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) lv[i] = v[i] - hv[i];
+                    *reinterpret_cast<uint4*>(Y2sp + oc) = h;
+                    *reinterpret_cast<uint4*>(Y2sp + p.y_plane + oc) = pack8(lv);
+                  }
+                }
+              }
+            }
+          } else {
+            // ---- (1) everything independent of the accumulator: operands of this lane's row, bias of the chunk
+            uint4 q_rp[4], q_mk[4], q_rs[4];
+  #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float4 b0 = reinterpret_cast<const float4*>(bias_s + cj * 32)[2 * u], b1 = reinterpret_cast<const float4*>(bias_s + cj * 32)[2 * u + 1];
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              float v[8], tmp[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaf(p.alpha, __uint_as_float(acc_r[8 * u + i]), bb[i]);
-              if (res_pre) {
-                unpack8<TO>(q_rp[u], tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+              q_rp[u] = q_mk[u] = q_rs[u] = make_uint4(0, 0, 0, 0);
+              if (o >= 0) {
+                if (res_pre) q_rp[u] = __ldg(reinterpret_cast<const uint4*>(res_pre + o + c0 + 8 * u));
+                if (mask) q_mk[u] = __ldg(reinterpret_cast<const uint4*>(mask + o + c0 + 8 * u));
+                if (res) q_rs[u] = __ldg(reinterpret_cast<const uint4*>(res + o + c0 + 8 * u));
               }
-              if (mask) {
-                unpack8<TO>(q_mk[u], tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= (tmp[i] > 0.f ? 1.f : p.mask_slope);
-              }
-              if (res) {
-                unpack8<TO>(q_rs[u], tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += tmp[i];
-              }
-              if (Y) *reinterpret_cast<uint4*>(Y + o + c0 + 8 * u) = pack8(v);
-              if (Y2) {   // second output: LeakyReLU (or identity: neg_slope = 1); tanh layers never reach this kernel
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : neg_slope * v[i];
-                *reinterpret_cast<uint4*>(Y2 + o + c0 + 8 * u) = pack8(v);
+            }
+            if (!waited) {
+              mbar_wait(&acc_full[acc.stage], acc.phase);
+              if (threadIdx.x == 64) dbg_mark(pl.dbg, 30);
+              tc_fence_after();
+              waited = true;
+            }
+            // ---- (2) accumulator chunk
+            uint32_t acc_r[32];
+            tmem_ld32(t_row + c0, acc_r);
+            tmem_ld_wait();
+            // ---- (3) bias / residual / mask / activation, stores
+            if (o >= 0) {
+  #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 b0 = reinterpret_cast<const float4*>(bias_s + cj * 32)[2 * u], b1 = reinterpret_cast<const float4*>(bias_s + cj * 32)[2 * u + 1];
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float v[8], tmp[8];
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaf(p.alpha, __uint_as_float(acc_r[8 * u + i]), bb[i]);
+                if (res_pre) {
+                  unpack8<TO>(q_rp[u], tmp);
+  #pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+                }
+                if (mask) {
+                  unpack8<TO>(q_mk[u], tmp);
+  #pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] *= (tmp[i] > 0.f ? 1.f : p.mask_slope);
+                }
+                if (res) {
+                  unpack8<TO>(q_rs[u], tmp);
+  #pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] += tmp[i];
+                }
+                if (Y) *reinterpret_cast<uint4*>(Y + o + c0 + 8 * u) = pack8(v);
+                if (Y2) {   // second output: LeakyReLU (or identity: neg_slope = 1); tanh layers never reach this kernel
+  #pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : neg_slope * v[i];
+                  *reinterpret_cast<uint4*>(Y2 + o + c0 + 8 * u) = pack8(v);
+                }
               }
             }
           }
@@ -523,9 +621,11 @@ static int max_smem() {
     if (optin <= 0) optin = 227 * 1024;
     cudaFuncAttributes fa;
     int stat = 2048;
-    if (cudaFuncGetAttributes(&fa, tapconv_tc_kernel) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+    if (cudaFuncGetAttributes(&fa, tapconv_tc_kernel<false>) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+    if (cudaFuncGetAttributes(&fa, tapconv_tc_kernel<true>) == cudaSuccess && (int)fa.sharedSizeBytes > stat) stat = (int)fa.sharedSizeBytes;
     int dyn = optin - stat;
-    if (cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tapconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess ||
+        cudaFuncSetAttribute(tapconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) {
       cudaGetLastError();
       dyn = 48 * 1024;
     }
@@ -577,20 +677,27 @@ extern "C" int artic_debug_set(int key, int value) {
   return ARTIC_OK;
 }
 
+static inline int w_all_bytes(const tc::Plan& pl, int ntaps, bool x3) { return (x3 ? 2 * pl.n_kcl : pl.n_kc) * ntaps * pl.w_tile_bytes; }
+
 // Plans one problem for the tensor-core kernel: returns 1 (pr filled: parameters, plan, tensor maps,
 // pr_smem / pr_cost set), 0 if the shape is not eligible, <0 on error.
 // n_share = number of problems that will share the grid (each gets ~1/n_share of the SMs).
 static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem, double& pr_cost, int n_share) {
   const artic_tapconv_t& p = *pp;
   if (tc::g_debug[1]) return 0;                       // debug: force the generic kernel
-  if (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16 || p.act == ARTIC_ACT_TANH || p.res2 != nullptr) return 0;
+  const bool x3 = p.dtype == ARTIC_F32 && p.out_dtype == ARTIC_F32 && p.X_sp != nullptr && p.Wt_sp != nullptr;
+  if (!x3 && (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16)) return 0;
+  if (x3 && tc::g_debug[20] == 1) return 0;            // debug: bf16x3 problems on the CUDA-core kernel
+  if (p.act == ARTIC_ACT_TANH || p.res2 != nullptr) return 0;
   if (p.si < 1 || p.si > 8) return 0;
   if (p.Cig % 16 != 0 || p.Cog % 32 != 0) return 0;
   if ((p.x.s_row % 8) || (p.x.s_outer % 8) || (p.x.n_inner > 1 && (p.x.s_inner % 8))) return 0;
   if ((p.y.s_row % 8) || (p.y.s_outer % 8) || (p.y.n_inner > 1 && (p.y.s_inner % 8))) return 0;
-  const void* ptrs[] = {p.X, p.Wt, p.res_pre, p.mask, p.res, p.res2, p.Y, p.Y2};
+  const void* ptrs[] = {x3 ? p.X_sp : p.X, x3 ? p.Wt_sp : p.Wt, p.res_pre, p.mask, p.res, p.res2, p.Y, p.Y2, x3 ? p.Y_sp : nullptr,
+                        x3 ? p.Y2_sp : nullptr};
   for (const void* q : ptrs)
     if (q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15)) return 0;
+  if (x3 && ((p.x_plane % 8) || (p.w_plane % 8) || (p.y_plane % 8))) return 0;
   tc::EncodeTiledFn enc = tc::encode_fn();
   if (enc == nullptr) return 0;
 
@@ -618,7 +725,8 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
   }
   pl.kch = (p.Cig % 64 == 0) ? 64 : (p.Cig % 32 == 0) ? 32 : 16;
   pl.row_bytes = pl.kch * 2;
-  pl.n_kc = p.Cig / pl.kch;
+  pl.n_kcl = p.Cig / pl.kch;
+  pl.n_kc = x3 ? 3 * pl.n_kcl : pl.n_kcl;
   pl.layout_type = pl.row_bytes == 128 ? 2 : pl.row_bytes == 64 ? 4 : 6;
   pl.bn = bn_req;
   pl.n_nt = p.Cog / pl.bn;
@@ -671,7 +779,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
   // generator stages — their per-tile weight traffic would otherwise serialise the producer) or
   // streamed through up to MAX_WS stages; the rest goes to activation stages, because the bytes in
   // flight per SM (x ~2 us TMA latency) are what bounds the operand bandwidth.
-  const int w_all = pl.n_kc * p.ntaps * pl.w_tile_bytes;
+  const int w_all = (x3 ? 2 * pl.n_kcl : pl.n_kc) * p.ntaps * pl.w_tile_bytes;
   pl.w_resident = (pl.n_nt == 1 && p.G == 1 && w_all <= 96 * 1024 && budget - w_all >= 2 * pl.a_stage_bytes &&
                    tc::g_debug[7] != 1) ? 1 : 0;
   if (pl.w_resident) {
@@ -768,9 +876,14 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
     // rows are traversed with stride si: a box of rows*si elements loads `rows` rows (one phase)
     cuuint32_t box[4] = {(cuuint32_t)pl.kch, 1, (cuuint32_t)((pl.packed ? pl.seg_rows : pl.boxr) * p.si), 1};
     cuuint32_t es[4] = {1, 1, (cuuint32_t)p.si, 1};
-    CUresult rc = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.X), dims, strides, box, es,
+    CUresult rc = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x3 ? p.X_sp : p.X), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swizzle_of(pl.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc == CUDA_SUCCESS && x3)
+      rc = enc(&pr.map_x_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+               const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(p.X_sp) + p.x_plane), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swizzle_of(pl.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("artic_tapconv: cuTensorMapEncodeTiled(X) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   }
   {
@@ -781,19 +894,24 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
     cuuint64_t strides[1] = {(cuuint64_t)p.Cig * 2};
     cuuint32_t box[2] = {(cuuint32_t)pl.kch, (cuuint32_t)pl.bn};
     cuuint32_t es[2] = {1, 1};
-    CUresult rc = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.Wt), dims, strides, box, es,
+    CUresult rc = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x3 ? p.Wt_sp : p.Wt), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swizzle_of(pl.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc == CUDA_SUCCESS && x3)
+      rc = enc(&pr.map_w_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+               const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(p.Wt_sp) + p.w_plane), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swizzle_of(pl.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("artic_tapconv: cuTensorMapEncodeTiled(W) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   }
-  pr_smem = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? pl.n_kc * p.ntaps * pl.w_tile_bytes : pl.n_ws * pl.w_stage_bytes) + 1024 + epi_bytes;
+  pr_smem = pl.n_as * pl.a_stage_bytes + (pl.w_resident ? w_all_bytes(pl, p.ntaps, x3) : pl.n_ws * pl.w_stage_bytes) + 1024 + epi_bytes;
   pr.p = p;
   pr.pl = pl;
   return 1;
 }
 
 // Launches up to MAXP planned problems as ONE grid of per-problem persistent CTA ranges.
-static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, cudaStream_t st) {
+static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, cudaStream_t st, bool x3) {
   const int n = mp.n;
   const int n_ew = (tc::g_debug[8] > 0 && tc::g_debug[8] * 1024 < tc::max_smem()) ? 4 : 8;
   int64_t tiles = 0;
@@ -831,7 +949,8 @@ static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, c
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = w_early ? 1 : 0;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, tc::tapconv_tc_kernel, mp);
+  cudaError_t le = x3 ? cudaLaunchKernelEx(&cfg, tc::tapconv_tc_kernel<true>, mp) : cudaLaunchKernelEx(&cfg, tc::tapconv_tc_kernel<false>, mp);
+  g_path_counts[x3 ? PATH_CONV_TC_X3 : PATH_CONV_TC] += n;
   if (le == cudaSuccess) le = cudaGetLastError();
   if (le != cudaSuccess) {
     const tc::Plan& pl = mp.prob[0].pl;
@@ -852,21 +971,29 @@ int artic_tapconv_tc_multi(const artic_tapconv_t* ps, int n, int* taken, cudaStr
   int n_live = 0;
   for (int i = 0; i < n; ++i) n_live += (ps[i].N != 0 && ps[i].nq != 0) ? 1 : 0;
   const int n_share = tc::g_debug[10] == 1 ? 1 : n_live < tc::MAXP ? n_live : tc::MAXP;   // debug key 10 = 1: plan as if alone
+  bool group_x3 = false;
   for (int i = 0; i < n; ++i) {
     taken[i] = 0;
     if (ps[i].N == 0 || ps[i].nq == 0) continue;
+    const bool x3 = ps[i].dtype == ARTIC_F32;       // the two modes are different kernel instantiations
+    if (mp.n > 0 && x3 != group_x3) {
+      const int lrc = tc_launch_group(mp, smem, cost, st, group_x3);
+      if (lrc != ARTIC_OK) return lrc;
+      mp.n = 0;
+    }
     const int rc = tc_plan_problem(&ps[i], mp.prob[mp.n], smem[mp.n], cost[mp.n], n_share);
     if (rc < 0) return rc;
     if (rc == 0) continue;
     taken[i] = 1;
+    group_x3 = x3;
     if (++mp.n == tc::MAXP) {
-      const int lrc = tc_launch_group(mp, smem, cost, st);
+      const int lrc = tc_launch_group(mp, smem, cost, st, group_x3);
       if (lrc != ARTIC_OK) return lrc;
       mp.n = 0;
     }
   }
   if (mp.n > 0) {
-    const int lrc = tc_launch_group(mp, smem, cost, st);
+    const int lrc = tc_launch_group(mp, smem, cost, st, group_x3);
     if (lrc != ARTIC_OK) return lrc;
   }
   return ARTIC_OK;

@@ -18,6 +18,9 @@
 // the tap groups are cut per phase when that moves fewer operand bytes, so a CTA loads only the
 // ONE panel its accumulators read and the co tile widens (up to 256).
 //
+// bf16x3 mode (template X3; fp32 X / dY with split copies, see tapconv_tc.cu): every position chunk is issued
+// three times — (x_hi, dy_hi), (x_hi, dy_lo), (x_lo, dy_hi) — into the same accumulators.
+//
 // Zero padding / sequence boundaries: rows outside [0, len) are zero-filled by TMA; short
 // sequences are packed back to back with their halos (pitch = L + span), the padding rows of
 // dY being zero so that they contribute nothing.  The staging area is zeroed once so that rows
@@ -79,9 +82,17 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+struct WMaps {
+  CUtensorMap x, y, x_lo, y_lo;
+};
+
+template <bool X3>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_constant__ WPlan pl,
-                   const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y) {
+                   const __grid_constant__ WMaps maps) {
+  const CUtensorMap& map_x = maps.x;
+  const CUtensorMap& map_y = maps.y;
+  constexpr int R = X3 ? 3 : 1;     // passes per position chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full[WG_MAX_STAGES], empty[WG_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full;
@@ -116,6 +127,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_x);
     prefetch_tmap(&map_y);
+    if (X3) { prefetch_tmap(&maps.x_lo); prefetch_tmap(&maps.y_lo); }
     for (int i = 0; i < pl.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -133,7 +145,10 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
       const int cx0 = g * p.Cig + mb * pl.mci;
       const int cy0 = g * p.Cog + nt * pl.bn;
       const int xch = pl.xrb / 2, ych = pl.yrb / 2;
-      for (int c = c_begin; c < c_end; ++c) {
+      for (int cc = c_begin * R; cc < c_end * R; ++cc) {
+        const int c = cc / R, part = cc % R;
+        const CUtensorMap* mx = (X3 && part == 2) ? &maps.x_lo : &map_x;
+        const CUtensorMap* my = (X3 && part == 1) ? &maps.y_lo : &map_y;
         mbar_wait(&empty[ps.stage], ps.phase ^ 1);
         const uint32_t xs = smem0 + (uint32_t)ps.stage * pl.stage_bytes;
         const uint32_t ys = xs + (uint32_t)(pl.n_ph * pl.nxp) * pl.x_panel_bytes;
@@ -145,11 +160,11 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
           for (int ph = 0; ph < pl.n_ph; ++ph)
             for (int pn = 0; pn < pl.nxp && ((ph_mask >> ph) & 1u); ++pn)
               for (int b = 0; b < pl.nxb; ++b)
-                tma_load_4d(xs + (uint32_t)(ph * pl.nxp + pn) * pl.x_panel_bytes + (uint32_t)b * pl.boxr * pl.xrb, &map_x,
+                tma_load_4d(xs + (uint32_t)(ph * pl.nxp + pn) * pl.x_panel_bytes + (uint32_t)b * pl.boxr * pl.xrb, mx,
                             &full[ps.stage], cx0 + pn * xch, n % p.x.n_inner, (qc + b * pl.boxr) * p.si + pl.min_off + ph,
                             n / p.x.n_inner);
           for (int pn = 0; pn < pl.nyp; ++pn)
-            tma_load_4d(ys + (uint32_t)pn * pl.y_panel_bytes, &map_y, &full[ps.stage], cy0 + pn * ych, n % p.y.n_inner,
+            tma_load_4d(ys + (uint32_t)pn * pl.y_panel_bytes, my, &full[ps.stage], cy0 + pn * ych, n % p.y.n_inner,
                         qc + p.yoff[0], n / p.y.n_inner);
         } else {
           const int n0 = c * pl.seg_per_chunk;
@@ -160,10 +175,10 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
             for (int ph = 0; ph < pl.n_ph; ++ph)
               for (int pn = 0; pn < pl.nxp && ((ph_mask >> ph) & 1u); ++pn)
                 tma_load_4d(xs + (uint32_t)(ph * pl.nxp + pn) * pl.x_panel_bytes + (uint32_t)j * pl.seg_pitch * pl.xrb,
-                            &map_x, &full[ps.stage], cx0 + pn * xch, n % p.x.n_inner, p.q0 * p.si + pl.min_off + ph,
+                            mx, &full[ps.stage], cx0 + pn * xch, n % p.x.n_inner, p.q0 * p.si + pl.min_off + ph,
                             n / p.x.n_inner);
             for (int pn = 0; pn < pl.nyp; ++pn)
-              tma_load_4d(ys + (uint32_t)pn * pl.y_panel_bytes + (uint32_t)j * pl.seg_pitch * pl.yrb, &map_y,
+              tma_load_4d(ys + (uint32_t)pn * pl.y_panel_bytes + (uint32_t)j * pl.seg_pitch * pl.yrb, my,
                           &full[ps.stage], cy0 + pn * ych, n % p.y.n_inner, p.q0 + p.yoff[0], n / p.y.n_inner);
           }
         }
@@ -185,7 +200,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
       const uint32_t a_lo0 = (((uint32_t)pl.a_lbo >> 4) & 0x3fffu) << 16;
       const uint32_t b_lo0 = (((uint32_t)pl.y_panel_bytes >> 4) & 0x3fffu) << 16;
       uint32_t accum = 0;
-      for (int c = c_begin; c < c_end; ++c) {
+      for (int cc = c_begin * R; cc < c_end * R; ++cc) {
         mbar_wait(&full[ps.stage], ps.phase);
         tc_fence_after();
         const uint32_t xs = smem0 + (uint32_t)ps.stage * pl.stage_bytes;
@@ -286,9 +301,11 @@ static int wg_max_smem() {
     if (optin <= 0) optin = 227 * 1024;
     cudaFuncAttributes fa;
     int stat = 2048;
-    if (cudaFuncGetAttributes(&fa, tapwgrad_tc_kernel) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+    if (cudaFuncGetAttributes(&fa, tapwgrad_tc_kernel<false>) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+    if (cudaFuncGetAttributes(&fa, tapwgrad_tc_kernel<true>) == cudaSuccess && (int)fa.sharedSizeBytes > stat) stat = (int)fa.sharedSizeBytes;
     int dyn = optin - stat;
-    if (cudaFuncSetAttribute(tapwgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tapwgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess ||
+        cudaFuncSetAttribute(tapwgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) {
       cudaGetLastError();
       dyn = 48 * 1024;
     }
@@ -320,12 +337,16 @@ using namespace artic;
 int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   const artic_tapwgrad_t& p = *pp;
   if (tc::g_debug[1] || tc::g_debug[5]) return 0;
-  if (p.dtype != ARTIC_BF16 || p.y_dtype != ARTIC_BF16) return 0;
+  const bool x3 = p.dtype == ARTIC_F32 && p.y_dtype == ARTIC_F32 && p.X_sp != nullptr && p.dY_sp != nullptr;
+  if (!x3 && (p.dtype != ARTIC_BF16 || p.y_dtype != ARTIC_BF16)) return 0;
+  if (x3 && (tc::g_debug[20] == 1 || (p.x_plane % 8) || (p.y_plane % 8))) return 0;
+  const void* Xb = x3 ? p.X_sp : p.X;
+  const void* Yb = x3 ? p.dY_sp : p.dY;
   if (p.si < 1 || p.si > 8 || p.so != 1) return 0;
   if (!(p.Cig == 32 || p.Cig == 64 || p.Cig % 128 == 0) || p.Cog % 32 != 0) return 0;
   if ((p.x.s_row % 8) || (p.x.s_outer % 8) || (p.x.n_inner > 1 && (p.x.s_inner % 8))) return 0;
   if ((p.y.s_row % 8) || (p.y.s_outer % 8) || (p.y.n_inner > 1 && (p.y.s_inner % 8))) return 0;
-  if ((reinterpret_cast<uintptr_t>(p.X) & 15) || (reinterpret_cast<uintptr_t>(p.dY) & 15) ||
+  if ((reinterpret_cast<uintptr_t>(Xb) & 15) || (reinterpret_cast<uintptr_t>(Yb) & 15) ||
       (reinterpret_cast<uintptr_t>(p.dW) & 15))
     return 0;
   for (int t = 1; t < p.ntaps; ++t)
@@ -469,7 +490,7 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
     // loop of at least `min_clk` tensor-core clocks (debug key 14, in units of 1000 clocks; default 6: 12.70 -> 12.55 ms) rather
     // than spreading a small layer over all SMs.
     const double per_mma = pl.bn / 2.0 > 32.0 + pl.bn / 4.0 ? pl.bn / 2.0 : 32.0 + pl.bn / 4.0;
-    const double chunk_clk = (double)pl.apc * (pl.kp / 16) * per_mma;
+    const double chunk_clk = (double)pl.apc * (pl.kp / 16) * per_mma * (x3 ? 3 : 1);
     const double min_clk = 1000.0 * (tc::g_debug[14] > 0 ? tc::g_debug[14] : tc::g_debug[14] < 0 ? 0 : 6);
     int64_t min_chunks = (int64_t)(min_clk / chunk_clk + 0.999);
     if (min_chunks < 1) min_chunks = 1;
@@ -479,17 +500,24 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   if (splits < 1) splits = 1;
   pl.chunks_per_split = (int)((pl.n_chunks + splits - 1) / splits);
   pl.n_splits = (pl.n_chunks + pl.chunks_per_split - 1) / pl.chunks_per_split;
-  if (pl.n_stages > pl.chunks_per_split + 1) pl.n_stages = pl.chunks_per_split + 1;
+  if (pl.n_stages > (x3 ? 3 : 1) * pl.chunks_per_split + 1) pl.n_stages = (x3 ? 3 : 1) * pl.chunks_per_split + 1;
   if (pl.n_stages < 2) pl.n_stages = 2;
   const int64_t grid = base * pl.n_splits;
   if (grid > (1 << 30)) return 0;
 
-  CUtensorMap map_x, map_y;
-  CUresult rc = tc::encode_seq_map(enc, &map_x, p.X, p.x, p.N, p.G * p.Cig, pl.xrb / 2,
+  static thread_local tc::WMaps maps;
+  CUresult rc = tc::encode_seq_map(enc, &maps.x, Xb, p.x, p.N, p.G * p.Cig, pl.xrb / 2,
                                    pl.packed ? pl.seg_pitch : pl.boxr, pl.xrb, si);
+  if (rc == CUDA_SUCCESS && x3)
+    rc = tc::encode_seq_map(enc, &maps.x_lo, reinterpret_cast<const __nv_bfloat16*>(Xb) + p.x_plane, p.x, p.N, p.G * p.Cig,
+                            pl.xrb / 2, pl.packed ? pl.seg_pitch : pl.boxr, pl.xrb, si);
   if (rc != CUDA_SUCCESS) { set_error("artic_tapconv_wgrad: cuTensorMapEncodeTiled(X) failed (%d)", (int)rc); return ARTIC_ECUDA; }
-  rc = tc::encode_seq_map(enc, &map_y, p.dY, p.y, p.N, p.G * p.Cog, pl.yrb / 2, pl.packed ? pl.seg_pitch : pl.kp, pl.yrb, 1);
+  rc = tc::encode_seq_map(enc, &maps.y, Yb, p.y, p.N, p.G * p.Cog, pl.yrb / 2, pl.packed ? pl.seg_pitch : pl.kp, pl.yrb, 1);
+  if (rc == CUDA_SUCCESS && x3)
+    rc = tc::encode_seq_map(enc, &maps.y_lo, reinterpret_cast<const __nv_bfloat16*>(Yb) + p.y_plane, p.y, p.N, p.G * p.Cog,
+                            pl.yrb / 2, pl.packed ? pl.seg_pitch : pl.kp, pl.yrb, 1);
   if (rc != CUDA_SUCCESS) { set_error("artic_tapconv_wgrad: cuTensorMapEncodeTiled(dY) failed (%d)", (int)rc); return ARTIC_ECUDA; }
+  if (!x3) { maps.x_lo = maps.x; maps.y_lo = maps.y; }
   pl.dbg_flags = tc::g_debug[13];
   pl.epi_transposed = tc::g_debug[18] == 1 ? 0 : 1;
   pl.trace = tc::g_trace_buf;
@@ -497,7 +525,9 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   pl.launch_id = tc::g_trace_buf != nullptr ? tc::g_trace_launch++ : 0;
   const int epi_need = 4 * 32 * 8 * 16 + 4 * 32 * 8;    // transpose stages + row pointers (overlaid on the operand stages)
   const int smem_bytes = (pl.n_stages * pl.stage_bytes > epi_need ? pl.n_stages * pl.stage_bytes : epi_need) + 1024 + tc::WG_EPI_BYTES;
-  tc::tapwgrad_tc_kernel<<<(unsigned)grid, tc::WG_THREADS, smem_bytes, st>>>(p, pl, map_x, map_y);
+  if (x3) tc::tapwgrad_tc_kernel<true><<<(unsigned)grid, tc::WG_THREADS, smem_bytes, st>>>(p, pl, maps);
+  else tc::tapwgrad_tc_kernel<false><<<(unsigned)grid, tc::WG_THREADS, smem_bytes, st>>>(p, pl, maps);
+  ++g_path_counts[x3 ? PATH_WGRAD_TC_X3 : PATH_WGRAD_TC];
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     set_error("artic_tapconv_wgrad(tc): launch failed: %s (grid %lld, smem %d of %d, bn %d acc %d stages %d packed %d)",

@@ -18,8 +18,12 @@ class SpeechCollater(object):
     """Customized collater for the PyTorch DataLoader in training (reference bin/train.py:865)."""
 
     def __init__(self, batch_max_steps=20480, hop_size=256, aux_context_window=0, use_noise_input=False,
-                 dataset_mode="a2w", use_spk_id=False, use_ph=False, config=None):
+                 dataset_mode="a2w", use_spk_id=False, use_ph=False, config=None, rng=None):
+        """``rng``: object with ``randint(lo, hi)`` drawing the window starts; default = the global ``np.random``
+        (as the reference).  A collater used beside a prefetching train loop (dev batches) gets its own
+        ``np.random.RandomState`` so that it does not perturb the train windows."""
         assert batch_max_steps % hop_size == 0
+        self.rng = np.random if rng is None else rng
         if dataset_mode != "a2w":
             raise NotImplementedError("only dataset_mode 'a2w' (articulatory -> waveform) is on the B200 hot path")
         if use_spk_id or use_ph:
@@ -66,7 +70,7 @@ class SpeechCollater(object):
                 audios.append(audio)
                 arts.append(art)
         # one np.random.randint per kept item, in order (reference :1013)
-        starts = np.array([np.random.randint(self.start_offset, len(c) + self.end_offset) for c in arts])
+        starts = np.array([self.rng.randint(self.start_offset, len(c) + self.end_offset) for c in arts])
         plans = [self.window_plan(len(a), len(c), int(s)) for a, c, s in zip(audios, arts, starts)]
         audio_batch = np.stack([a[p["wav"][0]:p["wav"][1]] for a, p in zip(audios, plans)], axis=0)
         art_batch = np.stack([c[p["art"][0]:p["art"][1]] for c, p in zip(arts, plans)], axis=0)
@@ -97,13 +101,17 @@ class BatchPrefetcher(object):
 
     _END = object()
 
-    def __init__(self, make_batch, jobs, depth=2, pin=True):
+    def __init__(self, make_batch, jobs, depth=2, pin=True, device=None):
+        """``device``: the rank's CUDA device.  The CUDA current device is per THREAD: without setting it here the
+        worker would pin through a fresh context on cuda:0 on every rank."""
         self._q = queue.Queue(maxsize=max(int(depth), 1))
         self._stop = threading.Event()
-        self._pin = pin
+        self._pin = pin and torch.cuda.is_available()
 
         def work():
             try:
+                if device is not None and torch.cuda.is_available():
+                    torch.cuda.set_device(device)
                 for job in jobs:
                     if self._stop.is_set():
                         return

@@ -28,15 +28,40 @@ from .convspec import ConvSpec
 # tensors                                                                     #
 # --------------------------------------------------------------------------- #
 class SeqT:
-    """Channels-last sequence batch in a torch tensor (see include/artic.h artic_seq_t)."""
-    __slots__ = ("t", "N", "L", "C", "n_inner", "s_outer", "s_inner", "s_row", "code")
+    """Channels-last sequence batch in a torch tensor (see include/artic.h artic_seq_t).
 
-    def __init__(self, t, N, L, C, n_inner=1, s_outer=None, s_inner=0, s_row=None):
+    bf16x3 mode: an fp32 batch may carry a SPLIT COPY ``sp`` — a bf16 tensor of shape (2,) + t.shape holding
+    hi = bf16(t) and lo = bf16(t - hi), the operand format of the error-compensated tensor-core contraction.  It is
+    written by the producing kernel (artic_tapconv_t.Y_sp) or on demand (``ensure_split``); views of the same
+    storage (``flat_period``) share it through ``_h``."""
+    __slots__ = ("t", "N", "L", "C", "n_inner", "s_outer", "s_inner", "s_row", "code", "_h")
+
+    def __init__(self, t, N, L, C, n_inner=1, s_outer=None, s_inner=0, s_row=None, _h=None):
         self.t, self.N, self.L, self.C, self.n_inner = t, N, L, C, n_inner
         self.s_row = C if s_row is None else s_row
         self.s_outer = L * C if s_outer is None else s_outer
         self.s_inner = s_inner
         self.code = _lib.DTYPE_CODE[t.dtype]
+        self._h = [None] if _h is None else _h
+
+    @property
+    def sp(self):
+        return self._h[0]
+
+    def split_out(self):
+        """The split-copy planes of this batch, allocated on first use (for a producer to fill)."""
+        if self._h[0] is None:
+            assert self.code == F32 and self.t.is_contiguous()
+            self._h[0] = torch.empty((2,) + tuple(self.t.shape), dtype=torch.bfloat16, device=self.t.device)
+        return self._h[0]
+
+    def ensure_split(self):
+        """Split copy of the CURRENT contents (one elementwise launch on the current stream unless a producer
+        already wrote it).  Call it on the stream that produced ``t``, before any fork that consumes it."""
+        if self._h[0] is None:
+            sp = self.split_out()
+            call("artic_split", ptr(self.t), ptr(sp), sp.stride(0), self.t.numel())
+        return self._h[0]
 
     @staticmethod
     def empty(N, L, C, code, device, zero=False):
@@ -75,10 +100,12 @@ def _fill_taps(dst_off, dst_idx, off, widx):
 def tapconv_params(launches, X: SeqT, W, G, Cig, Cog, Y: Optional[SeqT] = None, Y2: Optional[SeqT] = None,
                    bias=None, res_pre: Optional[SeqT] = None, mask: Optional[SeqT] = None,
                    res: Optional[SeqT] = None, res2: Optional[SeqT] = None, alpha=1.0, mask_slope=1.0,
-                   act=ACT_NONE, act_slope=0.0, Wt=None):
+                   act=ACT_NONE, act_slope=0.0, Wt=None, Wt_sp=None, sp_y=False, sp_y2=False):
     """The artic_tapconv_t parameter blocks of one layer direction (one per launch phase).  ``Wt`` is the
     same weight in the transposed prepared layout [K][G][Cog][Cig] (enables the tcgen05 kernel).
-    Returns (list of TapConv, tensors to keep alive until the launch is enqueued)."""
+    bf16x3 mode: ``Wt_sp`` = (split copy of Wt: bf16 hi plane, element distance to the lo plane); X then travels
+    with its split copy, and ``sp_y`` / ``sp_y2`` ask for split copies of Y / Y2 (outputs that already own one are
+    always kept in sync)."""
     yref = Y if Y is not None else Y2
     assert yref is not None and X.C == G * Cig and yref.C == G * Cog and X.N == yref.N
     for o in (Y, Y2, res_pre, mask, res, res2):
@@ -103,6 +130,16 @@ def tapconv_params(launches, X: SeqT, W, G, Cig, Cog, Y: Optional[SeqT] = None, 
         p.dtype, p.out_dtype = X.code, yref.code
         if Wt is not None and Wt.dtype == W.dtype:
             p.Wt, p.Wt_taps = ptr(Wt), Wt.shape[0]
+        if Wt_sp is not None and X.code == F32 and yref.code == F32:
+            xs = X.ensure_split()
+            p.X_sp, p.x_plane = ptr(xs), xs.stride(0)
+            p.Wt_sp, p.w_plane = ptr(Wt_sp[0]), Wt_sp[1]
+        for o, want, field in ((Y, sp_y, "Y_sp"), (Y2, sp_y2, "Y2_sp")):
+            if o is not None and o.code == F32 and (want or o.sp is not None):
+                so = o.split_out()
+                assert p.y_plane in (0, so.stride(0)), "Y and Y2 split copies must share their plane distance"
+                setattr(p, field, ptr(so))
+                p.y_plane = so.stride(0)
         out.append(p)
     return out
 
@@ -240,7 +277,8 @@ class SideQueue:
 
 def slice_seq(s: SeqT, lo: int, hi: int) -> SeqT:
     """View of batch items [lo, hi) (the batch is the leading tensor dim in every layout)."""
-    return SeqT(s.t[lo:hi], (hi - lo) * s.n_inner, s.L, s.C, s.n_inner, s.s_outer, s.s_inner, s.s_row)
+    h = [s.sp[:, lo:hi]] if s.sp is not None else None
+    return SeqT(s.t[lo:hi], (hi - lo) * s.n_inner, s.L, s.C, s.n_inner, s.s_outer, s.s_inner, s.s_row, _h=h)
 
 
 def flat_period(s: SeqT) -> SeqT:
@@ -250,7 +288,7 @@ def flat_period(s: SeqT) -> SeqT:
     if s.n_inner == 1:
         return s
     B = s.N // s.n_inner
-    return SeqT(s.t, B, s.L * s.n_inner, s.C, n_inner=1, s_outer=s.s_outer, s_inner=0, s_row=s.s_inner)
+    return SeqT(s.t, B, s.L * s.n_inner, s.C, n_inner=1, s_outer=s.s_outer, s_inner=0, s_row=s.s_inner, _h=s._h)
 
 
 class ConvLayer:
@@ -259,30 +297,37 @@ class ConvLayer:
     ``in_code`` is the storage dtype of the layer input (and of the forward weight),
     ``out_code`` the dtype of its output (and of the dY / backward weight)."""
 
-    def __init__(self, spec: ConvSpec, name: str, in_code: int, out_code: int, pad_in: bool = False):
+    def __init__(self, spec: ConvSpec, name: str, in_code: int, out_code: int, pad_in: bool = False, x3: bool = False):
         self.spec, self.name, self.in_code, self.out_code = spec, name, in_code, out_code
+        # bf16x3 mode: fp32 storage, split-operand tensor-core contraction (artic.h: artic_tapconv_t.X_sp)
+        self.x3 = bool(x3) and in_code == F32 and out_code == F32
+        tc = self.x3 or (in_code == BF16 and out_code == BF16)     # layer may run on the tcgen05 kernels
         # Narrow grouped convs (< 32 channels per group, e.g. the scale discriminator's 128->256
         # g16 layer with 8 -> 16 channels per group) would starve the tensor-core tiles: in the
         # bf16 mode `mg` groups are merged into one super-group whose weight is block-diagonal
         # (artic_wdesc_t.merge), trading mg x redundant MACs for full MMA tiles.
         mg = 1
-        if in_code == BF16 and out_code == BF16 and spec.groups > 1:
+        if tc and spec.groups > 1:
             while (spec.cig * mg < 32 or spec.cog * mg < 32) and spec.groups % (2 * mg) == 0:
                 mg *= 2
         self.mg = mg
         self.kG, self.kcig, self.kcog = spec.groups // mg, spec.cig * mg, spec.cog * mg   # kernel-facing dims
         # Odd input widths (the generator's 13 + 128 = 141-channel input conv) are zero-padded to a
         # multiple of 32 channels so that the layer runs on the tensor-core kernel.
-        if pad_in and in_code == BF16 and out_code == BF16 and spec.groups == 1 and spec.cin >= 32 and spec.cin % 16:
+        if pad_in and tc and spec.groups == 1 and spec.cin >= 32 and spec.cin % 16:
             self.kcig = (spec.cin + 31) // 32 * 32
             if self.kcig > 128:      # the tcgen05 weight-gradient kernel wants 32 / 64 / k * 128 input channels
                 self.kcig = (spec.cin + 127) // 128 * 128
         # Transposed convs get their weight gradient as the weight gradient of the equivalent strided conv
         # with X and dY exchanged (dW^T, i.e. the 'bwd' layout): that contraction has unit output stride,
         # which the tcgen05 wgrad kernel requires.
-        self.dw_swapped = spec.kind == "convT" and in_code == BF16 and out_code == BF16
+        if self.x3 and (self.kcig % 16 or self.kcog % 32):
+            self.x3 = False                      # channel-1 ends / odd widths stay on the fp32 CUDA-core kernels
+            tc = False
+        self.dw_swapped = spec.kind == "convT" and tc
         self.v = self.g = self.b = None          # torch parameters (fp32, device)
         self.Wf = self.Wb = self.scale = None    # prepared weights
+        self.Wf_sp = self.Wb_sp = None           # bf16x3: (hi plane of the split copy, distance to the lo plane)
         self.dWf = None                          # fp32 wgrad accumulator, 'fwd' layout
         self._own = None                         # single-layer WeightSet (tests / stand-alone use)
 
@@ -330,8 +375,10 @@ class ConvLayer:
     # ---- compute -------------------------------------------------------------
     def forward_params(self, X: SeqT, Y=None, Y2=None, spec=None, **epi):
         s = spec or self.spec
+        if self.x3:
+            epi.setdefault("sp_y2", True)        # the activated output feeds the next (tensor-core) layer
         return tapconv_params(s.fwd_launches(X.L), X, self.Wf, self.kG, self.kcig, self.kcog, Y=Y, Y2=Y2, bias=self.b,
-                              Wt=self.Wb, **epi)
+                              Wt=self.Wb, Wt_sp=self.Wb_sp, **epi)
 
     def forward(self, X: SeqT, Y=None, Y2=None, **epi):
         launch_tapconvs(self.forward_params(X, Y=Y, Y2=Y2, **epi))
@@ -339,8 +386,10 @@ class ConvLayer:
     def dgrad_params(self, dY: SeqT, dX: Optional[SeqT] = None, dX2: Optional[SeqT] = None, spec=None, **epi):
         s = spec or self.spec
         lin = (dX if dX is not None else dX2).L
+        if self.x3:
+            epi.setdefault("sp_y", True)         # data gradients feed the next dgrad and a weight gradient
         return tapconv_params(s.dgrad_launches(lin), dY, self.Wb, self.kG, self.kcog, self.kcig, Y=dX, Y2=dX2,
-                              Wt=self.Wf, **epi)
+                              Wt=self.Wf, Wt_sp=self.Wf_sp, **epi)
 
     def dgrad(self, dY: SeqT, dX: Optional[SeqT] = None, dX2: Optional[SeqT] = None, **epi):
         launch_tapconvs(self.dgrad_params(dY, dX=dX, dX2=dX2, **epi))
@@ -369,6 +418,11 @@ class ConvLayer:
             for i in range(p.ntaps):
                 p.off[i], p.yoff[i], p.widx[i] = L.off[i], L.yoff[i], L.widx[i]
             p.dtype, p.y_dtype = X.code, dY.code
+        if self.x3 and self.kcig % 32 == 0 and self.kcog % 32 == 0:
+            xs, ys = X.ensure_split(), dY.ensure_split()
+            if self.dw_swapped:
+                xs, ys = ys, xs
+            p.X_sp, p.x_plane, p.dY_sp, p.y_plane = ptr(xs), xs.stride(0), ptr(ys), ys.stride(0)
         call("artic_tapconv_wgrad", p)
         if self.b is not None:
             call("artic_colsum", ptr(dY.t), dY.seq(), dY.N, dY.C, dY.code, ptr(grads[self.name + ".bias"]))
@@ -384,13 +438,31 @@ class WeightSet:
         self.dev = dev
         self.any_norm = int(any(l.g is not None for l in self.layers))
         sizes = []
+        # bf16x3 layers: prepared fp32 weights in ONE flat buffer, so that one elementwise launch refreshes the
+        # split copies (bf16 hi / lo planes, `x3_total` elements apart) of every layer after a weight update
+        def up8(v):
+            return (v + 7) // 8 * 8
+
+        n3 = sum(2 * up8(l.spec.k * l.kG * l.kcig * l.kcog) for l in self.layers if l.x3)
+        self.x3_total = n3
+        self.W3 = torch.zeros(n3, dtype=torch.float32, device=dev) if n3 else None
+        self.W3_sp = torch.zeros((2, n3), dtype=torch.bfloat16, device=dev) if n3 else None
+        o3 = 0
         for l in self.layers:
             s = l.spec
             shape_f = (s.k, l.kG, l.kcig, l.kcog)
-            l.Wf = torch.zeros(shape_f, dtype=TORCH_DTYPE[l.in_code], device=dev)
-            l.Wb = torch.zeros((s.k, l.kG, l.kcog, l.kcig), dtype=TORCH_DTYPE[l.out_code], device=dev)
+            shape_b = (s.k, l.kG, l.kcog, l.kcig)
+            n = s.k * l.kG * l.kcig * l.kcog
+            if l.x3:
+                ob = o3 + up8(n)
+                l.Wf, l.Wb = self.W3[o3:o3 + n].view(shape_f), self.W3[ob:ob + n].view(shape_b)
+                l.Wf_sp, l.Wb_sp = (self.W3_sp[0, o3:o3 + n], n3), (self.W3_sp[0, ob:ob + n], n3)
+                o3 = ob + up8(n)
+            else:
+                l.Wf = torch.zeros(shape_f, dtype=TORCH_DTYPE[l.in_code], device=dev)
+                l.Wb = torch.zeros(shape_b, dtype=TORCH_DTYPE[l.out_code], device=dev)
             l.scale = torch.empty(2 * s.wn_rows()[0], dtype=torch.float32, device=dev) if l.g is not None else None
-            sizes.append(s.k * l.kG * l.kcig * l.kcog)
+            sizes.append(n)
         # one flat fp32 accumulator for all weight gradients: a single memset per backward
         self.dW = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
         o = 0
@@ -398,7 +470,7 @@ class WeightSet:
             s = l.spec
             l.dWf = self.dW[o:o + n].view(*((s.k, l.kG, l.kcog, l.kcig) if l.dw_swapped else (s.k, l.kG, l.kcig, l.kcog)))
             o += n
-        self._bufs = [(l.Wf, l.Wb, l.scale, l.dWf) for l in self.layers]
+        self._bufs = [(l.Wf, l.Wb, l.scale, l.dWf, l.Wf_sp, l.Wb_sp) for l in self.layers]
         self._tables = {}
 
     def _table(self, grads):
@@ -438,12 +510,14 @@ class WeightSet:
 
     def rebind(self):
         """Re-attach the buffers to the layers after ConvLayer.bind() (same parameter storage)."""
-        for l, (wf, wb, sc, dw) in zip(self.layers, self._bufs):
-            l.Wf, l.Wb, l.scale, l.dWf = wf, wb, sc, dw
+        for l, (wf, wb, sc, dw, wfs, wbs) in zip(self.layers, self._bufs):
+            l.Wf, l.Wb, l.scale, l.dWf, l.Wf_sp, l.Wb_sp = wf, wb, sc, dw, wfs, wbs
 
     def prep(self):
         tab = self._table(None)
         call("artic_weights_prep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
+        if self.W3 is not None:
+            call("artic_split", ptr(self.W3), ptr(self.W3_sp), self.x3_total, self.x3_total)
 
     def zero(self):
         self.dW.zero_()
@@ -491,10 +565,11 @@ class GeneratorEngine:
     def __init__(self, in_channels, out_channels, channels, kernel_size, upsample_scales,
                  upsample_kernel_sizes, paddings, output_paddings, resblock_kernel_sizes,
                  resblock_dilations, use_additional_convs, slope, use_weight_norm, use_ar, ar_input,
-                 ar_hidden, ar_output, use_tanh, code=F32):
+                 ar_hidden, ar_output, use_tanh, code=F32, x3=False):
         assert use_additional_convs, "use_additional_convs=False is not on the hot path"
         assert len(resblock_kernel_sizes) == 3, "the MRF mean kernel is written for 3 blocks"
         self.code, self.slope, self.use_ar, self.use_tanh = code, slope, use_ar, use_tanh
+        self.x3 = bool(x3) and code == F32
         self.in_channels, self.out_channels = in_channels, out_channels
         self.ar_input, self.ar_output = ar_input, ar_output
         self.scales = list(upsample_scales)
@@ -506,7 +581,7 @@ class GeneratorEngine:
         def add(name, spec, ic=c, oc=c, pad_in=False):
             spec.weight_norm = wn and spec.kind != "linear"
             spec.name = name
-            L[name] = ConvLayer(spec, name, ic, oc, pad_in=pad_in)
+            L[name] = ConvLayer(spec, name, ic, oc, pad_in=pad_in, x3=self.x3)
             return L[name]
 
         add("input_conv", ConvSpec("conv", in_channels, channels, k=kernel_size, padding=(kernel_size - 1) // 2),
@@ -691,7 +766,7 @@ class GeneratorEngine:
         oc.wgrad(a_c, dpre, grads)
         # gradient wrt each MRF block output of the last stage: (1/3) * lrelu'(a_c) * dgrad
         g = a_c.like()
-        oc.dgrad(dpre, dX=g, mask=a_c, mask_slope=stages[-1]["slope_out"], alpha=1.0 / self.n_blocks)
+        oc.dgrad(dpre, dX=g, mask=a_c, mask_slope=stages[-1]["slope_out"], alpha=1.0 / self.n_blocks, sp_y=self.x3)
         for i in range(len(stages) - 1, -1, -1):
             st = stages[i]
 
@@ -743,6 +818,8 @@ class GeneratorEngine:
                 held = [r[1].join() for r in res_b]      # noqa: F841  (tensors of queued wgrads stay alive until joined)
             du = dus[0].like()
             call("artic_sum3", ptr(dus[0].t), ptr(dus[1].t), ptr(dus[2].t), ptr(du.t), du.numel(), code)
+            if self.x3:
+                du.ensure_split()                # before the weight gradient's side stream forks off
             up = L[f"upsamples.{i}.1"]
             a_in = st["a_in"]
             up.wgrad(a_in, du, grads)
@@ -756,7 +833,7 @@ class GeneratorEngine:
         ic.wgrad(gin, g, grads)
         if self.use_ar:
             dgin = gin.like()
-            ic.dgrad(g, dX=dgin)
+            ic.dgrad(g, dX=dgin, sp_y=False)
             Ca = self.ar_output
             d_ar32 = torch.empty((B, Ca), dtype=torch.float32, device=dev)
             call("artic_gen_input_bwd", ptr(dgin.t), ptr(d_ar32), B, tape["Cc"], Ca, gin.C, tape["Tn"], code)
@@ -793,11 +870,12 @@ class DiscriminatorEngine:
     every chain reads the fp32 signal and the logits are written in fp32."""
 
     def __init__(self, scales, pool_params, scale_params, follow_official_norm, periods, period_params, code=F32,
-                 scale_prefix="msd.discriminators.{i}.", period_prefix="mpd.discriminators.{i}."):
+                 scale_prefix="msd.discriminators.{i}.", period_prefix="mpd.discriminators.{i}.", x3=False):
         """``scale_prefix`` / ``period_prefix`` name the parameters of sub-discriminator ``i`` (the
         stand-alone classes use "discriminators.{i}." or ""); ``scales`` may be 0 and ``periods`` empty."""
         from .convspec import ConvSpec as CS
         self.code = code
+        self.x3 = bool(x3) and code == F32
         self.pool = dict(pool_params or {"kernel_size": 4, "stride": 2, "padding": 2})
         scale_params = scale_params or {}
         period_params = period_params or {}
@@ -824,7 +902,7 @@ class DiscriminatorEngine:
             for li, spec in enumerate(specs):
                 last = li == len(specs) - 1
                 name = scale_prefix.format(i=s) + f"layers.{li}" + ("" if last else ".0")
-                layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code))
+                layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code, x3=self.x3))
             self.chains.append(_Chain(layers, "scale", scale_index=s))
         for pi, period in enumerate(periods):
             ks = pp["kernel_sizes"]
@@ -841,7 +919,7 @@ class DiscriminatorEngine:
             for li, spec in enumerate(specs):
                 last = li == len(specs) - 1
                 name = period_prefix.format(i=pi) + ("output_conv" if last else f"convs.{li}.0")
-                layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code))
+                layers.append(ConvLayer(spec, name, F32 if li == 0 else code, F32 if last else code, x3=self.x3))
             self.chains.append(_Chain(layers, "period", period=period))
         self.layers = {l.name: l for ch in self.chains for l in ch.layers}
         self._flat_specs = {}
@@ -955,9 +1033,10 @@ class DiscriminatorEngine:
                 if last:
                     lay.forward(h, Y=o)
                 elif fs is not None:
-                    launch_tapconvs(lay.forward_params(flat_period(h), Y2=flat_period(o), act=ACT_LRELU, act_slope=slope, spec=fs))
+                    launch_tapconvs(lay.forward_params(flat_period(h), Y2=flat_period(o), act=ACT_LRELU, act_slope=slope, spec=fs,
+                                                       sp_y2=self.x3))
                 else:
-                    lay.forward(h, Y2=o, act=ACT_LRELU, act_slope=slope)
+                    lay.forward(h, Y2=o, act=ACT_LRELU, act_slope=slope, sp_y2=self.x3)
                 acts.append(o)
                 h = o
             return acts
@@ -1016,9 +1095,9 @@ class DiscriminatorEngine:
                     if fs is not None:
                         rp = flat_period(dl[li - 1]) if dl[li - 1] is not None else None
                         launch_tapconvs(lay.dgrad_params(flat_period(dz), dX=flat_period(dn), res_pre=rp, mask=flat_period(acts[li]),
-                                                         mask_slope=slope, spec=fs))
+                                                         mask_slope=slope, spec=fs, sp_y=self.x3))
                     else:
-                        lay.dgrad(dz, dX=dn, res_pre=dl[li - 1], mask=acts[li], mask_slope=slope)
+                        lay.dgrad(dz, dX=dn, res_pre=dl[li - 1], mask=acts[li], mask_slope=slope, sp_y=self.x3)
                     dz = dn
                 elif need_dx:
                     if ch.kind == "scale":

@@ -70,8 +70,8 @@ class _SingleConv(torch.nn.Module):
     def _layer(self):
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if getattr(self, "_lay", None) is None or self._key != key:
-            code = _lib.F32 if self.precision == "fp32" else _lib.BF16
-            lay = ConvLayer(self._spec(), "l", code, code)
+            code = _lib.BF16 if self.precision == "bf16" else _lib.F32
+            lay = ConvLayer(self._spec(), "l", code, code, x3=self.precision == "bf16x3")
             lay.bind(self._engine_params())
             lay.prep()
             self._lay, self._key = lay, key

@@ -21,7 +21,11 @@ import torch
 from .. import _lib
 from ..engine import DiscriminatorEngine, GeneratorEngine, SeqT
 
-_PRECISIONS = {"fp32": _lib.F32, "bf16": _lib.BF16}
+#: storage dtype of hidden activations per precision mode.  "fp32": fp32 storage, CUDA-core kernels (debug / odd
+#: shapes).  "bf16x3": fp32 storage, every eligible contraction on the tcgen05 kernels as an error-compensated
+#: split product (x_hi w_hi + x_hi w_lo + x_lo w_hi, fp32 accumulate) — the PARITY-GATED tensor-core mode (1e-3 on
+#: waveforms / losses against the fp32 reference).  "bf16": bf16 storage, plain tcgen05 (speed mode).
+_PRECISIONS = {"fp32": _lib.F32, "bf16x3": _lib.F32, "bf16": _lib.BF16}
 #: default storage precision of hidden activations for newly built models
 DEFAULT_PRECISION = "fp32"
 
@@ -255,7 +259,7 @@ class HiFiGANGenerator(_EngineModule):
     def _build_engine(self):
         wn = any(n.endswith("weight_g") for n, _ in self.named_parameters())
         cfg = dict(self._cfg, use_weight_norm=wn)
-        return GeneratorEngine(code=_PRECISIONS[self.precision], **cfg)
+        return GeneratorEngine(code=_PRECISIONS[self.precision], x3=self.precision == "bf16x3", **cfg)
 
     def forward(self, c, spk_id=None, ar=None, ph=None):
         """c (B, in_channels - ar_output, T') [, ar (B, 1, ar_input)] -> (B, out_channels, T'*prod(scales))."""
@@ -411,7 +415,7 @@ class _DiscriminatorBase(_EngineModule):
         node.add_module(parts[-1], module)
 
     def _build_engine(self):
-        return DiscriminatorEngine(code=_PRECISIONS[self.precision], **self._cfg)
+        return DiscriminatorEngine(code=_PRECISIONS[self.precision], x3=self.precision == "bf16x3", **self._cfg)
 
     def _forward_lists(self, x):
         params = [p for _, p in self.named_parameters()]

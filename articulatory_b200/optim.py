@@ -73,14 +73,86 @@ class FusedAdam:
         raw = self.hyper.cpu().numpy().tobytes()
         return AdamHyper.from_buffer_copy(raw).step
 
-    def state_dict(self):
-        return {"step": self.step_count(), "exp_avg": self.m.cpu(), "exp_avg_sq": self.v.cpu(),
-                "lr0": self._host_hyper.lr0, "betas": (self._host_hyper.beta1, self._host_hyper.beta2),
-                "eps": self._host_hyper.eps, "gamma": self._host_hyper.gamma,
-                "milestones": [self._host_hyper.milestones[i] for i in range(self._host_hyper.n_milestones)]}
+    def _current_lr(self, step):
+        h = self._host_hyper
+        n = sum(1 for i in range(h.n_milestones) if step >= h.milestones[i])
+        return h.lr0 * (h.gamma ** n)
 
-    def load_state_dict(self, sd):
-        self.m.copy_(sd["exp_avg"])
-        self.v.copy_(sd["exp_avg_sq"])
-        self._host_hyper.step = int(sd["step"])
+    def state_dict(self):
+        """``torch.optim.Adam.state_dict()`` layout (the reference saves ``optimizer.state_dict()``,
+        bin/train.py:147-176): per-parameter ``state[i] = {step, exp_avg, exp_avg_sq}`` keyed by the index of the
+        parameter in ``module.parameters()`` order, and one ``param_groups`` entry — so a checkpoint written here
+        resumes in the reference and vice versa."""
+        step = self.step_count()
+        h = self._host_hyper
+        m, v = self.m.cpu(), self.v.cpu()
+        state, off = {}, 0
+        for i, (n, view) in enumerate(self.views.items()):
+            k = view.numel()
+            if step > 0:
+                state[i] = {"step": torch.tensor(float(step)), "exp_avg": m[off:off + k].view(view.shape).clone(),
+                            "exp_avg_sq": v[off:off + k].view(view.shape).clone()}
+            off += k
+        group = {"lr": self._current_lr(step), "betas": (h.beta1, h.beta2), "eps": h.eps, "weight_decay": 0.0,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "initial_lr": h.lr0, "params": list(range(len(self.views)))}
+        return {"state": state, "param_groups": [group]}
+
+    def scheduler_state_dict(self):
+        """``torch.optim.lr_scheduler.MultiStepLR.state_dict()`` layout (stepped once per iteration)."""
+        from collections import Counter
+        h = self._host_hyper
+        step = self.step_count()
+        return {"milestones": Counter(int(h.milestones[i]) for i in range(h.n_milestones)), "gamma": h.gamma,
+                "base_lrs": [h.lr0], "last_epoch": step, "_step_count": step + 1, "verbose": False,
+                "_get_lr_called_within_step": False, "_last_lr": [self._current_lr(step)]}
+
+    def load_state_dict(self, sd, scheduler_sd=None):
+        """Accepts ``torch.optim.Adam.state_dict()`` (reference checkpoints and the ones written here) or the flat
+        layout of earlier versions of this package; raises on anything else instead of silently restarting the
+        moments.  ``scheduler_sd`` (MultiStepLR state) supplies the step counter when the optimizer state holds
+        none (no step taken yet)."""
+        if "exp_avg" in sd and "step" in sd:                       # flat layout (round-1 checkpoints)
+            self.m.copy_(sd["exp_avg"])
+            self.v.copy_(sd["exp_avg_sq"])
+            step = int(sd["step"])
+        elif "state" in sd and "param_groups" in sd:
+            names = list(self.views.keys())
+            n_params = len(sd["param_groups"][0]["params"]) if len(sd["param_groups"]) == 1 else -1
+            if n_params != len(names):
+                raise ValueError(f"optimizer state has {n_params} parameters in {len(sd['param_groups'])} group(s), "
+                                 f"this module has {len(names)}")
+            step, off = 0, 0
+            m, v = torch.zeros_like(self.m, device="cpu"), torch.zeros_like(self.v, device="cpu")
+            for i, n in enumerate(names):
+                view = self.views[n]
+                k = view.numel()
+                st = sd["state"].get(i)
+                if st is not None:
+                    if tuple(st["exp_avg"].shape) != tuple(view.shape):
+                        raise ValueError(f"optimizer state {i} has shape {tuple(st['exp_avg'].shape)}, parameter "
+                                         f"{n} has {tuple(view.shape)} (parameter order differs)")
+                    m[off:off + k] = st["exp_avg"].reshape(-1).float()
+                    v[off:off + k] = st["exp_avg_sq"].reshape(-1).float()
+                    step = max(step, int(float(st["step"])))
+                off += k
+            self.m.copy_(m)
+            self.v.copy_(v)
+            g = sd["param_groups"][0]
+            self._host_hyper.lr0 = float(g.get("initial_lr", self._host_hyper.lr0))
+            self._host_hyper.beta1, self._host_hyper.beta2 = (float(b) for b in g["betas"])
+            self._host_hyper.eps = float(g["eps"])
+        else:
+            raise ValueError("unknown optimizer state layout (expected torch.optim.Adam.state_dict())")
+        if scheduler_sd is not None and "last_epoch" in scheduler_sd:
+            step = max(step, int(scheduler_sd["last_epoch"]))
+            if "gamma" in scheduler_sd:
+                self._host_hyper.gamma = float(scheduler_sd["gamma"])
+            ms = sorted(scheduler_sd.get("milestones", {}))
+            if ms:
+                assert len(ms) <= 8
+                self._host_hyper.n_milestones = len(ms)
+                for i, mval in enumerate(ms):
+                    self._host_hyper.milestones[i] = int(mval)
+        self._host_hyper.step = step
         self._upload()

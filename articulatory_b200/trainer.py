@@ -283,6 +283,9 @@ class TrainStep:
         (pinned) host tensors which are copied host->device inside the step."""
         steady = self.steps > max(self.g_start, self.d_start)
         self._ensure_numel(y.shape[0], y.shape[2])
+        if ar is None:      # non-AR generator (use_ar: false): the collater emits no 'ar'; a 0-length context stands in
+            assert self.ar_len == 0, "this generator is autoregressive: the batch must carry 'ar'"
+            ar = y.new_zeros((y.shape[0], 1, 0))
         if use_graph and steady:
             if self._graph is None or self._static[0].shape != x.shape:
                 self._capture(x, y, ar)
@@ -296,6 +299,10 @@ class TrainStep:
             if self.all_reduce is not None:
                 self.all_reduce(self.optD.grad)
             g3.replay()
+            # the replays re-wrote the flat weights (Adam) behind the modules' host-side caches: a later EAGER use
+            # (eval_step, checkpoint-time inference) must re-materialise the prepared weights
+            self.G.mark_weights_dirty()
+            self.D.mark_weights_dirty()
         else:
             x, y, ar = (t.to(self.dev, non_blocking=True).float().contiguous() for t in (x, y, ar))
             self._step_impl(x, y, ar, self.steps)
@@ -355,6 +362,9 @@ class TrainStep:
         (one host read); ``eval_running`` accumulates them for ``_eval_epoch``-style averaging.  D(real) and
         D(fake) are evaluated once and feed both the generator-side and the discriminator-side terms (the
         reference evaluates each twice, :572-587, with identical results under no_grad)."""
+        if ar is None:
+            assert self.ar_len == 0, "this generator is autoregressive: the batch must carry 'ar'"
+            ar = y.new_zeros((y.shape[0], 1, 0))
         x, y, ar = (t.to(self.dev, non_blocking=True).float().contiguous() for t in (x, y, ar))
         self._ensure_numel(y.shape[0], y.shape[2])
         if not hasattr(self, "eval_vals"):

@@ -281,7 +281,7 @@ def run_ours(args):
         "metric": "audio-samples/sec, e2w_hifigan G+D+spectral-loss train step",
         "value": value, "unit": "audio-samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (fp32 storage, split-bf16 tcgen05, fp32 accumulate)", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": "e2w_hifigan.yaml full G+D+mel+MR-STFT train step, synthetic 13-dim 200 Hz EMA -> 16 kHz, "
                                "batch 16 windows of 8000 samples per GPU (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": world * B, "frames": FRAMES, "samples_per_window": T,
@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("ARTIC_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("ARTIC_PRECISION", "bf16"), choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

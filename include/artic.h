@@ -100,6 +100,15 @@ typedef struct {
   const void* Wt;    /* optional transposed prepared weight [Wt_taps][G][Cog][Cig] (same dtype as W) */
   int32_t Wt_taps;   /* number of taps K stored in Wt */
   int32_t reserved_;
+  /* bf16x3 mode (fp32 storage, error-compensated tensor-core contraction): with dtype = out_dtype = ARTIC_F32,
+   * X_sp = a SPLIT COPY of X (artic_split: bf16 `hi` plane with X's element strides, `lo` plane x_plane elements
+   * further) and Wt_sp = the split copy of Wt (lo plane w_plane elements further), an eligible shape runs on the
+   * tcgen05 kernel as x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (fp32 accumulate, ~2^-16 relative operand error);
+   * otherwise the fp32 CUDA-core kernel reads X / W.  Y_sp / Y2_sp (optional): split copies of Y / Y2 (planes
+   * y_plane elements apart, Y's element strides), ALWAYS written when given, whichever kernel ran. */
+  const void* X_sp; const void* Wt_sp;
+  void* Y_sp; void* Y2_sp;
+  int64_t x_plane, w_plane, y_plane;
 } artic_tapconv_t;
 
 int artic_tapconv(const artic_tapconv_t* p, void* stream);
@@ -125,6 +134,9 @@ typedef struct {
   int32_t widx[ARTIC_MAX_TAPS];
   int32_t dtype;   /* storage type of X */
   int32_t y_dtype; /* storage type of dY */
+  /* bf16x3 mode (see artic_tapconv_t): split copies of X and dY; used when both are given with fp32 X / dY */
+  const void* X_sp; const void* dY_sp;
+  int64_t x_plane, y_plane;
 } artic_tapwgrad_t;
 
 int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream);
@@ -194,6 +206,15 @@ int artic_sum3(const void* a, const void* b, const void* c, void* out, int64_t n
 
 /* dpre = dy * (1 - y*y)  (torch.nn.Tanh backward, models/hifigan.py:158); fp32 dy/y in, `dtype` out. */
 int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64_t n, int32_t dtype, void* stream);
+
+/* bf16x3 operand split: hi[i] = bf16(src[i]), lo[i] = bf16(src[i] - hi[i]); lo lives `plane` elements after hi. */
+int artic_split(const float* src, void* hi, int64_t plane, int64_t n, void* stream);
+
+/* Host-side counters of which kernel family took each contraction since the last reset (tests assert that every
+ * eligible layer runs on the tensor cores): out[0..9] = conv {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic,
+ * channel-1 kernels}, wgrad {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic, channel-1 kernels}, reserved x2.
+ * Counted when a launch is ENQUEUED (graph replays do not count).  reset != 0 clears them after the read. */
+int artic_path_counts(int64_t* h_out, int32_t reset);
 
 /* dtype conversion helpers (n elements). */
 int artic_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);

@@ -49,14 +49,15 @@ def _torch_fwd(spec, x, w, b):
 
 @pytest.mark.parametrize("case", range(len(CONV_CASES)))
 @pytest.mark.parametrize("wn", [False, True])
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 def test_conv_layer_fwd_dgrad_wgrad(case, wn, prec):
     kw, N, lin = CONV_CASES[case]
     spec = ConvSpec(**kw)
     if spec.kind == "linear" and wn:
         pytest.skip("no weight norm on Linear")
-    code = F32 if prec == "fp32" else BF16
-    tol = 2e-5 if prec == "fp32" else 2e-2
+    code = BF16 if prec == "bf16" else F32
+    # bf16x3: split-operand tensor-core contraction, ~2^-16 relative operand error (artic.h: artic_tapconv_t.X_sp)
+    tol = {"fp32": 2e-5, "bf16": 2e-2, "bf16x3": 5e-5}[prec]
     torch.manual_seed(case)
     v = torch.randn(spec.weight_shape(), dtype=torch.float64) / math.sqrt(spec.cig * spec.k)
     g = (torch.rand(spec.weight_shape()[0], *([1] * (v.dim() - 1)), dtype=torch.float64) + 0.5) if wn else None
@@ -75,7 +76,8 @@ def test_conv_layer_fwd_dgrad_wgrad(case, wn, prec):
     ins = [x, v, b] + ([g] if wn else [])
     gr = torch.autograd.grad(y, ins, dy)
 
-    lay = ConvLayer(spec, "l", code, code)
+    lay = ConvLayer(spec, "l", code, code, x3=prec == "bf16x3")
+    _lib.path_counts(reset=True)
     params = {"l.bias": b.detach().float().to(DEV)}
     if wn:
         params["l.weight_v"] = v.detach().float().to(DEV).contiguous()
@@ -110,6 +112,16 @@ def test_conv_layer_fwd_dgrad_wgrad(case, wn, prec):
     assert rel_err(grads["l.bias"].cpu(), gr[2]) < tol
     if wn:
         assert rel_err(grads["l.weight_g"].cpu(), gr[3]) < tol
+    if prec == "bf16x3":
+        pc = _lib.path_counts()
+        if lay.x3:      # eligible shape: every contraction of the layer ran on the split-operand tcgen05 kernels
+            assert pc["conv_tc_x3"] >= 2 and pc["conv_generic"] == 0 and pc["conv_c1"] == 0, pc
+            assert pc["wgrad_tc_x3"] == 1 and pc["wgrad_generic"] == 0, pc
+            # the split copy written by the epilogue reproduces the fp32 output to ~2^-17
+            sp = Y2.sp.float()
+            assert rel_err((sp[0] + sp[1]).cpu(), Y2.t.cpu()) < 2e-5
+        else:
+            assert pc["conv_tc_x3"] == 0 and pc["wgrad_tc_x3"] == 0, pc
 
 
 def test_epilogue_mask_res_alpha():
