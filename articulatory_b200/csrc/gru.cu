@@ -1,0 +1,195 @@
+// Bidirectional GRU layer, inference forward (speech-to-EMA inversion encoder: reference
+// models/pytorch_models.py:22-77, torch.nn.GRU(batch_first, bidirectional) at :27,30 / :63-66).
+//
+// The input projections W_ih x + b_ih of ALL time steps are one plain GEMM (done by the caller through the
+// tap-gather contraction, k = 1); what remains is the strictly sequential part
+//
+//     gh = W_hh h + b_hh;  r = s(gi_r + gh_r);  z = s(gi_z + gh_z);  n = tanh(gi_n + r * gh_n);  h' = (1 - z) n + z h
+//
+// T dependent steps of a (items x H) x (H x 3H) product — latency bound, so the design is a PERSISTENT kernel that
+// keeps everything on chip for the whole sequence:
+//
+//   * one thread-block CLUSTER per (direction, group of 16 batch items); the cluster's CTAs split the hidden
+//     units (32 per CTA, cluster size H / 32 <= 8);
+//   * each CTA holds ITS rows of W_hh (3 gates x 32 units x H, fp32) in shared memory for the whole sequence
+//     (96 KB at H = 256) — the weights are read from HBM exactly once;
+//   * h lives in shared memory, replicated in every CTA of the cluster ([k][item] so that one 128-bit read feeds
+//     four items, broadcast to the warp); after each step a CTA writes its 32 new units straight into the OTHER
+//     CTAs' copies through distributed shared memory and the cluster synchronises once (double-buffered h);
+//   * fp32 FFMA throughout (lanes along the hidden units: conflict-free weight reads): the recurrence feeds its
+//     own rounding error back T times, and the parity gate is 1e-3 against the fp32 reference;
+//   * gi of step t+1 is fetched into registers before the FMA loop of step t (hides the L2 latency).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace artic {
+
+constexpr int GRU_ITEMS = 16;      // batch items per cluster
+constexpr int GRU_UNITS = 32;      // hidden units per CTA (= lanes)
+constexpr int GRU_THREADS = 256;   // 8 warps: (item group of 4) x (half of the k range)
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+                   float* __restrict__ out, int N, int T, int H) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = (int)cluster.num_blocks();          // = H / 32
+  const int rank = (int)cluster.block_rank();
+  const int cid = (int)blockIdx.x / csize;               // cluster index
+  const int n_groups = (N + GRU_ITEMS - 1) / GRU_ITEMS;
+  const int dir = cid / n_groups;                        // 0 forward, 1 reverse
+  const int n0 = (cid % n_groups) * GRU_ITEMS;
+
+  extern __shared__ __align__(16) float smem[];
+  float* Wt = smem;                                      // [3 gates][H k][32 units]
+  float* hbuf = Wt + 3 * H * GRU_UNITS;                  // [2][H k][16 items]
+  float* red = hbuf + 2 * H * GRU_ITEMS;                 // [128 threads][12]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ig = warp & 3;                               // item group: items ig*4 .. ig*4+3
+  const int kh = warp >> 2;                              // k half
+  const int unit = rank * GRU_UNITS + lane;              // hidden unit of this lane
+
+  // ---- one-time: this CTA's rows of W_hh (transposed to [gate][k][unit]), zero initial state
+  const float* Wd = w_hh + (size_t)dir * 3 * H * H;
+  for (int i = tid; i < 3 * GRU_UNITS * H; i += GRU_THREADS) {
+    const int k = i % H, u = (i / H) % GRU_UNITS, g = i / (H * GRU_UNITS);
+    Wt[(g * H + k) * GRU_UNITS + u] = __ldg(Wd + ((size_t)g * H + rank * GRU_UNITS + u) * H + k);
+  }
+  for (int i = tid; i < 2 * H * GRU_ITEMS; i += GRU_THREADS) hbuf[i] = 0.f;
+  float bh[3] = {0.f, 0.f, 0.f};
+  if (kh == 0) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) bh[g] = __ldg(b_hh + (size_t)dir * 3 * H + g * H + unit);
+  }
+  cluster.sync();
+
+  const int GS = 2 * 3 * H;                              // gi row stride (both directions)
+  const float* gi_d = gi + (size_t)dir * 3 * H + unit;
+  float gin[3][4];                                       // gi of the NEXT step (gate, item)
+  auto fetch = [&](int t) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ig * 4 + i;
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        gin[g][i] = (n < N) ? __ldg(gi_d + ((size_t)n * T + t) * GS + g * H) : 0.f;
+    }
+  };
+  if (kh == 0 && T > 0) fetch(dir ? T - 1 : 0);
+
+  const int kb = kh * (H / 2), ke = kb + H / 2;
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? T - 1 - s : s;
+    const float* hc = hbuf + (size_t)(s & 1) * H * GRU_ITEMS;          // h_t (complete, all units)
+    float* hn_local = hbuf + (size_t)((s + 1) & 1) * H * GRU_ITEMS;    // h_{t+1} (being assembled)
+    float gcur[3][4];
+    if (kh == 0) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gcur[g][i] = gin[g][i];
+      if (s + 1 < T) fetch(dir ? t - 1 : t + 1);
+    }
+    float acc[3][4];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
+#pragma unroll 4
+    for (int k = kb; k < ke; ++k) {
+      const float4 h4 = *reinterpret_cast<const float4*>(hc + k * GRU_ITEMS + ig * 4);   // warp-wide broadcast
+      const float wr = Wt[(0 * H + k) * GRU_UNITS + lane];
+      const float wz = Wt[(1 * H + k) * GRU_UNITS + lane];
+      const float wn = Wt[(2 * H + k) * GRU_UNITS + lane];
+      acc[0][0] = fmaf(wr, h4.x, acc[0][0]); acc[0][1] = fmaf(wr, h4.y, acc[0][1]);
+      acc[0][2] = fmaf(wr, h4.z, acc[0][2]); acc[0][3] = fmaf(wr, h4.w, acc[0][3]);
+      acc[1][0] = fmaf(wz, h4.x, acc[1][0]); acc[1][1] = fmaf(wz, h4.y, acc[1][1]);
+      acc[1][2] = fmaf(wz, h4.z, acc[1][2]); acc[1][3] = fmaf(wz, h4.w, acc[1][3]);
+      acc[2][0] = fmaf(wn, h4.x, acc[2][0]); acc[2][1] = fmaf(wn, h4.y, acc[2][1]);
+      acc[2][2] = fmaf(wn, h4.z, acc[2][2]); acc[2][3] = fmaf(wn, h4.w, acc[2][3]);
+    }
+    if (kh == 1) {
+      float* r = red + (size_t)(ig * 32 + lane) * 12;
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[g * 4 + i] = acc[g][i];
+    }
+    __syncthreads();
+    if (kh == 0) {
+      const float* r = red + (size_t)(ig * 32 + lane) * 12;
+      const float4 hold = *reinterpret_cast<const float4*>(hc + unit * GRU_ITEMS + ig * 4);
+      const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
+      float hv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float ghr = acc[0][i] + r[0 * 4 + i] + bh[0];
+        const float ghz = acc[1][i] + r[1 * 4 + i] + bh[1];
+        const float ghn = acc[2][i] + r[2 * 4 + i] + bh[2];
+        const float rg = sigmoidf_(gcur[0][i] + ghr);
+        const float zg = sigmoidf_(gcur[1][i] + ghz);
+        const float ng = tanhf(gcur[2][i] + rg * ghn);
+        hv[i] = (1.f - zg) * ng + zg * ho[i];
+        const int n = n0 + ig * 4 + i;
+        if (n < N) out[((size_t)n * T + t) * (2 * H) + dir * H + unit] = hv[i];
+      }
+      // publish this lane's unit of h_{t+1} to every CTA of the cluster (distributed shared memory)
+      const float4 hv4 = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      float* dst_local = hn_local + unit * GRU_ITEMS + ig * 4;
+      for (int pr = 0; pr < csize; ++pr) {
+        float* dst = cluster.map_shared_rank(dst_local, pr);
+        *reinterpret_cast<float4*>(dst) = hv4;
+      }
+    }
+    cluster.sync();     // h_{t+1} complete everywhere; also orders the reads of h_t before its next overwrite
+  }
+}
+
+}  // namespace artic
+
+using namespace artic;
+
+/* see include/artic.h */
+extern "C" int artic_bigru_layer(const float* gi, const float* w_hh, const float* b_hh, float* out, int32_t N, int32_t T,
+                                 int32_t H, void* stream) {
+  ARTIC_CHECK_ARG(gi && w_hh && b_hh && out, "null pointer");
+  ARTIC_CHECK_ARG(N >= 0 && T >= 0, "bad dims");
+  ARTIC_CHECK_ARG(H >= 32 && H <= 256 && H % 32 == 0 && (H / 32 == 1 || H / 32 == 2 || H / 32 == 4 || H / 32 == 8),
+                  "hidden size must be 32, 64, 128 or 256 (32 units per CTA, cluster of H/32 CTAs)");
+  if (N == 0 || T == 0) return ARTIC_OK;
+  const int csize = H / 32;
+  const int n_groups = (N + GRU_ITEMS - 1) / GRU_ITEMS;
+  const size_t smem = sizeof(float) * ((size_t)3 * H * GRU_UNITS + 2 * (size_t)H * GRU_ITEMS + 128 * 12);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    if (cudaFuncSetAttribute(bigru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("artic_bigru_layer: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
+      return ARTIC_ECUDA;
+    }
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * n_groups * csize));
+  cfg.blockDim = dim3(GRU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, bigru_layer_kernel, gi, w_hh, b_hh, out, (int)N, (int)T, (int)H);
+  if (e != cudaSuccess) {
+    set_error("artic_bigru_layer: launch failed: %s", cudaGetErrorString(e));
+    return ARTIC_ECUDA;
+  }
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}

@@ -10,6 +10,8 @@
 // (tap, in-channel) index so that C_in/groups < 16 does not waste the K chunk.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace artic {
@@ -488,6 +490,12 @@ static int tapconv_fallback(const artic_tapconv_t* p, cudaStream_t st) {
     return ARTIC_OK;
   }
   ++g_path_counts[PATH_CONV_GENERIC];
+  {   // ARTIC_LOG_GENERIC=1: name the shapes that run on the generic CUDA-core kernel (stderr)
+    static const bool log = getenv("ARTIC_LOG_GENERIC") != nullptr;
+    if (log)
+      fprintf(stderr, "[artic] generic conv: N=%d nq=%d G=%d Cig=%d Cog=%d taps=%d si=%d so=%d dtype=%d/%d x_sp=%d\n", p->N, p->nq,
+              p->G, p->Cig, p->Cog, p->ntaps, p->si, p->so, p->dtype, p->out_dtype, p->X_sp != nullptr);
+  }
   const bool ob = p->out_dtype == ARTIC_BF16;
   int rc;
   if (p->dtype == ARTIC_BF16) rc = ob ? launch_tapconv<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapconv<__nv_bfloat16, float>(*p, st);
@@ -566,6 +574,12 @@ extern "C" int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream) {
   if (rc < 0) return rc;
   if (rc == 1) return ARTIC_OK;
   ++g_path_counts[PATH_WGRAD_GENERIC];
+  {
+    static const bool log = getenv("ARTIC_LOG_GENERIC") != nullptr;
+    if (log)
+      fprintf(stderr, "[artic] generic wgrad: N=%d nq=%d G=%d Cig=%d Cog=%d taps=%d si=%d so=%d dtype=%d/%d\n", p->N, p->nq, p->G,
+              p->Cig, p->Cog, p->ntaps, p->si, p->so, p->dtype, p->y_dtype);
+  }
   if (p->dtype == ARTIC_BF16) rc = yb ? launch_tapwgrad<__nv_bfloat16, __nv_bfloat16>(*p, st) : launch_tapwgrad<__nv_bfloat16, float>(*p, st);
   else rc = yb ? launch_tapwgrad<float, __nv_bfloat16>(*p, st) : launch_tapwgrad<float, float>(*p, st);
   if (rc != ARTIC_OK) return rc;

@@ -340,7 +340,9 @@ def stft_frames(t, hop):
 
 def stft_magnitude(x, fft_size, hop_size, win_length, window):
     """stft() of losses/stft_loss.py:16-40 → (B, frames, fft_size//2+1)."""
-    s = torch.stft(x, fft_size, hop_size, win_length, window, return_complex=True)
+    # (.float(): a no-op in fp32; under bf16 autocast — bench.py's stock-torch GPU leg — cuFFT needs fp32 input, which
+    # is what torch.autocast's own fp32 list does for the other spectral ops)
+    s = torch.stft(x.float() if x.dtype == torch.bfloat16 else x, fft_size, hop_size, win_length, window, return_complex=True)
     power = s.real ** 2 + s.imag ** 2
     return torch.sqrt(torch.clamp(power, min=1e-7)).transpose(2, 1)
 
@@ -354,7 +356,7 @@ def mr_stft_loss(x, y, fft_sizes=(1024, 2048, 512), hop_sizes=(120, 240, 50),
         y = y.reshape(-1, y.size(2))
     sc, mag = 0.0, 0.0
     for fs, ss, wl in zip(fft_sizes, hop_sizes, win_lengths):
-        w = getattr(torch, window)(wl, dtype=x.dtype)
+        w = getattr(torch, window)(wl, dtype=x.dtype, device=x.device)
         xm = stft_magnitude(x, fs, ss, wl, w)
         ym = stft_magnitude(y, fs, ss, wl, w)
         sc = sc + torch.norm(ym - xm, p="fro") / torch.norm(ym, p="fro")      # :61
@@ -370,13 +372,13 @@ def mel_spectrogram(x, fs=22050, fft_size=1024, hop_size=256, win_length=None, w
     if x.dim() == 3:
         x = x.reshape(-1, x.size(2))
     win_length = fft_size if win_length is None else win_length
-    w = getattr(torch, f"{window}_window")(win_length, dtype=x.dtype) if window is not None else None
-    s = torch.stft(x, fft_size, hop_size, win_length, w, center=center, normalized=normalized,
-                   onesided=onesided, return_complex=True).transpose(1, 2)
+    w = getattr(torch, f"{window}_window")(win_length, dtype=x.dtype, device=x.device) if window is not None else None
+    s = torch.stft(x.float() if x.dtype == torch.bfloat16 else x, fft_size, hop_size, win_length, w, center=center,
+                   normalized=normalized, onesided=onesided, return_complex=True).transpose(1, 2)
     amp = torch.sqrt(torch.clamp(s.real ** 2 + s.imag ** 2, min=eps))
     fmin = 0 if fmin is None else fmin
     fmax = fs / 2 if fmax is None else fmax
-    melmat = torch.from_numpy(slaney_mel_basis(fs, fft_size, num_mels, fmin, fmax).T).to(x.dtype)
+    melmat = torch.from_numpy(slaney_mel_basis(fs, fft_size, num_mels, fmin, fmax).T).to(device=x.device, dtype=x.dtype)
     mel = torch.clamp(torch.matmul(amp, melmat), min=eps)
     if log_base is None:
         out = torch.log(mel)

@@ -244,7 +244,10 @@ def test_full_width_tensor_core_forward_vs_oracle(precision):
     # 5 AR linears, and the 32 -> 1 output conv (channel-1 kernel) are the only others
     assert pc_g[tc] >= 77 and pc_g["conv_generic"] <= 5 and pc_g["conv_c1"] == 1, pc_g
     # discriminator: per chain only the first (C_in = 1) and the logits (C_out = 1) convs are channel-1 kernels
-    assert pc_d["conv_c1"] == 16 and pc_d["conv_generic"] == 0 and pc_d[tc] >= 37, pc_d
+    # (the channel-1 kernels are written for the bf16 mode; with fp32 storage the first layers use the generic fp32 kernel)
+    assert pc_d["conv_c1"] + pc_d["conv_generic"] == 16 and pc_d[tc] >= 37, pc_d
+    if precision == "bf16":
+        assert pc_d["conv_generic"] == 0, pc_d
     assert e_wave < gate["wave"], e_wave
     assert max(map(max, e_d)) < gate["dout"], e_d
 
