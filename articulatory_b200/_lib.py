@@ -47,7 +47,8 @@ class TapWgrad(C.Structure):
                 ("ntaps", C.c_int32),
                 ("off", C.c_int32 * MAX_TAPS), ("yoff", C.c_int32 * MAX_TAPS), ("widx", C.c_int32 * MAX_TAPS),
                 ("dtype", C.c_int32), ("y_dtype", C.c_int32),
-                ("X_sp", C.c_void_p), ("dY_sp", C.c_void_p), ("x_plane", C.c_int64), ("y_plane", C.c_int64)]
+                ("X_sp", C.c_void_p), ("dY_sp", C.c_void_p), ("x_plane", C.c_int64), ("y_plane", C.c_int64),
+                ("dbias", C.c_void_p)]
 
 
 class AdamHyper(C.Structure):
@@ -116,6 +117,7 @@ SIGNATURES = {
     "artic_mel_loss_fwd_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _f, _f, _f, _p, _f, _p, _p]),
     "artic_add_rows": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p]),
     "artic_train_log": (C.c_int, [_p, _p, _p, _i32, _f, _f, _f, _p, _p, _p]),
+    "artic_bigru_layer": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p]),
     "artic_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
     "artic_adam_tick": (C.c_int, [_p, _p]),
 }
@@ -168,14 +170,15 @@ def call(name, *args):
         raise ArticError(f"{name} failed ({rc}): {lib.artic_last_error().decode()}")
 
 
-PATH_NAMES = ("conv_tc", "conv_tc_x3", "conv_generic", "conv_c1", "wgrad_tc", "wgrad_tc_x3", "wgrad_generic", "wgrad_c1")
+PATH_NAMES = ("conv_tc", "conv_tc_x3", "conv_generic", "conv_c1", "wgrad_tc", "wgrad_tc_x3", "wgrad_generic", "wgrad_c1",
+              "wgrad_bias_fused")
 
 
 def path_counts(reset=False):
     """Which kernel family took each contraction since the last reset (artic_path_counts)."""
     buf = (C.c_int64 * 10)()
     load().artic_path_counts(buf, int(reset))
-    return dict(zip(PATH_NAMES, list(buf)[:8]))
+    return dict(zip(PATH_NAMES, list(buf)[:len(PATH_NAMES)]))
 
 
 def ptr(t):

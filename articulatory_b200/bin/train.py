@@ -143,6 +143,7 @@ class Trainer(object):
                 self.steps += 1
                 if self.steps % self.config["log_interval_steps"] == 0:
                     n = self.config["log_interval_steps"]
+                    self.ts.sync_exchange()
                     vals = self.dp.mean_scalars(self.ts.running.clone()).cpu().tolist()
                     self.ts.running.zero_()
                     if self.dp.rank == 0:

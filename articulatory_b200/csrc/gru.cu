@@ -10,7 +10,7 @@
 // keeps everything on chip for the whole sequence:
 //
 //   * one thread-block CLUSTER per (direction, group of 16 batch items); the cluster's CTAs split the hidden
-//     units (32 per CTA, cluster size H / 32 <= 8);
+//     units (32 per CTA, cluster size ceil(H / 32) <= 8; lanes past H idle);
 //   * each CTA holds ITS rows of W_hh (3 gates x 32 units x H, fp32) in shared memory for the whole sequence
 //     (96 KB at H = 256) — the weights are read from HBM exactly once;
 //   * h lives in shared memory, replicated in every CTA of the cluster ([k][item] so that one 128-bit read feeds
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1)
 bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                    float* __restrict__ out, int N, int T, int H) {
   cg::cluster_group cluster = cg::this_cluster();
-  const int csize = (int)cluster.num_blocks();          // = H / 32
+  const int csize = (int)cluster.num_blocks();          // = ceil(H / 32)
   const int rank = (int)cluster.block_rank();
   const int cid = (int)blockIdx.x / csize;               // cluster index
   const int n_groups = (N + GRU_ITEMS - 1) / GRU_ITEMS;
@@ -53,16 +53,17 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
   const int ig = warp & 3;                               // item group: items ig*4 .. ig*4+3
   const int kh = warp >> 2;                              // k half
   const int unit = rank * GRU_UNITS + lane;              // hidden unit of this lane
+  const bool live = unit < H;
 
   // ---- one-time: this CTA's rows of W_hh (transposed to [gate][k][unit]), zero initial state
   const float* Wd = w_hh + (size_t)dir * 3 * H * H;
   for (int i = tid; i < 3 * GRU_UNITS * H; i += GRU_THREADS) {
     const int k = i % H, u = (i / H) % GRU_UNITS, g = i / (H * GRU_UNITS);
-    Wt[(g * H + k) * GRU_UNITS + u] = __ldg(Wd + ((size_t)g * H + rank * GRU_UNITS + u) * H + k);
+    Wt[(g * H + k) * GRU_UNITS + u] = (rank * GRU_UNITS + u < H) ? __ldg(Wd + ((size_t)g * H + rank * GRU_UNITS + u) * H + k) : 0.f;
   }
   for (int i = tid; i < 2 * H * GRU_ITEMS; i += GRU_THREADS) hbuf[i] = 0.f;
   float bh[3] = {0.f, 0.f, 0.f};
-  if (kh == 0) {
+  if (kh == 0 && live) {
 #pragma unroll
     for (int g = 0; g < 3; ++g) bh[g] = __ldg(b_hh + (size_t)dir * 3 * H + g * H + unit);
   }
@@ -77,12 +78,12 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
       const int n = n0 + ig * 4 + i;
 #pragma unroll
       for (int g = 0; g < 3; ++g)
-        gin[g][i] = (n < N) ? __ldg(gi_d + ((size_t)n * T + t) * GS + g * H) : 0.f;
+        gin[g][i] = (n < N && live) ? __ldg(gi_d + ((size_t)n * T + t) * GS + g * H) : 0.f;
     }
   };
   if (kh == 0 && T > 0) fetch(dir ? T - 1 : 0);
 
-  const int kb = kh * (H / 2), ke = kb + H / 2;
+  const int kb = kh ? H / 2 : 0, ke = kh ? H : H / 2;
   for (int s = 0; s < T; ++s) {
     const int t = dir ? T - 1 - s : s;
     const float* hc = hbuf + (size_t)(s & 1) * H * GRU_ITEMS;          // h_t (complete, all units)
@@ -121,7 +122,7 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
         for (int i = 0; i < 4; ++i) r[g * 4 + i] = acc[g][i];
     }
     __syncthreads();
-    if (kh == 0) {
+    if (kh == 0 && live) {
       const float* r = red + (size_t)(ig * 32 + lane) * 12;
       const float4 hold = *reinterpret_cast<const float4*>(hc + unit * GRU_ITEMS + ig * 4);
       const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
@@ -159,10 +160,9 @@ extern "C" int artic_bigru_layer(const float* gi, const float* w_hh, const float
                                  int32_t H, void* stream) {
   ARTIC_CHECK_ARG(gi && w_hh && b_hh && out, "null pointer");
   ARTIC_CHECK_ARG(N >= 0 && T >= 0, "bad dims");
-  ARTIC_CHECK_ARG(H >= 32 && H <= 256 && H % 32 == 0 && (H / 32 == 1 || H / 32 == 2 || H / 32 == 4 || H / 32 == 8),
-                  "hidden size must be 32, 64, 128 or 256 (32 units per CTA, cluster of H/32 CTAs)");
+  ARTIC_CHECK_ARG(H >= 1 && H <= 256, "hidden size must be <= 256 (32 units per CTA, portable cluster of <= 8 CTAs)");
   if (N == 0 || T == 0) return ARTIC_OK;
-  const int csize = H / 32;
+  const int csize = (H + 31) / 32;
   const int n_groups = (N + GRU_ITEMS - 1) / GRU_ITEMS;
   const size_t smem = sizeof(float) * ((size_t)3 * H * GRU_UNITS + 2 * (size_t)H * GRU_ITEMS + 128 * 12);
   static size_t smem_set = 0;

@@ -464,7 +464,7 @@ static int check_seq(const artic_seq_t& s) { return s.n_inner >= 1 && s.len >= 0
 // implemented in tapconv_tc.cu: returns 1 if it took the launch, 0 if the shape is not
 // eligible (fall through to the generic kernel), <0 on error.
 int artic_tapconv_tc_multi(const artic_tapconv_t* ps, int n, int* taken, cudaStream_t st);   // tapconv_tc.cu
-int artic_tapwgrad_tc_try(const artic_tapwgrad_t* p, cudaStream_t st);  // tapwgrad_tc.cu, same convention
+int artic_tapwgrad_tc_try(const artic_tapwgrad_t* p, cudaStream_t st, int* bias_fused);  // tapwgrad_tc.cu, same convention
 int artic_tapconv_co1_try(const artic_tapconv_t* p, cudaStream_t st);    // smallc.cu
 int artic_tapconv_ci1_try(const artic_tapconv_t* p, cudaStream_t st);    // smallc.cu
 int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* p, cudaStream_t st);  // smallc.cu
@@ -565,13 +565,21 @@ extern "C" int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream) {
   if (p->N == 0 || p->nq == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool yb = p->y_dtype == ARTIC_BF16;
+  if (p->dbias != nullptr)
+    ARTIC_CHECK_ARG(p->q0 + p->yoff[0] == 0 && p->nq == p->y.len && p->so == 1, "dbias needs a launch over every dY row");
   if (artic_tapwgrad_ci1_try(p, st) == 1) {
     ARTIC_LAUNCH_CHECK();
     ++g_path_counts[PATH_WGRAD_C1];
+    if (p->dbias != nullptr) return artic_colsum(p->dY, &p->y, p->N, p->G * p->Cog, p->y_dtype, p->dbias, stream);
     return ARTIC_OK;
   }
-  int rc = artic_tapwgrad_tc_try(p, st);
+  int bias_fused = 0;
+  int rc = artic_tapwgrad_tc_try(p, st, &bias_fused);
   if (rc < 0) return rc;
+  if (p->dbias != nullptr && !bias_fused) {
+    const int brc = artic_colsum(p->dY, &p->y, p->N, p->G * p->Cog, p->y_dtype, p->dbias, stream);
+    if (brc != ARTIC_OK) return brc;
+  }
   if (rc == 1) return ARTIC_OK;
   ++g_path_counts[PATH_WGRAD_GENERIC];
   {

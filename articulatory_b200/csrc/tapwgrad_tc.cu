@@ -21,6 +21,12 @@
 // bf16x3 mode (template X3; fp32 X / dY with split copies, see tapconv_tc.cu): every position chunk is issued
 // three times — (x_hi, dy_hi), (x_hi, dy_lo), (x_lo, dy_hi) — into the same accumulators.
 //
+// Bias gradient (artic_tapwgrad_t.dbias): the column sums of dY come from ONE MORE accumulator, D_bias = 1 x dY, i.e.
+// an A operand of all ones (a small constant tile in shared memory; with every element equal, swizzle and the
+// leading-dimension offset do not matter) against the dY tile that is staged anyway — every row of D_bias holds the
+// column sums of the chunk.  Only the CTAs of ci block 0 / tap group 0 do it, so each (co tile, split) counts once.
+// This replaces a separate column-sum launch per layer that re-read every dY from HBM.
+//
 // Zero padding / sequence boundaries: rows outside [0, len) are zero-filled by TMA; short
 // sequences are packed back to back with their halos (pitch = L + span), the padding rows of
 // dY being zero so that they contribute nothing.  The staging area is zeroed once so that rows
@@ -59,6 +65,8 @@ struct WPlan {
   int32_t launch_id;
   int32_t epi_transposed;      // 1: coalesced reductions through a shared-memory transpose (debug key 18 = 1 turns it off)
   int32_t dbg_flags;           // debug key 13: 1 = skip the reductions, 2 = skip the staging-area zeroing (timing experiments)
+  int32_t bias_acc;            // 1: CTAs with mb == 0 && tg == 0 also accumulate the bias gradient (ones x dY)
+  int32_t ones_off;            // byte offset (from the staging base) of the all-ones A tile
   // per accumulator: phase panel, row shift of slot 0, tap index of slot 0, number of valid slots
   int8_t acc_panel[ARTIC_MAX_TAPS];
   int16_t acc_shift[ARTIC_MAX_TAPS];
@@ -113,6 +121,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
   const int c_end = min(pl.n_chunks, c_begin + pl.chunks_per_split);
   const int acc0 = pl.tg_begin[tg];
   const int n_acc = pl.tg_begin[tg + 1] - acc0;
+  const bool do_bias = pl.bias_acc && mb == 0 && tg == 0;
   uint32_t ph_mask = 0;                     // phase panels this CTA's accumulators read
   for (int a = 0; a < n_acc; ++a) ph_mask |= 1u << pl.acc_panel[acc0 + a];
   const int n_ph_used = __popc(ph_mask);
@@ -122,6 +131,11 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
     uint4* z4 = reinterpret_cast<uint4*>(smem_raw + (smem0 - smem_u32(smem_raw)));
     const int n16 = pl.n_stages * pl.stage_bytes / 16;
     for (int i = threadIdx.x; i < n16; i += WG_THREADS) z4[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (do_bias) {   // all-ones A tile: kp positions x (<= 128-byte rows) of bf16 1.0
+    uint4* o4 = reinterpret_cast<uint4*>(smem_raw + (smem0 + (uint32_t)pl.ones_off - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < pl.kp * pl.xrb / 16; i += WG_THREADS) o4[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (threadIdx.x == 0) {
@@ -199,7 +213,8 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
       const uint32_t b_hi = (((8u * (uint32_t)pl.yrb) >> 4) & 0x3fffu) | (1u << 14) | ((uint32_t)(pl.y_layout & 7) << 29);
       const uint32_t a_lo0 = (((uint32_t)pl.a_lbo >> 4) & 0x3fffu) << 16;
       const uint32_t b_lo0 = (((uint32_t)pl.y_panel_bytes >> 4) & 0x3fffu) << 16;
-      uint32_t accum = 0;
+      uint32_t accum = 0, accum_b = 0;
+      const uint32_t ones16 = ((smem0 + (uint32_t)pl.ones_off) >> 4) & 0x3fffu;     // LBO = 0: every 64-row block reads the same ones
       for (int cc = c_begin * R; cc < c_end * R; ++cc) {
         mbar_wait(&full[ps.stage], ps.phase);
         tc_fence_after();
@@ -218,6 +233,17 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
             if (leader) umma_bf16(dcol, ((uint64_t)a_hi << 32) | ad, ((uint64_t)b_hi << 32) | bd, idesc, acc_k);
             acc_k = 1;
             ad += (uint32_t)pl.xrb;    // 16 positions * xrb bytes / 16
+            bd += (uint32_t)pl.yrb;
+          }
+        }
+        if (do_bias && (!X3 || cc % R != 2)) {      // bf16x3: dY = dy_hi + dy_lo, i.e. passes 0 and 1
+          uint32_t ad = ones16, bd = b16;
+          const uint32_t dcol = tmem_base + (uint32_t)n_acc * pl.bn;
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k) {
+            if (leader) umma_bf16(dcol, ((uint64_t)a_hi << 32) | ad, ((uint64_t)b_hi << 32) | bd, idesc, accum_b);
+            accum_b = 1;
+            ad += (uint32_t)pl.xrb;
             bd += (uint32_t)pl.yrb;
           }
         }
@@ -280,6 +306,18 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
           }
         }
       }
+      if (do_bias && ew == 0) {
+        // every row of the bias accumulator holds the column sums: lane i of the first lane quarter adds column i
+        for (int c0 = 0; c0 < pl.bn; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (uint32_t)n_acc * pl.bn + c0, r);
+          tmem_ld_wait();
+          float v = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v = (lane == i) ? __uint_as_float(r[i]) : v;
+          if (!(pl.dbg_flags & 1)) atomicAdd(p.dbias + (int64_t)g * p.Cog + nt * pl.bn + c0 + lane, v);
+        }
+      }
     }
   }
 
@@ -334,8 +372,9 @@ static CUresult encode_seq_map(EncodeTiledFn enc, CUtensorMap* map, const void* 
 using namespace artic;
 
 // returns 1 if the launch was taken, 0 if the shape is not eligible, <0 on error.
-int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
+int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st, int* bias_fused) {
   const artic_tapwgrad_t& p = *pp;
+  *bias_fused = 0;
   if (tc::g_debug[1] || tc::g_debug[5]) return 0;
   const bool x3 = p.dtype == ARTIC_F32 && p.y_dtype == ARTIC_F32 && p.X_sp != nullptr && p.dY_sp != nullptr;
   if (!x3 && (p.dtype != ARTIC_BF16 || p.y_dtype != ARTIC_BF16)) return 0;
@@ -445,13 +484,17 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   }
   pl.tg_begin[pl.n_tg] = (int16_t)n_acc_total;
   pl.n_acc = pl.apc;
-  const int cols = pl.apc * pl.bn;
+  // bias gradient: one more accumulator on the CTAs of ci block 0 / tap group 0, when TMEM has room for it
+  const int tg0_acc = pl.tg_begin[1] - pl.tg_begin[0];
+  pl.bias_acc = (p.dbias != nullptr && (tg0_acc + 1) * pl.bn <= 512 && tc::g_debug[21] != 1) ? 1 : 0;
+  const int cols = (pl.bias_acc && tg0_acc + 1 > pl.apc ? tg0_acc + 1 : pl.apc) * pl.bn;
   pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   const int align = 2;  // keeps every TMA destination 128-byte aligned for 64-byte rows
   const int lpad = ((p.nq + span_rows + align - 1) / align) * align;
   pl.packed = (p.N >= 2 && lpad <= 64 && lpad * si <= 256) ? 1 : 0;
   if (ext > 1024) return 0;
-  const int budget = tc::wg_max_smem() - 1024 - tc::WG_EPI_BYTES;
+  const int ones_bytes = pl.bias_acc ? 16 * 1024 : 0;      // kp <= 128 positions x 128-byte rows
+  const int budget = tc::wg_max_smem() - 1024 - tc::WG_EPI_BYTES - ones_bytes;
   // positions per chunk: shrink until at least 3 stages fit in shared memory
   int kp_cap = 128;
   for (;;) {
@@ -524,10 +567,13 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
   pl.trace_cap = tc::g_trace_cap;
   pl.launch_id = tc::g_trace_buf != nullptr ? tc::g_trace_launch++ : 0;
   const int epi_need = 4 * 32 * 8 * 16 + 4 * 32 * 8;    // transpose stages + row pointers (overlaid on the operand stages)
-  const int smem_bytes = (pl.n_stages * pl.stage_bytes > epi_need ? pl.n_stages * pl.stage_bytes : epi_need) + 1024 + tc::WG_EPI_BYTES;
+  pl.ones_off = pl.n_stages * pl.stage_bytes > epi_need ? pl.n_stages * pl.stage_bytes : epi_need;
+  const int smem_bytes = pl.ones_off + ones_bytes + 1024 + tc::WG_EPI_BYTES;
   if (x3) tc::tapwgrad_tc_kernel<true><<<(unsigned)grid, tc::WG_THREADS, smem_bytes, st>>>(p, pl, maps);
   else tc::tapwgrad_tc_kernel<false><<<(unsigned)grid, tc::WG_THREADS, smem_bytes, st>>>(p, pl, maps);
   ++g_path_counts[x3 ? PATH_WGRAD_TC_X3 : PATH_WGRAD_TC];
+  *bias_fused = pl.bias_acc;
+  if (pl.bias_acc) ++g_path_counts[8];
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     set_error("artic_tapconv_wgrad(tc): launch failed: %s (grid %lld, smem %d of %d, bn %d acc %d stages %d packed %d)",

@@ -423,8 +423,11 @@ class ConvLayer:
             if self.dw_swapped:
                 xs, ys = ys, xs
             p.X_sp, p.x_plane, p.dY_sp, p.y_plane = ptr(xs), xs.stride(0), ptr(ys), ys.stride(0)
+        fuse_bias = self.b is not None and not self.dw_swapped and p.so == 1 and p.q0 + p.yoff[0] == 0 and p.nq == dY.L
+        if fuse_bias:       # column sums of dY from one more tensor-core accumulator (or artic_colsum inside the call)
+            p.dbias = ptr(grads[self.name + ".bias"])
         call("artic_tapconv_wgrad", p)
-        if self.b is not None:
+        if self.b is not None and not fuse_bias:
             call("artic_colsum", ptr(dY.t), dY.seq(), dY.N, dY.C, dY.code, ptr(grads[self.name + ".bias"]))
 
 class WeightSet:

@@ -4,3 +4,4 @@ reference does on ``articulatory.models`` (bin/train.py:1649-1662, utils/utils.p
 from .hifigan import (HiFiGANGenerator, HiFiGANMultiPeriodDiscriminator,  # noqa: F401
                       HiFiGANMultiScaleDiscriminator, HiFiGANMultiScaleMultiPeriodDiscriminator,
                       HiFiGANPeriodDiscriminator, HiFiGANScaleDiscriminator, set_default_precision)
+from .inversion import BiGRU  # noqa: F401,E402

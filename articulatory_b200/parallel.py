@@ -21,9 +21,15 @@ def env_world():
 
 
 class DataParallel:
-    def __init__(self, backend=None, device=None):
+    def __init__(self, backend=None, device=None, compress=None):
+        """``compress="bf16"``: gradients cross the wire as bf16 (half the bytes; DDP's ``bf16_compress_hook``
+        semantics: cast, sum in bf16, cast back) — meant for the bf16 speed mode, whose gradients carry bf16 noise
+        anyway.  Default: exact fp32 sum."""
         self.rank, self.local_rank, self.world = env_world()
         self.device = device
+        self.compress = compress
+        self._wire = {}
+        self.bytes_reduced = 0
         if self.world > 1 and not dist.is_initialized():
             backend = backend or ("nccl" if (device is not None and torch.device(device).type == "cuda") else "gloo")
             kw = {"device_id": torch.device(device)} if backend == "nccl" else {}
@@ -44,7 +50,39 @@ class DataParallel:
     def all_reduce(self, flat: torch.Tensor):
         """Sum a flat gradient buffer over ranks, in place (called between the step's graph segments)."""
         if self.world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if self.compress == "bf16":
+                w = self._wire.get(flat.data_ptr())
+                if w is None:
+                    w = self._wire[flat.data_ptr()] = torch.empty_like(flat, dtype=torch.bfloat16)
+                w.copy_(flat)
+                dist.all_reduce(w, op=dist.ReduceOp.SUM)
+                flat.copy_(w)
+                self.bytes_reduced += w.numel() * 2
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                self.bytes_reduced += flat.numel() * flat.element_size()
+
+    def describe(self):
+        """What carried the gradient exchange (for the bench line): backend, wire dtype, and — when NCCL_DEBUG=INFO
+        was routed to a file by the caller (NCCL_DEBUG_FILE) — whether NCCL set up NVLS (in-switch reduction)."""
+        if self.world == 1:
+            return None
+        d = {"backend": dist.get_backend(), "world": self.world, "wire_dtype": self.compress or "fp32"}
+        try:
+            d["nccl_version"] = ".".join(map(str, torch.cuda.nccl.version()))
+        except Exception:
+            pass
+        path = os.environ.get("NCCL_DEBUG_FILE", "")
+        if path:
+            path = path.replace("%h", os.uname().nodename).replace("%p", str(os.getpid()))
+            try:
+                txt = open(path, errors="ignore").read()
+                d["nvls"] = "NVLS" in txt
+                algos = sorted({a for a in ("NVLS", "NVLSTree", "Ring", "Tree", "CollNet") if f" {a} " in txt or f"{a}/" in txt})
+                d["nccl_log_mentions"] = algos
+            except OSError:
+                pass
+        return d
 
     # ---- data -------------------------------------------------------------------------
     def shard(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -91,6 +91,7 @@ class TrainStep:
         self.steps = 0
         self._graph = None
         self._static = None
+        self._overlap, self._ev_d, self._gfwd = False, None, None
         self.ar_len = generator._cfg["ar_input"] if generator.use_ar else 0
 
     # ------------------------------------------------------------------------------
@@ -117,20 +118,31 @@ class TrainStep:
 
     # Both discriminator inputs of a phase travel as ONE batch [fake | real] (2B items): one set
     # of launches per layer, and in the D phase one backward / one weight gradient over both.
-    def _phase_g(self, x, y, ar, train_d_active):
+    def _phase_g_fwd(self, x, ar):
+        """Generator forward alone (its own graph segment in the data-parallel schedule: it needs nothing from the
+        discriminator, so it runs while the previous step's D gradients are still being exchanged)."""
+        engG = self.G._ensure_ready()
+        self._gfwd = (engG,) + tuple(engG.forward(x, ar, save=True))
+
+    def _phase_g(self, x, y, ar, train_d_active, forwarded=False):
         G, D = self.G, self.D
-        engG = G._ensure_ready()
         B, _, T = y.shape
         inv_w = 1.0 / self.world
-        # the discriminator's weights (updated at the end of the previous step) are re-materialised on a
-        # side stream while the generator forward runs
-        if "order2" in _BG:      # generator forward enqueued first (side stream), the big-grid weight prep after it
-            engD, (y_, tapeG) = fork_join([lambda: D._ensure_ready() if train_d_active else None,
-                                           lambda: engG.forward(x, ar, save=True)])
+        if forwarded:
+            engG, y_, tapeG = self._gfwd
+            self._gfwd = None
+            engD = D._ensure_ready() if train_d_active else None     # no-op: re-materialised right after Adam(D)
         else:
-            (y_, tapeG), engD = fork_join([lambda: engG.forward(x, ar, save=True),
-                                           lambda: D._ensure_ready() if train_d_active else None],
-                                          background=(1,) if "prep" in _BG else ())
+            engG = G._ensure_ready()
+            # the discriminator's weights (updated at the end of the previous step) are re-materialised on a
+            # side stream while the generator forward runs
+            if "order2" in _BG:      # generator forward enqueued first (side stream), the big-grid weight prep after it
+                engD, (y_, tapeG) = fork_join([lambda: D._ensure_ready() if train_d_active else None,
+                                               lambda: engG.forward(x, ar, save=True)])
+            else:
+                (y_, tapeG), engD = fork_join([lambda: engG.forward(x, ar, save=True),
+                                               lambda: D._ensure_ready() if train_d_active else None],
+                                              background=(1,) if "prep" in _BG else ())
         y2d, t2d = y_.reshape(B, T), y.reshape(B, T)
         dy = torch.zeros((B, 1, T), dtype=torch.float32, device=self.dev)
         self.slots.zero_()
@@ -245,10 +257,10 @@ class TrainStep:
     # The step is cut into three segments so that the (optional) data-parallel gradient
     # all-reduce can run between CUDA-graph replays:  seg1 = G phase up to dL/dθ_G,
     # seg2 = Adam(G) + D phase up to dL/dθ_D,  seg3 = Adam(D) + log assembly.
-    def _seg1(self, x, y, ar, steps):
+    def _seg1(self, x, y, ar, steps, forwarded=False):
         self._real = None
         if steps > self.g_start:
-            self._real = self._phase_g(x, y, ar, steps > self.d_start)
+            self._real = self._phase_g(x, y, ar, steps > self.d_start, forwarded=forwarded)
         else:
             self.slots.zero_()
             self.stft_sums.zero_()
@@ -260,12 +272,14 @@ class TrainStep:
             self._phase_d(x, y, ar, self._real)
         self._real = None
 
-    def _seg3(self, steps):
+    def _seg3(self, steps, prep_d=False):
         if steps > self.d_start:
             self.optD.step()
         call("artic_train_log", ptr(self.slots), ptr(self.stft_sums), ptr(self.stft_numel),
              self.R if steps > self.g_start else 0, self.l_aux, self.l_adv, self.l_fm, ptr(self.vals),
              ptr(self.running))
+        if prep_d:          # overlapped schedule: D's weights are re-materialised here, off the critical path
+            self.D._ensure_ready()
 
     def _step_impl(self, x, y, ar, steps):
         """One reference train step at global step ``steps`` (gates as bin/train.py:268,350,388)."""
@@ -291,22 +305,53 @@ class TrainStep:
                 self._capture(x, y, ar)
             for dst, src in zip(self._static, (x, y, ar)):
                 dst.copy_(src, non_blocking=True)
-            g1, g2, g3 = self._graph
-            g1.replay()
-            if self.all_reduce is not None:
+            if self._overlap:
+                # data-parallel schedule (four graphs): the exchange of the D gradients, Adam(D) and D's weight
+                # re-materialisation of step k run on the exchange stream UNDER the generator forward of step k + 1;
+                # only the (5x smaller) exchange of the G gradients is on the critical path
+                g1a, g1b, g2, g3 = self._graph
+                main = torch.cuda.current_stream()
+                g1a.replay()
+                main.wait_event(self._ev_d)
+                g1b.replay()
                 self.all_reduce(self.optG.grad)
-            g2.replay()
-            if self.all_reduce is not None:
-                self.all_reduce(self.optD.grad)
-            g3.replay()
+                g2.replay()
+                self._ev_2.record(main)
+                with torch.cuda.stream(self._xs):
+                    self._xs.wait_event(self._ev_2)
+                    self.all_reduce(self.optD.grad)
+                    g3.replay()
+                    self._ev_d.record(self._xs)
+            else:
+                g1, g2, g3 = self._graph
+                g1.replay()
+                if self.all_reduce is not None:
+                    self.all_reduce(self.optG.grad)
+                g2.replay()
+                if self.all_reduce is not None:
+                    self.all_reduce(self.optD.grad)
+                g3.replay()
             # the replays re-wrote the flat weights (Adam) behind the modules' host-side caches: a later EAGER use
             # (eval_step, checkpoint-time inference) must re-materialise the prepared weights
             self.G.mark_weights_dirty()
             self.D.mark_weights_dirty()
         else:
+            self.sync_exchange()
             x, y, ar = (t.to(self.dev, non_blocking=True).float().contiguous() for t in (x, y, ar))
             self._step_impl(x, y, ar, self.steps)
         self.steps += 1
+
+    def sync_exchange(self):
+        """Make the current stream wait for the overlapped tail of the last step (D gradient exchange, Adam(D), log
+        assembly); a no-op in the single-GPU / non-overlapped schedules.  Called by every reader of the logged values
+        and of D's parameters."""
+        if getattr(self, "_overlap", False) and self._ev_d is not None:
+            torch.cuda.current_stream().wait_event(self._ev_d)
+
+    def values_tensor(self):
+        """The nine logged scalars of the last step as a device tensor that is safe to read on the current stream."""
+        self.sync_exchange()
+        return self.vals
 
     def _ensure_numel(self, B, T):
         """Element counts of the STFT magnitude tensors (log-magnitude mean), kept on the device."""
@@ -331,14 +376,32 @@ class TrainStep:
         pool = torch.cuda.graph_pool_handle()
         graphs = []
         cap = critical_stream(self.dev)         # high priority: see engine.fork_join
-        for seg in (lambda: self._seg1(sx, sy, sa, self.steps), lambda: self._seg2(sx, sy, sa, self.steps),
-                    lambda: self._seg3(self.steps)):
+        self._overlap = ar_fn is not None and _os.environ.get("ARTIC_DP_OVERLAP", "1") != "0"
+        # G's prepared weights are refreshed inside the step (right after Adam(G)); materialise them now so that the
+        # generator phase does not capture a second, redundant re-materialisation per step
+        self.G._ensure_ready()
+        if self._overlap:
+            # D's prepared weights are refreshed by the tail segment (after Adam(D)); make them current before the
+            # first replay and keep the re-materialisation out of the generator-phase graph
+            self.D._ensure_ready()
+            segs = (lambda: self._phase_g_fwd(sx, sa), lambda: self._seg1(sx, sy, sa, self.steps, forwarded=True),
+                    lambda: self._seg2(sx, sy, sa, self.steps), lambda: self._seg3(self.steps, prep_d=True))
+        else:
+            segs = (lambda: self._seg1(sx, sy, sa, self.steps), lambda: self._seg2(sx, sy, sa, self.steps),
+                    lambda: self._seg3(self.steps))
+        for seg in segs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=cap):
                 seg()
             graphs.append(g)
         self.all_reduce = ar_fn
         self._restore(snap)
+        self.G._ensure_ready()
+        if self._overlap:
+            self.D._ensure_ready()
+            self._xs = torch.cuda.Stream(device=self.dev, priority=-1)
+            self._ev_2, self._ev_d = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_d.record(torch.cuda.current_stream())
         self._graph, self._static = tuple(graphs), (sx, sy, sa)
 
     def _snapshot(self):
@@ -365,6 +428,7 @@ class TrainStep:
         if ar is None:
             assert self.ar_len == 0, "this generator is autoregressive: the batch must carry 'ar'"
             ar = y.new_zeros((y.shape[0], 1, 0))
+        self.sync_exchange()
         x, y, ar = (t.to(self.dev, non_blocking=True).float().contiguous() for t in (x, y, ar))
         self._ensure_numel(y.shape[0], y.shape[2])
         if not hasattr(self, "eval_vals"):
@@ -403,10 +467,12 @@ class TrainStep:
 
     def read_logs(self, reset=True):
         """Device -> host read of the running sums (the reference's total_train_loss)."""
+        self.sync_exchange()
         vals = self.running.cpu().tolist()
         if reset:
             self.running.zero_()
         return dict(zip(LOG_KEYS, vals))
 
     def last_values(self):
+        self.sync_exchange()
         return dict(zip(LOG_KEYS, self.vals.cpu().tolist()))

@@ -266,7 +266,7 @@ def mode_agreement(dev, n_steps=4):
         per = []
         for _ in range(n_steps):
             ts.step(b["x"], b["y"], b["ar"], use_graph=False)
-            per.append(ts.vals.cpu().tolist())
+            per.append(ts.values_tensor().cpu().tolist())
         vals[prec] = per
         del ts
         torch.cuda.empty_cache()
@@ -319,6 +319,66 @@ def car_inference(dev, precision, iters=3):
                                  "dependent launches: latency bound"}}
 
 
+def inversion(dev, cpu=True, iters=5):
+    """BASELINE configs[4]: speech-to-EMA inversion encoder forward (BiGRU 2 x 256 bidirectional -> 12-dim EMA),
+    batch 128 on one B200.  Input = HuBERT-large-sized features (1024-d at 200 Hz, reference
+    egs/ema/voc1/local/predict_ema.py:83-90), 2-second utterances (400 frames); pinned host features in, host EMA out."""
+    from articulatory_b200.models import BiGRU
+    N, C, Tn, H = 128, 1024, 400, 256
+    torch.manual_seed(0)
+    m = BiGRU(in_channels=C, hidden_size=H, out_channels=12)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.eval().to(dev)
+    g = torch.Generator().manual_seed(5)
+    host = torch.randn(N, C, Tn, generator=g).pin_memory()
+    for _ in range(2):
+        m(host.to(dev, non_blocking=True))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        y = m(host.to(dev, non_blocking=True)).cpu()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xd = host.to(dev)
+    d0.record()
+    for _ in range(iters):
+        m(xd)
+    d1.record()
+    torch.cuda.synchronize()
+    ms_dev = d0.elapsed_time(d1) / iters
+    frames = N * Tn
+    flop = frames * (2 * C * 6 * H + 2 * (2 * H) * 6 * H + 2 * 2 * (2 * H * 3 * H) + 2 * 2 * H * 12)
+    peak_tf, _, _ = peaks()
+    out = {"metric": "EMA frames/sec, speech-to-EMA inversion encoder forward (BASELINE configs[4])",
+           "value": frames / (ms_dev / 1e3), "unit": "frames/s", "ms_per_batch": ms_dev,
+           "e2e": {"value": frames / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": host.numel() * 4,
+                   "d2h_bytes_per_step": y.numel() * 4},
+           "audio_seconds_per_second": frames / 200.0 / (ms_dev / 1e3),
+           "workload": f"{N} utterances x {Tn} frames (2 s at 200 Hz) of {C}-d features -> 12-dim EMA, hidden {H}, bf16x3 input "
+                       "projections on tcgen05 + persistent cluster GRU kernel (fp32 FFMA, W_hh resident in shared memory)",
+           "roofline": {"bound": "tensor", "achieved": flop / (ms_dev / 1e3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": flop / (ms_dev / 1e3) / 1e12 / peak_tf,
+                        "note": "6.3 MFLOP per frame; 2 x 400 strictly sequential recurrent steps bound the latency, and the "
+                                "recurrence runs in fp32 FFMA for parity (the fp32 CUDA-core peak, not the tensor peak, bounds it)"}}
+    if cpu:
+        from oracle import inversion_oracle as I
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        xs = host[:8].clone()
+        I.bigru_forward(sd, xs[:2])
+        t0 = time.perf_counter()
+        ref = I.bigru_forward(sd, xs)
+        dt = time.perf_counter() - t0
+        err = float((y[:8] - ref).norm() / ref.norm())
+        out["cpu_baseline"] = {"value": 8 * Tn / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+                               "sample": "8 utterances x 400 frames, oracle/inversion_oracle.py (fp32)"}
+        out["rel_err_vs_oracle"] = err
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -329,7 +389,10 @@ def run_ours(args):
     rank, local, world = env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dp = DataParallel(backend="nccl", device=dev)      # one process per GPU; NCCL over NVLink / NVSwitch
+    # (NCCL_DEBUG=INFO with NCCL_DEBUG_FILE set by the caller lets DataParallel.describe() name NVLS vs ring; it is not
+    # set here because NCCL then also prints its version banner on stdout, next to the one JSON line)
+    # one process per GPU; NCCL over NVLink / NVSwitch; the bf16 speed mode ships its gradients as bf16
+    dp = DataParallel(backend="nccl", device=dev, compress="bf16" if args.precision == "bf16" and not args.fp32_wire else None)
     _lib.load()
 
     B = BATCH_PER_GPU
@@ -371,7 +434,7 @@ def run_ours(args):
     last = None
     for _ in range(args.steps):
         ts.step(pinned["x"], pinned["y"], pinned["ar"])
-        last = ts.vals.cpu()            # D2H read of the nine logged scalars (forces completion)
+        last = ts.values_tensor().cpu()            # D2H read of the nine logged scalars (forces completion)
     f1.record()
     barrier()
     e2e_ms_total = f0.elapsed_time(f1)
@@ -471,6 +534,7 @@ def run_ours(args):
         return d
     guarded("stft_loss", stft)
     guarded("car_inference", lambda: car_inference(dev, args.precision))
+    guarded("inversion", lambda: inversion(dev, cpu=not args.no_cpu_baseline))
     if not args.no_cpu_baseline:
         guarded("stock_torch_gpu", lambda: stock_torch_gpu(dev))
 
@@ -495,6 +559,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("ARTIC_PRECISION", "bf16"), choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the legs that execute oracle/ (CPU + stock torch GPU)")
     ap.add_argument("--no-extras", action="store_true", help="headline line only")
+    ap.add_argument("--fp32-wire", action="store_true", help="exchange gradients in fp32 also in the bf16 mode")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

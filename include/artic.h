@@ -137,6 +137,11 @@ typedef struct {
   /* bf16x3 mode (see artic_tapconv_t): split copies of X and dY; used when both are given with fp32 X / dY */
   const void* X_sp; const void* dY_sp;
   int64_t x_plane, y_plane;
+  /* optional bias gradient: dbias[g*Cog + co] += sum over all (n, row) of dY (fp32, G*Cog entries).  The tcgen05
+   * kernel gets it from one extra accumulator (a ones-matrix times the dY tile it has staged anyway) — no second
+   * pass over dY; otherwise a column-sum kernel is launched (artic_colsum).  Requires q0 + yoff = 0 and nq = y.len,
+   * i.e. the launch covers every row of dY (true for every convolution's weight gradient). */
+  float* dbias;
 } artic_tapwgrad_t;
 
 int artic_tapconv_wgrad(const artic_tapwgrad_t* p, void* stream);
@@ -212,7 +217,8 @@ int artic_split(const float* src, void* hi, int64_t plane, int64_t n, void* stre
 
 /* Host-side counters of which kernel family took each contraction since the last reset (tests assert that every
  * eligible layer runs on the tensor cores): out[0..9] = conv {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic,
- * channel-1 kernels}, wgrad {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic, channel-1 kernels}, reserved x2.
+ * channel-1 kernels}, wgrad {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic, channel-1 kernels}, tcgen05 weight
+ * gradients that also produced the bias gradient, reserved.
  * Counted when a launch is ENQUEUED (graph replays do not count).  reset != 0 clears them after the read. */
 int artic_path_counts(int64_t* h_out, int32_t reset);
 
@@ -319,6 +325,21 @@ int artic_mel_loss_fwd_bwd(const float* x, const float* y, int32_t B, int32_t T,
                            int32_t win_length, const float* window, const float* melmat,
                            const int32_t* mel_ranges, int32_t n_mels, float eps, float log_scale,
                            float loss_scale, float* slot, float grad_scale, float* dx, void* stream);
+
+/* ---- speech-to-EMA inversion encoder (models/pytorch_models.py:22-77) ------------------------------ */
+
+/*
+ * One bidirectional GRU layer, inference forward (torch.nn.GRU(batch_first=True, bidirectional=True),
+ * models/pytorch_models.py:27,30,63-66), given the input projections of all steps:
+ *   gi   (N, T, 2*3H) fp32 = [W_ih x + b_ih | W_ih_reverse x + b_ih_reverse], gates [r|z|n] per direction
+ *        (a plain GEMM: artic_tapconv with one tap)
+ *   w_hh (2, 3H, H) fp32 = weight_hh_l0, weight_hh_l0_reverse;  b_hh (2, 3H) likewise
+ *   out  (N, T, 2H) fp32 = [forward h_t | reverse h_t]
+ * All N sequences have T steps; H <= 256.  One persistent cluster kernel: W_hh stays in shared memory for the
+ * whole sequence, h is exchanged through distributed shared memory once per step.
+ */
+int artic_bigru_layer(const float* gi, const float* w_hh, const float* b_hh, float* out, int32_t N, int32_t T,
+                      int32_t H, void* stream);
 
 /* ---- optimiser (torch.optim.Adam + MultiStepLR, bin/train.py:372-383,424-435,1750-1789) ---- */
 

@@ -117,6 +117,7 @@ def test_conv_layer_fwd_dgrad_wgrad(case, wn, prec):
         if lay.x3:      # eligible shape: every contraction of the layer ran on the split-operand tcgen05 kernels
             assert pc["conv_tc_x3"] >= 2 and pc["conv_generic"] == 0 and pc["conv_c1"] == 0, pc
             assert pc["wgrad_tc_x3"] == 1 and pc["wgrad_generic"] == 0, pc
+            assert pc["wgrad_bias_fused"] == (0 if lay.dw_swapped else 1), pc      # bias gradient from the same launch
             # the split copy written by the epilogue reproduces the fp32 output to ~2^-17
             sp = Y2.sp.float()
             assert rel_err((sp[0] + sp[1]).cpu(), Y2.t.cpu()) < 2e-5

@@ -65,3 +65,15 @@ def test_bigru_vs_reference_full_width():
         want = m(x)
     got = I.bigru_forward(m.state_dict(), x)
     assert rel_err(got, want) < 1e-5
+
+
+def test_plugin_class_has_the_reference_state_dict(gold):
+    """articulatory_b200.models.BiGRU (parameter containers of the CUDA path) loads the reference's state_dict
+    strictly, for the plain and the AR + tanh variants (no GPU needed)."""
+    from articulatory_b200.models import BiGRU
+    for k in ("plain", "ar_tanh"):
+        m = BiGRU(**gold[k]["params"])
+        res = m.load_state_dict(gold[k]["sd"], strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+    with pytest.raises(NotImplementedError):
+        BiGRU(use_spk_emb=True)
