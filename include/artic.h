@@ -304,6 +304,18 @@ int artic_stft_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, in
                         int32_t hop, int32_t win_length, const float* window, float eps,
                         const float* sums, float w_sc, float w_mag, float* dx, void* stream);
 
+/* All resolutions of MultiResolutionSTFTLoss (losses/stft_loss.py:146-170) in ONE launch each way.  h_res: HOST array of
+ * R <= 8 resolutions (window = device pointer to win_length taps); sums: R x 3 (row r = resolution r, as above);
+ * the backward applies the same w_sc / w_mag to every resolution (the loss is their mean: pass g / R). */
+typedef struct {
+  int32_t n_fft, hop, win_length, reserved_;
+  const float* window;
+} artic_stft_res_t;
+int artic_mrstft_loss_fwd(const float* x, const float* y, int32_t B, int32_t T, const artic_stft_res_t* h_res,
+                          int32_t R, float eps, float* sums, void* stream);
+int artic_mrstft_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, const artic_stft_res_t* h_res,
+                          int32_t R, float eps, const float* sums, float w_sc, float w_mag, float* dx, void* stream);
+
 /*
  * MelSpectrogramLoss (losses/mel_loss.py:82-111,151-166): STFT -> sqrt(clamp(power, eps))
  * -> melmat (n_bins x n_mels, row-major fp32) -> clamp(eps) -> log (log_scale = 1 for ln,
