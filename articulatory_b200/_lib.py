@@ -51,11 +51,6 @@ class TapWgrad(C.Structure):
                 ("dbias", C.c_void_p)]
 
 
-class StftRes(C.Structure):
-    _fields_ = [("n_fft", C.c_int32), ("hop", C.c_int32), ("win_length", C.c_int32), ("reserved_", C.c_int32),
-                ("window", C.c_void_p)]
-
-
 class AdamHyper(C.Structure):
     _fields_ = [("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("gamma", C.c_float), ("step", C.c_int32), ("n_milestones", C.c_int32),
@@ -117,8 +112,6 @@ SIGNATURES = {
     "artic_l1_bwd": (C.c_int, [_p, _p, _i64, _f, _p, _i32, _i32, _p]),
     "artic_stft_loss_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _p]),
     "artic_stft_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _f, _f, _p, _p]),
-    "artic_mrstft_loss_fwd": (C.c_int, [_p, _p, _i32, _i32, C.POINTER(StftRes), _i32, _f, _p, _p]),
-    "artic_mrstft_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, C.POINTER(StftRes), _i32, _f, _p, _f, _f, _p, _p]),
     "artic_mel_loss_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _f, _f, _p, _p]),
     "artic_mel_loss_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _f, _f, _p, _p]),
     "artic_mel_loss_fwd_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _f, _f, _f, _p, _f, _p, _p]),
@@ -178,7 +171,7 @@ def call(name, *args):
 
 
 PATH_NAMES = ("conv_tc", "conv_tc_x3", "conv_generic", "conv_c1", "wgrad_tc", "wgrad_tc_x3", "wgrad_generic", "wgrad_c1",
-              "wgrad_bias_fused")
+              "wgrad_bias_fused", "conv_tc_cluster")
 
 
 def path_counts(reset=False):

@@ -9,13 +9,14 @@
 // T dependent steps of a (items x H) x (H x 3H) product — latency bound, so the design is a PERSISTENT kernel that
 // keeps everything on chip for the whole sequence:
 //
-//   * one thread-block CLUSTER per (direction, group of 16 batch items); the cluster's CTAs split the hidden
-//     units (32 per CTA, cluster size ceil(H / 32) <= 8; lanes past H idle);
-//   * each CTA holds ITS rows of W_hh (3 gates x 32 units x H, fp32) in shared memory for the whole sequence
-//     (96 KB at H = 256) — the weights are read from HBM exactly once;
-//   * h lives in shared memory, replicated in every CTA of the cluster ([k][item] so that one 128-bit read feeds
-//     four items, broadcast to the warp); after each step a CTA writes its 32 new units straight into the OTHER
-//     CTAs' copies through distributed shared memory and the cluster synchronises once (double-buffered h);
+//   * one thread-block CLUSTER per (direction, group of 8 batch items); the cluster's CTAs split the hidden
+//     units (64 per CTA, cluster size ceil(H / 64) <= 4: 33 such clusters are co-resident on a B200, so batch 128 x
+//     2 directions is ONE wave; clusters of 8 are limited to ~1 per GPC and needed two);
+//   * each CTA holds ITS rows of W_hh (3 gates x 64 units x H, fp32) in shared memory for the whole sequence
+//     (192 KB at H = 256) — the weights are read from HBM exactly once;
+//   * h lives in shared memory, replicated in every CTA of the cluster ([k][item]: two broadcast 128-bit reads feed
+//     all eight items); after each step a CTA writes its 64 new units straight into the OTHER CTAs' copies through
+//     distributed shared memory and the cluster synchronises once (double-buffered h);
 //   * fp32 FFMA throughout (lanes along the hidden units: conflict-free weight reads): the recurrence feeds its
 //     own rounding error back T times, and the parity gate is 1e-3 against the fp32 reference;
 //   * gi of step t+1 is fetched into registers before the FMA loop of step t (hides the L2 latency).
@@ -27,17 +28,20 @@ namespace cg = cooperative_groups;
 
 namespace artic {
 
-constexpr int GRU_ITEMS = 16;      // batch items per cluster
-constexpr int GRU_UNITS = 32;      // hidden units per CTA (= lanes)
-constexpr int GRU_THREADS = 256;   // 8 warps: (item group of 4) x (half of the k range)
+constexpr int GRU_ITEMS = 8;       // batch items per cluster
+constexpr int GRU_UNITS = 64;      // hidden units per CTA
+constexpr int GRU_THREADS = 256;   // 8 warps = (unit half of 32 lanes) x (quarter of the k range)
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
+// Thread (unit u, k quarter kq) accumulates ALL 8 items x 3 gates over its quarter of k — every weight is read from
+// shared memory once per step per CTA (3 conflict-free 128-byte wavefronts + 2 broadcast reads of h per 24 FMAs) —
+// then the four partial sums meet through shared memory and the same thread finishes items 2kq, 2kq+1 of its unit.
 __global__ void __launch_bounds__(GRU_THREADS, 1)
 bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                    float* __restrict__ out, int N, int T, int H) {
   cg::cluster_group cluster = cg::this_cluster();
-  const int csize = (int)cluster.num_blocks();          // = ceil(H / 32)
+  const int csize = (int)cluster.num_blocks();          // = ceil(H / 64)
   const int rank = (int)cluster.block_rank();
   const int cid = (int)blockIdx.x / csize;               // cluster index
   const int n_groups = (N + GRU_ITEMS - 1) / GRU_ITEMS;
@@ -45,14 +49,14 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
   const int n0 = (cid % n_groups) * GRU_ITEMS;
 
   extern __shared__ __align__(16) float smem[];
-  float* Wt = smem;                                      // [3 gates][H k][32 units]
-  float* hbuf = Wt + 3 * H * GRU_UNITS;                  // [2][H k][16 items]
-  float* red = hbuf + 2 * H * GRU_ITEMS;                 // [128 threads][12]
+  float* Wt = smem;                                      // [3 gates][H k][64 units]
+  float* hbuf = Wt + 3 * H * GRU_UNITS;                  // [2][H k][8 items]
+  float* red = hbuf + 2 * H * GRU_ITEMS;                 // [4 dest kq][3 sources][6 = gate x item][64 units]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ig = warp & 3;                               // item group: items ig*4 .. ig*4+3
-  const int kh = warp >> 2;                              // k half
-  const int unit = rank * GRU_UNITS + lane;              // hidden unit of this lane
+  const int ul = (warp & 1) * 32 + lane;                 // unit inside the CTA
+  const int kq = warp >> 1;                              // k quarter; this thread FINISHES items 2kq, 2kq + 1
+  const int unit = rank * GRU_UNITS + ul;                // hidden unit
   const bool live = unit < H;
 
   // ---- one-time: this CTA's rows of W_hh (transposed to [gate][k][unit]), zero initial state
@@ -63,7 +67,7 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
   }
   for (int i = tid; i < 2 * H * GRU_ITEMS; i += GRU_THREADS) hbuf[i] = 0.f;
   float bh[3] = {0.f, 0.f, 0.f};
-  if (kh == 0 && live) {
+  if (live) {
 #pragma unroll
     for (int g = 0; g < 3; ++g) bh[g] = __ldg(b_hh + (size_t)dir * 3 * H + g * H + unit);
   }
@@ -71,83 +75,97 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
 
   const int GS = 2 * 3 * H;                              // gi row stride (both directions)
   const float* gi_d = gi + (size_t)dir * 3 * H + unit;
-  float gin[3][4];                                       // gi of the NEXT step (gate, item)
+  const int na = n0 + 2 * kq, nb = na + 1;               // the two batch items this thread finishes
+  float gin[3][2];                                       // their gi of the NEXT step (gate, item)
   auto fetch = [&](int t) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = n0 + ig * 4 + i;
-#pragma unroll
-      for (int g = 0; g < 3; ++g)
-        gin[g][i] = (n < N && live) ? __ldg(gi_d + ((size_t)n * T + t) * GS + g * H) : 0.f;
+    for (int g = 0; g < 3; ++g) {
+      gin[g][0] = (na < N && live) ? __ldg(gi_d + ((size_t)na * T + t) * GS + g * H) : 0.f;
+      gin[g][1] = (nb < N && live) ? __ldg(gi_d + ((size_t)nb * T + t) * GS + g * H) : 0.f;
     }
   };
-  if (kh == 0 && T > 0) fetch(dir ? T - 1 : 0);
+  if (T > 0) fetch(dir ? T - 1 : 0);
 
-  const int kb = kh ? H / 2 : 0, ke = kh ? H : H / 2;
+  const int kb = kq * (H / 4), ke = kb + H / 4;          // H % 4 == 0 (checked by the caller)
   for (int s = 0; s < T; ++s) {
     const int t = dir ? T - 1 - s : s;
     const float* hc = hbuf + (size_t)(s & 1) * H * GRU_ITEMS;          // h_t (complete, all units)
     float* hn_local = hbuf + (size_t)((s + 1) & 1) * H * GRU_ITEMS;    // h_{t+1} (being assembled)
-    float gcur[3][4];
-    if (kh == 0) {
+    float gcur[3][2];
 #pragma unroll
-      for (int g = 0; g < 3; ++g)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gcur[g][i] = gin[g][i];
-      if (s + 1 < T) fetch(dir ? t - 1 : t + 1);
-    }
-    float acc[3][4];
+    for (int g = 0; g < 3; ++g) { gcur[g][0] = gin[g][0]; gcur[g][1] = gin[g][1]; }
+    if (s + 1 < T) fetch(dir ? t - 1 : t + 1);
+    float acc[3][8];
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
+      for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
 #pragma unroll 4
     for (int k = kb; k < ke; ++k) {
-      const float4 h4 = *reinterpret_cast<const float4*>(hc + k * GRU_ITEMS + ig * 4);   // warp-wide broadcast
-      const float wr = Wt[(0 * H + k) * GRU_UNITS + lane];
-      const float wz = Wt[(1 * H + k) * GRU_UNITS + lane];
-      const float wn = Wt[(2 * H + k) * GRU_UNITS + lane];
-      acc[0][0] = fmaf(wr, h4.x, acc[0][0]); acc[0][1] = fmaf(wr, h4.y, acc[0][1]);
-      acc[0][2] = fmaf(wr, h4.z, acc[0][2]); acc[0][3] = fmaf(wr, h4.w, acc[0][3]);
-      acc[1][0] = fmaf(wz, h4.x, acc[1][0]); acc[1][1] = fmaf(wz, h4.y, acc[1][1]);
-      acc[1][2] = fmaf(wz, h4.z, acc[1][2]); acc[1][3] = fmaf(wz, h4.w, acc[1][3]);
-      acc[2][0] = fmaf(wn, h4.x, acc[2][0]); acc[2][1] = fmaf(wn, h4.y, acc[2][1]);
-      acc[2][2] = fmaf(wn, h4.z, acc[2][2]); acc[2][3] = fmaf(wn, h4.w, acc[2][3]);
+      const float4 ha = *reinterpret_cast<const float4*>(hc + k * GRU_ITEMS);        // warp-wide broadcasts
+      const float4 hb = *reinterpret_cast<const float4*>(hc + k * GRU_ITEMS + 4);
+      const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+      const float w0 = Wt[(0 * H + k) * GRU_UNITS + ul];
+      const float w1 = Wt[(1 * H + k) * GRU_UNITS + ul];
+      const float w2 = Wt[(2 * H + k) * GRU_UNITS + ul];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] = fmaf(w0, hv[i], acc[0][i]);
+        acc[1][i] = fmaf(w1, hv[i], acc[1][i]);
+        acc[2][i] = fmaf(w2, hv[i], acc[2][i]);
+      }
     }
-    if (kh == 1) {
-      float* r = red + (size_t)(ig * 32 + lane) * 12;
+    // hand the partial sums of the items finished by the other three k quarters to them
+    float own[3][2];
 #pragma unroll
-      for (int g = 0; g < 3; ++g)
+    for (int d = 0; d < 4; ++d) {
+      if (d == kq) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r[g * 4 + i] = acc[g][i];
+        for (int g = 0; g < 3; ++g) { own[g][0] = acc[g][2 * d]; own[g][1] = acc[g][2 * d + 1]; }
+      } else {
+        const int slot = kq < d ? kq : kq - 1;
+        float* r = red + (size_t)((d * 3 + slot) * 6) * GRU_UNITS + ul;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          r[(g * 2 + 0) * GRU_UNITS] = acc[g][2 * d];
+          r[(g * 2 + 1) * GRU_UNITS] = acc[g][2 * d + 1];
+        }
+      }
     }
     __syncthreads();
-    if (kh == 0 && live) {
-      const float* r = red + (size_t)(ig * 32 + lane) * 12;
-      const float4 hold = *reinterpret_cast<const float4*>(hc + unit * GRU_ITEMS + ig * 4);
-      const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
-      float hv[4];
+    if (live) {
+      float gh[3][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float ghr = acc[0][i] + r[0 * 4 + i] + bh[0];
-        const float ghz = acc[1][i] + r[1 * 4 + i] + bh[1];
-        const float ghn = acc[2][i] + r[2 * 4 + i] + bh[2];
-        const float rg = sigmoidf_(gcur[0][i] + ghr);
-        const float zg = sigmoidf_(gcur[1][i] + ghz);
-        const float ng = tanhf(gcur[2][i] + rg * ghn);
-        hv[i] = (1.f - zg) * ng + zg * ho[i];
-        const int n = n0 + ig * 4 + i;
-        if (n < N) out[((size_t)n * T + t) * (2 * H) + dir * H + unit] = hv[i];
+      for (int g = 0; g < 3; ++g) { gh[g][0] = own[g][0] + bh[g]; gh[g][1] = own[g][1] + bh[g]; }
+#pragma unroll
+      for (int slot = 0; slot < 3; ++slot) {
+        const float* r = red + (size_t)((kq * 3 + slot) * 6) * GRU_UNITS + ul;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          gh[g][0] += r[(g * 2 + 0) * GRU_UNITS];
+          gh[g][1] += r[(g * 2 + 1) * GRU_UNITS];
+        }
       }
-      // publish this lane's unit of h_{t+1} to every CTA of the cluster (distributed shared memory)
-      const float4 hv4 = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      float* dst_local = hn_local + unit * GRU_ITEMS + ig * 4;
+      const float2 hold = *reinterpret_cast<const float2*>(hc + unit * GRU_ITEMS + 2 * kq);
+      const float ho[2] = {hold.x, hold.y};
+      float hv2[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float rg = sigmoidf_(gcur[0][j] + gh[0][j]);
+        const float zg = sigmoidf_(gcur[1][j] + gh[1][j]);
+        const float ng = tanhf(gcur[2][j] + rg * gh[2][j]);
+        hv2[j] = (1.f - zg) * ng + zg * ho[j];
+        const int n = na + j;
+        if (n < N) out[((size_t)n * T + t) * (2 * H) + dir * H + unit] = hv2[j];
+      }
+      // publish this unit's two items of h_{t+1} to every CTA of the cluster (distributed shared memory)
+      float* dst_local = hn_local + unit * GRU_ITEMS + 2 * kq;
       for (int pr = 0; pr < csize; ++pr) {
         float* dst = cluster.map_shared_rank(dst_local, pr);
-        *reinterpret_cast<float4*>(dst) = hv4;
+        *reinterpret_cast<float2*>(dst) = make_float2(hv2[0], hv2[1]);
       }
     }
-    cluster.sync();     // h_{t+1} complete everywhere; also orders the reads of h_t before its next overwrite
+    cluster.sync();     // h_{t+1} complete everywhere; also orders the reads of h_t / red before their next overwrite
   }
 }
 
@@ -160,11 +178,11 @@ extern "C" int artic_bigru_layer(const float* gi, const float* w_hh, const float
                                  int32_t H, void* stream) {
   ARTIC_CHECK_ARG(gi && w_hh && b_hh && out, "null pointer");
   ARTIC_CHECK_ARG(N >= 0 && T >= 0, "bad dims");
-  ARTIC_CHECK_ARG(H >= 1 && H <= 256, "hidden size must be <= 256 (32 units per CTA, portable cluster of <= 8 CTAs)");
+  ARTIC_CHECK_ARG(H >= 4 && H <= 256 && H % 4 == 0, "hidden size must be a multiple of 4, <= 256 (64 units per CTA, cluster of <= 4)");
   if (N == 0 || T == 0) return ARTIC_OK;
-  const int csize = (H + 31) / 32;
+  const int csize = (H + 63) / 64;
   const int n_groups = (N + GRU_ITEMS - 1) / GRU_ITEMS;
-  const size_t smem = sizeof(float) * ((size_t)3 * H * GRU_UNITS + 2 * (size_t)H * GRU_ITEMS + 128 * 12);
+  const size_t smem = sizeof(float) * ((size_t)3 * H * GRU_UNITS + 2 * (size_t)H * GRU_ITEMS + 4 * 3 * 6 * GRU_UNITS);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     if (cudaFuncSetAttribute(bigru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

@@ -103,10 +103,12 @@ struct Smem {
   }
 };
 
-__device__ __forceinline__ void stft_loss_fwd_body(const float* __restrict__ x, const float* __restrict__ y,
-                                                   const FrameGeom& g, const float* __restrict__ window, float eps,
-                                                   float* __restrict__ sums, int f, int b, float* smem_f) {
+__global__ void __launch_bounds__(512) stft_loss_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            FrameGeom g, const float* __restrict__ window, float eps,
+                                                            float* __restrict__ sums) {
+  extern __shared__ __align__(16) float smem_f[];
   Smem sm(smem_f, g.N);
+  const int f = blockIdx.x, b = blockIdx.y;
   make_twiddles(sm.twr, sm.twi, g.N);
   load_frame(x + (int64_t)b * g.T, y + (int64_t)b * g.T, window, g, f, sm.r0, sm.i0);
   __syncthreads();
@@ -134,37 +136,6 @@ __device__ __forceinline__ void stft_loss_fwd_body(const float* __restrict__ x, 
   }
 }
 
-__global__ void __launch_bounds__(512) stft_loss_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                            FrameGeom g, const float* __restrict__ window, float eps,
-                                                            float* __restrict__ sums) {
-  extern __shared__ __align__(16) float smem_f[];
-  stft_loss_fwd_body(x, y, g, window, eps, sums, blockIdx.x, blockIdx.y, smem_f);
-}
-
-// All resolutions of MultiResolutionSTFTLoss in ONE launch: a 1-D grid over (resolution, batch item, frame), largest
-// transform first.  Three per-resolution launches of ~30 us each leave most SMs idle at their tails and pay three
-// launch latencies; together the ~4000 frame blocks fill the machine once.
-constexpr int MR_MAX = 8;
-struct MRGeom {
-  int R, B;
-  int blk_begin[MR_MAX + 1];
-  int frames[MR_MAX];
-  FrameGeom g[MR_MAX];
-  const float* window[MR_MAX];
-  float inv_numel[MR_MAX];
-  int slot[MR_MAX];            // row of `sums` (the caller's resolution index)
-};
-
-__global__ void __launch_bounds__(512) mrstft_loss_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                              const __grid_constant__ MRGeom mg, float eps,
-                                                              float* __restrict__ sums) {
-  extern __shared__ __align__(16) float smem_f[];
-  int r = 0;
-  while (r + 1 < mg.R && (int)blockIdx.x >= mg.blk_begin[r + 1]) ++r;
-  const int local = (int)blockIdx.x - mg.blk_begin[r];
-  stft_loss_fwd_body(x, y, mg.g[r], mg.window[r], eps, sums + 3 * mg.slot[r], local % mg.frames[r], local / mg.frames[r], smem_f);
-}
-
 // Adjoint of the framing + rFFT: the caller has written conj(G[k]) for k <= N/2 (zeros above)
 // into (gr, gi); result dx_frame[n] = w[n] * Re(FFT(conj G))[n] is overlap-added into dx.
 template <typename TW>
@@ -187,12 +158,14 @@ __device__ __forceinline__ void adjoint_to_dx(float* gr, float* gi, float* orr, 
 // forward transform; torch's fp32 path sits at ~1e-4).  The adjoint transform stays fp32.
 // smem (doubles): r0[N] i0[N] r1[N] i1[N] twr[N/2] twi[N/2]; the idle double pair is re-used as
 // four fp32 arrays for the adjoint.
-__device__ __forceinline__ void stft_loss_bwd_body(const float* __restrict__ x, const float* __restrict__ y,
-                                                   const FrameGeom& g, const float* __restrict__ window, float eps,
-                                                   const float* __restrict__ sums, float w_sc, float w_mag, float inv_numel,
-                                                   float* __restrict__ dx, int f, int b, double* smem_d) {
+__global__ void __launch_bounds__(512) stft_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            FrameGeom g, const float* __restrict__ window, float eps,
+                                                            const float* __restrict__ sums, float w_sc, float w_mag,
+                                                            float inv_numel, float* __restrict__ dx) {
+  extern __shared__ __align__(16) double smem_d[];
   const int N = g.N;
   double *r0 = smem_d, *i0 = r0 + N, *r1 = i0 + N, *i1 = r1 + N, *twr = i1 + N, *twi = twr + (N >> 1);
+  const int f = blockIdx.x, b = blockIdx.y;
   make_twiddles(twr, twi, N);
   load_frame(x + (int64_t)b * g.T, y + (int64_t)b * g.T, window, g, f, r0, i0);
   __syncthreads();
@@ -225,26 +198,6 @@ __device__ __forceinline__ void stft_loss_bwd_body(const float* __restrict__ x, 
   }
   __syncthreads();
   adjoint_to_dx(gr, gi, orr, oi, twr, twi, g, window, f, dx + (int64_t)b * g.T);
-}
-
-__global__ void __launch_bounds__(512) stft_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                            FrameGeom g, const float* __restrict__ window, float eps,
-                                                            const float* __restrict__ sums, float w_sc, float w_mag,
-                                                            float inv_numel, float* __restrict__ dx) {
-  extern __shared__ __align__(16) double smem_d[];
-  stft_loss_bwd_body(x, y, g, window, eps, sums, w_sc, w_mag, inv_numel, dx, blockIdx.x, blockIdx.y, smem_d);
-}
-
-__global__ void __launch_bounds__(512) mrstft_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                              const __grid_constant__ MRGeom mg, float eps,
-                                                              const float* __restrict__ sums, float w_sc, float w_mag,
-                                                              float* __restrict__ dx) {
-  extern __shared__ __align__(16) double smem_d[];
-  int r = 0;
-  while (r + 1 < mg.R && (int)blockIdx.x >= mg.blk_begin[r + 1]) ++r;
-  const int local = (int)blockIdx.x - mg.blk_begin[r];
-  stft_loss_bwd_body(x, y, mg.g[r], mg.window[r], eps, sums + 3 * mg.slot[r], w_sc, w_mag, mg.inv_numel[r], dx,
-                     local % mg.frames[r], local / mg.frames[r], smem_d);
 }
 
 // ---- mel ---------------------------------------------------------------------------
@@ -445,67 +398,6 @@ extern "C" int artic_stft_loss_bwd(const float* x, const float* y, int32_t B, in
   dim3 grid(frames, B);
   stft_loss_bwd_kernel<<<grid, fft_threads(n_fft), sb, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, y, g, window, eps, sums, w_sc, w_mag, inv_numel, dx);
-  ARTIC_LAUNCH_CHECK();
-  return ARTIC_OK;
-}
-
-// Fills the multi-resolution launch table (largest transform first); returns the grid size or <0.
-static int mr_table(MRGeom& mg, int B, int T, const artic_stft_res_t* res, int R, int* max_n) {
-  int order[MR_MAX];
-  for (int i = 0; i < R; ++i) order[i] = i;
-  for (int i = 0; i < R; ++i)
-    for (int j = i + 1; j < R; ++j)
-      if (res[order[j]].n_fft > res[order[i]].n_fft) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
-  mg.R = R;
-  mg.B = B;
-  mg.blk_begin[0] = 0;
-  *max_n = 0;
-  for (int i = 0; i < R; ++i) {
-    const artic_stft_res_t& r = res[order[i]];
-    if (!check_geom(B, T, r.n_fft, r.hop, r.win_length) || r.window == nullptr) return -1;
-    mg.g[i] = FrameGeom{T, r.n_fft, r.hop, r.win_length, (r.n_fft - r.win_length) / 2};
-    mg.frames[i] = 1 + T / r.hop;
-    mg.window[i] = r.window;
-    mg.inv_numel[i] = 1.0f / ((float)B * (float)mg.frames[i] * (float)(r.n_fft / 2 + 1));
-    mg.slot[i] = order[i];
-    mg.blk_begin[i + 1] = mg.blk_begin[i] + mg.frames[i] * B;
-    if (r.n_fft > *max_n) *max_n = r.n_fft;
-  }
-  return mg.blk_begin[R];
-}
-
-extern "C" int artic_mrstft_loss_fwd(const float* x, const float* y, int32_t B, int32_t T, const artic_stft_res_t* h_res,
-                                     int32_t R, float eps, float* sums, void* stream) {
-  ARTIC_CHECK_ARG(x && y && h_res && sums, "null pointer");
-  ARTIC_CHECK_ARG(R >= 1 && R <= MR_MAX, "1..8 resolutions");
-  if (B == 0) return ARTIC_OK;
-  MRGeom mg;
-  int max_n = 0;
-  const int grid = mr_table(mg, B, T, h_res, R, &max_n);
-  ARTIC_CHECK_ARG(grid > 0, "unsupported STFT geometry");
-  const size_t sb = smem_bytes(max_n, 0);
-  int rc = ensure_smem(mrstft_loss_fwd_kernel, sb);
-  if (rc) return rc;
-  mrstft_loss_fwd_kernel<<<grid, fft_threads(max_n), sb, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, mg, eps, sums);
-  ARTIC_LAUNCH_CHECK();
-  return ARTIC_OK;
-}
-
-extern "C" int artic_mrstft_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, const artic_stft_res_t* h_res,
-                                     int32_t R, float eps, const float* sums, float w_sc, float w_mag, float* dx,
-                                     void* stream) {
-  ARTIC_CHECK_ARG(x && y && h_res && sums && dx, "null pointer");
-  ARTIC_CHECK_ARG(R >= 1 && R <= MR_MAX, "1..8 resolutions");
-  if (B == 0) return ARTIC_OK;
-  MRGeom mg;
-  int max_n = 0;
-  const int grid = mr_table(mg, B, T, h_res, R, &max_n);
-  ARTIC_CHECK_ARG(grid > 0, "unsupported STFT geometry");
-  const size_t sb = sizeof(double) * (size_t)5 * max_n;
-  int rc = ensure_smem(mrstft_loss_bwd_kernel, sb);
-  if (rc) return rc;
-  mrstft_loss_bwd_kernel<<<grid, fft_threads(max_n), sb, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, mg, eps, sums, w_sc,
-                                                                                                 w_mag, dx);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
 }

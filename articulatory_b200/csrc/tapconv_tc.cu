@@ -17,6 +17,11 @@
 //   activation -> global; two warps per TMEM lane quarter on alternating 32-channel chunks).
 //   Persistent over tiles; the accumulator is double-buffered in TMEM when it fits, so the
 //   epilogue of tile i overlaps the main loop of tile i+1.
+// * Weight multicast (Plan.cs = 2 / 4): the CTAs of a thread-block cluster work on consecutive row tiles of the SAME
+//   channel tile, so they stream identical weight stages.  Each CTA fetches 1/cs of every stage (a slice of the bn
+//   output-channel rows) and TMA-multicasts it into all cs shared memories; a stage is refilled once all cs MMA warps
+//   have released it (tcgen05.commit multicast onto every CTA's `w_empty`).  The deep layers (C >= 256) re-stream
+//   their whole weight once per 128..512-row tile and are bound by that L2 -> SM traffic, which this divides by cs.
 // * bf16x3 mode (template X3): fp32 activations and weights live in HBM next to SPLIT COPIES
 //   (bf16 hi = rn(x), lo = rn(x - hi); artic_split / this kernel's epilogue).  Every K chunk is
 //   issued three times — (x_hi, w_hi), (x_hi, w_lo), (x_lo, w_hi) — into the same fp32 TMEM
@@ -65,6 +70,8 @@ struct Plan {
   int32_t a_off16[ARTIC_MAX_TAPS];  // (phase * panel_bytes + shift * row_bytes) / 16 : descriptor offset of the tap
   int32_t layout_type;            // UMMA smem descriptor swizzle code
   int32_t n_kcl;                  // logical ci chunks (n_kc = 3 * n_kcl in the bf16x3 mode)
+  int32_t cs;                     // cluster size (weight multicast); 1 = no cluster
+  int32_t n_mg;                   // row-tile groups of cs consecutive tiles (n_mt / cs)
   long long* dbg;                 // debug timeline buffer (artic_debug_buffer) or nullptr
   int32_t dbg_flags;              // debug: 1 = skip epilogue stores, 2 = skip operand use
 };
@@ -131,8 +138,14 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
   const CUtensorMap& map_w_lo = mp.prob[prob_j].map_w_lo;
   // bf16x3: K chunk kc = 3 * kcl + part; part 0 = (x_hi, w_hi), 1 = (x_hi, w_lo), 2 = (x_lo, w_hi)
   const int n_wres = X3 ? 2 * pl.n_kcl : pl.n_kc;      // resident weight chunks: [w_hi chunks | w_lo chunks]
-  const int cta = (int)blockIdx.x - mp.cta_begin[prob_j];                 // this CTA's index / count inside its problem
-  const int ncta = mp.cta_begin[prob_j + 1] - mp.cta_begin[prob_j];
+  const int cs = pl.cs;                                                   // cluster size (cs > 1: single-problem launch)
+  const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  // work units are "super tiles": (group, row-tile group of cs tiles, channel tile); CTA `crank` of a cluster takes row
+  // tile mg * cs + crank of it.  cs == 1: a super tile is a tile, cta / ncta are this CTA's index / count in its problem.
+  const int cta = ((int)blockIdx.x - mp.cta_begin[prob_j]) / cs;
+  const int ncta = (mp.cta_begin[prob_j + 1] - mp.cta_begin[prob_j]) / cs;
+  const int n_super = pl.total_tiles / cs;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_AS], a_empty[MAX_AS], w_full[MAX_WS], w_empty[MAX_WS];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], w_res_full;
@@ -164,7 +177,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
       prefetch_tmap(&map_w);
       if (X3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
       for (int i = 0; i < pl.n_as; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-      for (int i = 0; i < pl.n_ws; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+      for (int i = 0; i < pl.n_ws; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], (uint32_t)cs); }
       for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], blockDim.x - 64); }
       mbar_init(&w_res_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -177,6 +190,11 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x) : "memory");
     tc_fence_after();
     tmem_base = tmem_base_s;
+  }
+  if (cs > 1) {
+    // no CTA may multicast into a peer (or arrive on its barriers) before that peer has initialised them.  (Warp 0 took
+    // the early exit from the setup rendezvous: re-converge everything on the cluster barrier.)
+    cluster_sync_all();
   }
   if (threadIdx.x == 32) dbg_mark(pl.dbg, 2);
 
@@ -202,7 +220,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
             tma_load_2d(w_base + (uint32_t)(kc * ntaps + t) * pl.w_tile_bytes, lo ? &map_w_lo : &map_w, &w_res_full,
                         (lo ? kc - pl.n_kcl : kc) * pl.kch, p.widx[t] * p.Cog);
         }
-      } else if (cta < pl.total_tiles) {
+      } else if (cta < n_super && cs == 1) {
         // the weights are not written by the predecessor kernel (tc::note_weights_written): fill the
         // weight pipeline with the first tile's stages while the predecessor is still finishing
         const int nt = cta % pl.n_nt;
@@ -222,11 +240,13 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
         }
       }
       pdl_wait();   // activations (and everything the epilogue touches) come from the predecessor
-      for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
+      const int wsl_rows = pl.bn / cs;                                   // weight rows this CTA fetches per tap (multicast slice)
+      const uint32_t wsl_off = (uint32_t)(crank * wsl_rows) * pl.row_bytes;
+      for (int tile = cta; tile < n_super; tile += ncta) {
         const int nt = tile % pl.n_nt;
         const int r = tile / pl.n_nt;
-        const int mtile = r % pl.n_mt;
-        const int g = r / pl.n_mt;
+        const int mtile = (r % pl.n_mg) * cs + crank;
+        const int g = r / pl.n_mg;
         for (int kc = 0; kc < pl.n_kc; ++kc) {
           const int kcl = X3 ? kc / 3 : kc;
           const CUtensorMap* mx = (X3 && kc % 3 == 2) ? &map_x_lo : &map_x;
@@ -265,9 +285,16 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
             if (pl.dbg != nullptr && n_wl < 64) tr_issue[n_wl++] = clock64();
 #endif
             mbar_expect_tx(&w_full[ws.stage], (uint32_t)nt_g * w_bytes);
-            for (int j = 0; j < nt_g; ++j)
-              tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes, mw,
-                          &w_full[ws.stage], kcl * pl.kch, (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn);
+            if (cs == 1) {
+              for (int j = 0; j < nt_g; ++j)
+                tma_load_2d(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes, mw,
+                            &w_full[ws.stage], kcl * pl.kch, (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn);
+            } else {
+              for (int j = 0; j < nt_g; ++j)     // this CTA's row slice of every tap tile, into all cs CTAs
+                tma_load_2d_mc(w_base + (uint32_t)ws.stage * pl.w_stage_bytes + (uint32_t)j * pl.w_tile_bytes + wsl_off, mw,
+                               &w_full[ws.stage], kcl * pl.kch,
+                               (p.widx[t0 + j] * p.G + g) * p.Cog + nt * pl.bn + crank * wsl_rows, cmask);
+            }
             ws.next();
           }
         }
@@ -296,7 +323,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
       const uint32_t bn = (uint32_t)pl.bn;
       const uint32_t w_base16 = w_base >> 4, wt16 = (uint32_t)pl.w_tile_bytes >> 4, ws16 = (uint32_t)pl.w_stage_bytes >> 4;
       if (pl.w_resident) mbar_wait(&w_res_full, 0);
-      for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
+      for (int tile = cta; tile < n_super; tile += ncta) {
         mbar_wait(&acc_empty[acc.stage], acc.phase ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)acc.stage * acc_cols;
@@ -352,7 +379,10 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
             if (pl.dbg != nullptr && n_ws_seen < 64) { if (lane == 0) tr_done[n_ws_seen] = clock64(); ++n_ws_seen; }
 #endif
             if (!w_res) {
-              if (leader) umma_commit(&w_empty[ws.stage]);
+              if (leader) {
+                if (cs == 1) umma_commit(&w_empty[ws.stage]);
+                else umma_commit_mc(&w_empty[ws.stage], cmask);      // the stage is shared: release it in every CTA
+              }
               ws.next();
             }
           }
@@ -385,11 +415,11 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     long long* rowoff = reinterpret_cast<long long*>(epi + ewarp * EPI_WARP_BYTES);          // [sub-tile][32 rows]
     float* bias_s = reinterpret_cast<float*>(epi + ewarp * EPI_WARP_BYTES + 4 * 32 * 8);       // [chunk][32]
     const float neg_slope = p.act == ARTIC_ACT_LRELU ? p.act_slope : 1.f;
-    for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
+    for (int tile = cta; tile < n_super; tile += ncta) {
       const int nt = tile % pl.n_nt;
       const int r = tile / pl.n_nt;
-      const int mtile = r % pl.n_mt;
-      const int g = r / pl.n_mt;
+      const int mtile = (r % pl.n_mg) * cs + crank;
+      const int g = r / pl.n_mg;
       const int cbase = g * p.Cog + nt * pl.bn;
       for (int m = 0; m < pl.mt; ++m) {   // output offset of this lane's row in every sub-tile (-1: not stored)
         const int mrow = m * 128 + ew * 32 + lane;
@@ -570,6 +600,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();     // peers may still multicast into / arrive on this CTA's shared memory
   if (pl.dbg != nullptr && blockIdx.x == 0 && threadIdx.x < 40) {
     pl.dbg[1 + 2 * threadIdx.x] = g_ev_first[threadIdx.x];
     pl.dbg[2 + 2 * threadIdx.x] = g_ev_last[threadIdx.x];
@@ -682,7 +713,8 @@ static inline int w_all_bytes(const tc::Plan& pl, int ntaps, bool x3) { return (
 // Plans one problem for the tensor-core kernel: returns 1 (pr filled: parameters, plan, tensor maps,
 // pr_smem / pr_cost set), 0 if the shape is not eligible, <0 on error.
 // n_share = number of problems that will share the grid (each gets ~1/n_share of the SMs).
-static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem, double& pr_cost, int n_share) {
+static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem, double& pr_cost, int n_share,
+                           bool allow_cluster) {
   const artic_tapconv_t& p = *pp;
   if (tc::g_debug[1]) return 0;                       // debug: force the generic kernel
   const bool x3 = p.dtype == ARTIC_F32 && p.out_dtype == ARTIC_F32 && p.X_sp != nullptr && p.Wt_sp != nullptr;
@@ -806,6 +838,19 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
   const int64_t total = (int64_t)pl.n_mt * pl.n_nt * p.G;
   if (total > (1 << 30)) return false;
   pl.total_tiles = (int)total;
+  // Weight multicast across a cluster of cs CTAs on consecutive row tiles: debug key 22 = 2 / 4 turns it on.  OFF by
+  // default: alone, the deep layers gain 20-30 % (256 -> 256 k7: 30.5 -> 21.8 us, 1024 -> 1024 k5: 67.8 -> 49.4 us,
+  // profiles/r2_cluster_sweep.log), but inside the train step, where 3..8 chains keep every SM busy, co-scheduling CTA
+  // pairs costs more than the saved L2 traffic (12.46 ms off, 12.66 all layers, 12.54 only >= 1.1 MB of weights per
+  // tile; profiles/r2_cluster_step.log).  Debug key 23: minimum KB of weights streamed per tile for a layer to cluster.
+  pl.cs = 1;
+  const int w_kb_tile = (int)((int64_t)pl.n_kc * p.ntaps * pl.bn * pl.row_bytes / 1024);
+  if (allow_cluster && !pl.w_resident && (tc::g_debug[22] == 2 || tc::g_debug[22] == 4) && w_kb_tile >= tc::g_debug[23]) {
+    const int want = tc::g_debug[22];
+    for (int c = want; c >= 2; c >>= 1)
+      if (pl.n_mt % c == 0 && (pl.bn / c) % 8 == 0 && total >= 2 * c) { pl.cs = c; break; }
+  }
+  pl.n_mg = pl.n_mt / pl.cs;
     return true;
   };
   // Tile shape: a small clock model per candidate (bn, mt), fitted to tools/tc_sweep.py on B200:
@@ -830,7 +875,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
       const double main_clk = (double)cand.n_kc * p.ntaps * (cand.kch / 16) * cand.mt * per_mma;
       const double epi_clk = cand.mt * ((bn + 63) / 64) * 700.0;
       // operand streaming: bytes per tile over min(bytes in flight / ~3000-clock TMA latency, fair share of L2)
-      const double w_tile = cand.w_resident ? 0.0 : (double)cand.n_kc * p.ntaps * bn * cand.row_bytes;
+      const double w_tile = cand.w_resident ? 0.0 : (double)cand.n_kc * p.ntaps * bn * cand.row_bytes / cand.cs;
       const double tile_bytes = (double)cand.n_kc * cand.a_stage_bytes + w_tile;
       const double inflight = (double)cand.n_as * cand.a_stage_bytes + (cand.w_resident ? 0.0 : (double)cand.n_ws * cand.w_stage_bytes);
       // every SM is busy with some stream's CTA: the L2 share of a CTA is 1 / #SMs (debug key 17 = 1: of this launch only)
@@ -892,7 +937,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
     const int rows_total = p.Wt_taps > 0 ? p.Wt_taps : (wmax + 1);
     cuuint64_t dims[2] = {(cuuint64_t)p.Cig, (cuuint64_t)rows_total * p.G * p.Cog};
     cuuint64_t strides[1] = {(cuuint64_t)p.Cig * 2};
-    cuuint32_t box[2] = {(cuuint32_t)pl.kch, (cuuint32_t)pl.bn};
+    cuuint32_t box[2] = {(cuuint32_t)pl.kch, (cuuint32_t)(pl.bn / pl.cs)};     // multicast: every CTA fetches a row slice
     cuuint32_t es[2] = {1, 1};
     CUresult rc = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x3 ? p.Wt_sp : p.Wt), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swizzle_of(pl.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -919,6 +964,7 @@ static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, c
   for (int j = 0; j < n; ++j) { tiles += mp.prob[j].pl.total_tiles; work += cost[j]; }
   int smem_bytes = 0;
   mp.cta_begin[0] = 0;
+  const int cs = (n == 1) ? mp.prob[0].pl.cs : 1;       // clusters only in single-problem launches (tc_plan_problem)
   for (int j = 0; j < n; ++j) {
     const int t = mp.prob[j].pl.total_tiles;
     int c = t;
@@ -926,6 +972,10 @@ static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, c
       c = (int)(num_sms() * (cost[j] / work) + 0.5);
       if (c < 1) c = 1;
       if (c > t) c = t;
+    }
+    if (cs > 1) {              // whole clusters: at most floor(SMs / cs) of them, one per super tile
+      int cl = t / cs < num_sms() / cs ? t / cs : num_sms() / cs;
+      c = cl * cs;
     }
     mp.cta_begin[j + 1] = mp.cta_begin[j] + c;
     if (smem[j] > smem_bytes) smem_bytes = smem[j];
@@ -944,11 +994,23 @@ static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, c
   cfg.blockDim = dim3((unsigned)(64 + 32 * n_ew));
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (w_early) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cs > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cs;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    g_path_counts[9] += 1;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = w_early ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t le = x3 ? cudaLaunchKernelEx(&cfg, tc::tapconv_tc_kernel<true>, mp) : cudaLaunchKernelEx(&cfg, tc::tapconv_tc_kernel<false>, mp);
   g_path_counts[x3 ? PATH_CONV_TC_X3 : PATH_CONV_TC] += n;
   if (le == cudaSuccess) le = cudaGetLastError();
@@ -981,7 +1043,7 @@ int artic_tapconv_tc_multi(const artic_tapconv_t* ps, int n, int* taken, cudaStr
       if (lrc != ARTIC_OK) return lrc;
       mp.n = 0;
     }
-    const int rc = tc_plan_problem(&ps[i], mp.prob[mp.n], smem[mp.n], cost[mp.n], n_share);
+    const int rc = tc_plan_problem(&ps[i], mp.prob[mp.n], smem[mp.n], cost[mp.n], n_share, n_live == 1);
     if (rc < 0) return rc;
     if (rc == 0) continue;
     taken[i] = 1;

@@ -57,7 +57,8 @@ class _MRSTFTFn(torch.autograd.Function):
         x2, y2 = _as_2d(x), _as_2d(y)
         R = len(mod.resolutions)
         sums = torch.zeros((R, 3), dtype=torch.float32, device=x2.device)
-        mod.forward_sums(x2, y2, sums)
+        for r, res in enumerate(mod.resolutions):
+            res.forward(x2, y2, sums[r])
         numel = torch.tensor([res.numel(*x2.shape) for res in mod.resolutions], dtype=torch.float32, device=x2.device)
         sc = (sums[:, 0].sqrt() / sums[:, 1].sqrt()).mean()      # stft_loss.py:61, :166
         mag = (sums[:, 2] / numel).mean()                        # stft_loss.py:82, :167
@@ -72,7 +73,8 @@ class _MRSTFTFn(torch.autograd.Function):
         dx = torch.zeros_like(x2)
         # the kernel takes host scalars for the two upstream gradients
         w_sc, w_mag = float(g_sc) / R, float(g_mag) / R
-        ctx.mod.backward_dx(x2, y2, sums, w_sc, w_mag, dx)
+        for r, res in enumerate(ctx.mod.resolutions):
+            res.backward(x2, y2, sums[r], w_sc, w_mag, dx)
         return dx.view(ctx.shape), None, None
 
 
@@ -84,27 +86,6 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
         super().__init__()
         assert len(fft_sizes) == len(hop_sizes) == len(win_lengths)
         self.resolutions = [STFTResolution(f, h, w, window) for f, h, w in zip(fft_sizes, hop_sizes, win_lengths)]
-
-    def _table(self, device):
-        arr = (_lib.StftRes * len(self.resolutions))()
-        for i, r in enumerate(self.resolutions):
-            arr[i].n_fft, arr[i].hop, arr[i].win_length, arr[i].window = r.fft_size, r.hop, r.win_length, ptr(r.window(device))
-        return arr
-
-    def forward_sums(self, x, y, sums):
-        """sums (R, 3) fp32 device, pre-zeroed: every resolution's [sum (Y-X)^2, sum Y^2, sum |ln Y - ln X|] — ONE launch."""
-        B, T = x.shape
-        call("artic_mrstft_loss_fwd", ptr(x), ptr(y), B, T, self._table(x.device), len(self.resolutions), 1e-7, ptr(sums))
-
-    def backward_dx(self, x, y, sums, w_sc, w_mag, dx):
-        """dx (B, T) += d/dx [ w_sc * sum_r sc_r + w_mag * sum_r mag_r ] with the sums read on the device — ONE launch."""
-        B, T = x.shape
-        call("artic_mrstft_loss_bwd", ptr(x), ptr(y), B, T, self._table(x.device), len(self.resolutions), 1e-7, ptr(sums),
-             float(w_sc), float(w_mag), ptr(dx))
-
-    def loss_and_grad(self, x, y, sums, w_sc, w_mag, dx):
-        self.forward_sums(x, y, sums)
-        self.backward_dx(x, y, sums, w_sc, w_mag, dx)
 
     def forward(self, x, y):
         """x predicted, y ground truth, (B, T) or (B, C, T) -> (sc_loss, mag_loss)."""

@@ -35,8 +35,9 @@ class BiGRU(torch.nn.Module):
         super().__init__()
         if use_spk_emb:
             raise NotImplementedError("speaker-embedding conditioning is outside the B200 hot path")
-        if hidden_size > 256:
-            raise NotImplementedError("hidden_size > 256 needs a cluster of more than 8 CTAs (artic_bigru_layer)")
+        if hidden_size > 256 or hidden_size % 4:
+            raise NotImplementedError("artic_bigru_layer keeps W_hh in the shared memory of a 4-CTA cluster: hidden_size must "
+                                      "be a multiple of 4, <= 256")
         if precision not in ("bf16x3", "fp32"):
             raise ValueError("the inversion encoder runs in the fp32-accurate modes only (bf16x3 / fp32)")
         self.precision = precision

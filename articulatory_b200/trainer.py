@@ -152,10 +152,12 @@ class TrainStep:
             # the STFT resolutions and the mel loss are independent of each other (dy is accumulated atomically)
             jobs = []
             if self.use_stft:                                                 # bin/train.py:289-297
-                def stft_job():         # all resolutions: one launch for the sums, one for the gradient
-                    self.stft.loss_and_grad(y2d, t2d, self.stft_sums, self.l_aux * inv_w / self.R,
-                                            self.l_aux * inv_w / self.R, dy)
-                jobs.append(stft_job)
+                for r, res in enumerate(self.stft.resolutions):
+                    def job(r=r, res=res):
+                        res.forward(y2d, t2d, self.stft_sums[r])
+                        res.backward(y2d, t2d, self.stft_sums[r], self.l_aux * inv_w / self.R,
+                                     self.l_aux * inv_w / self.R, dy)
+                    jobs.append(job)
             if self.use_mel:                                                  # :313-316
                 def mel_job():
                     n = self.mel.numel(B, T)
@@ -439,7 +441,8 @@ class TrainStep:
         self.slots.zero_()
         self.stft_sums.zero_()
         if self.use_stft:                                                     # :515-520
-            self.stft.forward_sums(y2d, t2d, self.stft_sums)
+            for r, res in enumerate(self.stft.resolutions):
+                res.forward(y2d, t2d, self.stft_sums[r])
         if self.use_mel:                                                      # :536-540
             self.mel.accumulate(y2d, t2d, 1.0 / self.mel.numel(B, T), self.slots[_MEL:])
         outs2, _ = engD.forward(self._disc_input(ar, (y_, y)), save=False)    # :572-587, [fake | real]

@@ -218,7 +218,7 @@ int artic_split(const float* src, void* hi, int64_t plane, int64_t n, void* stre
 /* Host-side counters of which kernel family took each contraction since the last reset (tests assert that every
  * eligible layer runs on the tensor cores): out[0..9] = conv {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic,
  * channel-1 kernels}, wgrad {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic, channel-1 kernels}, tcgen05 weight
- * gradients that also produced the bias gradient, reserved.
+ * gradients that also produced the bias gradient, tcgen05 conv launches with cluster weight multicast.
  * Counted when a launch is ENQUEUED (graph replays do not count).  reset != 0 clears them after the read. */
 int artic_path_counts(int64_t* h_out, int32_t reset);
 
@@ -304,18 +304,6 @@ int artic_stft_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, in
                         int32_t hop, int32_t win_length, const float* window, float eps,
                         const float* sums, float w_sc, float w_mag, float* dx, void* stream);
 
-/* All resolutions of MultiResolutionSTFTLoss (losses/stft_loss.py:146-170) in ONE launch each way.  h_res: HOST array of
- * R <= 8 resolutions (window = device pointer to win_length taps); sums: R x 3 (row r = resolution r, as above);
- * the backward applies the same w_sc / w_mag to every resolution (the loss is their mean: pass g / R). */
-typedef struct {
-  int32_t n_fft, hop, win_length, reserved_;
-  const float* window;
-} artic_stft_res_t;
-int artic_mrstft_loss_fwd(const float* x, const float* y, int32_t B, int32_t T, const artic_stft_res_t* h_res,
-                          int32_t R, float eps, float* sums, void* stream);
-int artic_mrstft_loss_bwd(const float* x, const float* y, int32_t B, int32_t T, const artic_stft_res_t* h_res,
-                          int32_t R, float eps, const float* sums, float w_sc, float w_mag, float* dx, void* stream);
-
 /*
  * MelSpectrogramLoss (losses/mel_loss.py:82-111,151-166): STFT -> sqrt(clamp(power, eps))
  * -> melmat (n_bins x n_mels, row-major fp32) -> clamp(eps) -> log (log_scale = 1 for ln,
@@ -347,7 +335,7 @@ int artic_mel_loss_fwd_bwd(const float* x, const float* y, int32_t B, int32_t T,
  *        (a plain GEMM: artic_tapconv with one tap)
  *   w_hh (2, 3H, H) fp32 = weight_hh_l0, weight_hh_l0_reverse;  b_hh (2, 3H) likewise
  *   out  (N, T, 2H) fp32 = [forward h_t | reverse h_t]
- * All N sequences have T steps; H <= 256.  One persistent cluster kernel: W_hh stays in shared memory for the
+ * All N sequences have T steps; H <= 256, H % 4 == 0.  One persistent cluster kernel: W_hh stays in shared memory for the
  * whole sequence, h is exchanged through distributed shared memory once per step.
  */
 int artic_bigru_layer(const float* gi, const float* w_hh, const float* b_hh, float* out, int32_t N, int32_t T,

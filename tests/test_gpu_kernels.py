@@ -323,6 +323,58 @@ def test_tc_conv_with_unaligned_bias_and_views():
     assert rel_err(Y.t.float().cpu().permute(0, 2, 1), ref) < 2e-2
 
 
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("shape", [(256, 256, 7, 1, 4, 300), (512, 256, 3, 1, 6, 130), (256, 512, 5, 2, 2, 1000),
+                                   (1024, 1024, 5, 1, 8, 53)])
+def test_tc_conv_cluster_weight_multicast(prec, shape):
+    """Deep layers stream their weights through a thread-block cluster (TMA multicast, tapconv_tc.cu Plan.cs): forward
+    and data gradient against torch on the same operands, with the cluster path asserted taken (debug key 22 = 2 turns it
+    on; it is off by default because it does not pay inside the train step) and bit-identical to the plain path."""
+    cin, cout, k, dil, N, L = shape
+    spec = ConvSpec(kind="conv", cin=cin, cout=cout, k=k, dilation=dil, padding=(k - 1) // 2 * dil)
+    code = BF16 if prec == "bf16" else F32
+    torch.manual_seed(cin + k)
+    w = torch.randn(spec.weight_shape(), dtype=torch.float64) / math.sqrt(cin * k)
+    b = torch.randn(cout, dtype=torch.float64) * 0.1
+    x = torch.randn(N, cin, L, dtype=torch.float64)
+    if prec == "bf16":
+        x, w_eff = _bf16_round(x), _bf16_round(w)
+    else:
+        w_eff = w.float().double()
+    x.requires_grad_(True)
+    y = F.conv1d(x, w_eff, b, padding=spec.padding, dilation=dil)
+    dy = torch.randn_like(y)
+    if prec == "bf16":
+        dy = _bf16_round(dy)
+    gx, = torch.autograd.grad(y, [x], dy)
+    lay = ConvLayer(spec, "l", code, code, x3=prec == "bf16x3")
+    lay.bind({"l.weight": w.float().to(DEV).contiguous(), "l.bias": b.float().to(DEV)})
+    lay.prep()
+    td = _lib.TORCH_DTYPE[code]
+    tol = 6e-3 if prec == "bf16" else 5e-5
+    lib = _lib.load()
+    outs = []
+    for off in (0, 1):
+        lib.artic_debug_set(22, 0 if off else 2)
+        try:
+            _lib.path_counts(reset=True)
+            X = SeqT(x.detach().permute(0, 2, 1).contiguous().to(DEV, td), N, L, cin)
+            Y = SeqT.empty(N, L, cout, code, DEV)
+            lay.forward(X, Y=Y)
+            dY = SeqT(dy.permute(0, 2, 1).contiguous().to(DEV, td), N, L, cout)
+            dX = SeqT.empty(N, L, cin, code, DEV)
+            lay.dgrad(dY, dX=dX)
+            torch.cuda.synchronize()
+            pc = _lib.path_counts()
+        finally:
+            lib.artic_debug_set(22, 0)
+        assert pc["conv_tc_cluster"] == (0 if off else 2), pc
+        assert rel_err(Y.t.float().cpu().permute(0, 2, 1), y.detach()) < tol
+        assert rel_err(dX.t.float().cpu().permute(0, 2, 1), gx) < tol
+        outs.append((Y.t.float().cpu(), dX.t.float().cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])     # same MMAs, same order
+
+
 def _bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float64)
 
