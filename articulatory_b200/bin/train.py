@@ -65,6 +65,29 @@ def _load_items(dumpdir, config):
     return items
 
 
+class ScalarWriter(object):
+    """The reference logs every averaged scalar to TensorBoard (``tensorboardX.SummaryWriter(outdir)``, bin/train.py:110,
+    :746-748).  tensorboardX is an optional dependency: when it is not installed the same (tag, value, step) triples go
+    to ``<outdir>/scalars.jsonl``, one JSON object per line."""
+
+    def __init__(self, outdir):
+        self.tb, self.path = None, os.path.join(outdir, "scalars.jsonl")
+        try:
+            from tensorboardX import SummaryWriter
+            self.tb = SummaryWriter(outdir)
+        except ImportError:
+            pass
+
+    def add_scalars(self, values, step):
+        import json
+        if self.tb is not None:
+            for k, v in values.items():
+                self.tb.add_scalar(k, v, step)
+        else:
+            with open(self.path, "a") as f:
+                f.write(json.dumps({"step": int(step), **{k: float(v) for k, v in values.items()}}) + "\n")
+
+
 class Trainer(object):
     """Epoch / step loop, logging and checkpointing around ``TrainStep`` (reference Trainer, bin/train.py:60-780)."""
 
@@ -77,6 +100,46 @@ class Trainer(object):
         self.dev_items = dev_items or []
         self.best_mel_loss = float("inf")
         self.finish_train = False
+        self.writer = ScalarWriter(config["outdir"]) if dp.rank == 0 else None
+
+    @torch.no_grad()
+    def save_intermediate_result(self, batch):
+        """Reference Trainer._generate_and_save_intermediate_result (bin/train.py:651-744): generate the first dev batch
+        with the current generator and write ``predictions/<steps>steps/<idx>_{ref,gen}.wav`` (PCM-16) for the first
+        ``num_save_intermediate_results`` items (+ the reference's two-panel ``<idx>.png`` when matplotlib is there)."""
+        from articulatory_b200.bin.decode import _write_wav
+        n_save = int(self.config.get("num_save_intermediate_results", 4))
+        if n_save <= 0 or self.dp.rank != 0:
+            return
+        self.ts.sync_exchange()
+        G = self.model["generator"]
+        x, y = batch["x"][0].to(self.device), batch["y"]
+        ar = batch["ar"].to(self.device) if "ar" in batch else None
+        y_ = G(x, ar=ar).float().cpu()
+        dirname = os.path.join(self.config["outdir"], f"predictions/{self.steps}steps")
+        os.makedirs(dirname, exist_ok=True)
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+        except ImportError:
+            plt = None
+        for idx, (r, g) in enumerate(zip(y, y_), 1):
+            r, g = r.reshape(-1).numpy(), g.reshape(-1).numpy()
+            if plt is not None:
+                plt.subplot(2, 1, 1)
+                plt.plot(r)
+                plt.title("groundtruth speech")
+                plt.subplot(2, 1, 2)
+                plt.plot(g)
+                plt.title(f"generated speech @ {self.steps} steps")
+                plt.tight_layout()
+                plt.savefig(os.path.join(dirname, f"{idx}.png"))
+                plt.close()
+            _write_wav(os.path.join(dirname, f"{idx}_ref.wav"), r, self.config["sampling_rate"])
+            _write_wav(os.path.join(dirname, f"{idx}_gen.wav"), g, self.config["sampling_rate"])
+            if idx >= n_save:
+                break
 
     def eval_epoch(self):
         """Reference Trainer._eval_epoch (bin/train.py:605-648): average the eval losses over the dev set, keep the
@@ -89,6 +152,8 @@ class Trainer(object):
                 continue
             self.ts.eval_step(batch["x"][0], batch["y"], batch.get("ar"))
             n += 1
+            if n == 1:                                                     # reference :617-618
+                self.save_intermediate_result(batch)
         if n == 0:
             return {}
         logs = self.ts.read_eval_logs(n)
@@ -96,6 +161,7 @@ class Trainer(object):
             logging.info(f"(Steps: {self.steps}) Finished evaluation ({n} steps per epoch).")
             for k, v in logs.items():
                 logging.info(f"(Steps: {self.steps}) {k} = {v:.4f}.")
+            self.writer.add_scalars(logs, self.steps)                      # reference :640
             if logs["eval/mel_loss"] < self.best_mel_loss:
                 with open(os.path.join(self.config["outdir"], "best_mel_step.txt"), "w+") as ouf:
                     ouf.write("%d\n" % self.steps)
@@ -149,6 +215,7 @@ class Trainer(object):
                     if self.dp.rank == 0:
                         for k, v in zip(LOG_KEYS, vals):
                             logging.info(f"(Steps: {self.steps}) {k} = {v / n:.4f}.")
+                        self.writer.add_scalars({k: v / n for k, v in zip(LOG_KEYS, vals)}, self.steps)   # reference :763-773
                 if self.dev_items and self.steps % self.config.get("eval_interval_steps", 1000) == 0:
                     self.eval_epoch()                                          # reference :766-768
                 if self.steps % self.config["save_interval_steps"] == 0 and self.dp.rank == 0:
@@ -175,6 +242,9 @@ def main(argv=None):
     parser.add_argument("--verbose", type=int, default=1)
     parser.add_argument("--rank", "--local_rank", default=0, type=int)
     parser.add_argument("--synthetic", type=int, default=0, help="train on N synthetic utterances (B200 extension)")
+    parser.add_argument("--max-steps", type=int, default=0,
+                        help="stop after this many steps instead of the yaml's train_max_steps (B200 extension: smoke runs "
+                             "of an unchanged recipe yaml)")
     parser.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
                         help="bf16x3 (default): fp32 storage, error-compensated split-bf16 tcgen05 contraction — the mode "
                              "that meets the 1e-3 parity gate against the fp32 reference; bf16: bf16 storage, plain "
@@ -196,6 +266,8 @@ def main(argv=None):
     with open(args.config) as f:
         config = yaml.load(f, Loader=yaml.Loader)
     config.update(vars(args))
+    if args.max_steps > 0:
+        config["train_max_steps"] = args.max_steps
     config["version"] = articulatory_b200.__version__
     if dp.rank == 0:
         with open(os.path.join(args.outdir, "config.yml"), "w") as f:
@@ -241,6 +313,8 @@ def main(argv=None):
         trainer.load_checkpoint(args.resume)
     try:
         trainer.run()
+        if args.max_steps > 0 and dev_items and trainer.steps % config.get("eval_interval_steps", 1000) != 0:
+            trainer.eval_epoch()          # a shortened run still ends with one evaluation pass (+ intermediate results)
     finally:
         if dp.rank == 0:
             trainer.save_checkpoint(os.path.join(config["outdir"], f"checkpoint-{trainer.steps}steps.pkl"))

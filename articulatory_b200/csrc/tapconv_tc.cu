@@ -252,6 +252,10 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
           const CUtensorMap* mx = (X3 && kc % 3 == 2) ? &map_x_lo : &map_x;
           const CUtensorMap* mw = (X3 && kc % 3 == 1) ? &map_w_lo : &map_w;
           const int c0 = g * p.Cig + kcl * pl.kch;
+          // bf16x3: pass 1 (x_hi, w_lo) re-uses the x_hi tile staged for pass 0 — no second load, the stage is
+          // released after pass 1
+          const bool a_reuse = X3 && kc % 3 == 1;
+          if (!a_reuse) {
           mbar_wait(&a_empty[as.stage], as.phase ^ 1);
           const uint32_t a_dst = a_base + (uint32_t)as.stage * pl.a_stage_bytes;
           if (!pl.packed) {
@@ -276,6 +280,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
             }
           }
           as.next();
+          }
           if (pl.w_resident) continue;
           for (int t0 = 0; t0 < ntaps; t0 += pl.tps) {
             if (w_pre > 0) { --w_pre; continue; }
@@ -330,7 +335,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
         uint32_t accum = 0;
         bool first_tap = true;
         for (int kc = 0; kc < pl.n_kc; ++kc) {
-          mbar_wait(&a_full[as.stage], as.phase);
+          if (!(X3 && kc % 3 == 1)) mbar_wait(&a_full[as.stage], as.phase);     // bf16x3 pass 1: same x_hi stage as pass 0
           if (lane == 0) dbg_mark(pl.dbg, 20);
           const uint32_t a16 = desc_lo | (((a_base + (uint32_t)as.stage * pl.a_stage_bytes) >> 4) & 0x3fffu);
           for (int t0 = 0; t0 < ntaps; t0 += tps) {
@@ -386,8 +391,10 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
               ws.next();
             }
           }
-          if (leader) umma_commit(&a_empty[as.stage]);
-          as.next();
+          if (!(X3 && kc % 3 == 0)) {       // bf16x3: the x_hi stage stays for pass 1
+            if (leader) umma_commit(&a_empty[as.stage]);
+            as.next();
+          }
         }
         if (leader) umma_commit(&acc_full[acc.stage]);
         if (lane == 0) dbg_mark(pl.dbg, 22);
@@ -876,7 +883,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
       const double epi_clk = cand.mt * ((bn + 63) / 64) * 700.0;
       // operand streaming: bytes per tile over min(bytes in flight / ~3000-clock TMA latency, fair share of L2)
       const double w_tile = cand.w_resident ? 0.0 : (double)cand.n_kc * p.ntaps * bn * cand.row_bytes / cand.cs;
-      const double tile_bytes = (double)cand.n_kc * cand.a_stage_bytes + w_tile;
+      const double tile_bytes = (double)(x3 ? 2 * cand.n_kcl : cand.n_kc) * cand.a_stage_bytes + w_tile;
       const double inflight = (double)cand.n_as * cand.a_stage_bytes + (cand.w_resident ? 0.0 : (double)cand.n_ws * cand.w_stage_bytes);
       // every SM is busy with some stream's CTA: the L2 share of a CTA is 1 / #SMs (debug key 17 = 1: of this launch only)
       const double active = (n_share > 1 || tc::g_debug[17] != 1) ? num_sms() : cand.total_tiles < num_sms() ? cand.total_tiles : num_sms();

@@ -77,33 +77,55 @@ class BatchedARDecoder:
     @torch.no_grad()
     def decode(self, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         """feats: list of (T'_i, C) tensors (host or device).  Returns a list of (T'_i * hop,) waveforms,
-        each identical to the reference ``ar_loop`` run on that utterance alone."""
-        feats = [f.to(self.dev, dtype=torch.float32) for f in feats]
+        each identical to the reference ``ar_loop`` run on that utterance alone.
+
+        Host-side work per chunk is two strided copies around the graph replay: the features live in ONE padded
+        (B, C, T'max) device tensor, the waveforms in ONE (B, T'max * hop) buffer, and while every utterance is still
+        running (the common case: equal lengths) the AR context never leaves the graph's static buffer."""
+        B = len(feats)
         C = feats[0].shape[1]
-        outs = [torch.empty(len(f) * self.hop, dtype=torch.float32, device=self.dev) for f in feats]
-        max_frames = max(len(f) for f in feats)
-        prev = torch.zeros((len(feats), 1, self.past), dtype=torch.float32, device=self.dev)   # decode.py:59
+        lens = [len(f) for f in feats]
+        max_frames = max(lens)
+        # one H2D copy per utterance, straight into the padded channel-first layout
+        fpad = torch.zeros((B, C, max_frames), dtype=torch.float32, device=self.dev)
+        for i, f in enumerate(feats):
+            fpad[i, :, :lens[i]].copy_(f.to(self.dev, dtype=torch.float32, non_blocking=True).t())
+        obuf = torch.empty((B, max_frames * self.hop), dtype=torch.float32, device=self.dev)
+        prev = torch.zeros((B, 1, self.past), dtype=torch.float32, device=self.dev)   # decode.py:59
         F = self.chunk_frames
+        in_graph = None         # (graph tuple) whose static AR buffer currently holds `prev` for ALL utterances
         for lo in range(0, max_frames, F):
             # group the utterances still running by the length of their chunk at this index
             groups = {}
-            for i, f in enumerate(feats):
-                n = min(len(f) - lo, F)
+            for i, n_i in enumerate(lens):
+                n = min(n_i - lo, F)
                 if n > 0:
                     groups.setdefault(n, []).append(i)
             for n, idx in groups.items():
-                cin = torch.stack([feats[i][lo:lo + n] for i in idx]).permute(0, 2, 1).contiguous()   # (b, C, n)
-                sel = torch.tensor(idx, device=self.dev)
-                pv = prev.index_select(0, sel)
+                whole = len(idx) == B
                 if self.use_graph:
-                    graph, s_cin, s_prev, s_out = self._graph_for(len(idx), C, n)
-                    s_cin.copy_(cin)
-                    s_prev.copy_(pv)
+                    g = self._graph_for(len(idx), C, n)
+                    graph, s_cin, s_prev, s_out = g
+                    if whole:
+                        s_cin.copy_(fpad[:, :, lo:lo + n])
+                        if in_graph is not g:
+                            s_prev.copy_(prev if in_graph is None else in_graph[2])
+                        graph.replay()
+                        in_graph = g
+                        obuf[:, lo * self.hop:(lo + n) * self.hop].copy_(s_out[:, 0])
+                        continue
+                    if in_graph is not None:            # leave the all-utterances fast path: materialise the context
+                        prev.copy_(in_graph[2])
+                        in_graph = None
+                    sel = torch.tensor(idx, device=self.dev)
+                    s_cin.copy_(fpad.index_select(0, sel)[:, :, lo:lo + n])
+                    s_prev.copy_(prev.index_select(0, sel))
                     graph.replay()
                     cout, new_prev = s_out, s_prev
                 else:
-                    cout, new_prev = self._step_eager(cin, pv)
+                    sel = torch.tensor(idx, device=self.dev)
+                    cout, new_prev = self._step_eager(fpad.index_select(0, sel)[:, :, lo:lo + n].contiguous(),
+                                                      prev.index_select(0, sel))
                 prev.index_copy_(0, sel, new_prev)
-                for j, i in enumerate(idx):
-                    outs[i][lo * self.hop:(lo + n) * self.hop] = cout[j, 0]
-        return outs
+                obuf[:, lo * self.hop:(lo + n) * self.hop].index_copy_(0, sel, cout[:, 0])
+        return [obuf[i, :lens[i] * self.hop] for i in range(B)]

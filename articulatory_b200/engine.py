@@ -560,6 +560,7 @@ def planner_objective(sm_time_pct: int):
 
 
 _G_OBJECTIVE = int(_os.environ.get("ARTIC_G_OBJECTIVE", "60"))   # measured: 100 -> 12.93, 60 -> 12.82, 30 -> 13.15 ms
+_D_OBJECTIVE = int(_os.environ.get("ARTIC_D_OBJECTIVE", "100"))  # the discriminator's eight chains: see profiles/r2_objective_sweep.log
 
 
 class GeneratorEngine:
@@ -967,6 +968,10 @@ class DiscriminatorEngine:
 
     # ---- forward -------------------------------------------------------------
     def forward(self, x: torch.Tensor, save=True, into=None, lo=0):
+        with planner_objective(_D_OBJECTIVE):
+            return self._forward(x, save, into, lo)
+
+    def _forward(self, x: torch.Tensor, save=True, into=None, lo=0):
         """x (B, 1, T) fp32 -> (list of 8 lists of SeqT [feature maps..., logits], tape).
 
         ``into`` (a tape of an earlier forward over a batch of >= lo + B items) makes this call
@@ -1061,6 +1066,10 @@ class DiscriminatorEngine:
 
     # ---- backward ------------------------------------------------------------
     def backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True, pre_zeroed=False):
+        with planner_objective(_D_OBJECTIVE):
+            return self._backward(tape, douts, grads, need_dx, pre_zeroed)
+
+    def _backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True, pre_zeroed=False):
         """douts: per chain a list (same length as the chain's outputs) of SeqT gradients or
         None; the gradient wrt the logits must be present.  Accumulates parameter gradients
         into ``grads`` when given (None = skip every wgrad, as in the generator phase) and
