@@ -98,6 +98,7 @@ SIGNATURES = {
     "artic_sum3": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p]),
     "artic_tanh_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "artic_cast": (C.c_int, [_p, _i32, _p, _i32, _i64, _p]),
+    "artic_cut_windows": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "artic_split": (C.c_int, [_p, _p, _i64, _i64, _p]),
     "artic_path_counts": (C.c_int, [C.POINTER(C.c_int64), _i32]),
     "artic_concat_time": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i64, _i32, _p]),

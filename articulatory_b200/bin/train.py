@@ -25,7 +25,7 @@ import yaml
 
 import articulatory_b200
 import articulatory_b200.models
-from articulatory_b200.data import BatchPrefetcher, SpeechCollater, synthetic_utterances
+from articulatory_b200.data import BatchPrefetcher, DeviceWindowCutter, SpeechCollater, synthetic_utterances
 from articulatory_b200.parallel import DataParallel
 from articulatory_b200.trainer import LOG_KEYS, TrainStep
 
@@ -92,8 +92,11 @@ class Trainer(object):
     """Epoch / step loop, logging and checkpointing around ``TrainStep`` (reference Trainer, bin/train.py:60-780)."""
 
     def __init__(self, steps, epochs, items, collater, model, step_fn, config, dp, device, dev_items=None,
-                 dev_collater=None):
+                 dev_collater=None, device_data=True):
         self.steps, self.epochs = steps, epochs
+        # the training set lives in HBM and windows are cut by a kernel (data.DeviceWindowCutter); device_data=False
+        # keeps the host path: numpy slicing + pinning on a prefetch thread
+        self.cutter = DeviceWindowCutter(items, collater, device) if device_data else None
         self.items, self.collater, self.model, self.ts = items, collater, model, step_fn
         self.dev_collater = dev_collater or collater
         self.config, self.dp, self.device = config, dp, device
@@ -199,9 +202,11 @@ class Trainer(object):
             if not groups:
                 raise ValueError(f"{len(idx)} training utterances on this rank cannot fill one batch of {bs}")
             stepped = False
-            # window cutting + pinning of the next two batches run on a host thread under the current step
-            for batch in BatchPrefetcher(lambda g: self.collater([self.items[i] for i in g]), groups, depth=2,
-                                         device=self.device):
+            # device path: one index upload + one gather launch per batch; host path: window cutting + pinning of the
+            # next two batches on a host thread under the current step
+            batches = (self.cutter(g) for g in groups) if self.cutter is not None else \
+                BatchPrefetcher(lambda g: self.collater([self.items[i] for i in g]), groups, depth=2, device=self.device)
+            for batch in batches:
                 if batch["y"].shape[0] != bs:
                     continue          # an utterance shorter than the window was dropped: keep shapes static
                 stepped = True
@@ -242,6 +247,9 @@ def main(argv=None):
     parser.add_argument("--verbose", type=int, default=1)
     parser.add_argument("--rank", "--local_rank", default=0, type=int)
     parser.add_argument("--synthetic", type=int, default=0, help="train on N synthetic utterances (B200 extension)")
+    parser.add_argument("--host-data", action="store_true",
+                        help="cut the training windows on the host (numpy + pinned prefetch thread) instead of on the device "
+                             "from a dataset resident in HBM (B200 extension)")
     parser.add_argument("--max-steps", type=int, default=0,
                         help="stop after this many steps instead of the yaml's train_max_steps (B200 extension: smoke runs "
                              "of an unchanged recipe yaml)")
@@ -306,7 +314,8 @@ def main(argv=None):
                                   aux_context_window=config["generator_params"].get("aux_context_window", 0),
                                   dataset_mode=config.get("dataset_mode", "a2w"), config=config,
                                   rng=np.random.RandomState(777 + dp.rank))   # own stream: the prefetch thread owns np.random
-    trainer = Trainer(0, 0, items, collater, model, ts, config, dp, device, dev_items=dev_items, dev_collater=dev_collater)
+    trainer = Trainer(0, 0, items, collater, model, ts, config, dp, device, dev_items=dev_items, dev_collater=dev_collater,
+                      device_data=not args.host_data)
     if args.pretrain:
         trainer.load_checkpoint(args.pretrain, load_only_params=True)
     if args.resume:

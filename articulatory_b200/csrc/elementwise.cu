@@ -84,6 +84,36 @@ __global__ void split1_kernel(const float* __restrict__ s, __nv_bfloat16* __rest
   }
 }
 
+// Training windows cut on the device from a dataset that lives in HBM (SpeechCollater's index plan, bin/train.py:1009-1027,
+// 1082-1097, bit for bit): one thread per output element of x | y | ar.
+__global__ void cut_windows_kernel(const float* __restrict__ audio, const int64_t* __restrict__ aoff,
+                                   const float* __restrict__ art, const int64_t* __restrict__ toff,
+                                   const int32_t* __restrict__ pick, int B, int C, int frames, int aux, int hop, int ar_len,
+                                   float* __restrict__ x, float* __restrict__ y, float* __restrict__ ar) {
+  const int fx = frames + 2 * aux, T = frames * hop;
+  const int64_t nx = (int64_t)B * C * fx, ny = (int64_t)B * T, na = (int64_t)B * ar_len;
+  GRID_STRIDE(i, nx + ny + na) {
+    if (i < nx) {
+      const int t = (int)(i % fx);
+      const int c = (int)((i / fx) % C);
+      const int b = (int)(i / ((int64_t)fx * C));
+      const int u = pick[2 * b], start = pick[2 * b + 1];
+      x[i] = __ldg(art + toff[u] + (int64_t)(start - aux + t) * C + c);
+    } else if (i < nx + ny) {
+      const int64_t j = i - nx;
+      const int b = (int)(j / T);
+      const int u = pick[2 * b], start = pick[2 * b + 1];
+      y[j] = __ldg(audio + aoff[u] + (int64_t)start * hop + (j % T));
+    } else {
+      const int64_t j = i - nx - ny;
+      const int b = (int)(j / ar_len);
+      const int u = pick[2 * b], start = pick[2 * b + 1];
+      const int64_t src = (int64_t)start * hop - ar_len + (j % ar_len);      // left zero padding where the past runs out
+      ar[j] = src >= 0 ? __ldg(audio + aoff[u] + src) : 0.f;
+    }
+  }
+}
+
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
   GRID_STRIDE(i, n) { st_f(d + i, ld_f(s + i)); }
@@ -334,6 +364,19 @@ extern "C" int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64
   if (n == 0) return ARTIC_OK;
   DISPATCH(dtype, (tanh_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(dy, y, (float*)dpre, n)),
            (tanh_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(dy, y, (bf16*)dpre, n)));
+}
+
+extern "C" int artic_cut_windows(const float* audio, const int64_t* audio_off, const float* art, const int64_t* art_off,
+                                 const int32_t* pick, int32_t B, int32_t C, int32_t frames, int32_t aux, int32_t hop,
+                                 int32_t ar_len, float* x, float* y, float* ar, void* stream) {
+  ARTIC_CHECK_ARG(audio && audio_off && art && art_off && pick && x && y && (ar || ar_len == 0), "null pointer");
+  ARTIC_CHECK_ARG(B >= 0 && C >= 1 && frames >= 1 && aux >= 0 && hop >= 1 && ar_len >= 0, "bad dims");
+  const int64_t n = (int64_t)B * ((int64_t)C * (frames + 2 * aux) + (int64_t)frames * hop + ar_len);
+  if (n == 0) return ARTIC_OK;
+  cut_windows_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(audio, audio_off, art, art_off, pick, B, C, frames, aux, hop, ar_len,
+                                                         x, y, ar);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
 }
 
 extern "C" int artic_split(const float* src, void* hi, int64_t plane, int64_t n, void* stream) {

@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -33,6 +34,19 @@ constexpr int GRU_UNITS = 64;      // hidden units per CTA
 constexpr int GRU_THREADS = 256;   // 8 warps = (unit half of 32 lanes) x (quarter of the k range)
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// Remote shared-memory store that signals the destination CTA's mbarrier when it lands (no fence, no cluster barrier:
+// `cluster.sync` has release semantics over ALL earlier memory operations, so every step waited for its global output
+// stores to be acknowledged — 18 % of the kernel's stall samples, profiles/r2_ncu_gru_*).
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "r"(remote_bar) : "memory");
+}
 
 // Thread (unit u, k quarter kq) accumulates ALL 8 items x 3 gates over its quarter of k — every weight is read from
 // shared memory once per step per CTA (3 conflict-free 128-byte wavefronts + 2 broadcast reads of h per 24 FMAs) —
@@ -48,8 +62,9 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
   const int dir = cid / n_groups;                        // 0 forward, 1 reverse
   const int n0 = (cid % n_groups) * GRU_ITEMS;
 
+  __shared__ __align__(8) uint64_t hbar[2];             // "h buffer b is complete" (transaction barriers)
   extern __shared__ __align__(16) float smem[];
-  float* Wt = smem;                                      // [3 gates][H k][64 units]
+  float* Wt = smem;                                      // [H k][3 gates][64 units]
   float* hbuf = Wt + 3 * H * GRU_UNITS;                  // [2][H k][8 items]
   float* red = hbuf + 2 * H * GRU_ITEMS;                 // [4 dest kq][3 sources][6 = gate x item][64 units]
 
@@ -63,9 +78,15 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
   const float* Wd = w_hh + (size_t)dir * 3 * H * H;
   for (int i = tid; i < 3 * GRU_UNITS * H; i += GRU_THREADS) {
     const int k = i % H, u = (i / H) % GRU_UNITS, g = i / (H * GRU_UNITS);
-    Wt[(g * H + k) * GRU_UNITS + u] = (rank * GRU_UNITS + u < H) ? __ldg(Wd + ((size_t)g * H + rank * GRU_UNITS + u) * H + k) : 0.f;
+    Wt[(k * 3 + g) * GRU_UNITS + u] = (rank * GRU_UNITS + u < H) ? __ldg(Wd + ((size_t)g * H + rank * GRU_UNITS + u) * H + k) : 0.f;
   }
   for (int i = tid; i < 2 * H * GRU_ITEMS; i += GRU_THREADS) hbuf[i] = 0.f;
+  if (tid == 0) {
+    tc::mbar_init(&hbar[0], 1);
+    tc::mbar_init(&hbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t h_bytes = (uint32_t)H * GRU_ITEMS * sizeof(float);     // one complete h: every live unit x 8 items
   float bh[3] = {0.f, 0.f, 0.f};
   if (live) {
 #pragma unroll
@@ -91,30 +112,42 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
     const int t = dir ? T - 1 - s : s;
     const float* hc = hbuf + (size_t)(s & 1) * H * GRU_ITEMS;          // h_t (complete, all units)
     float* hn_local = hbuf + (size_t)((s + 1) & 1) * H * GRU_ITEMS;    // h_{t+1} (being assembled)
+    // arm the barrier of the buffer that fills during this step, then wait for h_t (filled during step s - 1: the
+    // ((s - 1) / 2)-th fill of buffer s & 1).  A peer can run at most one step ahead (it needs OUR h_{t+1} to go further),
+    // so its writes into hn_local never overtake our reads of that buffer from step s - 1.
+    if (tid == 0) tc::mbar_expect_tx(&hbar[(s + 1) & 1], h_bytes);
+    if (s > 0) tc::mbar_wait(&hbar[s & 1], (uint32_t)(((s - 1) >> 1) & 1));
     float gcur[3][2];
 #pragma unroll
     for (int g = 0; g < 3; ++g) { gcur[g][0] = gin[g][0]; gcur[g][1] = gin[g][1]; }
     if (s + 1 < T) fetch(dir ? t - 1 : t + 1);
+    // packed fp32 FMAs (fma.rn.f32x2: two items per instruction) — the loop is FMA-issue bound
+    float2 acc2[3][4];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc2[g][i] = make_float2(0.f, 0.f);
+    const float* wp = Wt + (size_t)kb * 3 * GRU_UNITS + ul;
+    const float* hp = hc + (size_t)kb * GRU_ITEMS;
+#pragma unroll 4
+    for (int k = kb; k < ke; ++k, wp += 3 * GRU_UNITS, hp += GRU_ITEMS) {
+      const float4 ha = *reinterpret_cast<const float4*>(hp);          // warp-wide broadcasts
+      const float4 hb = *reinterpret_cast<const float4*>(hp + 4);
+      const float2 h2[4] = {make_float2(ha.x, ha.y), make_float2(ha.z, ha.w), make_float2(hb.x, hb.y), make_float2(hb.z, hb.w)};
+      const float w0 = wp[0], w1 = wp[GRU_UNITS], w2 = wp[2 * GRU_UNITS];
+      const float2 w0p = make_float2(w0, w0), w1p = make_float2(w1, w1), w2p = make_float2(w2, w2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc2[0][i] = __ffma2_rn(w0p, h2[i], acc2[0][i]);
+        acc2[1][i] = __ffma2_rn(w1p, h2[i], acc2[1][i]);
+        acc2[2][i] = __ffma2_rn(w2p, h2[i], acc2[2][i]);
+      }
+    }
     float acc[3][8];
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
-#pragma unroll 4
-    for (int k = kb; k < ke; ++k) {
-      const float4 ha = *reinterpret_cast<const float4*>(hc + k * GRU_ITEMS);        // warp-wide broadcasts
-      const float4 hb = *reinterpret_cast<const float4*>(hc + k * GRU_ITEMS + 4);
-      const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-      const float w0 = Wt[(0 * H + k) * GRU_UNITS + ul];
-      const float w1 = Wt[(1 * H + k) * GRU_UNITS + ul];
-      const float w2 = Wt[(2 * H + k) * GRU_UNITS + ul];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[0][i] = fmaf(w0, hv[i], acc[0][i]);
-        acc[1][i] = fmaf(w1, hv[i], acc[1][i]);
-        acc[2][i] = fmaf(w2, hv[i], acc[2][i]);
-      }
-    }
+      for (int i = 0; i < 4; ++i) { acc[g][2 * i] = acc2[g][i].x; acc[g][2 * i + 1] = acc2[g][i].y; }
     // hand the partial sums of the items finished by the other three k quarters to them
     float own[3][2];
 #pragma unroll
@@ -158,15 +191,16 @@ bigru_layer_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
         const int n = na + j;
         if (n < N) out[((size_t)n * T + t) * (2 * H) + dir * H + unit] = hv2[j];
       }
-      // publish this unit's two items of h_{t+1} to every CTA of the cluster (distributed shared memory)
-      float* dst_local = hn_local + unit * GRU_ITEMS + 2 * kq;
-      for (int pr = 0; pr < csize; ++pr) {
-        float* dst = cluster.map_shared_rank(dst_local, pr);
-        *reinterpret_cast<float2*>(dst) = make_float2(hv2[0], hv2[1]);
-      }
+      // publish this unit's two items of h_{t+1} to every CTA of the cluster (distributed shared memory); each store
+      // counts its 8 bytes on the destination CTA's barrier
+      const uint32_t dst_local = tc::smem_u32(hn_local + unit * GRU_ITEMS + 2 * kq);
+      const uint32_t bar_local = tc::smem_u32(&hbar[(s + 1) & 1]);
+      for (int pr = 0; pr < csize; ++pr)
+        st_async_f2(map_to_rank(dst_local, (uint32_t)pr), hv2[0], hv2[1], map_to_rank(bar_local, (uint32_t)pr));
     }
-    cluster.sync();     // h_{t+1} complete everywhere; also orders the reads of h_t / red before their next overwrite
+    __syncthreads();    // `red` and this CTA's reads of h_t are done before the next step overwrites them
   }
+  cluster.sync();       // no CTA exits while a peer may still write into its shared memory
 }
 
 }  // namespace artic

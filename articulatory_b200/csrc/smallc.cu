@@ -203,7 +203,7 @@ template <typename T, int NT>
 __global__ void __launch_bounds__(256) tapconv_ci1_kernel(const __grid_constant__ artic_tapconv_t p, int min_off, int span) {
   __shared__ float xs[CI1_XS];
   __shared__ __align__(16) float wsm[CI1_WS];
-  __shared__ __align__(16) float bsm[256];
+  __shared__ __align__(16) float bsm[2048];       // Cog <= 8 * 256
   const int tpr = p.Cog >> 3, rpp = 256 / tpr;
   const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
   const int n = blockIdx.y;
@@ -238,8 +238,10 @@ __global__ void __launch_bounds__(256) tapconv_ci1_kernel(const __grid_constant_
   __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(p.Y);
   __nv_bfloat16* __restrict__ Y2 = reinterpret_cast<__nv_bfloat16*>(p.Y2);
   const int64_t ybase = seq_base(p.y, n);
+  const __nv_bfloat16* __restrict__ res_pre = reinterpret_cast<const __nv_bfloat16*>(p.res_pre);
+  const __nv_bfloat16* __restrict__ mask = reinterpret_cast<const __nv_bfloat16*>(p.mask);
   for (int q = qa + rl; q < qb; q += rpp) {
-    const int row = p.q0 + q;                       // so == 1, ro == 0
+    const int row = p.q0 + q + p.ro;                // so == 1
     if (row < 0 || row >= p.y.len) continue;
     float acc[8];
 #pragma unroll
@@ -266,9 +268,22 @@ __global__ void __launch_bounds__(256) tapconv_ci1_kernel(const __grid_constant_
       }
     }
     uint32_t o1[4], o2[4];
+    const int64_t o = ybase + (int64_t)row * p.y.s_row + cg * 8;
+    // data gradient of a 1-channel logit conv: + upstream feature-matching gradient, x LeakyReLU' of the saved activation
+    float rp[8], mk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { rp[i] = 0.f; mk[i] = 1.f; }
+    if (res_pre != nullptr) tc::unpack8<__nv_bfloat16>(__ldg(reinterpret_cast<const uint4*>(res_pre + o)), rp);
+    if (mask != nullptr) {
+      float m[8];
+      tc::unpack8<__nv_bfloat16>(__ldg(reinterpret_cast<const uint4*>(mask + o)), m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mk[i] = m[i] > 0.f ? 1.f : p.mask_slope;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float a = p.alpha * acc[2 * i] + bias8[2 * i], b = p.alpha * acc[2 * i + 1] + bias8[2 * i + 1];
+      float a = (p.alpha * acc[2 * i] + bias8[2 * i] + rp[2 * i]) * mk[2 * i];
+      float b = (p.alpha * acc[2 * i + 1] + bias8[2 * i + 1] + rp[2 * i + 1]) * mk[2 * i + 1];
       __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
       o1[i] = *reinterpret_cast<uint32_t*>(&h);
       if (p.act == ARTIC_ACT_LRELU) { a = a > 0.f ? a : p.act_slope * a; b = b > 0.f ? b : p.act_slope * b; }
@@ -276,7 +291,6 @@ __global__ void __launch_bounds__(256) tapconv_ci1_kernel(const __grid_constant_
       h = __floats2bfloat162_rn(a, b);
       o2[i] = *reinterpret_cast<uint32_t*>(&h);
     }
-    const int64_t o = ybase + (int64_t)row * p.y.s_row + cg * 8;
     if (Y) *reinterpret_cast<uint4*>(Y + o) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
     if (Y2) *reinterpret_cast<uint4*>(Y2 + o) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
   }
@@ -506,7 +520,8 @@ using namespace artic;
 int artic_tapconv_ci1_try(const artic_tapconv_t* pp, cudaStream_t st) {
   const artic_tapconv_t& p = *pp;
   if (p.Cig != 1 || p.G != 1 || p.dtype != ARTIC_F32 || p.out_dtype != ARTIC_BF16) return 0;
-  if (p.so != 1 || p.ro != 0 || p.res_pre || p.mask || p.res || p.res2 || p.N > 65535) return 0;
+  if (p.so != 1 || p.res || p.res2 || p.N > 65535) return 0;
+  if ((p.res_pre && (reinterpret_cast<uintptr_t>(p.res_pre) & 15)) || (p.mask && (reinterpret_cast<uintptr_t>(p.mask) & 15))) return 0;
   const int tpr = p.Cog / 8;
   if (p.Cog % 8 != 0 || tpr < 1 || tpr > 256 || 256 % tpr != 0 || p.ntaps * p.Cog > CI1_WS) return 0;
   if ((p.y.s_row % 8) || (p.y.s_outer % 8) || (p.y.n_inner > 1 && (p.y.s_inner % 8))) return 0;

@@ -89,6 +89,57 @@ class SpeechCollater(object):
         return out
 
 
+class DeviceWindowCutter(object):
+    """The dataset lives in HBM; a batch is cut ON THE DEVICE (reference data path: datasets/audio_mel_dataset.py:305-531
+    feeding SpeechCollater, bin/train.py:965-1098).
+
+    All utterances are uploaded once — MNGU0 is ~230 MB of fp32 audio + ~40 MB of features against 180 GB of HBM3e — and
+    every step costs one 8-byte-per-item index upload and one gather launch (``artic_cut_windows``) instead of numpy
+    slicing, a 628 KB host-to-device copy and a pinning thread.  The window starts are drawn on the host by the
+    collater's own RNG calls, in the collater's order, so a seeded run cuts EXACTLY the collater's windows
+    (``tests/test_gpu_plugins.py::test_device_window_cutter_matches_collater``)."""
+
+    def __init__(self, items, collater, device):
+        from ._lib import require_cuda
+        self.c, self.dev = collater, torch.device(device)
+        hop = collater.hop_size
+        self.art_len = [min(len(d["art"]), int(len(d["audio"]) / hop)) for d in items]            # bin/train.py:983
+        self.keep = [n + collater.end_offset > collater.start_offset for n in self.art_len]       # :984
+        audio = [np.asarray(d["audio"], dtype=np.float32).reshape(-1) for d in items]
+        art = [np.asarray(d["art"], dtype=np.float32)[:n] for d, n in zip(items, self.art_len)]
+        self.C = art[0].shape[1]
+        a_off = np.cumsum([0] + [len(a) for a in audio])[:-1]
+        t_off = np.cumsum([0] + [a.size for a in art])[:-1]
+        self.audio = torch.from_numpy(np.concatenate(audio)).to(self.dev)
+        self.art = torch.from_numpy(np.concatenate([a.reshape(-1) for a in art])).to(self.dev)
+        self.a_off = torch.from_numpy(a_off.astype(np.int64)).to(self.dev)
+        self.t_off = torch.from_numpy(t_off.astype(np.int64)).to(self.dev)
+        require_cuda(self.audio, "dataset")
+
+    def picks(self, indices):
+        """[(utterance, start frame)] of a batch: one ``rng.randint`` per kept item, in order (bin/train.py:1013)."""
+        c = self.c
+        return [(i, int(c.rng.randint(c.start_offset, self.art_len[i] + c.end_offset))) for i in indices if self.keep[i]]
+
+    def __call__(self, indices):
+        """Device batch {'x': ((B, C, T'),), 'y': (B, 1, T), ['ar': (B, 1, ar_len)]} of the utterances ``indices``."""
+        from ._lib import call, ptr
+        c = self.c
+        pk = self.picks(indices)
+        B, aux, frames = len(pk), c.aux_context_window, c.batch_max_frames
+        pick = torch.tensor(pk, dtype=torch.int32).reshape(B, 2).pin_memory().to(self.dev, non_blocking=True)
+        x = torch.empty((B, self.C, frames + 2 * aux), dtype=torch.float32, device=self.dev)
+        y = torch.empty((B, 1, c.batch_max_steps), dtype=torch.float32, device=self.dev)
+        ar_len = c.ar_len if c.use_ar else 0
+        ar = torch.empty((B, 1, ar_len), dtype=torch.float32, device=self.dev) if c.use_ar else None
+        call("artic_cut_windows", ptr(self.audio), ptr(self.a_off), ptr(self.art), ptr(self.t_off), ptr(pick), B, self.C,
+             frames, aux, c.hop_size, ar_len, ptr(x), ptr(y), ptr(ar))
+        out = {"art": x, "audio": y, "x": (x,), "y": y}
+        if c.use_ar:
+            out["ar"] = ar
+        return out
+
+
 class BatchPrefetcher(object):
     """Assemble (and pin) the next batches on ONE host thread while the GPU runs the current step.
 

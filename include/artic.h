@@ -225,6 +225,18 @@ int artic_path_counts(int64_t* h_out, int32_t reset);
 /* dtype conversion helpers (n elements). */
 int artic_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
 
+/* Training windows cut ON THE DEVICE from a dataset resident in HBM (SpeechCollater.__call__, bin/train.py:965-1098,
+ * random_window branch :1009-1027 and AR slice :1082-1097; same integer indexing, bit exact):
+ *   audio      all utterances' samples back to back (fp32), audio_off[u] = first sample of utterance u
+ *   art        all utterances' features back to back, (T'_u, C) row-major each, art_off[u] = first element
+ *   pick       B x 2 int32 (device): (utterance, start frame) per batch item, drawn by the host with the collater's RNG
+ *   x (B, C, frames + 2*aux)   = art[start-aux : start+frames+aux].T
+ *   y (B, frames*hop)          = audio[start*hop : start*hop + frames*hop]
+ *   ar (B, ar_len) (optional)  = audio[start*hop - ar_len : start*hop], zero where the index is negative */
+int artic_cut_windows(const float* audio, const int64_t* audio_off, const float* art, const int64_t* art_off,
+                      const int32_t* pick, int32_t B, int32_t C, int32_t frames, int32_t aux, int32_t hop,
+                      int32_t ar_len, float* x, float* y, float* ar, void* stream);
+
 /* D input assembly (bin/train.py:345-346): out[b] = cat(ar[b] (La), y[b] (Ly)) rows, fp32 in,
  * `dtype` out with row pitch `out_pitch` elements (>= La+Ly, rest untouched). */
 int artic_concat_time(const float* ar, const float* y, void* out, int32_t B, int32_t La, int32_t Ly,

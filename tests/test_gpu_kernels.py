@@ -375,6 +375,45 @@ def test_tc_conv_cluster_weight_multicast(prec, shape):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])     # same MMAs, same order
 
 
+@pytest.mark.parametrize("k,pad,ni", [(3, 1, 1), (2, 1, 3)])
+def test_logit_conv_data_gradient_channel1_kernel(k, pad, ni):
+    """Data gradient of a C -> 1 logit conv in the bf16 mode (fp32 logit gradient in, bf16 feature gradient out) with the
+    discriminator backward's epilogue: (dgrad + feature-matching gradient) x LeakyReLU'(saved activation).  Must run
+    on the channel-1 kernel (it used to fall to the generic one), plain and period layouts."""
+    C, B, H = 1024, 4, 23
+    spec = ConvSpec(kind="conv", cin=C, cout=1, k=k, padding=pad)
+    torch.manual_seed(k)
+    w = torch.randn(spec.weight_shape(), dtype=torch.float64) * 0.05
+    Ho = spec.out_len(H)
+    dz = torch.randn(B * ni, 1, Ho, dtype=torch.float64)
+    act = _bf16_round(torch.randn(B * ni, C, H))
+    fm = _bf16_round(torch.randn(B * ni, C, H) * 0.1)
+    gx = F.conv_transpose1d(dz, w.float().double(), padding=pad)          # dgrad of conv1d(stride 1)
+    want = (gx + fm) * torch.where(act > 0, 1.0, 0.1)
+    lay = ConvLayer(spec, "l", BF16, F32)
+    lay.bind({"l.weight": w.float().to(DEV).contiguous()})
+    lay.prep()
+
+    def seqs(t, dtype, Cc, L):          # (B*ni, Cc, L) -> SeqT in plain or period storage
+        if ni == 1:
+            return SeqT(t.permute(0, 2, 1).contiguous().to(DEV, dtype), B, L, Cc)
+        st = SeqT.period(B, L, ni, Cc, _lib.DTYPE_CODE[dtype], DEV)
+        st.t.copy_(t.view(B, ni, Cc, L).permute(0, 3, 1, 2))
+        return st
+
+    dZ = seqs(dz, torch.float32, 1, Ho)
+    A, FM = seqs(act, torch.bfloat16, C, H), seqs(fm, torch.bfloat16, C, H)
+    dX = A.like()
+    _lib.path_counts(reset=True)
+    lay.dgrad(dZ, dX=dX, res_pre=FM, mask=A, mask_slope=0.1)
+    torch.cuda.synchronize()
+    pc = _lib.path_counts()
+    assert pc["conv_c1"] == 1 and pc["conv_generic"] == 0, pc
+    got = dX.t.float().cpu()
+    got = got.permute(0, 2, 1) if ni == 1 else got.permute(0, 2, 3, 1).reshape(B * ni, C, H)
+    assert rel_err(got, want) < 6e-3
+
+
 def _bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float64)
 

@@ -280,6 +280,8 @@ def test_full_width_train_steps_vs_oracle(precision):
     _record(f"train_steps_{precision}", {"worst_rel_err": worst, "per_step": errs, "paths": pc})
     tcw = "wgrad_tc_x3" if precision == "bf16x3" else "wgrad_tc"
     assert pc[tcw] > 0 and pc["wgrad_generic"] <= 3 * 5, pc      # only the AR linears may use the generic wgrad
+    if precision == "bf16":
+        assert pc["conv_generic"] == 0, pc                       # every conv of the bf16 step: tcgen05 or a channel-1 kernel
     assert worst < gate, errs
 
 

@@ -231,6 +231,39 @@ def test_shipped_yaml_trains_and_decodes_unchanged(name, frames, tmp_path):
         assert np.abs(pcm).max() > 0
 
 
+@pytest.mark.parametrize("use_ar,aux", [(True, 0), (False, 2)])
+def test_device_window_cutter_matches_collater(use_ar, aux):
+    """Windows cut on the device from the HBM-resident dataset == SpeechCollater's host windows under the same seeded
+    RNG, bit for bit (x, y, ar), including dropped short utterances and the left-zero-padded AR context."""
+    import numpy as np
+    from articulatory_b200.data import DeviceWindowCutter, SpeechCollater, synthetic_utterances
+    hop, steps = 80, 2000
+    items = synthetic_utterances(9, n_frames=90, n_feats=13, hop_size=hop, seed=3)
+    items[2] = {"audio": items[2]["audio"][:hop * 20], "art": items[2]["art"][:20]}            # too short: dropped
+    items[5] = {"audio": items[5]["audio"][:hop * 61 + 17], "art": items[5]["art"]}            # art longer than the audio
+    cfg = {"generator_params": {"use_ar": use_ar, "ar_input": 512, "out_channels": 1}}
+    mk = lambda seed: SpeechCollater(batch_max_steps=steps, hop_size=hop, aux_context_window=aux, config=cfg,
+                                     rng=np.random.RandomState(seed))
+    host, dev_c = mk(11), mk(11)
+    cutter = DeviceWindowCutter(items, dev_c, DEV)
+    for group in ([0, 1, 2, 3], [4, 5, 6, 7, 8], [8, 0]):
+        want = host([items[i] for i in group])
+        got = cutter(group)
+        assert torch.equal(got["x"][0].cpu(), want["x"][0]) and torch.equal(got["y"].cpu(), want["y"])
+        if use_ar:
+            assert torch.equal(got["ar"].cpu(), want["ar"])
+        else:
+            assert "ar" not in got
+    # a start near the beginning exercises the zero padding of the AR context
+    if use_ar:
+        class First:
+            def randint(self, lo, hi):
+                return lo
+        dev_c.rng = host.rng = First()
+        want, got = host([items[0]]), cutter([0])
+        assert torch.equal(got["ar"].cpu(), want["ar"]) and float(got["ar"].abs().sum()) == 0.0
+
+
 def test_mri_recipe_shapes_vs_oracle():
     """egs/mri/voc1/conf/mri2w_hifigan_car.yaml (vendored): 358-dim MRI features, upsampling [8, 5, 3, 2] (hop 240, 20 kHz),
     k = 16 / 10 / 6 / 4 transposed convs, CAR conditioning — generator forward on the tensor cores against the oracle."""
