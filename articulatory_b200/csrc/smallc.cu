@@ -357,9 +357,10 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_kernel(const __grid_constant
 // is unrolled 4x so that four independent row loads are in flight (the scalar kernel above is
 // latency-bound: one 2-byte load per thread per iteration).
 constexpr int C1V_ROWS = 256;   // positions per CTA of the vector kernel (twice the CTAs of the scalar ones)
-template <typename T>
+template <typename T, typename TY = __nv_bfloat16>
 __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_constant__ artic_tapwgrad_t p, int tap0,
                                                                int min_off, int span, int dbg) {
+  constexpr bool YF = sizeof(TY) == 4;          // fp32 dY (bf16x3 / fp32 modes): two 128-bit loads per 8 channels
   __shared__ float xs[C1_SMEM];
   __shared__ float red[256][17];
   const int tpr = p.Cog >> 3, rpp = 256 / tpr;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
   const int qa = blockIdx.x * C1V_ROWS;
   const int qb = min(p.nq, qa + C1V_ROWS);
   const T* __restrict__ X = reinterpret_cast<const T*>(p.X) + seq_base(p.x, n);
-  const __nv_bfloat16* __restrict__ dY = reinterpret_cast<const __nv_bfloat16*>(p.dY) + seq_base(p.y, n);
+  const TY* __restrict__ dY = reinterpret_cast<const TY*>(p.dY) + seq_base(p.y, n);
   const int x0 = (p.q0 + qa) * p.si + min_off;
   const int nx = (qb - qa - 1) * p.si + span + 1;
   for (int i = threadIdx.x; i < nx; i += 256) {
@@ -389,17 +390,20 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
   int offr[C1_TAPS];
 #pragma unroll
   for (int t = 0; t < C1_TAPS; ++t) offr[t] = t < nt ? p.off[tap0 + t] - min_off : 0;
-  auto load4 = [&](uint4 (&u)[4], int q) {
+  constexpr int NV = YF ? 2 : 1;                // 128-bit loads per row and thread
+  auto load4 = [&](uint4 (&u)[4 * NV], int q) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int qq = q + j * rpp;
       const int ypos = (p.q0 + qq) * p.so + yo;
-      u[j] = (qq < qb && ypos >= 0 && ypos < p.y.len)
-                 ? __ldg(reinterpret_cast<const uint4*>(dY + (int64_t)ypos * p.y.s_row) + cg)
-                 : make_uint4(0, 0, 0, 0);
+      const bool ok = qq < qb && ypos >= 0 && ypos < p.y.len;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        u[j * NV + v] = ok ? __ldg(reinterpret_cast<const uint4*>(dY + (int64_t)ypos * p.y.s_row) + cg * NV + v)
+                           : make_uint4(0, 0, 0, 0);
     }
   };
-  uint4 u[4], un[4];
+  uint4 u[4 * NV], un[4 * NV];
   if (!(dbg & 2)) load4(u, qa + rl);
   for (int q = qa + rl; q < qb && !(dbg & 2); q += 4 * rpp) {
     load4(un, q + 4 * rpp);                      // rows past qb load zeros
@@ -408,11 +412,17 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
       const int qq = q + j * rpp;
       if (qq >= qb) break;
       float dy[8];
-      const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+      if (YF) {
+        const uint4 a = u[j * NV], b = u[j * NV + NV - 1];
+        dy[0] = __uint_as_float(a.x); dy[1] = __uint_as_float(a.y); dy[2] = __uint_as_float(a.z); dy[3] = __uint_as_float(a.w);
+        dy[4] = __uint_as_float(b.x); dy[5] = __uint_as_float(b.y); dy[6] = __uint_as_float(b.z); dy[7] = __uint_as_float(b.w);
+      } else {
+        const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        dy[2 * i] = __uint_as_float(w[i] << 16);
-        dy[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        for (int i = 0; i < 4; ++i) {
+          dy[2 * i] = __uint_as_float(w[i] << 16);
+          dy[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
       }
       // all tap samples first (16 independent shared-memory loads in flight: with two warps per scheduler a
       // load -> 8 dependent FMAs chain per tap stalls on the shared-memory latency), padded taps read offset 0
@@ -427,7 +437,7 @@ __global__ void __launch_bounds__(256) tapwgrad_ci1_vec_kernel(const __grid_cons
         for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(xv[t], dy[i], acc[t][i]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) u[j] = un[j];
+    for (int j = 0; j < 4 * NV; ++j) u[j] = un[j];
   }
 #pragma unroll
   for (int t = 0; t < C1_TAPS; t += 2) {       // two taps per reduction round
@@ -580,12 +590,13 @@ int artic_tapwgrad_ci1_try(const artic_tapwgrad_t* pp, cudaStream_t st) {
     else K<float, float><<<grid, 256, 0, st>>>(p, cw, tap0, min_off, span);                                        \
   } while (0)
     const int tpr = p.Cog / 8;
-    const bool vec = ci1 && yb && p.Cog % 8 == 0 && tpr <= 256 && 256 % tpr == 0 && p.y.s_row % 8 == 0 &&
+    const bool vec = ci1 && p.Cog % 8 == 0 && tpr <= 256 && 256 % tpr == 0 && p.y.s_row % 8 == 0 &&
                      p.y.s_outer % 8 == 0 && (p.y.n_inner == 1 || p.y.s_inner % 8 == 0) &&
-                     (reinterpret_cast<uintptr_t>(p.dY) & 15) == 0;
+                     (reinterpret_cast<uintptr_t>(p.dY) & 15) == 0 && (yb || !xb);
     if (vec) {
       dim3 vgrid((unsigned)((p.nq + C1V_ROWS - 1) / C1V_ROWS), grid.y, 1);
-      if (xb) tapwgrad_ci1_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span, tc::g_debug[20]);
+      if (!yb) tapwgrad_ci1_vec_kernel<float, float><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span, tc::g_debug[20]);
+      else if (xb) tapwgrad_ci1_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span, tc::g_debug[20]);
       else tapwgrad_ci1_vec_kernel<float><<<vgrid, 256, 0, st>>>(p, tap0, min_off, span, tc::g_debug[20]);
     } else if (ci1) ARTIC_C1_LAUNCH(tapwgrad_ci1_kernel);
     else ARTIC_C1_LAUNCH(tapwgrad_co1_kernel);

@@ -726,7 +726,7 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
   if (tc::g_debug[1]) return 0;                       // debug: force the generic kernel
   const bool x3 = p.dtype == ARTIC_F32 && p.out_dtype == ARTIC_F32 && p.X_sp != nullptr && p.Wt_sp != nullptr;
   if (!x3 && (p.Wt == nullptr || p.dtype != ARTIC_BF16 || p.out_dtype != ARTIC_BF16)) return 0;
-  if (x3 && tc::g_debug[20] == 1) return 0;            // debug: bf16x3 problems on the CUDA-core kernel
+  if (x3 && tc::g_debug[24] == 1) return 0;            // debug key 24: bf16x3 problems on the CUDA-core kernel
   if (p.act == ARTIC_ACT_TANH || p.res2 != nullptr) return 0;
   if (p.si < 1 || p.si > 8) return 0;
   if (p.Cig % 16 != 0 || p.Cog % 32 != 0) return 0;

@@ -378,7 +378,7 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st, int* bias
   if (tc::g_debug[1] || tc::g_debug[5]) return 0;
   const bool x3 = p.dtype == ARTIC_F32 && p.y_dtype == ARTIC_F32 && p.X_sp != nullptr && p.dY_sp != nullptr;
   if (!x3 && (p.dtype != ARTIC_BF16 || p.y_dtype != ARTIC_BF16)) return 0;
-  if (x3 && (tc::g_debug[20] == 1 || (p.x_plane % 8) || (p.y_plane % 8))) return 0;
+  if (x3 && (tc::g_debug[24] == 1 || (p.x_plane % 8) || (p.y_plane % 8))) return 0;
   const void* Xb = x3 ? p.X_sp : p.X;
   const void* Yb = x3 ? p.dY_sp : p.dY;
   if (p.si < 1 || p.si > 8 || p.so != 1) return 0;

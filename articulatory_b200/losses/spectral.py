@@ -57,8 +57,10 @@ class _MRSTFTFn(torch.autograd.Function):
         x2, y2 = _as_2d(x), _as_2d(y)
         R = len(mod.resolutions)
         sums = torch.zeros((R, 3), dtype=torch.float32, device=x2.device)
-        for r, res in enumerate(mod.resolutions):
-            res.forward(x2, y2, sums[r])
+        # the resolutions are independent: one stream each (a 2048-point frame block occupies an SM ~4x longer than a
+        # 512-point one; side by side the three launches fill the machine instead of queueing behind each other's tails)
+        from ..engine import fork_join
+        fork_join([lambda r=r, res=res: res.forward(x2, y2, sums[r]) for r, res in enumerate(mod.resolutions)])
         numel = torch.tensor([res.numel(*x2.shape) for res in mod.resolutions], dtype=torch.float32, device=x2.device)
         sc = (sums[:, 0].sqrt() / sums[:, 1].sqrt()).mean()      # stft_loss.py:61, :166
         mag = (sums[:, 2] / numel).mean()                        # stft_loss.py:82, :167
@@ -73,8 +75,9 @@ class _MRSTFTFn(torch.autograd.Function):
         dx = torch.zeros_like(x2)
         # the kernel takes host scalars for the two upstream gradients
         w_sc, w_mag = float(g_sc) / R, float(g_mag) / R
-        for r, res in enumerate(ctx.mod.resolutions):
-            res.backward(x2, y2, sums[r], w_sc, w_mag, dx)
+        from ..engine import fork_join
+        fork_join([lambda r=r, res=res: res.backward(x2, y2, sums[r], w_sc, w_mag, dx)
+                   for r, res in enumerate(ctx.mod.resolutions)])          # dx is accumulated atomically
         return dx.view(ctx.shape), None, None
 
 

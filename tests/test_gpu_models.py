@@ -121,6 +121,23 @@ def test_train_steps_golden(golden, use_graph):
     dsd = {k: v.detach().cpu() for k, v in D.state_dict().items()}
     for k, d in golden["dsd_delta"].items():
         check_digest(dsd[k] - golden["dsd"][k], d, 0.9, f"D delta {k}", sum_rtol=0.3)
+    # ... and tight against the ORACLE run live on the same four steps: direction and size of every network's update.
+    # (Element-wise the deltas are fragile — Adam's first steps are sign-like, so a weight whose gradient is ~0 flips
+    # with the summation order; over a whole network the update must agree.)
+    from oracle import torch_oracle as O
+    ogsd = {k: v.clone() for k, v in golden["gsd"].items()}
+    odsd = {k: v.clone() for k, v in golden["dsd"].items()}
+    gopt, dopt = O.AdamState(ogsd), O.AdamState(odsd)
+    for step in range(len(golden["train_logs"])):
+        O.train_step(ogsd, odsd, golden["generator_params"], golden["discriminator_params"], gopt, dopt, golden["batch"], step,
+                     use_stft_loss=True, use_mel_loss=True)
+    # thresholds: the fp32 oracle against ITSELF in fp64 gives cos 0.980 / norm ratio 0.986 for G (two sign-like Adam
+    # updates) and 0.9999999 / 1.000002 for D (three updates of well-conditioned gradients)
+    for name, mine, ref, init, cmin, ntol in (("G", gsd, ogsd, golden["gsd"], 0.9, 0.06), ("D", dsd, odsd, golden["dsd"], 0.995, 0.02)):
+        dm = torch.cat([(mine[k] - init[k]).flatten().double() for k in init])
+        dr = torch.cat([(ref[k] - init[k]).flatten().double() for k in init])
+        cos = float(dm @ dr / (dm.norm() * dr.norm()))
+        assert cos > cmin and abs(float(dm.norm() / dr.norm()) - 1.0) < ntol, (name, cos, float(dm.norm() / dr.norm()))
     # a 5th step replays the captured graph (when enabled) and must stay finite
     ts.step(b["x"], b["y"], b["ar"], use_graph=use_graph)
     assert all(map(lambda v: v == v and abs(v) < 1e6, ts.last_values().values()))
