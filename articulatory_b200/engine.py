@@ -254,10 +254,13 @@ class SideQueue:
         self.keep = []
         if not self.inline:
             dev = torch.cuda.current_stream().device_index
-            prio = PRIO_HIGH if os.environ.get("ARTIC_PRIORITIES", "1") != "0" else 0
-            pool = _QUEUE_STREAMS.setdefault(dev, [torch.cuda.Stream(device=dev, priority=prio) for _ in range(12)])
-            i = _QUEUE_NEXT.get(dev, 0)
-            _QUEUE_NEXT[dev] = (i + 1) % len(pool)
+            use_prio = os.environ.get("ARTIC_PRIORITIES", "1") != "0"
+            bg = use_prio and _IN_BACKGROUND[0]        # queues of a background branch stay in the background
+            prio = (PRIO_LOW if bg else PRIO_HIGH) if use_prio else 0
+            key = (dev, bg)
+            pool = _QUEUE_STREAMS.setdefault(key, [torch.cuda.Stream(device=dev, priority=prio) for _ in range(12)])
+            i = _QUEUE_NEXT.get(key, 0)
+            _QUEUE_NEXT[key] = (i + 1) % len(pool)
             self.s = pool[i]
 
     def run(self, fn, *tensors):
@@ -1065,16 +1068,18 @@ class DiscriminatorEngine:
                 "chains": [[slice_seq(a, lo, hi) for a in acts] for acts in tape["chains"]]}
 
     # ---- backward ------------------------------------------------------------
-    def backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True, pre_zeroed=False):
+    def backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True, pre_zeroed=False, finalize=True):
         with planner_objective(_D_OBJECTIVE):
-            return self._backward(tape, douts, grads, need_dx, pre_zeroed)
+            return self._backward(tape, douts, grads, need_dx, pre_zeroed, finalize)
 
-    def _backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True, pre_zeroed=False):
+    def _backward(self, tape, douts, grads: Optional[Dict[str, torch.Tensor]], need_dx=True, pre_zeroed=False, finalize=True):
         """douts: per chain a list (same length as the chain's outputs) of SeqT gradients or
         None; the gradient wrt the logits must be present.  Accumulates parameter gradients
         into ``grads`` when given (None = skip every wgrad, as in the generator phase) and
         returns d x (B, 1, T) fp32 when ``need_dx``.  ``pre_zeroed``: the caller already cleared the
-        weight-gradient accumulators (``wset.zero()``) off the critical path."""
+        weight-gradient accumulators (``wset.zero()``) off the critical path.  ``finalize=False``: leave the weight
+        gradients in the prepared-layout accumulators (another backward over other batch items will add to them and
+        finish with ``wset.unprep``)."""
         B, T = tape["B"], tape["T"]
         dev = tape["sigs"][0].t.device
         if grads is not None and not pre_zeroed:
@@ -1140,6 +1145,6 @@ class DiscriminatorEngine:
                      k, st, pd, 1, F32)
             # dx += dsig[0]  (via the reflect-pad backward with Lp == L: plain accumulate)
             call("artic_reflect_pad_right_bwd", ptr(dsig[0].t), ptr(dx), B, T, T, 1, F32)
-        if grads is not None:
+        if grads is not None and finalize:
             self.wset.unprep(grads)
         return dx

@@ -32,6 +32,13 @@ from .optim import FusedAdam
 #: chain's first (tiny) kernels.  "order2" (12.70): the generator forward is enqueued ahead of the big-grid weight
 #: prep / gradient clears it overlaps with.  "prep" (weight re-materialisation in the background) does not pay.
 _BG = set(filter(None, _os.environ.get("ARTIC_BG", "order,spectral,order2").split(",")))
+#: ARTIC_SPLIT_DBWD=1: the discriminator's backward over the REAL half of [fake | real] does not depend on the generator
+#: update, so it runs as a low-priority background branch under the generator backward of the G phase; the D phase then
+#: only back-propagates the fake half before the (single) weight-gradient relayout.  Same results (parity tests run both
+#: ways).  OFF by default: taking 1.7 ms of work off the critical path changed the step by 0.00 ms (12.430 vs 12.431 ms,
+#: bf16; 28.27 vs 28.16 bf16x3) — the step is bound by the total SM time of its ~500 tensor-core launches, not by its
+#: dependency chains.
+_SPLIT_DBWD = _os.environ.get("ARTIC_SPLIT_DBWD", "0") == "1"
 
 LOG_KEYS = ["train/spectral_convergence_loss", "train/log_stft_magnitude_loss", "train/mel_loss",
             "train/adversarial_loss", "train/feature_matching_loss", "train/generator_loss",
@@ -217,10 +224,31 @@ class TrainStep:
         else:
             fork_join([adversarial, spectral], background=(1,) if "spectral" in _BG else ())
         La = self.ar_len
-        call("artic_add_rows", ptr(state["d_in"]) + 4 * La, La + T, ptr(dy), T, B, T)
         tape2 = state["tape2"]
-        self.optG.zero_grad()
-        engG.backward(tapeG, dy, self.optG.grad_views)
+
+        def g_backward():
+            call("artic_add_rows", ptr(state["d_in"]) + 4 * La, La + T, ptr(dy), T, B, T)
+            self.optG.zero_grad()
+            engG.backward(tapeG, dy, self.optG.grad_views)
+
+        def d_real_backward():
+            # bin/train.py:415-418, real half: D(real) and D's weights are final here (D is updated at the very end of the
+            # step), so its share of dL_D/dθ_D is computed now, in the background of the generator backward
+            self.optD.zero_grad()
+            engD.wset.zero()
+            real = [[slice_seq(acts[-1], B, 2 * B)] for acts in tape2["chains"]]
+            lg = [lst[0].like() for lst in real]
+            fork_join([lambda ci=ci: self._adv_seed(real[ci:ci + 1], 1.0, _REAL, inv_w, lg[ci:ci + 1]) for ci in range(len(real))])
+            douts = [[None] * (len(acts) - 2) + [lg[ci]] for ci, acts in enumerate(tape2["chains"])]
+            engD.backward(engD.slice_tape(tape2, B, 2 * B), douts, grads=self.optD.grad_views, need_dx=False, pre_zeroed=True,
+                          finalize=False)
+
+        self._d_real_done = False
+        if _SPLIT_DBWD:
+            fork_join([g_backward, d_real_backward], background=(1,))
+            self._d_real_done = True
+        else:
+            g_backward()
         return tape2
 
     def _phase_d(self, x, y, ar, tape2):
@@ -233,7 +261,11 @@ class TrainStep:
             self.optD.zero_grad()
             engD.wset.zero()
 
-        if "order2" in _BG:
+        real_done = tape2 is not None and getattr(self, "_d_real_done", False)
+        self._d_real_done = False
+        if real_done:              # the gradient buffers already hold the real half's share (G phase): do not clear them
+            y_, _ = engG.forward(x, ar, save=False)                                            # bin/train.py:390-400
+        elif "order2" in _BG:
             _, (y_, _) = fork_join([clear_d_grads, lambda: engG.forward(x, ar, save=False)])
         else:
             (y_, _), _ = fork_join([lambda: engG.forward(x, ar, save=False), clear_d_grads])   # bin/train.py:390-400
@@ -242,6 +274,13 @@ class TrainStep:
         else:
             # D(real) is REUSED from the G phase; D(fake) overwrites the stale fake half in place
             engD.forward(self._disc_input(ar, (y_,)), save=True, into=tape2, lo=0)
+        if real_done:
+            fake = [[slice_seq(acts[-1], 0, B)] for acts in tape2["chains"]]
+            lg = [lst[0].like() for lst in fake]
+            fork_join([lambda ci=ci: self._adv_seed(fake[ci:ci + 1], 0.0, _FAKE, inv_w, lg[ci:ci + 1]) for ci in range(len(fake))])
+            douts = [[None] * (len(acts) - 2) + [lg[ci]] for ci, acts in enumerate(tape2["chains"])]
+            engD.backward(engD.slice_tape(tape2, 0, B), douts, grads=self.optD.grad_views, need_dx=False, pre_zeroed=True)
+            return
         outs2 = [acts[1:] for acts in tape2["chains"]]
         outs_f = [[slice_seq(lst[-1], 0, B)] for lst in outs2]
         outs_r = [[slice_seq(lst[-1], B, 2 * B)] for lst in outs2]

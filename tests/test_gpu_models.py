@@ -143,6 +143,21 @@ def test_train_steps_golden(golden, use_graph):
     assert all(map(lambda v: v == v and abs(v) < 1e6, ts.last_values().values()))
 
 
+def test_train_steps_golden_with_split_discriminator_backward(golden, monkeypatch):
+    """The alternative schedule (D backward over the real half in the background of the G backward, trainer._SPLIT_DBWD)
+    is the same arithmetic: the reference's logged scalars of four steps, graph mode."""
+    from articulatory_b200 import trainer
+    monkeypatch.setattr(trainer, "_SPLIT_DBWD", True)
+    G, D = _build(golden)
+    ts = trainer.TrainStep(G, D, _train_config(golden), DEV)
+    b = {k: v.to(DEV) for k, v in golden["batch"].items()}
+    for step, ref_logs in enumerate(golden["train_logs"]):
+        ts.step(b["x"], b["y"], b["ar"], use_graph=True)
+        vals = ts.last_values()
+        for k, v in ref_logs.items():
+            assert abs(vals[k] - v) <= 1e-3 * abs(v), (step, k, vals[k], v)
+
+
 def test_eval_step_vs_oracle(golden):
     """TrainStep.eval_step == the reference Trainer._eval_step arithmetic (bin/train.py:470-603), restated with the
     oracle's functions on the golden weights / batch: nine eval/* losses, no parameter change."""
