@@ -264,6 +264,36 @@ def test_device_window_cutter_matches_collater(use_ar, aux):
         assert torch.equal(got["ar"].cpu(), want["ar"]) and float(got["ar"].abs().sum()) == 0.0
 
 
+def test_train_step_without_ar_conditioning(golden):
+    """A non-autoregressive HiFi-GAN config (use_ar: false — the collater then emits no 'ar'): the fused train step and
+    the eval step accept ar=None, D sees the bare window (reference bin/train.py:345-349 else-branch), losses match the
+    oracle's step."""
+    from articulatory_b200 import models as M
+    from articulatory_b200.trainer import TrainStep
+    from oracle import torch_oracle as O
+    from tests.test_gpu_models import _train_config
+    gp = dict(golden["generator_params"], use_ar=False, in_channels=13)
+    torch.manual_seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = M.HiFiGANGenerator(**gp)
+        D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**golden["discriminator_params"])
+    gsd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    dsd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    ts = TrainStep(G.to(DEV), D.to(DEV), _train_config(golden), DEV)
+    b = {k: v for k, v in golden["batch"].items() if k != "ar"}
+    gopt, dopt = O.AdamState(gsd), O.AdamState(dsd)
+    for step in range(4):
+        ref = O.train_step(gsd, dsd, gp, golden["discriminator_params"], gopt, dopt, dict(b, ar=None), step,
+                           use_stft_loss=True, use_mel_loss=True)
+        ts.step(b["x"].to(DEV), b["y"].to(DEV), None, use_graph=True)
+        vals = ts.last_values()
+        for k, v in ref.items():
+            assert abs(vals[k] - v) <= 1e-3 * abs(v), (step, k, vals[k], v)
+    ev = ts.eval_step(b["x"].to(DEV), b["y"].to(DEV), None)
+    assert all(v == v for v in ev.values())
+
+
 def test_mri_recipe_shapes_vs_oracle():
     """egs/mri/voc1/conf/mri2w_hifigan_car.yaml (vendored): 358-dim MRI features, upsampling [8, 5, 3, 2] (hop 240, 20 kHz),
     k = 16 / 10 / 6 / 4 transposed convs, CAR conditioning — generator forward on the tensor cores against the oracle."""

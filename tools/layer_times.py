@@ -20,11 +20,10 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--top", type=int, default=45)
     args = ap.parse_args()
-    import bench
+    from articulatory_b200 import configs as O
     from articulatory_b200 import engine
     from articulatory_b200 import models as M
     from articulatory_b200.trainer import TrainStep
-    from oracle import torch_oracle as O
 
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
@@ -32,7 +31,7 @@ def main():
         warnings.simplefilter("ignore")
         G = M.HiFiGANGenerator(**O.E2W_GENERATOR_PARAMS, precision=args.precision).to(dev)
         D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**O.E2W_DISCRIMINATOR_PARAMS, precision=args.precision).to(dev)
-    ts = TrainStep(G, D, bench.train_config(), dev)
+    ts = TrainStep(G, D, O.e2w_train_config(use_stft_loss=True), dev)
     b = {k: v.to(dev) for k, v in O.synthetic_batch(args.batch, seed=1234).items()}
     for _ in range(4):
         ts.step(b["x"], b["y"], b["ar"], use_graph=False)
