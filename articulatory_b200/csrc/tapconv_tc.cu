@@ -70,6 +70,7 @@ struct Plan {
   int32_t a_off16[ARTIC_MAX_TAPS];  // (phase * panel_bytes + shift * row_bytes) / 16 : descriptor offset of the tap
   int32_t layout_type;            // UMMA smem descriptor swizzle code
   int32_t n_kcl;                  // logical ci chunks (n_kc = 3 * n_kcl in the bf16x3 mode)
+  int32_t ctas;                   // CTAs the planner wants for this problem (<= total_tiles: several tiles per CTA)
   int32_t cs;                     // cluster size (weight multicast); 1 = no cluster
   int32_t n_mg;                   // row-tile groups of cs consecutive tiles (n_mt / cs)
   long long* dbg;                 // debug timeline buffer (artic_debug_buffer) or nullptr
@@ -893,8 +894,12 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
       double tile_clk = main_clk > mem_clk ? main_clk : mem_clk;
       if (cand.acc_stages == 2) tile_clk = tile_clk > epi_clk ? tile_clk : epi_clk;
       else tile_clk += epi_clk;
-      double cost = waves * (tile_clk + 600.0) + (cand.acc_stages == 2 ? epi_clk : 0.0);
-      {
+      (void)waves;
+      cand.ctas = cand.total_tiles;
+      // Tiles per CTA (debug key 25 = largest factor tried, default 1): a CTA that loops over f tiles pays the fixed
+      // cost once and — with a double-buffered accumulator — hides all but the last epilogue under the next main loop.
+      const int fmax = tc::g_debug[25] > 1 ? tc::g_debug[25] : 1;
+      for (int f = 1; f <= fmax; ++f) {
         // Objective: the SM TIME of the launch, not its stand-alone latency.  The train step runs 3..8 independent
         // chains on concurrent streams, every CTA owns an SM (shared memory), and the SM-occupancy trace
         // (tools/sm_timeline.py) shows the step bound by the sum of CTA lifetimes: a plan with fewer, fuller CTAs
@@ -903,11 +908,18 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
         // CTA in units of 500 clocks (default 6: launch, barrier / TMEM setup, first TMA round trip).
         const double a = tc::g_debug[15] > 0 ? tc::g_debug[15] / 100.0 : tc::g_debug[15] < 0 ? 0.0 : 1.0;
         const double fixed = tc::g_debug[16] > 0 ? 500.0 * tc::g_debug[16] : 3000.0;
-        const double ctas = cand.total_tiles < sms_avail ? cand.total_tiles : sms_avail;
-        const double sm_time = ctas * (fixed + waves * (tile_clk + 600.0)) / sms_avail;
-        cost = (1.0 - a) * cost + a * sm_time;
+        double ctas = (double)((cand.total_tiles + f - 1) / f);
+        if (ctas > sms_avail) ctas = sms_avail;
+        const double waves_f = (double)(((long long)cand.total_tiles + (long long)ctas - 1) / (long long)ctas);
+        if (f > 1 && (waves_f < 2.0 || cand.cs > 1)) break;      // nothing left to fold
+        const double tail = cand.acc_stages == 2 ? epi_clk : 0.0;
+        const double lat = waves_f * (tile_clk + 600.0) + tail;
+        // (f == 1 keeps the round-1 form of the SM-time term, without the exposed last epilogue: the defaults were
+        // tuned against it)
+        const double sm_time = ctas * (fixed + lat - (f == 1 ? tail : 0.0)) / sms_avail;
+        const double cost_f = (1.0 - a) * lat + a * sm_time;
+        if (best < 0 || cost_f < best) { best = cost_f; pl = cand; pl.ctas = (int)ctas; }
       }
-      if (best < 0 || cost < best) { best = cost; pl = cand; }
     }
   }
   if (best < 0) return 0;
@@ -980,6 +992,7 @@ static int tc_launch_group(tc::Multi& mp, const int* smem, const double* cost, c
       if (c < 1) c = 1;
       if (c > t) c = t;
     }
+    if (mp.prob[j].pl.ctas > 0 && c > mp.prob[j].pl.ctas) c = mp.prob[j].pl.ctas;     // several tiles per CTA by plan
     if (cs > 1) {              // whole clusters: at most floor(SMs / cs) of them, one per super tile
       int cl = t / cs < num_sms() / cs ? t / cs : num_sms() / cs;
       c = cl * cs;
