@@ -74,7 +74,7 @@ struct Plan {
   int32_t cs;                     // cluster size (weight multicast); 1 = no cluster
   int32_t n_mg;                   // row-tile groups of cs consecutive tiles (n_mt / cs)
   long long* dbg;                 // debug timeline buffer (artic_debug_buffer) or nullptr
-  int32_t dbg_flags;              // debug: 1 = skip epilogue stores, 2 = skip operand use
+  int32_t dbg_flags;              // what-if timing (debug key 9): 1 = no epilogue loads / stores, 2 = no MMA issued
 };
 
 // Several independent problems (the phases of a strided data gradient / transposed conv, the three MRF
@@ -314,6 +314,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     // precomputed row shift, the sub-tile offset and the k-step are added).
     {
       const bool leader = elect_one();
+      const bool skip_mma = (pl.dbg_flags & 2) != 0;      // what-if timing (debug key 9): the pipeline runs, no MMA is issued
       PipeState as(pl.n_as), ws(pl.n_ws), acc(pl.acc_stages);
 #if ARTIC_TC_TRACE
       int n_ws_seen = 0;
@@ -361,17 +362,17 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
                 if (ksteps == 4) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    if (leader) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
+                    if (leader && !skip_mma) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
                     accum = 1;
                   }
                 } else if (ksteps == 2) {
 #pragma unroll
                   for (int k = 0; k < 2; ++k) {
-                    if (leader) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
+                    if (leader && !skip_mma) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | (at16 + 2 * k), ((uint64_t)desc_hi << 32) | (b16 + 2 * k), idesc, accum);
                     accum = 1;
                   }
                 } else {
-                  if (leader) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | at16, ((uint64_t)desc_hi << 32) | b16, idesc, accum);
+                  if (leader && !skip_mma) umma_bf16(dcol, ((uint64_t)desc_hi << 32) | at16, ((uint64_t)desc_hi << 32) | b16, idesc, accum);
                   accum = 1;
                 }
                 // the accumulate flag must stay 0 for the first k-step of EVERY sub-tile of the tile
@@ -448,7 +449,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
           const int row = (p.q0 + q) * p.so + p.ro;
           if (row >= 0 && row < p.y.len) o = seq_base(p.y, n) + (int64_t)row * p.y.s_row + cbase;
         }
-        rowoff[m * 32 + lane] = o;
+        rowoff[m * 32 + lane] = (pl.dbg_flags & 1) ? -1 : o;      // what-if timing (debug key 9 = 1): no epilogue loads / stores
       }
       {  // bias of this warp's channel chunks (same for every sub-tile): loaded before the accumulator is ready
         int j = 0;
