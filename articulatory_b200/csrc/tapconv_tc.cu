@@ -42,7 +42,8 @@ constexpr int MAX_AS = 8;   // activation stages
 #ifndef ARTIC_TC_TRACE
 #define ARTIC_TC_TRACE 0
 #endif
-constexpr int EPI_WARP_BYTES = 4 * 32 * 8 + 8 * 32 * 4;   // per epilogue warp: row offsets of 4 sub-tiles + bias of its (<= 8) channel chunks
+constexpr int MAX_MT = 8;   // 128-row sub-tiles per CTA tile (narrow layers: bn <= 64 leaves TMEM room for 8)
+constexpr int EPI_WARP_BYTES = MAX_MT * 32 * 8 + 8 * 32 * 4;   // per epilogue warp: row offsets of MAX_MT sub-tiles + bias of its (<= 8) channel chunks
 
 struct Plan {
   int32_t w_early;    // 1: the first weight stages may be loaded before the grid-dependency wait
@@ -162,6 +163,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
 
   const long long t_start = clock64();
   const long long t_trace = (mp.trace != nullptr && threadIdx.x == 0) ? global_timer() : 0;
+  if (pl.dbg_flags & 4) return;   // what-if timing (debug key 9 = 4): every CTA exits at once — the cost of the launches themselves
   pdl_launch_dependents();   // the next conv of the stream may start its prologue (and weight prefetch) under this one
   // Setup rendezvous on named barrier 1: the producer warp initialises the mbarriers, ARRIVES and goes
   // straight to its first TMA loads; the other warps (TMEM allocation in warp 1) SYNC on it.
@@ -422,7 +424,7 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
     uint8_t* epi = smem_raw + (epi_base - smem_u32(smem_raw));
     const int n_ew = (int)(blockDim.x >> 5) - 2;            // 4 or 8 epilogue warps
     long long* rowoff = reinterpret_cast<long long*>(epi + ewarp * EPI_WARP_BYTES);          // [sub-tile][32 rows]
-    float* bias_s = reinterpret_cast<float*>(epi + ewarp * EPI_WARP_BYTES + 4 * 32 * 8);       // [chunk][32]
+    float* bias_s = reinterpret_cast<float*>(epi + ewarp * EPI_WARP_BYTES + MAX_MT * 32 * 8);  // [chunk][32]
     const float neg_slope = p.act == ARTIC_ACT_LRELU ? p.act_slope : 1.f;
     for (int tile = cta; tile < n_super; tile += ncta) {
       const int nt = tile % pl.n_nt;
@@ -773,7 +775,10 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
   pl.n_nt = p.Cog / pl.bn;
   int mt = tmem_cap / pl.bn;   // up to the whole TMEM budget (single-buffered accumulator when > half of it)
   if (mt < 1) mt = 1;
-  if (mt > 4) mt = 4;
+  // up to 4 sub-tiles; narrow layers (bn <= 64: HBM / latency bound, the CTA count is what they cost) up to MAX_MT when
+  // debug key 26 asks for it
+  const int mt_cap = (pl.bn <= 64 && tc::g_debug[26] > 4) ? (tc::g_debug[26] < tc::MAX_MT ? tc::g_debug[26] : tc::MAX_MT) : 4;
+  if (mt > mt_cap) mt = mt_cap;
   if (mt_req > 0 && mt_req < mt) mt = mt_req;
   pl.w_tile_bytes = ((pl.bn * pl.row_bytes + 1023) / 1024) * 1024;
   pl.tps = 32 * 1024 / pl.w_tile_bytes;                  // stages of <= 32 KB
@@ -875,10 +880,10 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
     const int bn = bns[bi];
     if (p.Cog % bn != 0) continue;
     if (tc::g_debug[2] > 0 && bn != tc::g_debug[2]) continue;
-    for (int mt_req = 4; mt_req >= 1; --mt_req) {
+    for (int mt_req = tc::MAX_MT; mt_req >= 1; --mt_req) {
       if (tc::g_debug[3] > 0 && mt_req != tc::g_debug[3]) continue;
       if (!make_plan(cand, bn, mt_req)) continue;
-      if (cand.mt != mt_req && mt_req != 4) continue;   // already evaluated at a larger request
+      if (cand.mt != mt_req && mt_req != tc::MAX_MT) continue;   // already evaluated at a larger request
       const double waves = (double)((cand.total_tiles + sms_avail - 1) / sms_avail);
       const double per_mma = bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0;
       const double main_clk = (double)cand.n_kc * p.ntaps * (cand.kch / 16) * cand.mt * per_mma;

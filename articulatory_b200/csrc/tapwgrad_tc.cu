@@ -109,6 +109,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const long long t_trace = (pl.trace != nullptr && threadIdx.x == 0) ? global_timer() : 0;
+  if (pl.dbg_flags & 4) return;   // what-if timing (debug key 13 = 4): every CTA exits at once
 
   // ---- work decode: blockIdx.x -> (split z, co tile nt, ci block mb, tap group tg, group g)
   int w = blockIdx.x;

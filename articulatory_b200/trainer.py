@@ -353,12 +353,14 @@ class TrainStep:
                 g1a.replay()
                 main.wait_event(self._ev_d)
                 g1b.replay()
-                self.all_reduce(self.optG.grad)
+                if self.all_reduce is not None:
+                    self.all_reduce(self.optG.grad)
                 g2.replay()
                 self._ev_2.record(main)
                 with torch.cuda.stream(self._xs):
                     self._xs.wait_event(self._ev_2)
-                    self.all_reduce(self.optD.grad)
+                    if self.all_reduce is not None:
+                        self.all_reduce(self.optD.grad)
                     g3.replay()
                     self._ev_d.record(self._xs)
             else:
@@ -415,7 +417,10 @@ class TrainStep:
         pool = torch.cuda.graph_pool_handle()
         graphs = []
         cap = critical_stream(self.dev)         # high priority: see engine.fork_join
-        self._overlap = ar_fn is not None and _os.environ.get("ARTIC_DP_OVERLAP", "1") != "0"
+        # (ARTIC_TAIL_OVERLAP=1 runs the same four-graph schedule on one GPU: Adam(D) + D weight re-materialisation of
+        # step k under the generator forward of step k + 1)
+        self._overlap = (ar_fn is not None and _os.environ.get("ARTIC_DP_OVERLAP", "1") != "0") or \
+            _os.environ.get("ARTIC_TAIL_OVERLAP", "0") == "1"
         # G's prepared weights are refreshed inside the step (right after Adam(G)); materialise them now so that the
         # generator phase does not capture a second, redundant re-materialisation per step
         self.G._ensure_ready()
