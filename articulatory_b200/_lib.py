@@ -51,6 +51,13 @@ class TapWgrad(C.Structure):
                 ("dbias", C.c_void_p)]
 
 
+class ResUnit(C.Structure):
+    _fields_ = [("AX", C.c_void_p), ("XRES", C.c_void_p), ("W1t", C.c_void_p), ("W2t", C.c_void_p),
+                ("b1", C.c_void_p), ("b2", C.c_void_p), ("AT", C.c_void_p), ("Y", C.c_void_p), ("Y2", C.c_void_p),
+                ("N", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("k", C.c_int32), ("dil", C.c_int32),
+                ("slope", C.c_float), ("reserved_", C.c_int32 * 2)]
+
+
 class AdamHyper(C.Structure):
     _fields_ = [("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("gamma", C.c_float), ("step", C.c_int32), ("n_milestones", C.c_int32),
@@ -87,6 +94,7 @@ SIGNATURES = {
     "artic_trace_buffer": (C.c_int, [_p, C.c_longlong]),
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
     "artic_tapconv_multi": (C.c_int, [C.POINTER(TapConv), _i32, _p]),
+    "artic_resunit_fwd": (C.c_int, [C.POINTER(ResUnit), _p]),
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
     "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),
     "artic_wperm_tiles": (C.c_int64, [_i32, _i32, _i32, _i32]),
@@ -172,12 +180,12 @@ def call(name, *args):
 
 
 PATH_NAMES = ("conv_tc", "conv_tc_x3", "conv_generic", "conv_c1", "wgrad_tc", "wgrad_tc_x3", "wgrad_generic", "wgrad_c1",
-              "wgrad_bias_fused", "conv_tc_cluster")
+              "wgrad_bias_fused", "conv_tc_cluster", "conv_tc_fused")
 
 
 def path_counts(reset=False):
     """Which kernel family took each contraction since the last reset (artic_path_counts)."""
-    buf = (C.c_int64 * 10)()
+    buf = (C.c_int64 * 12)()
     load().artic_path_counts(buf, int(reset))
     return dict(zip(PATH_NAMES, list(buf)[:len(PATH_NAMES)]))
 

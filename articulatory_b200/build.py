@@ -9,7 +9,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libartic_sm100.so")
-SOURCES = ["tapconv.cu", "tapconv_tc.cu", "tapwgrad_tc.cu", "smallc.cu", "weights.cu", "elementwise.cu", "spectral.cu", "gru.cu"]
+SOURCES = ["tapconv.cu", "tapconv_tc.cu", "tapwgrad_tc.cu", "smallc.cu", "weights.cu", "elementwise.cu", "spectral.cu", "gru.cu", "resunit_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ float block_sum(float v, float* smem32) {
 // Which kernel family took a contraction (artic_path_counts): conv 0..3, wgrad 4..7
 enum { PATH_CONV_TC = 0, PATH_CONV_TC_X3 = 1, PATH_CONV_GENERIC = 2, PATH_CONV_C1 = 3,
        PATH_WGRAD_TC = 4, PATH_WGRAD_TC_X3 = 5, PATH_WGRAD_GENERIC = 6, PATH_WGRAD_C1 = 7 };
-extern long long g_path_counts[10];
+extern long long g_path_counts[12];
 
 inline int num_sms() {
   static int n = 0;

@@ -449,11 +449,11 @@ using namespace artic;
 
 extern "C" const char* artic_last_error(void) { return artic::g_err; }
 
-namespace artic { long long g_path_counts[10] = {0}; }
+namespace artic { long long g_path_counts[12] = {0}; }
 extern "C" int artic_path_counts(int64_t* h_out, int32_t reset) {
   ARTIC_CHECK_ARG(h_out != nullptr, "null pointer");
-  for (int i = 0; i < 10; ++i) h_out[i] = artic::g_path_counts[i];
-  if (reset) for (int i = 0; i < 10; ++i) artic::g_path_counts[i] = 0;
+  for (int i = 0; i < 12; ++i) h_out[i] = artic::g_path_counts[i];
+  if (reset) for (int i = 0; i < 12; ++i) artic::g_path_counts[i] = 0;
   return ARTIC_OK;
 }
 extern "C" int artic_version(void) { return 100; }

@@ -562,6 +562,38 @@ def planner_objective(sm_time_pct: int):
         lib.artic_debug_set(15, 0)
 
 
+#: ARTIC_FUSE_RES=0 turns the fused residual unit off (artic_resunit_fwd: conv1 -> LeakyReLU -> conv2 -> + x of the
+#: narrow MRF stages in one launch; bf16 mode, C = 32 / 64)
+_FUSE_RES = _os.environ.get("ARTIC_FUSE_RES", "1") != "0"
+
+
+def resunit_fusable(c1: "ConvLayer", c2: "ConvLayer") -> bool:
+    """Both convs of a residual unit fit the fused kernel: bf16, C -> C with C in {32, 64}, same odd kernel size <= 11,
+    conv2 undilated, and the two weights resident in shared memory next to the tiles (C = 64: k <= 7)."""
+    s1, s2 = c1.spec, c2.spec
+    C = s1.cin
+    return (_FUSE_RES and c1.in_code == BF16 and c1.out_code == BF16 and c2.in_code == BF16 and c2.out_code == BF16
+            and s1.kind == s2.kind == "conv" and s1.cout == C and s2.cin == C and s2.cout == C and C in (32, 64)
+            and s1.groups == s2.groups == 1 and s1.stride == s2.stride == 1 and s1.k == s2.k and s1.k % 2 == 1 and s1.k <= 11
+            and s2.dilation == 1 and s1.padding == (s1.k - 1) // 2 * s1.dilation and s2.padding == (s2.k - 1) // 2
+            and (s1.k // 2) * s1.dilation <= 32 and (C == 32 or s1.k <= 7) and c1.kcig == C and c2.kcig == C)
+
+
+def resunit_forward(c1: "ConvLayer", c2: "ConvLayer", ax: SeqT, x: SeqT, at: Optional[SeqT], xn: Optional[SeqT],
+                    axn: Optional[SeqT], slope: float):
+    """One launch for at = lrelu(conv1(ax) + b1), xn = conv2(at) + b2 + x, axn = lrelu(xn) (any of at / xn / axn may be
+    None, but one of xn / axn is required)."""
+    assert ax.n_inner == 1 and ax.s_row == ax.C and ax.s_outer == ax.L * ax.C, "plain (N, L, C) batches only"
+    p = _lib.ResUnit()
+    p.AX, p.XRES, p.W1t, p.W2t = ptr(ax.t), ptr(x.t), ptr(c1.Wb), ptr(c2.Wb)
+    p.b1, p.b2 = ptr(c1.b), ptr(c2.b)
+    p.AT = ptr(at.t) if at is not None else None
+    p.Y = ptr(xn.t) if xn is not None else None
+    p.Y2 = ptr(axn.t) if axn is not None else None
+    p.N, p.L, p.C, p.k, p.dil, p.slope = ax.N, ax.L, ax.C, c1.spec.k, c1.spec.dilation, slope
+    call("artic_resunit_fwd", p)
+
+
 _G_OBJECTIVE = int(_os.environ.get("ARTIC_G_OBJECTIVE", "60"))   # measured: 100 -> 12.93, 60 -> 12.82, 30 -> 13.15 ms
 _D_OBJECTIVE = int(_os.environ.get("ARTIC_D_OBJECTIVE", "100"))  # the discriminator's eight chains: see profiles/r2_objective_sweep.log
 
@@ -690,11 +722,18 @@ class GeneratorEngine:
                 pairs = []
                 nd = len(self.dilations[j])
                 for di in range(nd):
-                    at = u.like()
-                    L[f"blocks.{b}.convs1.{di}.1"].forward(ax, Y2=at, act=ACT_LRELU, act_slope=slope)
+                    c1, c2 = L[f"blocks.{b}.convs1.{di}.1"], L[f"blocks.{b}.convs2.{di}.1"]
                     xn = u.like()
                     axn = u.like() if di < nd - 1 else None
-                    L[f"blocks.{b}.convs2.{di}.1"].forward(at, Y=xn, Y2=axn, res=x, act=ACT_LRELU, act_slope=slope)
+                    if resunit_fusable(c1, c2):
+                        # narrow stages: both convs in one launch, the intermediate stays on chip (it is written out
+                        # only when the backward will need it)
+                        at = u.like() if save else None
+                        resunit_forward(c1, c2, ax, x, at, xn, axn, slope)
+                    else:
+                        at = u.like()
+                        c1.forward(ax, Y2=at, act=ACT_LRELU, act_slope=slope)
+                        c2.forward(at, Y=xn, Y2=axn, res=x, act=ACT_LRELU, act_slope=slope)
                     pairs.append((ax, at))
                     x, ax = xn, axn
                 return x, pairs

@@ -119,6 +119,29 @@ int artic_tapconv(const artic_tapconv_t* p, void* stream);
 int artic_tapconv_multi(const artic_tapconv_t* ps, int32_t n, void* stream);
 
 /*
+ * Fused residual unit of an MRF block, forward (layers/residual_block.py:207-222, one (convs1[i], convs2[i]) pair):
+ *     at  = lrelu(conv1(ax) + b1)      conv1: C -> C, kernel k, dilation dil, "same" padding
+ *     xn  = conv2(at) + b2 + xres      conv2: C -> C, kernel k, dilation 1
+ *     axn = lrelu(xn)
+ * in ONE tcgen05 launch for the narrow stages (bf16, C = 32 or 64, odd k <= 11, both weights resident in shared memory):
+ * the intermediate goes TMEM -> registers -> shared memory and feeds the second GEMM without an HBM round trip.
+ * All tensors are plain (N, L, C) channels-last bf16 batches.  AX = lrelu(x) (the previous layer's activated output),
+ * XRES = x.  AT (optional) receives `at` (the backward needs it), Y (optional) xn, Y2 (optional) axn.
+ * W1t / W2t: the layers' transposed prepared weights [k][1][C_out][C_in] (artic_weights_prep `out_b`).
+ * Returns ARTIC_ENOSUP when the shape is not covered (the caller then issues two artic_tapconv calls).
+ */
+typedef struct {
+  const void* AX; const void* XRES; const void* W1t; const void* W2t;
+  const float* b1; const float* b2;
+  void* AT; void* Y; void* Y2;
+  int32_t N, L, C, k, dil;
+  float slope;
+  int32_t reserved_[2];
+} artic_resunit_t;
+
+int artic_resunit_fwd(const artic_resunit_t* p, void* stream);
+
+/*
  * Weight gradient of the same contraction (cuDNN wgrad):
  *   dW[widx[t]][g][ci][co] += sum_n sum_q X[n, q*si+off[t], g*Cig+ci] * dY[n, q*so+yoff[t], g*Cog+co]
  * dW is fp32 [K][G][Cig][Cog] and is ACCUMULATED into (zero it first).
@@ -216,9 +239,9 @@ int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64_t n, int32
 int artic_split(const float* src, void* hi, int64_t plane, int64_t n, void* stream);
 
 /* Host-side counters of which kernel family took each contraction since the last reset (tests assert that every
- * eligible layer runs on the tensor cores): out[0..9] = conv {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic,
+ * eligible layer runs on the tensor cores): out[0..11] = conv {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic,
  * channel-1 kernels}, wgrad {tcgen05 bf16, tcgen05 bf16x3, CUDA-core generic, channel-1 kernels}, tcgen05 weight
- * gradients that also produced the bias gradient, tcgen05 conv launches with cluster weight multicast.
+ * gradients that also produced the bias gradient, tcgen05 conv launches with cluster weight multicast, fused residual units (artic_resunit_fwd: two convs each), reserved.
  * Counted when a launch is ENQUEUED (graph replays do not count).  reset != 0 clears them after the read. */
 int artic_path_counts(int64_t* h_out, int32_t reset);
 

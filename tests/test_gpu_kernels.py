@@ -414,6 +414,55 @@ def test_logit_conv_data_gradient_channel1_kernel(k, pad, ni):
     assert rel_err(got, want) < 6e-3
 
 
+@pytest.mark.parametrize("C,k,dil", [(32, 3, 1), (32, 7, 3), (32, 11, 5), (64, 3, 5), (64, 7, 1), (64, 7, 5), (32, 11, 1)])
+@pytest.mark.parametrize("N,L", [(3, 500), (2, 131), (5, 118)])
+def test_fused_residual_unit(C, k, dil, N, L):
+    """artic_resunit_fwd (conv1 dilated -> LeakyReLU -> conv2 -> + x, one tcgen05 launch, intermediate in shared memory)
+    against torch on the same bf16 operands: the intermediate `at`, xn and axn; tile edges (L not a multiple of the
+    118..126-row tiles), zero padding of both convs at the sequence ends."""
+    torch.manual_seed(C + k + dil)
+    slope = 0.1
+    specs = [ConvSpec(kind="conv", cin=C, cout=C, k=k, dilation=dil, padding=(k - 1) // 2 * dil),
+             ConvSpec(kind="conv", cin=C, cout=C, k=k, padding=(k - 1) // 2)]
+    ws = [torch.randn(sp.weight_shape(), dtype=torch.float64) / math.sqrt(C * k) for sp in specs]
+    bs = [torch.randn(C, dtype=torch.float64) * 0.1 for _ in specs]
+    x = _bf16_round(torch.randn(N, C, L))
+    ax = _bf16_round(F.leaky_relu(x, slope))
+    at = _bf16_round(F.leaky_relu(F.conv1d(ax, _bf16_round(ws[0]), bs[0].float().double(), padding=specs[0].padding, dilation=dil), slope))
+    xn = F.conv1d(at, _bf16_round(ws[1]), bs[1].float().double(), padding=specs[1].padding) + x
+    lays = []
+    for i, sp in enumerate(specs):
+        lay = ConvLayer(sp, f"l{i}", BF16, BF16)
+        lay.bind({f"l{i}.weight": ws[i].float().to(DEV).contiguous(), f"l{i}.bias": bs[i].float().to(DEV)})
+        lay.prep()
+        lays.append(lay)
+    cl = lambda t: t.permute(0, 2, 1).contiguous().to(DEV, torch.bfloat16)
+    AX, X = cl(ax), cl(x)
+    AT, Y, Y2 = (torch.full((N, L, C), float("nan"), dtype=torch.bfloat16, device=DEV) for _ in range(3))
+    p = _lib.ResUnit()
+    p.AX, p.XRES, p.W1t, p.W2t = ptr(AX), ptr(X), ptr(lays[0].Wb), ptr(lays[1].Wb)
+    p.b1, p.b2 = ptr(lays[0].b), ptr(lays[1].b)
+    p.AT, p.Y, p.Y2 = ptr(AT), ptr(Y), ptr(Y2)
+    p.N, p.L, p.C, p.k, p.dil, p.slope = N, L, C, k, dil, slope
+    call("artic_resunit_fwd", p)
+    torch.cuda.synchronize()
+    back = lambda t: t.float().cpu().permute(0, 2, 1)
+    assert torch.isfinite(AT.float()).all() and torch.isfinite(Y.float()).all() and torch.isfinite(Y2.float()).all()
+    assert rel_err(back(AT), at) < 6e-3
+    assert rel_err(back(Y), xn) < 6e-3
+    assert rel_err(back(Y2), F.leaky_relu(xn, slope)) < 6e-3
+
+
+def test_fused_residual_unit_refuses_what_does_not_fit():
+    """C = 64 with k = 11: the two weights (176 KB) do not fit beside the tiles -> ARTIC_ENOSUP, the engine falls back."""
+    p = _lib.ResUnit()
+    t = torch.zeros(64 * 64 * 11, dtype=torch.bfloat16, device=DEV)
+    p.AX = p.XRES = p.W1t = p.W2t = p.Y = ptr(t)
+    p.N, p.L, p.C, p.k, p.dil, p.slope = 1, 64, 64, 11, 1, 0.1
+    with pytest.raises(_lib.ArticError):
+        call("artic_resunit_fwd", p)
+
+
 def _bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float64)
 
