@@ -55,7 +55,7 @@ class ResUnit(C.Structure):
     _fields_ = [("AX", C.c_void_p), ("XRES", C.c_void_p), ("W1t", C.c_void_p), ("W2t", C.c_void_p),
                 ("b1", C.c_void_p), ("b2", C.c_void_p), ("AT", C.c_void_p), ("Y", C.c_void_p), ("Y2", C.c_void_p),
                 ("N", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("k", C.c_int32), ("dil", C.c_int32),
-                ("slope", C.c_float), ("reserved_", C.c_int32 * 2)]
+                ("slope", C.c_float), ("mode", C.c_int32), ("reserved_", C.c_int32), ("M1", C.c_void_p), ("M2", C.c_void_p)]
 
 
 class AdamHyper(C.Structure):

@@ -12,6 +12,9 @@
 // resident in shared memory for the CTA's lifetime; the input tile (128 + 2 p1 rows, p1 = p2 * dilation) is staged once
 // by TMA (zero fill outside the sequence = conv1's padding) and every tap reads it through a row-shifted descriptor.
 // Intermediate rows outside [0, L) are forced to zero (conv2's padding).
+// mode 1 is the matching DATA GRADIENT of the unit, the same two-GEMM structure with the convolutions transposed
+// (taps reversed, conv2's first):  dt = conv2^T(gx) * lrelu'(at);  gn = conv1^T(dt) * lrelu'(ax) + gx  — `dt` is
+// written out for conv1's weight gradient.  Here the SECOND GEMM is the dilated one, so R = 128 - (k - 1) * dilation.
 // Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (stage 1: TMEM -> at; stage 2: TMEM -> xn / axn).
 // The MMA warp runs GEMM1 of tile i+1 before GEMM2 of tile i, so the tensor pipe has work while the epilogue warps
 // convert tile i's intermediate; accumulators and the intermediate buffer are double-buffered.
@@ -24,7 +27,8 @@ constexpr int RU_THREADS = 320;
 constexpr int RU_MAX_AS = 4;
 
 struct RUPlan {
-  int32_t C, k, dil, p1, p2, R;
+  int32_t C, k, dil1, dil2, p1, p2, R;   // dil1 / p1: first GEMM, dil2 / p2: second GEMM
+  int32_t mode, rev;                     // mode 1 = data gradient (mask epilogues); rev = taps of both weights reversed
   int32_t row_bytes, layout_type;
   int32_t tiles_per_seq, total_tiles;
   int32_t nbox, a1_stage_bytes, n_as;
@@ -36,6 +40,8 @@ struct RUPlan {
 };
 
 struct RUArgs {
+  const __nv_bfloat16* m1;      // mode 1: activation whose sign masks the intermediate (at)
+  const __nv_bfloat16* m2;      // mode 1: activation whose sign masks the output (ax)
   const __nv_bfloat16* xres;
   const float* b1;
   const float* b2;
@@ -92,8 +98,8 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
     if (lane == 0) {
       pdl_wait();
       mbar_expect_tx(&w_full, (uint32_t)(2 * k) * (uint32_t)(C * pl.row_bytes));
-      for (int t = 0; t < k; ++t) tma_load_2d(w_base + (uint32_t)t * pl.w_tile_bytes, &map_w1, &w_full, 0, t * C);
-      for (int t = 0; t < k; ++t) tma_load_2d(w_base + (uint32_t)(k + t) * pl.w_tile_bytes, &map_w2, &w_full, 0, t * C);
+      for (int t = 0; t < k; ++t) tma_load_2d(w_base + (uint32_t)t * pl.w_tile_bytes, &map_w1, &w_full, 0, (pl.rev ? k - 1 - t : t) * C);
+      for (int t = 0; t < k; ++t) tma_load_2d(w_base + (uint32_t)(k + t) * pl.w_tile_bytes, &map_w2, &w_full, 0, (pl.rev ? k - 1 - t : t) * C);
       PipeState as(pl.n_as);
       for (int tile = cta; tile < pl.total_tiles; tile += ncta) {
         const int n = tile / pl.tiles_per_seq;
@@ -128,7 +134,7 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
       const uint32_t d = tmem_base + (uint32_t)(2 * C) + (uint32_t)s * C;
       uint32_t accum = 0;
       for (int t = 0; t < k; ++t) {
-        const uint32_t at16 = a16 + (uint32_t)t * rb16;
+        const uint32_t at16 = a16 + (uint32_t)(t * pl.dil2) * rb16;
         const uint32_t b16 = desc_lo | ((w16 + (uint32_t)(k + t) * wt16) & 0x3fffu);
         for (int ks = 0; ks < ksteps; ++ks) {
           if (leader) umma_bf16(d, ((uint64_t)desc_hi << 32) | (at16 + 2 * ks), ((uint64_t)desc_hi << 32) | (b16 + 2 * ks), idesc, accum);
@@ -148,7 +154,7 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
       const uint32_t d = tmem_base + (uint32_t)s * C;
       uint32_t accum = 0;
       for (int t = 0; t < k; ++t) {
-        const uint32_t at16 = a16 + (uint32_t)(t * pl.dil) * rb16;
+        const uint32_t at16 = a16 + (uint32_t)(t * pl.dil1) * rb16;
         const uint32_t b16 = desc_lo | ((w16 + (uint32_t)t * wt16) & 0x3fffu);
         for (int ks = 0; ks < ksteps; ++ks) {
           if (leader) umma_bf16(d, ((uint64_t)desc_hi << 32) | (at16 + 2 * ks), ((uint64_t)desc_hi << 32) | (b16 + 2 * ks), idesc, accum);
@@ -189,14 +195,24 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
         uint8_t* row = a2_ptr + (size_t)s * pl.a2_bytes + (size_t)r * pl.row_bytes;
         const bool keep = ar.at != nullptr && inside && r >= pl.p2 && r < pl.p2 + pl.R;
         TO* g = keep ? ar.at + (int64_t)n * pl.s_outer + (int64_t)gpos * C + c0 : nullptr;
+        const TO* mk = (pl.mode == 1 && inside) ? ar.m1 + (int64_t)n * pl.s_outer + (int64_t)gpos * C + c0 : nullptr;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float v[8];
+          if (pl.mode == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x = __uint_as_float(acc_r[8 * u + j]) + bias_s[0][c0 + 8 * u + j];
-            x = x > 0.f ? x : pl.slope * x;
-            v[j] = inside ? x : 0.f;                   // conv2 sees zero padding outside the sequence
+            for (int j = 0; j < 8; ++j) {
+              float x = __uint_as_float(acc_r[8 * u + j]) + bias_s[0][c0 + 8 * u + j];
+              x = x > 0.f ? x : pl.slope * x;
+              v[j] = inside ? x : 0.f;                   // conv2 sees zero padding outside the sequence
+            }
+          } else {
+            float m[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = 1.f;
+            if (mk != nullptr) unpack8<TO>(__ldg(reinterpret_cast<const uint4*>(mk + 8 * u)), m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = inside ? __uint_as_float(acc_r[8 * u + j]) * (m[j] > 0.f ? 1.f : pl.slope) : 0.f;
           }
           const uint4 pk = pack8(v);
           *reinterpret_cast<uint4*>(row + ((((uint32_t)(c0 >> 3) + u) ^ swz) << 4)) = pk;
@@ -215,9 +231,12 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
       const int gpos = q0 + r;
       const bool valid = r < pl.R && gpos < pl.L && has_ch;
       const int64_t o = (int64_t)n * pl.s_outer + (int64_t)gpos * C + c0;
-      uint4 q_rs[4];
+      uint4 q_rs[4], q_mk[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) q_rs[u] = valid ? __ldg(reinterpret_cast<const uint4*>(ar.xres + o + 8 * u)) : make_uint4(0, 0, 0, 0);
+      for (int u = 0; u < 4; ++u) {
+        q_rs[u] = valid ? __ldg(reinterpret_cast<const uint4*>(ar.xres + o + 8 * u)) : make_uint4(0, 0, 0, 0);
+        q_mk[u] = (valid && pl.mode == 1) ? __ldg(reinterpret_cast<const uint4*>(ar.m2 + o + 8 * u)) : make_uint4(0, 0, 0, 0);
+      }
       mbar_wait(&acc2_full[s], (uint32_t)ph);
       tc_fence_after();
       if (has_ch) {
@@ -229,8 +248,15 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
           for (int u = 0; u < 4; ++u) {
             float v[8], res[8];
             unpack8<TO>(q_rs[u], res);
+            if (pl.mode == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc_r[8 * u + j]) + bias_s[1][c0 + 8 * u + j] + res[j];
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc_r[8 * u + j]) + bias_s[1][c0 + 8 * u + j] + res[j];
+            } else {
+              float m[8];
+              unpack8<TO>(q_mk[u], m);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc_r[8 * u + j]) * (m[j] > 0.f ? 1.f : pl.slope) + res[j];
+            }
             if (ar.y != nullptr) *reinterpret_cast<uint4*>(ar.y + o + 8 * u) = pack8(v);
             if (ar.y2 != nullptr) {
 #pragma unroll
@@ -289,10 +315,11 @@ extern "C" int artic_resunit_fwd(const artic_resunit_t* pp, void* stream) {
   ARTIC_CHECK_ARG(pp != nullptr, "null params");
   const artic_resunit_t& p = *pp;
   ARTIC_CHECK_ARG(p.AX && p.XRES && p.W1t && p.W2t && (p.Y || p.Y2), "AX, XRES, W1t, W2t and one of Y / Y2 are required");
+  ARTIC_CHECK_ARG(p.mode == 0 || (p.mode == 1 && p.M1 && p.M2), "mode 1 (data gradient) needs the two mask tensors");
   ARTIC_CHECK_ARG(p.N >= 0 && p.L >= 1, "bad dims");
   if (p.C != 32 && p.C != 64) { set_error("artic_resunit_fwd: C must be 32 or 64"); return ARTIC_ENOSUP; }
   if (p.k < 1 || p.k > 11 || !(p.k & 1) || p.dil < 1 || (p.k / 2) * p.dil > 32) { set_error("artic_resunit_fwd: unsupported kernel size / dilation"); return ARTIC_ENOSUP; }
-  const void* ptrs[] = {p.AX, p.XRES, p.W1t, p.W2t, p.AT, p.Y, p.Y2};
+  const void* ptrs[] = {p.AX, p.XRES, p.W1t, p.W2t, p.AT, p.Y, p.Y2, p.M1, p.M2};
   for (const void* q : ptrs)
     if (q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15)) { set_error("artic_resunit_fwd: 16-byte alignment required"); return ARTIC_ENOSUP; }
   if (p.N == 0) return ARTIC_OK;
@@ -301,10 +328,14 @@ extern "C" int artic_resunit_fwd(const artic_resunit_t* pp, void* stream) {
 
   tc::RUPlan pl;
   memset(&pl, 0, sizeof(pl));
-  pl.C = p.C; pl.k = p.k; pl.dil = p.dil;
-  pl.p2 = p.k / 2;
-  pl.p1 = pl.p2 * p.dil;
-  pl.R = 128 - (p.k - 1);
+  pl.C = p.C; pl.k = p.k;
+  pl.mode = p.mode;
+  pl.rev = p.mode == 1 ? 1 : 0;                            // transposed convolutions: taps in reverse order
+  pl.dil1 = p.mode == 0 ? p.dil : 1;                       // forward: conv1 (dilated) first; data gradient: conv2^T first
+  pl.dil2 = p.mode == 0 ? 1 : p.dil;
+  pl.p1 = (p.k / 2) * pl.dil1;
+  pl.p2 = (p.k / 2) * pl.dil2;
+  pl.R = 128 - 2 * pl.p2;
   pl.row_bytes = p.C * 2;
   pl.layout_type = pl.row_bytes == 128 ? 2 : 4;
   pl.tiles_per_seq = (p.L + pl.R - 1) / pl.R;
@@ -314,7 +345,7 @@ extern "C" int artic_resunit_fwd(const artic_resunit_t* pp, void* stream) {
   pl.nbox = (128 + 2 * pl.p1 + 63) / 64;
   pl.a1_stage_bytes = pl.nbox * 64 * pl.row_bytes;
   pl.w_tile_bytes = ((p.C * pl.row_bytes + 1023) / 1024) * 1024;
-  pl.a2_bytes = ((144 * pl.row_bytes + 1023) / 1024) * 1024;
+  pl.a2_bytes = (((128 + 2 * pl.p2 + 8) * pl.row_bytes + 1023) / 1024) * 1024;   // rows >= 128 only feed discarded outputs
   pl.tmem_cols = 4 * p.C;                                  // two accumulators x two stages (128 or 256 columns)
   pl.N = p.N; pl.L = p.L; pl.s_outer = (int64_t)p.L * p.C;
   pl.slope = p.slope;
@@ -346,6 +377,8 @@ extern "C" int artic_resunit_fwd(const artic_resunit_t* pp, void* stream) {
     if (rc != CUDA_SUCCESS) { set_error("artic_resunit_fwd: cuTensorMapEncodeTiled(W) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   }
   tc::RUArgs ar;
+  ar.m1 = reinterpret_cast<const __nv_bfloat16*>(p.M1);
+  ar.m2 = reinterpret_cast<const __nv_bfloat16*>(p.M2);
   ar.xres = reinterpret_cast<const __nv_bfloat16*>(p.XRES);
   ar.b1 = p.b1;
   ar.b2 = p.b2;
@@ -367,7 +400,7 @@ extern "C" int artic_resunit_fwd(const artic_resunit_t* pp, void* stream) {
   cudaError_t le = cudaLaunchKernelEx(&cfg, tc::resunit_tc_kernel, pl, ar, map_x, map_w1, map_w2);
   if (le == cudaSuccess) le = cudaGetLastError();
   if (le != cudaSuccess) {
-    set_error("artic_resunit_fwd: launch failed: %s (grid %d, smem %d, C %d k %d)", cudaGetErrorString(le), grid, smem_bytes, p.C, p.k);
+    set_error("artic_resunit_fwd: launch failed: %s (grid %d, smem %d, C %d k %d mode %d)", cudaGetErrorString(le), grid, smem_bytes, p.C, p.k, p.mode);
     return ARTIC_ECUDA;
   }
   ++g_path_counts[10];     // fused residual units (two convs each)

@@ -565,6 +565,7 @@ def planner_objective(sm_time_pct: int):
 #: ARTIC_FUSE_RES=0 turns the fused residual unit off (artic_resunit_fwd: conv1 -> LeakyReLU -> conv2 -> + x of the
 #: narrow MRF stages in one launch; bf16 mode, C = 32 / 64)
 _FUSE_RES = _os.environ.get("ARTIC_FUSE_RES", "1") != "0"
+_FUSE_RES_BWD = _os.environ.get("ARTIC_FUSE_RES_BWD", "1") != "0"
 
 
 def resunit_fusable(c1: "ConvLayer", c2: "ConvLayer") -> bool:
@@ -591,6 +592,18 @@ def resunit_forward(c1: "ConvLayer", c2: "ConvLayer", ax: SeqT, x: SeqT, at: Opt
     p.Y = ptr(xn.t) if xn is not None else None
     p.Y2 = ptr(axn.t) if axn is not None else None
     p.N, p.L, p.C, p.k, p.dil, p.slope = ax.N, ax.L, ax.C, c1.spec.k, c1.spec.dilation, slope
+    call("artic_resunit_fwd", p)
+
+
+def resunit_backward(c1: "ConvLayer", c2: "ConvLayer", gx: SeqT, at: SeqT, ax: SeqT, dt: SeqT, gn: SeqT, slope: float):
+    """Data gradient of the unit in one launch: dt = conv2^T(gx) * lrelu'(at) (written out for conv1's weight
+    gradient), gn = conv1^T(dt) * lrelu'(ax) + gx."""
+    p = _lib.ResUnit()
+    p.AX = p.XRES = ptr(gx.t)
+    p.W1t, p.W2t = ptr(c2.Wf), ptr(c1.Wf)
+    p.M1, p.M2 = ptr(at.t), ptr(ax.t)
+    p.AT, p.Y = ptr(dt.t), ptr(gn.t)
+    p.N, p.L, p.C, p.k, p.dil, p.slope, p.mode = gx.N, gx.L, gx.C, c1.spec.k, c1.spec.dilation, slope, 1
     call("artic_resunit_fwd", p)
 
 
@@ -826,10 +839,14 @@ class GeneratorEngine:
                     c2, c1 = L[f"blocks.{b}.convs2.{di}.1"], L[f"blocks.{b}.convs1.{di}.1"]
                     wq.run(lambda c2=c2, at=at, gx=gx: c2.wgrad(at, gx, grads), at, gx)
                     dt = at.like()
-                    c2.dgrad(gx, dX=dt, mask=at, mask_slope=slope)
-                    wq.run(lambda c1=c1, ax=ax, dt=dt: c1.wgrad(ax, dt, grads), ax, dt)
                     gn = ax.like()
-                    c1.dgrad(dt, dX=gn, mask=ax, mask_slope=slope, res=gx)
+                    if _FUSE_RES_BWD and resunit_fusable(c1, c2):
+                        resunit_backward(c1, c2, gx, at, ax, dt, gn, slope)      # both data gradients, one launch
+                        wq.run(lambda c1=c1, ax=ax, dt=dt: c1.wgrad(ax, dt, grads), ax, dt)
+                    else:
+                        c2.dgrad(gx, dX=dt, mask=at, mask_slope=slope)
+                        wq.run(lambda c1=c1, ax=ax, dt=dt: c1.wgrad(ax, dt, grads), ax, dt)
+                        c1.dgrad(dt, dX=gn, mask=ax, mask_slope=slope, res=gx)
                     gx = gn
                 return gx, wq        # gradient wrt the block input (pre-activation u); queue joined by the caller
 

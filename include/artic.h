@@ -129,6 +129,12 @@ int artic_tapconv_multi(const artic_tapconv_t* ps, int32_t n, void* stream);
  * XRES = x.  AT (optional) receives `at` (the backward needs it), Y (optional) xn, Y2 (optional) axn.
  * W1t / W2t: the layers' transposed prepared weights [k][1][C_out][C_in] (artic_weights_prep `out_b`).
  * Returns ARTIC_ENOSUP when the shape is not covered (the caller then issues two artic_tapconv calls).
+ *
+ * mode = 1: the DATA GRADIENT of the same unit, also one launch (the two transposed convolutions, conv2's first):
+ *     dt = conv2^T(gx) * lrelu'(at)          gn = conv1^T(dt) * lrelu'(ax) + gx
+ * with AX = XRES = gx (gradient wrt xn), M1 = at, M2 = ax (the saved activations whose signs are the LeakyReLU masks),
+ * W1t = conv2's weight and W2t = conv1's weight in the FORWARD prepared layout [k][1][C_in][C_out] (`out_f`), AT
+ * receives dt (conv1's weight gradient needs it), Y receives gn; b1 / b2 / Y2 are unused.
  */
 typedef struct {
   const void* AX; const void* XRES; const void* W1t; const void* W2t;
@@ -136,7 +142,8 @@ typedef struct {
   void* AT; void* Y; void* Y2;
   int32_t N, L, C, k, dil;
   float slope;
-  int32_t reserved_[2];
+  int32_t mode, reserved_;
+  const void* M1; const void* M2;
 } artic_resunit_t;
 
 int artic_resunit_fwd(const artic_resunit_t* p, void* stream);

@@ -453,6 +453,43 @@ def test_fused_residual_unit(C, k, dil, N, L):
     assert rel_err(back(Y2), F.leaky_relu(xn, slope)) < 6e-3
 
 
+@pytest.mark.parametrize("C,k,dil", [(32, 3, 1), (32, 7, 3), (32, 11, 5), (64, 3, 5), (64, 7, 1), (64, 7, 5)])
+@pytest.mark.parametrize("N,L", [(3, 500), (2, 131), (4, 78)])
+def test_fused_residual_unit_data_gradient(C, k, dil, N, L):
+    """artic_resunit_fwd mode 1: dt = conv2^T(gx) * lrelu'(at), gn = conv1^T(dt) * lrelu'(ax) + gx against torch autograd
+    of the same unit on the same bf16 operands (dt is bf16-rounded before the second transposed conv, as in the kernel)."""
+    torch.manual_seed(7 * C + k + dil)
+    slope = 0.1
+    specs = [ConvSpec(kind="conv", cin=C, cout=C, k=k, dilation=dil, padding=(k - 1) // 2 * dil),
+             ConvSpec(kind="conv", cin=C, cout=C, k=k, padding=(k - 1) // 2)]
+    ws = [_bf16_round(torch.randn(sp.weight_shape(), dtype=torch.float64) / math.sqrt(C * k)) for sp in specs]
+    ax = _bf16_round(torch.randn(N, C, L))                   # saved activations: only their signs matter here
+    at = _bf16_round(torch.randn(N, C, L))
+    gx = _bf16_round(torch.randn(N, C, L))
+    dt = _bf16_round(F.conv_transpose1d(gx, ws[1], padding=specs[1].padding) * torch.where(at > 0, 1.0, slope))
+    gn = F.conv_transpose1d(dt, ws[0], padding=specs[0].padding, dilation=dil) * torch.where(ax > 0, 1.0, slope) + gx
+    lays = []
+    for i, sp in enumerate(specs):
+        lay = ConvLayer(sp, f"l{i}", BF16, BF16)
+        lay.bind({f"l{i}.weight": ws[i].float().to(DEV).contiguous()})
+        lay.prep()
+        lays.append(lay)
+    cl = lambda t: t.permute(0, 2, 1).contiguous().to(DEV, torch.bfloat16)
+    GX, AT, AX = cl(gx), cl(at), cl(ax)
+    DT, GN = (torch.full((N, L, C), float("nan"), dtype=torch.bfloat16, device=DEV) for _ in range(2))
+    p = _lib.ResUnit()
+    p.AX = p.XRES = ptr(GX)
+    p.W1t, p.W2t = ptr(lays[1].Wf), ptr(lays[0].Wf)
+    p.M1, p.M2, p.AT, p.Y = ptr(AT), ptr(AX), ptr(DT), ptr(GN)
+    p.N, p.L, p.C, p.k, p.dil, p.slope, p.mode = N, L, C, k, dil, slope, 1
+    call("artic_resunit_fwd", p)
+    torch.cuda.synchronize()
+    back = lambda t: t.float().cpu().permute(0, 2, 1)
+    assert torch.isfinite(DT.float()).all() and torch.isfinite(GN.float()).all()
+    assert rel_err(back(DT), dt) < 6e-3
+    assert rel_err(back(GN), gn) < 6e-3
+
+
 def test_fused_residual_unit_refuses_what_does_not_fit():
     """C = 64 with k = 11: the two weights (176 KB) do not fit beside the tiles -> ARTIC_ENOSUP, the engine falls back."""
     p = _lib.ResUnit()
