@@ -26,7 +26,7 @@ def main(path, out):
             a["us"] += v
     res = {k: {"launches": len(v["launches"]), "dram_bytes_per_step": v["dram_bytes"], "us_per_step": v["us"]}
            for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["us"])}
-    tc = [v for k, v in res.items() if "tapconv_tc_kernel" in k or "tapwgrad_tc_kernel" in k]
+    tc = [v for k, v in res.items() if "tapconv_tc_kernel" in k or "tapwgrad_tc_kernel" in k or "resunit_tc_kernel" in k]
     summary = {"source": path, "tensor_core_kernels": {"launches": sum(v["launches"] for v in tc),
                                                         "dram_bytes_per_step": sum(v["dram_bytes_per_step"] for v in tc),
                                                         "us_per_step_serialised": sum(v["us_per_step"] for v in tc)},
