@@ -58,6 +58,12 @@ class ResUnit(C.Structure):
                 ("slope", C.c_float), ("mode", C.c_int32), ("reserved_", C.c_int32), ("M1", C.c_void_p), ("M2", C.c_void_p)]
 
 
+class Mlp(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("W", C.c_void_p * 8), ("bias", C.c_void_p * 8), ("act0", C.c_void_p),
+                ("outs", C.c_void_p * 8), ("dims", C.c_int32 * 9), ("B", C.c_int32), ("n_layers", C.c_int32),
+                ("dtype", C.c_int32), ("slope", C.c_float)]
+
+
 class AdamHyper(C.Structure):
     _fields_ = [("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("gamma", C.c_float), ("step", C.c_int32), ("n_milestones", C.c_int32),
@@ -94,6 +100,7 @@ SIGNATURES = {
     "artic_trace_buffer": (C.c_int, [_p, C.c_longlong]),
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
     "artic_tapconv_multi": (C.c_int, [C.POINTER(TapConv), _i32, _p]),
+    "artic_mlp_fwd": (C.c_int, [C.POINTER(Mlp), _p]),
     "artic_resunit_fwd": (C.c_int, [C.POINTER(ResUnit), _p]),
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
     "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),

@@ -114,6 +114,53 @@ __global__ void cut_windows_kernel(const float* __restrict__ audio, const int64_
   }
 }
 
+// PastFCEncoder (layers/pytorch_layers.py:426-460) in ONE launch: Linear -> LeakyReLU x (n - 1) -> Linear for one batch item
+// per CTA.  Five dependent GEMV-sized layers (0.36 M weights) are pure launch latency as separate launches (5 x ~13 us at
+// the head of every generator forward and of every decode chunk); here the activations stay in shared memory, the
+// weights stream from L2 with coalesced reads (threads along the output features, the input features split over
+// 1024 / cout thread groups).  Every layer's (storage-rounded) output is also written out: the backward needs them.
+__device__ __forceinline__ float mlp_f(float v) { return v; }
+__device__ __forceinline__ float mlp_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T mlp_t(float v);
+template <> __device__ __forceinline__ float mlp_t<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 mlp_t<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+constexpr int MLP_THREADS = 1024;
+constexpr int MLP_MAX_DIM = 1024;
+template <typename T>
+__global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(const __grid_constant__ artic_mlp_t p) {
+  __shared__ float h[MLP_MAX_DIM];
+  __shared__ float part[MLP_THREADS];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < p.dims[0]; i += MLP_THREADS) {
+    const T v = mlp_t<T>(__ldg(p.in + (int64_t)b * p.dims[0] + i));   // the input enters in the storage type, as the tape keeps it
+    if (p.act0 != nullptr) reinterpret_cast<T*>(p.act0)[(int64_t)b * p.dims[0] + i] = v;
+    h[i] = mlp_f(v);
+  }
+  __syncthreads();
+  for (int l = 0; l < p.n_layers; ++l) {
+    const int cin = p.dims[l], cout = p.dims[l + 1];
+    const T* __restrict__ W = reinterpret_cast<const T*>(p.W[l]);            // prepared layout [cin][cout]
+    const int groups = MLP_THREADS / cout;                                    // cout divides 1024 (checked by the host)
+    const int j = threadIdx.x % cout, g = threadIdx.x / cout;
+    const int per = (cin + groups - 1) / groups;
+    const int i0 = g * per, i1 = min(cin, i0 + per);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = i0; i < i1; ++i) acc = fmaf(h[i], ld_f(W + (int64_t)i * cout + j), acc);
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < cout) {
+      float v = p.bias[l] != nullptr ? __ldg(p.bias[l] + threadIdx.x) : 0.f;
+      for (int q = 0; q < groups; ++q) v += part[q * cout + threadIdx.x];
+      if (l + 1 < p.n_layers) v = v > 0.f ? v : p.slope * v;
+      const T o = mlp_t<T>(v);
+      if (p.outs[l] != nullptr) reinterpret_cast<T*>(p.outs[l])[(int64_t)b * cout + threadIdx.x] = o;
+      h[threadIdx.x] = mlp_f(o);
+    }
+    __syncthreads();
+  }
+}
+
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
   GRID_STRIDE(i, n) { st_f(d + i, ld_f(s + i)); }
@@ -364,6 +411,22 @@ extern "C" int artic_tanh_bwd(const float* dy, const float* y, void* dpre, int64
   if (n == 0) return ARTIC_OK;
   DISPATCH(dtype, (tanh_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(dy, y, (float*)dpre, n)),
            (tanh_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(dy, y, (bf16*)dpre, n)));
+}
+
+extern "C" int artic_mlp_fwd(const artic_mlp_t* p, void* stream) {
+  ARTIC_CHECK_ARG(p != nullptr && p->in != nullptr, "null pointer");
+  ARTIC_CHECK_ARG(p->n_layers >= 1 && p->n_layers <= 8 && p->B >= 0, "1..8 layers");
+  ARTIC_CHECK_ARG(p->dtype == ARTIC_F32 || p->dtype == ARTIC_BF16, "bad dtype");
+  for (int l = 0; l <= p->n_layers; ++l) ARTIC_CHECK_ARG(p->dims[l] >= 1 && p->dims[l] <= MLP_MAX_DIM, "layer width out of range");
+  for (int l = 0; l < p->n_layers; ++l) {
+    ARTIC_CHECK_ARG(p->W[l] != nullptr, "null weight");
+    if (MLP_THREADS % p->dims[l + 1] != 0) { set_error("artic_mlp_fwd: output widths must divide %d", MLP_THREADS); return ARTIC_ENOSUP; }
+  }
+  if (p->B == 0) return ARTIC_OK;
+  if (p->dtype == ARTIC_BF16) mlp_fwd_kernel<__nv_bfloat16><<<p->B, MLP_THREADS, 0, ST(stream)>>>(*p);
+  else mlp_fwd_kernel<float><<<p->B, MLP_THREADS, 0, ST(stream)>>>(*p);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
 }
 
 extern "C" int artic_cut_windows(const float* audio, const int64_t* audio_off, const float* art, const int64_t* art_off,

@@ -611,6 +611,20 @@ _G_OBJECTIVE = int(_os.environ.get("ARTIC_G_OBJECTIVE", "60"))   # measured: 100
 _D_OBJECTIVE = int(_os.environ.get("ARTIC_D_OBJECTIVE", "100"))  # the discriminator's eight chains: see profiles/r2_objective_sweep.log
 
 
+def mlp_forward(x: torch.Tensor, lays, acts, code: int, slope: float):
+    """Linear -> [LeakyReLU -> Linear] x (n - 1) in ONE launch (artic_mlp_fwd): x (B, dims[0]) fp32, acts[0] receives x
+    in the storage type, acts[l + 1] layer l's output (activated for all but the last)."""
+    p = _lib.Mlp()
+    p.in_, p.act0 = ptr(x), ptr(acts[0].t)
+    p.B, p.n_layers, p.dtype, p.slope = acts[0].N, len(lays), code, slope
+    p.dims[0] = lays[0].spec.cin
+    for l, lay in enumerate(lays):
+        assert lay.kcig == lay.spec.cin and lay.kcog == lay.spec.cout and lay.in_code == code
+        p.dims[l + 1] = lay.spec.cout
+        p.W[l], p.bias[l], p.outs[l] = ptr(lay.Wf), ptr(lay.b), ptr(acts[l + 1].t)
+    call("artic_mlp_fwd", p)
+
+
 class GeneratorEngine:
     """HiFiGANGenerator.forward (reference models/hifigan.py:198-239) and its backward."""
 
@@ -696,18 +710,10 @@ class GeneratorEngine:
         if self.use_ar:
             Ca = self.ar_output
             a0 = SeqT.empty(B, 1, self.ar_input, code, dev)
-            call("artic_cast", ptr(ar.contiguous().float()), F32, ptr(a0.t), code, B * self.ar_input)
-            acts = [a0]
-            h = a0
-            for li in range(5):
-                lay = L[f"ar_model.model.{2 * li}"]
-                o = SeqT.empty(B, 1, lay.spec.cout, code, dev)
-                if li < 4:
-                    lay.forward(h, Y2=o, act=ACT_LRELU, act_slope=0.1)   # pytorch_layers.py:440,446
-                else:
-                    lay.forward(h, Y=o)
-                acts.append(o)
-                h = o
+            lays = [L[f"ar_model.model.{2 * li}"] for li in range(5)]
+            acts = [a0] + [SeqT.empty(B, 1, lay.spec.cout, code, dev) for lay in lays]
+            mlp_forward(ar.contiguous().float(), lays, acts, code, 0.1)          # pytorch_layers.py:440,446
+            h = acts[-1]
             ar_feats = h
             if save:
                 tape["ar_acts"] = acts

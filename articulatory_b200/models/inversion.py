@@ -24,7 +24,7 @@ import torch
 from .. import _lib
 from .._lib import F32, call, ptr
 from ..convspec import ConvSpec
-from ..engine import ConvLayer, SeqT
+from ..engine import ConvLayer, SeqT, mlp_forward
 from .hifigan import _PastFC
 
 
@@ -121,14 +121,9 @@ class BiGRU(torch.nn.Module):
         ar_feats, Ca = None, 0
         if self.use_ar:                                                          # :57-60
             Ca = self.ar_output
-            h = SeqT(ar.reshape(N, 1, -1).contiguous().float(), N, 1, ar.numel() // N)
-            for li, lay in enumerate(P["ar"]):
-                o = SeqT.empty(N, 1, lay.spec.cout, F32, dev)
-                if li < 4:
-                    lay.forward(h, Y2=o, act=_lib.ACT_LRELU, act_slope=0.1)
-                else:
-                    lay.forward(h, Y=o)
-                h = o
+            acts = [SeqT.empty(N, 1, ar.numel() // N, F32, dev)] + [SeqT.empty(N, 1, lay.spec.cout, F32, dev) for lay in P["ar"]]
+            mlp_forward(ar.reshape(N, -1).contiguous().float(), P["ar"], acts, F32, 0.1)
+            h = acts[-1]
             ar_feats = h
         assert C + Ca == self.in_channels, f"in_channels {self.in_channels} != {C} + {Ca}"
         lin1 = P["gru1"]["lin"]

@@ -230,6 +230,23 @@ int artic_gen_input(const float* c, const void* ar_feats, void* out, int32_t B, 
 int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int32_t Ca, int32_t Cpad,
                         int32_t T, int32_t dtype, void* stream);
 
+/* PastFCEncoder forward (layers/pytorch_layers.py:426-460: Linear, then [LeakyReLU, Linear] x (n_layers - 1)) in one
+ * launch, one batch item per thread block.  in: (B, dims[0]) fp32; W[l]: prepared weight [dims[l]][dims[l+1]] in `dtype`
+ * (artic_weights_prep `out_f` of a linear layer); bias[l]: fp32 or NULL; act0 (optional): the input cast to `dtype`;
+ * outs[l] (optional): the layer's output (B, dims[l+1]) in `dtype` — activated for all but the last layer.  Widths
+ * <= 1024, output widths must divide 1024. */
+typedef struct {
+  const float* in;
+  const void* W[8];
+  const float* bias[8];
+  void* act0;
+  void* outs[8];
+  int32_t dims[9];
+  int32_t B, n_layers, dtype;
+  float slope;
+} artic_mlp_t;
+int artic_mlp_fwd(const artic_mlp_t* p, void* stream);
+
 /* MRF average + activation (models/hifigan.py:226-230 and the LeakyReLU of the next
  * layer): out_act = lrelu((a+b+c)/3, slope); n elements; inputs in `dtype`, output in `out_dtype`. */
 int artic_mean3_act(const void* a, const void* b, const void* c, void* out_act, int64_t n,

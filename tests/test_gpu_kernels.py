@@ -504,6 +504,45 @@ def _bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float64)
 
 
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("B", [1, 16, 33])
+def test_fused_past_fc_encoder(dtype, B):
+    """artic_mlp_fwd (the PastFCEncoder, 5 Linear layers with LeakyReLU(0.1) between, one launch) against torch float64 on
+    the same (storage-rounded) weights; every saved activation is compared, not only the result."""
+    from articulatory_b200.engine import mlp_forward
+    torch.manual_seed(B)
+    code = F32 if dtype == "f32" else BF16
+    rnd = (lambda t: t.double()) if dtype == "f32" else _bf16_round
+    dims = [512, 256, 256, 256, 256, 128]
+    ws = [torch.randn(dims[i + 1], dims[i]) / math.sqrt(dims[i]) for i in range(5)]
+    bs = [torch.randn(dims[i + 1]) * 0.1 for i in range(5)]
+    x = torch.randn(B, 512)
+    lays = []
+    for i in range(5):
+        lay = ConvLayer(ConvSpec("linear", dims[i], dims[i + 1]), f"m{i}", code, code)
+        lay.bind({f"m{i}.weight": ws[i].to(DEV).contiguous(), f"m{i}.bias": bs[i].to(DEV)})
+        lay.prep()
+        lays.append(lay)
+    acts = [SeqT.empty(B, 1, d, code, DEV) for d in dims]
+    for a in acts:
+        a.t.fill_(float("nan"))
+    launches = _lib.launch_count
+    mlp_forward(x.to(DEV), lays, acts, code, 0.1)
+    torch.cuda.synchronize()
+    assert _lib.launch_count - launches == 1
+    h = rnd(x)
+    tol = 1e-5 if dtype == "f32" else 6e-3
+    assert rel_err(acts[0].t.float().cpu().reshape(B, -1), h) < tol
+    for i in range(5):
+        h = F.linear(h, rnd(ws[i]), bs[i].double())
+        if i < 4:
+            h = F.leaky_relu(h, 0.1)
+        h = rnd(h)
+        got = acts[i + 1].t.float().cpu().reshape(B, -1)
+        assert torch.isfinite(got).all()
+        assert rel_err(got, h) < tol, i
+
+
 MIXED_CASES = [
     # (spec kwargs, N, Lin, in dtype): the shapes whose bf16-mode kernels the uniform-precision cases above do not reach
     (dict(kind="conv", cin=1, cout=128, k=15, padding=7), 3, 1500, "f32"),               # Cin = 1 kernels (MSD first layer)
