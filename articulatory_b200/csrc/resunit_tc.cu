@@ -31,12 +31,11 @@ struct RUPlan {
   int32_t mode, rev;                     // mode 1 = data gradient (mask epilogues); rev = taps of both weights reversed
   int32_t row_bytes, layout_type;
   int32_t tiles_per_seq, total_tiles;
-  int32_t nbox, a1_stage_bytes, n_as;
+  int32_t nbox, a1_stage_bytes, n_as, n_a2;   // n_a2: intermediate buffers (2; 1 when the weights leave no room)
   int32_t w_tile_bytes, a2_bytes, tmem_cols;
   int32_t N, L;
   int64_t s_outer;
   float slope;
-  int32_t pad_;
 };
 
 struct RUArgs {
@@ -127,10 +126,11 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
     tc_fence_after();
     auto gemm2 = [&](int i) {                       // conv2 of the CTA's i-th tile: A = the intermediate in shared memory
       const int s = i & 1, ph = (i >> 1) & 1;
-      mbar_wait(&a2_full[s], (uint32_t)ph);
+      const int s2 = i % pl.n_a2, ph2 = (i / pl.n_a2) & 1;
+      mbar_wait(&a2_full[s2], (uint32_t)ph2);
       mbar_wait(&acc2_empty[s], (uint32_t)(ph ^ 1));
       tc_fence_after();
-      const uint32_t a16 = desc_lo | (((a2_base + (uint32_t)s * pl.a2_bytes) >> 4) & 0x3fffu);
+      const uint32_t a16 = desc_lo | (((a2_base + (uint32_t)s2 * pl.a2_bytes) >> 4) & 0x3fffu);
       const uint32_t d = tmem_base + (uint32_t)(2 * C) + (uint32_t)s * C;
       uint32_t accum = 0;
       for (int t = 0; t < k; ++t) {
@@ -141,7 +141,7 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
           accum = 1;
         }
       }
-      if (leader) { umma_commit(&a2_empty[s]); umma_commit(&acc2_full[s]); }
+      if (leader) { umma_commit(&a2_empty[s2]); umma_commit(&acc2_full[s]); }
     };
     int i = 0;
     for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i) {
@@ -181,18 +181,19 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
 
     auto stage1 = [&](int i, int tile) {        // TMEM acc1 -> at (shared memory + optional HBM copy)
       const int s = i & 1, ph = (i >> 1) & 1;
+      const int s2 = i % pl.n_a2, ph2 = (i / pl.n_a2) & 1;
       const int n = tile / pl.tiles_per_seq;
       const int q0 = (tile % pl.tiles_per_seq) * pl.R;
       const int gpos = q0 - pl.p2 + r;
       const bool inside = gpos >= 0 && gpos < pl.L;
       mbar_wait(&acc1_full[s], (uint32_t)ph);
-      mbar_wait(&a2_empty[s], (uint32_t)(ph ^ 1));     // conv2 of tile i - 2 has finished reading this buffer
+      mbar_wait(&a2_empty[s2], (uint32_t)(ph2 ^ 1));   // conv2 of tile i - n_a2 has finished reading this buffer
       tc_fence_after();
       if (has_ch) {
         uint32_t acc_r[32];
         tmem_ld32(t_lane + (uint32_t)s * C + c0, acc_r);
         tmem_ld_wait();
-        uint8_t* row = a2_ptr + (size_t)s * pl.a2_bytes + (size_t)r * pl.row_bytes;
+        uint8_t* row = a2_ptr + (size_t)s2 * pl.a2_bytes + (size_t)r * pl.row_bytes;
         const bool keep = ar.at != nullptr && inside && r >= pl.p2 && r < pl.p2 + pl.R;
         TO* g = keep ? ar.at + (int64_t)n * pl.s_outer + (int64_t)gpos * C + c0 : nullptr;
         const TO* mk = (pl.mode == 1 && inside) ? ar.m1 + (int64_t)n * pl.s_outer + (int64_t)gpos * C + c0 : nullptr;
@@ -222,7 +223,7 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mbar_arrive(&acc1_empty[s]);
-      mbar_arrive(&a2_full[s]);
+      mbar_arrive(&a2_full[s2]);
     };
     auto stage2 = [&](int i, int tile) {        // TMEM acc2 -> xn = conv2 + b2 + x, axn = lrelu(xn)
       const int s = i & 1, ph = (i >> 1) & 1;
@@ -349,11 +350,18 @@ extern "C" int artic_resunit_fwd(const artic_resunit_t* pp, void* stream) {
   pl.tmem_cols = 4 * p.C;                                  // two accumulators x two stages (128 or 256 columns)
   pl.N = p.N; pl.L = p.L; pl.s_outer = (int64_t)p.L * p.C;
   pl.slope = p.slope;
-  const int fixed = 2 * p.k * pl.w_tile_bytes + 2 * pl.a2_bytes + 1024;
+  // C = 64 with k = 11: the two resident weights take 176 KB; one input stage and one intermediate buffer still fit (the
+  // accumulators stay double-buffered, so conv1 of tile i + 1 still overlaps the conversion of tile i)
+  pl.n_a2 = 2;
+  int fixed = 2 * p.k * pl.w_tile_bytes + pl.n_a2 * pl.a2_bytes + 1024;
+  if (tc::ru_smem_limit() - fixed < 2 * pl.a1_stage_bytes) {
+    pl.n_a2 = 1;
+    fixed = 2 * p.k * pl.w_tile_bytes + pl.n_a2 * pl.a2_bytes + 1024;
+  }
   const int budget = tc::ru_smem_limit() - fixed;
   pl.n_as = budget / pl.a1_stage_bytes;
   if (pl.n_as > tc::RU_MAX_AS) pl.n_as = tc::RU_MAX_AS;
-  if (pl.n_as < 2) { set_error("artic_resunit_fwd: weights do not fit in shared memory (C %d, k %d)", p.C, p.k); return ARTIC_ENOSUP; }
+  if (pl.n_as < 1) { set_error("artic_resunit_fwd: weights do not fit in shared memory (C %d, k %d)", p.C, p.k); return ARTIC_ENOSUP; }
 
   CUtensorMap map_x, map_w1, map_w2;
   {

@@ -570,14 +570,15 @@ _FUSE_RES_BWD = _os.environ.get("ARTIC_FUSE_RES_BWD", "1") != "0"
 
 def resunit_fusable(c1: "ConvLayer", c2: "ConvLayer") -> bool:
     """Both convs of a residual unit fit the fused kernel: bf16, C -> C with C in {32, 64}, same odd kernel size <= 11,
-    conv2 undilated, and the two weights resident in shared memory next to the tiles (C = 64: k <= 7)."""
+    conv2 undilated; the two weights stay resident in shared memory next to the tiles (C = 64, k = 11: 176 KB of weights,
+    single-buffered tiles)."""
     s1, s2 = c1.spec, c2.spec
     C = s1.cin
     return (_FUSE_RES and c1.in_code == BF16 and c1.out_code == BF16 and c2.in_code == BF16 and c2.out_code == BF16
             and s1.kind == s2.kind == "conv" and s1.cout == C and s2.cin == C and s2.cout == C and C in (32, 64)
             and s1.groups == s2.groups == 1 and s1.stride == s2.stride == 1 and s1.k == s2.k and s1.k % 2 == 1 and s1.k <= 11
             and s2.dilation == 1 and s1.padding == (s1.k - 1) // 2 * s1.dilation and s2.padding == (s2.k - 1) // 2
-            and (s1.k // 2) * s1.dilation <= 32 and (C == 32 or s1.k <= 7) and c1.kcig == C and c2.kcig == C)
+            and (s1.k // 2) * s1.dilation <= 32 and c1.kcig == C and c2.kcig == C)
 
 
 def resunit_forward(c1: "ConvLayer", c2: "ConvLayer", ax: SeqT, x: SeqT, at: Optional[SeqT], xn: Optional[SeqT],
