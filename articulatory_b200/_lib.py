@@ -135,6 +135,7 @@ SIGNATURES = {
     "artic_train_log": (C.c_int, [_p, _p, _p, _i32, _f, _f, _f, _p, _p, _p]),
     "artic_bigru_layer": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p]),
     "artic_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
+    "artic_adam_step_wire": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _p, _p]),
     "artic_adam_tick": (C.c_int, [_p, _p]),
 }
 

@@ -309,7 +309,8 @@ def main(argv=None):
              "discriminator": discriminator_class(**config["discriminator_params"], precision=args.precision).to(device)}
     dp.broadcast_parameters(model["generator"], model["discriminator"])
     ts = TrainStep(model["generator"], model["discriminator"], config, device, world_size=dp.world,
-                   all_reduce=dp.all_reduce if dp.world > 1 else None)
+                   all_reduce=dp.all_reduce if dp.world > 1 else None,
+                   grad_wire=dp.wire_of if dp.world > 1 else None)
     dev_collater = SpeechCollater(batch_max_steps=config["batch_max_steps"], hop_size=config["hop_size"],
                                   aux_context_window=config["generator_params"].get("aux_context_window", 0),
                                   dataset_mode=config.get("dataset_mode", "a2w"), config=config,

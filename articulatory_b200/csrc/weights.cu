@@ -511,7 +511,20 @@ __global__ void __launch_bounds__(256) wn_bwd4_kernel(const artic_wdesc_t* __res
   }
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+__device__ __forceinline__ float4 adam_ld4(const float* g, int64_t i) { return reinterpret_cast<const float4*>(g)[i]; }
+__device__ __forceinline__ float4 adam_ld4(const __nv_bfloat16* g, int64_t i) {
+  const uint2 q = reinterpret_cast<const uint2*>(g)[i];
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float adam_ld1(const float* g, int64_t i) { return g[i]; }
+__device__ __forceinline__ float adam_ld1(const __nv_bfloat16* g, int64_t i) { return __bfloat162float(g[i]); }
+
+// TG = float: the local gradient; TG = bf16: the data-parallel wire buffer (the reduced gradient is consumed as it came
+// off the wire, without a cast back to fp32)
+template <typename TG>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const TG* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                    const artic_adam_hyper_t* __restrict__ hyper) {
   const artic_adam_hyper_t h = *hyper;
@@ -532,12 +545,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
   };
   float4* p4 = reinterpret_cast<float4*>(p);
-  const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = p4[i], mm = m4[i], vv = v4[i];
-    const float4 gg = g4[i];
+    const float4 gg = adam_ld4(g, i);
     upd(pp.x, gg.x, mm.x, vv.x);
     upd(pp.y, gg.y, mm.y, vv.y);
     upd(pp.z, gg.z, mm.z, vv.z);
@@ -546,7 +558,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
   for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i], mi = m[i], vi = v[i];
-    upd(pi, g[i], mi, vi);
+    upd(pi, adam_ld1(g, i), mi, vi);
     p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
@@ -609,7 +621,21 @@ extern "C" int artic_adam_step(float* p, const float* g, float* m, float* v, int
   if (n == 0) return ARTIC_OK;
   int64_t blocks = (n + 1023) / 1024;
   if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
-  adam_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, hyper);
+  adam_kernel<float><<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, hyper);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
+}
+
+extern "C" int artic_adam_step_wire(float* p, const void* g, int32_t g_dtype, float* m, float* v, int64_t n,
+                                    const artic_adam_hyper_t* hyper, void* stream) {
+  ARTIC_CHECK_ARG(p && g && m && v && hyper, "null pointer");
+  ARTIC_CHECK_ARG(g_dtype == ARTIC_F32 || g_dtype == ARTIC_BF16, "bad gradient dtype");
+  if (g_dtype == ARTIC_F32) return artic_adam_step(p, reinterpret_cast<const float*>(g), m, v, n, hyper, stream);
+  if (n == 0) return ARTIC_OK;
+  int64_t blocks = (n + 1023) / 1024;
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+  adam_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, reinterpret_cast<const __nv_bfloat16*>(g), m, v, n, hyper);
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;
 }

@@ -31,6 +31,7 @@ class FusedAdam:
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.wire = None
         self.views, self.grad_views = {}, {}
         off = 0
         with torch.no_grad():
@@ -62,8 +63,11 @@ class FusedAdam:
         self.grad.zero_()
 
     def step(self):
-        call("artic_adam_step", ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), self.flat.numel(),
-             ptr(self.hyper))
+        """One Adam update from ``self.grad`` — or from ``self.wire`` when the data-parallel exchange left the reduced
+        gradient in a (bf16) wire buffer (set by TrainStep)."""
+        g = self.wire if self.wire is not None else self.grad
+        call("artic_adam_step_wire", ptr(self.flat), ptr(g), _lib.DTYPE_CODE[g.dtype], ptr(self.m), ptr(self.v),
+             self.flat.numel(), ptr(self.hyper))
         call("artic_adam_tick", ptr(self.hyper))
         if hasattr(self.module, "mark_weights_dirty"):
             self.module.mark_weights_dirty()

@@ -14,6 +14,9 @@ import torch
 import torch.distributed as dist
 
 
+_SKIP = os.environ.get("ARTIC_DP_SKIP", "")       # "all" | "big" | "small": what-if switch for scaling experiments
+
+
 def env_world():
     """(rank, local_rank, world_size) from the launcher's environment (1 process = defaults)."""
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
@@ -28,7 +31,7 @@ class DataParallel:
         self.rank, self.local_rank, self.world = env_world()
         self.device = device
         self.compress = compress
-        self._wire = {}
+        self._wire, self._claimed = {}, set()
         self.bytes_reduced = 0
         if self.world > 1 and not dist.is_initialized():
             backend = backend or ("nccl" if (device is not None and torch.device(device).type == "cuda") else "gloo")
@@ -47,16 +50,31 @@ class DataParallel:
                 m.mark_weights_dirty()
 
     # ---- gradients --------------------------------------------------------------------
+    def wire_of(self, flat: torch.Tensor):
+        """The bf16 wire buffer of a flat gradient buffer (None for the exact fp32 exchange).  A caller that asks for it
+        CONSUMES the reduced gradient from it (``FusedAdam.wire``): ``all_reduce(flat)`` then skips the cast back to
+        fp32 — one 6-byte-per-parameter pass less on the exchange path."""
+        if self.world == 1 or self.compress != "bf16":
+            return None
+        w = self._wire.get(flat.data_ptr())
+        if w is None:
+            w = self._wire[flat.data_ptr()] = torch.empty_like(flat, dtype=torch.bfloat16)
+        self._claimed.add(flat.data_ptr())
+        return w
+
     def all_reduce(self, flat: torch.Tensor):
         """Sum a flat gradient buffer over ranks, in place (called between the step's graph segments)."""
         if self.world > 1:
+            if _SKIP and (_SKIP == "all" or (_SKIP == "big") == (flat.numel() > 30_000_000)):
+                return                      # timing experiments only (ARTIC_DP_SKIP): the step's results are wrong
             if self.compress == "bf16":
                 w = self._wire.get(flat.data_ptr())
                 if w is None:
                     w = self._wire[flat.data_ptr()] = torch.empty_like(flat, dtype=torch.bfloat16)
                 w.copy_(flat)
                 dist.all_reduce(w, op=dist.ReduceOp.SUM)
-                flat.copy_(w)
+                if flat.data_ptr() not in self._claimed:
+                    flat.copy_(w)
                 self.bytes_reduced += w.numel() * 2
             else:
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM)

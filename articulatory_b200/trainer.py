@@ -46,12 +46,18 @@ LOG_KEYS = ["train/spectral_convergence_loss", "train/log_stft_magnitude_loss", 
 _MEL, _ADV, _FM, _REAL, _FAKE = range(5)
 
 
+def _event_on(stream):
+    e = torch.cuda.Event(enable_timing=True)
+    e.record(stream)
+    return e
+
+
 class TrainStep:
-    def __init__(self, generator, discriminator, config: Dict, device, world_size=1, all_reduce=None):
+    def __init__(self, generator, discriminator, config: Dict, device, world_size=1, all_reduce=None, grad_wire=None):
         """``config`` uses the reference YAML keys (use_stft_loss, stft_loss_params, use_mel_loss,
         mel_loss_params, lambda_aux, lambda_adv, lambda_feat_match, *_optimizer_params,
         *_scheduler_params, *_train_start_steps).  ``all_reduce(flat_grad)`` (optional) sums a
-        flat gradient buffer over data-parallel ranks."""
+        flat gradient buffer over data-parallel ranks; ``grad_wire`` (optional): see below."""
         self.G, self.D, self.cfg, self.dev = generator, discriminator, config, torch.device(device)
         self.world, self.all_reduce = world_size, all_reduce
         if config.get("generator_optimizer_type", "Adam") != "Adam" or \
@@ -88,6 +94,10 @@ class TrainStep:
                              gamma=sp.get("gamma", 0.1), milestones=tuple(sp.get("milestones", ())))
 
         self.optG, self.optD = opt(generator, "generator"), opt(discriminator, "discriminator")
+        if all_reduce is not None and grad_wire is not None:
+            # ``grad_wire(flat)`` (DataParallel.wire_of): the buffer all_reduce leaves the reduced gradient in; Adam reads
+            # it directly (bf16 wire: no cast back to the fp32 gradient buffer)
+            self.optG.wire, self.optD.wire = grad_wire(self.optG.grad), grad_wire(self.optD.grad)
         R = len(self.stft.resolutions) if self.use_stft else 0
         self.R = R
         self.slots = torch.zeros(8, dtype=torch.float32, device=self.dev)
@@ -99,6 +109,7 @@ class TrainStep:
         self._graph = None
         self._static = None
         self._overlap, self._ev_d, self._gfwd = False, None, None
+        self._trace = None
         self.ar_len = generator._cfg["ar_input"] if generator.use_ar else 0
 
     # ------------------------------------------------------------------------------
@@ -350,19 +361,30 @@ class TrainStep:
                 # only the (5x smaller) exchange of the G gradients is on the critical path
                 g1a, g1b, g2, g3 = self._graph
                 main = torch.cuda.current_stream()
+                tr = self._trace                     # tools/dp_timeline.py: CUDA events at the schedule's joints
+                mark = (lambda st: tr[-1].append(_event_on(st))) if tr is not None else (lambda st: None)
+                if tr is not None:
+                    tr.append([])
+                mark(main)
                 g1a.replay()
+                mark(main)
                 main.wait_event(self._ev_d)
                 g1b.replay()
+                mark(main)
                 if self.all_reduce is not None:
                     self.all_reduce(self.optG.grad)
+                mark(main)
                 g2.replay()
                 self._ev_2.record(main)
+                mark(main)
                 with torch.cuda.stream(self._xs):
                     self._xs.wait_event(self._ev_2)
                     if self.all_reduce is not None:
                         self.all_reduce(self.optD.grad)
+                    mark(self._xs)
                     g3.replay()
                     self._ev_d.record(self._xs)
+                    mark(self._xs)
             else:
                 g1, g2, g3 = self._graph
                 g1.replay()

@@ -237,7 +237,8 @@ def build_step(precision, dev, world, dp, seed=0):
         dp.broadcast_parameters(G, D)
     # gradient exchange: sum of the flat gradient buffers (1/world is folded into the loss seeds)
     return TrainStep(G, D, C.e2w_train_config(use_stft_loss=True), dev, world_size=world,
-                     all_reduce=dp.all_reduce if (dp is not None and world > 1) else None)
+                     all_reduce=dp.all_reduce if (dp is not None and world > 1) else None,
+                     grad_wire=dp.wire_of if (dp is not None and world > 1) else None)
 
 
 def timed_steps(ts, b, steps, warmup, barrier):

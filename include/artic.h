@@ -413,6 +413,10 @@ typedef struct {
 /* p, m, v updated in place from g over n fp32 elements; reads *hyper (device) for lr/step. */
 int artic_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
                     const artic_adam_hyper_t* hyper, void* stream);
+/* The same update with the gradient read in `g_dtype` (ARTIC_F32 / ARTIC_BF16): the data-parallel step hands the bf16
+ * wire buffer of the gradient exchange straight to the optimiser. */
+int artic_adam_step_wire(float* p, const void* g, int32_t g_dtype, float* m, float* v, int64_t n,
+                         const artic_adam_hyper_t* hyper, void* stream);
 /* hyper->step += 1 (device side; call once after all artic_adam_step of one optimiser step) */
 int artic_adam_tick(artic_adam_hyper_t* hyper, void* stream);
 

@@ -34,7 +34,7 @@ def _batch(golden):
             "ar": torch.cat([b["ar"], b["ar"].flip(2)])}
 
 
-def _worker(rank, world, port, out_dir, overlap="1"):
+def _worker(rank, world, port, out_dir, overlap="1", compress=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
                       LOCAL_RANK=str(rank), ARTIC_DP_OVERLAP=overlap)
     from articulatory_b200.parallel import DataParallel
@@ -43,10 +43,11 @@ def _worker(rank, world, port, out_dir, overlap="1"):
                         weights_only=False)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dp = DataParallel(backend="nccl", device=dev)
+    dp = DataParallel(backend="nccl", device=dev, compress=compress)
     G, D = _build(golden, dev)
     dp.broadcast_parameters(G, D)
-    ts = TrainStep(G, D, _cfg(golden), dev, world_size=world, all_reduce=dp.all_reduce)
+    ts = TrainStep(G, D, _cfg(golden), dev, world_size=world, all_reduce=dp.all_reduce, grad_wire=dp.wire_of)
+    assert (ts.optD.wire is not None) == (compress == "bf16")
     shard = {k: v.to(dev) for k, v in dp.shard(_batch(golden)).items()}
     for _ in range(6):
         ts.step(shard["x"], shard["y"], shard["ar"], use_graph=True)
@@ -54,7 +55,7 @@ def _worker(rank, world, port, out_dir, overlap="1"):
     torch.cuda.synchronize()
     assert ts._overlap == (overlap == "1")
     torch.save({"g": {k: v.cpu() for k, v in G.state_dict().items()}, "d": {k: v.cpu() for k, v in D.state_dict().items()},
-                "vals": vals}, os.path.join(out_dir, f"r{rank}_{overlap}.pt"))
+                "vals": vals}, os.path.join(out_dir, f"r{rank}_{overlap}{compress or ''}.pt"))
     dp.barrier()
     dp.close()
 
@@ -71,6 +72,7 @@ def test_two_gpu_step_matches_single_gpu(golden, tmp_path):
     s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path), "1"), nprocs=2, join=True)
     mp.spawn(_worker, args=(2, port + 1 if port < 65000 else port - 1, str(tmp_path), "0"), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port + 2 if port < 65000 else port - 2, str(tmp_path), "1", "bf16"), nprocs=2, join=True)
     r0 = torch.load(tmp_path / "r0_1.pt", weights_only=False)
     r1 = torch.load(tmp_path / "r1_1.pt", weights_only=False)
     s0 = torch.load(tmp_path / "r0_0.pt", weights_only=False)
@@ -84,6 +86,18 @@ def test_two_gpu_step_matches_single_gpu(golden, tmp_path):
             assert rel_err(r0[name][k], s0[name][k]) < 1e-4, f"overlapped schedule changed {name} parameter {k}"
     for k, v in s0["vals"].items():
         assert abs(r0["vals"][k] - v) <= 1e-4 * abs(v), (k, r0["vals"][k], v)
+    # bf16 wire (the bench's exchange in the bf16 mode; Adam consumes the wire buffer directly): the ranks stay in lock
+    # step, and six steps land where the exact exchange lands up to the wire's rounding (2^-9 per gradient element)
+    w0 = torch.load(tmp_path / "r0_1bf16.pt", weights_only=False)
+    w1 = torch.load(tmp_path / "r1_1bf16.pt", weights_only=False)
+    for name in ("g", "d"):
+        for k in w0[name]:
+            assert torch.equal(w0[name][k], w1[name][k]), f"ranks diverged on {k} (bf16 wire)"
+            delta = r0[name][k] - golden["gsd" if name == "g" else "dsd"][k]
+            if delta.abs().max() > 0:
+                assert rel_err(w0[name][k] - golden["gsd" if name == "g" else "dsd"][k], delta) < 0.1, (name, k)
+    for k, v in r0["vals"].items():
+        assert abs(w0["vals"][k] - v) <= 5e-3 * abs(v), (k, w0["vals"][k], v)
     dev = torch.device("cuda", 0)
     G, D = _build(golden, dev)
     ts = TrainStep(G, D, _cfg(golden), dev)
