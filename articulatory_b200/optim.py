@@ -26,24 +26,28 @@ class FusedAdam:
         assert named, "module has no parameters"
         dev = named[0][1].device
         _lib.require_cuda(named[0][1], "parameters")
-        total = sum(p.numel() for _, p in named)
-        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        # every parameter starts on a 128-byte boundary of the flat buffers: the weight-side kernels (prep / unprep /
+        # weight-norm / their 128-bit row accesses) need 16-byte aligned rows, and a dense concatenation loses that after
+        # the first 1-element bias (86 % of the discriminator's elements sat at odd offsets).  The gaps stay zero.
+        self.offsets, total = {}, 0
+        for n, p in named:
+            self.offsets[n] = total
+            total += (p.numel() + 31) // 32 * 32
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.wire = None
         self.views, self.grad_views = {}, {}
-        off = 0
         with torch.no_grad():
             for n, p in named:
-                k = p.numel()
+                k, off = p.numel(), self.offsets[n]
                 view = self.flat[off:off + k].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
                 gview = self.grad[off:off + k].view(p.shape)
                 p.grad = gview
                 self.views[n], self.grad_views[n] = view, gview
-                off += k
         h = AdamHyper()
         h.lr0, h.beta1, h.beta2, h.eps, h.gamma = lr, betas[0], betas[1], eps, gamma
         h.step, h.n_milestones = 0, len(milestones)
@@ -90,13 +94,12 @@ class FusedAdam:
         step = self.step_count()
         h = self._host_hyper
         m, v = self.m.cpu(), self.v.cpu()
-        state, off = {}, 0
+        state = {}
         for i, (n, view) in enumerate(self.views.items()):
-            k = view.numel()
+            k, off = view.numel(), self.offsets[n]
             if step > 0:
                 state[i] = {"step": torch.tensor(float(step)), "exp_avg": m[off:off + k].view(view.shape).clone(),
                             "exp_avg_sq": v[off:off + k].view(view.shape).clone()}
-            off += k
         group = {"lr": self._current_lr(step), "betas": (h.beta1, h.beta2), "eps": h.eps, "weight_decay": 0.0,
                  "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
                  "fused": None, "initial_lr": h.lr0, "params": list(range(len(self.views)))}
@@ -116,9 +119,19 @@ class FusedAdam:
         layout of earlier versions of this package; raises on anything else instead of silently restarting the
         moments.  ``scheduler_sd`` (MultiStepLR state) supplies the step counter when the optimizer state holds
         none (no step taken yet)."""
-        if "exp_avg" in sd and "step" in sd:                       # flat layout (round-1 checkpoints)
-            self.m.copy_(sd["exp_avg"])
-            self.v.copy_(sd["exp_avg_sq"])
+        if "exp_avg" in sd and "step" in sd:                       # flat layout (round-1 checkpoints: dense concatenation)
+            dense = sum(v.numel() for v in self.views.values())
+            if sd["exp_avg"].numel() != dense:
+                raise ValueError(f"flat optimizer state has {sd['exp_avg'].numel()} elements, this module has {dense}")
+            m, v = torch.zeros_like(self.m, device="cpu"), torch.zeros_like(self.v, device="cpu")
+            src = 0
+            for n, view in self.views.items():
+                k, off = view.numel(), self.offsets[n]
+                m[off:off + k] = sd["exp_avg"].reshape(-1)[src:src + k].float().cpu()
+                v[off:off + k] = sd["exp_avg_sq"].reshape(-1)[src:src + k].float().cpu()
+                src += k
+            self.m.copy_(m)
+            self.v.copy_(v)
             step = int(sd["step"])
         elif "state" in sd and "param_groups" in sd:
             names = list(self.views.keys())
@@ -126,11 +139,11 @@ class FusedAdam:
             if n_params != len(names):
                 raise ValueError(f"optimizer state has {n_params} parameters in {len(sd['param_groups'])} group(s), "
                                  f"this module has {len(names)}")
-            step, off = 0, 0
+            step = 0
             m, v = torch.zeros_like(self.m, device="cpu"), torch.zeros_like(self.v, device="cpu")
             for i, n in enumerate(names):
                 view = self.views[n]
-                k = view.numel()
+                k, off = view.numel(), self.offsets[n]
                 st = sd["state"].get(i)
                 if st is not None:
                     if tuple(st["exp_avg"].shape) != tuple(view.shape):
@@ -139,7 +152,6 @@ class FusedAdam:
                     m[off:off + k] = st["exp_avg"].reshape(-1).float()
                     v[off:off + k] = st["exp_avg_sq"].reshape(-1).float()
                     step = max(step, int(float(st["step"])))
-                off += k
             self.m.copy_(m)
             self.v.copy_(v)
             g = sd["param_groups"][0]

@@ -23,7 +23,7 @@ def main():
     import bench
     from articulatory_b200 import models as M
     from articulatory_b200.trainer import TrainStep
-    from oracle import torch_oracle as O
+    from articulatory_b200 import configs as O
     from torch.profiler import ProfilerActivity, profile
 
     dev = torch.device("cuda", 0)

@@ -30,7 +30,7 @@ def main():
     from articulatory_b200 import models as M
     from articulatory_b200.engine import fork_join, slice_seq
     from articulatory_b200.trainer import TrainStep
-    from oracle import torch_oracle as O
+    from articulatory_b200 import configs as O
 
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)

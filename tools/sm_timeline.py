@@ -26,7 +26,7 @@ def main():
     from articulatory_b200 import _lib
     from articulatory_b200 import models as M
     from articulatory_b200.trainer import TrainStep
-    from oracle import torch_oracle as O
+    from articulatory_b200 import configs as O
 
     dev = torch.device("cuda", 0)
     lib = _lib.load()

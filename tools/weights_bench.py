@@ -15,7 +15,7 @@ def main():
     ncu = "--ncu" in sys.argv
     from articulatory_b200 import models as M
     from articulatory_b200.optim import FusedAdam
-    from oracle import torch_oracle as O
+    from articulatory_b200 import configs as O
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     with warnings.catch_warnings():
