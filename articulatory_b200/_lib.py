@@ -75,7 +75,7 @@ class WDesc(C.Structure):
                 ("out_f", C.c_void_p), ("out_b", C.c_void_p),
                 ("dWp", C.c_void_p), ("dv", C.c_void_p), ("dg", C.c_void_p),
                 ("row_len", C.c_int64), ("sk", C.c_int64), ("sg", C.c_int64), ("sa", C.c_int64), ("sb", C.c_int64),
-                ("tile_begin", C.c_int64),
+                ("tile_begin", C.c_int64), ("tile2_begin", C.c_int64),
                 ("rows", C.c_int32), ("K", C.c_int32), ("G", C.c_int32), ("A", C.c_int32), ("B", C.c_int32),
                 ("merge", C.c_int32), ("a_pad", C.c_int32), ("b_pad", C.c_int32),
                 ("dtype_f", C.c_int32), ("dtype_b", C.c_int32), ("dw_swapped", C.c_int32), ("reserved_", C.c_int32)]
@@ -105,8 +105,9 @@ SIGNATURES = {
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
     "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),
     "artic_wperm_tiles": (C.c_int64, [_i32, _i32, _i32, _i32]),
-    "artic_weights_prep": (C.c_int, [_p, _i32, _i32, _i64, _p]),
-    "artic_weights_unprep": (C.c_int, [_p, _i32, _i32, _i64, _p]),
+    "artic_wrow_tiles": (C.c_int64, [_i32, _i32, _i32, _i32, _i64, _i64, _i64]),
+    "artic_weights_prep": (C.c_int, [_p, _i32, _i32, _i64, _i64, _p]),
+    "artic_weights_unprep": (C.c_int, [_p, _i32, _i32, _i64, _i64, _p]),
     "artic_gen_input": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "artic_gen_input_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "artic_mean3_act": (C.c_int, [_p, _p, _p, _p, _i64, _f, _i32, _i32, _p]),

@@ -511,6 +511,375 @@ __global__ void __launch_bounds__(256) wn_bwd4_kernel(const artic_wdesc_t* __res
   }
 }
 
+// ---- row-run relayout kernels (the default) ------------------------------------------------------------------
+// The torch weight of a conv / linear / transposed-conv layer is, per group, a matrix [outer][inner * K] whose rows are
+// CONTIGUOUS (outer = torch dim 0 = the weight-norm row; conv: outer = out-ch, inner = in-ch; convT: outer = in-ch,
+// inner = out-ch; the taps are the fastest index).  A tile is 32 outer rows x TI inner columns x ALL K taps
+// (TI * K <= 352 floats, TI = 32 for K <= 11, 8 for K = 41): the torch side moves as whole-row runs with 128-bit
+// accesses, the prepared side as 16-byte items (8 bf16 / 4 fp32) along the prepared layout's fastest index:
+//   X1 = the outer-fastest layout  (conv: 'fwd' [k][a][b];  convT: 'bwd' [k][b][a])   item = (k, i, 8 outer)
+//   X2 = the inner-fastest layout  (conv: 'bwd' [k][b][a];  convT: 'fwd' [k][a][b])   item = (k, o, 8 inner)
+// Shared-memory tile: row pitch odd (run + 1), which makes both item gathers bank-conflict free for odd K.
+// Against wprep_kernel / wunprep_kernel (32 x 32 x <= 8-tap tiles, 4-byte stores, per-element index arithmetic) this
+// issues ~4x fewer instructions per element (ncu: the old kernels were issue-bound at 47 % of peak issue rate with
+// 25 % of DRAM throughput).
+constexpr int RT_O = 32;
+constexpr int RT_RUN = 352;
+constexpr int RT_SMEM = RT_O * (RT_RUN + 1);
+
+__host__ __device__ __forceinline__ int rt_inner(int K) {
+  int ti = 32;
+  while (ti > 1 && ti * K > RT_RUN) ti >>= 1;
+  return ti;
+}
+
+struct RTile {
+  uint32_t no, ni, run, pitch;      // live outer rows / inner columns, ni * K, smem row pitch
+  uint32_t tb, s_out;               // torch offset of the tile's first row, torch row stride
+  uint32_t base1, pitch1, base2, pitch2, kstride;
+  bool a_inner;
+};
+
+__device__ __forceinline__ RTile rt_geom(const artic_wdesc_t& d, long long gt) {
+  RTile t;
+  const uint32_t K = (uint32_t)d.K;
+  t.a_inner = d.sa < d.sb || (d.sa == d.sb && d.A == 1);
+  const uint32_t O = t.a_inner ? d.B : d.A, I = t.a_inner ? d.A : d.B;
+  const uint32_t TI = (uint32_t)rt_inner(d.K);
+  const uint32_t n_it = (I + TI - 1) / TI, n_ot = (O + RT_O - 1) / RT_O;
+  uint32_t w = (uint32_t)(gt - d.tile2_begin);
+  const uint32_t it = w % n_it; w /= n_it;
+  const uint32_t ot = w % n_ot;
+  const uint32_t g = w / n_ot;
+  const uint32_t o0 = ot * RT_O, i0 = it * TI;
+  t.no = min((uint32_t)RT_O, O - o0);
+  t.ni = min(TI, I - i0);
+  t.run = t.ni * K;
+  t.pitch = (TI * K) | 1u;
+  t.s_out = (uint32_t)(t.a_inner ? d.sb : d.sa);
+  t.tb = g * (uint32_t)d.sg + o0 * t.s_out + i0 * K;
+  const uint32_t m = d.merge, Gs = d.G / m, gm = g % m, gd = g / m;
+  t.kstride = Gs * (uint32_t)d.a_pad * (uint32_t)d.b_pad;
+  const uint32_t a0 = t.a_inner ? i0 : o0, b0 = t.a_inner ? o0 : i0;
+  const uint32_t base_f = (gd * d.a_pad + gm * d.A + a0) * d.b_pad + gm * d.B + b0;   // [k][a][b]
+  const uint32_t base_b = (gd * d.b_pad + gm * d.B + b0) * d.a_pad + gm * d.A + a0;   // [k][b][a]
+  if (t.a_inner) { t.base1 = base_f; t.pitch1 = d.b_pad; t.base2 = base_b; t.pitch2 = d.a_pad; }
+  else           { t.base1 = base_b; t.pitch1 = d.a_pad; t.base2 = base_f; t.pitch2 = d.b_pad; }
+  return t;
+}
+
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// One 16-byte item of a prepared layout: E consecutive elements read from shared memory at stride `ss`
+template <typename T> struct RtItem;
+template <> struct RtItem<__nv_bfloat16> {
+  static constexpr int E = 8;
+  static __device__ __forceinline__ void store(__nv_bfloat16* dst, const float* src, uint32_t ss, uint32_t n) {
+    if (n == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      uint4 q;
+      q.x = pack_bf2(src[0], src[ss]); q.y = pack_bf2(src[2 * ss], src[3 * ss]);
+      q.z = pack_bf2(src[4 * ss], src[5 * ss]); q.w = pack_bf2(src[6 * ss], src[7 * ss]);
+      *reinterpret_cast<uint4*>(dst) = q;
+    } else {
+      for (uint32_t j = 0; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j * ss]);
+    }
+  }
+};
+template <> struct RtItem<float> {
+  static constexpr int E = 4;
+  static __device__ __forceinline__ void store(float* dst, const float* src, uint32_t ss, uint32_t n) {
+    if (n == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[ss], src[2 * ss], src[3 * ss]);
+    } else {
+      for (uint32_t j = 0; j < n; ++j) dst[j] = src[j * ss];
+    }
+  }
+};
+
+// tile (shared memory, [o][i * K + k]) -> X1 (outer-fastest): items (k, i, group of E outer rows)
+template <typename T>
+__device__ __forceinline__ void rt_store_x1(T* out, const float* tile, const RTile& t, uint32_t K) {
+  constexpr uint32_t E = RtItem<T>::E;
+  const uint32_t ng = (t.no + E - 1) / E;
+  const uint32_t per_k = t.ni * ng, total = K * per_k;
+  for (uint32_t q = threadIdx.x; q < total; q += 256) {
+    const uint32_t k = q / per_k, r = q - k * per_k;
+    const uint32_t i = r / ng, og = r - i * ng;
+    const uint32_t o = og * E;
+    RtItem<T>::store(out + t.base1 + k * t.kstride + i * t.pitch1 + o, tile + o * t.pitch + i * K + k, t.pitch, min(E, t.no - o));
+  }
+}
+
+// tile -> X2 (inner-fastest): items (k, o, group of E inner columns)
+template <typename T>
+__device__ __forceinline__ void rt_store_x2(T* out, const float* tile, const RTile& t, uint32_t K) {
+  constexpr uint32_t E = RtItem<T>::E;
+  const uint32_t ng = (t.ni + E - 1) / E;
+  const uint32_t per_k = t.no * ng, total = K * per_k;
+  for (uint32_t q = threadIdx.x; q < total; q += 256) {
+    const uint32_t k = q / per_k, r = q - k * per_k;
+    const uint32_t o = r / ng, ig = r - o * ng;
+    const uint32_t i = ig * E;
+    RtItem<T>::store(out + t.base2 + k * t.kstride + o * t.pitch2 + i, tile + o * t.pitch + i * K + k, K, min(E, t.ni - i));
+  }
+}
+
+__global__ void __launch_bounds__(256) wprep_rows_kernel(const artic_wdesc_t* __restrict__ descs, int n_layers,
+                                                         long long total_tiles) {
+  __shared__ float tile[RT_SMEM];
+  const int lane = threadIdx.x & 31, w8 = threadIdx.x >> 5;
+  for (long long gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+    int lo = 0, hi = n_layers - 1;                       // last layer with tile2_begin <= gt
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&descs[mid].tile2_begin) <= gt) lo = mid; else hi = mid - 1;
+    }
+    const artic_wdesc_t& d = descs[lo];
+    const RTile t = rt_geom(d, gt);
+    const uint32_t K = (uint32_t)d.K;
+    const float* __restrict__ v = d.v;
+    const float* __restrict__ scale = d.g != nullptr ? d.scale : nullptr;
+    const uint32_t row_len = (uint32_t)d.row_len;
+    // ---- torch rows -> shared memory (weight-norm scale applied): warp w8 takes rows w8, w8 + 8, ...
+    const bool vec = (t.run & 3) == 0 && (t.s_out & 3) == 0 && (reinterpret_cast<uintptr_t>(v + t.tb) & 15) == 0;
+    if (vec) {
+      const uint32_t r4 = t.run >> 2;                    // <= 88 float4 per row: <= 3 per lane
+      float4 x[4][3];
+      float sc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t r = w8 + 8 * i;
+        const uint32_t src0 = t.tb + r * t.s_out;
+        sc[i] = (r < t.no && scale != nullptr) ? __ldg(scale + src0 / row_len) : 1.f;
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+          const uint32_t e = lane + 32 * it;
+          x[i][it] = (r < t.no && e < r4) ? __ldg(reinterpret_cast<const float4*>(v + src0) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t r = w8 + 8 * i;
+        float* dst = tile + r * t.pitch;
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+          const uint32_t e = lane + 32 * it;
+          if (r < t.no && e < r4) {
+            dst[4 * e] = x[i][it].x * sc[i]; dst[4 * e + 1] = x[i][it].y * sc[i];
+            dst[4 * e + 2] = x[i][it].z * sc[i]; dst[4 * e + 3] = x[i][it].w * sc[i];
+          }
+        }
+      }
+    } else {
+      for (uint32_t r = w8; r < t.no; r += 8) {
+        const uint32_t src0 = t.tb + r * t.s_out;
+        const float sc = scale != nullptr ? __ldg(scale + src0 / row_len) : 1.f;
+        float* dst = tile + r * t.pitch;
+        for (uint32_t e = lane; e < t.run; e += 32) dst[e] = __ldg(v + src0 + e) * sc;
+      }
+    }
+    __syncthreads();
+    void* p1 = t.a_inner ? d.out_f : d.out_b;
+    void* p2 = t.a_inner ? d.out_b : d.out_f;
+    const int dt1 = t.a_inner ? d.dtype_f : d.dtype_b, dt2 = t.a_inner ? d.dtype_b : d.dtype_f;
+    if (p1 != nullptr) {
+      if (dt1 == ARTIC_BF16) rt_store_x1(reinterpret_cast<__nv_bfloat16*>(p1), tile, t, K);
+      else rt_store_x1(reinterpret_cast<float*>(p1), tile, t, K);
+    }
+    if (p2 != nullptr) {
+      if (dt2 == ARTIC_BF16) rt_store_x2(reinterpret_cast<__nv_bfloat16*>(p2), tile, t, K);
+      else rt_store_x2(reinterpret_cast<float*>(p2), tile, t, K);
+    }
+    __syncthreads();
+  }
+}
+
+// Prepared fp32 gradient -> torch layout.  The gradient is in the 'fwd' layout, or in the 'bwd' layout for
+// dw_swapped layers: outer-fastest (X1) for conv / linear and for swapped transposed convs, inner-fastest (X2) for
+// transposed convs in the CUDA-core modes.
+__global__ void __launch_bounds__(256) wunprep_rows_kernel(const artic_wdesc_t* __restrict__ descs, int n_layers,
+                                                           long long total_tiles) {
+  __shared__ float tile[RT_SMEM];
+  const int lane = threadIdx.x & 31, w8 = threadIdx.x >> 5;
+  for (long long gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+    int lo = 0, hi = n_layers - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&descs[mid].tile2_begin) <= gt) lo = mid; else hi = mid - 1;
+    }
+    const artic_wdesc_t& d = descs[lo];
+    if (d.dv == nullptr || d.dWp == nullptr) continue;
+    const RTile t = rt_geom(d, gt);
+    const uint32_t K = (uint32_t)d.K;
+    const float* __restrict__ src = d.dWp;
+    // which of the two layouts holds the gradient, seen from the tile: 'fwd' = X1 iff a_inner
+    const bool x1 = (d.dw_swapped == 0) == t.a_inner;
+    if (x1) {
+      const uint32_t ng = (t.no + 3) >> 2, per_k = t.ni * ng, total = K * per_k;
+      for (uint32_t q = threadIdx.x; q < total; q += 256) {
+        const uint32_t k = q / per_k, r = q - k * per_k;
+        const uint32_t i = r / ng, o = (r - i * ng) * 4;
+        const float* p = src + t.base1 + k * t.kstride + i * t.pitch1 + o;
+        float* dst = tile + o * t.pitch + i * K + k;
+        const uint32_t n = min(4u, t.no - o);
+        if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+          dst[0] = x.x; dst[t.pitch] = x.y; dst[2 * t.pitch] = x.z; dst[3 * t.pitch] = x.w;
+        } else {
+          for (uint32_t j = 0; j < n; ++j) dst[j * t.pitch] = __ldg(p + j);
+        }
+      }
+    } else {
+      const uint32_t ng = (t.ni + 3) >> 2, per_k = t.no * ng, total = K * per_k;
+      for (uint32_t q = threadIdx.x; q < total; q += 256) {
+        const uint32_t k = q / per_k, r = q - k * per_k;
+        const uint32_t o = r / ng, i = (r - o * ng) * 4;
+        const float* p = src + t.base2 + k * t.kstride + o * t.pitch2 + i;
+        float* dst = tile + o * t.pitch + i * K + k;
+        const uint32_t n = min(4u, t.ni - i);
+        if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+          dst[0] = x.x; dst[K] = x.y; dst[2 * K] = x.z; dst[3 * K] = x.w;
+        } else {
+          for (uint32_t j = 0; j < n; ++j) dst[j * K] = __ldg(p + j);
+        }
+      }
+    }
+    __syncthreads();
+    float* __restrict__ dv = d.dv;
+    const bool vec = (t.run & 3) == 0 && (t.s_out & 3) == 0 && (reinterpret_cast<uintptr_t>(dv + t.tb) & 15) == 0;
+    for (uint32_t r = w8; r < t.no; r += 8) {
+      float* dst = dv + t.tb + r * t.s_out;
+      const float* s = tile + r * t.pitch;
+      if (vec) {
+        for (uint32_t e = 4 * lane; e < t.run; e += 128)
+          *reinterpret_cast<float4*>(dst + e) = make_float4(s[e], s[e + 1], s[e + 2], s[e + 3]);
+      } else {
+        for (uint32_t e = lane; e < t.run; e += 32) dst[e] = s[e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Warp-per-row versions (the default): no block barrier between a row's load, reduction and store phases, eight rows
+// in flight per block, eight independent 128-bit loads in flight per lane.  The backward makes two passes over its row
+// (dot product, then update); the second one hits L1 / L2, so DRAM still sees 12 bytes per element.
+
+__global__ void __launch_bounds__(256) wn_scale_rows_kernel(const artic_wdesc_t* __restrict__ descs) {
+  const artic_wdesc_t& d = descs[blockIdx.y];
+  if (d.g == nullptr) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row_len = d.row_len;
+  const bool vec = (row_len & 3) == 0 && (reinterpret_cast<uintptr_t>(d.v) & 15) == 0;
+  for (int row = blockIdx.x * 8 + w; row < d.rows; row += gridDim.x * 8) {
+    const float* vr = d.v + (int64_t)row * row_len;
+    float s = 0.f;
+    if (vec) {
+      const float4* v4 = reinterpret_cast<const float4*>(vr);
+      const int n4 = (int)(row_len >> 2);
+      for (int e0 = 0; e0 < n4; e0 += 256) {
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = e0 + lane + 32 * i;
+          x[i] = e < n4 ? __ldg(v4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(x[i].x, x[i].x, fmaf(x[i].y, x[i].y, fmaf(x[i].z, x[i].z, fmaf(x[i].w, x[i].w, s))));
+      }
+    } else {
+      for (int64_t e = lane; e < row_len; e += 32) {
+        const float x = __ldg(vr + e);
+        s = fmaf(x, x, s);
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float nrm = sqrtf(s);
+      d.scale[row] = d.g[row] / nrm;
+      d.scale[d.rows + row] = nrm;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) wn_bwd_rows_kernel(const artic_wdesc_t* __restrict__ descs) {
+  const artic_wdesc_t& d = descs[blockIdx.y];
+  if (d.g == nullptr || d.dv == nullptr) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row_len = d.row_len;
+  const bool vec = (row_len & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.v) | reinterpret_cast<uintptr_t>(d.dv)) & 15) == 0;
+  for (int row = blockIdx.x * 8 + w; row < d.rows; row += gridDim.x * 8) {
+    const int64_t e0 = (int64_t)row * row_len;
+    const float s = d.scale[row], nrm = d.scale[d.rows + row];
+    float dot = 0.f;
+    if (vec) {
+      const float4* v4 = reinterpret_cast<const float4*>(d.v + e0);
+      float4* g4 = reinterpret_cast<float4*>(d.dv + e0);
+      const int n4 = (int)(row_len >> 2);
+      if (n4 <= 256) {                      // the row fits in registers (8 x 128 bits per lane per array): one pass
+        float4 gv[8], vv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = lane + 32 * i;
+          gv[i] = e < n4 ? g4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+          vv[i] = e < n4 ? __ldg(v4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(gv[i].x, vv[i].x, fmaf(gv[i].y, vv[i].y, fmaf(gv[i].z, vv[i].z, fmaf(gv[i].w, vv[i].w, dot))));
+        dot = warp_sum(dot);
+        const float coef = s * dot / (nrm * nrm);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = lane + 32 * i;
+          if (e < n4)
+            g4[e] = make_float4(s * gv[i].x - coef * vv[i].x, s * gv[i].y - coef * vv[i].y, s * gv[i].z - coef * vv[i].z,
+                                s * gv[i].w - coef * vv[i].w);
+        }
+      } else {
+        for (int c0 = 0; c0 < n4; c0 += 128) {
+          float4 gv[4], vv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = c0 + lane + 32 * i;
+            gv[i] = e < n4 ? g4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+            vv[i] = e < n4 ? v4[e] : make_float4(0.f, 0.f, 0.f, 0.f);     // plain loads: the second pass re-reads them
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dot = fmaf(gv[i].x, vv[i].x, fmaf(gv[i].y, vv[i].y, fmaf(gv[i].z, vv[i].z, fmaf(gv[i].w, vv[i].w, dot))));
+        }
+        dot = warp_sum(dot);
+        const float coef = s * dot / (nrm * nrm);
+        for (int c0 = 0; c0 < n4; c0 += 128) {
+          float4 gv[4], vv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = c0 + lane + 32 * i;
+            gv[i] = e < n4 ? g4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+            vv[i] = e < n4 ? v4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = c0 + lane + 32 * i;
+            if (e < n4)
+              g4[e] = make_float4(s * gv[i].x - coef * vv[i].x, s * gv[i].y - coef * vv[i].y, s * gv[i].z - coef * vv[i].z,
+                                  s * gv[i].w - coef * vv[i].w);
+          }
+        }
+      }
+    } else {
+      for (int64_t e = lane; e < row_len; e += 32) dot = fmaf(d.dv[e0 + e], d.v[e0 + e], dot);
+      dot = warp_sum(dot);
+      const float coef = s * dot / (nrm * nrm);
+      for (int64_t e = lane; e < row_len; e += 32) d.dv[e0 + e] = s * d.dv[e0 + e] - coef * d.v[e0 + e];
+    }
+    if (lane == 0) d.dg[row] = dot / nrm;
+  }
+}
+
 __device__ __forceinline__ float4 adam_ld4(const float* g, int64_t i) { return reinterpret_cast<const float4*>(g)[i]; }
 __device__ __forceinline__ float4 adam_ld4(const __nv_bfloat16* g, int64_t i) {
   const uint2 q = reinterpret_cast<const uint2*>(g)[i];
@@ -581,9 +950,18 @@ extern "C" int64_t artic_wperm_tiles(int32_t K, int32_t G, int32_t A, int32_t B)
   return (int64_t)((A + PT - 1) / PT) * ((B + PT - 1) / PT) * ((K + kc - 1) / kc) * G;
 }
 
+/* see include/artic.h */
+extern "C" int64_t artic_wrow_tiles(int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sa, int64_t sb) {
+  if (K < 1 || G < 1 || A < 1 || B < 1 || K > RT_RUN) return 0;
+  const bool a_inner = sa < sb || (sa == sb && A == 1);
+  if ((a_inner ? sa : sb) != K || !(sk == 1 || K == 1)) return 0;      // taps must be the torch-inner index
+  const int O = a_inner ? B : A, I = a_inner ? A : B, TI = rt_inner(K);
+  return (int64_t)G * ((O + RT_O - 1) / RT_O) * ((I + TI - 1) / TI);
+}
+
 extern "C" int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles,
-                                  void* stream) {
-  ARTIC_CHECK_ARG(descs != nullptr && n >= 0 && total_tiles >= 0, "bad descriptor table");
+                                  int64_t total_tiles2, void* stream) {
+  ARTIC_CHECK_ARG(descs != nullptr && n >= 0 && total_tiles >= 0 && total_tiles2 >= 0, "bad descriptor table");
   if (n == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (tc::g_debug[12] == 1) {          // debug: the generic three-pass version
@@ -591,8 +969,12 @@ extern "C" int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t
     wperm_kernel<0><<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
     wperm_kernel<1><<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
   } else {
-    if (any_norm) wn_scale4_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
-    wprep_kernel<<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
+    if (any_norm) {
+      if (tc::g_debug[27] == 1) wn_scale4_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
+      else wn_scale_rows_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
+    }
+    if (total_tiles > 0) wprep_kernel<<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
+    if (total_tiles2 > 0) wprep_rows_kernel<<<wperm_grid(total_tiles2), 256, 0, st>>>(descs, n, total_tiles2);
   }
   tc::note_weights_written(st);   // the next tensor-core conv on `st` must not prefetch weights early
   ARTIC_LAUNCH_CHECK();
@@ -600,16 +982,20 @@ extern "C" int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t
 }
 
 extern "C" int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles,
-                                    void* stream) {
-  ARTIC_CHECK_ARG(descs != nullptr && n >= 0 && total_tiles >= 0, "bad descriptor table");
+                                    int64_t total_tiles2, void* stream) {
+  ARTIC_CHECK_ARG(descs != nullptr && n >= 0 && total_tiles >= 0 && total_tiles2 >= 0, "bad descriptor table");
   if (n == 0) return ARTIC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (tc::g_debug[12] == 1) {
     wperm_kernel<2><<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
     if (any_norm) wn_bwd_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
   } else {
-    wunprep_kernel<<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
-    if (any_norm) wn_bwd4_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
+    if (total_tiles > 0) wunprep_kernel<<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
+    if (total_tiles2 > 0) wunprep_rows_kernel<<<wperm_grid(total_tiles2), 256, 0, st>>>(descs, n, total_tiles2);
+    if (any_norm) {
+      if (tc::g_debug[27] == 1) wn_bwd4_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
+      else wn_bwd_rows_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
+    }
   }
   ARTIC_LAUNCH_CHECK();
   return ARTIC_OK;

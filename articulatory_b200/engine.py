@@ -433,6 +433,9 @@ class ConvLayer:
         if self.b is not None and not fuse_bias:
             call("artic_colsum", ptr(dY.t), dY.seq(), dY.N, dY.C, dY.code, ptr(grads[self.name + ".bias"]))
 
+_WEIGHTS_GENERIC = _os.environ.get("ARTIC_WEIGHTS_GENERIC", "0") == "1"
+
+
 class WeightSet:
     """The prepared weights and weight-gradient accumulators of a set of layers, handled by the
     batched kernels (artic_weights_prep / artic_weights_unprep: one launch per pass for the
@@ -484,7 +487,7 @@ class WeightSet:
         tab = self._tables.get(key)
         if tab is None:
             descs = []
-            tiles = 0
+            tiles = tiles2 = 0
             lib = _lib.load()
             for l in self.layers:
                 s = l.spec
@@ -504,10 +507,15 @@ class WeightSet:
                 d.merge, d.a_pad, d.b_pad = l.mg, l.kcig, l.kcog
                 d.dtype_f, d.dtype_b = l.in_code, l.out_code
                 d.dw_swapped = int(l.dw_swapped)
-                d.tile_begin = tiles
-                tiles += lib.artic_wperm_tiles(s.k, s.groups, A, B)
+                d.tile_begin, d.tile2_begin = tiles, tiles2
+                # row-run kernels (the default; ARTIC_WEIGHTS_GENERIC=1 forces the generic tile kernels) ...
+                n2 = 0 if _WEIGHTS_GENERIC else lib.artic_wrow_tiles(s.k, s.groups, A, B, sk, sa, sb)
+                if n2 > 0:
+                    tiles2 += n2
+                else:                                                           # ... or the generic tile kernels
+                    tiles += lib.artic_wperm_tiles(s.k, s.groups, A, B)
                 descs.append(d)
-            self.total_tiles = tiles
+            self.total_tiles, self.total_tiles2 = tiles, tiles2
             tab = _lib.upload_structs(descs, self.dev)
             if len(self._tables) > 4:       # the autograd path hands in fresh grads every backward
                 self._tables = {k: v for k, v in self._tables.items() if k is None}
@@ -521,7 +529,7 @@ class WeightSet:
 
     def prep(self):
         tab = self._table(None)
-        call("artic_weights_prep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
+        call("artic_weights_prep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles, self.total_tiles2)
         if self.W3 is not None:
             call("artic_split", ptr(self.W3), ptr(self.W3_sp), self.x3_total, self.x3_total)
 
@@ -532,7 +540,7 @@ class WeightSet:
         """dW (prepared layout) -> dv / dg of the torch parameters (OVERWRITES those entries of
         ``grads``; bias gradients were accumulated by ConvLayer.wgrad)."""
         tab = self._table(grads)
-        call("artic_weights_unprep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles)
+        call("artic_weights_unprep", ptr(tab), len(self.layers), self.any_norm, self.total_tiles, self.total_tiles2)
 
 
 def _zero_grads_like(layers: List[ConvLayer]) -> Dict[str, torch.Tensor]:

@@ -206,17 +206,24 @@ typedef struct {
   void* out_f; void* out_b;
   const float* dWp; float* dv; float* dg;
   int64_t row_len, sk, sg, sa, sb;
-  int64_t tile_begin;   /* exclusive prefix sum of artic_wperm_tiles() over the table */
+  int64_t tile_begin;   /* exclusive prefix sum of artic_wperm_tiles() over the layers the generic kernels take */
+  int64_t tile2_begin;  /* exclusive prefix sum of artic_wrow_tiles() (row-run kernels, the default) */
   int32_t rows, K, G, A, B, merge, a_pad, b_pad, dtype_f, dtype_b, dw_swapped, reserved_;
 } artic_wdesc_t;
 
-/* Number of relayout tiles of one layer (host helper: fills tile_begin / total_tiles). */
+/* Host helpers that size the two relayout tile spaces.  A layer is taken by the ROW-RUN kernels (whole torch rows of
+ * 32 x TI x K tiles, 16-byte accesses on both sides) when artic_wrow_tiles() > 0 — every conv / linear / transposed
+ * conv weight whose taps are the innermost torch index and K <= 352 — and then counts 0 generic tiles; otherwise it
+ * counts artic_wperm_tiles() generic tiles (32 x 32 x <= 8 taps, any strides). */
 int64_t artic_wperm_tiles(int32_t K, int32_t G, int32_t A, int32_t B);
-/* scale + out_f + out_b of every descriptor (any_norm = 0 skips the norm pass); total_tiles = sum of
- * artic_wperm_tiles over the table. */
-int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles, void* stream);
+int64_t artic_wrow_tiles(int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sa, int64_t sb);
+/* scale + out_f + out_b of every descriptor (any_norm = 0 skips the norm pass); total_tiles / total_tiles2 = the sums
+ * behind tile_begin / tile2_begin. */
+int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles,
+                       int64_t total_tiles2, void* stream);
 /* Backward of artic_weights_prep: dWp -> dv (and dg, through the weight-norm Jacobian). */
-int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles, void* stream);
+int artic_weights_unprep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles,
+                         int64_t total_tiles2, void* stream);
 
 /* ---- small fused elementwise ops on the path ---------------------------------------- */
 
