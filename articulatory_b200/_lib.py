@@ -78,7 +78,7 @@ class WDesc(C.Structure):
                 ("tile_begin", C.c_int64), ("tile2_begin", C.c_int64),
                 ("rows", C.c_int32), ("K", C.c_int32), ("G", C.c_int32), ("A", C.c_int32), ("B", C.c_int32),
                 ("merge", C.c_int32), ("a_pad", C.c_int32), ("b_pad", C.c_int32),
-                ("dtype_f", C.c_int32), ("dtype_b", C.c_int32), ("dw_swapped", C.c_int32), ("reserved_", C.c_int32)]
+                ("dtype_f", C.c_int32), ("dtype_b", C.c_int32), ("dw_swapped", C.c_int32), ("row_chunk", C.c_int32)]
 
 
 def upload_structs(items, device):
@@ -105,7 +105,7 @@ SIGNATURES = {
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),
     "artic_colsum": (C.c_int, [_p, C.POINTER(Seq), _i32, _i32, _i32, _p, _p]),
     "artic_wperm_tiles": (C.c_int64, [_i32, _i32, _i32, _i32]),
-    "artic_wrow_tiles": (C.c_int64, [_i32, _i32, _i32, _i32, _i64, _i64, _i64]),
+    "artic_wrow_tiles": (C.c_int64, [_i32, _i32, _i32, _i32, _i64, _i64, _i64, _i32]),
     "artic_weights_prep": (C.c_int, [_p, _i32, _i32, _i64, _i64, _p]),
     "artic_weights_unprep": (C.c_int, [_p, _i32, _i32, _i64, _i64, _p]),
     "artic_gen_input": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -526,6 +526,8 @@ __global__ void __launch_bounds__(256) wn_bwd4_kernel(const artic_wdesc_t* __res
 constexpr int RT_O = 32;
 constexpr int RT_RUN = 352;
 constexpr int RT_SMEM = RT_O * (RT_RUN + 1);
+constexpr int RT_CHUNK_MAX = 8;      // inner tiles per work unit (artic_wdesc_t.row_chunk: the unit's index arithmetic is done once)
+constexpr int RT_WPL = RT_RUN / 32;  // 32-bit words per lane per row
 
 __host__ __device__ __forceinline__ int rt_inner(int K) {
   int ti = 32;
@@ -533,39 +535,69 @@ __host__ __device__ __forceinline__ int rt_inner(int K) {
   return ti;
 }
 
+struct RUnit {                      // one work unit: 32 outer rows x up to RT_CHUNK inner tiles of one group
+  uint32_t O, I, TI, K, g, o0, no, it0, it1, pitch, s_out, kstride;
+  uint32_t tb0;                     // torch offset of (g, o0, inner 0)
+  uint32_t base_f0, base_b0;        // prepared offsets of (k = 0, a/b origin of the unit with inner index 0)
+  bool a_inner;
+};
+
 struct RTile {
   uint32_t no, ni, run, pitch;      // live outer rows / inner columns, ni * K, smem row pitch
   uint32_t tb, s_out;               // torch offset of the tile's first row, torch row stride
   uint32_t base1, pitch1, base2, pitch2, kstride;
-  bool a_inner;
+  uint32_t lg_ti;                   // log2(TI) when the tile is full (32 outer x TI inner), else 0xffffffff
 };
 
-__device__ __forceinline__ RTile rt_geom(const artic_wdesc_t& d, long long gt) {
-  RTile t;
-  const uint32_t K = (uint32_t)d.K;
-  t.a_inner = d.sa < d.sb || (d.sa == d.sb && d.A == 1);
-  const uint32_t O = t.a_inner ? d.B : d.A, I = t.a_inner ? d.A : d.B;
-  const uint32_t TI = (uint32_t)rt_inner(d.K);
-  const uint32_t n_it = (I + TI - 1) / TI, n_ot = (O + RT_O - 1) / RT_O;
+__device__ __forceinline__ RUnit rt_unit(const artic_wdesc_t& d, long long gt) {
+  RUnit u;
+  u.K = (uint32_t)d.K;
+  u.a_inner = d.sa < d.sb || (d.sa == d.sb && d.A == 1);
+  u.O = u.a_inner ? d.B : d.A; u.I = u.a_inner ? d.A : d.B;
+  u.TI = (uint32_t)rt_inner(d.K);
+  const uint32_t ch = (uint32_t)max(1, min(d.row_chunk, RT_CHUNK_MAX));
+  const uint32_t n_it = (u.I + u.TI - 1) / u.TI, n_ic = (n_it + ch - 1) / ch, n_ot = (u.O + RT_O - 1) / RT_O;
   uint32_t w = (uint32_t)(gt - d.tile2_begin);
-  const uint32_t it = w % n_it; w /= n_it;
+  const uint32_t ic = w % n_ic; w /= n_ic;
   const uint32_t ot = w % n_ot;
-  const uint32_t g = w / n_ot;
-  const uint32_t o0 = ot * RT_O, i0 = it * TI;
-  t.no = min((uint32_t)RT_O, O - o0);
-  t.ni = min(TI, I - i0);
-  t.run = t.ni * K;
-  t.pitch = (TI * K) | 1u;
-  t.s_out = (uint32_t)(t.a_inner ? d.sb : d.sa);
-  t.tb = g * (uint32_t)d.sg + o0 * t.s_out + i0 * K;
-  const uint32_t m = d.merge, Gs = d.G / m, gm = g % m, gd = g / m;
-  t.kstride = Gs * (uint32_t)d.a_pad * (uint32_t)d.b_pad;
-  const uint32_t a0 = t.a_inner ? i0 : o0, b0 = t.a_inner ? o0 : i0;
-  const uint32_t base_f = (gd * d.a_pad + gm * d.A + a0) * d.b_pad + gm * d.B + b0;   // [k][a][b]
-  const uint32_t base_b = (gd * d.b_pad + gm * d.B + b0) * d.a_pad + gm * d.A + a0;   // [k][b][a]
-  if (t.a_inner) { t.base1 = base_f; t.pitch1 = d.b_pad; t.base2 = base_b; t.pitch2 = d.a_pad; }
-  else           { t.base1 = base_b; t.pitch1 = d.a_pad; t.base2 = base_f; t.pitch2 = d.b_pad; }
+  u.g = w / n_ot;
+  u.o0 = ot * RT_O;
+  u.no = min((uint32_t)RT_O, u.O - u.o0);
+  u.it0 = ic * ch; u.it1 = min(n_it, u.it0 + ch);
+  u.pitch = (u.TI * u.K) | 1u;
+  u.s_out = (uint32_t)(u.a_inner ? d.sb : d.sa);
+  u.tb0 = u.g * (uint32_t)d.sg + u.o0 * u.s_out;
+  const uint32_t m = d.merge, Gs = d.G / m, gm = u.g % m, gd = u.g / m;
+  u.kstride = Gs * (uint32_t)d.a_pad * (uint32_t)d.b_pad;
+  const uint32_t a0 = u.a_inner ? 0 : u.o0, b0 = u.a_inner ? u.o0 : 0;
+  u.base_f0 = (gd * d.a_pad + gm * d.A + a0) * d.b_pad + gm * d.B + b0;   // [k][a][b]
+  u.base_b0 = (gd * d.b_pad + gm * d.B + b0) * d.a_pad + gm * d.A + a0;   // [k][b][a]
+  return u;
+}
+
+__device__ __forceinline__ RTile rt_tile(const artic_wdesc_t& d, const RUnit& u, uint32_t it) {
+  RTile t;
+  const uint32_t i0 = it * u.TI;
+  t.no = u.no;
+  t.ni = min(u.TI, u.I - i0);
+  t.run = t.ni * u.K;
+  t.pitch = u.pitch;
+  t.s_out = u.s_out;
+  t.tb = u.tb0 + i0 * u.K;
+  t.kstride = u.kstride;
+  if (u.a_inner) { t.base1 = u.base_f0 + i0 * d.b_pad; t.pitch1 = d.b_pad; t.base2 = u.base_b0 + i0; t.pitch2 = d.a_pad; }
+  else           { t.base1 = u.base_b0 + i0 * d.a_pad; t.pitch1 = d.a_pad; t.base2 = u.base_f0 + i0; t.pitch2 = d.b_pad; }
+  t.lg_ti = (t.no == RT_O && t.ni == u.TI) ? (uint32_t)(31 - __clz((int)u.TI)) : 0xffffffffu;
   return t;
+}
+
+__device__ __forceinline__ int rt_find(const artic_wdesc_t* __restrict__ descs, int n_layers, long long gt) {
+  int lo = 0, hi = n_layers - 1;                       // last layer with tile2_begin <= gt
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&descs[mid].tile2_begin) <= gt) lo = mid; else hi = mid - 1;
+  }
+  return lo;
 }
 
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
@@ -576,7 +608,7 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
 // One 16-byte item of a prepared layout: E consecutive elements read from shared memory at stride `ss`
 template <typename T> struct RtItem;
 template <> struct RtItem<__nv_bfloat16> {
-  static constexpr int E = 8;
+  static constexpr int E = 8, LG = 3;
   static __device__ __forceinline__ void store(__nv_bfloat16* dst, const float* src, uint32_t ss, uint32_t n) {
     if (n == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
       uint4 q;
@@ -589,7 +621,7 @@ template <> struct RtItem<__nv_bfloat16> {
   }
 };
 template <> struct RtItem<float> {
-  static constexpr int E = 4;
+  static constexpr int E = 4, LG = 2;
   static __device__ __forceinline__ void store(float* dst, const float* src, uint32_t ss, uint32_t n) {
     if (n == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
       *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[ss], src[2 * ss], src[3 * ss]);
@@ -599,10 +631,19 @@ template <> struct RtItem<float> {
   }
 };
 
-// tile (shared memory, [o][i * K + k]) -> X1 (outer-fastest): items (k, i, group of E outer rows)
+// tile (shared memory, [o][i * K + k]) -> X1 (outer-fastest): items (k, i, group of E outer rows), groups fastest
 template <typename T>
 __device__ __forceinline__ void rt_store_x1(T* out, const float* tile, const RTile& t, uint32_t K) {
   constexpr uint32_t E = RtItem<T>::E;
+  if (t.lg_ti != 0xffffffffu) {                       // full tile: shifts instead of divisions
+    constexpr uint32_t LGG = 5 - RtItem<T>::LG;       // log2(groups per (k, i)) = log2(32 / E)
+    const uint32_t total = K << (t.lg_ti + LGG);
+    for (uint32_t q = threadIdx.x; q < total; q += 256) {
+      const uint32_t o = (q & ((1u << LGG) - 1)) * E, i = (q >> LGG) & ((1u << t.lg_ti) - 1), k = q >> (LGG + t.lg_ti);
+      RtItem<T>::store(out + t.base1 + k * t.kstride + i * t.pitch1 + o, tile + o * t.pitch + i * K + k, t.pitch, E);
+    }
+    return;
+  }
   const uint32_t ng = (t.no + E - 1) / E;
   const uint32_t per_k = t.ni * ng, total = K * per_k;
   for (uint32_t q = threadIdx.x; q < total; q += 256) {
@@ -613,10 +654,19 @@ __device__ __forceinline__ void rt_store_x1(T* out, const float* tile, const RTi
   }
 }
 
-// tile -> X2 (inner-fastest): items (k, o, group of E inner columns)
+// tile -> X2 (inner-fastest): items (k, o, group of E inner columns), groups fastest
 template <typename T>
 __device__ __forceinline__ void rt_store_x2(T* out, const float* tile, const RTile& t, uint32_t K) {
   constexpr uint32_t E = RtItem<T>::E;
+  if (t.lg_ti != 0xffffffffu && t.lg_ti >= RtItem<T>::LG) {
+    const uint32_t lgg = t.lg_ti - RtItem<T>::LG;     // log2(groups per (k, o))
+    const uint32_t total = K << (lgg + 5);
+    for (uint32_t q = threadIdx.x; q < total; q += 256) {
+      const uint32_t i = (q & ((1u << lgg) - 1)) * E, o = (q >> lgg) & 31u, k = q >> (lgg + 5);
+      RtItem<T>::store(out + t.base2 + k * t.kstride + o * t.pitch2 + i, tile + o * t.pitch + i * K + k, K, E);
+    }
+    return;
+  }
   const uint32_t ng = (t.ni + E - 1) / E;
   const uint32_t per_k = t.no * ng, total = K * per_k;
   for (uint32_t q = threadIdx.x; q < total; q += 256) {
@@ -628,72 +678,64 @@ __device__ __forceinline__ void rt_store_x2(T* out, const float* tile, const RTi
 }
 
 __global__ void __launch_bounds__(256) wprep_rows_kernel(const artic_wdesc_t* __restrict__ descs, int n_layers,
-                                                         long long total_tiles) {
+                                                         long long total_units) {
   __shared__ float tile[RT_SMEM];
-  const int lane = threadIdx.x & 31, w8 = threadIdx.x >> 5;
-  for (long long gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
-    int lo = 0, hi = n_layers - 1;                       // last layer with tile2_begin <= gt
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(&descs[mid].tile2_begin) <= gt) lo = mid; else hi = mid - 1;
-    }
-    const artic_wdesc_t& d = descs[lo];
-    const RTile t = rt_geom(d, gt);
-    const uint32_t K = (uint32_t)d.K;
+  const uint32_t lane = threadIdx.x & 31, w8 = threadIdx.x >> 5;
+  for (long long gt = blockIdx.x; gt < total_units; gt += gridDim.x) {
+    const artic_wdesc_t& d = descs[rt_find(descs, n_layers, gt)];
+    const RUnit u = rt_unit(d, gt);
     const float* __restrict__ v = d.v;
     const float* __restrict__ scale = d.g != nullptr ? d.scale : nullptr;
-    const uint32_t row_len = (uint32_t)d.row_len;
-    // ---- torch rows -> shared memory (weight-norm scale applied): warp w8 takes rows w8, w8 + 8, ...
-    const bool vec = (t.run & 3) == 0 && (t.s_out & 3) == 0 && (reinterpret_cast<uintptr_t>(v + t.tb) & 15) == 0;
-    if (vec) {
-      const uint32_t r4 = t.run >> 2;                    // <= 88 float4 per row: <= 3 per lane
-      float4 x[4][3];
-      float sc[4];
+    void* p1 = u.a_inner ? d.out_f : d.out_b;
+    void* p2 = u.a_inner ? d.out_b : d.out_f;
+    const int dt1 = u.a_inner ? d.dtype_f : d.dtype_b, dt2 = u.a_inner ? d.dtype_b : d.dtype_f;
+    // weight-norm scale of this warp's four rows (a row of the tile lies inside ONE torch row)
+    float sc[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t r = w8 + 8 * i;
-        const uint32_t src0 = t.tb + r * t.s_out;
-        sc[i] = (r < t.no && scale != nullptr) ? __ldg(scale + src0 / row_len) : 1.f;
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t r = w8 + 8 * i;
+      sc[i] = (r < u.no && scale != nullptr) ? __ldg(scale + (u.tb0 + r * u.s_out) / (uint32_t)d.row_len) : 1.f;
+    }
+    for (uint32_t it = u.it0; it < u.it1; ++it) {
+      const RTile t = rt_tile(d, u, it);
+      // ---- torch rows -> shared memory, lane-consecutive words (conflict-free stores), all loads of a row pair issued
+      // before their first use
+      const int nw = (int)((t.run + 31) >> 5);
 #pragma unroll
-        for (int it = 0; it < 3; ++it) {
-          const uint32_t e = lane + 32 * it;
-          x[i][it] = (r < t.no && e < r4) ? __ldg(reinterpret_cast<const float4*>(v + src0) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int h = 0; h < 2; ++h) {
+        float x[2][RT_WPL];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t r = w8 + 8 * (2 * h + i);
+          const float* src = v + t.tb + r * t.s_out;
+#pragma unroll
+          for (int j = 0; j < RT_WPL; ++j) {
+            const uint32_t e = lane + 32 * j;
+            x[i][j] = (j < nw && r < t.no && e < t.run) ? __ldg(src + e) : 0.f;
+          }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t r = w8 + 8 * i;
-        float* dst = tile + r * t.pitch;
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t r = w8 + 8 * (2 * h + i);
+          float* dst = tile + r * t.pitch;
 #pragma unroll
-        for (int it = 0; it < 3; ++it) {
-          const uint32_t e = lane + 32 * it;
-          if (r < t.no && e < r4) {
-            dst[4 * e] = x[i][it].x * sc[i]; dst[4 * e + 1] = x[i][it].y * sc[i];
-            dst[4 * e + 2] = x[i][it].z * sc[i]; dst[4 * e + 3] = x[i][it].w * sc[i];
+          for (int j = 0; j < RT_WPL; ++j) {
+            const uint32_t e = lane + 32 * j;
+            if (j < nw && r < t.no && e < t.run) dst[e] = x[i][j] * sc[2 * h + i];
           }
         }
       }
-    } else {
-      for (uint32_t r = w8; r < t.no; r += 8) {
-        const uint32_t src0 = t.tb + r * t.s_out;
-        const float sc = scale != nullptr ? __ldg(scale + src0 / row_len) : 1.f;
-        float* dst = tile + r * t.pitch;
-        for (uint32_t e = lane; e < t.run; e += 32) dst[e] = __ldg(v + src0 + e) * sc;
+      __syncthreads();
+      if (p1 != nullptr) {
+        if (dt1 == ARTIC_BF16) rt_store_x1(reinterpret_cast<__nv_bfloat16*>(p1), tile, t, u.K);
+        else rt_store_x1(reinterpret_cast<float*>(p1), tile, t, u.K);
       }
+      if (p2 != nullptr) {
+        if (dt2 == ARTIC_BF16) rt_store_x2(reinterpret_cast<__nv_bfloat16*>(p2), tile, t, u.K);
+        else rt_store_x2(reinterpret_cast<float*>(p2), tile, t, u.K);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    void* p1 = t.a_inner ? d.out_f : d.out_b;
-    void* p2 = t.a_inner ? d.out_b : d.out_f;
-    const int dt1 = t.a_inner ? d.dtype_f : d.dtype_b, dt2 = t.a_inner ? d.dtype_b : d.dtype_f;
-    if (p1 != nullptr) {
-      if (dt1 == ARTIC_BF16) rt_store_x1(reinterpret_cast<__nv_bfloat16*>(p1), tile, t, K);
-      else rt_store_x1(reinterpret_cast<float*>(p1), tile, t, K);
-    }
-    if (p2 != nullptr) {
-      if (dt2 == ARTIC_BF16) rt_store_x2(reinterpret_cast<__nv_bfloat16*>(p2), tile, t, K);
-      else rt_store_x2(reinterpret_cast<float*>(p2), tile, t, K);
-    }
-    __syncthreads();
   }
 }
 
@@ -701,67 +743,79 @@ __global__ void __launch_bounds__(256) wprep_rows_kernel(const artic_wdesc_t* __
 // dw_swapped layers: outer-fastest (X1) for conv / linear and for swapped transposed convs, inner-fastest (X2) for
 // transposed convs in the CUDA-core modes.
 __global__ void __launch_bounds__(256) wunprep_rows_kernel(const artic_wdesc_t* __restrict__ descs, int n_layers,
-                                                           long long total_tiles) {
+                                                           long long total_units) {
   __shared__ float tile[RT_SMEM];
-  const int lane = threadIdx.x & 31, w8 = threadIdx.x >> 5;
-  for (long long gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
-    int lo = 0, hi = n_layers - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(&descs[mid].tile2_begin) <= gt) lo = mid; else hi = mid - 1;
-    }
-    const artic_wdesc_t& d = descs[lo];
+  const uint32_t lane = threadIdx.x & 31, w8 = threadIdx.x >> 5;
+  for (long long gt = blockIdx.x; gt < total_units; gt += gridDim.x) {
+    const artic_wdesc_t& d = descs[rt_find(descs, n_layers, gt)];
     if (d.dv == nullptr || d.dWp == nullptr) continue;
-    const RTile t = rt_geom(d, gt);
-    const uint32_t K = (uint32_t)d.K;
+    const RUnit u = rt_unit(d, gt);
+    const uint32_t K = u.K;
     const float* __restrict__ src = d.dWp;
-    // which of the two layouts holds the gradient, seen from the tile: 'fwd' = X1 iff a_inner
-    const bool x1 = (d.dw_swapped == 0) == t.a_inner;
-    if (x1) {
-      const uint32_t ng = (t.no + 3) >> 2, per_k = t.ni * ng, total = K * per_k;
-      for (uint32_t q = threadIdx.x; q < total; q += 256) {
-        const uint32_t k = q / per_k, r = q - k * per_k;
-        const uint32_t i = r / ng, o = (r - i * ng) * 4;
-        const float* p = src + t.base1 + k * t.kstride + i * t.pitch1 + o;
-        float* dst = tile + o * t.pitch + i * K + k;
-        const uint32_t n = min(4u, t.no - o);
-        if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-          const float4 x = __ldg(reinterpret_cast<const float4*>(p));
-          dst[0] = x.x; dst[t.pitch] = x.y; dst[2 * t.pitch] = x.z; dst[3 * t.pitch] = x.w;
-        } else {
-          for (uint32_t j = 0; j < n; ++j) dst[j * t.pitch] = __ldg(p + j);
-        }
-      }
-    } else {
-      const uint32_t ng = (t.ni + 3) >> 2, per_k = t.no * ng, total = K * per_k;
-      for (uint32_t q = threadIdx.x; q < total; q += 256) {
-        const uint32_t k = q / per_k, r = q - k * per_k;
-        const uint32_t o = r / ng, i = (r - o * ng) * 4;
-        const float* p = src + t.base2 + k * t.kstride + o * t.pitch2 + i;
-        float* dst = tile + o * t.pitch + i * K + k;
-        const uint32_t n = min(4u, t.ni - i);
-        if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-          const float4 x = __ldg(reinterpret_cast<const float4*>(p));
-          dst[0] = x.x; dst[K] = x.y; dst[2 * K] = x.z; dst[3 * K] = x.w;
-        } else {
-          for (uint32_t j = 0; j < n; ++j) dst[j * K] = __ldg(p + j);
-        }
-      }
-    }
-    __syncthreads();
     float* __restrict__ dv = d.dv;
-    const bool vec = (t.run & 3) == 0 && (t.s_out & 3) == 0 && (reinterpret_cast<uintptr_t>(dv + t.tb) & 15) == 0;
-    for (uint32_t r = w8; r < t.no; r += 8) {
-      float* dst = dv + t.tb + r * t.s_out;
-      const float* s = tile + r * t.pitch;
-      if (vec) {
-        for (uint32_t e = 4 * lane; e < t.run; e += 128)
-          *reinterpret_cast<float4*>(dst + e) = make_float4(s[e], s[e + 1], s[e + 2], s[e + 3]);
+    // which of the two layouts holds the gradient, seen from the tile: 'fwd' = X1 iff a_inner
+    const bool x1 = (d.dw_swapped == 0) == u.a_inner;
+    for (uint32_t it = u.it0; it < u.it1; ++it) {
+      const RTile t = rt_tile(d, u, it);
+      if (x1) {
+        if (t.lg_ti != 0xffffffffu) {
+          const uint32_t total = K << (t.lg_ti + 3);               // items (k, i, 4 outer rows): 8 groups per (k, i)
+          for (uint32_t q = threadIdx.x; q < total; q += 256) {
+            const uint32_t o = (q & 7u) * 4, i = (q >> 3) & ((1u << t.lg_ti) - 1), k = q >> (3 + t.lg_ti);
+            const float* p = src + t.base1 + k * t.kstride + i * t.pitch1 + o;
+            float* dst = tile + o * t.pitch + i * K + k;
+            if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+              const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+              dst[0] = x.x; dst[t.pitch] = x.y; dst[2 * t.pitch] = x.z; dst[3 * t.pitch] = x.w;
+            } else {
+              for (uint32_t j = 0; j < 4; ++j) dst[j * t.pitch] = __ldg(p + j);
+            }
+          }
+        } else {
+          const uint32_t ng = (t.no + 3) >> 2, per_k = t.ni * ng, total = K * per_k;
+          for (uint32_t q = threadIdx.x; q < total; q += 256) {
+            const uint32_t k = q / per_k, r = q - k * per_k;
+            const uint32_t i = r / ng, o = (r - i * ng) * 4;
+            const float* p = src + t.base1 + k * t.kstride + i * t.pitch1 + o;
+            float* dst = tile + o * t.pitch + i * K + k;
+            const uint32_t n = min(4u, t.no - o);
+            if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+              const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+              dst[0] = x.x; dst[t.pitch] = x.y; dst[2 * t.pitch] = x.z; dst[3 * t.pitch] = x.w;
+            } else {
+              for (uint32_t j = 0; j < n; ++j) dst[j * t.pitch] = __ldg(p + j);
+            }
+          }
+        }
       } else {
-        for (uint32_t e = lane; e < t.run; e += 32) dst[e] = s[e];
+        const uint32_t ng = (t.ni + 3) >> 2, per_k = t.no * ng, total = K * per_k;
+        for (uint32_t q = threadIdx.x; q < total; q += 256) {
+          const uint32_t k = q / per_k, r = q - k * per_k;
+          const uint32_t o = r / ng, i = (r - o * ng) * 4;
+          const float* p = src + t.base2 + k * t.kstride + o * t.pitch2 + i;
+          float* dst = tile + o * t.pitch + i * K + k;
+          const uint32_t n = min(4u, t.ni - i);
+          if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+            dst[0] = x.x; dst[K] = x.y; dst[2 * K] = x.z; dst[3 * K] = x.w;
+          } else {
+            for (uint32_t j = 0; j < n; ++j) dst[j * K] = __ldg(p + j);
+          }
+        }
       }
+      __syncthreads();
+      // ---- shared memory -> torch rows, lane-consecutive words (conflict-free loads, 128-byte store segments)
+      for (uint32_t r = w8; r < t.no; r += 8) {
+        float* dst = dv + t.tb + r * t.s_out;
+        const float* s = tile + r * t.pitch;
+#pragma unroll
+        for (int j = 0; j < RT_WPL; ++j) {
+          const uint32_t e = lane + 32 * j;
+          if (e < t.run) dst[e] = s[e];
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -951,12 +1005,15 @@ extern "C" int64_t artic_wperm_tiles(int32_t K, int32_t G, int32_t A, int32_t B)
 }
 
 /* see include/artic.h */
-extern "C" int64_t artic_wrow_tiles(int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sa, int64_t sb) {
+extern "C" int64_t artic_wrow_tiles(int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sa, int64_t sb,
+                                    int32_t row_chunk) {
   if (K < 1 || G < 1 || A < 1 || B < 1 || K > RT_RUN) return 0;
   const bool a_inner = sa < sb || (sa == sb && A == 1);
   if ((a_inner ? sa : sb) != K || !(sk == 1 || K == 1)) return 0;      // taps must be the torch-inner index
   const int O = a_inner ? B : A, I = a_inner ? A : B, TI = rt_inner(K);
-  return (int64_t)G * ((O + RT_O - 1) / RT_O) * ((I + TI - 1) / TI);
+  const int n_it = (I + TI - 1) / TI;
+  const int ch = row_chunk < 1 ? 1 : (row_chunk > RT_CHUNK_MAX ? RT_CHUNK_MAX : row_chunk);
+  return (int64_t)G * ((O + RT_O - 1) / RT_O) * ((n_it + ch - 1) / ch);    // work units of <= row_chunk inner tiles
 }
 
 extern "C" int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles,

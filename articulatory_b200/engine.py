@@ -489,6 +489,11 @@ class WeightSet:
             descs = []
             tiles = tiles2 = 0
             lib = _lib.load()
+            # inner tiles per work unit of the row-run kernels: large nets amortise the per-unit index arithmetic over
+            # up to 8 tiles, small ones keep one tile per unit so that the grid still fills the machine
+            single = sum(lib.artic_wrow_tiles(l.spec.k, l.spec.groups, *l.spec.prep_strides("fwd")[:2],
+                                              *(l.spec.prep_strides("fwd")[i] for i in (2, 4, 5)), 1) for l in self.layers)
+            chunk = max(1, min(8, single // 2400))
             for l in self.layers:
                 s = l.spec
                 rows, row_len = s.wn_rows()
@@ -509,7 +514,8 @@ class WeightSet:
                 d.dw_swapped = int(l.dw_swapped)
                 d.tile_begin, d.tile2_begin = tiles, tiles2
                 # row-run kernels (the default; ARTIC_WEIGHTS_GENERIC=1 forces the generic tile kernels) ...
-                n2 = 0 if _WEIGHTS_GENERIC else lib.artic_wrow_tiles(s.k, s.groups, A, B, sk, sa, sb)
+                n2 = 0 if _WEIGHTS_GENERIC else lib.artic_wrow_tiles(s.k, s.groups, A, B, sk, sa, sb, chunk)
+                d.row_chunk = chunk
                 if n2 > 0:
                     tiles2 += n2
                 else:                                                           # ... or the generic tile kernels

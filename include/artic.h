@@ -208,7 +208,8 @@ typedef struct {
   int64_t row_len, sk, sg, sa, sb;
   int64_t tile_begin;   /* exclusive prefix sum of artic_wperm_tiles() over the layers the generic kernels take */
   int64_t tile2_begin;  /* exclusive prefix sum of artic_wrow_tiles() (row-run kernels, the default) */
-  int32_t rows, K, G, A, B, merge, a_pad, b_pad, dtype_f, dtype_b, dw_swapped, reserved_;
+  int32_t rows, K, G, A, B, merge, a_pad, b_pad, dtype_f, dtype_b, dw_swapped;
+  int32_t row_chunk;    /* row-run kernels: inner tiles per work unit (1..8), the value given to artic_wrow_tiles() */
 } artic_wdesc_t;
 
 /* Host helpers that size the two relayout tile spaces.  A layer is taken by the ROW-RUN kernels (whole torch rows of
@@ -216,7 +217,8 @@ typedef struct {
  * conv weight whose taps are the innermost torch index and K <= 352 — and then counts 0 generic tiles; otherwise it
  * counts artic_wperm_tiles() generic tiles (32 x 32 x <= 8 taps, any strides). */
 int64_t artic_wperm_tiles(int32_t K, int32_t G, int32_t A, int32_t B);
-int64_t artic_wrow_tiles(int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sa, int64_t sb);
+int64_t artic_wrow_tiles(int32_t K, int32_t G, int32_t A, int32_t B, int64_t sk, int64_t sa, int64_t sb,
+                         int32_t row_chunk);
 /* scale + out_f + out_b of every descriptor (any_norm = 0 skips the norm pass); total_tiles / total_tiles2 = the sums
  * behind tile_begin / tile2_begin. */
 int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t any_norm, int64_t total_tiles,
