@@ -609,6 +609,12 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
 template <typename T> struct RtItem;
 template <> struct RtItem<__nv_bfloat16> {
   static constexpr int E = 8, LG = 3;
+  static __device__ __forceinline__ void store_full(__nv_bfloat16* dst, const float* src, uint32_t ss) {
+    uint4 q;
+    q.x = pack_bf2(src[0], src[ss]); q.y = pack_bf2(src[2 * ss], src[3 * ss]);
+    q.z = pack_bf2(src[4 * ss], src[5 * ss]); q.w = pack_bf2(src[6 * ss], src[7 * ss]);
+    *reinterpret_cast<uint4*>(dst) = q;
+  }
   static __device__ __forceinline__ void store(__nv_bfloat16* dst, const float* src, uint32_t ss, uint32_t n) {
     if (n == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
       uint4 q;
@@ -622,6 +628,9 @@ template <> struct RtItem<__nv_bfloat16> {
 };
 template <> struct RtItem<float> {
   static constexpr int E = 4, LG = 2;
+  static __device__ __forceinline__ void store_full(float* dst, const float* src, uint32_t ss) {
+    *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[ss], src[2 * ss], src[3 * ss]);
+  }
   static __device__ __forceinline__ void store(float* dst, const float* src, uint32_t ss, uint32_t n) {
     if (n == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
       *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[ss], src[2 * ss], src[3 * ss]);
@@ -638,9 +647,18 @@ __device__ __forceinline__ void rt_store_x1(T* out, const float* tile, const RTi
   if (t.lg_ti != 0xffffffffu) {                       // full tile: shifts instead of divisions
     constexpr uint32_t LGG = 5 - RtItem<T>::LG;       // log2(groups per (k, i)) = log2(32 / E)
     const uint32_t total = K << (t.lg_ti + LGG);
-    for (uint32_t q = threadIdx.x; q < total; q += 256) {
-      const uint32_t o = (q & ((1u << LGG) - 1)) * E, i = (q >> LGG) & ((1u << t.lg_ti) - 1), k = q >> (LGG + t.lg_ti);
-      RtItem<T>::store(out + t.base1 + k * t.kstride + i * t.pitch1 + o, tile + o * t.pitch + i * K + k, t.pitch, E);
+    // every item 16-byte aligned?  (uniform: decided once per tile)
+    const bool al = ((t.base1 | t.kstride | t.pitch1) & (E - 1)) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (al) {
+      for (uint32_t q = threadIdx.x; q < total; q += 256) {
+        const uint32_t o = (q & ((1u << LGG) - 1)) * E, i = (q >> LGG) & ((1u << t.lg_ti) - 1), k = q >> (LGG + t.lg_ti);
+        RtItem<T>::store_full(out + t.base1 + k * t.kstride + i * t.pitch1 + o, tile + o * t.pitch + i * K + k, t.pitch);
+      }
+    } else {
+      for (uint32_t q = threadIdx.x; q < total; q += 256) {
+        const uint32_t o = (q & ((1u << LGG) - 1)) * E, i = (q >> LGG) & ((1u << t.lg_ti) - 1), k = q >> (LGG + t.lg_ti);
+        RtItem<T>::store(out + t.base1 + k * t.kstride + i * t.pitch1 + o, tile + o * t.pitch + i * K + k, t.pitch, E);
+      }
     }
     return;
   }
@@ -661,9 +679,17 @@ __device__ __forceinline__ void rt_store_x2(T* out, const float* tile, const RTi
   if (t.lg_ti != 0xffffffffu && t.lg_ti >= RtItem<T>::LG) {
     const uint32_t lgg = t.lg_ti - RtItem<T>::LG;     // log2(groups per (k, o))
     const uint32_t total = K << (lgg + 5);
-    for (uint32_t q = threadIdx.x; q < total; q += 256) {
-      const uint32_t i = (q & ((1u << lgg) - 1)) * E, o = (q >> lgg) & 31u, k = q >> (lgg + 5);
-      RtItem<T>::store(out + t.base2 + k * t.kstride + o * t.pitch2 + i, tile + o * t.pitch + i * K + k, K, E);
+    const bool al = ((t.base2 | t.kstride | t.pitch2) & (E - 1)) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (al) {
+      for (uint32_t q = threadIdx.x; q < total; q += 256) {
+        const uint32_t i = (q & ((1u << lgg) - 1)) * E, o = (q >> lgg) & 31u, k = q >> (lgg + 5);
+        RtItem<T>::store_full(out + t.base2 + k * t.kstride + o * t.pitch2 + i, tile + o * t.pitch + i * K + k, K);
+      }
+    } else {
+      for (uint32_t q = threadIdx.x; q < total; q += 256) {
+        const uint32_t i = (q & ((1u << lgg) - 1)) * E, o = (q >> lgg) & 31u, k = q >> (lgg + 5);
+        RtItem<T>::store(out + t.base2 + k * t.kstride + o * t.pitch2 + i, tile + o * t.pitch + i * K + k, K, E);
+      }
     }
     return;
   }
@@ -674,6 +700,39 @@ __device__ __forceinline__ void rt_store_x2(T* out, const float* tile, const RTi
     const uint32_t o = r / ng, ig = r - o * ng;
     const uint32_t i = ig * E;
     RtItem<T>::store(out + t.base2 + k * t.kstride + o * t.pitch2 + i, tile + o * t.pitch + i * K + k, K, min(E, t.ni - i));
+  }
+}
+
+// Rows w8, w8 + 8, w8 + 16, w8 + 24 of the tile, NW words per lane and row; the loads of two rows are issued before
+// their first use.
+template <int NW>
+__device__ __forceinline__ void rt_load_rows(float* tile, const float* __restrict__ v, const RTile& t, const float (&sc)[4],
+                                             uint32_t lane, uint32_t w8) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float x[2][NW];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t r = w8 + 8 * (2 * h + i);
+      const float* src = v + t.tb + r * t.s_out;
+      const uint32_t lim = r < t.no ? t.run : 0u;
+#pragma unroll
+      for (int j = 0; j < NW; ++j) {
+        const uint32_t e = lane + 32 * j;
+        x[i][j] = e < lim ? __ldg(src + e) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t r = w8 + 8 * (2 * h + i);
+      float* dst = tile + r * t.pitch;
+      const uint32_t lim = r < t.no ? t.run : 0u;
+#pragma unroll
+      for (int j = 0; j < NW; ++j) {
+        const uint32_t e = lane + 32 * j;
+        if (e < lim) dst[e] = x[i][j] * sc[2 * h + i];
+      }
+    }
   }
 }
 
@@ -698,33 +757,12 @@ __global__ void __launch_bounds__(256) wprep_rows_kernel(const artic_wdesc_t* __
     }
     for (uint32_t it = u.it0; it < u.it1; ++it) {
       const RTile t = rt_tile(d, u, it);
-      // ---- torch rows -> shared memory, lane-consecutive words (conflict-free stores), all loads of a row pair issued
-      // before their first use
-      const int nw = (int)((t.run + 31) >> 5);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float x[2][RT_WPL];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const uint32_t r = w8 + 8 * (2 * h + i);
-          const float* src = v + t.tb + r * t.s_out;
-#pragma unroll
-          for (int j = 0; j < RT_WPL; ++j) {
-            const uint32_t e = lane + 32 * j;
-            x[i][j] = (j < nw && r < t.no && e < t.run) ? __ldg(src + e) : 0.f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const uint32_t r = w8 + 8 * (2 * h + i);
-          float* dst = tile + r * t.pitch;
-#pragma unroll
-          for (int j = 0; j < RT_WPL; ++j) {
-            const uint32_t e = lane + 32 * j;
-            if (j < nw && r < t.no && e < t.run) dst[e] = x[i][j] * sc[2 * h + i];
-          }
-        }
-      }
+      // ---- torch rows -> shared memory, lane-consecutive words (conflict-free stores)
+      const uint32_t nw = (t.run + 31) >> 5;
+      if (nw <= 3) rt_load_rows<3>(tile, v, t, sc, lane, w8);
+      else if (nw <= 5) rt_load_rows<5>(tile, v, t, sc, lane, w8);
+      else if (nw <= 7) rt_load_rows<7>(tile, v, t, sc, lane, w8);
+      else rt_load_rows<RT_WPL>(tile, v, t, sc, lane, w8);
       __syncthreads();
       if (p1 != nullptr) {
         if (dt1 == ARTIC_BF16) rt_store_x1(reinterpret_cast<__nv_bfloat16*>(p1), tile, t, u.K);
@@ -808,11 +846,8 @@ __global__ void __launch_bounds__(256) wunprep_rows_kernel(const artic_wdesc_t* 
       for (uint32_t r = w8; r < t.no; r += 8) {
         float* dst = dv + t.tb + r * t.s_out;
         const float* s = tile + r * t.pitch;
-#pragma unroll
-        for (int j = 0; j < RT_WPL; ++j) {
-          const uint32_t e = lane + 32 * j;
-          if (e < t.run) dst[e] = s[e];
-        }
+#pragma unroll 4
+        for (uint32_t e = lane; e < t.run; e += 32) dst[e] = s[e];
       }
       __syncthreads();
     }
