@@ -126,10 +126,27 @@ template <> __device__ __forceinline__ float mlp_t<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 mlp_t<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 constexpr int MLP_THREADS = 1024;
 constexpr int MLP_MAX_DIM = 1024;
+__device__ __forceinline__ void mlp_ld8(const float* w, float (&x)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(w)), b = __ldg(reinterpret_cast<const float4*>(w) + 1);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void mlp_ld8(const __nv_bfloat16* w, float (&x)[8]) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(w));
+  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[i]));
+    x[2 * i] = f.x; x[2 * i + 1] = f.y;
+  }
+}
+
+// Each thread owns 8 consecutive output features (one 16- or 32-byte weight load per input feature) and a slice of
+// the input features; cout / 8 threads cover a weight row, 1024 / (cout / 8) slices split the reduction, whose
+// partial sums meet in shared memory.  A layer is 4 .. 16 dependent load rounds instead of 64 .. 128.
 template <typename T>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(const __grid_constant__ artic_mlp_t p) {
   __shared__ float h[MLP_MAX_DIM];
-  __shared__ float part[MLP_THREADS];
+  __shared__ __align__(16) float part[8 * MLP_THREADS];
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < p.dims[0]; i += MLP_THREADS) {
     const T v = mlp_t<T>(__ldg(p.in + (int64_t)b * p.dims[0] + i));   // the input enters in the storage type, as the tape keeps it
@@ -140,14 +157,23 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(const __grid_const
   for (int l = 0; l < p.n_layers; ++l) {
     const int cin = p.dims[l], cout = p.dims[l + 1];
     const T* __restrict__ W = reinterpret_cast<const T*>(p.W[l]);            // prepared layout [cin][cout]
-    const int groups = MLP_THREADS / cout;                                    // cout divides 1024 (checked by the host)
-    const int j = threadIdx.x % cout, g = threadIdx.x / cout;
-    const int per = (cin + groups - 1) / groups;
-    const int i0 = g * per, i1 = min(cin, i0 + per);
-    float acc = 0.f;
-#pragma unroll 8
-    for (int i = i0; i < i1; ++i) acc = fmaf(h[i], ld_f(W + (int64_t)i * cout + j), acc);
-    part[threadIdx.x] = acc;
+    const int tpr = cout >> 3;                                                // threads per weight row (host: cout % 8 == 0, tpr | 1024)
+    const int groups = MLP_THREADS / tpr;
+    const int jt = threadIdx.x % tpr, g = threadIdx.x / tpr;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int i = g; i < cin; i += groups) {
+      float w[8];
+      mlp_ld8(W + (int64_t)i * cout + jt * 8, w);
+      const float x = h[i];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(x, w[c], acc[c]);
+    }
+    float* pp = part + (size_t)g * cout + jt * 8;
+    *reinterpret_cast<float4*>(pp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     __syncthreads();
     if (threadIdx.x < cout) {
       float v = p.bias[l] != nullptr ? __ldg(p.bias[l] + threadIdx.x) : 0.f;
@@ -420,7 +446,11 @@ extern "C" int artic_mlp_fwd(const artic_mlp_t* p, void* stream) {
   for (int l = 0; l <= p->n_layers; ++l) ARTIC_CHECK_ARG(p->dims[l] >= 1 && p->dims[l] <= MLP_MAX_DIM, "layer width out of range");
   for (int l = 0; l < p->n_layers; ++l) {
     ARTIC_CHECK_ARG(p->W[l] != nullptr, "null weight");
-    if (MLP_THREADS % p->dims[l + 1] != 0) { set_error("artic_mlp_fwd: output widths must divide %d", MLP_THREADS); return ARTIC_ENOSUP; }
+    const int co = p->dims[l + 1];
+    if (co % 8 != 0 || MLP_THREADS % (co / 8) != 0 || (reinterpret_cast<uintptr_t>(p->W[l]) & 15) != 0) {
+      set_error("artic_mlp_fwd: output widths must be 8 x a divisor of %d, weights 16-byte aligned", MLP_THREADS);
+      return ARTIC_ENOSUP;
+    }
   }
   if (p->B == 0) return ARTIC_OK;
   if (p->dtype == ARTIC_BF16) mlp_fwd_kernel<__nv_bfloat16><<<p->B, MLP_THREADS, 0, ST(stream)>>>(*p);

@@ -627,15 +627,26 @@ _D_OBJECTIVE = int(_os.environ.get("ARTIC_D_OBJECTIVE", "100"))  # the discrimin
 
 
 def mlp_forward(x: torch.Tensor, lays, acts, code: int, slope: float):
-    """Linear -> [LeakyReLU -> Linear] x (n - 1) in ONE launch (artic_mlp_fwd): x (B, dims[0]) fp32, acts[0] receives x
-    in the storage type, acts[l + 1] layer l's output (activated for all but the last)."""
+    """Linear -> [LeakyReLU -> Linear] x (n - 1): x (B, dims[0]) fp32, acts[0] receives x in the storage type,
+    acts[l + 1] layer l's output (activated for all but the last).  ONE launch (artic_mlp_fwd) when the widths allow,
+    else one tap-conv launch per layer."""
+    dims = [lays[0].spec.cin] + [lay.spec.cout for lay in lays]
+    fused = len(lays) <= 8 and max(dims) <= 1024 and all(c % 8 == 0 and 1024 % (c // 8) == 0 for c in dims[1:]) and \
+        all(lay.kcig == lay.spec.cin and lay.kcog == lay.spec.cout and lay.in_code == code for lay in lays)
+    if not fused:
+        call("artic_cast", ptr(x), F32, ptr(acts[0].t), code, x.numel())
+        for l, lay in enumerate(lays):
+            if l < len(lays) - 1:
+                lay.forward(acts[l], Y2=acts[l + 1], act=ACT_LRELU, act_slope=slope)
+            else:
+                lay.forward(acts[l], Y=acts[l + 1])
+        return
     p = _lib.Mlp()
     p.in_, p.act0 = ptr(x), ptr(acts[0].t)
     p.B, p.n_layers, p.dtype, p.slope = acts[0].N, len(lays), code, slope
-    p.dims[0] = lays[0].spec.cin
+    for l, d in enumerate(dims):
+        p.dims[l] = d
     for l, lay in enumerate(lays):
-        assert lay.kcig == lay.spec.cin and lay.kcog == lay.spec.cout and lay.in_code == code
-        p.dims[l + 1] = lay.spec.cout
         p.W[l], p.bias[l], p.outs[l] = ptr(lay.Wf), ptr(lay.b), ptr(acts[l + 1].t)
     call("artic_mlp_fwd", p)
 

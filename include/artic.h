@@ -243,7 +243,7 @@ int artic_gen_input_bwd(const void* dX, float* d_ar, int32_t B, int32_t Cc, int3
  * launch, one batch item per thread block.  in: (B, dims[0]) fp32; W[l]: prepared weight [dims[l]][dims[l+1]] in `dtype`
  * (artic_weights_prep `out_f` of a linear layer); bias[l]: fp32 or NULL; act0 (optional): the input cast to `dtype`;
  * outs[l] (optional): the layer's output (B, dims[l+1]) in `dtype` — activated for all but the last layer.  Widths
- * <= 1024, output widths must divide 1024. */
+ * <= 1024; output widths 8 x a divisor of 1024 (else ARTIC_ENOSUP: the caller runs the layers one by one). */
 typedef struct {
   const float* in;
   const void* W[8];

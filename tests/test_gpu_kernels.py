@@ -506,15 +506,16 @@ def _bf16_round(t):
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
-@pytest.mark.parametrize("B", [1, 16, 33])
-def test_fused_past_fc_encoder(dtype, B):
+@pytest.mark.parametrize("B,hidden", [(1, 256), (16, 256), (33, 256), (5, 100)])
+def test_fused_past_fc_encoder(dtype, B, hidden):
     """artic_mlp_fwd (the PastFCEncoder, 5 Linear layers with LeakyReLU(0.1) between, one launch) against torch float64 on
-    the same (storage-rounded) weights; every saved activation is compared, not only the result."""
+    the same (storage-rounded) weights; every saved activation is compared, not only the result.  hidden = 100 is a
+    width the one-launch kernel does not take: the same call then runs the layers one by one."""
     from articulatory_b200.engine import mlp_forward
     torch.manual_seed(B)
     code = F32 if dtype == "f32" else BF16
     rnd = (lambda t: t.double()) if dtype == "f32" else _bf16_round
-    dims = [512, 256, 256, 256, 256, 128]
+    dims = [512, hidden, hidden, hidden, hidden, 128]
     ws = [torch.randn(dims[i + 1], dims[i]) / math.sqrt(dims[i]) for i in range(5)]
     bs = [torch.randn(dims[i + 1]) * 0.1 for i in range(5)]
     x = torch.randn(B, 512)
@@ -530,7 +531,7 @@ def test_fused_past_fc_encoder(dtype, B):
     launches = _lib.launch_count
     mlp_forward(x.to(DEV), lays, acts, code, 0.1)
     torch.cuda.synchronize()
-    assert _lib.launch_count - launches == 1
+    assert _lib.launch_count - launches == (1 if hidden == 256 else 6)
     h = rnd(x)
     tol = 1e-5 if dtype == "f32" else 6e-3
     assert rel_err(acts[0].t.float().cpu().reshape(B, -1), h) < tol

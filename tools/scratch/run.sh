@@ -1,5 +1,9 @@
-python -m pytest tests/test_gpu_kernels.py -q -m gpu -x 2>&1 | tail -2
-python tools/weights_bench.py 2>&1 | tail -7
-ncu --set full --clock-control none --import-source on -k regex:'wprep_rows|wunprep_rows' -c 3 -o gpurun_out/weights_ncu3 -f python tools/weights_bench.py --ncu > /dev/null 2>&1
-ncu -i gpurun_out/weights_ncu3.ncu-rep --page raw --csv > gpurun_out/weights_ncu3_raw.csv
-ncu -i gpurun_out/weights_ncu3.ncu-rep --page source --csv --kernel-name wprep_rows_kernel > gpurun_out/weights_ncu3_src.csv 2>/dev/null
+python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "past_fc" 2>&1 | tail -3
+python -m pytest tests/test_gpu_models.py tests/test_gpu_plugins.py tests/test_gpu_inversion.py -q -m gpu -x 2>&1 | tail -2
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_mlp2.json 2>/dev/null
+python - <<'PY'
+import json
+for l in open('gpurun_out/bench_mlp2.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['ms_per_step'], d['car_inference']['ms_per_batch'])
+PY
