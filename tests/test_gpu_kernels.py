@@ -223,6 +223,35 @@ def test_small_ops():
         rs.step()
         assert torch.allclose(lin.weight.detach().cpu(), ref.weight.detach(), atol=1e-6), it
     assert opt.step_count() == 8
+    # every parameter starts on a 128-byte boundary of the flat buffers (the weight-side kernels' 16-byte row accesses)
+    assert all(o % 32 == 0 for o in opt.offsets.values()) and opt.flat.numel() == 96 + 32
+    assert all(v.data_ptr() % 128 == 0 for v in opt.views.values())
+
+
+def test_adam_reads_the_bf16_wire_buffer():
+    """artic_adam_step_wire with bf16 gradients (the data-parallel wire buffer, FusedAdam.wire) == torch.optim.Adam fed
+    the same bf16-rounded gradients; sizes with a scalar tail and a long vector body."""
+    from articulatory_b200.optim import FusedAdam
+    torch.manual_seed(1)
+    mod = torch.nn.Sequential(torch.nn.Linear(257, 129), torch.nn.Linear(129, 3)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(257, 129), torch.nn.Linear(129, 3))
+    ref.load_state_dict({k: v.cpu() for k, v in mod.state_dict().items()})
+    opt = FusedAdam(mod, lr=1e-3, betas=(0.5, 0.9), gamma=0.5, milestones=(2, 4))
+    opt.wire = torch.zeros(opt.grad.numel(), dtype=torch.bfloat16, device=DEV)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3, betas=(0.5, 0.9))
+    rs = torch.optim.lr_scheduler.MultiStepLR(ropt, gamma=0.5, milestones=[2, 4])
+    for it in range(5):
+        opt.grad.fill_(float("nan"))                          # the fp32 gradient buffer must not be read
+        for (n, p), rp in zip(mod.named_parameters(), ref.parameters()):
+            g = torch.randn(p.shape).to(torch.bfloat16)
+            o = opt.offsets[n]
+            opt.wire[o:o + g.numel()].copy_(g.reshape(-1))
+            rp.grad = g.float()
+        opt.step()
+        ropt.step()
+        rs.step()
+        for p, rp in zip(mod.parameters(), ref.parameters()):
+            assert torch.allclose(p.detach().cpu(), rp.detach(), atol=1e-6), it
 
 
 @pytest.mark.parametrize("res", [(1024, 120, 600), (2048, 240, 1200), (512, 50, 240), (1024, 80, 1024)])
