@@ -534,6 +534,78 @@ def _bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float64)
 
 
+WEIGHT_CASES = [
+    dict(kind="conv", cin=1024, cout=1024, k=5, stride=1, padding=2),                    # the discriminators' big layers
+    dict(kind="conv", cin=1024, cout=1024, k=41, stride=1, padding=20, groups=16),       # K = 41: 8 inner columns per tile
+    dict(kind="conv", cin=128, cout=256, k=41, stride=4, padding=20, groups=16),         # merged narrow groups (8 -> 16 per group)
+    dict(kind="conv", cin=128, cout=128, k=11, dilation=5, padding=25),                  # K = 11: 352-float rows
+    dict(kind="conv", cin=141, cout=256, k=7, padding=3),                                # padded input width
+    dict(kind="conv", cin=1, cout=128, k=15, padding=7),                                 # one input channel
+    dict(kind="conv", cin=32, cout=1, k=7, padding=3),                                   # one output channel
+    dict(kind="conv", cin=40, cout=72, k=3, padding=1),                                  # ragged tiles
+    dict(kind="convT", cin=256, cout=128, k=10, stride=5, padding=3, output_padding=1),  # outer = in-ch, even K
+    dict(kind="convT", cin=64, cout=32, k=4, stride=2, padding=1),
+    dict(kind="linear", cin=512, cout=256),
+]
+
+
+@pytest.mark.parametrize("case", range(len(WEIGHT_CASES)))
+@pytest.mark.parametrize("wn", [False, True])
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3", "fp32"])
+def test_row_run_weight_kernels_match_generic_tile_kernels(case, wn, prec, monkeypatch):
+    """artic_weights_prep / _unprep: the row-run kernels (default) against the generic 32 x 32 x 8-tap tile kernels
+    (ARTIC_WEIGHTS_GENERIC) on the same parameters — prepared weights BIT-identical in both layouts, gradients of v / g
+    equal up to the summation order of the weight-norm dot products — and against torch for the weight itself."""
+    from articulatory_b200 import engine
+    spec = ConvSpec(**WEIGHT_CASES[case])
+    if spec.kind == "linear" and wn:
+        pytest.skip("no weight norm on Linear")
+    code = BF16 if prec == "bf16" else F32
+    torch.manual_seed(100 + case)
+    v = torch.randn(spec.weight_shape()) / math.sqrt(spec.cig * spec.k)
+    params = {"l.bias": torch.randn(spec.cout).to(DEV)}
+    if wn:
+        params["l.weight_v"] = v.to(DEV).contiguous()
+        params["l.weight_g"] = (torch.rand(spec.weight_shape()[0], *([1] * (v.dim() - 1))) + 0.5).to(DEV).contiguous()
+    else:
+        params["l.weight"] = v.to(DEV).contiguous()
+    out = {}
+    for generic in (True, False):
+        monkeypatch.setattr(engine, "_WEIGHTS_GENERIC", generic)
+        lay = ConvLayer(spec, "l", code, code, pad_in=True, x3=prec == "bf16x3")
+        lay.bind(params)
+        lay.prep()
+        ws = lay._single()
+        assert (ws.total_tiles2 == 0) == generic and (ws.total_tiles == 0) != generic
+        g = torch.Generator(device="cpu").manual_seed(7)
+        lay.dWf.copy_(torch.randn(lay.dWf.shape, generator=g).to(DEV))
+        grads = {k: torch.full_like(t, float("nan")) for k, t in params.items()}
+        lay.finish_grads(grads)
+        torch.cuda.synchronize()
+        out[generic] = (lay.Wf.clone(), lay.Wb.clone(), {k: t.clone() for k, t in grads.items() if "weight" in k})
+    assert torch.equal(out[True][0], out[False][0]) and torch.equal(out[True][1], out[False][1])
+    for k in out[True][2]:
+        a, b = out[True][2][k], out[False][2][k]
+        assert torch.isfinite(b).all(), k
+        assert rel_err(b.cpu(), a.cpu()) < 1e-5, k
+    # the prepared 'fwd' weight against torch: w = g * v / ||v|| in the layout [K][G/m][a_pad][b_pad]
+    if wn:
+        gg = params["l.weight_g"].cpu().double()
+        vv = v.double()
+        w = gg * vv / vv.pow(2).sum(dim=tuple(range(1, vv.dim())), keepdim=True).sqrt()
+    else:
+        w = v.double()
+    lay_mg = lay.mg
+    if lay_mg == 1 and lay.kcig == spec.cig:
+        if spec.kind == "conv":       # [cout][cig][K] -> [K][G][cig][cog]
+            ref = w.view(spec.groups, spec.cog, spec.cig, spec.k).permute(3, 0, 2, 1)
+        elif spec.kind == "convT":    # [cin][cout][K] -> [K][1][cin][cout]
+            ref = w.permute(2, 0, 1).unsqueeze(1)
+        else:                         # [cout][cin] -> [1][1][cin][cout]
+            ref = w.t().reshape(1, 1, spec.cin, spec.cout)
+        assert rel_err(out[False][0].double().cpu(), ref) < (4e-3 if prec == "bf16" else 1e-6)
+
+
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("B,hidden", [(1, 256), (16, 256), (33, 256), (5, 100)])
 def test_fused_past_fc_encoder(dtype, B, hidden):
