@@ -170,8 +170,13 @@ def load():
     for kv in filter(None, os.environ.get("ARTIC_DEBUG", "").split(",")):
         k, v = kv.split("=")
         lib.artic_debug_set(int(k), int(v))
+        ENV_DEBUG[int(k)] = int(v)
     _lib = lib
     return lib
+
+
+#: raw debug keys set through ARTIC_DEBUG (scoped overrides restore these values)
+ENV_DEBUG = {}
 
 
 def stream_ptr():

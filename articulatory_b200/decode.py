@@ -14,6 +14,8 @@ from typing import List, Sequence
 
 import torch
 
+from .engine import weight_multicast
+
 
 def chunk_plan(n_frames: int, batch_max_steps: int, hop_size: int):
     """[(frame_lo, frame_hi, sample_lo, sample_hi)] of reference bin/decode.py:45-56."""
@@ -62,12 +64,13 @@ class BatchedARDecoder:
             s_prev = torch.zeros((B, 1, self.past), dtype=torch.float32, device=self.dev)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                                 # warm-up: lazy allocations, smem attributes
+            with torch.cuda.stream(side), weight_multicast(2):            # warm-up: lazy allocations, smem attributes
                 self._step_eager(s_cin, s_prev)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # few rows per chunk and three chains in flight: pairs of CTAs share the streamed weight tiles (TMA multicast)
+            with torch.cuda.graph(graph), weight_multicast(2):
                 cout, new_prev = self._step_eager(s_cin, s_prev)
                 s_prev.copy_(new_prev)
             g = (graph, s_cin, s_prev, cout)
