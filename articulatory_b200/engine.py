@@ -587,11 +587,19 @@ def weight_multicast(cluster_size: int):
     if 22 in _lib.ENV_DEBUG:
         yield
         return
+    _MCAST_STACK.append(int(cluster_size))
     lib.artic_debug_set(22, int(cluster_size))
     try:
         yield
     finally:
-        lib.artic_debug_set(22, 0)
+        _MCAST_STACK.pop()
+        lib.artic_debug_set(22, _MCAST_STACK[-1] if _MCAST_STACK else 0)
+
+
+_MCAST_STACK: List[int] = []
+#: experiment knobs: cluster weight multicast for the generator's forward / backward launches inside the train step
+_G_MCAST_FWD = int(_os.environ.get("ARTIC_G_MCAST_FWD", "0"))
+_G_MCAST_BWD = int(_os.environ.get("ARTIC_G_MCAST_BWD", "0"))
 
 
 #: ARTIC_FUSE_RES=0 turns the fused residual unit off (artic_resunit_fwd: conv1 -> LeakyReLU -> conv2 -> + x of the
@@ -740,6 +748,9 @@ class GeneratorEngine:
     def forward(self, c: torch.Tensor, ar: Optional[torch.Tensor], save=True):
         """c (B, Cc, T') fp32 channel-first, ar (B, 1, ar_input) fp32 -> ((B, 1, T) fp32, tape)."""
         with planner_objective(_G_OBJECTIVE):
+            if _G_MCAST_FWD:
+                with weight_multicast(_G_MCAST_FWD):
+                    return self._forward(c, ar, save)
             return self._forward(c, ar, save)
 
     def _forward(self, c, ar, save):
@@ -855,6 +866,9 @@ class GeneratorEngine:
         """dy: (B, C_out, T) fp32 gradient of the waveform.  Accumulates parameter gradients
         into ``grads`` (name -> fp32 tensor shaped like the parameter)."""
         with planner_objective(_G_OBJECTIVE):
+            if _G_MCAST_BWD:
+                with weight_multicast(_G_MCAST_BWD):
+                    return self._backward(tape, dy, grads)
             return self._backward(tape, dy, grads)
 
     def _backward(self, tape, dy, grads):
