@@ -1,4 +1,11 @@
 // Weight preparation (weight-norm + relayout), its backward, and the fused Adam step.
+//
+// Three generations of the relayout live here; the host (artic_weights_prep / artic_weights_unprep) picks per layer:
+//   * row-run kernels (wprep_rows / wunprep_rows + warp-per-row wn_scale_rows / wn_bwd_rows): the default for every
+//     conv / linear / transposed-conv weight (taps innermost in the torch layout) — see the block comment above RT_O;
+//   * 32 x 32 x <= 8-tap tile kernels (wprep / wunprep + block-per-row wn_scale4 / wn_bwd4): any strides
+//     (ARTIC_WEIGHTS_GENERIC=1 forces them; debug key 27 selects the block-per-row weight-norm kernels);
+//   * the three-pass wperm<0,1,2> + wn_scale / wn_bwd originals (debug key 12), kept as the plainest statement.
 #include "common.cuh"
 #include "tc_common.cuh"
 
