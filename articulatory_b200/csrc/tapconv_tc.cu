@@ -859,7 +859,8 @@ static int tc_plan_problem(const artic_tapconv_t* pp, tc::Prob& pr, int& pr_smem
   // tile; profiles/r2_cluster_step.log).  Debug key 23: minimum KB of weights streamed per tile for a layer to cluster.
   pl.cs = 1;
   const int w_kb_tile = (int)((int64_t)pl.n_kc * p.ntaps * pl.bn * pl.row_bytes / 1024);
-  if (allow_cluster && !pl.w_resident && (tc::g_debug[22] == 2 || tc::g_debug[22] == 4) && w_kb_tile >= tc::g_debug[23]) {
+  if (allow_cluster && !pl.w_resident && (tc::g_debug[22] == 2 || tc::g_debug[22] == 4) && w_kb_tile >= tc::g_debug[23] &&
+      (tc::g_debug[28] <= 0 || total <= tc::g_debug[28])) {            // key 28: only launches of at most that many tiles
     const int want = tc::g_debug[22];
     for (int c = want; c >= 2; c >>= 1)
       if (pl.n_mt % c == 0 && (pl.bn / c) % 8 == 0 && total >= 2 * c) { pl.cs = c; break; }
