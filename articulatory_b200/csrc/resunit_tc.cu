@@ -15,7 +15,8 @@
 // mode 1 is the matching DATA GRADIENT of the unit, the same two-GEMM structure with the convolutions transposed
 // (taps reversed, conv2's first):  dt = conv2^T(gx) * lrelu'(at);  gn = conv1^T(dt) * lrelu'(ax) + gx  — `dt` is
 // written out for conv1's weight gradient.  Here the SECOND GEMM is the dilated one, so R = 128 - (k - 1) * dilation.
-// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (stage 1: TMEM -> at; stage 2: TMEM -> xn / axn).
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (stage 1: TMEM -> at; stage 2: TMEM -> xn / axn; C = 64:
+// every warp runs both stages for its 32-channel chunk; C = 32: warps 2..5 run stage 1, warps 6..9 stage 2, concurrently).
 // The MMA warp runs GEMM1 of tile i+1 before GEMM2 of tile i, so the tensor pipe has work while the epilogue warps
 // convert tile i's intermediate; accumulators and the intermediate buffer are double-buffered.
 #include "tc_common.cuh"
@@ -73,10 +74,13 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
     prefetch_tmap(&map_w2);
     for (int i = 0; i < pl.n_as; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     mbar_init(&w_full, 1);
+    // C = 32: the two epilogue stages are SPLIT between the warp quartets (one channel chunk: half of the warps would
+    // idle otherwise) and run concurrently; C = 64: every warp does both stages for its 32-channel chunk
+    const uint32_t n_arr = C == 32 ? (uint32_t)n_epi / 2 : (uint32_t)n_epi;
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], (uint32_t)n_epi);
-      mbar_init(&a2_full[i], (uint32_t)n_epi); mbar_init(&a2_empty[i], 1);
-      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], (uint32_t)n_epi);
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], n_arr);
+      mbar_init(&a2_full[i], n_arr); mbar_init(&a2_empty[i], 1);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], n_arr);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -170,10 +174,11 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
     // =============================== epilogue ===================================
     pdl_wait();
     const int ew = warp & 3;                   // TMEM lane quarter
-    const int eh = (warp - 2) >> 2;            // channel-chunk parity (C = 64: chunk eh; C = 32: only eh = 0 has channels)
+    const int eh = (warp - 2) >> 2;            // C = 64: channel chunk; C = 32: which epilogue stage this quartet runs
     const int r = ew * 32 + lane;              // tile row = TMEM lane
-    const int c0 = eh * 32;
-    const bool has_ch = c0 < C;
+    const bool split = C == 32;
+    const int c0 = split ? 0 : eh * 32;
+    const bool has_ch = true;
     const uint32_t swz = pl.row_bytes == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
     const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
     uint8_t* a2_ptr = smem_raw + (a2_base - smem_u32(smem_raw));
@@ -270,13 +275,19 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
       tc_fence_before();
       mbar_arrive(&acc2_empty[s]);
     };
-    int i = 0, prev_tile = -1;
-    for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i) {
-      stage1(i, tile);
+    if (split) {
+      int i = 0;
+      if (eh == 0) { for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i) stage1(i, tile); }
+      else         { for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i) stage2(i, tile); }
+    } else {
+      int i = 0, prev_tile = -1;
+      for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i) {
+        stage1(i, tile);
+        if (i > 0) stage2(i - 1, prev_tile);
+        prev_tile = tile;
+      }
       if (i > 0) stage2(i - 1, prev_tile);
-      prev_tile = tile;
     }
-    if (i > 0) stage2(i - 1, prev_tile);
   }
 
   tc_fence_before();
