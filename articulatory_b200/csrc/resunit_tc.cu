@@ -32,6 +32,7 @@ struct RUPlan {
   int32_t mode, rev;                     // mode 1 = data gradient (mask epilogues); rev = taps of both weights reversed
   int32_t row_bytes, layout_type;
   int32_t tiles_per_seq, total_tiles;
+  int32_t split;                         // epilogue stages split between the warp quartets (C = 32 always; C = 64: debug key 30)
   int32_t nbox, a1_stage_bytes, n_as, n_a2;   // n_a2: intermediate buffers (2; 1 when the weights leave no room)
   int32_t w_tile_bytes, a2_bytes, tmem_cols;
   int32_t N, L;
@@ -76,7 +77,7 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
     mbar_init(&w_full, 1);
     // C = 32: the two epilogue stages are SPLIT between the warp quartets (one channel chunk: half of the warps would
     // idle otherwise) and run concurrently; C = 64: every warp does both stages for its 32-channel chunk
-    const uint32_t n_arr = C == 32 ? (uint32_t)n_epi / 2 : (uint32_t)n_epi;
+    const uint32_t n_arr = pl.split ? (uint32_t)n_epi / 2 : (uint32_t)n_epi;
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], n_arr);
       mbar_init(&a2_full[i], n_arr); mbar_init(&a2_empty[i], 1);
@@ -176,24 +177,25 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
     const int ew = warp & 3;                   // TMEM lane quarter
     const int eh = (warp - 2) >> 2;            // C = 64: channel chunk; C = 32: which epilogue stage this quartet runs
     const int r = ew * 32 + lane;              // tile row = TMEM lane
-    const bool split = C == 32;
-    const int c0 = split ? 0 : eh * 32;
+    const bool split = pl.split != 0;
     const bool has_ch = true;
     const uint32_t swz = pl.row_bytes == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
     const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
     uint8_t* a2_ptr = smem_raw + (a2_base - smem_u32(smem_raw));
     using TO = __nv_bfloat16;
 
-    auto stage1 = [&](int i, int tile) {        // TMEM acc1 -> at (shared memory + optional HBM copy)
+    auto stage1 = [&](int i, int tile, int c0, bool first, bool last) {   // TMEM acc1 -> at (shared memory + optional HBM copy)
       const int s = i & 1, ph = (i >> 1) & 1;
       const int s2 = i % pl.n_a2, ph2 = (i / pl.n_a2) & 1;
       const int n = tile / pl.tiles_per_seq;
       const int q0 = (tile % pl.tiles_per_seq) * pl.R;
       const int gpos = q0 - pl.p2 + r;
       const bool inside = gpos >= 0 && gpos < pl.L;
-      mbar_wait(&acc1_full[s], (uint32_t)ph);
-      mbar_wait(&a2_empty[s2], (uint32_t)(ph2 ^ 1));   // conv2 of tile i - n_a2 has finished reading this buffer
-      tc_fence_after();
+      if (first) {
+        mbar_wait(&acc1_full[s], (uint32_t)ph);
+        mbar_wait(&a2_empty[s2], (uint32_t)(ph2 ^ 1));   // conv2 of tile i - n_a2 has finished reading this buffer
+        tc_fence_after();
+      }
       if (has_ch) {
         uint32_t acc_r[32];
         tmem_ld32(t_lane + (uint32_t)s * C + c0, acc_r);
@@ -225,12 +227,14 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
           if (g != nullptr) *reinterpret_cast<uint4*>(g + 8 * u) = pk;
         }
       }
-      tc_fence_before();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(&acc1_empty[s]);
-      mbar_arrive(&a2_full[s2]);
+      if (last) {
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(&acc1_empty[s]);
+        mbar_arrive(&a2_full[s2]);
+      }
     };
-    auto stage2 = [&](int i, int tile) {        // TMEM acc2 -> xn = conv2 + b2 + x, axn = lrelu(xn)
+    auto stage2 = [&](int i, int tile, int c0, bool first, bool last) {   // TMEM acc2 -> xn = conv2 + b2 + x, axn = lrelu(xn)
       const int s = i & 1, ph = (i >> 1) & 1;
       const int n = tile / pl.tiles_per_seq;
       const int q0 = (tile % pl.tiles_per_seq) * pl.R;
@@ -243,8 +247,10 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
         q_rs[u] = valid ? __ldg(reinterpret_cast<const uint4*>(ar.xres + o + 8 * u)) : make_uint4(0, 0, 0, 0);
         q_mk[u] = (valid && pl.mode == 1) ? __ldg(reinterpret_cast<const uint4*>(ar.m2 + o + 8 * u)) : make_uint4(0, 0, 0, 0);
       }
-      mbar_wait(&acc2_full[s], (uint32_t)ph);
-      tc_fence_after();
+      if (first) {
+        mbar_wait(&acc2_full[s], (uint32_t)ph);
+        tc_fence_after();
+      }
       if (has_ch) {
         uint32_t acc_r[32];
         tmem_ld32(t_lane + (uint32_t)(2 * C) + (uint32_t)s * C + c0, acc_r);
@@ -272,21 +278,29 @@ resunit_tc_kernel(const __grid_constant__ RUPlan pl, const __grid_constant__ RUA
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&acc2_empty[s]);
+      if (last) {
+        tc_fence_before();
+        mbar_arrive(&acc2_empty[s]);
+      }
     };
     if (split) {
       int i = 0;
-      if (eh == 0) { for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i) stage1(i, tile); }
-      else         { for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i) stage2(i, tile); }
+      if (eh == 0) {
+        for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i)
+          for (int c0 = 0; c0 < C; c0 += 32) stage1(i, tile, c0, c0 == 0, c0 + 32 >= C);
+      } else {
+        for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i)
+          for (int c0 = 0; c0 < C; c0 += 32) stage2(i, tile, c0, c0 == 0, c0 + 32 >= C);
+      }
     } else {
       int i = 0, prev_tile = -1;
+      const int c0 = eh * 32;
       for (int tile = cta; tile < pl.total_tiles; tile += ncta, ++i) {
-        stage1(i, tile);
-        if (i > 0) stage2(i - 1, prev_tile);
+        stage1(i, tile, c0, true, true);
+        if (i > 0) stage2(i - 1, prev_tile, c0, true, true);
         prev_tile = tile;
       }
-      if (i > 0) stage2(i - 1, prev_tile);
+      if (i > 0) stage2(i - 1, prev_tile, c0, true, true);
     }
   }
 
@@ -342,6 +356,7 @@ extern "C" int artic_resunit_fwd(const artic_resunit_t* pp, void* stream) {
   memset(&pl, 0, sizeof(pl));
   pl.C = p.C; pl.k = p.k;
   pl.mode = p.mode;
+  pl.split = (p.C == 32 || tc::g_debug[30] == 1) ? 1 : 0;
   pl.rev = p.mode == 1 ? 1 : 0;                            // transposed convolutions: taps in reverse order
   pl.dil1 = p.mode == 0 ? p.dil : 1;                       // forward: conv1 (dilated) first; data gradient: conv2^T first
   pl.dil2 = p.mode == 0 ? 1 : p.dil;
