@@ -453,17 +453,22 @@ tapconv_tc_kernel(const __grid_constant__ Multi mp) {
         }
         rowoff[m * 32 + lane] = (pl.dbg_flags & 1) ? -1 : o;      // what-if timing (debug key 9 = 1): no epilogue loads / stores
       }
+      // bn == 32 (one channel chunk): the two warp quartets take ALTERNATE sub-tiles instead of alternate chunks (the
+      // second quartet would idle otherwise)
+      const bool alt_m = pl.bn == 32 && n_ew == 8;
+      const int c_first = alt_m ? 0 : eh * 32;
       {  // bias of this warp's channel chunks (same for every sub-tile): loaded before the accumulator is ready
         int j = 0;
-        for (int c0 = eh * 32; c0 < pl.bn; c0 += 8 * n_ew, ++j)
+        for (int c0 = c_first; c0 < pl.bn; c0 += 8 * n_ew, ++j)
           bias_s[j * 32 + lane] = p.bias != nullptr ? __ldg(p.bias + cbase + c0 + lane) : 0.f;
       }
       __syncwarp();
       bool waited = false;
       for (int m = 0; m < pl.mt; ++m) {
+        if (alt_m && (m & 1) != eh) continue;
         const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc.stage * acc_cols + (uint32_t)m * pl.bn;
         int cj = 0;
-        for (int c0 = eh * 32; c0 < pl.bn; c0 += 8 * n_ew, ++cj) {
+        for (int c0 = c_first; c0 < pl.bn; c0 += 8 * n_ew, ++cj) {
           // Fused epilogue in the TMEM row-per-lane layout: lane = output row, 32 channels per chunk as
           // four 16-byte pieces.  (A shared-memory transposed variant with lanes along the channels
           // coalesces better but costs ~5x the instructions; the epilogue of these small tiles is
