@@ -64,6 +64,13 @@ class Mlp(C.Structure):
                 ("dtype", C.c_int32), ("slope", C.c_float)]
 
 
+class DiscPrep(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ar", C.c_void_p), ("y", C.c_void_p * 2), ("x_out", C.c_void_p),
+                ("pool", C.c_void_p * 4), ("xp", C.c_void_p * 8), ("pool_len", C.c_int32 * 4), ("xp_len", C.c_int32 * 8),
+                ("N", C.c_int32), ("B", C.c_int32), ("T", C.c_int32), ("La", C.c_int32), ("n_pool", C.c_int32),
+                ("n_xp", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("reserved_", C.c_int32)]
+
+
 class AdamHyper(C.Structure):
     _fields_ = [("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("gamma", C.c_float), ("step", C.c_int32), ("n_milestones", C.c_int32),
@@ -100,6 +107,7 @@ SIGNATURES = {
     "artic_trace_buffer": (C.c_int, [_p, C.c_longlong]),
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),
     "artic_tapconv_multi": (C.c_int, [C.POINTER(TapConv), _i32, _p]),
+    "artic_disc_prep": (C.c_int, [C.POINTER(DiscPrep), _p]),
     "artic_mlp_fwd": (C.c_int, [C.POINTER(Mlp), _p]),
     "artic_resunit_fwd": (C.c_int, [C.POINTER(ResUnit), _p]),
     "artic_tapconv_wgrad": (C.c_int, [C.POINTER(TapWgrad), _p]),

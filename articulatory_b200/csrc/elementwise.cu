@@ -221,6 +221,51 @@ __global__ void avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int B
   }
 }
 
+// Discriminator input preamble in ONE launch (one thread block per batch row, the row staged in shared memory): the
+// signal [past samples | waveform] (models/hifigan.py:809-811 via bin/train.py:345-346), the AvgPool1d pyramid of the
+// scale discriminators (:733-736) and the right reflect-padded copies of the period discriminators (:413-416).  As
+// seven dependent 4-10 us launches this chain was a ~100 us bubble without a single tensor-core CTA at the head of
+// every discriminator forward (profiles/r2_gaps_final.txt).  Arithmetic identical to the single kernels.
+__global__ void __launch_bounds__(1024) disc_prep_kernel(const __grid_constant__ artic_disc_prep_t p) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.x, T = p.T;
+  if (p.x != nullptr) {
+    for (int t = threadIdx.x; t < T; t += blockDim.x) sm[t] = __ldg(p.x + (int64_t)n * T + t);
+  } else {
+    const int b = n % p.B, Ty = T - p.La;
+    const float* __restrict__ y = p.y[n / p.B] + (int64_t)b * Ty;
+    const float* __restrict__ ar = p.La > 0 ? p.ar + (int64_t)b * p.La : nullptr;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) sm[t] = t < p.La ? __ldg(ar + t) : __ldg(y + (t - p.La));
+  }
+  __syncthreads();
+  if (p.x_out != nullptr)
+    for (int t = threadIdx.x; t < T; t += blockDim.x) p.x_out[(int64_t)n * T + t] = sm[t];
+  for (int j = 0; j < p.n_xp; ++j) {
+    const int Lp = p.xp_len[j];
+    float* __restrict__ o = p.xp[j] + (int64_t)n * Lp;
+    for (int t = threadIdx.x; t < Lp; t += blockDim.x) o[t] = sm[t < T ? t : 2 * (T - 1) - t];
+  }
+  const float* prev = sm;
+  int lp = T;
+  float* cur = sm + T;
+  for (int l = 0; l < p.n_pool; ++l) {
+    const int lo = p.pool_len[l];
+    float* __restrict__ o = p.pool[l] + (int64_t)n * lo;
+    for (int u = threadIdx.x; u < lo; u += blockDim.x) {
+      float s = 0.f;
+      for (int j = 0; j < p.k; ++j) {
+        const int q = u * p.stride - p.pad + j;
+        if (q >= 0 && q < lp) s += prev[q];
+      }
+      const float v = s / (float)p.k;      // count_include_pad = True: the divisor is always k
+      cur[u] = v;
+      o[u] = v;
+    }
+    __syncthreads();
+    prev = cur; lp = lo; cur += lo;
+  }
+}
+
 template <typename T>
 __global__ void avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int L, int Lout, int k,
                                    int stride, int pad, int accumulate) {
@@ -506,6 +551,39 @@ extern "C" int artic_concat_time(const float* ar, const float* y, void* out, int
   if (n == 0) return ARTIC_OK;
   DISPATCH(dtype, (concat_time_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(ar, y, (float*)out, B, La, Ly, out_pitch)),
            (concat_time_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(ar, y, (bf16*)out, B, La, Ly, out_pitch)));
+}
+
+extern "C" int artic_disc_prep(const artic_disc_prep_t* p, void* stream) {
+  ARTIC_CHECK_ARG(p != nullptr, "null params");
+  ARTIC_CHECK_ARG(p->N >= 0 && p->T >= 1 && p->n_pool >= 0 && p->n_pool <= 4 && p->n_xp >= 0 && p->n_xp <= 8, "bad dims");
+  ARTIC_CHECK_ARG(p->x != nullptr || (p->B >= 1 && p->N % p->B == 0 && p->N / p->B <= 2 && p->La >= 0 && p->La < p->T &&
+                                      (p->La == 0 || p->ar != nullptr) && p->y[0] != nullptr && (p->N / p->B < 2 || p->y[1] != nullptr)),
+                  "assembling the signal needs ar (La > 0) and one waveform batch per B rows");
+  int64_t fl = p->T;
+  int lp = p->T;
+  for (int l = 0; l < p->n_pool; ++l) {
+    ARTIC_CHECK_ARG(p->pool[l] != nullptr && p->k >= 1 && p->stride >= 1 && p->pad >= 0 &&
+                    p->pool_len[l] == (lp + 2 * p->pad - p->k) / p->stride + 1, "bad pooling geometry");
+    lp = p->pool_len[l];
+    fl += lp;
+  }
+  for (int j = 0; j < p->n_xp; ++j)
+    ARTIC_CHECK_ARG(p->xp[j] != nullptr && p->xp_len[j] >= p->T && p->xp_len[j] - p->T < p->T, "reflect pad must be smaller than the input");
+  if (p->N == 0) return ARTIC_OK;
+  const size_t smem = (size_t)fl * sizeof(float);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    if (smem > 200 * 1024 ||
+        cudaFuncSetAttribute(disc_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("artic_disc_prep: a row of %lld floats does not fit in shared memory", (long long)fl);
+      return ARTIC_ENOSUP;
+    }
+    smem_set = 200 * 1024;
+  }
+  disc_prep_kernel<<<(unsigned)p->N, 1024, smem, ST(stream)>>>(*p);
+  ARTIC_LAUNCH_CHECK();
+  return ARTIC_OK;
 }
 
 extern "C" int artic_avgpool1d(const void* x, void* y, int32_t B, int32_t L, int32_t Lout, int32_t k, int32_t stride,

@@ -1073,7 +1073,14 @@ extern "C" int artic_weights_prep(const artic_wdesc_t* descs, int32_t n, int32_t
       else wn_scale_rows_kernel<<<dim3(128, (unsigned)n), 256, 0, st>>>(descs);
     }
     if (total_tiles > 0) wprep_kernel<<<wperm_grid(total_tiles), 256, 0, st>>>(descs, n, total_tiles);
-    if (total_tiles2 > 0) wprep_rows_kernel<<<wperm_grid(total_tiles2), 256, 0, st>>>(descs, n, total_tiles2);
+    if (total_tiles2 > 0) {
+      // debug key 31: cap on the grid (the kernel strides): a prep that runs BESIDE tensor-core launches (D's weights
+      // under the generator forward) then holds only that many SMs — its 45 KB blocks cannot share an SM with a
+      // 200+ KB tensor-core CTA, and an uncapped grid starves those CTAs until it has drained
+      unsigned grid = wperm_grid(total_tiles2);
+      if (tc::g_debug[31] > 0 && grid > (unsigned)tc::g_debug[31]) grid = (unsigned)tc::g_debug[31];
+      wprep_rows_kernel<<<grid, 256, 0, st>>>(descs, n, total_tiles2);
+    }
   }
   tc::note_weights_written(st);   // the next tensor-core conv on `st` must not prefetch weights early
   ARTIC_LAUNCH_CHECK();

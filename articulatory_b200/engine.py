@@ -1090,25 +1090,42 @@ class DiscriminatorEngine:
         return fs
 
     # ---- forward -------------------------------------------------------------
-    def forward(self, x: torch.Tensor, save=True, into=None, lo=0):
+    def forward(self, x: Optional[torch.Tensor], save=True, into=None, lo=0, parts=None):
         with planner_objective(_D_OBJECTIVE):
-            return self._forward(x, save, into, lo)
+            return self._forward(x, save, into, lo, parts)
 
-    def _forward(self, x: torch.Tensor, save=True, into=None, lo=0):
+    def _forward(self, x: Optional[torch.Tensor], save=True, into=None, lo=0, parts=None):
         """x (B, 1, T) fp32 -> (list of 8 lists of SeqT [feature maps..., logits], tape).
+
+        ``parts = (ar, ys)`` instead of ``x``: the input is cat([ar, y], dim=2) for every y in ``ys`` (one or two
+        (B0, 1, Ty) batches) stacked along the batch (bin/train.py:345-346) — assembled by the same single launch
+        that builds the pooled and reflect-padded views.
 
         ``into`` (a tape of an earlier forward over a batch of >= lo + B items) makes this call
         write its activations into batch items [lo, lo + B) of that tape's buffers instead of
         allocating: the train step keeps [fake | real] in ONE 2B batch so that the discriminator
         backward (and every weight gradient) runs once over both halves."""
-        _lib.require_cuda(x, "x")
-        assert self._prepped and x.dim() == 3 and x.shape[1] == 1
-        B, _, T = x.shape
-        dev = x.device
+        assert self._prepped
+        if parts is not None:
+            ar, ys = parts
+            B0, _, Ty = ys[0].shape
+            La = 0 if ar is None else ar.shape[-1]
+            B, T = len(ys) * B0, La + Ty
+            dev = ys[0].device
+            for t in ys:
+                _lib.require_cuda(t, "y")
+                assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (B0, 1, Ty)
+            assert ar is None or (ar.dtype == torch.float32 and ar.is_contiguous() and ar.numel() == B0 * La)
+        else:
+            _lib.require_cuda(x, "x")
+            assert x.dim() == 3 and x.shape[1] == 1
+            B, _, T = x.shape
+            dev = x.device
         if into is not None:
             assert into["T"] == T and lo + B <= into["B"]
             x2d = into["x"][lo:lo + B]
-            x2d.copy_(x.reshape(B, T))
+        elif parts is not None:
+            x2d = torch.empty((B, T), dtype=torch.float32, device=dev)
         else:
             x2d = x.contiguous().float().view(B, T)
 
@@ -1116,29 +1133,56 @@ class DiscriminatorEngine:
             return slice_seq(full, lo, lo + B)
 
         outs, tape = [], {"B": B, "T": T, "x": x2d, "chains": [], "xp": {}}
-        # AvgPool pyramid (hifigan.py:733-736)
+        # signal assembly + AvgPool pyramid (hifigan.py:733-736) + reflect-padded period inputs (hifigan.py:413-416):
+        # one launch (artic_disc_prep)
         k, st, pd = self.pool["kernel_size"], self.pool["stride"], self.pool["padding"]
         sigs = [SeqT(x2d.view(B, T, 1), B, T, 1)]
         n_scales = sum(1 for c in self.chains if c.kind == "scale")
         for s in range(1, n_scales):
-            lp = sigs[-1].L
-            lo_ = (lp + 2 * pd - k) // st + 1
-            nxt = take(into["sigs"][s]) if into is not None else SeqT.empty(B, lo_, 1, F32, dev)
-            call("artic_avgpool1d", ptr(sigs[-1].t), ptr(nxt.t), B, lp, lo_, k, st, pd, F32)
-            sigs.append(nxt)
-        xps = {}
-        for ci, ch in enumerate(self.chains):          # reflect-padded period inputs (hifigan.py:413-416)
+            lo_ = (sigs[-1].L + 2 * pd - k) // st + 1
+            sigs.append(take(into["sigs"][s]) if into is not None else SeqT.empty(B, lo_, 1, F32, dev))
+        xps, padded = {}, []
+        for ci, ch in enumerate(self.chains):
             if ch.kind != "period":
                 continue
             p = ch.period
             Tp = T if T % p == 0 else T + (p - T % p)
             if Tp != T:
                 xp = into["xp"][ci][lo:lo + B] if into is not None else torch.empty((B, Tp), dtype=torch.float32, device=dev)
-                call("artic_reflect_pad_right", ptr(x2d), ptr(xp), B, T, Tp, F32)
+                padded.append(xp)
             else:
                 xp = x2d
             xps[ci] = xp
         tape["xp"] = xps
+        dp = _lib.DiscPrep()
+        if parts is not None:
+            dp.ar = ptr(ar)
+            for i, t in enumerate(ys):
+                dp.y[i] = ptr(t)
+            dp.B, dp.La, dp.x_out = B0, La, ptr(x2d)
+        else:
+            xin = x2d if into is None else x.contiguous().float().view(B, T)
+            dp.x, dp.x_out = ptr(xin), (ptr(x2d) if into is not None else None)
+        dp.N, dp.T, dp.k, dp.stride, dp.pad = B, T, k, st, pd
+        assert len(sigs) - 1 <= 4 and len(padded) <= 8
+        dp.n_pool, dp.n_xp = len(sigs) - 1, len(padded)
+        for i, sg in enumerate(sigs[1:]):
+            dp.pool[i], dp.pool_len[i] = ptr(sg.t), sg.L
+        for i, xp in enumerate(padded):
+            dp.xp[i], dp.xp_len[i] = ptr(xp), xp.shape[1]
+        if 4 * (T + sum(sg.L for sg in sigs[1:])) > 200 * 1024:
+            # a row with its pyramid does not fit the one-launch kernel's shared memory: the single-purpose kernels
+            if parts is not None:
+                for i, t in enumerate(ys):
+                    call("artic_concat_time", ptr(ar) if La else None, ptr(t), ptr(x2d[i * B0:]), B0, La, Ty, T, F32)
+            elif into is not None:
+                x2d.copy_(x.reshape(B, T))
+            for a, b in zip(sigs[:-1], sigs[1:]):
+                call("artic_avgpool1d", ptr(a.t), ptr(b.t), B, a.L, b.L, k, st, pd, F32)
+            for xp in padded:
+                call("artic_reflect_pad_right", ptr(x2d), ptr(xp), B, T, xp.shape[1], F32)
+        elif dp.n_pool or dp.n_xp or dp.x_out:
+            call("artic_disc_prep", dp)
 
         def chain_fwd(ci):
             ch = self.chains[ci]

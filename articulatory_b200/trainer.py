@@ -201,7 +201,7 @@ class TrainStep:
         state = {}
 
         def adversarial():
-            outs2, tape2 = engD.forward(self._disc_input(ar, (y_, y)), save=True)
+            outs2, tape2 = engD.forward(None, save=True, parts=(ar if self.ar_len else None, (y_, y)))
             state["tape2"] = tape2
             outs_f = [[slice_seq(o, 0, B) for o in lst] for lst in outs2]
             outs_r = [[slice_seq(o, B, 2 * B) for o in lst] for lst in outs2]
@@ -281,10 +281,10 @@ class TrainStep:
         else:
             (y_, _), _ = fork_join([lambda: engG.forward(x, ar, save=False), clear_d_grads])   # bin/train.py:390-400
         if tape2 is None:
-            _, tape2 = engD.forward(self._disc_input(ar, (y_, y)), save=True)
+            _, tape2 = engD.forward(None, save=True, parts=(ar if self.ar_len else None, (y_, y)))
         else:
             # D(real) is REUSED from the G phase; D(fake) overwrites the stale fake half in place
-            engD.forward(self._disc_input(ar, (y_,)), save=True, into=tape2, lo=0)
+            engD.forward(None, save=True, into=tape2, lo=0, parts=(ar if self.ar_len else None, (y_,)))
         if real_done:
             fake = [[slice_seq(acts[-1], 0, B)] for acts in tape2["chains"]]
             lg = [lst[0].like() for lst in fake]
@@ -511,7 +511,7 @@ class TrainStep:
                 res.forward(y2d, t2d, self.stft_sums[r])
         if self.use_mel:                                                      # :536-540
             self.mel.accumulate(y2d, t2d, 1.0 / self.mel.numel(B, T), self.slots[_MEL:])
-        outs2, _ = engD.forward(self._disc_input(ar, (y_, y)), save=False)    # :572-587, [fake | real]
+        outs2, _ = engD.forward(None, save=False, parts=(ar if self.ar_len else None, (y_, y)))    # :572-587, [fake | real]
         outs_f = [[slice_seq(o, 0, B) for o in lst] for lst in outs2]
         outs_r = [[slice_seq(o, B, 2 * B) for o in lst] for lst in outs2]
         self._adv_seed(outs_f, 1.0, _ADV, 0.0)                                # gen_adv(p_)

@@ -256,6 +256,28 @@ typedef struct {
 } artic_mlp_t;
 int artic_mlp_fwd(const artic_mlp_t* p, void* stream);
 
+/* Discriminator input preamble in one launch (one thread block per batch row):
+ *   signal   x (N, T) given, or assembled: row n = cat(ar[n % B] (La samples), y[n / B][n % B] (T - La samples))
+ *            (models/hifigan.py:809-811 fed by bin/train.py:345-346; up to two waveform batches stacked along N);
+ *            x_out (optional) receives it
+ *   pool[l]  AvgPool1d(k, stride, pad, count_include_pad = True) of level l - 1 (level -1 = the signal),
+ *            pool_len[l] = (len + 2 pad - k) / stride + 1 (hifigan.py:733-736)
+ *   xp[j]    the signal right reflect-padded to xp_len[j] samples (hifigan.py:413-416)
+ * Same arithmetic as artic_concat_time / artic_avgpool1d / artic_reflect_pad_right.  ARTIC_ENOSUP when a row with its
+ * pyramid exceeds 200 KB of shared memory (the caller then uses those). */
+typedef struct {
+  const float* x;
+  const float* ar;
+  const float* y[2];
+  float* x_out;
+  float* pool[4];
+  float* xp[8];
+  int32_t pool_len[4];
+  int32_t xp_len[8];
+  int32_t N, B, T, La, n_pool, n_xp, k, stride, pad, reserved_;
+} artic_disc_prep_t;
+int artic_disc_prep(const artic_disc_prep_t* p, void* stream);
+
 /* MRF average + activation (models/hifigan.py:226-230 and the LeakyReLU of the next
  * layer): out_act = lrelu((a+b+c)/3, slope); n elements; inputs in `dtype`, output in `out_dtype`. */
 int artic_mean3_act(const void* a, const void* b, const void* c, void* out_act, int64_t n,

@@ -32,7 +32,7 @@ def main():
         warnings.simplefilter("ignore")
         G = M.HiFiGANGenerator(**O.E2W_GENERATOR_PARAMS, precision=args.precision).to(dev)
         D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**O.E2W_DISCRIMINATOR_PARAMS, precision=args.precision).to(dev)
-    ts = TrainStep(G, D, bench.train_config(), dev)
+    ts = TrainStep(G, D, O.e2w_train_config(use_stft_loss=True), dev)
     b = {k: v.to(dev) for k, v in O.synthetic_batch(args.batch, seed=1234).items()}
     for _ in range(6):
         ts.step(b["x"], b["y"], b["ar"])

@@ -38,7 +38,7 @@ def main():
         warnings.simplefilter("ignore")
         G = M.HiFiGANGenerator(**O.E2W_GENERATOR_PARAMS, precision=args.precision).to(dev)
         D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**O.E2W_DISCRIMINATOR_PARAMS, precision=args.precision).to(dev)
-    ts = TrainStep(G, D, bench.train_config(), dev)
+    ts = TrainStep(G, D, O.e2w_train_config(use_stft_loss=True), dev)
     b = {k: v.to(dev) for k, v in O.synthetic_batch(args.batch, seed=1234).items()}
     x, y, ar = b["x"], b["y"], b["ar"]
     B, _, T = y.shape
@@ -52,7 +52,7 @@ def main():
         st["y_"], st["tapeG"] = engG.forward(x, ar, save=True)
 
     def d_fwd2():
-        st["outs2"], st["tape2"] = engD.forward(ts._disc_input(ar, (st["y_"], y)), save=True)
+        st["outs2"], st["tape2"] = engD.forward(None, save=True, parts=(ar, (st["y_"], y)))
 
     def seeds_dgrad():
         outs2 = st["outs2"]
@@ -89,7 +89,7 @@ def main():
         st["y2"], _ = engG.forward(x, ar, save=False)
 
     def d_fwd1():
-        engD.forward(ts._disc_input(ar, (st["y2"],)), save=True, into=st["tape2"], lo=0)
+        engD.forward(None, save=True, into=st["tape2"], lo=0, parts=(ar, (st["y2"],)))
 
     def d_bwd():
         outs2 = [acts[1:] for acts in st["tape2"]["chains"]]
