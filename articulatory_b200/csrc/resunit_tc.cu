@@ -420,7 +420,10 @@ extern "C" int artic_resunit_fwd(const artic_resunit_t* pp, void* stream) {
   ar.y = reinterpret_cast<__nv_bfloat16*>(p.Y);
   ar.y2 = reinterpret_cast<__nv_bfloat16*>(p.Y2);
   const int smem_bytes = pl.n_as * pl.a1_stage_bytes + fixed;
-  const int grid = pl.total_tiles < num_sms() ? pl.total_tiles : num_sms();
+  // as few CTAs as finish in the same number of tile rounds: 525 tiles take 4 rounds on 148 or on 132 SMs, and the 16
+  // SMs left free go to the launches of the other MRF branches that run beside this one
+  const int rounds = (pl.total_tiles + num_sms() - 1) / num_sms();
+  const int grid = (pl.total_tiles + rounds - 1) / rounds;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(tc::RU_THREADS);
