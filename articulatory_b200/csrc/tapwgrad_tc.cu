@@ -67,6 +67,7 @@ struct WPlan {
   int32_t dbg_flags;           // debug key 13: 1 = skip the reductions, 2 = skip the staging-area zeroing (timing experiments)
   int32_t bias_acc;            // 1: CTAs with mb == 0 && tg == 0 also accumulate the bias gradient (ones x dY)
   int32_t ones_off;            // byte offset (from the staging base) of the all-ones A tile
+  long long* dbg;              // artic_debug_buffer: CTA 0 writes clock64 marks to dbg[200 + tag] (tools/wgrad_timeline.py)
   // per accumulator: phase panel, row shift of slot 0, tap index of slot 0, number of valid slots
   int8_t acc_panel[ARTIC_MAX_TAPS];
   int16_t acc_shift[ARTIC_MAX_TAPS];
@@ -108,6 +109,8 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto mark = [&](int tag) { if (pl.dbg != nullptr && blockIdx.x == 0) pl.dbg[200 + tag] = clock64(); };
+  if (threadIdx.x == 0) mark(1);
   const long long t_trace = (pl.trace != nullptr && threadIdx.x == 0) ? global_timer() : 0;
   if (pl.dbg_flags & 4) return;   // what-if timing (debug key 13 = 4): every CTA exits at once
 
@@ -152,6 +155,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) mark(2);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -219,6 +223,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
       for (int cc = c_begin * R; cc < c_end * R; ++cc) {
         mbar_wait(&full[ps.stage], ps.phase);
         tc_fence_after();
+        if (leader && cc == c_begin * R) mark(20);
         const uint32_t xs = smem0 + (uint32_t)ps.stage * pl.stage_bytes;
         const uint32_t ys = xs + (uint32_t)(pl.n_ph * pl.nxp) * pl.x_panel_bytes;
         const uint32_t b16 = b_lo0 | ((ys >> 4) & 0x3fffu);
@@ -252,7 +257,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
         if (leader) umma_commit(&empty[ps.stage]);
         ps.next();
       }
-      if (leader) umma_commit(&acc_full);
+      if (leader) { umma_commit(&acc_full); mark(22); }
     }
   } else {
     // =============================== epilogue ===================================
@@ -267,6 +272,7 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
     if (c_end > c_begin) {
       mbar_wait(&acc_full, 0);
       tc_fence_after();
+      if (threadIdx.x == 64) mark(30);
       for (int a = 0; a < n_acc; ++a) {
         const bool valid = slot < pl.acc_cnt[acc0 + a] && ci < p.Cig;
         float* dst = nullptr;
@@ -322,12 +328,14 @@ tapwgrad_tc_kernel(const __grid_constant__ artic_tapwgrad_t p, const __grid_cons
     }
   }
 
+  if (threadIdx.x == 64) mark(31);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
   }
+  if (threadIdx.x == 0) mark(32);
   if (pl.trace != nullptr && threadIdx.x == 0) trace_cta(pl.trace, pl.trace_cap, pl.launch_id, 8, t_trace);
 }
 
@@ -507,11 +515,21 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st, int* bias
       pl.n_chunks = (p.N + pl.seg_per_chunk - 1) / pl.seg_per_chunk;
       pl.x_rows = pl.kp + ext + 8;
     } else {
-      pl.kp = min(kp_cap, 64);
+      // Narrow layers (64-byte / 128-byte rows, one panel): the main loop is bound by the ROWS the TMA unit requests
+      // (~7 clocks per row whatever its width: tools/wgrad_timeline.py: 1.4 k clocks per 64-position chunk of a
+      // 32-channel layer for 8 or for 16 MMAs), so the X tile is ONE box of exactly the rows the taps read
+      // (kp + span) instead of 64-row boxes that over-fetch up to 2x, and a chunk covers 128 positions.
+      const bool narrow = si == 1 && p.Cig <= 64 && tc::g_debug[29] != 1;
+      pl.kp = min(kp_cap, narrow ? 128 : 64);
       pl.chunks_per_seq = (p.nq + pl.kp - 1) / pl.kp;
       pl.n_chunks = p.N * pl.chunks_per_seq;
-      pl.boxr = si == 1 ? min(64, pl.kp) : 32;
-      pl.nxb = (pl.kp + span_rows + pl.boxr - 1) / pl.boxr;
+      if (narrow && pl.kp + span_rows <= 256) {
+        pl.boxr = ((pl.kp + span_rows + 7) / 8) * 8;
+        pl.nxb = 1;
+      } else {
+        pl.boxr = si == 1 ? min(64, pl.kp) : 32;
+        pl.nxb = (pl.kp + span_rows + pl.boxr - 1) / pl.boxr;
+      }
       pl.x_rows = max(pl.nxb * pl.boxr, pl.kp + ext + 8);
     }
     pl.x_panel_bytes = ((pl.x_rows * pl.xrb + 1023) / 1024) * 1024;
@@ -563,6 +581,7 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st, int* bias
   if (rc != CUDA_SUCCESS) { set_error("artic_tapconv_wgrad: cuTensorMapEncodeTiled(dY) failed (%d)", (int)rc); return ARTIC_ECUDA; }
   if (!x3) { maps.x_lo = maps.x; maps.y_lo = maps.y; }
   pl.dbg_flags = tc::g_debug[13];
+  pl.dbg = tc::g_dbg_buf;
   pl.epi_transposed = tc::g_debug[18] == 1 ? 0 : 1;
   pl.trace = tc::g_trace_buf;
   pl.trace_cap = tc::g_trace_cap;

@@ -187,6 +187,7 @@ extern int g_debug[32];              // artic_debug_set knobs
 // SM-occupancy trace (artic_trace_buffer): every CTA of the tensor-core kernels appends one record
 // {launch id << 32 | kind << 28 | blockIdx, smid, globaltimer at start, at exit}; slot 0 = record count.
 extern long long* g_trace_buf;
+extern long long* g_dbg_buf;            // artic_debug_buffer (in-kernel clock marks of CTA 0)
 extern long long g_trace_cap;
 extern int g_trace_launch;
 // Prepared weights were (re)written by a kernel on stream `st`: the next tensor-core conv on that stream
