@@ -523,7 +523,7 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st, int* bias
       pl.kp = min(kp_cap, narrow ? 128 : 64);
       pl.chunks_per_seq = (p.nq + pl.kp - 1) / pl.kp;
       pl.n_chunks = p.N * pl.chunks_per_seq;
-      if (narrow && pl.kp + span_rows <= 256) {
+      if (si == 1 && pl.kp + span_rows <= 256 && tc::g_debug[29] != 1 && (narrow || tc::g_debug[29] != 2)) {   // wide layers too (key 29 = 2: narrow only)
         pl.boxr = ((pl.kp + span_rows + 7) / 8) * 8;
         pl.nxb = 1;
       } else {
