@@ -549,11 +549,12 @@ int artic_tapwgrad_tc_try(const artic_tapwgrad_t* pp, cudaStream_t st, int* bias
   {
     // Every CTA pays ~6 us of fixed cost (launch, staging, first-load latency, the split-K reduction of its
     // whole accumulator) while it holds an SM that the concurrent streams could use: give each split a main
-    // loop of at least `min_clk` tensor-core clocks (debug key 14, in units of 1000 clocks; default 6: 12.70 -> 12.55 ms) rather
+    // loop of at least `min_clk` tensor-core clocks (debug key 14, in units of 1000 clocks; round 1: 6, 12.70 -> 12.55 ms;
+    // re-swept on the round-2 build: 3 -> 11.36, 6 -> 11.27, 10 -> 11.23, 12 -> 11.19, 16 -> 11.26 ms: default 12) rather
     // than spreading a small layer over all SMs.
     const double per_mma = pl.bn / 2.0 > 32.0 + pl.bn / 4.0 ? pl.bn / 2.0 : 32.0 + pl.bn / 4.0;
     const double chunk_clk = (double)pl.apc * (pl.kp / 16) * per_mma * (x3 ? 3 : 1);
-    const double min_clk = 1000.0 * (tc::g_debug[14] > 0 ? tc::g_debug[14] : tc::g_debug[14] < 0 ? 0 : 6);
+    const double min_clk = 1000.0 * (tc::g_debug[14] > 0 ? tc::g_debug[14] : tc::g_debug[14] < 0 ? 0 : 12);
     int64_t min_chunks = (int64_t)(min_clk / chunk_clk + 0.999);
     if (min_chunks < 1) min_chunks = 1;
     const int64_t cap = (pl.n_chunks + min_chunks - 1) / min_chunks;
