@@ -103,6 +103,7 @@ SIGNATURES = {
     "artic_arch": (C.c_char_p, []),
     "artic_last_error": (C.c_char_p, []),
     "artic_debug_set": (C.c_int, [C.c_int, C.c_int]),
+    "artic_debug_get": (C.c_int, [C.c_int]),
     "artic_debug_buffer": (C.c_int, [_p]),
     "artic_trace_buffer": (C.c_int, [_p, C.c_longlong]),
     "artic_tapconv": (C.c_int, [C.POINTER(TapConv), _p]),

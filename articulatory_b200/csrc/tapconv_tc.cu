@@ -724,6 +724,8 @@ extern "C" int artic_debug_set(int key, int value) {
   return ARTIC_OK;
 }
 
+extern "C" int artic_debug_get(int key) { return (key < 0 || key >= 32) ? 0 : tc::g_debug[key]; }
+
 static inline int w_all_bytes(const tc::Plan& pl, int ntaps, bool x3) { return (x3 ? 2 * pl.n_kcl : pl.n_kc) * ntaps * pl.w_tile_bytes; }
 
 // Plans one problem for the tensor-core kernel: returns 1 (pr filled: parameters, plan, tensor maps,

@@ -44,8 +44,9 @@ extern "C" {
 int artic_version(void);          /* 100 * major + minor */
 const char* artic_arch(void);     /* "sm_100a" */
 const char* artic_last_error(void);
-/* Debug / tuning knobs of the tensor-core path (key 0..7); not part of the reference surface. */
+/* Debug / tuning knobs of the kernels' planners (keys 0..31); not part of the reference surface. */
 int artic_debug_set(int key, int value);
+int artic_debug_get(int key);     /* current value of a knob (0 for an unknown key) */
 /* Debug: device buffer (>= 4001 int64, zeroed) into which CTA 0 of the tensor-core conv kernel records a
  * (tag, clock64) timeline; NULL disables. */
 int artic_debug_buffer(void* dev_buf);

@@ -36,6 +36,50 @@ def test_abi_library_exports_every_declared_symbol():
     assert lib.artic_arch() == b"sm_100a"
 
 
+def test_relayout_tile_spaces_host_helpers():
+    """artic_wrow_tiles / artic_wperm_tiles (host-only): every conv / linear / transposed-conv weight of the nets is taken by
+    the row-run kernels; work units = groups x ceil(outer / 32) x ceil(inner tiles / chunk); a tap stride that is not the
+    innermost torch index falls back to the generic tile space."""
+    from articulatory_b200 import _lib
+    from articulatory_b200.convspec import ConvSpec
+    lib = _lib.load()
+
+    def units(spec, chunk):
+        A, B, sk, sg, sa, sb = spec.prep_strides("fwd")
+        return lib.artic_wrow_tiles(spec.k, spec.groups, A, B, sk, sa, sb, chunk)
+
+    big = ConvSpec("conv", 1024, 1024, k=5, padding=2)                      # outer = 1024 out-ch, inner = 1024 in-ch, TI = 32
+    assert units(big, 1) == 32 * 32 and units(big, 8) == 32 * 4 and units(big, 100) == 32 * 4
+    k41 = ConvSpec("conv", 1024, 1024, k=41, padding=20, groups=16)         # per group 64 x 64, TI = 8 (8 * 41 = 328 <= 352)
+    assert units(k41, 1) == 16 * 2 * 8
+    k11 = ConvSpec("conv", 128, 128, k=11, dilation=5, padding=25)          # 32 * 11 = 352 floats: TI stays 32
+    assert units(k11, 1) == 4 * 4
+    up = ConvSpec("convT", 256, 128, k=10, stride=5, padding=3, output_padding=1)   # outer = in-ch (torch dim 0), inner = out-ch
+    assert units(up, 1) == 8 * 4
+    assert units(ConvSpec("linear", 512, 256), 1) == 8 * 16
+    assert units(ConvSpec("conv", 1, 128, k=15, padding=7), 1) == 4 and units(ConvSpec("conv", 32, 1, k=7, padding=3), 1) == 1
+    assert lib.artic_wrow_tiles(5, 1, 64, 64, 7, 5, 320, 1) == 0            # taps not contiguous: generic tiles
+    assert lib.artic_wrow_tiles(400, 1, 4, 4, 1, 400, 1600, 1) == 0         # a tap run beyond the tile's row
+    assert lib.artic_wperm_tiles(5, 1, 64, 64) == 2 * 2 * 1 and lib.artic_wperm_tiles(41, 16, 64, 64) == 16 * 2 * 2 * 6
+
+
+def test_scoped_planner_knobs_are_reentrant():
+    """engine.weight_multicast / planner_objective set raw debug keys for the launches enqueued inside and restore the
+    enclosing value on exit (nested use: the decoder's chunk capture around the engine's own scopes)."""
+    from articulatory_b200 import _lib, engine
+    lib = _lib.load()
+    assert lib.artic_debug_get(22) == 0
+    with engine.weight_multicast(2):
+        assert lib.artic_debug_get(22) == 2
+        with engine.weight_multicast(4):
+            assert lib.artic_debug_get(22) == 4
+        assert lib.artic_debug_get(22) == 2
+        with engine.planner_objective(60):
+            assert lib.artic_debug_get(15) == 60
+        assert lib.artic_debug_get(15) == 0
+    assert lib.artic_debug_get(22) == 0
+
+
 def test_struct_sizes_match_header():
     """ctypes mirrors of the ABI structs have the C layout (nvcc and ctypes agree on padding)."""
     from articulatory_b200 import _lib
