@@ -88,6 +88,62 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.TapConv) % 8 == 0 and ctypes.sizeof(_lib.TapWgrad) % 8 == 0
 
 
+def test_ctypes_signatures_have_the_header_arity():
+    """Every prototype of include/artic.h has as many parameters as its ctypes signature (plus pointer / integer /
+    float kind for each): a missing argument would shift the stream pointer into a size."""
+    from articulatory_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "artic.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char\*)\s+(artic_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 40
+    seen = set()
+    for name, args in protos:
+        seen.add(name)
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        res, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, params, argtypes)
+        for prm, at in zip(params, argtypes):
+            is_ptr = "*" in prm
+            ct_ptr = at is ctypes.c_void_p or at is ctypes.c_char_p or hasattr(at, "contents") or getattr(at, "_type_", None) is not None and isinstance(getattr(at, "_type_"), type)
+            if is_ptr:
+                assert ct_ptr, (name, prm, at)
+            elif prm.startswith("float"):
+                assert at is ctypes.c_float, (name, prm, at)
+            elif prm.startswith("int64_t") or prm.startswith("long long"):
+                assert ctypes.sizeof(at) == 8 and at not in (ctypes.c_double,), (name, prm, at)
+            else:
+                assert at in (ctypes.c_int32, ctypes.c_int), (name, prm, at)
+    assert seen == set(_lib.SIGNATURES), set(_lib.SIGNATURES) ^ seen
+
+
+def test_ctypes_mirrors_match_the_header_compiled_by_gcc(tmp_path):
+    """include/artic.h compiled as plain C: sizeof of every ABI struct and the offset of its last field equal the ctypes
+    mirrors' (a drifted mirror would hand the kernels shifted fields)."""
+    import shutil
+    import subprocess
+    from articulatory_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = [("artic_seq_t", _lib.Seq), ("artic_tapconv_t", _lib.TapConv), ("artic_tapwgrad_t", _lib.TapWgrad),
+             ("artic_resunit_t", _lib.ResUnit), ("artic_wdesc_t", _lib.WDesc), ("artic_mlp_t", _lib.Mlp),
+             ("artic_disc_prep_t", _lib.DiscPrep), ("artic_adam_hyper_t", _lib.AdamHyper)]
+    lines = []
+    for cname, mirror in pairs:
+        last = mirror._fields_[-1][0].rstrip("_") if mirror._fields_[-1][0] in ("in_",) else mirror._fields_[-1][0]
+        lines.append(f'printf("%s %zu %zu\\n", "{cname}", sizeof({cname}), offsetof({cname}, {last}));')
+    src = tmp_path / "sizes.c"
+    src.write_text("#include <stdio.h>\n#include <stddef.h>\n#include \"artic.h\"\nint main(void) {\n" + "\n".join(lines) +
+                   "\nreturn 0; }\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {ln.split()[0]: (int(ln.split()[1]), int(ln.split()[2])) for ln in out if ln.strip()}
+    for cname, mirror in pairs:
+        last = mirror._fields_[-1][0]
+        assert got[cname] == (ctypes.sizeof(mirror), getattr(mirror, last).offset), (cname, got[cname])
+
+
 def test_product_path_fails_loudly_without_gpu():
     from articulatory_b200 import models as M
     from articulatory_b200._lib import ArticError
