@@ -433,6 +433,8 @@ class ConvLayer:
         if self.b is not None and not fuse_bias:
             call("artic_colsum", ptr(dY.t), dY.seq(), dY.N, dY.C, dY.code, ptr(grads[self.name + ".bias"]))
 
+#: a discriminator input row with its AvgPool pyramid must fit the one-launch preamble kernel's shared memory
+_DISC_PREP_MAX_BYTES = 200 * 1024
 _WEIGHTS_GENERIC = _os.environ.get("ARTIC_WEIGHTS_GENERIC", "0") == "1"
 
 
@@ -1170,7 +1172,7 @@ class DiscriminatorEngine:
             dp.pool[i], dp.pool_len[i] = ptr(sg.t), sg.L
         for i, xp in enumerate(padded):
             dp.xp[i], dp.xp_len[i] = ptr(xp), xp.shape[1]
-        if 4 * (T + sum(sg.L for sg in sigs[1:])) > 200 * 1024:
+        if 4 * (T + sum(sg.L for sg in sigs[1:])) > _DISC_PREP_MAX_BYTES:
             # a row with its pyramid does not fit the one-launch kernel's shared memory: the single-purpose kernels
             if parts is not None:
                 for i, t in enumerate(ys):

@@ -360,3 +360,33 @@ def test_off_path_options_fail_loudly():
         M.HiFiGANGenerator(use_spk_id=True, num_spk=4)
     with pytest.raises(NotImplementedError):
         M.HiFiGANPeriodDiscriminator(use_weight_norm=False, use_spectral_norm=True)
+
+
+def test_discriminator_preamble_one_launch_equals_the_single_kernels(golden, monkeypatch):
+    """DiscriminatorEngine: the one-launch input preamble (artic_disc_prep: signal assembly, AvgPool pyramid, reflect-padded
+    period views) against the single-purpose kernels that take over when a row does not fit its shared memory (long
+    signals) — every output of the full discriminator bit-identical, with the signal given and assembled from parts."""
+    from articulatory_b200 import engine
+    from articulatory_b200 import models as M
+    torch.manual_seed(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        D = M.HiFiGANMultiScaleMultiPeriodDiscriminator(**copy.deepcopy(golden["discriminator_params"])).to(DEV)
+    ar, y = golden["batch"]["ar"].to(DEV), golden["batch"]["y"].to(DEV)
+    x = torch.cat([ar, y], dim=2)                       # (2, 1, 2512): 2512 % 3, % 5, % 7, % 11 != 0 -> reflect pads
+    eng = D._ensure_ready()
+    outs = {}
+    for name, limit in (("one launch", 200 * 1024), ("single kernels", 0)):
+        monkeypatch.setattr(engine, "_DISC_PREP_MAX_BYTES", limit)
+        with torch.no_grad():
+            a, _ = eng.forward(x, save=False)
+            b, _ = eng.forward(None, save=False, parts=(ar.contiguous(), (y.contiguous(),)))
+        torch.cuda.synchronize()
+        outs[name] = [[o.t.clone() for o in lst] for lst in a], [[o.t.clone() for o in lst] for lst in b]
+    for i in range(2):
+        for la, lb in zip(outs["one launch"][i], outs["single kernels"][i]):
+            for ta, tb in zip(la, lb):
+                assert torch.equal(ta, tb)
+    for la, lb in zip(outs["one launch"][0], outs["one launch"][1]):      # given signal == assembled signal
+        for ta, tb in zip(la, lb):
+            assert torch.equal(ta, tb)
